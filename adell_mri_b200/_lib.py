@@ -1,0 +1,136 @@
+"""ctypes binding of the C-ABI shared library (include/adell_b200.h).
+
+The library is built in-tree by ``adell_mri_b200/csrc/build.sh`` (nvcc, sm_100a only).
+There is deliberately NO fallback: if the library is missing or a call returns a
+non-zero status a ``RuntimeError`` is raised.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libadell_b200.so")
+
+# constants mirrored from include/adell_b200.h
+F32, I16, U8 = 0, 1, 2
+NEAREST, TRILINEAR = 0, 1
+PAD_ZEROS, PAD_BORDER, PAD_REFLECTION = 0, 1, 2
+F_IDENTITY, F_CLIP, F_STRICT, F_PHILOX, F_PRE_DEV, F_TMAP, F_FASTCOORD = 0x01, 0x02, 0x04, 0x08, 0x10, 0x20, 0x40
+SCALER_MINMAX, SCALER_ADC_SEG, SCALER_ADC_CLASS, SCALER_RANGE = 0, 1, 2, 3
+
+PADDING_MODES = {"zeros": PAD_ZEROS, "border": PAD_BORDER, "reflection": PAD_REFLECTION}
+INTERP_MODES = {"nearest": NEAREST, "bilinear": TRILINEAR, "trilinear": TRILINEAR, "linear": TRILINEAR}
+
+
+class Item(C.Structure):
+    """Mirror of ``adell_item`` (512 bytes, 64-byte aligned)."""
+
+    _fields_ = [
+        ("tmap", C.c_uint8 * 128),
+        ("src", C.c_void_p),
+        ("dst", C.c_void_p),
+        ("noise", C.c_void_p),
+        ("pre_dev", C.c_void_p),
+        ("tmap_base", C.c_void_p),
+        ("src_stride", C.c_int64 * 3),
+        ("dst_stride", C.c_int64 * 3),
+        ("src_shape", C.c_int32 * 3),
+        ("src_vlo", C.c_int32 * 3),
+        ("src_vhi", C.c_int32 * 3),
+        ("out_shape", C.c_int32 * 3),
+        ("grid_shape", C.c_int32 * 3),
+        ("grid_off", C.c_int32 * 3),
+        ("grid_sign", C.c_int32 * 3),
+        ("grid_vlo", C.c_int32 * 3),
+        ("grid_vhi", C.c_int32 * 3),
+        ("tmap_off", C.c_int32 * 3),
+        ("tmap_sign", C.c_int32 * 3),
+        ("tmap_box", C.c_int32 * 3),
+        ("A", C.c_float * 12),
+        ("nrm", C.c_float * 3),
+        ("pre_scale", C.c_float),
+        ("pre_offset", C.c_float),
+        ("clip_lo", C.c_float),
+        ("clip_hi", C.c_float),
+        ("post_scale", C.c_float),
+        ("post_offset", C.c_float),
+        ("noise_std", C.c_float),
+        ("philox_seed", C.c_uint64),
+        ("philox_offset", C.c_uint64),
+        ("src_dtype", C.c_uint8),
+        ("interp", C.c_uint8),
+        ("padding", C.c_uint8),
+        ("flags", C.c_uint8),
+        ("reserved", C.c_uint8 * 44),
+    ]
+
+
+assert C.sizeof(Item) == 512, C.sizeof(Item)
+
+
+class Vol(C.Structure):
+    """Mirror of ``adell_vol``."""
+
+    _fields_ = [("data", C.c_void_p), ("n", C.c_int64), ("dtype", C.c_int32), ("_pad", C.c_int32)]
+
+
+assert C.sizeof(Vol) == 24
+
+_SIGNATURES = {
+    "adell_abi_version": (C.c_int, []),
+    "adell_status_string": (C.c_char_p, [C.c_int]),
+    "adell_item_size": (C.c_int, []),
+    "adell_device_sm_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "adell_aug_plan_tiles": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int64)]),
+    "adell_item_encode_tensormap": (C.c_int, [C.c_void_p]),
+    "adell_aug_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
+    "adell_aug_gather_launches": (C.c_int, []),
+    "adell_minmax": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
+    "adell_intensity_map": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_void_p],
+    ),
+    "adell_scaler_coefs": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
+    "adell_coefs_to_affine": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "adell_hist_pass": (
+        C.c_int,
+        [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p],
+    ),
+    "adell_hist_select": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "adell_percentile_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load ``libadell_b200.so`` (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with adell_mri_b200/csrc/build.sh "
+            "(or __graft_entry__.build()); there is no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.adell_abi_version() != 1:
+        raise RuntimeError("adell_b200 ABI version mismatch")
+    if lib.adell_item_size() != C.sizeof(Item):
+        raise RuntimeError("adell_item layout mismatch between header and binding")
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = load().adell_status_string(status).decode()
+        raise RuntimeError(f"{what} failed: {msg} (status {status})")

@@ -1,0 +1,432 @@
+// K2/K3 — intensity statistics on device: min/max, exact radix-histogram order statistics
+// (percentiles), and the elementwise intensity program of the reference's scalers.
+//
+// Replaces the CPU reductions inside monai ScaleIntensityd / ScaleIntensityRangePercentilesd and
+// the reference's ConditionalRescalingd / Offsetd
+// (/root/reference/adell_mri/transform_factory/transforms.py:143-155,430-443,772-786;
+//  /root/reference/adell_mri/utils/monai_transforms/image_intensity_ops.py:71-74,119-121).
+// All kernels are HBM-bound streaming passes: 128-bit coalesced loads, warp-shuffle /
+// shared-memory privatised reductions, one global atomic per block per result.
+#include "common.cuh"
+
+namespace {
+
+constexpr int ST_THREADS = 256;
+constexpr int HIST_MAX_BITS = 11;
+constexpr int HIST_REPL = 8;  // lane-interleaved copies of the first-pass histogram
+
+inline int st_blocks_per_vol(int64_t max_n, int n_vols, int elems_per_thread) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int64_t need = (max_n + static_cast<int64_t>(ST_THREADS) * elems_per_thread - 1) /
+                 (static_cast<int64_t>(ST_THREADS) * elems_per_thread);
+  int64_t cap = (static_cast<int64_t>(sms) * 8 + n_vols - 1) / n_vols;  // ~8 resident CTAs per SM overall
+  if (cap < 1) cap = 1;
+  if (need < 1) need = 1;
+  return static_cast<int>(need < cap ? need : cap);
+}
+
+// Visit every element of a volume as float, 128-bit loads for aligned fp32.
+template <typename F>
+__device__ __forceinline__ void st_for_each(const adell_vol& v, F&& f) {
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nthr = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  if (v.dtype == ADELL_F32) {
+    const float* p = reinterpret_cast<const float*>(v.data);
+    if ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
+      const int64_t n4 = v.n >> 2;
+      const float4* p4 = reinterpret_cast<const float4*>(p);
+      for (int64_t i = tid; i < n4; i += nthr) {
+        float4 q = __ldg(p4 + i);
+        f(q.x, 4 * i); f(q.y, 4 * i + 1); f(q.z, 4 * i + 2); f(q.w, 4 * i + 3);
+      }
+      for (int64_t i = (n4 << 2) + tid; i < v.n; i += nthr) f(__ldg(p + i), i);
+    } else {
+      for (int64_t i = tid; i < v.n; i += nthr) f(__ldg(p + i), i);
+    }
+  } else if (v.dtype == ADELL_I16) {
+    const short* p = reinterpret_cast<const short*>(v.data);
+    for (int64_t i = tid; i < v.n; i += nthr) f(static_cast<float>(__ldg(p + i)), i);
+  } else {
+    const unsigned char* p = reinterpret_cast<const unsigned char*>(v.data);
+    for (int64_t i = tid; i < v.n; i += nthr) f(static_cast<float>(__ldg(p + i)), i);
+  }
+}
+
+// ---------------------------------------------------------------- min / max --------------
+__global__ void st_minmax_init(uint32_t* out, int n_vols) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_vols) {
+    out[2 * i + 0] = 0xffffffffu;  // key-space +max
+    out[2 * i + 1] = 0u;           // key-space min
+  }
+}
+
+__global__ void __launch_bounds__(ST_THREADS) st_minmax(const adell_vol* __restrict__ vols, uint32_t* out) {
+  const adell_vol v = vols[blockIdx.y];
+  uint32_t kmin = 0xffffffffu, kmax = 0u;
+  st_for_each(v, [&](float x, int64_t) {
+    uint32_t k = adell_key_f32(x);
+    kmin = min(kmin, k);
+    kmax = max(kmax, k);
+  });
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+    kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+  }
+  __shared__ uint32_t smin[ST_THREADS / 32], smax[ST_THREADS / 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { smin[warp] = kmin; smax[warp] = kmax; }
+  __syncthreads();
+  if (warp == 0) {
+    kmin = lane < ST_THREADS / 32 ? smin[lane] : 0xffffffffu;
+    kmax = lane < ST_THREADS / 32 ? smax[lane] : 0u;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+      kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    }
+    if (lane == 0 && v.n > 0) {
+      atomicMin(out + 2 * blockIdx.y + 0, kmin);
+      atomicMax(out + 2 * blockIdx.y + 1, kmax);
+    }
+  }
+}
+
+__global__ void st_minmax_fin(uint32_t* out, int n_vols) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 2 * n_vols) reinterpret_cast<float*>(out)[i] = adell_unkey_f32(out[i]);
+}
+
+// ---------------------------------------------------------------- intensity program -------
+// y = ((x*m0 - a)/d)*m1*m2 + b, each op rounded to fp32 (IEEE division).
+__device__ __forceinline__ float st_program(float x, const float* __restrict__ c) {
+  float y = __fmul_rn(x, c[0]);
+  y = __fsub_rn(y, c[1]);
+  y = __fdiv_rn(y, c[2]);
+  y = __fmul_rn(y, c[3]);
+  y = __fmul_rn(y, c[4]);
+  y = __fadd_rn(y, c[5]);
+  return y;
+}
+
+__global__ void __launch_bounds__(ST_THREADS)
+st_intensity_map(const adell_vol* __restrict__ vols, float* const* __restrict__ dsts,
+                 const float* __restrict__ coefs, int clip, float lo, float hi) {
+  const adell_vol v = vols[blockIdx.y];
+  float* __restrict__ dst = dsts[blockIdx.y];
+  float c[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) c[i] = __ldg(coefs + 6 * blockIdx.y + i);
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nthr = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const bool vec = v.dtype == ADELL_F32 && ((reinterpret_cast<uintptr_t>(v.data) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0;
+  if (vec) {
+    const float4* p4 = reinterpret_cast<const float4*>(v.data);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    const int64_t n4 = v.n >> 2;
+    for (int64_t i = tid; i < n4; i += nthr) {
+      float4 q = __ldg(p4 + i);
+      q.x = st_program(q.x, c); q.y = st_program(q.y, c); q.z = st_program(q.z, c); q.w = st_program(q.w, c);
+      if (clip) {
+        q.x = fminf(hi, fmaxf(q.x, lo)); q.y = fminf(hi, fmaxf(q.y, lo));
+        q.z = fminf(hi, fmaxf(q.z, lo)); q.w = fminf(hi, fmaxf(q.w, lo));
+      }
+      d4[i] = q;
+    }
+    for (int64_t i = (n4 << 2) + tid; i < v.n; i += nthr) {
+      float y = st_program(__ldg(reinterpret_cast<const float*>(v.data) + i), c);
+      dst[i] = clip ? fminf(hi, fmaxf(y, lo)) : y;
+    }
+  } else {
+    for (int64_t i = tid; i < v.n; i += nthr) {
+      float y = st_program(adell_load_src(v.data, i, v.dtype), c);
+      dst[i] = clip ? fminf(hi, fmaxf(y, lo)) : y;
+    }
+  }
+}
+
+__global__ void st_scaler_coefs(const float* __restrict__ stats, int n_vols, int scaler, double p0, double p1,
+                                float* __restrict__ coefs) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_vols) return;
+  const float lo = stats[2 * i], hi = stats[2 * i + 1];
+  float m0 = 1.f, a = 0.f, d = 1.f, m1 = 1.f, m2 = 1.f, b = 0.f;
+  const float adc_mult = static_cast<float>(1.0 + (-2.0 / 3.0));  // ScaleIntensity(factor): x*(1+factor)
+  if (scaler == ADELL_SCALER_MINMAX) {
+    if (lo == hi) {
+      m0 = static_cast<float>(p0);  // rescale_array: mina == maxa -> arr * minv
+    } else {
+      a = lo;
+      d = __fsub_rn(hi, lo);
+      m1 = static_cast<float>(p1 - p0);
+      b = static_cast<float>(p0);
+    }
+  } else if (scaler == ADELL_SCALER_ADC_SEG) {
+    if (hi > static_cast<float>(p0)) m0 = static_cast<float>(p1);
+    m1 = adc_mult;
+  } else if (scaler == ADELL_SCALER_ADC_CLASS) {
+    if (hi > static_cast<float>(p0)) m0 = static_cast<float>(p1);
+    a = __fmul_rn(lo, m0);  // Offsetd(None): minus the minimum of the (rescaled) array
+    m1 = adc_mult;
+  } else {  // ADELL_SCALER_RANGE
+    a = lo;
+    if (__fsub_rn(hi, lo) != 0.0f) {
+      d = __fsub_rn(hi, lo);
+      m1 = static_cast<float>(p1 - p0);
+    }
+    b = static_cast<float>(p0);
+  }
+  float* c = coefs + 6 * i;
+  c[0] = m0; c[1] = a; c[2] = d; c[3] = m1; c[4] = m2; c[5] = b;
+}
+
+__global__ void st_coefs_to_affine(const float* __restrict__ coefs, int n_vols, float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_vols) return;
+  const float* c = coefs + 6 * i;
+  double g = static_cast<double>(c[3]) * c[4] / c[2];
+  out[2 * i + 0] = static_cast<float>(c[0] * g);
+  out[2 * i + 1] = static_cast<float>(c[5] - c[1] * g);
+}
+
+// ---------------------------------------------------------------- radix histogram ---------
+// First pass (shift+bits == 32): one histogram per volume, HIST_REPL lane-interleaved copies
+// in shared memory so that a warp full of equal keys (background voxels) collides 4-way
+// instead of 32-way.  Later passes: only elements whose high bits match a selection's prefix
+// count; matching lanes are warp-aggregated with __match_any_sync before the atomic.
+__global__ void __launch_bounds__(ST_THREADS)
+st_hist_first(const adell_vol* __restrict__ vols, int shared_bins, int bits, unsigned long long* __restrict__ bins) {
+  extern __shared__ uint32_t sh[];  // [nb][HIST_REPL]
+  const int nb = 1 << bits;
+  for (int i = threadIdx.x; i < nb * HIST_REPL; i += blockDim.x) sh[i] = 0u;
+  __syncthreads();
+  const adell_vol v = vols[blockIdx.y];
+  const int shift = 32 - bits;
+  const int copy = threadIdx.x & (HIST_REPL - 1);
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nthr = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  if (v.dtype == ADELL_F32 && (reinterpret_cast<uintptr_t>(v.data) & 15u) == 0) {
+    const float4* p4 = reinterpret_cast<const float4*>(v.data);
+    const int64_t n4 = v.n >> 2;
+    for (int64_t i = tid; i < n4; i += nthr) {
+      float4 q = __ldg(p4 + i);
+      uint32_t b0 = adell_key_f32(q.x) >> shift, b1 = adell_key_f32(q.y) >> shift;
+      uint32_t b2 = adell_key_f32(q.z) >> shift, b3 = adell_key_f32(q.w) >> shift;
+      if (b0 == b1 && b1 == b2 && b2 == b3) {
+        atomicAdd(&sh[b0 * HIST_REPL + copy], 4u);
+      } else {
+        atomicAdd(&sh[b0 * HIST_REPL + copy], 1u); atomicAdd(&sh[b1 * HIST_REPL + copy], 1u);
+        atomicAdd(&sh[b2 * HIST_REPL + copy], 1u); atomicAdd(&sh[b3 * HIST_REPL + copy], 1u);
+      }
+    }
+    const float* p = reinterpret_cast<const float*>(v.data);
+    for (int64_t i = (n4 << 2) + tid; i < v.n; i += nthr)
+      atomicAdd(&sh[(adell_key_f32(__ldg(p + i)) >> shift) * HIST_REPL + copy], 1u);
+  } else {
+    for (int64_t i = tid; i < v.n; i += nthr)
+      atomicAdd(&sh[(adell_key(v.data, i, v.dtype) >> shift) * HIST_REPL + copy], 1u);
+  }
+  __syncthreads();
+  unsigned long long* out = bins + (shared_bins ? 0 : static_cast<size_t>(blockIdx.y) << bits);
+  for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+    uint32_t s = 0;
+#pragma unroll
+    for (int r = 0; r < HIST_REPL; ++r) s += sh[b * HIST_REPL + r];
+    if (s) atomicAdd(out + b, static_cast<unsigned long long>(s));
+  }
+}
+
+__global__ void __launch_bounds__(ST_THREADS)
+st_hist_next(const adell_vol* __restrict__ vols, int n_sel, int shared_bins, const uint32_t* __restrict__ prefix,
+             int shift, int bits, unsigned long long* __restrict__ bins) {
+  extern __shared__ uint32_t sh[];  // [n_sel][nb]
+  __shared__ uint32_t spre[8];
+  const int nb = 1 << bits;
+  for (int i = threadIdx.x; i < nb * n_sel; i += blockDim.x) sh[i] = 0u;
+  const int h = shared_bins ? 0 : blockIdx.y;
+  const int hi_shift = shift + bits;  // < 32 here
+  if (threadIdx.x < n_sel) spre[threadIdx.x] = __ldg(prefix + h * n_sel + threadIdx.x) >> hi_shift;
+  __syncthreads();
+  const adell_vol v = vols[blockIdx.y];
+  const uint32_t mask = static_cast<uint32_t>(nb - 1);
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nthr = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  // whole warps iterate together so that __match_any_sync sees a full mask
+  const int64_t n_round = ((v.n + nthr - 1) / nthr) * nthr;
+  for (int64_t i = tid; i < n_round; i += nthr) {
+    const bool live = i < v.n;
+    uint32_t key = live ? adell_key(v.data, i, v.dtype) : 0u;
+    const uint32_t khi = key >> hi_shift;
+    for (int s = 0; s < n_sel; ++s) {
+      const bool m = live && khi == spre[s];
+      const unsigned ballot = __ballot_sync(0xffffffffu, m);
+      if (ballot == 0u) continue;
+      if (m) {
+        const uint32_t bin = (key >> shift) & mask;
+        const unsigned peers = __match_any_sync(ballot, bin);
+        if ((threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&sh[s * nb + bin], __popc(peers));
+      }
+    }
+  }
+  __syncthreads();
+  unsigned long long* out = bins + ((static_cast<size_t>(h) * n_sel) << bits);
+  for (int b = threadIdx.x; b < nb * n_sel; b += blockDim.x) {
+    uint32_t s = sh[b];
+    if (s) atomicAdd(out + b, static_cast<unsigned long long>(s));
+  }
+}
+
+// One block per (histogram, selection): find the bin that holds the requested rank.
+__global__ void __launch_bounds__(ST_THREADS)
+st_hist_select(const unsigned long long* __restrict__ bins, int n_sel, int first_pass, int shift, int bits,
+               uint32_t* __restrict__ prefix, unsigned long long* __restrict__ rank) {
+  const int h = blockIdx.x / n_sel, s = blockIdx.x % n_sel;
+  const int nb = 1 << bits;
+  const unsigned long long* hb = bins + ((first_pass ? static_cast<size_t>(h) : static_cast<size_t>(h) * n_sel + s) << bits);
+  const int per = (nb + ST_THREADS - 1) / ST_THREADS;  // bins per thread (contiguous)
+  const int b_lo = threadIdx.x * per;
+  unsigned long long local = 0;
+  for (int b = b_lo; b < min(nb, b_lo + per); ++b) local += hb[b];
+  __shared__ unsigned long long scan[ST_THREADS];
+  scan[threadIdx.x] = local;
+  __syncthreads();
+  // inclusive Hillis-Steele scan over 256 partial sums
+  for (int o = 1; o < ST_THREADS; o <<= 1) {
+    unsigned long long t = threadIdx.x >= o ? scan[threadIdx.x - o] : 0ull;
+    __syncthreads();
+    scan[threadIdx.x] += t;
+    __syncthreads();
+  }
+  const unsigned long long r = rank[blockIdx.x];
+  const unsigned long long before = scan[threadIdx.x] - local;
+  if (r >= before && r < scan[threadIdx.x]) {  // exactly one thread
+    unsigned long long cum = before;
+    for (int b = b_lo; b < min(nb, b_lo + per); ++b) {
+      unsigned long long c = hb[b];
+      if (r < cum + c) {
+        uint32_t p = first_pass ? 0u : prefix[blockIdx.x];
+        prefix[blockIdx.x] = p | (static_cast<uint32_t>(b) << shift);
+        rank[blockIdx.x] = r - cum;
+        break;
+      }
+      cum += c;
+    }
+  }
+}
+
+__global__ void st_percentile_finalize(const uint32_t* __restrict__ keys, const double* __restrict__ frac, int n,
+                                       int dtype, float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float a = adell_unkey(keys[2 * i], dtype), b = adell_unkey(keys[2 * i + 1], dtype);
+  const double t = frac[i];
+  // numpy _lerp on float32 samples with a float64 weight
+  const float diff = __fsub_rn(b, a);
+  double r = __dadd_rn(static_cast<double>(a), __dmul_rn(static_cast<double>(diff), t));
+  if (t >= 0.5) r = __dsub_rn(static_cast<double>(b), __dmul_rn(static_cast<double>(diff), __dsub_rn(1.0, t)));
+  out[i] = static_cast<float>(r);
+}
+
+}  // namespace
+
+extern "C" int adell_minmax(const adell_vol* vols_dev, int n_vols, int64_t max_n, float* out_dev, void* stream) {
+  if (n_vols == 0) return ADELL_OK;
+  if (vols_dev == nullptr || out_dev == nullptr || n_vols < 0 || max_n < 0) return ADELL_ERR_BAD_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint32_t* o = reinterpret_cast<uint32_t*>(out_dev);
+  st_minmax_init<<<(n_vols + 127) / 128, 128, 0, st>>>(o, n_vols);
+  dim3 grid(st_blocks_per_vol(max_n, n_vols, 32), n_vols);
+  st_minmax<<<grid, ST_THREADS, 0, st>>>(vols_dev, o);
+  st_minmax_fin<<<(2 * n_vols + 127) / 128, 128, 0, st>>>(o, n_vols);
+  ADELL_CUDA_CHECK_LAUNCH();
+  return ADELL_OK;
+}
+
+extern "C" int adell_intensity_map(const adell_vol* vols_dev, float* const* dst_dev, const float* coef_dev,
+                                   int n_vols, int64_t max_n, int clip, float clip_lo, float clip_hi,
+                                   void* stream) {
+  if (n_vols == 0) return ADELL_OK;
+  if (vols_dev == nullptr || dst_dev == nullptr || coef_dev == nullptr || n_vols < 0 || max_n < 0)
+    return ADELL_ERR_BAD_ARG;
+  dim3 grid(st_blocks_per_vol(max_n, n_vols, 16), n_vols);
+  st_intensity_map<<<grid, ST_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(vols_dev, dst_dev, coef_dev, clip,
+                                                                                clip_lo, clip_hi);
+  ADELL_CUDA_CHECK_LAUNCH();
+  return ADELL_OK;
+}
+
+extern "C" int adell_scaler_coefs(const float* stats_dev, int n_vols, int scaler, double p0, double p1,
+                                  float* coef_dev, void* stream) {
+  if (n_vols == 0) return ADELL_OK;
+  if (stats_dev == nullptr || coef_dev == nullptr || n_vols < 0 || scaler < 0 || scaler > ADELL_SCALER_RANGE)
+    return ADELL_ERR_BAD_ARG;
+  st_scaler_coefs<<<(n_vols + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(stats_dev, n_vols, scaler, p0,
+                                                                                       p1, coef_dev);
+  ADELL_CUDA_CHECK_LAUNCH();
+  return ADELL_OK;
+}
+
+extern "C" int adell_coefs_to_affine(const float* coef_dev, int n_vols, float* pre_dev_out, void* stream) {
+  if (n_vols == 0) return ADELL_OK;
+  if (coef_dev == nullptr || pre_dev_out == nullptr || n_vols < 0) return ADELL_ERR_BAD_ARG;
+  st_coefs_to_affine<<<(n_vols + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(coef_dev, n_vols,
+                                                                                          pre_dev_out);
+  ADELL_CUDA_CHECK_LAUNCH();
+  return ADELL_OK;
+}
+
+extern "C" int adell_hist_pass(const adell_vol* vols_dev, int n_vols, int64_t max_n, int n_sel, int shared,
+                               const uint32_t* prefix_dev, int pass_shift, int pass_bits, uint64_t* bins_dev,
+                               void* stream) {
+  if (n_vols == 0) return ADELL_OK;
+  if (vols_dev == nullptr || bins_dev == nullptr || n_vols < 0 || max_n < 0 || pass_bits < 1 ||
+      pass_bits > HIST_MAX_BITS || pass_shift < 0 || pass_shift + pass_bits > 32 || n_sel < 1 || n_sel > 8)
+    return ADELL_ERR_BAD_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned long long* bins = reinterpret_cast<unsigned long long*>(bins_dev);
+  const bool first = pass_shift + pass_bits == 32;
+  if (first) {
+    dim3 grid(st_blocks_per_vol(max_n, n_vols, 64), n_vols);
+    size_t smem = (static_cast<size_t>(1) << pass_bits) * HIST_REPL * sizeof(uint32_t);
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(st_hist_first, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    st_hist_first<<<grid, ST_THREADS, smem, st>>>(vols_dev, shared, pass_bits, bins);
+  } else {
+    if (prefix_dev == nullptr) return ADELL_ERR_BAD_ARG;
+    dim3 grid(st_blocks_per_vol(max_n, n_vols, 64), n_vols);
+    size_t smem = (static_cast<size_t>(1) << pass_bits) * n_sel * sizeof(uint32_t);
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(st_hist_next, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    st_hist_next<<<grid, ST_THREADS, smem, st>>>(vols_dev, n_sel, shared, prefix_dev, pass_shift, pass_bits, bins);
+  }
+  ADELL_CUDA_CHECK_LAUNCH();
+  return ADELL_OK;
+}
+
+extern "C" int adell_hist_select(const uint64_t* bins_dev, int n_hist, int n_sel, int pass_shift, int pass_bits,
+                                 uint32_t* prefix_dev, uint64_t* rank_dev, void* stream) {
+  if (n_hist == 0) return ADELL_OK;
+  if (bins_dev == nullptr || prefix_dev == nullptr || rank_dev == nullptr || n_hist < 0 || n_sel < 1 || n_sel > 8 ||
+      pass_bits < 1 || pass_bits > HIST_MAX_BITS || pass_shift < 0 || pass_shift + pass_bits > 32)
+    return ADELL_ERR_BAD_ARG;
+  const int first = pass_shift + pass_bits == 32;
+  st_hist_select<<<n_hist * n_sel, ST_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const unsigned long long*>(bins_dev), n_sel, first, pass_shift, pass_bits, prefix_dev,
+      reinterpret_cast<unsigned long long*>(rank_dev));
+  ADELL_CUDA_CHECK_LAUNCH();
+  return ADELL_OK;
+}
+
+extern "C" int adell_percentile_finalize(const uint32_t* keys_dev, const double* frac_dev, int n_vols, int n_q,
+                                         int dtype, float* out_dev, void* stream) {
+  const int n = n_vols * n_q;
+  if (n == 0) return ADELL_OK;
+  if (keys_dev == nullptr || frac_dev == nullptr || out_dev == nullptr || n < 0 || dtype < 0 || dtype > ADELL_U8)
+    return ADELL_ERR_BAD_ARG;
+  st_percentile_finalize<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(keys_dev, frac_dev, n, dtype,
+                                                                                         out_dev);
+  ADELL_CUDA_CHECK_LAUNCH();
+  return ADELL_OK;
+}

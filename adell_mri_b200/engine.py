@@ -1,0 +1,85 @@
+"""Launch side of K1: uploads a composed :class:`~adell_mri_b200.plan.BatchPlan` and enqueues
+the fused gather on the current CUDA stream (one launch per pass; a chain with a single
+resample is exactly one launch for the whole batch).
+
+Replaces the per-sample eager execution + ``safe_collate`` + pin + H2D of the reference's
+DataLoader path (/root/reference/adell_mri/utils/utils.py:308-377,
+/root/reference/adell_mri/entrypoints/segmentation/train.py:604-615).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .plan import ITEM_DTYPE, BatchPlan
+
+#: number of K1 launches issued so far in this process (bench.py reports the delta per step)
+launch_count = 0
+
+
+def _require_cuda(device: torch.device):
+    if device.type != "cuda":
+        raise RuntimeError(
+            "adell_mri_b200 executes on CUDA devices only (there is no CPU fallback); "
+            f"got a plan living on {device}"
+        )
+
+
+def pack_launch(items: np.ndarray):
+    """Host-side packing of one launch: ``(pinned-able uint8 buffer, n_items, total_tiles)``.
+    Layout: items (512 B each) followed by the int32 tile prefix (n_items + 1)."""
+    lib = _lib.load()
+    n = items.shape[0]
+    buf = np.empty(n * 512 + 4 * (n + 1), np.uint8)
+    buf[: n * 512] = items.view(np.uint8).reshape(-1)
+    tiles = np.empty(n + 1, np.int32)
+    total = C.c_int64(0)
+    _lib.check(
+        lib.adell_aug_plan_tiles(items.ctypes.data, n, tiles.ctypes.data, C.byref(total)), "adell_aug_plan_tiles"
+    )
+    buf[n * 512 :] = tiles.view(np.uint8)
+    return buf, n, int(total.value)
+
+
+def launch_packed(buf_dev: torch.Tensor, n: int, total: int, stream: int | None = None):
+    """Enqueue one K1 launch from a device-resident packed buffer (see :func:`pack_launch`)."""
+    global launch_count
+    lib = _lib.load()
+    if stream is None:
+        stream = torch.cuda.current_stream(buf_dev.device).cuda_stream
+    base = buf_dev.data_ptr()
+    _lib.check(lib.adell_aug_gather(base, base + n * 512, n, total, C.c_void_p(stream)), "adell_aug_gather")
+    launch_count += lib.adell_aug_gather_launches()
+
+
+def execute(plan: BatchPlan, dsts: Sequence[torch.Tensor]) -> None:
+    """Run every recorded pass of ``plan``; volume ``i`` is written to ``dsts[i]`` (fp32
+    ``[O0,O1,O2]`` views, any strides — typically channel slices of the collated batch)."""
+    _require_cuda(plan.device)
+    if len(dsts) != plan.n:
+        raise ValueError("one destination per volume")
+    shape = plan.shape
+    dst_ptr = np.empty(plan.n, np.uint64)
+    dst_stride = np.empty((plan.n, 3), np.int64)
+    for i, d in enumerate(dsts):
+        if d.dtype != torch.float32 or d.device != plan.device:
+            raise ValueError("destinations must be float32 on the plan's device")
+        if tuple(d.shape) != tuple(int(x) for x in shape[i]):
+            raise ValueError(f"destination {i} has shape {tuple(d.shape)}, plan produces {tuple(shape[i])}")
+        dst_ptr[i] = d.data_ptr()
+        dst_stride[i] = d.stride()
+    with torch.cuda.device(plan.device):
+        launches = plan.build_launches(
+            dst_ptr, dst_stride, lambda n: torch.empty(max(n, 1), dtype=torch.float32, device=plan.device)
+        )
+        for items in launches:
+            buf, n, total = pack_launch(items)
+            host = torch.from_numpy(buf).pin_memory()
+            dev = host.to(plan.device, non_blocking=True)
+            launch_packed(dev, n, total)
+            plan.keep.append(dev)

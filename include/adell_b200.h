@@ -1,0 +1,211 @@
+/*
+ * adell_b200.h — C ABI of the B200-native volumetric augmentation hot path.
+ *
+ * The reference (CCIG-Champalimaud/adell-mri) is pure Python and has NO FFI layer;
+ * the seam this ABI replaces is the per-sample MONAI transform chain that
+ * adell_mri/transform_factory assembles and that DataLoader workers execute:
+ *
+ *   adell_aug_gather          <- RandAffined + RandFlipd + RandSpatialCropd/SpatialPadd/
+ *                                CenterSpatialCropd + RandGaussianNoised/RandScale/ShiftIntensityd
+ *                                + ConcatItemsd + safe_collate
+ *                                (adell_mri/transform_factory/augmentations.py:98-176,255-301,427-515;
+ *                                 adell_mri/modules/augmentations.py:165-256;
+ *                                 adell_mri/transform_factory/transforms.py:169-214,463-509,787-820;
+ *                                 adell_mri/utils/utils.py:308-377)
+ *   adell_minmax              <- the two reductions inside monai ScaleIntensityd(minv=0,maxv=1)
+ *                                (transforms.py:143-148,430-435,772-777) and
+ *                                ConditionalRescalingd/Offsetd (utils/monai_transforms/image_intensity_ops.py:71-74,119-121)
+ *   adell_intensity_map       <- the elementwise part of ScaleIntensityd / ConditionalRescalingd /
+ *                                Offsetd / ScaleIntensityRange (exact fp32 op order)
+ *   adell_hist_pass/_select/
+ *   adell_percentile_finalize <- np.percentile inside monai ScaleIntensityRangePercentilesd
+ *                                (named by BASELINE.json north_star; new capability, the reference
+ *                                 itself only uses the (0,100) special case = min-max)
+ *
+ * Conventions: every pointer named *_dev is caller-owned DEVICE memory (e.g. from the
+ * torch allocator); nothing is allocated, freed or synchronised inside; work is enqueued
+ * on `stream` (a cudaStream_t passed as void*).  Every entry point returns ADELL_OK (0)
+ * or a negative status and never throws across the ABI.  Re-entrant, no global mutable
+ * state.  There is NO CPU fallback: without a CUDA device the compute entry points return
+ * ADELL_ERR_NO_DEVICE / ADELL_ERR_LAUNCH.
+ */
+#ifndef ADELL_B200_H_
+#define ADELL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADELL_ABI_VERSION 1
+
+/* status codes */
+#define ADELL_OK 0
+#define ADELL_ERR_BAD_ARG (-1)
+#define ADELL_ERR_DTYPE (-2)
+#define ADELL_ERR_ALIGN (-3)
+#define ADELL_ERR_LAUNCH (-4)
+#define ADELL_ERR_NO_DEVICE (-5)
+#define ADELL_ERR_NO_DRIVER (-6)
+#define ADELL_ERR_UNSUPPORTED (-7)
+
+/* source element types */
+#define ADELL_F32 0
+#define ADELL_I16 1
+#define ADELL_U8 2
+
+/* interpolation (MONAI mode "nearest" / "bilinear") */
+#define ADELL_NEAREST 0
+#define ADELL_TRILINEAR 1
+
+/* padding_mode of grid_sample */
+#define ADELL_PAD_ZEROS 0
+#define ADELL_PAD_BORDER 1
+#define ADELL_PAD_REFLECTION 2
+
+/* item flags */
+#define ADELL_F_IDENTITY 0x01 /* no resample fired: pure integer flip/crop/pad copy (bit-exact)     */
+#define ADELL_F_CLIP 0x02     /* clamp each tap to [clip_lo, clip_hi] after the pre map              */
+#define ADELL_F_STRICT 0x04   /* ATen operation order for the trilinear sum (mul, add; no fma) and
+                                 separate mul/add for post_scale/post_offset                         */
+#define ADELL_F_PHILOX 0x08   /* add N(0, noise_std) from Philox4x32-10 (fast mode; not comparable
+                                 with the reference's RandomState stream)                            */
+#define ADELL_F_PRE_DEV 0x10  /* read {pre_scale, pre_offset} from pre_dev (device-side statistics)  */
+#define ADELL_F_TMAP 0x20     /* tmap holds a valid CUtensorMap of the valid source box (staged path)*/
+#define ADELL_F_FASTCOORD 0x40 /* trilinear only: incremental coordinates (<=1e-4 contract), no
+                                  bit-faithful replay of the MONAI/ATen fp32 coordinate chain         */
+
+/*
+ * One unit of work = one (sample, key): the whole reference chain for one volume,
+ * composed on the host into canonical form
+ *
+ *   parent --(integer: crop/pad/flip BEFORE the resample)--> resample domain S
+ *          --(RandAffined: A, grid G, interp, padding)-----> grid G
+ *          --(integer: flip/crop/pad AFTER the resample)---> output O
+ *          --(post intensity map, noise)--------------------> dst
+ *
+ * Resample domain index t (per axis, 0 <= t < S) addresses  src + sum_a t_a*src_stride[a]
+ * (strides are SIGNED: a flip before the resample is a negative stride) and reads literal 0
+ * when t_a is outside [src_vlo[a], src_vhi[a]) (constant SpatialPadd band).  Output index o
+ * maps to grid index g_a = grid_off[a] + grid_sign[a]*o_a and reads literal 0 when g_a is
+ * outside [grid_vlo[a], grid_vhi[a]).  Source coordinates follow MONAI/ATen bit for bit:
+ *   c_a = g_a - (G_a-1)/2 ;  x_a = fma(A[a][3],1, fma(A[a][2],c_2, fma(A[a][1],c_1, A[a][0]*c_0)))
+ *   n_a = x_a * nrm[a]    ;  u_a = ((n_a + 1) * S_a - 1) / 2       (each op rounded to fp32)
+ * then padding_mode / floor / rint exactly as ATen's grid_sampler_3d CPU kernel.
+ * Axis order is MONAI's [H, W, D] = axes 0,1,2; axis 2 is the contiguous one.
+ */
+typedef struct __attribute__((aligned(64))) adell_item {
+  uint8_t tmap[128];       /* opaque CUtensorMap (see adell_item_encode_tensormap)                  */
+  const void* src;         /* element t=(0,0,0); may lie outside the allocation, never read there  */
+  float* dst;              /* fp32 output, element o=(0,0,0)                                        */
+  const float* noise;      /* optional injected noise, contiguous [O0,O1,O2] fp32, or NULL          */
+  const float* pre_dev;    /* optional device {scale, offset} (ADELL_F_PRE_DEV)                     */
+  const void* tmap_base;   /* device address of tmap box element (0,0,0) (informational)            */
+  int64_t src_stride[3];   /* signed, in elements                                                   */
+  int64_t dst_stride[3];   /* in elements                                                           */
+  int32_t src_shape[3];    /* S                                                                      */
+  int32_t src_vlo[3];
+  int32_t src_vhi[3];
+  int32_t out_shape[3];    /* O                                                                      */
+  int32_t grid_shape[3];   /* G                                                                      */
+  int32_t grid_off[3];
+  int32_t grid_sign[3];    /* +1 or -1                                                               */
+  int32_t grid_vlo[3];
+  int32_t grid_vhi[3];
+  int32_t tmap_off[3];     /* t-space index of the tmap box origin (staged path)                    */
+  int32_t tmap_sign[3];    /* +1/-1: box index = tmap_sign*(t - tmap_off) (staged path)             */
+  int32_t tmap_box[3];     /* staged box extents actually encoded (z,y,x order = axes 2,1,0)        */
+  float A[12];             /* rows 0..2 of the fp32 4x4 MONAI affine (row-major 3x4)                 */
+  float nrm[3];            /* (float)(2.0 / max(2, S_a)) — MONAI Resample norm_coords factor        */
+  float pre_scale, pre_offset, clip_lo, clip_hi;
+  float post_scale, post_offset, noise_std;
+  uint64_t philox_seed, philox_offset;
+  uint8_t src_dtype, interp, padding, flags;
+  uint8_t reserved[44]; /* pads the struct to 512 bytes */
+} adell_item;
+
+/* -- library / device ---------------------------------------------------------------- */
+int adell_abi_version(void);
+const char* adell_status_string(int status);
+int adell_item_size(void);           /* sizeof(adell_item), for bindings to cross-check      */
+int adell_device_sm_count(int* out); /* number of SMs of the current device                   */
+
+/* -- K1: fused gather ----------------------------------------------------------------- */
+/* Host-only: fills tile_start_host[0..n_items] with the exclusive prefix of per-item tile
+ * counts for the tiling policy compiled into the library (so the caller can upload it next
+ * to the items); returns total tiles in *total_tiles. */
+int adell_aug_plan_tiles(const adell_item* items_host, int n_items, int32_t* tile_start_host,
+                         int64_t* total_tiles);
+/* Host-only: encodes items_host[i].tmap for the staged (TMA) path when eligible, setting or
+ * clearing ADELL_F_TMAP.  Needs libcuda (driver entry point); ADELL_ERR_NO_DRIVER otherwise. */
+int adell_item_encode_tensormap(adell_item* item_host);
+/* Enqueue the fused gather over all items: one launch per call. */
+int adell_aug_gather(const adell_item* items_dev, const int32_t* tile_start_dev, int n_items,
+                     int64_t total_tiles, void* stream);
+/* Number of kernel launches the last-compiled policy issues per adell_aug_gather call. */
+int adell_aug_gather_launches(void);
+
+/* -- statistics for intensity normalisation -------------------------------------------- */
+/* One descriptor per volume for the batched statistics kernels. */
+typedef struct adell_vol {
+  const void* data; /* contiguous volume                              */
+  int64_t n;        /* number of elements                             */
+  int32_t dtype;    /* ADELL_F32 / ADELL_I16 / ADELL_U8               */
+  int32_t _pad;
+} adell_vol;
+
+/* out_dev[2*v+0] = min, out_dev[2*v+1] = max over volume v (as fp32).  out_dev must be
+ * pre-initialised by the call itself (it is: +inf/-inf written by a first tiny kernel). */
+int adell_minmax(const adell_vol* vols_dev, int n_vols, int64_t max_n, float* out_dev, void* stream);
+
+/* Exact elementwise intensity program  y = ((x*m0 - a)/d)*m1*m2 + b  with every op rounded to
+ * fp32 in that order and no-op steps skipped bit-exactly (m0=1, a=0, d=1, m1=1, m2=1, b=0); the
+ * six coefficients are read from coef_dev[6*v ..] so they can come from device statistics.
+ * Optional clamp to [clip_lo, clip_hi] when clip != 0.  dst is fp32, contiguous. */
+int adell_intensity_map(const adell_vol* vols_dev, float* const* dst_dev, const float* coef_dev,
+                        int n_vols, int64_t max_n, int clip, float clip_lo, float clip_hi,
+                        void* stream);
+/* Fills coef_dev from device min/max per the reference's scalers (see ADELL_SCALER_*). */
+#define ADELL_SCALER_MINMAX 0    /* ScaleIntensityd(minv,maxv): ((x-min)/(max-min))*(maxv-minv)+minv */
+#define ADELL_SCALER_ADC_SEG 1   /* ConditionalRescalingd(500,.001) -> ScaleIntensityd(factor=-2/3)  */
+#define ADELL_SCALER_ADC_CLASS 2 /* ConditionalRescalingd -> Offsetd(None) -> ScaleIntensityd(factor) */
+#define ADELL_SCALER_RANGE 3     /* ScaleIntensityRange(a_min=lo,a_max=hi,b_min=p0,b_max=p1) as used by
+                                    ScaleIntensityRangePercentilesd; stats = the two percentiles     */
+/* stats_dev holds {lo, hi} per volume (min/max from adell_minmax, or two percentiles).
+ * MINMAX: p0=minv, p1=maxv.  ADC_*: p0=max_value (500), p1=scale (0.001); factor fixed at -2/3
+ * (ADC_FACTOR, transforms.py:25). */
+int adell_scaler_coefs(const float* stats_dev, int n_vols, int scaler, double p0, double p1,
+                       float* coef_dev, void* stream);
+/* Collapses the 6-coefficient program into the fused-mode pair {scale, offset} that
+ * adell_item.pre_dev points at (x*scale+offset; <=1e-4 contract instead of bit-exact). */
+int adell_coefs_to_affine(const float* coef_dev, int n_vols, float* pre_dev_out, void* stream);
+
+/* Radix histogram of the order-preserving 32-bit key of every element (fp32: sign-flip
+ * transform; int16/uint8: biased value).  A pass looks at key bits [shift, shift+bits) of the
+ * elements whose bits above shift+bits equal those of prefix_dev[h*n_sel+s] (first pass,
+ * shift+bits==32: every element, one histogram shared by all selections) and counts into
+ *   bins_dev[((h*n_sel_eff)+s) << bits],  h = shared ? 0 : v,  n_sel_eff = first pass ? 1 : n_sel.
+ * shared!=0 accumulates every volume into histogram 0 (dataset-wide statistics: all-reduce
+ * bins_dev across ranks between adell_hist_pass and adell_hist_select).  bins must be zeroed
+ * by the caller (torch.zero_ / cudaMemsetAsync) before each pass. */
+int adell_hist_pass(const adell_vol* vols_dev, int n_vols, int64_t max_n, int n_sel, int shared,
+                    const uint32_t* prefix_dev, int pass_shift, int pass_bits, uint64_t* bins_dev,
+                    void* stream);
+/* For every (histogram h, selection s): walk the bins, find the bin holding rank_dev[h*n_sel+s]
+ * (0-based order statistic among the elements counted there), OR its index << shift into
+ * prefix_dev[h*n_sel+s] and subtract the count of the preceding bins from the rank.  After the
+ * last pass (shift==0) prefix_dev holds the full key of the order statistic. */
+int adell_hist_select(const uint64_t* bins_dev, int n_hist, int n_sel, int pass_shift, int pass_bits,
+                      uint32_t* prefix_dev, uint64_t* rank_dev, void* stream);
+/* Converts selected keys back to values and evaluates numpy's 'linear' percentile
+ *   v = a + (b-a)*t  (t<0.5)   |   v = b - (b-a)*(1-t)  (t>=0.5)      in float64, cast to fp32
+ * for n_q quantiles per volume from the (lo, hi) order statistics; keys_dev is
+ * [n_vols][n_q][2], frac_dev [n_vols][n_q] float64, out_dev [n_vols][n_q] fp32. */
+int adell_percentile_finalize(const uint32_t* keys_dev, const double* frac_dev, int n_vols, int n_q,
+                              int dtype, float* out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADELL_B200_H_ */

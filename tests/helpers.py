@@ -1,0 +1,42 @@
+"""Shared test helpers: run a composed BatchPlan through the C restatement (CPU) or the
+CUDA path, and build reference chains with the literal torch oracle."""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from adell_mri_b200.plan import BatchPlan
+from oracle import cref
+from oracle import monai_restated as M
+
+
+def run_plan_cref(plan: BatchPlan) -> list[torch.Tensor]:
+    """Execute every pass of a CPU-resident plan with oracle/gather_ref.c."""
+    shape = plan.shape
+    outs = [torch.empty(tuple(int(x) for x in s), dtype=torch.float32) for s in shape]
+    dst_ptr = np.array([o.data_ptr() for o in outs], np.uint64)
+    dst_stride = np.array([o.stride() for o in outs], np.int64)
+    launches = plan.build_launches(dst_ptr, dst_stride, lambda n: torch.empty(max(n, 1), dtype=torch.float32))
+    for items in launches:
+        cref.gather(items)
+    return outs
+
+
+def run_plan_cuda(plan: BatchPlan) -> list[torch.Tensor]:
+    from adell_mri_b200 import engine
+
+    shape = plan.shape
+    outs = [torch.empty(tuple(int(x) for x in s), dtype=torch.float32, device=plan.device) for s in shape]
+    engine.execute(plan, outs)
+    torch.cuda.synchronize()
+    return outs
+
+
+def rand_affine_matrix(R: np.random.RandomState, rotate=(0.4, 0.4, 0.2), shear=None, translate=(6, 6, 2), scale=(0.1, 0.1, 0.1)):
+    p = M.rand_affine_grid_params(R, rotate_range=rotate, shear_range=shear, translate_range=translate, scale_range=scale)
+    return M.compose_affine(p["rotate"], p["shear"], p["translate"], p["scale"])
+
+
+def mismatch(a: torch.Tensor, b: torch.Tensor) -> int:
+    return int((a != b).sum())
