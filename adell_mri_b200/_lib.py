@@ -43,8 +43,8 @@ class Item(C.Structure):
         ("grid_shape", C.c_int32 * 3),
         ("grid_off", C.c_int32 * 3),
         ("grid_sign", C.c_int32 * 3),
-        ("grid_vlo", C.c_int32 * 3),
-        ("grid_vhi", C.c_int32 * 3),
+        ("out_vlo", C.c_int32 * 3),
+        ("out_vhi", C.c_int32 * 3),
         ("tmap_off", C.c_int32 * 3),
         ("tmap_sign", C.c_int32 * 3),
         ("tmap_box", C.c_int32 * 3),
@@ -83,6 +83,7 @@ _SIGNATURES = {
     "adell_status_string": (C.c_char_p, [C.c_int]),
     "adell_item_size": (C.c_int, []),
     "adell_device_sm_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "adell_mat4_chain": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "adell_aug_plan_tiles": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int64)]),
     "adell_item_encode_tensormap": (C.c_int, [C.c_void_p]),
     "adell_aug_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),

@@ -117,14 +117,14 @@ __device__ __forceinline__ void k1_tile(const K1Ctx& c, int b0, int b1, int b2, 
   if (o0 >= it.out_shape[0] || o2 >= it.out_shape[2]) return;
   const int g0 = it.grid_off[0] + it.grid_sign[0] * o0;
   const int g2 = it.grid_off[2] + it.grid_sign[2] * o2;
-  const bool gv02 = (g0 >= it.grid_vlo[0]) & (g0 < it.grid_vhi[0]) & (g2 >= it.grid_vlo[2]) & (g2 < it.grid_vhi[2]);
+  const bool gv02 = (o0 >= it.out_vlo[0]) & (o0 < it.out_vhi[0]) & (o2 >= it.out_vlo[2]) & (o2 < it.out_vhi[2]);
   const bool strict = (it.flags & ADELL_F_STRICT) != 0;
   for (int s = 0; s < 4; s += rpw) {
     const int o1 = j_base + s + r;
     if (o1 >= it.out_shape[1]) continue;
     const int g1 = it.grid_off[1] + it.grid_sign[1] * o1;
     float val = 0.0f;
-    if (gv02 && g1 >= it.grid_vlo[1] && g1 < it.grid_vhi[1]) {
+    if (gv02 && o1 >= it.out_vlo[1] && o1 < it.out_vhi[1]) {
       val = IDENT ? k1_identity_voxel<DT>(c, g0, g1, g2)
                   : k1_resample_voxel<INTERP, PAD, DT, PERTAP>(c, g0, g1, g2);
     }

@@ -73,6 +73,14 @@ def execute(plan: BatchPlan, dsts: Sequence[torch.Tensor]) -> None:
             raise ValueError(f"destination {i} has shape {tuple(d.shape)}, plan produces {tuple(shape[i])}")
         dst_ptr[i] = d.data_ptr()
         dst_stride[i] = d.stride()
+    execute_ptrs(plan, dst_ptr, dst_stride)
+
+
+def execute_ptrs(plan: BatchPlan, dst_ptr: np.ndarray, dst_stride: np.ndarray, keep=None) -> None:
+    """Like :func:`execute` with raw destination pointers (``[n]`` uint64, ``[n,3]`` element strides)."""
+    _require_cuda(plan.device)
+    if keep:
+        plan.keep.extend(keep)
     with torch.cuda.device(plan.device):
         launches = plan.build_launches(
             dst_ptr, dst_stride, lambda n: torch.empty(max(n, 1), dtype=torch.float32, device=plan.device)

@@ -1,0 +1,108 @@
+"""Host-side affine composition, batched, in MONAI's exact fp32 operation order.
+
+MONAI's ``AffineGrid`` builds ``eye(4) @ rotate @ shear @ translate @ scale`` with torch fp32
+ops (sin/cos of the fp32-cast angle; 3-D rotate = Rx @ Ry @ Rz with only the leading
+rotations if fewer than three angles are given).  This module does the same for a whole
+batch at once (``[B, 4, 4]`` torch CPU tensors) so that the matrices handed to K1 are the
+ones the reference's RandAffined would have produced for the same parameter draws
+(wiring: /root/reference/adell_mri/transform_factory/augmentations.py:98-116,279-301;
+/root/reference/adell_mri/modules/augmentations.py:131-186).
+"""
+
+from __future__ import annotations
+
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _eye(b: int) -> torch.Tensor:
+    return torch.eye(4, dtype=torch.float32).repeat(b, 1, 1)
+
+
+def _as_param(x, b: int) -> torch.Tensor | None:
+    """``[B, k]`` float32 tensor (k = number of parameters given) or None when empty."""
+    if x is None:
+        return None
+    a = np.asarray(x, dtype=np.float64)
+    if a.size == 0:
+        return None
+    if a.ndim == 1:
+        a = np.broadcast_to(a, (b, a.shape[0]))
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32)
+
+
+def rotate_factors(radians: torch.Tensor) -> list[torch.Tensor]:
+    """The Rx, Ry, Rz factors (leading ones only) — multiplied left to right by the caller."""
+    b, k = radians.shape
+    s, c = torch.sin(radians), torch.cos(radians)
+    out = []
+    if k >= 1:
+        m = _eye(b)
+        m[:, 1, 1], m[:, 1, 2] = c[:, 0], -s[:, 0]
+        m[:, 2, 1], m[:, 2, 2] = s[:, 0], c[:, 0]
+        out.append(m)
+    if k >= 2:
+        m = _eye(b)
+        m[:, 0, 0], m[:, 0, 2] = c[:, 1], s[:, 1]
+        m[:, 2, 0], m[:, 2, 2] = -s[:, 1], c[:, 1]
+        out.append(m)
+    if k >= 3:
+        m = _eye(b)
+        m[:, 0, 0], m[:, 0, 1] = c[:, 2], -s[:, 2]
+        m[:, 1, 0], m[:, 1, 1] = s[:, 2], c[:, 2]
+        out.append(m)
+    return out
+
+
+def shear_matrices(coefs: torch.Tensor) -> torch.Tensor:
+    b, k = coefs.shape
+    c = torch.zeros(b, 6, dtype=torch.float32)
+    c[:, : min(k, 6)] = coefs[:, :6]
+    out = _eye(b)
+    out[:, 0, 1], out[:, 0, 2] = c[:, 0], c[:, 1]
+    out[:, 1, 0], out[:, 1, 2] = c[:, 2], c[:, 3]
+    out[:, 2, 0], out[:, 2, 1] = c[:, 4], c[:, 5]
+    return out
+
+
+def translate_matrices(shift: torch.Tensor) -> torch.Tensor:
+    b, k = shift.shape
+    out = _eye(b)
+    out[:, : min(k, 3), 3] = shift[:, :3]
+    return out
+
+
+def scale_matrices(factors: torch.Tensor) -> torch.Tensor:
+    b, k = factors.shape
+    out = _eye(b)
+    for i in range(min(k, 3)):
+        out[:, i, i] = factors[:, i]
+    return out
+
+
+def compose_affine(rotate=None, shear=None, translate=None, scale=None, batch: int | None = None) -> np.ndarray:
+    """``[B, 4, 4]`` float32 MONAI AffineGrid matrices for a batch of parameter sets.
+    Every argument is ``[B, k]`` (or ``[k]``, broadcast) or None/empty."""
+    if batch is None:
+        batch = 1
+        for x in (rotate, shear, translate, scale):
+            if x is not None and np.asarray(x).ndim == 2:
+                batch = np.asarray(x).shape[0]
+    r, sh, t, sc = (_as_param(x, batch) for x in (rotate, shear, translate, scale))
+    mats = [_eye(batch)]
+    if r is not None:
+        mats.extend(rotate_factors(r))
+    if sh is not None:
+        mats.append(shear_matrices(sh))
+    if t is not None:
+        mats.append(translate_matrices(t))
+    if sc is not None:
+        mats.append(scale_matrices(sc))
+    stack = np.ascontiguousarray(torch.stack(mats, dim=1).numpy())  # [B, K, 4, 4]
+    out = np.empty((batch, 4, 4), np.float32)
+    _lib.check(_lib.load().adell_mat4_chain(stack.ctypes.data, batch, stack.shape[1], out.ctypes.data), "adell_mat4_chain")
+    return out

@@ -443,8 +443,8 @@ class BatchPlan:
         it["grid_shape"] = st.pre.size  # spatial_size=None: the affine grid has the source size
         it["grid_off"] = np.where(ha, st.post.off, 0)
         it["grid_sign"] = np.where(ha, st.post.sign, 1)
-        it["grid_vlo"] = np.where(ha, st.post.vlo, 0)
-        it["grid_vhi"] = np.where(ha, st.post.vhi, st.pre.size)
+        it["out_vlo"] = np.where(ha, st.post.vlo, 0)
+        it["out_vhi"] = np.where(ha, st.post.vhi, st.pre.size)
         it["A"] = st.A.reshape(n, 12)
         it["nrm"] = (2.0 / np.maximum(2, st.pre.size)).astype(np.float32)
         it["pre_scale"] = st.pre_s.astype(np.float32)

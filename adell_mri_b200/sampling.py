@@ -1,0 +1,81 @@
+"""Host-side random-parameter draws that follow the reference's RandomState streams.
+
+The reference seeds its pipelines with ``Compose.set_random_state(seed)``
+(/root/reference/adell_mri/entrypoints/segmentation/train.py:449, classification/train.py:243,
+ssl/train_3d.py:196) and MONAI then draws, per sample, in a fixed order from per-transform
+``numpy.random.RandomState`` objects.  The classes below reproduce those draw orders († —
+restated from MONAI 1.3-1.6; MONAI is not importable here) so that, given the same seed,
+the same geometric parameters reach the GPU.  Parity of *voxels* is asserted at the
+parameter boundary; stream fidelity is best effort and documented as such in DESIGN.md.
+"""
+
+from __future__ import annotations
+
+from typing import Sequence
+
+import numpy as np
+
+MAX_SEED = np.iinfo(np.uint32).max + 1
+
+
+def _issequence(f):
+    return isinstance(f, (list, tuple, np.ndarray))
+
+
+def rand_param(R: np.random.RandomState, param_range, add_scalar: float = 0.0) -> list[float]:
+    """RandAffineGrid._get_rand_param †."""
+    out = []
+    for f in param_range or []:
+        if _issequence(f):
+            if len(f) != 2:
+                raise ValueError("If giving range as [min,max], should only have two elements per dim.")
+            out.append(R.uniform(f[0], f[1]) + add_scalar)
+        elif f is not None:
+            out.append(R.uniform(-f, f) + add_scalar)
+    return out
+
+
+class RandAffineSampler:
+    """Draw order of ``monai.transforms.RandAffined.__call__`` (three identically seeded
+    streams: the dict transform, its RandAffine and its RandAffineGrid) †."""
+
+    def __init__(self, prob=0.1, rotate_range=None, shear_range=None, translate_range=None, scale_range=None):
+        self.prob = prob
+        self.rotate_range, self.shear_range = rotate_range, shear_range
+        self.translate_range, self.scale_range = translate_range, scale_range
+        self.set_random_state()
+
+    def set_random_state(self, seed=None, state=None):
+        if state is not None:
+            self.R = self.R_inner = self.R_grid = state  # a shared state object, as MONAI does
+        else:
+            self.R = np.random.RandomState(seed)
+            self.R_inner = np.random.RandomState(seed)
+            self.R_grid = np.random.RandomState(seed)
+        return self
+
+    def _grid_params(self):
+        R = self.R_grid
+        return dict(
+            rotate=rand_param(R, self.rotate_range),
+            shear=rand_param(R, self.shear_range),
+            translate=rand_param(R, self.translate_range),
+            scale=rand_param(R, self.scale_range, 1.0),
+        )
+
+    def draw(self, n_keys: int = 1):
+        """One ``__call__``: returns ``(fired, params-or-None)``."""
+        fired = self.R.rand() < self.prob          # RandAffined.randomize
+        self.R_inner.rand()                        # RandAffine.randomize (prob=1.0) ...
+        self._grid_params()                        # ... -> RandAffineGrid.randomize (discarded)
+        used = self._grid_params() if fired else None  # RandAffineGrid.__call__ re-randomises: USED
+        for _ in range(n_keys):                    # per key: RandAffine.__call__(randomize=True)
+            self.R_inner.rand()
+            self._grid_params()
+        return fired, used
+
+
+def child_seeds(seed: int, n: int) -> list[int]:
+    """``Compose.set_random_state(seed)``: one ``R.randint(MAX_SEED, dtype=uint32)`` per Randomizable child †."""
+    R = np.random.RandomState(seed)
+    return [int(R.randint(MAX_SEED, dtype="uint32")) for _ in range(n)]

@@ -1,0 +1,179 @@
+"""Device-side intensity statistics and scalers (K2/K3 + the exact intensity program).
+
+Mirrors what the reference computes on the CPU inside its cached pre-transforms:
+``ScaleIntensityd(minv=0, maxv=1)``, ``ConditionalRescalingd(500, 0.001)``, ``Offsetd(None)``,
+``ScaleIntensityd(factor=-2/3)`` (/root/reference/adell_mri/transform_factory/transforms.py:
+143-155,430-443,772-786; /root/reference/adell_mri/utils/monai_transforms/
+image_intensity_ops.py:71-74,119-121) and the percentile scaler the north star names
+(monai ``ScaleIntensityRangePercentilesd`` — ``np.percentile`` 'linear' semantics).
+Everything stays on the device and on the current stream: no host round trip between the
+statistics and the kernels that consume them.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .plan import _TORCH_TO_ADELL
+
+HIST_BITS = 11
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _check_vols(vols: Sequence[torch.Tensor]):
+    if len(vols) == 0:
+        raise ValueError("no volumes")
+    dev = vols[0].device
+    if dev.type != "cuda":
+        raise RuntimeError("adell_mri_b200.stats runs on CUDA devices only (no CPU fallback)")
+    for v in vols:
+        if v.device != dev or not v.is_contiguous() or v.dtype not in _TORCH_TO_ADELL:
+            raise ValueError("volumes must be contiguous f32/i16/u8 tensors on one CUDA device")
+    return dev
+
+
+def vol_descriptors(vols: Sequence[torch.Tensor]) -> tuple[torch.Tensor, int]:
+    """Upload the ``adell_vol`` descriptor array; returns (device buffer, max element count)."""
+    dev = _check_vols(vols)
+    arr = np.zeros(len(vols), np.dtype(_lib.Vol))
+    arr["data"] = [v.data_ptr() for v in vols]
+    arr["n"] = [v.numel() for v in vols]
+    arr["dtype"] = [_TORCH_TO_ADELL[v.dtype] for v in vols]
+    host = torch.from_numpy(arr.view(np.uint8).reshape(-1).copy()).pin_memory()
+    return host.to(dev, non_blocking=True), int(arr["n"].max())
+
+
+def minmax(vols: Sequence[torch.Tensor], desc=None) -> torch.Tensor:
+    """``[n, 2]`` fp32 (min, max) per volume."""
+    dev = _check_vols(vols)
+    d, max_n = desc if desc is not None else vol_descriptors(vols)
+    out = torch.empty(len(vols), 2, dtype=torch.float32, device=dev)
+    _lib.check(_lib.load().adell_minmax(d.data_ptr(), len(vols), max_n, out.data_ptr(), _stream(dev)), "adell_minmax")
+    return out
+
+
+def scaler_coefs(stats: torch.Tensor, scaler: int, p0: float, p1: float) -> torch.Tensor:
+    """``[n, 6]`` coefficients of ``y = ((x*m0 - a)/d)*m1*m2 + b`` for one of the reference scalers."""
+    n = stats.shape[0]
+    coefs = torch.empty(n, 6, dtype=torch.float32, device=stats.device)
+    _lib.check(
+        _lib.load().adell_scaler_coefs(stats.data_ptr(), n, scaler, float(p0), float(p1), coefs.data_ptr(), _stream(stats.device)),
+        "adell_scaler_coefs",
+    )
+    return coefs
+
+
+def coefs_to_affine(coefs: torch.Tensor) -> torch.Tensor:
+    """Collapse the exact program into the fused-mode ``{scale, offset}`` pair (``[n, 2]``)."""
+    n = coefs.shape[0]
+    out = torch.empty(n, 2, dtype=torch.float32, device=coefs.device)
+    _lib.check(_lib.load().adell_coefs_to_affine(coefs.data_ptr(), n, out.data_ptr(), _stream(coefs.device)), "adell_coefs_to_affine")
+    return out
+
+
+def intensity_map(vols: Sequence[torch.Tensor], coefs: torch.Tensor, clip=None, desc=None) -> list[torch.Tensor]:
+    """Exact (bit-faithful op order) elementwise scaler; returns new fp32 volumes."""
+    dev = _check_vols(vols)
+    d, max_n = desc if desc is not None else vol_descriptors(vols)
+    outs = [torch.empty(v.shape, dtype=torch.float32, device=dev) for v in vols]
+    ptrs = torch.tensor([o.data_ptr() for o in outs], dtype=torch.int64).pin_memory().to(dev, non_blocking=True)
+    lo, hi = (0.0, 0.0) if clip is None else clip
+    _lib.check(
+        _lib.load().adell_intensity_map(
+            d.data_ptr(), ptrs.data_ptr(), coefs.data_ptr(), len(vols), max_n, int(clip is not None), lo, hi, _stream(dev)
+        ),
+        "adell_intensity_map",
+    )
+    return outs
+
+
+def _pass_schedule(dtype: torch.dtype):
+    """(shift, bits) per radix pass over the 32-bit order-preserving key."""
+    if dtype == torch.float32:
+        return [(21, 11), (10, 11), (0, 10)]
+    if dtype == torch.int16:
+        return [(21, 11), (16, 5)]
+    return [(24, 8)]
+
+
+def numpy_virtual_index(n: int, q: float):
+    """numpy ``_compute_virtual_index`` (method 'linear': alpha=beta=1) and ``_get_indexes`` /
+    ``_get_gamma`` in float64: returns (lo, hi, gamma)."""
+    quant = np.true_divide(np.float64(q), 100.0)
+    vi = n * quant + (1.0 + quant * (1.0 - 1.0 - 1.0)) - 1.0
+    if vi >= n - 1:
+        return n - 1, n - 1, 0.0
+    if vi < 0:
+        return 0, 0, 0.0
+    lo = int(np.floor(vi))
+    return lo, lo + 1, float(vi - lo)
+
+
+def percentiles(
+    vols: Sequence[torch.Tensor],
+    qs: Sequence[float],
+    dataset_wide: bool = False,
+    all_reduce=None,
+    total_n: int | None = None,
+) -> torch.Tensor:
+    """Exact percentiles (numpy 'linear' method) of each volume: ``[n_vols, len(qs)]`` fp32.
+
+    ``dataset_wide=True`` pools all volumes into one histogram (result ``[1, len(qs)]``);
+    ``all_reduce(bins_tensor)`` — e.g. ``torch.distributed.all_reduce`` over NCCL — is then
+    called on the int64 bin counts after every pass so that every rank selects identically,
+    with ``total_n`` the element count over all ranks.
+    """
+    dev = _check_vols(vols)
+    lib = _lib.load()
+    dtype = vols[0].dtype
+    if any(v.dtype != dtype for v in vols):
+        raise ValueError("percentiles: mixed dtypes")
+    n_vols, n_q = len(vols), len(qs)
+    n_sel = 2 * n_q
+    if n_sel > 8:
+        raise ValueError("at most 4 quantiles per call")
+    desc, max_n = vol_descriptors(vols)
+    n_hist = 1 if dataset_wide else n_vols
+    counts = [sum(v.numel() for v in vols) if total_n is None else total_n] if dataset_wide else [v.numel() for v in vols]
+    ranks = np.zeros((n_hist, n_q, 2), np.uint64)
+    frac = np.zeros((n_hist, n_q), np.float64)
+    for h, n in enumerate(counts):
+        for j, q in enumerate(qs):
+            lo, hi, g = numpy_virtual_index(n, q)
+            ranks[h, j] = (lo, hi)
+            frac[h, j] = g
+    rank_dev = torch.from_numpy(ranks.reshape(-1).view(np.int64)).pin_memory().to(dev, non_blocking=True)
+    frac_dev = torch.from_numpy(frac.reshape(-1)).pin_memory().to(dev, non_blocking=True)
+    prefix = torch.zeros(n_hist * n_sel, dtype=torch.int32, device=dev)
+    st = _stream(dev)
+    first = True
+    for shift, bits in _pass_schedule(dtype):
+        n_sel_eff = 1 if first else n_sel
+        bins = torch.zeros(n_hist * n_sel_eff << bits, dtype=torch.int64, device=dev)
+        _lib.check(
+            lib.adell_hist_pass(desc.data_ptr(), n_vols, max_n, n_sel, int(dataset_wide), prefix.data_ptr(), shift, bits,
+                                bins.data_ptr(), st),
+            "adell_hist_pass",
+        )
+        if all_reduce is not None:
+            all_reduce(bins)
+        _lib.check(
+            lib.adell_hist_select(bins.data_ptr(), n_hist, n_sel, shift, bits, prefix.data_ptr(), rank_dev.data_ptr(), st),
+            "adell_hist_select",
+        )
+        first = False
+    out = torch.empty(n_hist, n_q, dtype=torch.float32, device=dev)
+    _lib.check(
+        lib.adell_percentile_finalize(prefix.data_ptr(), frac_dev.data_ptr(), n_hist, n_q, _TORCH_TO_ADELL[dtype],
+                                      out.data_ptr(), st),
+        "adell_percentile_finalize",
+    )
+    return out

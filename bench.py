@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py — augmented voxels/s of the fused GPU augmentation hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload seg|affine_a] [--impl reference]
+
+One *step* = one batch through the whole random chain (host parameter draws in the
+reference's RandomState order -> host composition -> one K1 launch writing the collated
+batch).  Default workload = BASELINE.json configs[1]: the u-net-3d-resnet segmentation
+pipeline, 3 image keys (trilinear) + label mask (nearest), 256x256x32, batch 8,
+get_augmentations_unet(["affine","flip"], flip_axis=[0,1,2]) with the reference's own
+probabilities (affine 0.2, each flip 0.25).  `value` is device-resident throughput (CUDA
+events, max over ranks); `e2e` adds pinned-host H2D of the sources and D2H of the batch;
+`roofline` is algorithmic bytes / mean K1 launch time vs the measured HBM copy peak;
+`cpu_baseline` is the oracle port (torch CPU grid_sample, the kernel MONAI calls) on the
+host cores, one single-threaded worker process per core like the reference's DataLoader.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "augmented voxels/s (RandAffine+flip+crop+norm)"
+UNIT = "voxels/s"
+SEED = 42
+
+WORKLOADS = {
+    # name: (description, spatial shape, image keys, batch per GPU)
+    "seg": ("u-net-3d-resnet segmentation pipeline: T2/ADC/DWI trilinear + mask nearest, 256x256x32, batch 8, "
+            "affine p=0.2 reflection + 3 flips p=0.25", (256, 256, 32), ["t2", "adc", "dwi"], 8),
+    "seg_all_affine": ("same pipeline with the affine forced to fire for every sample (worst case for K1)",
+                       (256, 256, 32), ["t2", "adc", "dwi"], 8),
+}
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi during the timed region (SM clock, throttle reasons)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        exe = shutil.which("nvidia-smi")
+        if exe is None:
+            return self
+        self.proc = subprocess.Popen(
+            [exe, f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+            stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- data
+def make_cache(workload: str, n_samples: int, device, seed: int):
+    """Synthetic device-resident cache: what CacheDataset would hold after the deterministic
+    pre-transforms (intensity-scaled fp32 images, 0/1 fp32 mask)."""
+    import torch
+
+    _, shape, image_keys, _ = WORKLOADS[workload]
+    g = torch.Generator(device=device).manual_seed(seed)
+    cache = []
+    for _ in range(n_samples):
+        s = {k: torch.rand((1, *shape), device=device, generator=g) for k in image_keys}
+        s["mask"] = (torch.rand((1, *shape), device=device, generator=g) > 0.7).float()
+        cache.append(s)
+    return cache
+
+
+def make_augmenter(workload: str):
+    from adell_mri_b200.pipelines import SegmentationBatchAugmenter
+
+    _, _, image_keys, _ = WORKLOADS[workload]
+    aug = SegmentationBatchAugmenter(["affine", "flip"], image_keys + ["mask"], image_keys, flip_axis=[0, 1, 2])
+    if workload == "seg_all_affine":
+        for s in aug.samplers:
+            s.prob = 1.0
+    return aug
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+def _cpu_worker(args):
+    """One single-threaded worker (the reference's DataLoader-worker model): runs the oracle
+    chain for `n` samples and returns (voxel-channels, seconds)."""
+    workload, n, seed = args
+    import numpy as np
+    import torch
+
+    torch.set_num_threads(1)
+    from oracle import monai_restated as M
+
+    _, shape, image_keys, _ = WORKLOADS[workload]
+    R = np.random.RandomState(seed)
+    keys = image_keys + ["mask"]
+    sample = {k: torch.from_numpy(R.rand(1, *shape).astype(np.float32)) for k in keys}
+    prob = 1.0 if workload == "seg_all_affine" else 0.2
+    draws = M.RandAffinedDraws(prob, rotate_range=[np.pi / 8, np.pi / 8, np.pi / 16], n_keys=len(keys)).set_random_state(seed)
+    flipR = [np.random.RandomState(seed + 1 + a) for a in range(3)]
+    vox = 0
+    t0 = time.perf_counter()
+    for _ in range(n):
+        fired, p = draws.draw()
+        A = M.compose_affine(p["rotate"]) if fired else None
+        flips = [a for a in range(3) if flipR[a].rand() < 0.25]
+        outs = []
+        for k in keys:
+            o = M.canonical_item(sample[k], affine=A, mode="nearest" if k == "mask" else "bilinear",
+                                 padding_mode="reflection", post_ops=[("flip", [a]) for a in flips])
+            outs.append(o)
+            vox += o.numel()
+        torch.cat(outs[:-1], 0)  # ConcatItemsd(image_keys -> "image")
+    return vox, time.perf_counter() - t0
+
+
+class CpuReference:
+    """Persistent pool of single-threaded workers (one per host core)."""
+
+    def __init__(self, workload: str, cores: int | None = None):
+        import multiprocessing as mp
+
+        self.workload = workload
+        self.cores = cores or os.cpu_count() or 1
+        self.pool = mp.get_context("spawn").Pool(self.cores)
+        self.pool.map(_cpu_worker, [(workload, 0, 0)] * self.cores)  # import torch in every worker
+        self.calls = 0
+
+    def run(self, samples_per_worker: int):
+        self.calls += 1
+        res = self.pool.map(_cpu_worker, [(self.workload, samples_per_worker, SEED + 17 * i + 1009 * self.calls)
+                                          for i in range(self.cores)], chunksize=1)
+        vox = sum(r[0] for r in res)
+        busy = max(r[1] for r in res)  # workers run concurrently: throughput over the slowest worker's time
+        self.last = (vox, busy)
+        return dict(value=vox / busy, unit=UNIT, cores=self.cores, kind="port",
+                    sample=f"{self.cores} single-threaded worker processes x {samples_per_worker} samples of the "
+                           f"'{self.workload}' chain (oracle port: torch CPU grid_sample + flip + concat); "
+                           f"{vox} voxel-channels in {busy:.2f}s")
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+# ----------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="seg", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-samples", type=int, default=6, help="samples per CPU worker for the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cache-samples", type=int, default=32)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    desc, shape, image_keys, batch = WORKLOADS[args.workload]
+    nk = len(image_keys) + 1
+    vox_per_step = batch * nk * shape[0] * shape[1] * shape[2]
+    config = {"workload": f"{args.workload}: {desc}", "batch_per_gpu": batch, "shape": list(shape), "keys": nk,
+              "src_dtype": "f32", "l2": "inputs larger than L2: each step reads 268 MB of sources from a rotating "
+              f"{args.cache_samples}-sample device cache and writes 268 MB", "sharding": "by sample, no collective"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        # each step = a bounded sample of the workload on all host cores
+        ref = CpuReference(args.workload)
+        per_step, raw = [], []
+        for _ in range(args.warmup + args.steps):
+            per_step.append(ref.run(1))
+            raw.append(ref.last)
+        ref.close()
+        # whole-run throughput = total voxel-channels / total busy time of the timed steps
+        tot_v = sum(r[0] for r in raw[args.warmup:])
+        tot_t = sum(r[1] for r in raw[args.warmup:])
+        v = tot_v / tot_t
+        cb = dict(per_step[-1]); cb["value"] = v
+        cb["sample"] = f"{args.steps} steps, each: " + cb["sample"].split(";")[0]
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * vox_per_step / v, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "cpu_baseline": cb,
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import numpy as np
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    from adell_mri_b200 import _lib, engine
+
+    if not os.path.exists(_lib.LIB_PATH):
+        raise SystemExit("libadell_b200.so missing: run __graft_entry__.build() first")
+    _lib.load()
+
+    cache = make_cache(args.workload, args.cache_samples, dev, 1234 + rank)
+    aug = make_augmenter(args.workload).set_random_state(SEED + rank)
+    out = {"image": torch.empty((batch, len(image_keys), *shape), device=dev),
+           "mask": torch.empty((batch, 1, *shape), device=dev)}
+    n_batches = args.cache_samples // batch
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i):
+        b0 = (i % n_batches) * batch
+        aug(cache[b0:b0 + batch], out=out)
+
+    # ---- device-resident throughput ("value") ----
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    clocks = ClockSampler(local_rank).start()
+    stream = torch.cuda.current_stream()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps)]
+    launches0 = engine.launch_count
+    e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_start.record(stream)
+    for i in range(args.steps):
+        ev[2 * i].record(stream)
+        step(args.warmup + i)
+        ev[2 * i + 1].record(stream)
+    e_stop.record(stream)
+    barrier()
+    clock_info = clocks.stop()
+    total_ms = e_start.elapsed_time(e_stop)
+    k1_ms = [ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps)]  # H2D of 16 KB params + K1
+    launches = engine.launch_count - launches0
+
+    # ---- roofline: K1 launch duration alone (params already uploaded), same seeded steps ----
+    from adell_mri_b200.engine import launch_packed, pack_launch
+
+    prepared = []
+    aug_r = make_augmenter(args.workload).set_random_state(SEED + rank)
+    for i in range(min(args.steps, 16)):
+        b0 = (i % n_batches) * batch
+        plan = aug_r.plan(cache[b0:b0 + batch])
+        ptr = np.array([out["image"][b, c].data_ptr() for b in range(batch) for c in range(len(image_keys))]
+                       ).reshape(batch, -1)
+        mptr = np.array([out["mask"][b, 0].data_ptr() for b in range(batch)]).reshape(batch, 1)
+        dst_ptr = np.concatenate([ptr, mptr], 1).reshape(-1).astype(np.uint64)
+        dst_stride = np.tile(np.asarray(out["image"].stride()[2:], np.int64), (batch * nk, 1))
+        items = plan.build_launches(dst_ptr, dst_stride, lambda n: torch.empty(max(n, 1), device=dev))[-1]
+        buf, n, total = pack_launch(items)
+        prepared.append((torch.from_numpy(buf).to(dev), n, total, plan))
+    torch.cuda.synchronize()
+    kev = []
+    for rep in range(3):
+        for (buf, n, total, _) in prepared:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream); launch_packed(buf, n, total); b.record(stream)
+            kev.append((a, b))
+    torch.cuda.synchronize()
+    kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in kev[len(prepared):])
+    alg_bytes = 8.0 * vox_per_step  # fp32 source read + fp32 write per output voxel-channel
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "k1_gather_direct", "kernel_ms": kernel_ms, "algorithmic_bytes": alg_bytes,
+                "peak_source": peak_src}
+
+    # ---- end to end with host buffers ("e2e") ----
+    host_cache = [{k: v.cpu().pin_memory() for k, v in s.items()} for s in cache[:2 * batch]]
+    host_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}
+    stage = [{k: torch.empty_like(v) for k, v in s.items()} for s in cache[:batch]]
+    h2d = sum(v.numel() * 4 for s in host_cache[:batch] for v in s.values())
+    d2h = sum(v.numel() * 4 for v in out.values())
+
+    def e2e_step(i):
+        b0 = (i % 2) * batch
+        for j in range(batch):
+            for k in stage[j]:
+                stage[j][k].copy_(host_cache[b0 + j][k], non_blocking=True)
+        aug(stage, out=out)
+        for k in out:
+            host_out[k].copy_(out[k], non_blocking=True)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for i in range(e2e_steps):
+        e2e_step(i)
+    b.record(stream)
+    barrier()
+    e2e_ms = a.elapsed_time(b) / e2e_steps
+
+    ms_per_step = total_ms / args.steps
+    t = torch.tensor([ms_per_step, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": world * vox_per_step / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "roofline": roofline,
+            "e2e": {"value": world * vox_per_step / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
+            "gpu_launches": launches, "clocks": clock_info,
+            "step_ms_median_incl_param_upload": statistics.median(k1_ms),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            ref = CpuReference(args.workload)
+            line["cpu_baseline"] = ref.run(args.cpu_samples)
+            ref.close()
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

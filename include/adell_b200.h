@@ -88,8 +88,8 @@ extern "C" {
  * Resample domain index t (per axis, 0 <= t < S) addresses  src + sum_a t_a*src_stride[a]
  * (strides are SIGNED: a flip before the resample is a negative stride) and reads literal 0
  * when t_a is outside [src_vlo[a], src_vhi[a]) (constant SpatialPadd band).  Output index o
- * maps to grid index g_a = grid_off[a] + grid_sign[a]*o_a and reads literal 0 when g_a is
- * outside [grid_vlo[a], grid_vhi[a]).  Source coordinates follow MONAI/ATen bit for bit:
+ * maps to grid index g_a = grid_off[a] + grid_sign[a]*o_a and reads literal 0 when o_a is
+ * outside [out_vlo[a], out_vhi[a]) (SpatialPadd after the resample).  Source coordinates follow MONAI/ATen bit for bit:
  *   c_a = g_a - (G_a-1)/2 ;  x_a = fma(A[a][3],1, fma(A[a][2],c_2, fma(A[a][1],c_1, A[a][0]*c_0)))
  *   n_a = x_a * nrm[a]    ;  u_a = ((n_a + 1) * S_a - 1) / 2       (each op rounded to fp32)
  * then padding_mode / floor / rint exactly as ATen's grid_sampler_3d CPU kernel.
@@ -111,8 +111,8 @@ typedef struct __attribute__((aligned(64))) adell_item {
   int32_t grid_shape[3];   /* G                                                                      */
   int32_t grid_off[3];
   int32_t grid_sign[3];    /* +1 or -1                                                               */
-  int32_t grid_vlo[3];
-  int32_t grid_vhi[3];
+  int32_t out_vlo[3];
+  int32_t out_vhi[3];
   int32_t tmap_off[3];     /* t-space index of the tmap box origin (staged path)                    */
   int32_t tmap_sign[3];    /* +1/-1: box index = tmap_sign*(t - tmap_off) (staged path)             */
   int32_t tmap_box[3];     /* staged box extents actually encoded (z,y,x order = axes 2,1,0)        */
@@ -130,6 +130,11 @@ int adell_abi_version(void);
 const char* adell_status_string(int status);
 int adell_item_size(void);           /* sizeof(adell_item), for bindings to cross-check      */
 int adell_device_sm_count(int* out); /* number of SMs of the current device                   */
+
+/* Host-only: out[b] = mats[b][0] @ ... @ mats[b][k-1] (4x4 fp32, row-major), every product an
+ * fp32 FMA chain in k order = what torch's CPU `@` yields for MONAI's AffineGrid composition
+ * (monai AffineGrid: affine = eye @ rotate @ shear @ translate @ scale). */
+int adell_mat4_chain(const float* mats, int batch, int k, float* out);
 
 /* -- K1: fused gather ----------------------------------------------------------------- */
 /* Host-only: fills tile_start_host[0..n_items] with the exclusive prefix of per-item tile

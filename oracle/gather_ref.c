@@ -145,7 +145,7 @@ int adell_ref_gather(const adell_item* items, int n_items) {
           int g[3], ok = 1;
           for (int a = 0; a < 3; ++a) {
             g[a] = it->grid_off[a] + it->grid_sign[a] * o[a];
-            if (g[a] < it->grid_vlo[a] || g[a] >= it->grid_vhi[a]) ok = 0;
+            if (o[a] < it->out_vlo[a] || o[a] >= it->out_vhi[a]) ok = 0;
           }
           float val = ok ? voxel(it, g[0], g[1], g[2], pre_s, pre_o) : 0.0f;
           if (strict) {

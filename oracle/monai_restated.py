@@ -392,7 +392,8 @@ def percentile(x: torch.Tensor, q: float) -> float:
     >1e6 elements ⇒ numpy 'linear' percentile (float64 lerp, cast back to the
     tensor dtype); else torch.quantile."""
     if x.numel() > 1_000_000:
-        r = np.percentile(x.numpy(), q)
+        # MONAI hands q over as a float64 ndarray -> numpy interpolates in float64
+        r = np.percentile(x.numpy(), np.asarray(q, dtype=np.float64))
         return torch.as_tensor(r).to(x.dtype)
     return torch.quantile(x, torch.as_tensor(q / 100.0, dtype=x.dtype))
 

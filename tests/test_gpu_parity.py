@@ -1,0 +1,155 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) vs the oracle on the same
+seeded inputs.  Bit-exact for integer/index work, nearest masks and strict trilinear;
+<=1e-4 (relative to the reference / its dynamic range) for the default fused trilinear."""
+
+import numpy as np
+import pytest
+import torch
+
+from adell_mri_b200.plan import BatchPlan
+from oracle import monai_restated as M
+from tests.cases import CHAIN_CASES, chain_case, noise_then_resample_case, two_resample_case
+from tests.helpers import mismatch, rand_affine_matrix, run_plan_cref, run_plan_cuda
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("name,kw", CHAIN_CASES, ids=[c[0] for c in CHAIN_CASES])
+def test_chain_bit_exact_vs_torch_oracle(name, kw):
+    for seed in range(3):
+        plan, ref = chain_case(seed, device=DEV, **kw)
+        out = run_plan_cuda(plan)[0].cpu()
+        assert out.shape == ref.shape
+        assert mismatch(out, ref) == 0, name
+
+
+@pytest.mark.parametrize("name,kw", CHAIN_CASES, ids=[c[0] for c in CHAIN_CASES])
+def test_chain_default_mode_matches_c_restatement_and_tolerance(name, kw):
+    plan_gpu, ref = chain_case(21, device=DEV, strict=False, **kw)
+    plan_cpu, _ = chain_case(21, device="cpu", strict=False, **kw)
+    out = run_plan_cuda(plan_gpu)[0].cpu()
+    cref_out = run_plan_cref(plan_cpu)[0]
+    tol = 1e-4 * float(ref.abs().max())
+    assert torch.allclose(out, ref, rtol=1e-4, atol=tol)
+    # the C restatement mirrors the fused arithmetic (fma accumulate): identical bits expected
+    assert mismatch(out, cref_out) == 0
+
+
+def test_multi_pass_chains():
+    for fn in (two_resample_case, noise_then_resample_case):
+        plan, ref = fn(3, device=DEV)
+        assert mismatch(run_plan_cuda(plan)[0].cpu(), ref) == 0
+
+
+@pytest.mark.parametrize("padding", ["zeros", "border", "reflection"])
+@pytest.mark.parametrize("mode", ["nearest", "bilinear"])
+def test_benchmark_random_affine_shapes(mode, padding):
+    """Config A: the reference's own micro-benchmark shapes and ranges
+    (/root/reference/benchmarks/benchmark-random-affine.py:90-103)."""
+    R = np.random.RandomState(42)
+    for shape in [(128, 128, 16), (64, 64, 8), (128, 128, 32)]:
+        img = torch.from_numpy(R.rand(1, *shape).astype(np.float32))
+        A = rand_affine_matrix(R, rotate=(np.pi / 6,) * 3, translate=(10, 10, 3), scale=(0.1, 0.1, 0.1))
+        ref = M.affine_resample(img, A, mode, padding)[0]
+        out = run_plan_cuda(BatchPlan([img[0].to(DEV)], strict=True).affine(A.numpy(), mode, padding))[0].cpu()
+        assert mismatch(out, ref) == 0
+
+
+def test_far_out_of_range_coordinates():
+    R = np.random.RandomState(7)
+    img = torch.from_numpy(R.rand(1, 12, 10, 8).astype(np.float32))
+    for _ in range(6):
+        A = rand_affine_matrix(R, rotate=(1.5, 1.5, 1.5), translate=(60, 50, 40), scale=(0.8, 0.8, 0.8))
+        for padding in ["zeros", "border", "reflection"]:
+            for mode in ["nearest", "bilinear"]:
+                ref = M.affine_resample(img, A, mode, padding)[0]
+                out = run_plan_cuda(BatchPlan([img[0].to(DEV)], strict=True).affine(A.numpy(), mode, padding))[0].cpu()
+                assert mismatch(out, ref) == 0, (padding, mode)
+
+
+def test_segmentation_batch_collated_in_place():
+    """Config B at reduced size: 3 image keys + mask per sample written straight into the
+    collated [B,C,H,W,D] batch by ONE launch; mask bit-exact, images bit-exact (strict)."""
+    from adell_mri_b200 import engine
+
+    R = np.random.RandomState(1)
+    B, shape = 4, (64, 64, 32)
+    image = torch.zeros(B, 3, *shape, device=DEV)
+    mask = torch.zeros(B, 1, *shape, device=DEV)
+    plans, refs, dsts = [], [], []
+    for b in range(B):
+        fired = R.rand() < 0.6
+        A = rand_affine_matrix(R, rotate=(np.pi / 8, np.pi / 8, np.pi / 16), translate=None, scale=None)
+        flips = [a for a in range(3) if R.rand() < 0.25]
+        vols = [torch.from_numpy(R.rand(1, *shape).astype(np.float32)) for _ in range(3)]
+        vols.append(torch.from_numpy((R.rand(1, *shape) > 0.7).astype(np.float32)))
+        modes = ["bilinear"] * 3 + ["nearest"]
+        for v, m in zip(vols, modes):
+            refs.append(M.canonical_item(v, affine=A if fired else None, mode=m, padding_mode="reflection",
+                                         post_ops=[("flip", flips)] if flips else [])[0])
+        plan = BatchPlan([v[0].to(DEV) for v in vols], strict=True)
+        plan.affine(A.numpy(), modes, "reflection", where=fired)
+        plan.flip(np.array([a in flips for a in range(3)]))
+        plans.append(plan)
+        dsts += [image[b, 0], image[b, 1], image[b, 2], mask[b, 0]]
+    before = engine.launch_count
+    engine.execute(BatchPlan.concat(plans), dsts)
+    torch.cuda.synchronize()
+    assert engine.launch_count - before == 1
+    for d, r in zip(dsts, refs):
+        assert mismatch(d.cpu(), r) == 0
+
+
+def test_full_size_properties():
+    """BASELINE full sizes (256x256x32, 192x192x48, 512x512x128): size-independent properties."""
+    g = torch.Generator(device=DEV).manual_seed(0)
+    for shape in [(256, 256, 32), (192, 192, 48), (512, 512, 128)]:
+        x = torch.rand(shape, device=DEV, generator=g)
+        # identity affine == copy (nearest exact, trilinear exact: weights are 1 and 0)
+        for mode in ("nearest", "bilinear"):
+            out = run_plan_cuda(BatchPlan([x], strict=True).affine(np.eye(4, dtype=np.float32), mode, "zeros"))[0]
+            assert torch.equal(out, x)
+        # flip twice == identity; flip == torch.flip; crop == slicing
+        out = run_plan_cuda(BatchPlan([x]).flip(np.array([True, True, True])))[0]
+        assert torch.equal(out, torch.flip(x, [0, 1, 2]))
+        out = run_plan_cuda(BatchPlan([x]).flip(np.array([True, False, True])).flip(np.array([True, False, True])))[0]
+        assert torch.equal(out, x)
+        crop = tuple(s // 2 for s in shape)
+        out = run_plan_cuda(BatchPlan([x]).center_crop(crop))[0]
+        sl = tuple(slice(s // 2 - c // 2, s // 2 - c // 2 + c) for s, c in zip(shape, crop))
+        assert torch.equal(out, x[sl])
+        # linearity of the trilinear resample: T(a*x) == a*T(x) up to rounding
+        A = rand_affine_matrix(np.random.RandomState(3)).numpy()
+        t1 = run_plan_cuda(BatchPlan([x]).affine(A, "bilinear", "zeros"))[0]
+        t2 = run_plan_cuda(BatchPlan([x * 2.0]).affine(A, "bilinear", "zeros"))[0]
+        assert torch.allclose(t2, 2.0 * t1, rtol=1e-5, atol=1e-6)
+        # 90-degree rotation about axis 2 twice == flip of axes 0 and 1 (square in-plane shapes)
+        if shape[0] == shape[1]:
+            Rz = M.compose_affine(rotate=[0.0, 0.0, np.pi / 2]).numpy()
+            Rz = np.round(Rz)  # exact quarter turn
+            r2 = run_plan_cuda(BatchPlan([x], strict=True).affine(Rz, "nearest", "zeros").affine(Rz, "nearest", "zeros"))[0]
+            assert torch.equal(r2, torch.flip(x, [0, 1]))
+
+
+def test_philox_noise_statistics():
+    x = torch.zeros(64, 64, 32, device=DEV)
+    out = run_plan_cuda(BatchPlan([x]).add_philox_noise(0.5, seed=1234))[0]
+    assert abs(float(out.mean())) < 5e-3
+    assert abs(float(out.std()) - 0.5) < 5e-3
+    out2 = run_plan_cuda(BatchPlan([x]).add_philox_noise(0.5, seed=1234))[0]
+    assert torch.equal(out, out2)
+
+
+def test_c_abi_rejects_bad_items():
+    import ctypes as C
+
+    from adell_mri_b200 import _lib
+
+    lib = _lib.load()
+    items = np.zeros(1, np.dtype(_lib.Item))
+    tiles = np.zeros(2, np.int32)
+    total = C.c_int64(0)
+    assert lib.adell_aug_plan_tiles(items.ctypes.data, 1, tiles.ctypes.data, C.byref(total)) == -1
+    assert lib.adell_aug_gather(8, 8, 1, 1, None) == -3  # misaligned items pointer
+    assert lib.adell_aug_gather(None, None, 0, 0, None) == 0  # empty batch is a no-op

@@ -1,0 +1,115 @@
+"""GPU: K2/K3 statistics kernels vs the oracle (min/max, exact scalers, exact percentiles)."""
+
+import numpy as np
+import pytest
+import torch
+
+from adell_mri_b200 import _lib, stats
+from oracle import monai_restated as M
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _vols(R, n, shape, kind):
+    out = []
+    for i in range(n):
+        if kind == "uniform":
+            v = R.rand(*shape).astype(np.float32) * (i + 1) * 700
+        elif kind == "lognormal":
+            v = R.lognormal(0, 1, size=shape).astype(np.float32)
+        elif kind == "signed":
+            v = R.normal(0, 100, size=shape).astype(np.float32)
+        else:  # mri-like: 40 % exact-zero background + skewed foreground
+            v = R.gamma(2.0, 300.0, size=shape).astype(np.float32)
+            v[R.rand(*shape) < 0.4] = 0.0
+        out.append(torch.from_numpy(v))
+    return out
+
+
+@pytest.mark.parametrize("kind", ["uniform", "lognormal", "signed", "mri"])
+def test_minmax_and_exact_scalers(kind):
+    R = np.random.RandomState(0)
+    vols = _vols(R, 3, (40, 36, 20), kind)
+    dv = [v.to(DEV) for v in vols]
+    mm = stats.minmax(dv)
+    for i, v in enumerate(vols):
+        assert float(mm[i, 0]) == float(v.min()) and float(mm[i, 1]) == float(v.max())
+    # ScaleIntensityd(minv=0, maxv=1)
+    outs = stats.intensity_map(dv, stats.scaler_coefs(mm, _lib.SCALER_MINMAX, 0.0, 1.0))
+    for o, v in zip(outs, vols):
+        assert torch.equal(o.cpu(), M.scale_intensity(v[None], 0.0, 1.0)[0])
+    # GenerationTransforms-style minv=-1, maxv=1
+    outs = stats.intensity_map(dv, stats.scaler_coefs(mm, _lib.SCALER_MINMAX, -1.0, 1.0))
+    for o, v in zip(outs, vols):
+        assert torch.equal(o.cpu(), M.scale_intensity(v[None], -1.0, 1.0)[0])
+    # ADC (segmentation order): ConditionalRescalingd(500, .001) -> ScaleIntensityd(factor=-2/3)
+    outs = stats.intensity_map(dv, stats.scaler_coefs(mm, _lib.SCALER_ADC_SEG, 500, 0.001))
+    for o, v in zip(outs, vols):
+        ref = M.scale_intensity(M.conditional_rescaling(v[None], 500, 0.001), None, None, -2 / 3)[0]
+        assert torch.equal(o.cpu(), ref)
+    # ADC (classification order): + Offsetd(None) in between
+    outs = stats.intensity_map(dv, stats.scaler_coefs(mm, _lib.SCALER_ADC_CLASS, 500, 0.001))
+    for o, v in zip(outs, vols):
+        ref = M.scale_intensity(M.offset(M.conditional_rescaling(v[None], 500, 0.001)), None, None, -2 / 3)[0]
+        assert torch.equal(o.cpu(), ref)
+
+
+def test_constant_volume_minmax_scaler():
+    v = torch.full((8, 8, 8), 3.5)
+    dv = [v.to(DEV)]
+    out = stats.intensity_map(dv, stats.scaler_coefs(stats.minmax(dv), _lib.SCALER_MINMAX, 0.0, 1.0))[0]
+    assert torch.equal(out.cpu(), M.scale_intensity(v[None], 0.0, 1.0)[0])
+
+
+@pytest.mark.parametrize("kind", ["uniform", "lognormal", "signed", "mri"])
+@pytest.mark.parametrize("shape", [(30, 20, 10), (128, 100, 90)])
+def test_percentiles_match_numpy(kind, shape):
+    R = np.random.RandomState(1)
+    vols = _vols(R, 2, shape, kind)
+    qs = [0.5, 99.5]
+    got = stats.percentiles([v.to(DEV) for v in vols], qs).cpu().numpy()
+    for i, v in enumerate(vols):
+        ref = np.percentile(v.numpy().reshape(-1), np.asarray(qs, np.float64)).astype(np.float32)
+        assert np.array_equal(got[i], ref), (got[i], ref)
+
+
+def test_percentiles_edge_quantiles_and_int16():
+    R = np.random.RandomState(2)
+    v = torch.from_numpy(R.randint(-300, 4000, size=(50, 40, 30)).astype(np.int16))
+    qs = [0.0, 1.0, 50.0, 100.0]
+    got = stats.percentiles([v.to(DEV)], qs).cpu().numpy()[0]
+    ref = np.percentile(v.numpy().astype(np.float32).reshape(-1), np.asarray(qs, np.float64)).astype(np.float32)
+    assert np.array_equal(got, ref)
+    u = torch.from_numpy(R.randint(0, 256, size=(33, 31, 7)).astype(np.uint8))
+    got = stats.percentiles([u.to(DEV)], [2.0, 98.0]).cpu().numpy()[0]
+    ref = np.percentile(u.numpy().astype(np.float32).reshape(-1), np.asarray([2.0, 98.0])).astype(np.float32)
+    assert np.array_equal(got, ref)
+
+
+def test_dataset_wide_percentile_pools_volumes():
+    R = np.random.RandomState(3)
+    vols = _vols(R, 4, (32, 32, 16), "lognormal")
+    got = stats.percentiles([v.to(DEV) for v in vols], [1.0, 99.0], dataset_wide=True).cpu().numpy()[0]
+    pooled = np.concatenate([v.numpy().reshape(-1) for v in vols])
+    ref = np.percentile(pooled, np.asarray([1.0, 99.0])).astype(np.float32)
+    assert np.array_equal(got, ref)
+
+
+def test_percentile_scaler_fused_and_exact():
+    """ScaleIntensityRangePercentilesd(0.5, 99.5, 0, 1, clip=True): exact program vs oracle and
+    fused {scale, offset} + per-tap clip inside K1 within 1e-4."""
+    from adell_mri_b200.plan import BatchPlan
+    from tests.helpers import run_plan_cuda
+
+    R = np.random.RandomState(4)
+    v = _vols(R, 1, (128, 100, 90), "mri")[0]
+    dv = v.to(DEV)
+    pct = stats.percentiles([dv], [0.5, 99.5])
+    coefs = stats.scaler_coefs(pct, _lib.SCALER_RANGE, 0.0, 1.0)
+    exact = stats.intensity_map([dv], coefs, clip=(0.0, 1.0))[0]
+    ref = M.scale_intensity_range_percentiles(v[None], 0.5, 99.5, 0.0, 1.0, clip=True)[0]
+    assert torch.equal(exact.cpu(), ref)
+    plan = BatchPlan([dv]).intensity_from_device(stats.coefs_to_affine(coefs)).clip(0.0, 1.0)
+    fused = run_plan_cuda(plan)[0]
+    assert torch.allclose(fused.cpu(), ref, rtol=1e-4, atol=1e-4)
