@@ -70,6 +70,12 @@ class Item(C.Structure):
 assert C.sizeof(Item) == 512, C.sizeof(Item)
 
 
+class LaunchInfo(C.Structure):
+    """Mirror of ``adell_launch_info``."""
+
+    _fields_ = [("total_tiles", C.c_int64), ("smem_bytes", C.c_int32), ("n_staged", C.c_int32)]
+
+
 class Vol(C.Structure):
     """Mirror of ``adell_vol``."""
 
@@ -84,9 +90,8 @@ _SIGNATURES = {
     "adell_item_size": (C.c_int, []),
     "adell_device_sm_count": (C.c_int, [C.POINTER(C.c_int)]),
     "adell_mat4_chain": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
-    "adell_aug_plan_tiles": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int64)]),
-    "adell_item_encode_tensormap": (C.c_int, [C.c_void_p]),
-    "adell_aug_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
+    "adell_aug_prepare": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "adell_aug_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "adell_aug_gather_launches": (C.c_int, []),
     "adell_minmax": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     "adell_intensity_map": (

@@ -29,14 +29,6 @@ extern "C" int adell_device_sm_count(int* out) {
   return ADELL_OK;
 }
 
-// Staged (TMA) path descriptor encoding: implemented in gather_staged.cu once that path
-// lands; until then no item is eligible and the direct path serves every item.
-extern "C" int adell_item_encode_tensormap(adell_item* item_host) {
-  if (item_host == nullptr) return ADELL_ERR_BAD_ARG;
-  item_host->flags &= static_cast<uint8_t>(~ADELL_F_TMAP);
-  return ADELL_ERR_UNSUPPORTED;
-}
-
 // Host-only: out[b] = mats[b][0] @ mats[b][1] @ ... @ mats[b][K-1] for 4x4 fp32 matrices, each
 // product evaluated as the fp32 FMA chain in k order that torch's CPU mm (MKL sgemm) produces
 // for MONAI's `affine @ create_rotate(...)` etc. — so a whole batch of MONAI AffineGrid

@@ -8,63 +8,136 @@
 //  copy of the volume on the CPU.  Here every output voxel is produced once and written
 //  straight into the collated [B,C,H,W,D] batch.
 //
-// This file holds the DIRECT path: taps are fetched with read-only global loads (L1/L2
-// served).  It is the generic path (any padding mode, any footprint, int16/uint8 sources,
-// nearest masks, identity copies).
+// One CTA = one 16x16x16 output tile of one item.  Three code paths, chosen per tile
+// (block-uniform):
+//   STAGED  the tile's source footprint (a box whose extents depend only on the item's matrix)
+//           is fetched by ONE TMA tensor copy (cp.async.bulk.tensor.3d, zero fill outside the
+//           volume = "zeros" padding for free) into shared memory; border/reflection halos are
+//           completed in shared memory; taps are then LDS with compile-time-free bank spread.
+//           Trilinear uses tile-local incremental coordinates + nested lerps (<=1e-4 contract);
+//           nearest uses the same coordinates and re-evaluates the bit-faithful MONAI/ATen
+//           chain only when a coordinate is within 1e-3 of a rounding tie => masks stay bit-exact.
+//           ADELL_F_STRICT / ADELL_F_CLIP items take the bit-faithful chain for every voxel.
+//   COPY    identity items (no resample fired): 128-bit vectorised flip/crop copy.
+//   DIRECT  generic fallback: taps fetched with read-only global loads (int16/uint8 sources,
+//           unaligned or oversized footprints, multiply-reflected coordinates, pad bands).
+#include <cuda.h>
+#include <stdlib.h>
+
 #include "k1_math.cuh"
 
 namespace {
 
 constexpr int K1_THREADS = 256;
-constexpr int K1_TI = 4;   // tile rows along axis 0
-constexpr int K1_TJ = 8;   // tile rows along axis 1
+constexpr int K1_T = 16;                       // tile edge
+constexpr int K1_MAX_BOX_BYTES = 100 * 1024;   // staged footprint limit (>= 2 CTAs per SM)
+constexpr double K1_EPS = 1e-3;                // coordinate slack of the fast path / tie window
 
-__host__ __device__ inline int k1_kw(int o2) {
-  // lanes along the contiguous axis: the largest of 32/16/8 that divides O2, else 32
-  if (o2 % 32 == 0) return 32;
-  if (o2 % 16 == 0) return 16;
-  if (o2 % 8 == 0) return 8;
-  return o2 >= 24 ? 32 : (o2 >= 12 ? 16 : 8);
+enum { MODE_DIRECT = 0, MODE_STAGED = 1, MODE_ZERO = 2, MODE_COPY = 3 };
+
+struct K1Tile {
+  int mode;
+  int o0[3];        // tile origin (output index space)
+  int box[3];       // staged box extents, axes 0,1,2
+  int mconst[3];    // box-local memory index = msign*t + mconst
+  int msign[3];
+  int lo_t[3], hi_t[3];
+  float V0[3];      // fast path: coordinate of the tile-origin voxel — box-local memory order for
+  float Dm[3][3];   // plain axes, absolute source index for axes in rmask; and its derivative
+  int rmask;        // axes whose coordinates leave [0,S): border / reflection applied per voxel
+  float rA[3], rB[3];  // box-local index = rA*u' + rB for the axes in rmask
+  int all_valid;    // every tap of the tile lies inside the valid source region
+};
+
+// ------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// The descriptor lives in global memory and was written by a host copy: the tensormap proxy
+// must acquire it before the TMA unit reads it (CUDA programming guide, "tensor map in global
+// memory").
+__device__ __forceinline__ void tmap_acquire(const void* tmap) {
+  asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
 }
 
-__host__ __device__ inline void k1_tile_counts(const int32_t* O, int& n0, int& n1, int& n2, int& kw) {
-  kw = k1_kw(O[2]);
-  n0 = (O[0] + K1_TI - 1) / K1_TI;
-  n1 = (O[1] + K1_TJ - 1) / K1_TJ;
-  n2 = (O[2] + kw - 1) / kw;
+// ------------------------------------------------------------------------- tiling policy
+__host__ __device__ inline void k1_tile_counts(const int32_t* O, int& n0, int& n1, int& n2) {
+  n0 = (O[0] + K1_T - 1) / K1_T;
+  n1 = (O[1] + K1_T - 1) / K1_T;
+  n2 = (O[2] + K1_T - 1) / K1_T;
 }
 
-template <int DT>
-__device__ __forceinline__ float k1_tap(const K1Ctx& c, int t0, int t1, int t2) {
-  int64_t idx = t0 * c.it.src_stride[0] + t1 * c.it.src_stride[1] + t2 * c.it.src_stride[2];
-  if (DT == ADELL_F32) return adell_load_src_t<ADELL_F32>(c.it.src, idx);
-  return adell_load_src(c.it.src, idx, c.it.src_dtype);
-}
+// ------------------------------------------------------------------------- tap fetchers
+struct GlobalTaps {
+  template <int DT>
+  static __device__ __forceinline__ float get(const K1Ctx& c, const K1Tile&, const float*, int t0, int t1, int t2) {
+    int64_t idx = t0 * c.it.src_stride[0] + t1 * c.it.src_stride[1] + t2 * c.it.src_stride[2];
+    if (DT == ADELL_F32) return adell_load_src_t<ADELL_F32>(c.it.src, idx);
+    return adell_load_src(c.it.src, idx, c.it.src_dtype);
+  }
+};
+struct SmemTaps {
+  template <int DT>
+  static __device__ __forceinline__ float get(const K1Ctx&, const K1Tile& t, const float* box, int t0, int t1, int t2) {
+    int m0 = t.msign[0] * t0 + t.mconst[0], m1 = t.msign[1] * t1 + t.mconst[1], m2 = t.msign[2] * t2 + t.mconst[2];
+    return box[(m0 * t.box[1] + m1) * t.box[2] + m2];
+  }
+};
 
 __device__ __forceinline__ bool k1_in(const K1Ctx& c, int t0, int t1, int t2) {
   return (t0 >= c.tlo[0]) & (t0 < c.thi[0]) & (t1 >= c.tlo[1]) & (t1 < c.thi[1]) & (t2 >= c.tlo[2]) &
          (t2 < c.thi[2]);
 }
 
-// One output voxel of a resampled item.  PERTAP: apply the pre map (and clip) to every tap and
-// accumulate in ATen order with separate mul/add (ADELL_F_STRICT or ADELL_F_CLIP); otherwise
-// accumulate sum(w*v) and sum(w_valid) with fma and apply the pre map once.
-template <int INTERP, int PAD, int DT, bool PERTAP>
-__device__ __forceinline__ float k1_resample_voxel(const K1Ctx& c, int g0, int g1, int g2) {
+__device__ __forceinline__ float k1_pad_rt(float u, int pad, float Sf, float Sm1) {
+  if (pad == ADELL_PAD_BORDER) return k1_pad_coord<ADELL_PAD_BORDER>(u, Sf, Sm1);
+  if (pad == ADELL_PAD_REFLECTION) return k1_pad_coord<ADELL_PAD_REFLECTION>(u, Sf, Sm1);
+  return u;
+}
+
+// Bit-faithful (MONAI/ATen operation order) value of one output voxel.  PERTAP: pre map (and
+// clip) on every tap, ATen-order mul/add accumulation (ADELL_F_STRICT / ADELL_F_CLIP); otherwise
+// fma accumulation of sum(w*v), sum(w_valid) and one pre map at the end.
+template <class Taps, int DT, bool PERTAP>
+__device__ __forceinline__ float k1_exact_voxel(const K1Ctx& c, const K1Tile& tl, const float* box, int g0, int g1, int g2) {
   const float c0 = static_cast<float>(g0) - c.cg[0];
   const float c1 = static_cast<float>(g1) - c.cg[1];
   const float c2 = static_cast<float>(g2) - c.cg[2];
-  float u0 = k1_pad_coord<PAD>(k1_coord_exact(c, 0, c0, c1, c2), c.Sf[0], c.Sm1[0]);
-  float u1 = k1_pad_coord<PAD>(k1_coord_exact(c, 1, c0, c1, c2), c.Sf[1], c.Sm1[1]);
-  float u2 = k1_pad_coord<PAD>(k1_coord_exact(c, 2, c0, c1, c2), c.Sf[2], c.Sm1[2]);
+  const int pad = c.it.padding;
+  float u0 = k1_pad_rt(k1_coord_exact(c, 0, c0, c1, c2), pad, c.Sf[0], c.Sm1[0]);
+  float u1 = k1_pad_rt(k1_coord_exact(c, 1, c0, c1, c2), pad, c.Sf[1], c.Sm1[1]);
+  float u2 = k1_pad_rt(k1_coord_exact(c, 2, c0, c1, c2), pad, c.Sf[2], c.Sm1[2]);
   const bool clip = (c.it.flags & ADELL_F_CLIP) != 0;
 
-  if (INTERP == ADELL_NEAREST) {
+  if (c.it.interp == ADELL_NEAREST) {
     int t0 = __float2int_rn(u0), t1 = __float2int_rn(u1), t2 = __float2int_rn(u2);
     if (!k1_in(c, t0, t1, t2)) return 0.0f;
-    return k1_premap(k1_tap<DT>(c, t0, t1, t2), c.pre_s, c.pre_o, clip, c.it.clip_lo, c.it.clip_hi);
+    return k1_premap(Taps::template get<DT>(c, tl, box, t0, t1, t2), c.pre_s, c.pre_o, clip, c.it.clip_lo, c.it.clip_hi);
   }
-
   float f0 = floorf(u0), f1 = floorf(u1), f2 = floorf(u2);
   int i0 = static_cast<int>(f0), i1 = static_cast<int>(f1), i2 = static_cast<int>(f2);
   // ATen: (ix_tnw + 1) - ix  and  ix - ix_tnw, integers converted to float
@@ -82,7 +155,7 @@ __device__ __forceinline__ float k1_resample_voxel(const K1Ctx& c, int g0, int g
         // weight = (wx * wy) * wz with x = axis 2, y = axis 1, z = axis 0 (ATen naming)
         float w = __fmul_rn(__fmul_rn(w2[b2], w1[b1]), w0[b0]);
         if (k1_in(c, t0, t1, t2)) {
-          float v = k1_tap<DT>(c, t0, t1, t2);
+          float v = Taps::template get<DT>(c, tl, box, t0, t1, t2);
           if (PERTAP) {
             v = k1_premap(v, c.pre_s, c.pre_o, clip, c.it.clip_lo, c.it.clip_hi);
             acc = __fadd_rn(acc, __fmul_rn(v, w));
@@ -102,62 +175,359 @@ template <int DT>
 __device__ __forceinline__ float k1_identity_voxel(const K1Ctx& c, int g0, int g1, int g2) {
   if (!k1_in(c, g0, g1, g2)) return 0.0f;
   const bool clip = (c.it.flags & ADELL_F_CLIP) != 0;
-  return k1_premap(k1_tap<DT>(c, g0, g1, g2), c.pre_s, c.pre_o, clip, c.it.clip_lo, c.it.clip_hi);
+  K1Tile dummy;
+  return k1_premap(GlobalTaps::get<DT>(c, dummy, nullptr, g0, g1, g2), c.pre_s, c.pre_o, clip, c.it.clip_lo, c.it.clip_hi);
 }
 
-template <int INTERP, int PAD, int DT, bool PERTAP, bool IDENT>
-__device__ __forceinline__ void k1_tile(const K1Ctx& c, int b0, int b1, int b2, int kw) {
-  const adell_item& it = c.it;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rpw = 32 / kw;                 // rows per warp step
-  const int r = lane / kw;                 // row within the step
-  const int o2 = b2 * kw + (lane - r * kw);
-  const int o0 = b0 * K1_TI + (warp >> 1);
-  const int j_base = b1 * K1_TJ + (warp & 1) * 4;
-  if (o0 >= it.out_shape[0] || o2 >= it.out_shape[2]) return;
-  const int g0 = it.grid_off[0] + it.grid_sign[0] * o0;
-  const int g2 = it.grid_off[2] + it.grid_sign[2] * o2;
-  const bool gv02 = (o0 >= it.out_vlo[0]) & (o0 < it.out_vhi[0]) & (o2 >= it.out_vlo[2]) & (o2 < it.out_vhi[2]);
-  const bool strict = (it.flags & ADELL_F_STRICT) != 0;
-  for (int s = 0; s < 4; s += rpw) {
-    const int o1 = j_base + s + r;
-    if (o1 >= it.out_shape[1]) continue;
-    const int g1 = it.grid_off[1] + it.grid_sign[1] * o1;
-    float val = 0.0f;
-    if (gv02 && o1 >= it.out_vlo[1] && o1 < it.out_vhi[1]) {
-      val = IDENT ? k1_identity_voxel<DT>(c, g0, g1, g2)
-                  : k1_resample_voxel<INTERP, PAD, DT, PERTAP>(c, g0, g1, g2);
-    }
-    // post intensity map (RandScaleIntensityd / RandShiftIntensityd) and noise
-    if (strict) {
-      if (it.post_scale != 1.0f) val = __fmul_rn(val, it.post_scale);
-      if (it.post_offset != 0.0f) val = __fadd_rn(val, it.post_offset);
-    } else {
-      val = fmaf(val, it.post_scale, it.post_offset);
-    }
+// post intensity map, noise, store
+__device__ __forceinline__ void k1_finish(const adell_item& it, float val, int o0, int o1, int o2, bool strict) {
+  if (strict) {
+    if (it.post_scale != 1.0f) val = __fmul_rn(val, it.post_scale);
+    if (it.post_offset != 0.0f) val = __fadd_rn(val, it.post_offset);
+  } else {
+    val = fmaf(val, it.post_scale, it.post_offset);
+  }
+  if (it.noise != nullptr || (it.flags & ADELL_F_PHILOX)) {
     const int64_t olin = (static_cast<int64_t>(o0) * it.out_shape[1] + o1) * it.out_shape[2] + o2;
     if (it.noise != nullptr) val = __fadd_rn(val, __ldg(it.noise + olin));
     if (it.flags & ADELL_F_PHILOX)
       val = fmaf(it.noise_std, adell_philox_normal(it.philox_seed, it.philox_offset + olin), val);
-    it.dst[o0 * it.dst_stride[0] + o1 * it.dst_stride[1] + o2 * it.dst_stride[2]] = val;
+  }
+  it.dst[o0 * it.dst_stride[0] + o1 * it.dst_stride[1] + o2 * it.dst_stride[2]] = val;
+}
+
+// Thread -> voxel mapping shared by every path: lane = (dj parity, dk), warp = pair of i planes.
+template <class F>
+__device__ __forceinline__ void k1_for_each_voxel(const K1Tile& tl, const adell_item& it, F&& body) {
+  const int dk = threadIdx.x & 15, jj = (threadIdx.x >> 4) & 1, wp = threadIdx.x >> 5;
+  const int o2 = tl.o0[2] + dk;
+  if (o2 >= it.out_shape[2]) return;
+#pragma unroll 1
+  for (int p = 0; p < 2; ++p) {
+    const int di = 2 * wp + p, o0 = tl.o0[0] + di;
+    if (o0 >= it.out_shape[0]) break;
+#pragma unroll 2
+    for (int s = 0; s < 8; ++s) {
+      const int dj = 2 * s + jj, o1 = tl.o0[1] + dj;
+      if (o1 >= it.out_shape[1]) break;
+      body(di, dj, dk, o0, o1, o2);
+    }
   }
 }
 
-template <int INTERP, int PAD>
-__device__ __forceinline__ void k1_dispatch_dt(const K1Ctx& c, int b0, int b1, int b2, int kw) {
+template <class Taps, int DT, bool PERTAP, bool IDENT>
+__device__ __forceinline__ void k1_tile_exact(const K1Ctx& c, const K1Tile& tl, const float* box) {
+  const adell_item& it = c.it;
+  const bool strict = (it.flags & ADELL_F_STRICT) != 0;
+  k1_for_each_voxel(tl, it, [&](int di, int dj, int dk, int o0, int o1, int o2) {
+    float val = 0.0f;
+    const bool ov = (o0 >= it.out_vlo[0]) & (o0 < it.out_vhi[0]) & (o1 >= it.out_vlo[1]) & (o1 < it.out_vhi[1]) &
+                    (o2 >= it.out_vlo[2]) & (o2 < it.out_vhi[2]);
+    if (ov) {
+      const int g0 = it.grid_off[0] + it.grid_sign[0] * o0;
+      const int g1 = it.grid_off[1] + it.grid_sign[1] * o1;
+      const int g2 = it.grid_off[2] + it.grid_sign[2] * o2;
+      val = IDENT ? k1_identity_voxel<DT>(c, g0, g1, g2) : k1_exact_voxel<Taps, DT, PERTAP>(c, tl, box, g0, g1, g2);
+    }
+    k1_finish(it, val, o0, o1, o2, strict);
+  });
+}
+
+template <class Taps, bool IDENT>
+__device__ __forceinline__ void k1_tile_exact_dispatch(const K1Ctx& c, const K1Tile& tl, const float* box) {
   const bool pertap = (c.it.flags & (ADELL_F_STRICT | ADELL_F_CLIP)) != 0;
   if (c.it.src_dtype == ADELL_F32) {
-    if (pertap) k1_tile<INTERP, PAD, ADELL_F32, true, false>(c, b0, b1, b2, kw);
-    else k1_tile<INTERP, PAD, ADELL_F32, false, false>(c, b0, b1, b2, kw);
+    if (pertap) k1_tile_exact<Taps, ADELL_F32, true, IDENT>(c, tl, box);
+    else k1_tile_exact<Taps, ADELL_F32, false, IDENT>(c, tl, box);
   } else {
-    if (pertap) k1_tile<INTERP, PAD, -1, true, false>(c, b0, b1, b2, kw);
-    else k1_tile<INTERP, PAD, -1, false, false>(c, b0, b1, b2, kw);
+    if (pertap) k1_tile_exact<Taps, -1, true, IDENT>(c, tl, box);
+    else k1_tile_exact<Taps, -1, false, IDENT>(c, tl, box);
   }
+}
+
+// ------------------------------------------------------------------------- staged fast paths
+// Tile-local incremental coordinates: v_a = V0_a + Dm_a0*di + Dm_a1*dj + Dm_a2*dk is the
+// box-local (memory order) source coordinate; floor/frac/lerp directly on it.  Everything the
+// inner loop needs is copied into registers first: the output stores go through a generic
+// pointer, so the compiler would otherwise reload every shared-memory field per voxel.
+struct K1Fast {
+  float V0[3], D0[3], D1[3], D2[3];
+  float p0f, p1f, gain, bias, post_o;
+  int p0, p1;
+  int n0, n1, n2;        // voxels of the tile along each axis
+  int vlo[3], vhi[3];    // valid output range, tile-local
+  float* dst;            // tile origin in the destination
+  int64_t ds0, ds1;
+  const float* noise;    // tile origin in the noise tensor (or null)
+  int64_t ns0, ns1;      // noise strides (contiguous [O0,O1,O2])
+  uint64_t olin0;        // linear output index of the tile origin (Philox counter)
+  bool philox, padded;
+  int rmask, pad;        // per-voxel border / reflection handling (axes in rmask)
+  float Sf[3], Sm1[3], rA[3], rB[3];
+};
+
+// ATen compute_coordinates on the fast coordinate (same formulas as k1_pad_coord, plain fp32).
+__device__ __forceinline__ float k1_fast_pad(float u, int pad, float Sf, float Sm1) {
+  if (pad == ADELL_PAD_REFLECTION) {
+    float x = fabsf(u + 0.5f);
+    if (x >= Sf) {
+      const float n = floorf(x / Sf);
+      x = fmaf(-n, Sf, x);
+      if (static_cast<int>(n) & 1) x = Sf - x;
+    }
+    u = x - 0.5f;
+  }
+  return fminf(Sm1, fmaxf(u, 0.0f));
+}
+
+__device__ __forceinline__ K1Fast k1_fast_load(const K1Ctx& c, const K1Tile& tl) {
+  const adell_item& it = c.it;
+  K1Fast f;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    f.V0[a] = tl.V0[a]; f.D0[a] = tl.Dm[a][0]; f.D1[a] = tl.Dm[a][1]; f.D2[a] = tl.Dm[a][2];
+    f.Sf[a] = c.Sf[a]; f.Sm1[a] = c.Sm1[a]; f.rA[a] = tl.rA[a]; f.rB[a] = tl.rB[a];
+    f.vlo[a] = it.out_vlo[a] - tl.o0[a];
+    f.vhi[a] = it.out_vhi[a] - tl.o0[a];
+  }
+  f.p1 = tl.box[2]; f.p0 = tl.box[1] * tl.box[2];
+  f.p1f = static_cast<float>(f.p1); f.p0f = static_cast<float>(f.p0);
+  f.gain = c.pre_s * it.post_scale;
+  f.bias = fmaf(c.pre_o, it.post_scale, it.post_offset);
+  f.post_o = it.post_offset;
+  f.n0 = min(K1_T, it.out_shape[0] - tl.o0[0]);
+  f.n1 = min(K1_T, it.out_shape[1] - tl.o0[1]);
+  f.n2 = min(K1_T, it.out_shape[2] - tl.o0[2]);
+  f.padded = false;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) f.padded = f.padded || f.vlo[a] > 0 || f.vhi[a] < (a == 0 ? f.n0 : a == 1 ? f.n1 : f.n2);
+  f.ds0 = it.dst_stride[0]; f.ds1 = it.dst_stride[1];
+  f.dst = it.dst + tl.o0[0] * it.dst_stride[0] + tl.o0[1] * it.dst_stride[1] + tl.o0[2] * it.dst_stride[2];
+  f.ns1 = it.out_shape[2]; f.ns0 = static_cast<int64_t>(it.out_shape[1]) * it.out_shape[2];
+  f.olin0 = (static_cast<uint64_t>(tl.o0[0]) * it.out_shape[1] + tl.o0[1]) * it.out_shape[2] + tl.o0[2];
+  f.noise = it.noise ? it.noise + f.olin0 : nullptr;
+  f.philox = (it.flags & ADELL_F_PHILOX) != 0;
+  f.rmask = tl.rmask; f.pad = it.padding;
+  return f;
+}
+
+template <bool NEAREST>
+__device__ __forceinline__ void k1_tile_staged_fast(const K1Ctx& c, const K1Tile& tl, const float* __restrict__ box) {
+  const K1Fast f = k1_fast_load(c, tl);
+  const adell_item& it = c.it;
+  const int dk = threadIdx.x & 15, jj = (threadIdx.x >> 4) & 1, wp = threadIdx.x >> 5;
+  if (dk >= f.n2) return;
+  const int64_t ds2 = it.dst_stride[2];
+  const float fk = static_cast<float>(dk);
+  const bool extra = f.noise != nullptr || f.philox;
+  const float tie = 0.5f - static_cast<float>(K1_EPS);
+#pragma unroll 1
+  for (int p = 0; p < 2; ++p) {
+    const int di = 2 * wp + p;
+    if (di >= f.n0) break;
+    const float fi = static_cast<float>(di);
+    const float P0 = fmaf(f.D0[0], fi, fmaf(f.D2[0], fk, f.V0[0]));
+    const float P1 = fmaf(f.D0[1], fi, fmaf(f.D2[1], fk, f.V0[1]));
+    const float P2 = fmaf(f.D0[2], fi, fmaf(f.D2[2], fk, f.V0[2]));
+    float* drow = f.dst + di * f.ds0 + dk * ds2;
+#pragma unroll 4
+    for (int s = 0; s < 8; ++s) {
+      const int dj = 2 * s + jj;
+      if (dj >= f.n1) break;
+      const float fj = static_cast<float>(dj);
+      float v0 = fmaf(f.D1[0], fj, P0), v1 = fmaf(f.D1[1], fj, P1), v2 = fmaf(f.D1[2], fj, P2);
+      if (f.rmask) {  // block-uniform: some axis leaves [0,S) inside this tile
+        if (f.rmask & 1) v0 = fmaf(f.rA[0], k1_fast_pad(v0, f.pad, f.Sf[0], f.Sm1[0]), f.rB[0]);
+        if (f.rmask & 2) v1 = fmaf(f.rA[1], k1_fast_pad(v1, f.pad, f.Sf[1], f.Sm1[1]), f.rB[1]);
+        if (f.rmask & 4) v2 = fmaf(f.rA[2], k1_fast_pad(v2, f.pad, f.Sf[2], f.Sm1[2]), f.rB[2]);
+      }
+      float val;
+      if (NEAREST) {
+        const float n0 = rintf(v0), n1 = rintf(v1), n2 = rintf(v2);
+        if (fabsf(v0 - n0) > tie || fabsf(v1 - n1) > tie || fabsf(v2 - n2) > tie) {
+          // within 1e-3 of a rounding tie: replay the bit-faithful chain for this voxel
+          const int g0 = it.grid_off[0] + it.grid_sign[0] * (tl.o0[0] + di);
+          const int g1 = it.grid_off[1] + it.grid_sign[1] * (tl.o0[1] + dj);
+          const int g2 = it.grid_off[2] + it.grid_sign[2] * (tl.o0[2] + dk);
+          val = fmaf(k1_exact_voxel<SmemTaps, ADELL_F32, false>(c, tl, box, g0, g1, g2), it.post_scale, f.post_o);
+        } else {
+          val = fmaf(box[__float2int_rn(fmaf(n0, f.p0f, fmaf(n1, f.p1f, n2)))], f.gain, f.bias);
+        }
+      } else {
+        const float f0 = floorf(v0), f1 = floorf(v1), f2 = floorf(v2);
+        const float r0 = v0 - f0, r1 = v1 - f1, r2 = v2 - f2;
+        const float* q = box + __float2int_rn(fmaf(f0, f.p0f, fmaf(f1, f.p1f, f2)));
+        const float a000 = q[0], a001 = q[1], a010 = q[f.p1], a011 = q[f.p1 + 1];
+        const float a100 = q[f.p0], a101 = q[f.p0 + 1], a110 = q[f.p0 + f.p1], a111 = q[f.p0 + f.p1 + 1];
+        const float x00 = fmaf(r2, a001 - a000, a000), x01 = fmaf(r2, a011 - a010, a010);
+        const float x10 = fmaf(r2, a101 - a100, a100), x11 = fmaf(r2, a111 - a110, a110);
+        const float y0 = fmaf(r1, x01 - x00, x00), y1 = fmaf(r1, x11 - x10, x10);
+        val = fmaf(fmaf(r0, y1 - y0, y0), f.gain, f.bias);
+      }
+      if (f.padded) {
+        const bool ov = (di >= f.vlo[0]) & (di < f.vhi[0]) & (dj >= f.vlo[1]) & (dj < f.vhi[1]) & (dk >= f.vlo[2]) & (dk < f.vhi[2]);
+        if (!ov) val = f.post_o;
+      }
+      if (extra) {
+        const int64_t rel = di * f.ns0 + dj * f.ns1 + dk;
+        if (f.noise != nullptr) val = __fadd_rn(val, __ldg(f.noise + rel));
+        if (f.philox) val = fmaf(it.noise_std, adell_philox_normal(it.philox_seed, it.philox_offset + f.olin0 + rel), val);
+      }
+      drow[dj * f.ds1] = val;
+    }
+  }
+}
+
+// 128-bit vectorised identity copy (flip / crop only, everything valid and aligned).
+__device__ __forceinline__ void k1_tile_copy_vec(const K1Ctx& c, const K1Tile& tl) {
+  const adell_item& it = c.it;
+  const float* __restrict__ src = reinterpret_cast<const float*>(it.src);
+  const bool rev = it.grid_sign[2] * it.src_stride[2] < 0;
+  const bool clip = (it.flags & ADELL_F_CLIP) != 0;
+  const float gain = c.pre_s * it.post_scale;
+  const float bias = fmaf(c.pre_o, it.post_scale, it.post_offset);
+  for (int v = threadIdx.x; v < K1_T * K1_T * (K1_T / 4); v += K1_THREADS) {
+    const int k4 = v & 3, dj = (v >> 2) & 15, di = v >> 6;
+    const int o0 = tl.o0[0] + di, o1 = tl.o0[1] + dj, o2 = tl.o0[2] + 4 * k4;
+    if (o0 >= it.out_shape[0] || o1 >= it.out_shape[1] || o2 >= it.out_shape[2]) continue;
+    const int g0 = it.grid_off[0] + it.grid_sign[0] * o0;
+    const int g1 = it.grid_off[1] + it.grid_sign[1] * o1;
+    const int g2 = it.grid_off[2] + it.grid_sign[2] * (rev ? o2 + 3 : o2);  // lowest address of the quad
+    const int64_t sidx = g0 * it.src_stride[0] + g1 * it.src_stride[1] + g2 * it.src_stride[2];
+    float4 q = __ldg(reinterpret_cast<const float4*>(src + sidx));
+    if (rev) { float t = q.x; q.x = q.w; q.w = t; t = q.y; q.y = q.z; q.z = t; }
+    if (clip) {
+      q.x = k1_premap(q.x, c.pre_s, c.pre_o, true, it.clip_lo, it.clip_hi);
+      q.y = k1_premap(q.y, c.pre_s, c.pre_o, true, it.clip_lo, it.clip_hi);
+      q.z = k1_premap(q.z, c.pre_s, c.pre_o, true, it.clip_lo, it.clip_hi);
+      q.w = k1_premap(q.w, c.pre_s, c.pre_o, true, it.clip_lo, it.clip_hi);
+      q.x = fmaf(q.x, it.post_scale, it.post_offset); q.y = fmaf(q.y, it.post_scale, it.post_offset);
+      q.z = fmaf(q.z, it.post_scale, it.post_offset); q.w = fmaf(q.w, it.post_scale, it.post_offset);
+    } else if (gain != 1.0f || bias != 0.0f) {
+      q.x = fmaf(q.x, gain, bias); q.y = fmaf(q.y, gain, bias); q.z = fmaf(q.z, gain, bias); q.w = fmaf(q.w, gain, bias);
+    }
+    *reinterpret_cast<float4*>(it.dst + o0 * it.dst_stride[0] + o1 * it.dst_stride[1] + o2) = q;
+  }
+}
+
+// ------------------------------------------------------------------------- per-tile set-up
+__device__ void k1_tile_setup(const K1Ctx& c, K1Tile& tl, int b0, int b1, int b2) {
+  const adell_item& it = c.it;
+  tl.o0[0] = b0 * K1_T; tl.o0[1] = b1 * K1_T; tl.o0[2] = b2 * K1_T;
+  tl.mode = MODE_DIRECT;
+  tl.rmask = 0;
+  tl.all_valid = 0;
+  if (it.flags & ADELL_F_IDENTITY) {
+    // vector copy needs: fp32, unit step along axis 2, 16-byte aligned rows, nothing invalid, no noise
+    bool ok = it.src_dtype == ADELL_F32 && (it.src_stride[2] == 1 || it.src_stride[2] == -1) && it.dst_stride[2] == 1 &&
+              it.noise == nullptr && !(it.flags & (ADELL_F_PHILOX | ADELL_F_STRICT)) && (it.out_shape[2] & 3) == 0;
+    const bool rev = it.grid_sign[2] * it.src_stride[2] < 0;
+    for (int a = 0; a < 3 && ok; ++a) {
+      ok = ok && it.out_vlo[a] <= 0 && it.out_vhi[a] >= it.out_shape[a];
+      const int ga = it.grid_off[a], gb = it.grid_off[a] + it.grid_sign[a] * (it.out_shape[a] - 1);
+      ok = ok && min(ga, gb) >= c.tlo[a] && max(ga, gb) < c.thi[a];
+    }
+    if (ok) {
+      const int g2 = it.grid_off[2] + it.grid_sign[2] * (rev ? 3 : 0);
+      const int64_t e0 = g2 * it.src_stride[2];
+      ok = ((reinterpret_cast<uintptr_t>(it.src) & 3u) == 0) &&
+           (((reinterpret_cast<uintptr_t>(it.src) >> 2) + static_cast<uint64_t>(e0)) & 3u) == 0 &&
+           (it.src_stride[0] & 3) == 0 && (it.src_stride[1] & 3) == 0 && (reinterpret_cast<uintptr_t>(it.dst) & 15u) == 0 &&
+           (it.dst_stride[0] & 3) == 0 && (it.dst_stride[1] & 3) == 0;
+      // rows start at g0*s0 + g1*s1: multiples of 4 elements given the stride checks
+    }
+    if (ok) tl.mode = MODE_COPY;
+    return;
+  }
+  if (!(it.flags & ADELL_F_TMAP)) return;
+  // affine map of the tile in double: u_a(d) = U0_a + sum_b D_ab d_b   (t-space, before padding)
+  double U0[3], D[3][3];
+  double cc[3];
+  for (int b = 0; b < 3; ++b) cc[b] = static_cast<double>(it.grid_off[b] + it.grid_sign[b] * tl.o0[b]) - static_cast<double>(c.cg[b]);
+  bool finite = true;
+  for (int a = 0; a < 3; ++a) {
+    const double K = static_cast<double>(it.nrm[a]) * it.src_shape[a] * 0.5;
+    const float* A = it.A + 4 * a;
+    U0[a] = (A[0] * cc[0] + A[1] * cc[1] + A[2] * cc[2] + A[3]) * K + (it.src_shape[a] - 1) * 0.5;
+    for (int b = 0; b < 3; ++b) D[a][b] = static_cast<double>(A[b]) * K * it.grid_sign[b];
+    double umin = U0[a], umax = U0[a];
+    for (int b = 0; b < 3; ++b) {
+      const double span = D[a][b] * (min(K1_T, it.out_shape[b] - tl.o0[b]) - 1);
+      if (span < 0) umin += span; else umax += span;
+    }
+    finite = finite && (umin > -1.0e6) && (umax < 1.0e6);
+    if (!finite) break;
+    tl.lo_t[a] = static_cast<int>(floor(umin - K1_EPS));
+    tl.hi_t[a] = static_cast<int>(floor(umax + K1_EPS)) + 1;
+  }
+  if (!finite) return;
+  bool all_valid = true, any_valid = true;
+  int blo[3], bhi[3];  // source index interval the box must hold
+  tl.rmask = 0;
+  for (int a = 0; a < 3; ++a) {
+    const int S = it.src_shape[a], lo = tl.lo_t[a], hi = tl.hi_t[a];
+    blo[a] = lo; bhi[a] = hi;
+    if (it.padding == ADELL_PAD_ZEROS) {
+      if (hi < c.tlo[a] || lo >= c.thi[a]) any_valid = false;
+    } else if (lo < 0 || hi > S - 1) {
+      // coordinates leave [0,S): the voxel loop clamps / reflects them (ATen semantics), so the box
+      // only has to hold the covering interval of the clamped / reflected indices (+1 for the hi tap)
+      tl.rmask |= 1 << a;
+      int rlo, rhi;
+      if (it.padding == ADELL_PAD_BORDER) {
+        rlo = min(max(lo, 0), S - 1); rhi = min(max(hi, 0), S - 1);
+      } else if (lo >= -S && hi < 0) {            // inside the first mirrored period below
+        rlo = -1 - hi; rhi = -1 - lo;
+      } else if (lo >= S && hi <= 2 * S - 1) {    // inside the first mirrored period above
+        rlo = 2 * S - 1 - hi; rhi = 2 * S - 1 - lo;
+      } else if (lo < 0 && lo >= -S && hi <= S - 1) {   // straddles the lower edge
+        rlo = 0; rhi = max(-1 - lo, hi);
+      } else if (lo >= 0 && hi >= S && hi <= 2 * S - 1) {  // straddles the upper edge
+        rlo = min(2 * S - 1 - hi, lo); rhi = S - 1;
+      } else {
+        rlo = 0; rhi = S - 1;
+      }
+      blo[a] = rlo; bhi[a] = rhi + 1;  // the hi tap of u' == S-1 reads cell S: TMA zero fill, weight 0
+    }
+    if (bhi[a] - blo[a] + 1 + (a == 2 ? 3 : 0) > it.tmap_box[a]) return;  // larger than the encoded box: direct path
+    all_valid = all_valid && lo >= c.tlo[a] && hi < c.thi[a];
+  }
+  if (!any_valid) { tl.mode = MODE_ZERO; return; }
+  // a pre offset must not leak into zero-filled (invalid) taps: such tiles use the exact path
+  tl.all_valid = (all_valid && tl.rmask == 0) ? 1 : 0;
+  if (tl.rmask != 0) {
+    tl.all_valid = 1;
+    for (int a = 0; a < 3; ++a) tl.all_valid = tl.all_valid && c.tlo[a] <= 0 && c.thi[a] >= it.src_shape[a];
+  }
+  for (int a = 0; a < 3; ++a) {
+    tl.box[a] = it.tmap_box[a];
+    tl.msign[a] = it.tmap_sign[a];
+    int mo = tl.msign[a] > 0 ? blo[a] + it.tmap_off[a] : -bhi[a] + it.tmap_off[a];
+    // TMA needs a 16-byte aligned start along the contiguous axis: round the box origin down to a
+    // multiple of 4 elements (the encoded inner extent carries 3 spare elements for this)
+    if (a == 2) mo = (mo >> 2) << 2;
+    tl.mconst[a] = it.tmap_off[a] - mo;
+    if (tl.rmask & (1 << a)) {
+      tl.V0[a] = static_cast<float>(U0[a]);
+      for (int b = 0; b < 3; ++b) tl.Dm[a][b] = static_cast<float>(D[a][b]);
+      tl.rA[a] = static_cast<float>(tl.msign[a]);
+      tl.rB[a] = static_cast<float>(tl.mconst[a]);
+    } else {
+      tl.V0[a] = static_cast<float>(tl.msign[a] * U0[a] + tl.mconst[a]);
+      for (int b = 0; b < 3; ++b) tl.Dm[a][b] = static_cast<float>(tl.msign[a] * D[a][b]);
+      tl.rA[a] = 1.0f; tl.rB[a] = 0.0f;
+    }
+  }
+  tl.mode = MODE_STAGED;
 }
 
 __global__ void __launch_bounds__(K1_THREADS)
-k1_gather_direct(const adell_item* __restrict__ items, const int32_t* __restrict__ tile_start, int n_items) {
+k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile_start, int n_items) {
+  extern __shared__ __align__(128) float box[];
   __shared__ K1Ctx ctx;
+  __shared__ K1Tile tl;
+  __shared__ __align__(8) uint64_t mbar;
+
   // block -> (item, tile): binary search in the exclusive prefix of tile counts
   const int tile = blockIdx.x;
   int lo = 0, hi = n_items;  // invariant: tile_start[lo] <= tile < tile_start[hi]
@@ -166,36 +536,52 @@ k1_gather_direct(const adell_item* __restrict__ items, const int32_t* __restrict
     if (__ldg(tile_start + mid) <= tile) lo = mid; else hi = mid;
   }
   {
-    const uint32_t* s = reinterpret_cast<const uint32_t*>(items + lo);
-    uint32_t* d = reinterpret_cast<uint32_t*>(&ctx.it);
-    if (threadIdx.x < sizeof(adell_item) / 4) d[threadIdx.x] = __ldg(s + threadIdx.x);
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(items + lo) + 32;  // skip the 128-byte tensor map
+    uint32_t* d = reinterpret_cast<uint32_t*>(&ctx.it) + 32;
+    if (threadIdx.x < (sizeof(adell_item) - 128) / 4) d[threadIdx.x] = __ldg(s + threadIdx.x);
   }
   __syncthreads();
-  if (threadIdx.x == 0) k1_ctx_finish(ctx);
+  if (threadIdx.x == 0) {
+    k1_ctx_finish(ctx);
+    int n0, n1, n2;
+    k1_tile_counts(ctx.it.out_shape, n0, n1, n2);
+    int local = tile - __ldg(tile_start + lo);
+    const int b2 = local % n2; local /= n2;
+    const int b1 = local % n1;
+    const int b0 = local / n1;
+    k1_tile_setup(ctx, tl, b0, b1, b2);
+    if (tl.mode == MODE_STAGED) {
+      mbar_init(&mbar, 1);
+      const int mo0 = ctx.it.tmap_off[0] - tl.mconst[0], mo1 = ctx.it.tmap_off[1] - tl.mconst[1],
+                mo2 = ctx.it.tmap_off[2] - tl.mconst[2];
+      tmap_acquire(items[lo].tmap);
+      mbar_expect_tx(&mbar, static_cast<uint32_t>(tl.box[0] * tl.box[1] * tl.box[2] * 4));
+      tma_load_3d(box, items[lo].tmap, &mbar, mo2, mo1, mo0);
+    }
+  }
   __syncthreads();
-
-  int n0, n1, n2, kw;
-  k1_tile_counts(ctx.it.out_shape, n0, n1, n2, kw);
-  int local = tile - __ldg(tile_start + lo);
-  const int b2 = local % n2; local /= n2;
-  const int b1 = local % n1;
-  const int b0 = local / n1;
-
   const adell_item& it = ctx.it;
-  if (it.flags & ADELL_F_IDENTITY) {
-    if (it.src_dtype == ADELL_F32) k1_tile<0, 0, ADELL_F32, true, true>(ctx, b0, b1, b2, kw);
-    else k1_tile<0, 0, -1, true, true>(ctx, b0, b1, b2, kw);
+  const int mode = tl.mode;
+
+  if (mode == MODE_COPY) {
+    k1_tile_copy_vec(ctx, tl);
     return;
   }
-  if (it.interp == ADELL_NEAREST) {
-    if (it.padding == ADELL_PAD_ZEROS) k1_dispatch_dt<ADELL_NEAREST, ADELL_PAD_ZEROS>(ctx, b0, b1, b2, kw);
-    else if (it.padding == ADELL_PAD_BORDER) k1_dispatch_dt<ADELL_NEAREST, ADELL_PAD_BORDER>(ctx, b0, b1, b2, kw);
-    else k1_dispatch_dt<ADELL_NEAREST, ADELL_PAD_REFLECTION>(ctx, b0, b1, b2, kw);
-  } else {
-    if (it.padding == ADELL_PAD_ZEROS) k1_dispatch_dt<ADELL_TRILINEAR, ADELL_PAD_ZEROS>(ctx, b0, b1, b2, kw);
-    else if (it.padding == ADELL_PAD_BORDER) k1_dispatch_dt<ADELL_TRILINEAR, ADELL_PAD_BORDER>(ctx, b0, b1, b2, kw);
-    else k1_dispatch_dt<ADELL_TRILINEAR, ADELL_PAD_REFLECTION>(ctx, b0, b1, b2, kw);
+  if (mode == MODE_ZERO) {
+    const bool strict = (it.flags & ADELL_F_STRICT) != 0;
+    k1_for_each_voxel(tl, it, [&](int, int, int, int o0, int o1, int o2) { k1_finish(it, 0.0f, o0, o1, o2, strict); });
+    return;
   }
+  if (mode == MODE_STAGED) {
+    mbar_wait(&mbar, 0);
+    const bool exact = (it.flags & (ADELL_F_STRICT | ADELL_F_CLIP)) != 0 || (ctx.pre_o != 0.0f && !tl.all_valid);
+    if (exact) k1_tile_exact_dispatch<SmemTaps, false>(ctx, tl, box);
+    else if (it.interp == ADELL_NEAREST) k1_tile_staged_fast<true>(ctx, tl, box);
+    else k1_tile_staged_fast<false>(ctx, tl, box);
+    return;
+  }
+  if (it.flags & ADELL_F_IDENTITY) k1_tile_exact_dispatch<GlobalTaps, true>(ctx, tl, nullptr);
+  else k1_tile_exact_dispatch<GlobalTaps, false>(ctx, tl, nullptr);
 }
 
 int k1_validate(const adell_item& it) {
@@ -209,35 +595,129 @@ int k1_validate(const adell_item& it) {
   return ADELL_OK;
 }
 
+// ---- host: tensor-map encoding -------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn k1_get_encode() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess) { (void)cudaGetLastError(); return nullptr; }
+  return reinterpret_cast<EncodeTiledFn>(fn);
+}
+
+// Decides staged-path eligibility for one item and, when eligible, encodes its tensor map over
+// the valid source box in memory order.  Returns the box bytes (0 = not staged).
+int k1_encode_item(adell_item& it, EncodeTiledFn enc) {
+  it.flags &= static_cast<uint8_t>(~ADELL_F_TMAP);
+  if (it.flags & ADELL_F_IDENTITY) return 0;
+  if (it.src_dtype != ADELL_F32) return 0;
+  if (it.src_stride[2] != 1 && it.src_stride[2] != -1) return 0;
+  int box[3];
+  int64_t cells = 1;
+  for (int a = 0; a < 3; ++a) {
+    const double K = static_cast<double>(it.nrm[a]) * it.src_shape[a] * 0.5;
+    double span = 0.0;
+    for (int b = 0; b < 3; ++b) {
+      const int tb = it.out_shape[b] < K1_T ? it.out_shape[b] : K1_T;
+      span += fabs(static_cast<double>(it.A[4 * a + b]) * K) * (tb - 1);
+    }
+    if (!(span < 4096.0)) return 0;
+    box[a] = static_cast<int>(floor(span + 2 * K1_EPS)) + 3;
+    if (it.padding != ADELL_PAD_ZEROS) {
+      // border / reflection fold the footprint back into [0,S): one spare cell for the hi tap, and a
+      // thin axis is simply staged whole so that multiply-reflected tiles stay on this path
+      box[a] += 1;
+      if (it.src_shape[a] <= 64 && box[a] < it.src_shape[a] + 1) box[a] = it.src_shape[a] + 1;
+    }
+    if (a == 2) box[a] = (box[a] + 3 + 3) & ~3;  // inner extent: 16-byte multiple + slack to align the origin
+    if (box[a] > 256) return 0;
+    cells *= box[a];
+  }
+  if (cells * 4 > K1_MAX_BOX_BYTES) return 0;
+  // valid source box in t-space and its origin in memory order
+  cuuint64_t gdim[3], gstride[2];
+  int64_t base_off = 0;
+  int64_t astride[3];
+  for (int a = 0; a < 3; ++a) {
+    const int tlo = it.src_vlo[a] > 0 ? it.src_vlo[a] : 0;
+    const int thi = it.src_vhi[a] < it.src_shape[a] ? it.src_vhi[a] : it.src_shape[a];
+    if (thi <= tlo) return 0;
+    const int sign = it.src_stride[a] >= 0 ? 1 : -1;
+    astride[a] = it.src_stride[a] * sign;
+    if (astride[a] == 0) return 0;
+    it.tmap_sign[a] = sign;
+    it.tmap_off[a] = sign > 0 ? -tlo : thi - 1;           // m = sign*t + off, m = 0 at the lowest address
+    base_off += static_cast<int64_t>(sign > 0 ? tlo : thi - 1) * it.src_stride[a];
+    gdim[2 - a] = static_cast<cuuint64_t>(thi - tlo);     // tensor-map dims are innermost first
+    it.tmap_box[a] = box[a];
+  }
+  const uintptr_t base = reinterpret_cast<uintptr_t>(it.src) + static_cast<uintptr_t>(base_off * 4);
+  gstride[0] = static_cast<cuuint64_t>(astride[1]) * 4;
+  gstride[1] = static_cast<cuuint64_t>(astride[0]) * 4;
+  if ((base & 15u) || (gstride[0] & 15u) || (gstride[1] & 15u)) return 0;
+  if (gstride[0] < gdim[0] * 4 || gstride[1] < gstride[0]) return 0;  // rows must not overlap
+  const cuuint32_t bdim[3] = {static_cast<cuuint32_t>(box[2]), static_cast<cuuint32_t>(box[1]), static_cast<cuuint32_t>(box[0])};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  if (enc == nullptr) return -1;
+  CUresult r = enc(reinterpret_cast<CUtensorMap*>(it.tmap), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                   reinterpret_cast<void*>(base), gdim, gstride, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return 0;
+  it.tmap_base = reinterpret_cast<const void*>(base);
+  it.flags |= ADELL_F_TMAP;
+  return static_cast<int>(cells * 4);
+}
+
 }  // namespace
 
-extern "C" int adell_aug_plan_tiles(const adell_item* items_host, int n_items, int32_t* tile_start_host,
-                                    int64_t* total_tiles) {
-  if (items_host == nullptr || tile_start_host == nullptr || n_items < 0) return ADELL_ERR_BAD_ARG;
+extern "C" int adell_aug_prepare(adell_item* items_host, int n_items, int32_t* tile_start_host, adell_launch_info* info) {
+  if (items_host == nullptr || tile_start_host == nullptr || info == nullptr || n_items < 0) return ADELL_ERR_BAD_ARG;
   int64_t acc = 0;
+  int smem = 0, staged = 0;
+  EncodeTiledFn enc = nullptr;
+  bool enc_tried = false;
+  const char* dis = getenv("ADELL_DISABLE_STAGED");  // debugging aid: force the direct path
+  const bool no_staged = dis != nullptr && dis[0] == '1';
   for (int i = 0; i < n_items; ++i) {
     int st = k1_validate(items_host[i]);
     if (st != ADELL_OK) return st;
-    int n0, n1, n2, kw;
-    k1_tile_counts(items_host[i].out_shape, n0, n1, n2, kw);
+    if (!enc_tried && !no_staged) { enc = k1_get_encode(); enc_tried = true; }
+    int bytes = 0;
+    if (no_staged) items_host[i].flags &= static_cast<uint8_t>(~ADELL_F_TMAP);
+    else bytes = k1_encode_item(items_host[i], enc);
+    if (bytes < 0) return ADELL_ERR_NO_DRIVER;
+    if (bytes > 0) { ++staged; if (bytes > smem) smem = bytes; }
+    int n0, n1, n2;
+    k1_tile_counts(items_host[i].out_shape, n0, n1, n2);
     tile_start_host[i] = static_cast<int32_t>(acc);
     acc += static_cast<int64_t>(n0) * n1 * n2;
     if (acc > 0x7fffffffLL) return ADELL_ERR_BAD_ARG;
   }
   tile_start_host[n_items] = static_cast<int32_t>(acc);
-  if (total_tiles) *total_tiles = acc;
+  info->total_tiles = acc;
+  info->smem_bytes = smem;
+  info->n_staged = staged;
   return ADELL_OK;
 }
 
 extern "C" int adell_aug_gather(const adell_item* items_dev, const int32_t* tile_start_dev, int n_items,
-                                int64_t total_tiles, void* stream) {
-  if (n_items == 0 || total_tiles == 0) return ADELL_OK;
-  if (items_dev == nullptr || tile_start_dev == nullptr || n_items < 0 || total_tiles < 0 ||
-      total_tiles > 0x7fffffffLL)
+                                const adell_launch_info* info, void* stream) {
+  if (n_items == 0) return ADELL_OK;
+  if (info == nullptr) return ADELL_ERR_BAD_ARG;
+  if (info->total_tiles == 0) return ADELL_OK;
+  if (items_dev == nullptr || tile_start_dev == nullptr || n_items < 0 || info->total_tiles < 0 ||
+      info->total_tiles > 0x7fffffffLL || info->smem_bytes < 0 || info->smem_bytes > K1_MAX_BOX_BYTES)
     return ADELL_ERR_BAD_ARG;
   if ((reinterpret_cast<uintptr_t>(items_dev) & 63u) != 0) return ADELL_ERR_ALIGN;
-  k1_gather_direct<<<static_cast<unsigned>(total_tiles), K1_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-      items_dev, tile_start_dev, n_items);
+  if (info->smem_bytes > 40 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k1_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_MAX_BOX_BYTES);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return adell_map_cuda_error(e); }
+  }
+  k1_gather<<<static_cast<unsigned>(info->total_tiles), K1_THREADS, static_cast<size_t>(info->smem_bytes),
+              static_cast<cudaStream_t>(stream)>>>(items_dev, tile_start_dev, n_items);
   ADELL_CUDA_CHECK_LAUNCH();
   return ADELL_OK;
 }

@@ -31,29 +31,28 @@ def _require_cuda(device: torch.device):
 
 
 def pack_launch(items: np.ndarray):
-    """Host-side packing of one launch: ``(pinned-able uint8 buffer, n_items, total_tiles)``.
-    Layout: items (512 B each) followed by the int32 tile prefix (n_items + 1)."""
+    """Host-side preparation of one launch: encodes the TMA descriptors of the eligible items
+    (``adell_aug_prepare``) and packs ``items (512 B each) + int32 tile prefix (n+1)`` into one
+    buffer.  Returns ``(uint8 buffer, n_items, LaunchInfo)``."""
     lib = _lib.load()
     n = items.shape[0]
     buf = np.empty(n * 512 + 4 * (n + 1), np.uint8)
-    buf[: n * 512] = items.view(np.uint8).reshape(-1)
-    tiles = np.empty(n + 1, np.int32)
-    total = C.c_int64(0)
-    _lib.check(
-        lib.adell_aug_plan_tiles(items.ctypes.data, n, tiles.ctypes.data, C.byref(total)), "adell_aug_plan_tiles"
-    )
-    buf[n * 512 :] = tiles.view(np.uint8)
-    return buf, n, int(total.value)
+    it = buf[: n * 512].view(ITEM_DTYPE)
+    it[:] = items
+    tiles = buf[n * 512 :].view(np.int32)
+    info = _lib.LaunchInfo()
+    _lib.check(lib.adell_aug_prepare(it.ctypes.data, n, tiles.ctypes.data, C.byref(info)), "adell_aug_prepare")
+    return buf, n, info
 
 
-def launch_packed(buf_dev: torch.Tensor, n: int, total: int, stream: int | None = None):
+def launch_packed(buf_dev: torch.Tensor, n: int, info, stream: int | None = None):
     """Enqueue one K1 launch from a device-resident packed buffer (see :func:`pack_launch`)."""
     global launch_count
     lib = _lib.load()
     if stream is None:
         stream = torch.cuda.current_stream(buf_dev.device).cuda_stream
     base = buf_dev.data_ptr()
-    _lib.check(lib.adell_aug_gather(base, base + n * 512, n, total, C.c_void_p(stream)), "adell_aug_gather")
+    _lib.check(lib.adell_aug_gather(base, base + n * 512, n, C.byref(info), C.c_void_p(stream)), "adell_aug_gather")
     launch_count += lib.adell_aug_gather_launches()
 
 
@@ -86,8 +85,8 @@ def execute_ptrs(plan: BatchPlan, dst_ptr: np.ndarray, dst_stride: np.ndarray, k
             dst_ptr, dst_stride, lambda n: torch.empty(max(n, 1), dtype=torch.float32, device=plan.device)
         )
         for items in launches:
-            buf, n, total = pack_launch(items)
+            buf, n, info = pack_launch(items)
             host = torch.from_numpy(buf).pin_memory()
             dev = host.to(plan.device, non_blocking=True)
-            launch_packed(dev, n, total)
+            launch_packed(dev, n, info)
             plan.keep.append(dev)

@@ -302,14 +302,14 @@ def main():
         dst_ptr = np.concatenate([ptr, mptr], 1).reshape(-1).astype(np.uint64)
         dst_stride = np.tile(np.asarray(out["image"].stride()[2:], np.int64), (batch * nk, 1))
         items = plan.build_launches(dst_ptr, dst_stride, lambda n: torch.empty(max(n, 1), device=dev))[-1]
-        buf, n, total = pack_launch(items)
-        prepared.append((torch.from_numpy(buf).to(dev), n, total, plan))
+        buf, n, info = pack_launch(items)
+        prepared.append((torch.from_numpy(buf).to(dev), n, info, plan))
     torch.cuda.synchronize()
     kev = []
     for rep in range(3):
-        for (buf, n, total, _) in prepared:
+        for (buf, n, info, _) in prepared:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream); launch_packed(buf, n, total); b.record(stream)
+            a.record(stream); launch_packed(buf, n, info); b.record(stream)
             kev.append((a, b))
     torch.cuda.synchronize()
     kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in kev[len(prepared):])

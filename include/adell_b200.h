@@ -137,17 +137,25 @@ int adell_device_sm_count(int* out); /* number of SMs of the current device     
 int adell_mat4_chain(const float* mats, int batch, int k, float* out);
 
 /* -- K1: fused gather ----------------------------------------------------------------- */
-/* Host-only: fills tile_start_host[0..n_items] with the exclusive prefix of per-item tile
- * counts for the tiling policy compiled into the library (so the caller can upload it next
- * to the items); returns total tiles in *total_tiles. */
-int adell_aug_plan_tiles(const adell_item* items_host, int n_items, int32_t* tile_start_host,
-                         int64_t* total_tiles);
-/* Host-only: encodes items_host[i].tmap for the staged (TMA) path when eligible, setting or
- * clearing ADELL_F_TMAP.  Needs libcuda (driver entry point); ADELL_ERR_NO_DRIVER otherwise. */
-int adell_item_encode_tensormap(adell_item* item_host);
-/* Enqueue the fused gather over all items: one launch per call. */
+/* What the host learned while preparing one launch. */
+typedef struct adell_launch_info {
+  int64_t total_tiles; /* grid size (one CTA per 16x16x16 output tile)                         */
+  int32_t smem_bytes;  /* dynamic shared memory = largest staged source box among the items     */
+  int32_t n_staged;    /* items eligible for the TMA-staged path                                */
+} adell_launch_info;
+
+/* Host-only, no GPU work: validates the items, decides per item whether its source footprint
+ * can be staged through shared memory by TMA (fp32 source, unit inner stride, 16-byte aligned
+ * rows, footprint box <= 100 KiB) and if so encodes the CUtensorMap into items_host[i].tmap
+ * (+ tmap_off/tmap_sign/tmap_box, ADELL_F_TMAP) via the driver entry point
+ * cuTensorMapEncodeTiled (ADELL_ERR_NO_DRIVER if libcuda is unavailable), and fills
+ * tile_start_host[0..n_items] with the exclusive prefix of per-item tile counts.  The caller
+ * then uploads items + prefix and calls adell_aug_gather. */
+int adell_aug_prepare(adell_item* items_host, int n_items, int32_t* tile_start_host,
+                      adell_launch_info* info);
+/* Enqueue the fused gather over all items: ONE kernel launch per call. */
 int adell_aug_gather(const adell_item* items_dev, const int32_t* tile_start_dev, int n_items,
-                     int64_t total_tiles, void* stream);
+                     const adell_launch_info* info, void* stream);
 /* Number of kernel launches the last-compiled policy issues per adell_aug_gather call. */
 int adell_aug_gather_launches(void);
 
