@@ -28,8 +28,12 @@
 
 namespace {
 
-constexpr int K1_THREADS = 256;
+constexpr int K1_CWARPS = 16;                  // consumer warps per CTA
+constexpr int K1_CTHREADS = 32 * K1_CWARPS;    // consumer threads: one 16x16x16 tile = 8 voxels each
+constexpr int K1_THREADS = K1_CTHREADS + 32;   // + one producer warp (item fetch, tile set-up, TMA issue)
 constexpr int K1_T = 16;                       // tile edge
+constexpr int K1_MAX_STAGES = 4;
+constexpr int K1_SMEM_BUDGET = 224 * 1024;     // dynamic shared memory per persistent CTA (1 CTA per SM)
 constexpr int K1_MAX_BOX_BYTES = 100 * 1024;   // staged footprint limit (>= 2 CTAs per SM)
 constexpr double K1_EPS = 1e-3;                // coordinate slack of the fast path / tie window
 
@@ -59,6 +63,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
@@ -196,22 +203,17 @@ __device__ __forceinline__ void k1_finish(const adell_item& it, float val, int o
   it.dst[o0 * it.dst_stride[0] + o1 * it.dst_stride[1] + o2 * it.dst_stride[2]] = val;
 }
 
-// Thread -> voxel mapping shared by every path: lane = (dj parity, dk), warp = pair of i planes.
+// Thread -> voxel mapping shared by every path: lane = (dj parity, dk), consumer warp = i plane.
 template <class F>
 __device__ __forceinline__ void k1_for_each_voxel(const K1Tile& tl, const adell_item& it, F&& body) {
-  const int dk = threadIdx.x & 15, jj = (threadIdx.x >> 4) & 1, wp = threadIdx.x >> 5;
-  const int o2 = tl.o0[2] + dk;
-  if (o2 >= it.out_shape[2]) return;
-#pragma unroll 1
-  for (int p = 0; p < 2; ++p) {
-    const int di = 2 * wp + p, o0 = tl.o0[0] + di;
-    if (o0 >= it.out_shape[0]) break;
+  const int dk = threadIdx.x & 15, jj = (threadIdx.x >> 4) & 1, di = threadIdx.x >> 5;
+  const int o2 = tl.o0[2] + dk, o0 = tl.o0[0] + di;
+  if (o2 >= it.out_shape[2] || o0 >= it.out_shape[0]) return;
 #pragma unroll 2
-    for (int s = 0; s < 8; ++s) {
-      const int dj = 2 * s + jj, o1 = tl.o0[1] + dj;
-      if (o1 >= it.out_shape[1]) break;
-      body(di, dj, dk, o0, o1, o2);
-    }
+  for (int s = 0; s < 8; ++s) {
+    const int dj = 2 * s + jj, o1 = tl.o0[1] + dj;
+    if (o1 >= it.out_shape[1]) break;
+    body(di, dj, dk, o0, o1, o2);
   }
 }
 
@@ -315,16 +317,13 @@ template <bool NEAREST>
 __device__ __forceinline__ void k1_tile_staged_fast(const K1Ctx& c, const K1Tile& tl, const float* __restrict__ box) {
   const K1Fast f = k1_fast_load(c, tl);
   const adell_item& it = c.it;
-  const int dk = threadIdx.x & 15, jj = (threadIdx.x >> 4) & 1, wp = threadIdx.x >> 5;
-  if (dk >= f.n2) return;
+  const int dk = threadIdx.x & 15, jj = (threadIdx.x >> 4) & 1, di = threadIdx.x >> 5;
+  if (dk >= f.n2 || di >= f.n0) return;
   const int64_t ds2 = it.dst_stride[2];
   const float fk = static_cast<float>(dk);
   const bool extra = f.noise != nullptr || f.philox;
   const float tie = 0.5f - static_cast<float>(K1_EPS);
-#pragma unroll 1
-  for (int p = 0; p < 2; ++p) {
-    const int di = 2 * wp + p;
-    if (di >= f.n0) break;
+  {
     const float fi = static_cast<float>(di);
     const float P0 = fmaf(f.D0[0], fi, fmaf(f.D2[0], fk, f.V0[0]));
     const float P1 = fmaf(f.D0[1], fi, fmaf(f.D2[1], fk, f.V0[1]));
@@ -386,7 +385,7 @@ __device__ __forceinline__ void k1_tile_copy_vec(const K1Ctx& c, const K1Tile& t
   const bool clip = (it.flags & ADELL_F_CLIP) != 0;
   const float gain = c.pre_s * it.post_scale;
   const float bias = fmaf(c.pre_o, it.post_scale, it.post_offset);
-  for (int v = threadIdx.x; v < K1_T * K1_T * (K1_T / 4); v += K1_THREADS) {
+  for (int v = threadIdx.x; v < K1_T * K1_T * (K1_T / 4); v += K1_CTHREADS) {
     const int k4 = v & 3, dj = (v >> 2) & 15, di = v >> 6;
     const int o0 = tl.o0[0] + di, o1 = tl.o0[1] + dj, o2 = tl.o0[2] + 4 * k4;
     if (o0 >= it.out_shape[0] || o1 >= it.out_shape[1] || o2 >= it.out_shape[2]) continue;
@@ -521,67 +520,102 @@ __device__ void k1_tile_setup(const K1Ctx& c, K1Tile& tl, int b0, int b1, int b2
   tl.mode = MODE_STAGED;
 }
 
-__global__ void __launch_bounds__(K1_THREADS)
-k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile_start, int n_items) {
-  extern __shared__ __align__(128) float box[];
-  __shared__ K1Ctx ctx;
-  __shared__ K1Tile tl;
-  __shared__ __align__(8) uint64_t mbar;
+struct K1Stage {
+  K1Ctx ctx;
+  K1Tile tl;
+};
 
-  // block -> (item, tile): binary search in the exclusive prefix of tile counts
-  const int tile = blockIdx.x;
-  int lo = 0, hi = n_items;  // invariant: tile_start[lo] <= tile < tile_start[hi]
-  while (hi - lo > 1) {
-    int mid = (lo + hi) >> 1;
-    if (__ldg(tile_start + mid) <= tile) lo = mid; else hi = mid;
-  }
-  {
-    const uint32_t* s = reinterpret_cast<const uint32_t*>(items + lo) + 32;  // skip the 128-byte tensor map
-    uint32_t* d = reinterpret_cast<uint32_t*>(&ctx.it) + 32;
-    if (threadIdx.x < (sizeof(adell_item) - 128) / 4) d[threadIdx.x] = __ldg(s + threadIdx.x);
-  }
-  __syncthreads();
+// Persistent, warp-specialised: one CTA per SM walks tiles blockIdx.x, +gridDim.x, ...  The
+// producer warp fetches the tile's item, runs the tile set-up and issues the TMA box load into
+// the next free stage of a shared-memory ring (full/empty mbarrier pair per stage); the 16
+// consumer warps compute the tile of the oldest full stage.  Box loads, descriptor fetches
+// and the set-up arithmetic therefore overlap the interpolation of earlier tiles.
+__global__ void __launch_bounds__(K1_THREADS, 1)
+k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile_start, int n_items, int total_tiles,
+          int n_stages, int stage_bytes) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  K1Stage* stages = reinterpret_cast<K1Stage*>(smem + static_cast<size_t>(n_stages) * stage_bytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(stages + n_stages);
+  uint64_t* empty = full + n_stages;
   if (threadIdx.x == 0) {
-    k1_ctx_finish(ctx);
-    int n0, n1, n2;
-    k1_tile_counts(ctx.it.out_shape, n0, n1, n2);
-    int local = tile - __ldg(tile_start + lo);
-    const int b2 = local % n2; local /= n2;
-    const int b1 = local % n1;
-    const int b0 = local / n1;
-    k1_tile_setup(ctx, tl, b0, b1, b2);
-    if (tl.mode == MODE_STAGED) {
-      mbar_init(&mbar, 1);
-      const int mo0 = ctx.it.tmap_off[0] - tl.mconst[0], mo1 = ctx.it.tmap_off[1] - tl.mconst[1],
-                mo2 = ctx.it.tmap_off[2] - tl.mconst[2];
-      tmap_acquire(items[lo].tmap);
-      mbar_expect_tx(&mbar, static_cast<uint32_t>(tl.box[0] * tl.box[1] * tl.box[2] * 4));
-      tma_load_3d(box, items[lo].tmap, &mbar, mo2, mo1, mo0);
+    for (int s = 0; s < n_stages; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(full + s)), "r"(1));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(empty + s)), "r"(K1_CWARPS));
     }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const adell_item& it = ctx.it;
-  const int mode = tl.mode;
+  const int lane = threadIdx.x & 31;
 
-  if (mode == MODE_COPY) {
-    k1_tile_copy_vec(ctx, tl);
+  if (threadIdx.x >= K1_CTHREADS) {
+    // ------------------------------------------------------------------ producer warp
+    int item = 0;
+    int next_start = __ldg(tile_start + 1);
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      const int s = iter % n_stages;
+      mbar_wait(empty + s, ((iter / n_stages) & 1) ^ 1);
+      while (tile >= next_start) { ++item; next_start = __ldg(tile_start + item + 1); }
+      K1Stage& st = stages[s];
+      {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(items + item) + 32;  // skip the tensor map
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&st.ctx.it) + 32;
+        uint32_t w0 = __ldg(src + lane), w1 = __ldg(src + lane + 32), w2 = __ldg(src + lane + 64);
+        dst[lane] = w0; dst[lane + 32] = w1; dst[lane + 64] = w2;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        k1_ctx_finish(st.ctx);
+        int n0, n1, n2;
+        k1_tile_counts(st.ctx.it.out_shape, n0, n1, n2);
+        int local = tile - __ldg(tile_start + item);
+        const int b2 = local % n2; local /= n2;
+        const int b1 = local % n1;
+        const int b0 = local / n1;
+        k1_tile_setup(st.ctx, st.tl, b0, b1, b2);
+        if (st.tl.mode == MODE_STAGED) {
+          const int mo0 = st.ctx.it.tmap_off[0] - st.tl.mconst[0], mo1 = st.ctx.it.tmap_off[1] - st.tl.mconst[1],
+                    mo2 = st.ctx.it.tmap_off[2] - st.tl.mconst[2];
+          tmap_acquire(items[item].tmap);
+          mbar_expect_tx(full + s, static_cast<uint32_t>(st.tl.box[0] * st.tl.box[1] * st.tl.box[2] * 4));
+          tma_load_3d(smem + static_cast<size_t>(s) * stage_bytes, items[item].tmap, full + s, mo2, mo1, mo0);
+        } else {
+          mbar_arrive(full + s);
+        }
+      }
+      __syncwarp();
+    }
     return;
   }
-  if (mode == MODE_ZERO) {
-    const bool strict = (it.flags & ADELL_F_STRICT) != 0;
-    k1_for_each_voxel(tl, it, [&](int, int, int, int o0, int o1, int o2) { k1_finish(it, 0.0f, o0, o1, o2, strict); });
-    return;
+
+  // -------------------------------------------------------------------- consumer warps
+  int iter = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+    const int s = iter % n_stages;
+    mbar_wait(full + s, (iter / n_stages) & 1);
+    const K1Ctx& ctx = stages[s].ctx;
+    const K1Tile& tl = stages[s].tl;
+    const float* box = reinterpret_cast<const float*>(smem + static_cast<size_t>(s) * stage_bytes);
+    const adell_item& it = ctx.it;
+    const int mode = tl.mode;
+    if (mode == MODE_COPY) {
+      k1_tile_copy_vec(ctx, tl);
+    } else if (mode == MODE_ZERO) {
+      const bool strict = (it.flags & ADELL_F_STRICT) != 0;
+      k1_for_each_voxel(tl, it, [&](int, int, int, int o0, int o1, int o2) { k1_finish(it, 0.0f, o0, o1, o2, strict); });
+    } else if (mode == MODE_STAGED) {
+      const bool exact = (it.flags & (ADELL_F_STRICT | ADELL_F_CLIP)) != 0 || (ctx.pre_o != 0.0f && !tl.all_valid);
+      if (exact) k1_tile_exact_dispatch<SmemTaps, false>(ctx, tl, box);
+      else if (it.interp == ADELL_NEAREST) k1_tile_staged_fast<true>(ctx, tl, box);
+      else k1_tile_staged_fast<false>(ctx, tl, box);
+    } else if (it.flags & ADELL_F_IDENTITY) {
+      k1_tile_exact_dispatch<GlobalTaps, true>(ctx, tl, nullptr);
+    } else {
+      k1_tile_exact_dispatch<GlobalTaps, false>(ctx, tl, nullptr);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + s);
   }
-  if (mode == MODE_STAGED) {
-    mbar_wait(&mbar, 0);
-    const bool exact = (it.flags & (ADELL_F_STRICT | ADELL_F_CLIP)) != 0 || (ctx.pre_o != 0.0f && !tl.all_valid);
-    if (exact) k1_tile_exact_dispatch<SmemTaps, false>(ctx, tl, box);
-    else if (it.interp == ADELL_NEAREST) k1_tile_staged_fast<true>(ctx, tl, box);
-    else k1_tile_staged_fast<false>(ctx, tl, box);
-    return;
-  }
-  if (it.flags & ADELL_F_IDENTITY) k1_tile_exact_dispatch<GlobalTaps, true>(ctx, tl, nullptr);
-  else k1_tile_exact_dispatch<GlobalTaps, false>(ctx, tl, nullptr);
 }
 
 int k1_validate(const adell_item& it) {
@@ -712,12 +746,22 @@ extern "C" int adell_aug_gather(const adell_item* items_dev, const int32_t* tile
       info->total_tiles > 0x7fffffffLL || info->smem_bytes < 0 || info->smem_bytes > K1_MAX_BOX_BYTES)
     return ADELL_ERR_BAD_ARG;
   if ((reinterpret_cast<uintptr_t>(items_dev) & 63u) != 0) return ADELL_ERR_ALIGN;
-  if (info->smem_bytes > 40 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(k1_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_MAX_BOX_BYTES);
-    if (e != cudaSuccess) { (void)cudaGetLastError(); return adell_map_cuda_error(e); }
-  }
-  k1_gather<<<static_cast<unsigned>(info->total_tiles), K1_THREADS, static_cast<size_t>(info->smem_bytes),
-              static_cast<cudaStream_t>(stream)>>>(items_dev, tile_start_dev, n_items);
+  int dev = 0, sms = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return adell_map_cuda_error(e); }
+  // ring of staged boxes: as many stages as fit next to the per-stage tile state
+  const int stage_bytes = (info->smem_bytes + 127) & ~127;
+  const int per_stage = stage_bytes + static_cast<int>(sizeof(K1Stage)) + 16;
+  int n_stages = K1_SMEM_BUDGET / per_stage;
+  if (n_stages > K1_MAX_STAGES) n_stages = K1_MAX_STAGES;
+  if (n_stages < 1) return ADELL_ERR_BAD_ARG;
+  const int smem = n_stages * per_stage;
+  e = cudaFuncSetAttribute(k1_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BUDGET);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return adell_map_cuda_error(e); }
+  const int64_t grid = info->total_tiles < sms ? info->total_tiles : sms;
+  k1_gather<<<static_cast<unsigned>(grid), K1_THREADS, static_cast<size_t>(smem), static_cast<cudaStream_t>(stream)>>>(
+      items_dev, tile_start_dev, n_items, static_cast<int>(info->total_tiles), n_stages, stage_bytes);
   ADELL_CUDA_CHECK_LAUNCH();
   return ADELL_OK;
 }
