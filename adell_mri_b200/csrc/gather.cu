@@ -41,6 +41,7 @@ enum { MODE_DIRECT = 0, MODE_STAGED = 1, MODE_ZERO = 2, MODE_COPY = 3 };
 
 struct K1Tile {
   int mode;
+  int item;         // index of the tile's item (descriptor address for the TMA issue)
   int o0[3];        // tile origin (output index space)
   int box[3];       // staged box extents, axes 0,1,2
   int mconst[3];    // box-local memory index = msign*t + mconst
@@ -235,8 +236,10 @@ __device__ __forceinline__ void k1_tile_exact(const K1Ctx& c, const K1Tile& tl, 
   });
 }
 
+// Out of line on purpose: the exact / direct variants are cold next to the staged fast loops, and
+// inlining all of them made the kernel ~400 KB of SASS (instruction-cache misses dominated).
 template <class Taps, bool IDENT>
-__device__ __forceinline__ void k1_tile_exact_dispatch(const K1Ctx& c, const K1Tile& tl, const float* box) {
+__device__ __noinline__ void k1_tile_exact_dispatch(const K1Ctx& c, const K1Tile& tl, const float* box) {
   const bool pertap = (c.it.flags & (ADELL_F_STRICT | ADELL_F_CLIP)) != 0;
   if (c.it.src_dtype == ADELL_F32) {
     if (pertap) k1_tile_exact<Taps, ADELL_F32, true, IDENT>(c, tl, box);
@@ -252,39 +255,59 @@ __device__ __forceinline__ void k1_tile_exact_dispatch(const K1Ctx& c, const K1T
 // box-local (memory order) source coordinate; floor/frac/lerp directly on it.  Everything the
 // inner loop needs is copied into registers first: the output stores go through a generic
 // pointer, so the compiler would otherwise reload every shared-memory field per voxel.
-struct K1Fast {
+struct __align__(16) K1Fast {
   float V0[3], D0[3], D1[3], D2[3];
-  float p0f, p1f, gain, bias, post_o;
+  float Sf[3], Sm1[3], rA[3], rB[3];
+  float p0f, p1f, gain, bias, post_o, noise_std;
   int p0, p1;
   int n0, n1, n2;        // voxels of the tile along each axis
   int vlo[3], vhi[3];    // valid output range, tile-local
+  int rmask, pad;        // per-voxel border / reflection handling (axes in rmask)
+  int philox, padded;
   float* dst;            // tile origin in the destination
-  int64_t ds0, ds1;
   const float* noise;    // tile origin in the noise tensor (or null)
+  int64_t ds0, ds1, ds2;
   int64_t ns0, ns1;      // noise strides (contiguous [O0,O1,O2])
   uint64_t olin0;        // linear output index of the tile origin (Philox counter)
-  bool philox, padded;
-  int rmask, pad;        // per-voxel border / reflection handling (axes in rmask)
-  float Sf[3], Sm1[3], rA[3], rB[3];
+  uint64_t philox_seed, philox_offset;
 };
 
 // ATen compute_coordinates on the fast coordinate (same formulas as k1_pad_coord, plain fp32).
+__device__ __noinline__ float k1_fast_reflect_far(float x, float Sf) {
+  const float n = floorf(x / Sf);
+  x = fmaf(-n, Sf, x);
+  if (static_cast<int>(n) & 1) x = Sf - x;
+  return x;
+}
 __device__ __forceinline__ float k1_fast_pad(float u, int pad, float Sf, float Sm1) {
   if (pad == ADELL_PAD_REFLECTION) {
     float x = fabsf(u + 0.5f);
-    if (x >= Sf) {
-      const float n = floorf(x / Sf);
-      x = fmaf(-n, Sf, x);
-      if (static_cast<int>(n) & 1) x = Sf - x;
-    }
+    if (x >= Sf) x = k1_fast_reflect_far(x, Sf);
     u = x - 0.5f;
   }
   return fminf(Sm1, fmaxf(u, 0.0f));
 }
 
-__device__ __forceinline__ K1Fast k1_fast_load(const K1Ctx& c, const K1Tile& tl) {
+// bit-faithful replay for one nearest voxel (tie window of the fast path); cold
+__device__ __noinline__ float k1_exact_nearest_smem(const K1Ctx& c, const K1Tile& tl, const float* box, int di, int dj, int dk) {
   const adell_item& it = c.it;
-  K1Fast f;
+  const int g0 = it.grid_off[0] + it.grid_sign[0] * (tl.o0[0] + di);
+  const int g1 = it.grid_off[1] + it.grid_sign[1] * (tl.o0[1] + dj);
+  const int g2 = it.grid_off[2] + it.grid_sign[2] * (tl.o0[2] + dk);
+  return fmaf(k1_exact_voxel<SmemTaps, ADELL_F32, false>(c, tl, box, g0, g1, g2), it.post_scale, it.post_offset);
+}
+
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
+// Filled by the producer lane once per staged tile; the consumers copy it into registers with
+// 128-bit shared loads (the output stores go through a generic pointer, so anything left in
+// shared memory would be reloaded per voxel).
+__device__ __forceinline__ void k1_fast_fill(const K1Ctx& c, const K1Tile& tl, K1Fast& f) {
+  const adell_item& it = c.it;
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     f.V0[a] = tl.V0[a]; f.D0[a] = tl.Dm[a][0]; f.D1[a] = tl.Dm[a][1]; f.D2[a] = tl.Dm[a][2];
@@ -297,83 +320,148 @@ __device__ __forceinline__ K1Fast k1_fast_load(const K1Ctx& c, const K1Tile& tl)
   f.gain = c.pre_s * it.post_scale;
   f.bias = fmaf(c.pre_o, it.post_scale, it.post_offset);
   f.post_o = it.post_offset;
+  f.noise_std = it.noise_std;
   f.n0 = min(K1_T, it.out_shape[0] - tl.o0[0]);
   f.n1 = min(K1_T, it.out_shape[1] - tl.o0[1]);
   f.n2 = min(K1_T, it.out_shape[2] - tl.o0[2]);
-  f.padded = false;
+  bool padded = false;
 #pragma unroll
-  for (int a = 0; a < 3; ++a) f.padded = f.padded || f.vlo[a] > 0 || f.vhi[a] < (a == 0 ? f.n0 : a == 1 ? f.n1 : f.n2);
-  f.ds0 = it.dst_stride[0]; f.ds1 = it.dst_stride[1];
+  for (int a = 0; a < 3; ++a) padded = padded || f.vlo[a] > 0 || f.vhi[a] < (a == 0 ? f.n0 : a == 1 ? f.n1 : f.n2);
+  f.padded = padded ? 1 : 0;
+  f.ds0 = it.dst_stride[0]; f.ds1 = it.dst_stride[1]; f.ds2 = it.dst_stride[2];
   f.dst = it.dst + tl.o0[0] * it.dst_stride[0] + tl.o0[1] * it.dst_stride[1] + tl.o0[2] * it.dst_stride[2];
   f.ns1 = it.out_shape[2]; f.ns0 = static_cast<int64_t>(it.out_shape[1]) * it.out_shape[2];
   f.olin0 = (static_cast<uint64_t>(tl.o0[0]) * it.out_shape[1] + tl.o0[1]) * it.out_shape[2] + tl.o0[2];
   f.noise = it.noise ? it.noise + f.olin0 : nullptr;
-  f.philox = (it.flags & ADELL_F_PHILOX) != 0;
+  f.philox = (it.flags & ADELL_F_PHILOX) ? 1 : 0;
+  f.philox_seed = it.philox_seed; f.philox_offset = it.philox_offset;
   f.rmask = tl.rmask; f.pad = it.padding;
-  return f;
 }
 
-template <bool NEAREST>
-__device__ __forceinline__ void k1_tile_staged_fast(const K1Ctx& c, const K1Tile& tl, const float* __restrict__ box) {
-  const K1Fast f = k1_fast_load(c, tl);
-  const adell_item& it = c.it;
+// Hot register image of a staged tile (everything else stays in the shared-memory K1Fast and is
+// only touched on the rare padded / noise paths).
+struct K1Hot {
+  float D1[3], P[3];
+  float Sf[3], Sm1[3], rA[3], rB[3];
+  float p0f, p1f, gain, bias;
+  int rmask, pad, n1;
+  int64_t ds1;
+  float* drow;
+  bool cold;  // padded output region or noise: take the slow store
+};
+
+__device__ __forceinline__ K1Hot k1_hot_load(const K1Fast& f, int di, int dk) {
+  K1Hot h;
+  const float fk = static_cast<float>(dk), fi = static_cast<float>(di);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    h.D1[a] = f.D1[a];
+    h.P[a] = fmaf(f.D0[a], fi, fmaf(f.D2[a], fk, f.V0[a]));
+    h.Sf[a] = f.Sf[a]; h.Sm1[a] = f.Sm1[a]; h.rA[a] = f.rA[a]; h.rB[a] = f.rB[a];
+  }
+  h.p0f = f.p0f; h.p1f = f.p1f; h.gain = f.gain; h.bias = f.bias;
+  h.rmask = f.rmask; h.pad = f.pad; h.n1 = f.n1;
+  h.ds1 = f.ds1;
+  h.drow = f.dst + di * f.ds0 + dk * f.ds2;
+  h.cold = f.padded || f.noise != nullptr || f.philox;
+  return h;
+}
+
+__device__ __forceinline__ void k1_fast_coords(const K1Hot& h, int dj, float& v0, float& v1, float& v2) {
+  const float fj = static_cast<float>(dj);
+  v0 = fmaf(h.D1[0], fj, h.P[0]); v1 = fmaf(h.D1[1], fj, h.P[1]); v2 = fmaf(h.D1[2], fj, h.P[2]);
+  if (h.rmask) {  // block-uniform: some axis leaves [0,S) inside this tile
+    if (h.rmask & 1) v0 = fmaf(h.rA[0], k1_fast_pad(v0, h.pad, h.Sf[0], h.Sm1[0]), h.rB[0]);
+    if (h.rmask & 2) v1 = fmaf(h.rA[1], k1_fast_pad(v1, h.pad, h.Sf[1], h.Sm1[1]), h.rB[1]);
+    if (h.rmask & 4) v2 = fmaf(h.rA[2], k1_fast_pad(v2, h.pad, h.Sf[2], h.Sm1[2]), h.rB[2]);
+  }
+}
+
+// rare: output pad band (SpatialPadd after the resample), injected or Philox noise
+__device__ __noinline__ void k1_cold_store(const K1Fast& f, float* p, int di, int dj, int dk, float val) {
+  if (f.padded) {
+    const bool ov = (di >= f.vlo[0]) & (di < f.vhi[0]) & (dj >= f.vlo[1]) & (dj < f.vhi[1]) & (dk >= f.vlo[2]) & (dk < f.vhi[2]);
+    if (!ov) val = f.post_o;
+  }
+  const int64_t rel = di * f.ns0 + dj * f.ns1 + dk;
+  if (f.noise != nullptr) val = __fadd_rn(val, __ldg(f.noise + rel));
+  if (f.philox) val = fmaf(f.noise_std, adell_philox_normal(f.philox_seed, f.philox_offset + f.olin0 + rel), val);
+  *p = val;
+}
+
+__device__ __forceinline__ void k1_fast_store(const K1Fast& f, const K1Hot& h, int di, int dj, int dk, float val) {
+  float* p = h.drow + dj * h.ds1;
+  if (h.cold) k1_cold_store(f, p, di, dj, dk, val);
+  else *p = val;
+}
+
+__device__ __forceinline__ void k1_tile_staged_nearest(const K1Ctx& c, const K1Tile& tl, const K1Fast& f, const float* __restrict__ box) {
   const int dk = threadIdx.x & 15, jj = (threadIdx.x >> 4) & 1, di = threadIdx.x >> 5;
   if (dk >= f.n2 || di >= f.n0) return;
-  const int64_t ds2 = it.dst_stride[2];
-  const float fk = static_cast<float>(dk);
-  const bool extra = f.noise != nullptr || f.philox;
+  const K1Hot h = k1_hot_load(f, di, dk);
   const float tie = 0.5f - static_cast<float>(K1_EPS);
-  {
-    const float fi = static_cast<float>(di);
-    const float P0 = fmaf(f.D0[0], fi, fmaf(f.D2[0], fk, f.V0[0]));
-    const float P1 = fmaf(f.D0[1], fi, fmaf(f.D2[1], fk, f.V0[1]));
-    const float P2 = fmaf(f.D0[2], fi, fmaf(f.D2[2], fk, f.V0[2]));
-    float* drow = f.dst + di * f.ds0 + dk * ds2;
-#pragma unroll 4
-    for (int s = 0; s < 8; ++s) {
-      const int dj = 2 * s + jj;
-      if (dj >= f.n1) break;
-      const float fj = static_cast<float>(dj);
-      float v0 = fmaf(f.D1[0], fj, P0), v1 = fmaf(f.D1[1], fj, P1), v2 = fmaf(f.D1[2], fj, P2);
-      if (f.rmask) {  // block-uniform: some axis leaves [0,S) inside this tile
-        if (f.rmask & 1) v0 = fmaf(f.rA[0], k1_fast_pad(v0, f.pad, f.Sf[0], f.Sm1[0]), f.rB[0]);
-        if (f.rmask & 2) v1 = fmaf(f.rA[1], k1_fast_pad(v1, f.pad, f.Sf[1], f.Sm1[1]), f.rB[1]);
-        if (f.rmask & 4) v2 = fmaf(f.rA[2], k1_fast_pad(v2, f.pad, f.Sf[2], f.Sm1[2]), f.rB[2]);
-      }
-      float val;
-      if (NEAREST) {
-        const float n0 = rintf(v0), n1 = rintf(v1), n2 = rintf(v2);
-        if (fabsf(v0 - n0) > tie || fabsf(v1 - n1) > tie || fabsf(v2 - n2) > tie) {
-          // within 1e-3 of a rounding tie: replay the bit-faithful chain for this voxel
-          const int g0 = it.grid_off[0] + it.grid_sign[0] * (tl.o0[0] + di);
-          const int g1 = it.grid_off[1] + it.grid_sign[1] * (tl.o0[1] + dj);
-          const int g2 = it.grid_off[2] + it.grid_sign[2] * (tl.o0[2] + dk);
-          val = fmaf(k1_exact_voxel<SmemTaps, ADELL_F32, false>(c, tl, box, g0, g1, g2), it.post_scale, f.post_o);
-        } else {
-          val = fmaf(box[__float2int_rn(fmaf(n0, f.p0f, fmaf(n1, f.p1f, n2)))], f.gain, f.bias);
-        }
-      } else {
-        const float f0 = floorf(v0), f1 = floorf(v1), f2 = floorf(v2);
-        const float r0 = v0 - f0, r1 = v1 - f1, r2 = v2 - f2;
-        const float* q = box + __float2int_rn(fmaf(f0, f.p0f, fmaf(f1, f.p1f, f2)));
-        const float a000 = q[0], a001 = q[1], a010 = q[f.p1], a011 = q[f.p1 + 1];
-        const float a100 = q[f.p0], a101 = q[f.p0 + 1], a110 = q[f.p0 + f.p1], a111 = q[f.p0 + f.p1 + 1];
-        const float x00 = fmaf(r2, a001 - a000, a000), x01 = fmaf(r2, a011 - a010, a010);
-        const float x10 = fmaf(r2, a101 - a100, a100), x11 = fmaf(r2, a111 - a110, a110);
-        const float y0 = fmaf(r1, x01 - x00, x00), y1 = fmaf(r1, x11 - x10, x10);
-        val = fmaf(fmaf(r0, y1 - y0, y0), f.gain, f.bias);
-      }
-      if (f.padded) {
-        const bool ov = (di >= f.vlo[0]) & (di < f.vhi[0]) & (dj >= f.vlo[1]) & (dj < f.vhi[1]) & (dk >= f.vlo[2]) & (dk < f.vhi[2]);
-        if (!ov) val = f.post_o;
-      }
-      if (extra) {
-        const int64_t rel = di * f.ns0 + dj * f.ns1 + dk;
-        if (f.noise != nullptr) val = __fadd_rn(val, __ldg(f.noise + rel));
-        if (f.philox) val = fmaf(it.noise_std, adell_philox_normal(it.philox_seed, it.philox_offset + f.olin0 + rel), val);
-      }
-      drow[dj * f.ds1] = val;
-    }
+#pragma unroll 2
+  for (int s = 0; s < 8; ++s) {
+    const int dj = 2 * s + jj;
+    if (dj >= h.n1) break;
+    float v0, v1, v2;
+    k1_fast_coords(h, dj, v0, v1, v2);
+    const float n0 = rintf(v0), n1 = rintf(v1), n2 = rintf(v2);
+    float val;
+    if (fabsf(v0 - n0) > tie || fabsf(v1 - n1) > tie || fabsf(v2 - n2) > tie)
+      val = k1_exact_nearest_smem(c, tl, box, di, dj, dk);  // within 1e-3 of a rounding tie
+    else
+      val = fmaf(box[__float2int_rn(fmaf(n0, h.p0f, fmaf(n1, h.p1f, n2)))], h.gain, h.bias);
+    k1_fast_store(f, h, di, dj, dk, val);
+  }
+}
+
+struct K1Vox {
+  float r0, r1, r2;
+  uint32_t a;  // shared-memory byte address of tap (0,0,0)
+};
+
+__device__ __forceinline__ K1Vox k1_fast_vox(const K1Hot& h, int dj, uint32_t box_addr) {
+  float v0, v1, v2;
+  k1_fast_coords(h, dj, v0, v1, v2);
+  const float f0 = floorf(v0), f1 = floorf(v1), f2 = floorf(v2);
+  K1Vox x;
+  x.r0 = v0 - f0; x.r1 = v1 - f1; x.r2 = v2 - f2;
+  x.a = box_addr + 4u * static_cast<uint32_t>(__float2int_rn(fmaf(f0, h.p0f, fmaf(f1, h.p1f, f2))));
+  return x;
+}
+
+__device__ __forceinline__ float k1_lerp8(const K1Vox& x, const float* t) {
+  const float x00 = fmaf(x.r2, t[1] - t[0], t[0]), x01 = fmaf(x.r2, t[3] - t[2], t[2]);
+  const float x10 = fmaf(x.r2, t[5] - t[4], t[4]), x11 = fmaf(x.r2, t[7] - t[6], t[6]);
+  const float y0 = fmaf(x.r1, x01 - x00, x00), y1 = fmaf(x.r1, x11 - x10, x10);
+  return fmaf(x.r0, y1 - y0, y0);
+}
+
+// Two voxels per iteration, all sixteen shared-memory taps issued before any arithmetic that
+// depends on them (the loads are volatile asm so ptxas keeps them batched).
+__device__ __forceinline__ void k1_tile_staged_trilinear(const K1Ctx&, const K1Tile&, const K1Fast& f, const float* __restrict__ box) {
+  const int dk = threadIdx.x & 15, jj = (threadIdx.x >> 4) & 1, di = threadIdx.x >> 5;
+  if (dk >= f.n2 || di >= f.n0) return;
+  const K1Hot h = k1_hot_load(f, di, dk);
+  const uint32_t box_addr = smem_u32(box);
+  const uint32_t o1 = 4u * f.p1, o0 = 4u * f.p0;
+#pragma unroll 1
+  for (int s = 0; s < 8; s += 2) {
+    const int dja = 2 * s + jj, djb = dja + 2;
+    if (dja >= h.n1) break;
+    const bool hasb = djb < h.n1;
+    const K1Vox xa = k1_fast_vox(h, dja, box_addr);
+    const K1Vox xb = k1_fast_vox(h, hasb ? djb : dja, box_addr);
+    float ta[8], tb[8];
+    ta[0] = lds_f32(xa.a); ta[1] = lds_f32(xa.a + 4); ta[2] = lds_f32(xa.a + o1); ta[3] = lds_f32(xa.a + o1 + 4);
+    tb[0] = lds_f32(xb.a); tb[1] = lds_f32(xb.a + 4); tb[2] = lds_f32(xb.a + o1); tb[3] = lds_f32(xb.a + o1 + 4);
+    ta[4] = lds_f32(xa.a + o0); ta[5] = lds_f32(xa.a + o0 + 4); ta[6] = lds_f32(xa.a + o0 + o1); ta[7] = lds_f32(xa.a + o0 + o1 + 4);
+    tb[4] = lds_f32(xb.a + o0); tb[5] = lds_f32(xb.a + o0 + 4); tb[6] = lds_f32(xb.a + o0 + o1); tb[7] = lds_f32(xb.a + o0 + o1 + 4);
+    const float va = fmaf(k1_lerp8(xa, ta), h.gain, h.bias);
+    const float vb = fmaf(k1_lerp8(xb, tb), h.gain, h.bias);
+    k1_fast_store(f, h, di, dja, dk, va);
+    if (hasb) k1_fast_store(f, h, di, djb, dk, vb);
   }
 }
 
@@ -520,22 +608,59 @@ __device__ void k1_tile_setup(const K1Ctx& c, K1Tile& tl, int b0, int b1, int b2
   tl.mode = MODE_STAGED;
 }
 
-struct K1Stage {
+#ifdef K1_PROFILE
+__device__ unsigned long long k1_prof[8];
+#define K1_PROF_T0 long long _t0 = clock64();
+#define K1_PROF_ADD(i) { long long _t1 = clock64(); if ((threadIdx.x & 31) == 0) atomicAdd(&k1_prof[i], (unsigned long long)(_t1 - _t0)); _t0 = _t1; }
+#else
+#define K1_PROF_T0
+#define K1_PROF_ADD(i)
+#endif
+
+struct K1Slot {
   K1Ctx ctx;
   K1Tile tl;
+  K1Fast fast;
 };
 
+// Producer: fetch the tile's item, derive the tile state (and the consumers' register image).
+__device__ __forceinline__ void k1_prepare(const adell_item* __restrict__ items, const int32_t* __restrict__ tile_start,
+                                           int tile, int& item, int& next_start, K1Slot& sl, int lane) {
+  while (tile >= next_start) { ++item; next_start = __ldg(tile_start + item + 1); }
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(items + item) + 32;  // skip the tensor map
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sl.ctx.it) + 32;
+    uint32_t w0 = __ldg(src + lane), w1 = __ldg(src + lane + 32), w2 = __ldg(src + lane + 64);
+    dst[lane] = w0; dst[lane + 32] = w1; dst[lane + 64] = w2;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    k1_ctx_finish(sl.ctx);
+    int n0, n1, n2;
+    k1_tile_counts(sl.ctx.it.out_shape, n0, n1, n2);
+    int local = tile - __ldg(tile_start + item);
+    const int b2 = local % n2; local /= n2;
+    const int b1 = local % n1;
+    const int b0 = local / n1;
+    k1_tile_setup(sl.ctx, sl.tl, b0, b1, b2);
+    sl.tl.item = item;
+    if (sl.tl.mode == MODE_STAGED) k1_fast_fill(sl.ctx, sl.tl, sl.fast);
+  }
+  __syncwarp();
+}
+
 // Persistent, warp-specialised: one CTA per SM walks tiles blockIdx.x, +gridDim.x, ...  The
-// producer warp fetches the tile's item, runs the tile set-up and issues the TMA box load into
-// the next free stage of a shared-memory ring (full/empty mbarrier pair per stage); the 16
-// consumer warps compute the tile of the oldest full stage.  Box loads, descriptor fetches
-// and the set-up arithmetic therefore overlap the interpolation of earlier tiles.
+// producer warp prepares tile k+1 (item fetch + set-up) while the TMA box load of tile k is in
+// flight, and issues each load the moment its ring stage is released; the 16 consumer warps
+// interpolate the oldest full stage.  Rings: n_stages boxes (full/empty mbarrier pair each) and
+// n_stages+1 tile-state slots, so set-up never waits for shared-memory space.
 __global__ void __launch_bounds__(K1_THREADS, 1)
 k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile_start, int n_items, int total_tiles,
           int n_stages, int stage_bytes) {
   extern __shared__ __align__(128) uint8_t smem[];
-  K1Stage* stages = reinterpret_cast<K1Stage*>(smem + static_cast<size_t>(n_stages) * stage_bytes);
-  uint64_t* full = reinterpret_cast<uint64_t*>(stages + n_stages);
+  const int n_slots = n_stages + 1;
+  K1Slot* slots = reinterpret_cast<K1Slot*>(smem + static_cast<size_t>(n_stages) * stage_bytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(slots + n_slots);
   uint64_t* empty = full + n_stages;
   if (threadIdx.x == 0) {
     for (int s = 0; s < n_stages; ++s) {
@@ -546,56 +671,50 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
+  int stage = 0, phase = 0, slot = 0;
 
   if (threadIdx.x >= K1_CTHREADS) {
     // ------------------------------------------------------------------ producer warp
     int item = 0;
     int next_start = __ldg(tile_start + 1);
-    int iter = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-      const int s = iter % n_stages;
-      mbar_wait(empty + s, ((iter / n_stages) & 1) ^ 1);
-      while (tile >= next_start) { ++item; next_start = __ldg(tile_start + item + 1); }
-      K1Stage& st = stages[s];
-      {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(items + item) + 32;  // skip the tensor map
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&st.ctx.it) + 32;
-        uint32_t w0 = __ldg(src + lane), w1 = __ldg(src + lane + 32), w2 = __ldg(src + lane + 64);
-        dst[lane] = w0; dst[lane + 32] = w1; dst[lane + 64] = w2;
-      }
-      __syncwarp();
+    int tile = blockIdx.x;
+    if (tile < total_tiles) k1_prepare(items, tile_start, tile, item, next_start, slots[0], lane);
+    while (tile < total_tiles) {
+      K1_PROF_T0
+      mbar_wait(empty + stage, phase ^ 1);
+      K1_PROF_ADD(0)
       if (lane == 0) {
-        k1_ctx_finish(st.ctx);
-        int n0, n1, n2;
-        k1_tile_counts(st.ctx.it.out_shape, n0, n1, n2);
-        int local = tile - __ldg(tile_start + item);
-        const int b2 = local % n2; local /= n2;
-        const int b1 = local % n1;
-        const int b0 = local / n1;
-        k1_tile_setup(st.ctx, st.tl, b0, b1, b2);
-        if (st.tl.mode == MODE_STAGED) {
-          const int mo0 = st.ctx.it.tmap_off[0] - st.tl.mconst[0], mo1 = st.ctx.it.tmap_off[1] - st.tl.mconst[1],
-                    mo2 = st.ctx.it.tmap_off[2] - st.tl.mconst[2];
-          tmap_acquire(items[item].tmap);
-          mbar_expect_tx(full + s, static_cast<uint32_t>(st.tl.box[0] * st.tl.box[1] * st.tl.box[2] * 4));
-          tma_load_3d(smem + static_cast<size_t>(s) * stage_bytes, items[item].tmap, full + s, mo2, mo1, mo0);
+        const K1Slot& sl = slots[slot];
+        if (sl.tl.mode == MODE_STAGED) {
+          const int mo0 = sl.ctx.it.tmap_off[0] - sl.tl.mconst[0], mo1 = sl.ctx.it.tmap_off[1] - sl.tl.mconst[1],
+                    mo2 = sl.ctx.it.tmap_off[2] - sl.tl.mconst[2];
+          tmap_acquire(items[sl.tl.item].tmap);
+          mbar_expect_tx(full + stage, static_cast<uint32_t>(sl.tl.box[0] * sl.tl.box[1] * sl.tl.box[2] * 4));
+          tma_load_3d(smem + static_cast<size_t>(stage) * stage_bytes, items[sl.tl.item].tmap, full + stage, mo2, mo1, mo0);
         } else {
-          mbar_arrive(full + s);
+          mbar_arrive(full + stage);
         }
       }
       __syncwarp();
+      if (++stage == n_stages) { stage = 0; phase ^= 1; }
+      if (++slot == n_slots) slot = 0;
+      tile += gridDim.x;
+      // the slot being overwritten belonged to tile k - n_stages, whose stage release was just awaited
+      K1_PROF_ADD(1)
+      if (tile < total_tiles) k1_prepare(items, tile_start, tile, item, next_start, slots[slot], lane);
+      K1_PROF_ADD(2)
     }
     return;
   }
 
   // -------------------------------------------------------------------- consumer warps
-  int iter = 0;
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-    const int s = iter % n_stages;
-    mbar_wait(full + s, (iter / n_stages) & 1);
-    const K1Ctx& ctx = stages[s].ctx;
-    const K1Tile& tl = stages[s].tl;
-    const float* box = reinterpret_cast<const float*>(smem + static_cast<size_t>(s) * stage_bytes);
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    K1_PROF_T0
+    mbar_wait(full + stage, phase);
+    K1_PROF_ADD(3)
+    const K1Ctx& ctx = slots[slot].ctx;
+    const K1Tile& tl = slots[slot].tl;
+    const float* box = reinterpret_cast<const float*>(smem + static_cast<size_t>(stage) * stage_bytes);
     const adell_item& it = ctx.it;
     const int mode = tl.mode;
     if (mode == MODE_COPY) {
@@ -606,15 +725,18 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
     } else if (mode == MODE_STAGED) {
       const bool exact = (it.flags & (ADELL_F_STRICT | ADELL_F_CLIP)) != 0 || (ctx.pre_o != 0.0f && !tl.all_valid);
       if (exact) k1_tile_exact_dispatch<SmemTaps, false>(ctx, tl, box);
-      else if (it.interp == ADELL_NEAREST) k1_tile_staged_fast<true>(ctx, tl, box);
-      else k1_tile_staged_fast<false>(ctx, tl, box);
+      else if (it.interp == ADELL_NEAREST) k1_tile_staged_nearest(ctx, tl, slots[slot].fast, box);
+      else k1_tile_staged_trilinear(ctx, tl, slots[slot].fast, box);
     } else if (it.flags & ADELL_F_IDENTITY) {
       k1_tile_exact_dispatch<GlobalTaps, true>(ctx, tl, nullptr);
     } else {
       k1_tile_exact_dispatch<GlobalTaps, false>(ctx, tl, nullptr);
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(empty + s);
+    K1_PROF_ADD(4)
+    if (lane == 0) mbar_arrive(empty + stage);
+    if (++stage == n_stages) { stage = 0; phase ^= 1; }
+    if (++slot == n_slots) slot = 0;
   }
 }
 
@@ -752,11 +874,11 @@ extern "C" int adell_aug_gather(const adell_item* items_dev, const int32_t* tile
   if (e != cudaSuccess) { (void)cudaGetLastError(); return adell_map_cuda_error(e); }
   // ring of staged boxes: as many stages as fit next to the per-stage tile state
   const int stage_bytes = (info->smem_bytes + 127) & ~127;
-  const int per_stage = stage_bytes + static_cast<int>(sizeof(K1Stage)) + 16;
-  int n_stages = K1_SMEM_BUDGET / per_stage;
+  const int per_stage = stage_bytes + static_cast<int>(sizeof(K1Slot)) + 16;
+  int n_stages = (K1_SMEM_BUDGET - static_cast<int>(sizeof(K1Slot))) / per_stage;
   if (n_stages > K1_MAX_STAGES) n_stages = K1_MAX_STAGES;
   if (n_stages < 1) return ADELL_ERR_BAD_ARG;
-  const int smem = n_stages * per_stage;
+  const int smem = n_stages * per_stage + static_cast<int>(sizeof(K1Slot));
   e = cudaFuncSetAttribute(k1_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BUDGET);
   if (e != cudaSuccess) { (void)cudaGetLastError(); return adell_map_cuda_error(e); }
   const int64_t grid = info->total_tiles < sms ? info->total_tiles : sms;
@@ -767,3 +889,12 @@ extern "C" int adell_aug_gather(const adell_item* items_dev, const int32_t* tile
 }
 
 extern "C" int adell_aug_gather_launches(void) { return 1; }
+
+#ifdef K1_PROFILE
+// debug builds only: cumulative cycle counters {producer wait-empty, issue, prepare, consumer wait-full, compute}
+extern "C" int adell_debug_prof(unsigned long long* out8, int reset) {
+  cudaMemcpyFromSymbol(out8, k1_prof, sizeof(unsigned long long) * 8);
+  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(k1_prof, z, sizeof(z)); }
+  return 0;
+}
+#endif
