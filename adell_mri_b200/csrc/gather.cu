@@ -30,7 +30,8 @@ namespace {
 
 constexpr int K1_CWARPS = 16;                  // consumer warps per CTA
 constexpr int K1_CTHREADS = 32 * K1_CWARPS;    // consumer threads: one 16x16x16 tile = 8 voxels each
-constexpr int K1_THREADS = K1_CTHREADS + 32;   // + one producer warp (item fetch, tile set-up, TMA issue)
+constexpr int K1_PWARPS = 4;                   // producer warps: tile k is prepared and issued by warp k % 4
+constexpr int K1_THREADS = K1_CTHREADS + 32 * K1_PWARPS;
 constexpr int K1_T = 16;                       // tile edge
 constexpr int K1_MAX_STAGES = 4;
 constexpr int K1_SMEM_BUDGET = 224 * 1024;     // dynamic shared memory per persistent CTA (1 CTA per SM)
@@ -623,22 +624,34 @@ struct K1Slot {
   K1Fast fast;
 };
 
-// Producer: fetch the tile's item, derive the tile state (and the consumers' register image).
+// Producer: derive the tile state (and the consumers' register image) in the given slot.  The
+// item itself is fetched from global memory only when the tile sequence moves on to a new item
+// (tiles of one item are consecutive); otherwise it is copied from the producer's private copy.
 __device__ __forceinline__ void k1_prepare(const adell_item* __restrict__ items, const int32_t* __restrict__ tile_start,
-                                           int tile, int& item, int& next_start, K1Slot& sl, int lane) {
-  while (tile >= next_start) { ++item; next_start = __ldg(tile_start + item + 1); }
-  {
+                                           int tile, int& item, int& cur_start, int& next_start, int& cached_item,
+                                           K1Ctx& priv, K1Slot& sl, int lane) {
+  while (tile >= next_start) { ++item; cur_start = next_start; next_start = __ldg(tile_start + item + 1); }
+  uint32_t* pw = reinterpret_cast<uint32_t*>(&priv) + 32;
+  if (item != cached_item) {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(items + item) + 32;  // skip the tensor map
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&sl.ctx.it) + 32;
     uint32_t w0 = __ldg(src + lane), w1 = __ldg(src + lane + 32), w2 = __ldg(src + lane + 64);
-    dst[lane] = w0; dst[lane + 32] = w1; dst[lane + 64] = w2;
+    pw[lane] = w0; pw[lane + 32] = w1; pw[lane + 64] = w2;
+    __syncwarp();
+    if (lane == 0) k1_ctx_finish(priv);
+    __syncwarp();
+    cached_item = item;
+  }
+  {
+    // whole K1Ctx (item image + derived constants), minus the unused tensor-map bytes
+    constexpr int kWords = (sizeof(K1Ctx) - 128) / 4;
+    uint32_t* dw = reinterpret_cast<uint32_t*>(&sl.ctx) + 32;
+    for (int w = lane; w < kWords; w += 32) dw[w] = pw[w];
   }
   __syncwarp();
   if (lane == 0) {
-    k1_ctx_finish(sl.ctx);
     int n0, n1, n2;
     k1_tile_counts(sl.ctx.it.out_shape, n0, n1, n2);
-    int local = tile - __ldg(tile_start + item);
+    int local = tile - cur_start;
     const int b2 = local % n2; local /= n2;
     const int b1 = local % n1;
     const int b0 = local / n1;
@@ -658,11 +671,14 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
 k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile_start, int n_items, int total_tiles,
           int n_stages, int stage_bytes) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int n_slots = n_stages + 1;
+  const int n_slots = n_stages + K1_PWARPS;
   K1Slot* slots = reinterpret_cast<K1Slot*>(smem + static_cast<size_t>(n_stages) * stage_bytes);
-  uint64_t* full = reinterpret_cast<uint64_t*>(slots + n_slots);
+  K1Ctx* privs = reinterpret_cast<K1Ctx*>(slots + n_slots);   // one private item copy per producer warp
+  uint64_t* full = reinterpret_cast<uint64_t*>(privs + K1_PWARPS);
   uint64_t* empty = full + n_stages;
+  volatile int* issued = reinterpret_cast<volatile int*>(empty + n_stages);  // tiles issued so far (in order)
   if (threadIdx.x == 0) {
+    *issued = 0;
     for (int s = 0; s < n_stages; ++s) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(full + s)), "r"(1));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(empty + s)), "r"(K1_CWARPS));
@@ -674,13 +690,28 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
   int stage = 0, phase = 0, slot = 0;
 
   if (threadIdx.x >= K1_CTHREADS) {
-    // ------------------------------------------------------------------ producer warp
-    int item = 0;
+    // ------------------------------------------------------------------ producer warps
+    // warp p owns tiles k = p, p+P, ... of this CTA's sequence; ring positions follow k
+    const int pw = (threadIdx.x - K1_CTHREADS) >> 5;
+    K1Ctx& priv = privs[pw];
+    int item = 0, cached_item = -1, cur_start = 0;
     int next_start = __ldg(tile_start + 1);
-    int tile = blockIdx.x;
-    if (tile < total_tiles) k1_prepare(items, tile_start, tile, item, next_start, slots[0], lane);
+    int tile = blockIdx.x + pw * gridDim.x;
+    int seq = pw;  // position of `tile` in this CTA's tile sequence
+    for (int j = 0; j < pw; ++j) {
+      if (++stage == n_stages) { stage = 0; phase ^= 1; }
+      if (++slot == n_slots) slot = 0;
+    }
     while (tile < total_tiles) {
       K1_PROF_T0
+      // safe to overwrite: the slot's previous tile (k - n_slots) was released before this warp's
+      // previous issue (tile k - P waited for the stage of tile k - P - n_stages = k - n_slots)
+      k1_prepare(items, tile_start, tile, item, cur_start, next_start, cached_item, priv, slots[slot], lane);
+      K1_PROF_ADD(2)
+      // issues happen strictly in tile order (the parity wait below is only meaningful for the
+      // warp that is at most one ring revolution behind the consumers)
+      if (lane == 0) { while (*issued != seq) { __nanosleep(20); } }
+      __syncwarp();
       mbar_wait(empty + stage, phase ^ 1);
       K1_PROF_ADD(0)
       if (lane == 0) {
@@ -694,15 +725,17 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
         } else {
           mbar_arrive(full + stage);
         }
+        __threadfence_block();
+        *issued = seq + 1;
       }
       __syncwarp();
-      if (++stage == n_stages) { stage = 0; phase ^= 1; }
-      if (++slot == n_slots) slot = 0;
-      tile += gridDim.x;
-      // the slot being overwritten belonged to tile k - n_stages, whose stage release was just awaited
       K1_PROF_ADD(1)
-      if (tile < total_tiles) k1_prepare(items, tile_start, tile, item, next_start, slots[slot], lane);
-      K1_PROF_ADD(2)
+      seq += K1_PWARPS;
+      for (int j = 0; j < K1_PWARPS; ++j) {
+        if (++stage == n_stages) { stage = 0; phase ^= 1; }
+        if (++slot == n_slots) slot = 0;
+      }
+      tile += K1_PWARPS * gridDim.x;
     }
     return;
   }
@@ -874,11 +907,12 @@ extern "C" int adell_aug_gather(const adell_item* items_dev, const int32_t* tile
   if (e != cudaSuccess) { (void)cudaGetLastError(); return adell_map_cuda_error(e); }
   // ring of staged boxes: as many stages as fit next to the per-stage tile state
   const int stage_bytes = (info->smem_bytes + 127) & ~127;
-  const int per_stage = stage_bytes + static_cast<int>(sizeof(K1Slot)) + 16;
-  int n_stages = (K1_SMEM_BUDGET - static_cast<int>(sizeof(K1Slot))) / per_stage;
+  const int per_stage = stage_bytes + static_cast<int>(sizeof(K1Slot)) + 16;  // box + tile state + 2 mbarriers
+  const int fixed = static_cast<int>(K1_PWARPS * (sizeof(K1Slot) + sizeof(K1Ctx))) + 16;
+  int n_stages = (K1_SMEM_BUDGET - fixed) / per_stage;
   if (n_stages > K1_MAX_STAGES) n_stages = K1_MAX_STAGES;
   if (n_stages < 1) return ADELL_ERR_BAD_ARG;
-  const int smem = n_stages * per_stage + static_cast<int>(sizeof(K1Slot));
+  const int smem = n_stages * per_stage + fixed;
   e = cudaFuncSetAttribute(k1_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BUDGET);
   if (e != cudaSuccess) { (void)cudaGetLastError(); return adell_map_cuda_error(e); }
   const int64_t grid = info->total_tiles < sms ? info->total_tiles : sms;
