@@ -466,36 +466,46 @@ __device__ __forceinline__ void k1_tile_staged_trilinear(const K1Ctx&, const K1T
   }
 }
 
-// 128-bit vectorised identity copy (flip / crop only, everything valid and aligned).
+// 128-bit vectorised identity copy (flip / crop only, everything valid and aligned).  Each
+// consumer thread moves two float4: rows (di, dj) and (di + 8, dj), quad k4 of the 16-wide tile.
 __device__ __forceinline__ void k1_tile_copy_vec(const K1Ctx& c, const K1Tile& tl) {
   const adell_item& it = c.it;
-  const float* __restrict__ src = reinterpret_cast<const float*>(it.src);
+  const int k4 = threadIdx.x & 3, dj = (threadIdx.x >> 2) & 15, di = threadIdx.x >> 6;
+  const int o0 = tl.o0[0] + di, o1 = tl.o0[1] + dj, o2 = tl.o0[2] + 4 * k4;
+  const int O0 = it.out_shape[0];
+  if (o1 >= it.out_shape[1] || o2 >= it.out_shape[2] || o0 >= O0) return;
   const bool rev = it.grid_sign[2] * it.src_stride[2] < 0;
   const bool clip = (it.flags & ADELL_F_CLIP) != 0;
-  const float gain = c.pre_s * it.post_scale;
-  const float bias = fmaf(c.pre_o, it.post_scale, it.post_offset);
-  for (int v = threadIdx.x; v < K1_T * K1_T * (K1_T / 4); v += K1_CTHREADS) {
-    const int k4 = v & 3, dj = (v >> 2) & 15, di = v >> 6;
-    const int o0 = tl.o0[0] + di, o1 = tl.o0[1] + dj, o2 = tl.o0[2] + 4 * k4;
-    if (o0 >= it.out_shape[0] || o1 >= it.out_shape[1] || o2 >= it.out_shape[2]) continue;
-    const int g0 = it.grid_off[0] + it.grid_sign[0] * o0;
-    const int g1 = it.grid_off[1] + it.grid_sign[1] * o1;
-    const int g2 = it.grid_off[2] + it.grid_sign[2] * (rev ? o2 + 3 : o2);  // lowest address of the quad
-    const int64_t sidx = g0 * it.src_stride[0] + g1 * it.src_stride[1] + g2 * it.src_stride[2];
-    float4 q = __ldg(reinterpret_cast<const float4*>(src + sidx));
+  const float pre_s = c.pre_s, pre_o = c.pre_o, post_s = it.post_scale, post_o = it.post_offset;
+  const float clo = it.clip_lo, chi = it.clip_hi;
+  const float gain = pre_s * post_s, bias = fmaf(pre_o, post_s, post_o);
+  const bool plain = !clip && gain == 1.0f && bias == 0.0f;
+  const int g0 = it.grid_off[0] + it.grid_sign[0] * o0;
+  const int g1 = it.grid_off[1] + it.grid_sign[1] * o1;
+  const int g2 = it.grid_off[2] + it.grid_sign[2] * (rev ? o2 + 3 : o2);  // lowest address of the quad
+  const int64_t sstep = 8 * it.grid_sign[0] * it.src_stride[0], dstep = 8 * it.dst_stride[0];
+  const float4* sp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(it.src) + g0 * it.src_stride[0] +
+                                                      g1 * it.src_stride[1] + g2 * it.src_stride[2]);
+  float4* dp = reinterpret_cast<float4*>(it.dst + o0 * it.dst_stride[0] + o1 * it.dst_stride[1] + o2);
+  const bool two = o0 + 8 < O0 && di + 8 < K1_T;
+  float4 qa = __ldg(sp);
+  float4 qb = qa;
+  if (two) qb = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sp) + sstep));
+  auto fix = [&](float4 q) {
     if (rev) { float t = q.x; q.x = q.w; q.w = t; t = q.y; q.y = q.z; q.z = t; }
+    if (plain) return q;
     if (clip) {
-      q.x = k1_premap(q.x, c.pre_s, c.pre_o, true, it.clip_lo, it.clip_hi);
-      q.y = k1_premap(q.y, c.pre_s, c.pre_o, true, it.clip_lo, it.clip_hi);
-      q.z = k1_premap(q.z, c.pre_s, c.pre_o, true, it.clip_lo, it.clip_hi);
-      q.w = k1_premap(q.w, c.pre_s, c.pre_o, true, it.clip_lo, it.clip_hi);
-      q.x = fmaf(q.x, it.post_scale, it.post_offset); q.y = fmaf(q.y, it.post_scale, it.post_offset);
-      q.z = fmaf(q.z, it.post_scale, it.post_offset); q.w = fmaf(q.w, it.post_scale, it.post_offset);
-    } else if (gain != 1.0f || bias != 0.0f) {
+      q.x = fmaf(k1_premap(q.x, pre_s, pre_o, true, clo, chi), post_s, post_o);
+      q.y = fmaf(k1_premap(q.y, pre_s, pre_o, true, clo, chi), post_s, post_o);
+      q.z = fmaf(k1_premap(q.z, pre_s, pre_o, true, clo, chi), post_s, post_o);
+      q.w = fmaf(k1_premap(q.w, pre_s, pre_o, true, clo, chi), post_s, post_o);
+    } else {
       q.x = fmaf(q.x, gain, bias); q.y = fmaf(q.y, gain, bias); q.z = fmaf(q.z, gain, bias); q.w = fmaf(q.w, gain, bias);
     }
-    *reinterpret_cast<float4*>(it.dst + o0 * it.dst_stride[0] + o1 * it.dst_stride[1] + o2) = q;
-  }
+    return q;
+  };
+  *dp = fix(qa);
+  if (two) *reinterpret_cast<float4*>(reinterpret_cast<float*>(dp) + dstep) = fix(qb);
 }
 
 // ------------------------------------------------------------------------- per-tile set-up
@@ -506,25 +516,7 @@ __device__ void k1_tile_setup(const K1Ctx& c, K1Tile& tl, int b0, int b1, int b2
   tl.rmask = 0;
   tl.all_valid = 0;
   if (it.flags & ADELL_F_IDENTITY) {
-    // vector copy needs: fp32, unit step along axis 2, 16-byte aligned rows, nothing invalid, no noise
-    bool ok = it.src_dtype == ADELL_F32 && (it.src_stride[2] == 1 || it.src_stride[2] == -1) && it.dst_stride[2] == 1 &&
-              it.noise == nullptr && !(it.flags & (ADELL_F_PHILOX | ADELL_F_STRICT)) && (it.out_shape[2] & 3) == 0;
-    const bool rev = it.grid_sign[2] * it.src_stride[2] < 0;
-    for (int a = 0; a < 3 && ok; ++a) {
-      ok = ok && it.out_vlo[a] <= 0 && it.out_vhi[a] >= it.out_shape[a];
-      const int ga = it.grid_off[a], gb = it.grid_off[a] + it.grid_sign[a] * (it.out_shape[a] - 1);
-      ok = ok && min(ga, gb) >= c.tlo[a] && max(ga, gb) < c.thi[a];
-    }
-    if (ok) {
-      const int g2 = it.grid_off[2] + it.grid_sign[2] * (rev ? 3 : 0);
-      const int64_t e0 = g2 * it.src_stride[2];
-      ok = ((reinterpret_cast<uintptr_t>(it.src) & 3u) == 0) &&
-           (((reinterpret_cast<uintptr_t>(it.src) >> 2) + static_cast<uint64_t>(e0)) & 3u) == 0 &&
-           (it.src_stride[0] & 3) == 0 && (it.src_stride[1] & 3) == 0 && (reinterpret_cast<uintptr_t>(it.dst) & 15u) == 0 &&
-           (it.dst_stride[0] & 3) == 0 && (it.dst_stride[1] & 3) == 0;
-      // rows start at g0*s0 + g1*s1: multiples of 4 elements given the stride checks
-    }
-    if (ok) tl.mode = MODE_COPY;
+    if (c.copy_ok) tl.mode = MODE_COPY;
     return;
   }
   if (!(it.flags & ADELL_F_TMAP)) return;
@@ -790,11 +782,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 EncodeTiledFn k1_get_encode() {
+  // the driver entry point never changes within a process: look it up once (benign cache)
+  static EncodeTiledFn cached = nullptr;
+  if (cached != nullptr) return cached;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult q;
   cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
   if (e != cudaSuccess || q != cudaDriverEntryPointSuccess) { (void)cudaGetLastError(); return nullptr; }
-  return reinterpret_cast<EncodeTiledFn>(fn);
+  cached = reinterpret_cast<EncodeTiledFn>(fn);
+  return cached;
 }
 
 // Decides staged-path eligibility for one item and, when eligible, encodes its tensor map over

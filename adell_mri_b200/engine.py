@@ -90,3 +90,53 @@ def execute_ptrs(plan: BatchPlan, dst_ptr: np.ndarray, dst_stride: np.ndarray, k
             dev = host.to(plan.device, non_blocking=True)
             launch_packed(dev, n, info)
             plan.keep.append(dev)
+
+
+class PreparedSteps:
+    """Several steps composed and uploaded at once (one H2D copy), launched one by one."""
+
+    def __init__(self, launches, keep):
+        self.launches = launches  # [(device buffer view, n_items, LaunchInfo)]
+        self.keep = keep
+
+    def __len__(self):
+        return len(self.launches)
+
+    def run(self, k: int) -> None:
+        buf, n, info = self.launches[k]
+        launch_packed(buf, n, info)
+
+
+def prepare_steps(plan: BatchPlan, dst_ptr: np.ndarray, dst_stride: np.ndarray, step_sizes, keep=None) -> PreparedSteps:
+    """Compose once, launch many: ``plan`` holds the volumes of several consecutive steps
+    (``step_sizes[k]`` volumes each, in order).  Host composition, TMA descriptor encoding and
+    the parameter upload are done for all steps in one go, which amortises the Python / numpy
+    overhead that would otherwise dominate a ~0.2 ms kernel.  Only single-pass plans (at most
+    one resample per volume) can be split this way."""
+    _require_cuda(plan.device)
+    if plan.passes:
+        raise ValueError("prepare_steps needs a single-pass plan (one resample per volume)")
+    items = plan.build_launches(dst_ptr, dst_stride, None)[-1]
+    lib = _lib.load()
+    sizes = [int(x) for x in step_sizes]
+    if sum(sizes) != items.shape[0]:
+        raise ValueError("step_sizes must add up to the number of volumes")
+    # layout per step: items (512 B each) + int32 prefix, padded to 512 B so every slice stays aligned
+    offs, total = [], 0
+    for n in sizes:
+        offs.append(total)
+        total += n * 512 + ((4 * (n + 1) + 511) // 512) * 512
+    buf = np.zeros(total, np.uint8)
+    infos, start = [], 0
+    for n, o in zip(sizes, offs):
+        it = buf[o : o + n * 512].view(ITEM_DTYPE)
+        it[:] = items[start : start + n]
+        tiles = buf[o + n * 512 : o + n * 512 + 4 * (n + 1)].view(np.int32)
+        info = _lib.LaunchInfo()
+        _lib.check(lib.adell_aug_prepare(it.ctypes.data, n, tiles.ctypes.data, C.byref(info)), "adell_aug_prepare")
+        infos.append(info)
+        start += n
+    with torch.cuda.device(plan.device):
+        dev = torch.from_numpy(buf).pin_memory().to(plan.device, non_blocking=True)
+    launches = [(dev[o : o + n * 512 + 4 * (n + 1)], n, info) for n, o, info in zip(sizes, offs, infos)]
+    return PreparedSteps(launches, [dev, plan] + list(keep or []))

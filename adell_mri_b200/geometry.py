@@ -19,12 +19,13 @@ import torch
 from . import _lib
 
 
-def _eye(b: int) -> torch.Tensor:
-    return torch.eye(4, dtype=torch.float32).repeat(b, 1, 1)
+def _eye(b: int) -> np.ndarray:
+    return np.tile(np.eye(4, dtype=np.float32), (b, 1, 1))
 
 
-def _as_param(x, b: int) -> torch.Tensor | None:
-    """``[B, k]`` float32 tensor (k = number of parameters given) or None when empty."""
+def _as_param(x, b: int) -> np.ndarray | None:
+    """``[B, k]`` float32 array (k = number of parameters given) or None when empty.  The cast to
+    fp32 is the one ``torch.as_tensor(th, dtype=torch.float32)`` performs in MONAI."""
     if x is None:
         return None
     a = np.asarray(x, dtype=np.float64)
@@ -32,13 +33,15 @@ def _as_param(x, b: int) -> torch.Tensor | None:
         return None
     if a.ndim == 1:
         a = np.broadcast_to(a, (b, a.shape[0]))
-    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32)
+    return np.ascontiguousarray(a).astype(np.float32)
 
 
-def rotate_factors(radians: torch.Tensor) -> list[torch.Tensor]:
-    """The Rx, Ry, Rz factors (leading ones only) — multiplied left to right by the caller."""
+def rotate_factors(radians: np.ndarray) -> list[np.ndarray]:
+    """The Rx, Ry, Rz factors (leading ones only) — multiplied left to right by the caller.
+    sin / cos are evaluated by torch in fp32 exactly as MONAI's ``create_rotate`` does."""
     b, k = radians.shape
-    s, c = torch.sin(radians), torch.cos(radians)
+    t = torch.from_numpy(radians)
+    s, c = torch.sin(t).numpy(), torch.cos(t).numpy()
     out = []
     if k >= 1:
         m = _eye(b)
@@ -58,9 +61,9 @@ def rotate_factors(radians: torch.Tensor) -> list[torch.Tensor]:
     return out
 
 
-def shear_matrices(coefs: torch.Tensor) -> torch.Tensor:
+def shear_matrices(coefs: np.ndarray) -> np.ndarray:
     b, k = coefs.shape
-    c = torch.zeros(b, 6, dtype=torch.float32)
+    c = np.zeros((b, 6), np.float32)
     c[:, : min(k, 6)] = coefs[:, :6]
     out = _eye(b)
     out[:, 0, 1], out[:, 0, 2] = c[:, 0], c[:, 1]
@@ -69,14 +72,14 @@ def shear_matrices(coefs: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def translate_matrices(shift: torch.Tensor) -> torch.Tensor:
+def translate_matrices(shift: np.ndarray) -> np.ndarray:
     b, k = shift.shape
     out = _eye(b)
     out[:, : min(k, 3), 3] = shift[:, :3]
     return out
 
 
-def scale_matrices(factors: torch.Tensor) -> torch.Tensor:
+def scale_matrices(factors: np.ndarray) -> np.ndarray:
     b, k = factors.shape
     out = _eye(b)
     for i in range(min(k, 3)):
@@ -102,7 +105,7 @@ def compose_affine(rotate=None, shear=None, translate=None, scale=None, batch: i
         mats.append(translate_matrices(t))
     if sc is not None:
         mats.append(scale_matrices(sc))
-    stack = np.ascontiguousarray(torch.stack(mats, dim=1).numpy())  # [B, K, 4, 4]
+    stack = np.ascontiguousarray(np.stack(mats, axis=1))  # [B, K, 4, 4]
     out = np.empty((batch, 4, 4), np.float32)
     _lib.check(_lib.load().adell_mat4_chain(stack.ctypes.data, batch, stack.shape[1], out.ctypes.data), "adell_mat4_chain")
     return out

@@ -94,6 +94,8 @@ class SegmentationBatchAugmenter:
         self.flip_axis = list(flip_axis) if "flip" in augment else []
         self.flip_R = [np.random.RandomState() for _ in self.flip_axis]
         self.crop_R = np.random.RandomState()
+        self._meta = {}
+        self._dst_cache = {}
         self.set_random_state(None)
 
     def set_random_state(self, seed=None):
@@ -120,32 +122,41 @@ class SegmentationBatchAugmenter:
             pre = [int(i * 1.10) for i in self.random_crop_size]
             pre = [min(p, s) for p, s in zip(pre, shape)]
             starts = np.zeros((batch, 3), np.int64)
-        drawn = [[] for _ in self.samplers]
-        for b in range(batch):
-            if starts is not None:
-                # RandSpatialCropd(random_size=False): one randint per axis
+        if starts is not None:
+            # RandSpatialCropd(random_size=False): one randint per axis per sample, in order
+            for b in range(batch):
                 starts[b] = [self.crop_R.randint(s - p + 1) for s, p in zip(shape, pre)]
-            for si, smp in enumerate(self.samplers):
-                f, p = smp.draw(n_keys=nk)
-                fired[si, b] = f
-                if f:
-                    drawn[si].append(p)
-            for j, ax in enumerate(self.flip_axis):
-                flips[b, ax] ^= self.flip_R[j].rand() < 0.25
-        for si, plist in enumerate(drawn):
-            if plist:  # one batched composition per RandAffined (all draws share a parameter layout)
-                cols = {k: np.asarray([p[k] for p in plist], np.float64) for k in ("rotate", "shear", "translate", "scale")}
-                mats[si, fired[si]] = geometry.compose_affine(cols["rotate"], cols["shear"], cols["translate"],
-                                                              cols["scale"], batch=len(plist))
+        for si, smp in enumerate(self.samplers):
+            f, p = smp.draw_batch(batch, n_keys=nk)
+            fired[si] = f
+            if f.any():  # one batched composition per RandAffined (all draws share a parameter layout)
+                mats[si, f] = geometry.compose_affine(p["rotate"], p["shear"], p["translate"], p["scale"],
+                                                      batch=int(f.sum()))
+        for j, ax in enumerate(self.flip_axis):
+            flips[:, ax] ^= self.flip_R[j].random_sample(batch) < 0.25
         return dict(fired=fired, mats=mats, flips=flips, starts=starts)
+
+    def _sample_meta(self, s: dict):
+        """Per-sample volume metadata, cached on the sample dict's identity (a device-resident cache
+        hands the same dicts back every epoch)."""
+        m = self._meta.get(id(s))
+        if m is None or m[0] is not s:
+            vols = [s[k][0] for k in self.keys]
+            plan = BatchPlan(vols)
+            m = (s, plan.parent_ptr, plan.parent_stride, plan.parent_dtype, plan.shape, vols)
+            self._meta[id(s)] = m
+        return m
 
     def plan(self, samples: Sequence[dict], params=None) -> BatchPlan:
         B, nk = len(samples), len(self.keys)
-        vols = [s[k][0] for s in samples for k in self.keys]
-        shape = tuple(vols[0].shape)
+        metas = [self._sample_meta(s) for s in samples]
+        shape = tuple(int(x) for x in metas[0][4][0])
         if params is None:
             params = self.draw(B, shape)
-        plan = BatchPlan(vols, fast=self.fast, strict=self.strict)
+        plan = BatchPlan.from_arrays(
+            np.concatenate([m[1] for m in metas]), np.concatenate([m[2] for m in metas]),
+            np.concatenate([m[3] for m in metas]), np.concatenate([m[4] for m in metas]),
+            metas[0][5][0].device, [m[5] for m in metas], fast=self.fast, strict=self.strict)
         rep = lambda x: np.repeat(x, nk, axis=0)
         modes = self.modes * B
         if self.random_crop_size is not None:
@@ -159,16 +170,26 @@ class SegmentationBatchAugmenter:
             plan.center_crop(self.random_crop_size)
         return plan
 
-    def __call__(self, samples: Sequence[dict], params=None, out: dict | None = None) -> dict:
-        plan = self.plan(samples, params)
-        B, nk, ni = len(samples), len(self.keys), len(self.image_keys)
-        oshape = tuple(int(x) for x in plan.shape[0])
-        dev = plan.device
-        if out is None:
-            out = {self.output_image_key: torch.empty((B, ni, *oshape), dtype=torch.float32, device=dev)}
-            if self.has_label:
-                out["mask"] = torch.empty((B, 1, *oshape), dtype=torch.float32, device=dev)
-        img, ptrs, strides = out[self.output_image_key], [], []
+    def _alloc_out(self, B, oshape, dev):
+        out = {self.output_image_key: torch.empty((B, len(self.image_keys), *oshape), dtype=torch.float32, device=dev)}
+        if self.has_label:
+            out["mask"] = torch.empty((B, 1, *oshape), dtype=torch.float32, device=dev)
+        return out
+
+    def _dst(self, out, B):
+        """Destination pointers / strides of every (sample, key) volume inside the collated batch."""
+        key = (id(out), B) + tuple(t.data_ptr() for t in out.values())
+        hit = self._dst_cache.get(key)
+        if hit is None:
+            if len(self._dst_cache) > 64:
+                self._dst_cache.clear()
+            hit = self._dst_uncached(out, B)
+            self._dst_cache[key] = hit
+        return hit
+
+    def _dst_uncached(self, out, B):
+        ni = len(self.image_keys)
+        img = out[self.output_image_key]
         bi = np.arange(B, dtype=np.int64)[:, None]
         ci = np.arange(ni, dtype=np.int64)[None, :]
         p_img = img.data_ptr() + 4 * (bi * img.stride(0) + ci * img.stride(1))
@@ -181,5 +202,27 @@ class SegmentationBatchAugmenter:
             dst_stride = np.concatenate([s_img, s_m], axis=1).reshape(-1, 3)
         else:
             dst_ptr, dst_stride = p_img.reshape(-1), s_img.reshape(-1, 3)
-        engine.execute_ptrs(plan, dst_ptr.astype(np.uint64), dst_stride, keep=list(out.values()))
+        return dst_ptr.astype(np.uint64), dst_stride
+
+    def __call__(self, samples: Sequence[dict], params=None, out: dict | None = None) -> dict:
+        plan = self.plan(samples, params)
+        B = len(samples)
+        if out is None:
+            out = self._alloc_out(B, tuple(int(x) for x in plan.shape[0]), plan.device)
+        dst_ptr, dst_stride = self._dst(out, B)
+        engine.execute_ptrs(plan, dst_ptr, dst_stride, keep=list(out.values()))
         return out
+
+    def prepare_steps(self, batches: Sequence[Sequence[dict]], outs: Sequence[dict]) -> "engine.PreparedSteps":
+        """Draw and compose several consecutive steps at once (same RandomState order as calling
+        the augmenter step by step); ``outs[k]`` receives step ``k`` when ``prepared.run(k)`` is
+        called.  Amortises host composition over the steps."""
+        samples = [s for b in batches for s in b]
+        plan = self.plan(samples)
+        ptrs, strides = [], []
+        for b, out in zip(batches, outs):
+            p, st = self._dst(out, len(b))
+            ptrs.append(p); strides.append(st)
+        nk = len(self.keys)
+        return engine.prepare_steps(plan, np.concatenate(ptrs), np.concatenate(strides), [len(b) * nk for b in batches],
+                                    keep=[t for o in outs for t in o.values()])

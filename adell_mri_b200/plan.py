@@ -174,6 +174,25 @@ class _Stage:
 class BatchPlan:
     """``n`` volumes with their pending (recorded, not yet executed) transform chains."""
 
+    @classmethod
+    def from_arrays(cls, ptr, stride, dtype, shape, device, keep, fast=False, strict=False) -> "BatchPlan":
+        """Build from precomputed per-volume metadata (``ptr`` uint64 [n], ``stride`` int64 [n,3],
+        ``dtype`` uint8 [n], ``shape`` int64 [n,3]) — skips the per-tensor Python work."""
+        self = cls.__new__(cls)
+        self.n = int(ptr.shape[0])
+        self.fast = fast
+        self.keep = list(keep)
+        self.parent_ptr = np.asarray(ptr, np.uint64).copy()
+        self.parent_stride = np.asarray(stride, np.int64).copy()
+        self.parent_dtype = np.asarray(dtype, np.uint8).copy()
+        self.device = device
+        self.st = _Stage(np.asarray(shape, np.int64))
+        if strict:
+            self.st.strict[:] = True
+        self.default_strict = strict
+        self.passes = []
+        return self
+
     def __init__(self, parents: Sequence[torch.Tensor], fast: bool = False, strict: bool = False):
         n = len(parents)
         self.n = n
@@ -478,6 +497,8 @@ class BatchPlan:
         for idx, st, pptr, pstride, pdtype in self.passes:
             size = st.out_size()
             offs = np.concatenate([[0], np.cumsum(size.prod(axis=1))])
+            if alloc is None:
+                raise ValueError("this plan needs scratch volumes (multi-pass) but no allocator was given")
             buf = alloc(int(offs[-1]))
             self.keep.append(buf)
             tptr = (buf.data_ptr() + 4 * offs[:-1]).astype(np.uint64)

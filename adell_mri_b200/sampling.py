@@ -75,6 +75,44 @@ class RandAffineSampler:
         return fired, used
 
 
+    # ---- vectorised over a batch of consecutive calls (bit-identical to calling draw() B times) ----
+    def _n_per_randomize(self):
+        return sum(len(r) if r is not None else 0 for r in (self.rotate_range, self.shear_range,
+                                                            self.translate_range, self.scale_range))
+
+    def _params_from_uniforms(self, u: np.ndarray):
+        """``u``: [m, K] raw ``random_sample`` values of m RandAffineGrid.randomize calls -> dict of arrays."""
+        out, col = {}, 0
+        for name, rng, add in (("rotate", self.rotate_range, 0.0), ("shear", self.shear_range, 0.0),
+                               ("translate", self.translate_range, 0.0), ("scale", self.scale_range, 1.0)):
+            cols = []
+            for f in rng or []:
+                lo, hi = (f[0], f[1]) if _issequence(f) else (-f, f)
+                cols.append(lo + (hi - lo) * u[:, col] + add)  # numpy's uniform(): low + (high-low)*random_sample()
+                col += 1
+            out[name] = np.stack(cols, axis=1) if cols else np.zeros((u.shape[0], 0))
+        return out
+
+    def draw_batch(self, batch: int, n_keys: int = 1):
+        """``batch`` consecutive ``__call__``s at once: returns ``(fired[batch], params)`` with
+        ``params[name]`` of shape ``[n_fired, k]`` — the same values, consumed from the same three
+        streams in the same order, as ``batch`` calls of :meth:`draw`."""
+        K = self._n_per_randomize()
+        if self.R is self.R_inner:  # shared state object: the streams interleave, no batching possible
+            res = [self.draw(n_keys) for _ in range(batch)]
+            fired = np.array([r[0] for r in res], bool)
+            plist = [r[1] for r in res if r[0]]
+            names = ("rotate", "shear", "translate", "scale")
+            return fired, {k: np.asarray([p[k] for p in plist], np.float64).reshape(len(plist), -1) for k in names}
+        fired = self.R.random_sample(batch) < self.prob
+        self.R_inner.random_sample(batch * (1 + n_keys))
+        calls = 1 + fired.astype(np.int64) + n_keys          # randomize() calls on the grid stream per sample
+        start = np.concatenate([[0], np.cumsum(calls)[:-1]])
+        u = self.R_grid.random_sample(int(calls.sum()) * K).reshape(-1, K) if K else np.zeros((int(calls.sum()), 0))
+        used = u[start[fired] + 1]                             # the second randomize of a firing call is the used one
+        return fired, self._params_from_uniforms(used)
+
+
 def child_seeds(seed: int, n: int) -> list[int]:
     """``Compose.set_random_state(seed)``: one ``R.randint(MAX_SEED, dtype=uint32)`` per Randomizable child †."""
     R = np.random.RandomState(seed)

@@ -263,29 +263,42 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(i):
+    CHUNK = 16  # steps composed / uploaded together (host composition amortised; see engine.prepare_steps)
+
+    def batch_of(i):
         b0 = (i % n_batches) * batch
-        aug(cache[b0:b0 + batch], out=out)
+        return cache[b0:b0 + batch]
+
+    def run_steps(first, count, events=None):
+        """`count` steps starting at global step index `first`: draws + composition + upload for up to
+        CHUNK steps at a time, then one K1 launch per step."""
+        done = 0
+        while done < count:
+            n = min(CHUNK, count - done)
+            prepared = aug.prepare_steps([batch_of(first + done + k) for k in range(n)], [out] * n)
+            for k in range(n):
+                if events is not None:
+                    events[2 * (done + k)].record(stream)
+                prepared.run(k)
+                if events is not None:
+                    events[2 * (done + k) + 1].record(stream)
+            done += n
 
     # ---- device-resident throughput ("value") ----
-    for i in range(args.warmup):
-        step(i)
+    stream = torch.cuda.current_stream()
+    run_steps(0, args.warmup)
     barrier()
     clocks = ClockSampler(local_rank).start()
-    stream = torch.cuda.current_stream()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps)]
     launches0 = engine.launch_count
     e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e_start.record(stream)
-    for i in range(args.steps):
-        ev[2 * i].record(stream)
-        step(args.warmup + i)
-        ev[2 * i + 1].record(stream)
+    run_steps(args.warmup, args.steps, ev)
     e_stop.record(stream)
     barrier()
     clock_info = clocks.stop()
     total_ms = e_start.elapsed_time(e_stop)
-    k1_ms = [ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps)]  # H2D of 16 KB params + K1
+    k1_ms = [ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps)]
     launches = engine.launch_count - launches0
 
     # ---- roofline: K1 launch duration alone (params already uploaded), same seeded steps ----
@@ -320,8 +333,12 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per K1 launch, from the committed ncu capture
+    tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.workload)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "k1_gather_direct", "kernel_ms": kernel_ms, "algorithmic_bytes": alg_bytes,
+                "traffic": traffic, "kernel": "k1_gather", "kernel_ms": kernel_ms, "algorithmic_bytes": alg_bytes,
                 "peak_source": peak_src}
 
     # ---- end to end with host buffers ("e2e") ----
@@ -331,16 +348,35 @@ def main():
     h2d = sum(v.numel() * 4 for s in host_cache[:batch] for v in s.values())
     d2h = sum(v.numel() * 4 for v in out.values())
 
-    def e2e_step(i):
-        b0 = (i % 2) * batch
-        for j in range(batch):
-            for k in stage[j]:
-                stage[j][k].copy_(host_cache[b0 + j][k], non_blocking=True)
-        aug(stage, out=out)
-        for k in out:
-            host_out[k].copy_(out[k], non_blocking=True)
+    # three streams, double-buffered staging: H2D of step i+1 overlaps K1 of step i and D2H of step i-1
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    stage2 = [stage, [{k: torch.empty_like(v) for k, v in s_.items()} for s_ in cache[:batch]]]
+    out2 = [out, {k: torch.empty_like(v) for k, v in out.items()}]
+    host_out2 = [host_out, {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}]
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_k = [torch.cuda.Event() for _ in range(2)]
+    ev_out = [torch.cuda.Event() for _ in range(2)]
 
-    e2e_steps = max(3, min(args.steps, 10))
+    def e2e_step(i):
+        j = i % 2
+        b0 = j * batch
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(ev_k[j])  # staging buffer j free again (its previous kernel is done)
+            for b in range(batch):
+                for k in stage2[j][b]:
+                    stage2[j][b][k].copy_(host_cache[b0 + b][k], non_blocking=True)
+            ev_in[j].record(s_in)
+        stream.wait_event(ev_in[j])
+        stream.wait_event(ev_out[j])  # output buffer j has been drained
+        aug(stage2[j], out=out2[j])
+        ev_k[j].record(stream)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_k[j])
+            for k in out2[j]:
+                host_out2[j][k].copy_(out2[j][k], non_blocking=True)
+            ev_out[j].record(s_out)
+
+    e2e_steps = max(4, min(args.steps, 10))
     for i in range(2):
         e2e_step(i)
     barrier()
@@ -348,6 +384,8 @@ def main():
     a.record(stream)
     for i in range(e2e_steps):
         e2e_step(i)
+    stream.wait_stream(s_out)
+    stream.wait_stream(s_in)
     b.record(stream)
     barrier()
     e2e_ms = a.elapsed_time(b) / e2e_steps
@@ -367,7 +405,7 @@ def main():
             "e2e": {"value": world * vox_per_step / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
             "gpu_launches": launches, "clocks": clock_info,
-            "step_ms_median_incl_param_upload": statistics.median(k1_ms),
+            "k1_launch_ms_median_in_loop": statistics.median(k1_ms), "host_chunk_steps": CHUNK,
         }
         if world == 1 and not args.no_cpu_baseline:
             ref = CpuReference(args.workload)
