@@ -22,6 +22,44 @@ from .plan import ITEM_DTYPE, BatchPlan
 launch_count = 0
 
 
+class _PinnedRing:
+    """Rotating pinned staging buffers for the parameter uploads.  torch's caching host allocator
+    cannot hand a pinned block back while the copy that used it is still queued behind kernels,
+    so under a full launch queue every upload would fall through to cudaHostAlloc (which blocks
+    until the device is idle); a private ring with one event per slot avoids that."""
+
+    def __init__(self, slots: int = 8):
+        self.slots = [None] * slots
+        self.events = [None] * slots
+        self.i = 0
+
+    def stage(self, buf: np.ndarray, device: torch.device) -> torch.Tensor:
+        k = self.i
+        self.i = (self.i + 1) % len(self.slots)
+        n = buf.shape[0]
+        if self.events[k] is not None:
+            self.events[k].synchronize()  # normally long complete
+        if self.slots[k] is None or self.slots[k].numel() < n:
+            self.slots[k] = torch.empty(max(n, 1 << 16), dtype=torch.uint8).pin_memory()
+        host = self.slots[k][:n]
+        host.numpy()[:] = buf
+        dev = host.to(device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        self.events[k] = ev
+        return dev
+
+
+_rings: dict = {}
+
+
+def _stage(buf: np.ndarray, device: torch.device) -> torch.Tensor:
+    ring = _rings.get(device)
+    if ring is None:
+        ring = _rings[device] = _PinnedRing()
+    return ring.stage(buf, device)
+
+
 def _require_cuda(device: torch.device):
     if device.type != "cuda":
         raise RuntimeError(
@@ -86,8 +124,7 @@ def execute_ptrs(plan: BatchPlan, dst_ptr: np.ndarray, dst_stride: np.ndarray, k
         )
         for items in launches:
             buf, n, info = pack_launch(items)
-            host = torch.from_numpy(buf).pin_memory()
-            dev = host.to(plan.device, non_blocking=True)
+            dev = _stage(buf, plan.device)
             launch_packed(dev, n, info)
             plan.keep.append(dev)
 
@@ -137,6 +174,6 @@ def prepare_steps(plan: BatchPlan, dst_ptr: np.ndarray, dst_stride: np.ndarray, 
         infos.append(info)
         start += n
     with torch.cuda.device(plan.device):
-        dev = torch.from_numpy(buf).pin_memory().to(plan.device, non_blocking=True)
+        dev = _stage(buf, plan.device)
     launches = [(dev[o : o + n * 512 + 4 * (n + 1)], n, info) for n, o, info in zip(sizes, offs, infos)]
     return PreparedSteps(launches, [dev, plan] + list(keep or []))
