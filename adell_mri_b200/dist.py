@@ -1,0 +1,45 @@
+"""Multi-GPU plumbing of the hot path: one process per GPU (``torch.distributed``, NCCL).
+
+Batches shard by sample, so the transforms need no collective — each rank augments the samples
+it owns from its own device-resident cache, exactly as the reference shards by seeding every
+rank's sampler with ``seed + rank`` (/root/reference/adell_mri/utils/torch_utils.py:326-354).
+The single exchange on the path is the dataset-wide percentile: per-rank histogram counts are
+summed over NCCL after every radix pass, then every rank runs the identical selection.
+"""
+
+from __future__ import annotations
+
+from typing import Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import stats
+
+
+def rank_world(group=None) -> tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def shard_indices(n: int, rank: int | None = None, world: int | None = None) -> list[int]:
+    """Samples owned by ``rank``: ``i ≡ rank (mod world)``."""
+    if rank is None or world is None:
+        rank, world = rank_world()
+    return list(range(rank, n, world))
+
+
+def dataset_percentiles(vols: Sequence[torch.Tensor], qs: Sequence[float], group=None, kernels=None) -> torch.Tensor:
+    """Percentiles over the union of all ranks' volumes (numpy 'linear' semantics on the pooled
+    data): ``[1, len(qs)]`` fp32, identical on every rank."""
+    rank, world = rank_world(group)
+    local_n = sum(v.numel() for v in vols)
+    if world == 1:
+        return stats.percentiles(vols, qs, dataset_wide=True, kernels=kernels)
+    n = torch.tensor([local_n], dtype=torch.int64, device=vols[0].device)
+    dist.all_reduce(n, group=group)
+    return stats.percentiles(
+        vols, qs, dataset_wide=True, total_n=int(n.item()),
+        all_reduce=lambda bins: dist.all_reduce(bins, group=group), kernels=kernels,
+    )

@@ -117,22 +117,56 @@ def numpy_virtual_index(n: int, q: float):
     return lo, lo + 1, float(vi - lo)
 
 
+class _CudaKernels:
+    """The three device entry points of the radix selection (C ABI)."""
+
+    def __init__(self, vols):
+        self.dev = _check_vols(vols)
+        self.lib = _lib.load()
+        self.desc, self.max_n = vol_descriptors(vols)
+        self.n_vols = len(vols)
+        self.dtype = vols[0].dtype
+        self.st = _stream(self.dev)
+
+    def zeros(self, n, dtype):
+        return torch.zeros(n, dtype=dtype, device=self.dev)
+
+    def upload(self, arr: np.ndarray):
+        return torch.from_numpy(arr).pin_memory().to(self.dev, non_blocking=True)
+
+    def hist_pass(self, n_sel, shared, prefix, shift, bits, bins):
+        _lib.check(self.lib.adell_hist_pass(self.desc.data_ptr(), self.n_vols, self.max_n, n_sel, int(shared),
+                                            prefix.data_ptr(), shift, bits, bins.data_ptr(), self.st), "adell_hist_pass")
+
+    def hist_select(self, bins, n_hist, n_sel, shift, bits, prefix, rank):
+        _lib.check(self.lib.adell_hist_select(bins.data_ptr(), n_hist, n_sel, shift, bits, prefix.data_ptr(),
+                                              rank.data_ptr(), self.st), "adell_hist_select")
+
+    def finalize(self, prefix, frac, n_hist, n_q):
+        out = torch.empty(n_hist, n_q, dtype=torch.float32, device=self.dev)
+        _lib.check(self.lib.adell_percentile_finalize(prefix.data_ptr(), frac.data_ptr(), n_hist, n_q,
+                                                      _TORCH_TO_ADELL[self.dtype], out.data_ptr(), self.st),
+                   "adell_percentile_finalize")
+        return out
+
+
 def percentiles(
     vols: Sequence[torch.Tensor],
     qs: Sequence[float],
     dataset_wide: bool = False,
     all_reduce=None,
     total_n: int | None = None,
+    kernels=None,
 ) -> torch.Tensor:
     """Exact percentiles (numpy 'linear' method) of each volume: ``[n_vols, len(qs)]`` fp32.
 
     ``dataset_wide=True`` pools all volumes into one histogram (result ``[1, len(qs)]``);
     ``all_reduce(bins_tensor)`` — e.g. ``torch.distributed.all_reduce`` over NCCL — is then
     called on the int64 bin counts after every pass so that every rank selects identically,
-    with ``total_n`` the element count over all ranks.
+    with ``total_n`` the element count over all ranks.  ``kernels`` is the device back end
+    (the C ABI by default; the multi-rank host protocol is unit-tested with an injected one).
     """
-    dev = _check_vols(vols)
-    lib = _lib.load()
+    kern = kernels if kernels is not None else _CudaKernels(vols)
     dtype = vols[0].dtype
     if any(v.dtype != dtype for v in vols):
         raise ValueError("percentiles: mixed dtypes")
@@ -140,7 +174,6 @@ def percentiles(
     n_sel = 2 * n_q
     if n_sel > 8:
         raise ValueError("at most 4 quantiles per call")
-    desc, max_n = vol_descriptors(vols)
     n_hist = 1 if dataset_wide else n_vols
     counts = [sum(v.numel() for v in vols) if total_n is None else total_n] if dataset_wide else [v.numel() for v in vols]
     ranks = np.zeros((n_hist, n_q, 2), np.uint64)
@@ -150,30 +183,16 @@ def percentiles(
             lo, hi, g = numpy_virtual_index(n, q)
             ranks[h, j] = (lo, hi)
             frac[h, j] = g
-    rank_dev = torch.from_numpy(ranks.reshape(-1).view(np.int64)).pin_memory().to(dev, non_blocking=True)
-    frac_dev = torch.from_numpy(frac.reshape(-1)).pin_memory().to(dev, non_blocking=True)
-    prefix = torch.zeros(n_hist * n_sel, dtype=torch.int32, device=dev)
-    st = _stream(dev)
+    rank_dev = kern.upload(ranks.reshape(-1).view(np.int64))
+    frac_dev = kern.upload(frac.reshape(-1))
+    prefix = kern.zeros(n_hist * n_sel, torch.int32)
     first = True
     for shift, bits in _pass_schedule(dtype):
         n_sel_eff = 1 if first else n_sel
-        bins = torch.zeros(n_hist * n_sel_eff << bits, dtype=torch.int64, device=dev)
-        _lib.check(
-            lib.adell_hist_pass(desc.data_ptr(), n_vols, max_n, n_sel, int(dataset_wide), prefix.data_ptr(), shift, bits,
-                                bins.data_ptr(), st),
-            "adell_hist_pass",
-        )
+        bins = kern.zeros((n_hist * n_sel_eff) << bits, torch.int64)
+        kern.hist_pass(n_sel, dataset_wide, prefix, shift, bits, bins)
         if all_reduce is not None:
             all_reduce(bins)
-        _lib.check(
-            lib.adell_hist_select(bins.data_ptr(), n_hist, n_sel, shift, bits, prefix.data_ptr(), rank_dev.data_ptr(), st),
-            "adell_hist_select",
-        )
+        kern.hist_select(bins, n_hist, n_sel, shift, bits, prefix, rank_dev)
         first = False
-    out = torch.empty(n_hist, n_q, dtype=torch.float32, device=dev)
-    _lib.check(
-        lib.adell_percentile_finalize(prefix.data_ptr(), frac_dev.data_ptr(), n_hist, n_q, _TORCH_TO_ADELL[dtype],
-                                      out.data_ptr(), st),
-        "adell_percentile_finalize",
-    )
-    return out
+    return kern.finalize(prefix, frac_dev, n_hist, n_q)
