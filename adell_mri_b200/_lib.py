@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libadell_b200.so")
+LIB_PATH = os.environ.get("ADELL_B200_LIB") or os.path.join(_HERE, "libadell_b200.so")  # override: tooling only
 
 # constants mirrored from include/adell_b200.h
 F32, I16, U8 = 0, 1, 2
@@ -25,7 +25,7 @@ INTERP_MODES = {"nearest": NEAREST, "bilinear": TRILINEAR, "trilinear": TRILINEA
 
 
 class Item(C.Structure):
-    """Mirror of ``adell_item`` (512 bytes, 64-byte aligned)."""
+    """Mirror of ``adell_item`` (640 bytes, 64-byte aligned)."""
 
     _fields_ = [
         ("tmap", C.c_uint8 * 128),
@@ -63,11 +63,21 @@ class Item(C.Structure):
         ("interp", C.c_uint8),
         ("padding", C.c_uint8),
         ("flags", C.c_uint8),
-        ("reserved", C.c_uint8 * 44),
+        # derived by adell_aug_prepare (callers leave them zero)
+        ("tile_dim", C.c_uint8 * 3),
+        ("kind", C.c_uint8),
+        ("n_tiles", C.c_int32 * 3),
+        ("fp_smin", C.c_float * 3),
+        ("fp_smax", C.c_float * 3),
+        ("fp_fix", C.c_int32),
+        ("fp_U0", C.c_double * 3),
+        ("fp_D", C.c_double * 9),
+        ("reserved", C.c_uint8 * 32),
     ]
 
 
-assert C.sizeof(Item) == 512, C.sizeof(Item)
+ITEM_SIZE = C.sizeof(Item)
+assert ITEM_SIZE == 640, ITEM_SIZE
 
 
 class LaunchInfo(C.Structure):
@@ -110,6 +120,7 @@ _SIGNATURES = {
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
+ABI_VERSION = 2
 _lib = None
 
 
@@ -128,7 +139,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.adell_abi_version() != 1:
+    if lib.adell_abi_version() != ABI_VERSION:
         raise RuntimeError("adell_b200 ABI version mismatch")
     if lib.adell_item_size() != C.sizeof(Item):
         raise RuntimeError("adell_item layout mismatch between header and binding")

@@ -5,7 +5,7 @@
 
 #include "../../include/adell_b200.h"
 
-static_assert(sizeof(adell_item) == 512, "adell_item must stay 512 bytes (ABI)");
+static_assert(sizeof(adell_item) == 640, "adell_item must stay 640 bytes (ABI v2)");
 
 #define ADELL_CUDA_CHECK_LAUNCH()                         \
   do {                                                    \

@@ -8,20 +8,23 @@
 //  copy of the volume on the CPU.  Here every output voxel is produced once and written
 //  straight into the collated [B,C,H,W,D] batch.
 //
-// One CTA = one 16x16x16 output tile of one item.  Three code paths, chosen per tile
-// (block-uniform):
+// Persistent kernel, one CTA per SM, walking output tiles (extents chosen per item by
+// adell_aug_prepare).  One producer warp prepares tile state and issues the TMA box loads into
+// a shared-memory ring; sixteen consumer warps produce the voxels.  Paths, per tile:
 //   STAGED  the tile's source footprint (a box whose extents depend only on the item's matrix)
 //           is fetched by ONE TMA tensor copy (cp.async.bulk.tensor.3d, zero fill outside the
-//           volume = "zeros" padding for free) into shared memory; border/reflection halos are
-//           completed in shared memory; taps are then LDS with compile-time-free bank spread.
-//           Trilinear uses tile-local incremental coordinates + nested lerps (<=1e-4 contract);
-//           nearest uses the same coordinates and re-evaluates the bit-faithful MONAI/ATen
-//           chain only when a coordinate is within 1e-3 of a rounding tie => masks stay bit-exact.
+//           volume = "zeros" padding for free); taps are LDS.  Trilinear uses tile-local
+//           incremental coordinates + nested lerps (<=1e-4 contract); floor / rint / float->int
+//           are done with round-down adds of 1.5*2^23 on the FMA pipe (no XU conversions in the
+//           loop).  Nearest re-evaluates the bit-faithful MONAI/ATen chain only when a
+//           coordinate is within 1e-3 of a rounding tie => masks stay bit-exact.
 //           ADELL_F_STRICT / ADELL_F_CLIP items take the bit-faithful chain for every voxel.
-//   COPY    identity items (no resample fired): 128-bit vectorised flip/crop copy.
+//   COPY    identity items (no resample fired): 128-bit vectorised flip/crop copy, 64 KiB tiles,
+//           eight independent loads in flight per thread.
 //   DIRECT  generic fallback: taps fetched with read-only global loads (int16/uint8 sources,
-//           unaligned or oversized footprints, multiply-reflected coordinates, pad bands).
+//           unaligned or oversized footprints, pad bands).
 #include <cuda.h>
+#include <math.h>
 #include <stdlib.h>
 
 #include "k1_math.cuh"
@@ -29,14 +32,19 @@
 namespace {
 
 constexpr int K1_CWARPS = 16;                  // consumer warps per CTA
-constexpr int K1_CTHREADS = 32 * K1_CWARPS;    // consumer threads: one 16x16x16 tile = 8 voxels each
-constexpr int K1_PWARPS = 4;                   // producer warps: tile k is prepared and issued by warp k % 4
-constexpr int K1_THREADS = K1_CTHREADS + 32 * K1_PWARPS;
-constexpr int K1_T = 16;                       // tile edge
-constexpr int K1_MAX_STAGES = 4;
+constexpr int K1_CTHREADS = 32 * K1_CWARPS;    // consumer threads
+constexpr int K1_THREADS = K1_CTHREADS + 32;   // + one producer warp
+constexpr int K1_T = 16;                       // base tile edge
+constexpr int K1_MAX_STAGES = 6;
 constexpr int K1_SMEM_BUDGET = 224 * 1024;     // dynamic shared memory per persistent CTA (1 CTA per SM)
-constexpr int K1_MAX_BOX_BYTES = 100 * 1024;   // staged footprint limit (>= 2 CTAs per SM)
+constexpr int K1_MAX_BOX_BYTES = 100 * 1024;   // staged footprint limit (two stages)
+constexpr int K1_PREF_BOX_BYTES = 68 * 1024;   // preferred limit for the larger tile shapes (three stages)
 constexpr double K1_EPS = 1e-3;                // coordinate slack of the fast path / tie window
+constexpr float K1_MAGIC = 12582912.0f;        // 1.5 * 2^23: x + MAGIC has ulp 1 for |x| < 2^22
+constexpr uint32_t K1_MAGIC_BITS = 0x4B400000u;
+#ifndef K1_NV
+#define K1_NV 4                                 // trilinear voxels interleaved per consumer-thread iteration
+#endif
 
 enum { MODE_DIRECT = 0, MODE_STAGED = 1, MODE_ZERO = 2, MODE_COPY = 3 };
 
@@ -44,6 +52,7 @@ struct K1Tile {
   int mode;
   int item;         // index of the tile's item (descriptor address for the TMA issue)
   int o0[3];        // tile origin (output index space)
+  int T[3];         // tile extents (powers of two)
   int box[3];       // staged box extents, axes 0,1,2
   int mconst[3];    // box-local memory index = msign*t + mconst
   int msign[3];
@@ -53,6 +62,8 @@ struct K1Tile {
   int rmask;        // axes whose coordinates leave [0,S): border / reflection applied per voxel
   float rA[3], rB[3];  // box-local index = rA*u' + rB for the axes in rmask
   int all_valid;    // every tap of the tile lies inside the valid source region
+  int fix_lo, fix_hi;  // box columns [fix_lo, fix_hi) along axis 2 hold bytes that precede the valid
+                       // source box (16-byte alignment slack of the tensor map): zeroed after the load
 };
 
 // ------------------------------------------------------------------------- PTX helpers
@@ -93,11 +104,8 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const void* tmap, uint64_
       : "memory");
 }
 
-// ------------------------------------------------------------------------- tiling policy
-__host__ __device__ inline void k1_tile_counts(const int32_t* O, int& n0, int& n1, int& n2) {
-  n0 = (O[0] + K1_T - 1) / K1_T;
-  n1 = (O[1] + K1_T - 1) / K1_T;
-  n2 = (O[2] + K1_T - 1) / K1_T;
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------- tap fetchers
@@ -205,16 +213,16 @@ __device__ __forceinline__ void k1_finish(const adell_item& it, float val, int o
   it.dst[o0 * it.dst_stride[0] + o1 * it.dst_stride[1] + o2 * it.dst_stride[2]] = val;
 }
 
-// Thread -> voxel mapping shared by every path: lane = (dj parity, dk), consumer warp = i plane.
+// Thread -> voxel mapping of the generic paths: consecutive threads walk the tile in memory
+// order (axis 2 fastest), so rows are written coalesced whatever the tile extents are.
 template <class F>
 __device__ __forceinline__ void k1_for_each_voxel(const K1Tile& tl, const adell_item& it, F&& body) {
-  const int dk = threadIdx.x & 15, jj = (threadIdx.x >> 4) & 1, di = threadIdx.x >> 5;
-  const int o2 = tl.o0[2] + dk, o0 = tl.o0[0] + di;
-  if (o2 >= it.out_shape[2] || o0 >= it.out_shape[0]) return;
-#pragma unroll 2
-  for (int s = 0; s < 8; ++s) {
-    const int dj = 2 * s + jj, o1 = tl.o0[1] + dj;
-    if (o1 >= it.out_shape[1]) break;
+  const int s2 = __ffs(tl.T[2]) - 1, s1 = __ffs(tl.T[1]) - 1;
+  const int nvox = tl.T[0] << (s1 + s2);
+  for (int v = threadIdx.x; v < nvox; v += K1_CTHREADS) {
+    const int dk = v & (tl.T[2] - 1), dj = (v >> s2) & (tl.T[1] - 1), di = v >> (s1 + s2);
+    const int o0 = tl.o0[0] + di, o1 = tl.o0[1] + dj, o2 = tl.o0[2] + dk;
+    if (o0 >= it.out_shape[0] || o1 >= it.out_shape[1] || o2 >= it.out_shape[2]) continue;
     body(di, dj, dk, o0, o1, o2);
   }
 }
@@ -259,10 +267,11 @@ __device__ __noinline__ void k1_tile_exact_dispatch(const K1Ctx& c, const K1Tile
 struct __align__(16) K1Fast {
   float V0[3], D0[3], D1[3], D2[3];
   float Sf[3], Sm1[3], rA[3], rB[3];
+  int vlo[3], vhi[3];    // valid output range, tile-local
   float p0f, p1f, gain, bias, post_o, noise_std;
   int p0, p1;
   int n0, n1, n2;        // voxels of the tile along each axis
-  int vlo[3], vhi[3];    // valid output range, tile-local
+  int kw;                // tile extent along axis 2 (16 or 32): lanes of a warp along that axis
   int rmask, pad;        // per-voxel border / reflection handling (axes in rmask)
   int philox, padded;
   float* dst;            // tile origin in the destination
@@ -304,54 +313,20 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
   return v;
 }
 
-// Filled by the producer lane once per staged tile; the consumers copy it into registers with
-// 128-bit shared loads (the output stores go through a generic pointer, so anything left in
-// shared memory would be reloaded per voxel).
-__device__ __forceinline__ void k1_fast_fill(const K1Ctx& c, const K1Tile& tl, K1Fast& f) {
-  const adell_item& it = c.it;
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    f.V0[a] = tl.V0[a]; f.D0[a] = tl.Dm[a][0]; f.D1[a] = tl.Dm[a][1]; f.D2[a] = tl.Dm[a][2];
-    f.Sf[a] = c.Sf[a]; f.Sm1[a] = c.Sm1[a]; f.rA[a] = tl.rA[a]; f.rB[a] = tl.rB[a];
-    f.vlo[a] = it.out_vlo[a] - tl.o0[a];
-    f.vhi[a] = it.out_vhi[a] - tl.o0[a];
-  }
-  f.p1 = tl.box[2]; f.p0 = tl.box[1] * tl.box[2];
-  f.p1f = static_cast<float>(f.p1); f.p0f = static_cast<float>(f.p0);
-  f.gain = c.pre_s * it.post_scale;
-  f.bias = fmaf(c.pre_o, it.post_scale, it.post_offset);
-  f.post_o = it.post_offset;
-  f.noise_std = it.noise_std;
-  f.n0 = min(K1_T, it.out_shape[0] - tl.o0[0]);
-  f.n1 = min(K1_T, it.out_shape[1] - tl.o0[1]);
-  f.n2 = min(K1_T, it.out_shape[2] - tl.o0[2]);
-  bool padded = false;
-#pragma unroll
-  for (int a = 0; a < 3; ++a) padded = padded || f.vlo[a] > 0 || f.vhi[a] < (a == 0 ? f.n0 : a == 1 ? f.n1 : f.n2);
-  f.padded = padded ? 1 : 0;
-  f.ds0 = it.dst_stride[0]; f.ds1 = it.dst_stride[1]; f.ds2 = it.dst_stride[2];
-  f.dst = it.dst + tl.o0[0] * it.dst_stride[0] + tl.o0[1] * it.dst_stride[1] + tl.o0[2] * it.dst_stride[2];
-  f.ns1 = it.out_shape[2]; f.ns0 = static_cast<int64_t>(it.out_shape[1]) * it.out_shape[2];
-  f.olin0 = (static_cast<uint64_t>(tl.o0[0]) * it.out_shape[1] + tl.o0[1]) * it.out_shape[2] + tl.o0[2];
-  f.noise = it.noise ? it.noise + f.olin0 : nullptr;
-  f.philox = (it.flags & ADELL_F_PHILOX) ? 1 : 0;
-  f.philox_seed = it.philox_seed; f.philox_offset = it.philox_offset;
-  f.rmask = tl.rmask; f.pad = it.padding;
-}
-
 // Hot register image of a staged tile (everything else stays in the shared-memory K1Fast and is
 // only touched on the rare padded / noise paths).
 struct K1Hot {
   float D1[3], P[3];
   float Sf[3], Sm1[3], rA[3], rB[3];
-  float p0f, p1f, gain, bias;
+  float gain, bias;
+  uint32_t p0, p1, cbase;   // tap address = cbase + 4*(bits0*p0 + bits1*p1 + bits2), bits = float bits of x + MAGIC
   int rmask, pad, n1;
   int64_t ds1;
   float* drow;
   bool cold;  // padded output region or noise: take the slow store
 };
 
-__device__ __forceinline__ K1Hot k1_hot_load(const K1Fast& f, int di, int dk) {
+__device__ __forceinline__ K1Hot k1_hot_load(const K1Fast& f, int di, int dk, uint32_t box_addr) {
   K1Hot h;
   const float fk = static_cast<float>(dk), fi = static_cast<float>(di);
 #pragma unroll
@@ -360,7 +335,9 @@ __device__ __forceinline__ K1Hot k1_hot_load(const K1Fast& f, int di, int dk) {
     h.P[a] = fmaf(f.D0[a], fi, fmaf(f.D2[a], fk, f.V0[a]));
     h.Sf[a] = f.Sf[a]; h.Sm1[a] = f.Sm1[a]; h.rA[a] = f.rA[a]; h.rB[a] = f.rB[a];
   }
-  h.p0f = f.p0f; h.p1f = f.p1f; h.gain = f.gain; h.bias = f.bias;
+  h.gain = f.gain; h.bias = f.bias;
+  h.p0 = static_cast<uint32_t>(f.p0); h.p1 = static_cast<uint32_t>(f.p1);
+  h.cbase = box_addr - 4u * (K1_MAGIC_BITS * (h.p0 + h.p1 + 1u));  // modulo 2^32 on purpose
   h.rmask = f.rmask; h.pad = f.pad; h.n1 = f.n1;
   h.ds1 = f.ds1;
   h.drow = f.dst + di * f.ds0 + dk * f.ds2;
@@ -396,23 +373,34 @@ __device__ __forceinline__ void k1_fast_store(const K1Fast& f, const K1Hot& h, i
   else *p = val;
 }
 
+// lane -> (dk, first dj, dj step): 32 lanes along axis 2 for 32-wide tiles, else 16 x 2 rows
+__device__ __forceinline__ void k1_lane_map(const K1Fast& f, int& dk, int& jj, int& jstep) {
+  const int lane = threadIdx.x & 31;
+  if (f.kw == 32) { dk = lane; jj = 0; jstep = 1; }
+  else { dk = lane & 15; jj = lane >> 4; jstep = 2; }
+}
+
 __device__ __forceinline__ void k1_tile_staged_nearest(const K1Ctx& c, const K1Tile& tl, const K1Fast& f, const float* __restrict__ box) {
-  const int dk = threadIdx.x & 15, jj = (threadIdx.x >> 4) & 1, di = threadIdx.x >> 5;
+  int dk, jj, jstep;
+  k1_lane_map(f, dk, jj, jstep);
+  const int di = threadIdx.x >> 5;
   if (dk >= f.n2 || di >= f.n0) return;
-  const K1Hot h = k1_hot_load(f, di, dk);
+  const K1Hot h = k1_hot_load(f, di, dk, smem_u32(box));
   const float tie = 0.5f - static_cast<float>(K1_EPS);
 #pragma unroll 2
-  for (int s = 0; s < 8; ++s) {
-    const int dj = 2 * s + jj;
-    if (dj >= h.n1) break;
+  for (int dj = jj; dj < h.n1; dj += jstep) {
     float v0, v1, v2;
     k1_fast_coords(h, dj, v0, v1, v2);
-    const float n0 = rintf(v0), n1 = rintf(v1), n2 = rintf(v2);
+    // rint (ties to even) on the FMA pipe: x + 1.5*2^23 rounds to the nearest integer
+    const float t0 = __fadd_rn(v0, K1_MAGIC), t1 = __fadd_rn(v1, K1_MAGIC), t2 = __fadd_rn(v2, K1_MAGIC);
+    const float n0 = t0 - K1_MAGIC, n1 = t1 - K1_MAGIC, n2 = t2 - K1_MAGIC;
     float val;
-    if (fabsf(v0 - n0) > tie || fabsf(v1 - n1) > tie || fabsf(v2 - n2) > tie)
+    if (fabsf(v0 - n0) > tie || fabsf(v1 - n1) > tie || fabsf(v2 - n2) > tie) {
       val = k1_exact_nearest_smem(c, tl, box, di, dj, dk);  // within 1e-3 of a rounding tie
-    else
-      val = fmaf(box[__float2int_rn(fmaf(n0, h.p0f, fmaf(n1, h.p1f, n2)))], h.gain, h.bias);
+    } else {
+      const uint32_t a = h.cbase + 4u * (__float_as_uint(t0) * h.p0 + __float_as_uint(t1) * h.p1 + __float_as_uint(t2));
+      val = fmaf(lds_f32(a), h.gain, h.bias);
+    }
     k1_fast_store(f, h, di, dj, dk, val);
   }
 }
@@ -422,13 +410,14 @@ struct K1Vox {
   uint32_t a;  // shared-memory byte address of tap (0,0,0)
 };
 
-__device__ __forceinline__ K1Vox k1_fast_vox(const K1Hot& h, int dj, uint32_t box_addr) {
+__device__ __forceinline__ K1Vox k1_fast_vox(const K1Hot& h, int dj) {
   float v0, v1, v2;
   k1_fast_coords(h, dj, v0, v1, v2);
-  const float f0 = floorf(v0), f1 = floorf(v1), f2 = floorf(v2);
+  // floor on the FMA pipe: round-down add of 1.5*2^23 leaves floor(x) in the low mantissa bits
+  const float t0 = __fadd_rd(v0, K1_MAGIC), t1 = __fadd_rd(v1, K1_MAGIC), t2 = __fadd_rd(v2, K1_MAGIC);
   K1Vox x;
-  x.r0 = v0 - f0; x.r1 = v1 - f1; x.r2 = v2 - f2;
-  x.a = box_addr + 4u * static_cast<uint32_t>(__float2int_rn(fmaf(f0, h.p0f, fmaf(f1, h.p1f, f2))));
+  x.r0 = v0 - (t0 - K1_MAGIC); x.r1 = v1 - (t1 - K1_MAGIC); x.r2 = v2 - (t2 - K1_MAGIC);
+  x.a = h.cbase + 4u * (__float_as_uint(t0) * h.p0 + __float_as_uint(t1) * h.p1 + __float_as_uint(t2));
   return x;
 }
 
@@ -439,39 +428,51 @@ __device__ __forceinline__ float k1_lerp8(const K1Vox& x, const float* t) {
   return fmaf(x.r0, y1 - y0, y0);
 }
 
-// Two voxels per iteration, all sixteen shared-memory taps issued before any arithmetic that
+// NV voxels per iteration, all their shared-memory taps issued before any arithmetic that
 // depends on them (the loads are volatile asm so ptxas keeps them batched).
-__device__ __forceinline__ void k1_tile_staged_trilinear(const K1Ctx&, const K1Tile&, const K1Fast& f, const float* __restrict__ box) {
-  const int dk = threadIdx.x & 15, jj = (threadIdx.x >> 4) & 1, di = threadIdx.x >> 5;
+template <int NV>
+__device__ __forceinline__ void k1_tile_staged_trilinear(const K1Fast& f, const float* __restrict__ box) {
+  int dk, jj, jstep;
+  k1_lane_map(f, dk, jj, jstep);
+  const int di = threadIdx.x >> 5;
   if (dk >= f.n2 || di >= f.n0) return;
-  const K1Hot h = k1_hot_load(f, di, dk);
-  const uint32_t box_addr = smem_u32(box);
-  const uint32_t o1 = 4u * f.p1, o0 = 4u * f.p0;
+  const K1Hot h = k1_hot_load(f, di, dk, smem_u32(box));
+  const uint32_t o1 = 4u * h.p1, o0 = 4u * h.p0;
 #pragma unroll 1
-  for (int s = 0; s < 8; s += 2) {
-    const int dja = 2 * s + jj, djb = dja + 2;
-    if (dja >= h.n1) break;
-    const bool hasb = djb < h.n1;
-    const K1Vox xa = k1_fast_vox(h, dja, box_addr);
-    const K1Vox xb = k1_fast_vox(h, hasb ? djb : dja, box_addr);
-    float ta[8], tb[8];
-    ta[0] = lds_f32(xa.a); ta[1] = lds_f32(xa.a + 4); ta[2] = lds_f32(xa.a + o1); ta[3] = lds_f32(xa.a + o1 + 4);
-    tb[0] = lds_f32(xb.a); tb[1] = lds_f32(xb.a + 4); tb[2] = lds_f32(xb.a + o1); tb[3] = lds_f32(xb.a + o1 + 4);
-    ta[4] = lds_f32(xa.a + o0); ta[5] = lds_f32(xa.a + o0 + 4); ta[6] = lds_f32(xa.a + o0 + o1); ta[7] = lds_f32(xa.a + o0 + o1 + 4);
-    tb[4] = lds_f32(xb.a + o0); tb[5] = lds_f32(xb.a + o0 + 4); tb[6] = lds_f32(xb.a + o0 + o1); tb[7] = lds_f32(xb.a + o0 + o1 + 4);
-    const float va = fmaf(k1_lerp8(xa, ta), h.gain, h.bias);
-    const float vb = fmaf(k1_lerp8(xb, tb), h.gain, h.bias);
-    k1_fast_store(f, h, di, dja, dk, va);
-    if (hasb) k1_fast_store(f, h, di, djb, dk, vb);
+  for (int dj0 = jj; dj0 < h.n1; dj0 += NV * jstep) {
+    K1Vox x[NV];
+    float t[NV][8];
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      const int dj = dj0 + u * jstep;
+      x[u] = k1_fast_vox(h, dj < h.n1 ? dj : dj0);
+    }
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      t[u][0] = lds_f32(x[u].a); t[u][1] = lds_f32(x[u].a + 4);
+      t[u][2] = lds_f32(x[u].a + o1); t[u][3] = lds_f32(x[u].a + o1 + 4);
+    }
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      t[u][4] = lds_f32(x[u].a + o0); t[u][5] = lds_f32(x[u].a + o0 + 4);
+      t[u][6] = lds_f32(x[u].a + o0 + o1); t[u][7] = lds_f32(x[u].a + o0 + o1 + 4);
+    }
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      const int dj = dj0 + u * jstep;
+      const float val = fmaf(k1_lerp8(x[u], t[u]), h.gain, h.bias);
+      if (dj < h.n1) k1_fast_store(f, h, di, dj, dk, val);
+    }
   }
 }
 
-// 128-bit vectorised identity copy (flip / crop only, everything valid and aligned).  Each
-// consumer thread moves two float4: rows (di, dj) and (di + 8, dj), quad k4 of the 16-wide tile.
+// 128-bit vectorised identity copy (flip / crop only, everything valid and aligned): one 32x16x32
+// tile = 64 KiB; each consumer thread moves eight float4 (rows di0 + 4r of column quad q), all
+// eight loads issued before the first store so that ~64 KiB per SM are in flight.
 __device__ __forceinline__ void k1_tile_copy_vec(const K1Ctx& c, const K1Tile& tl) {
   const adell_item& it = c.it;
-  const int k4 = threadIdx.x & 3, dj = (threadIdx.x >> 2) & 15, di = threadIdx.x >> 6;
-  const int o0 = tl.o0[0] + di, o1 = tl.o0[1] + dj, o2 = tl.o0[2] + 4 * k4;
+  const int q = threadIdx.x & 7, dj = (threadIdx.x >> 3) & 15, di0 = threadIdx.x >> 7;
+  const int o0 = tl.o0[0] + di0, o1 = tl.o0[1] + dj, o2 = tl.o0[2] + 4 * q;
   const int O0 = it.out_shape[0];
   if (o1 >= it.out_shape[1] || o2 >= it.out_shape[2] || o0 >= O0) return;
   const bool rev = it.grid_sign[2] * it.src_stride[2] < 0;
@@ -483,122 +484,153 @@ __device__ __forceinline__ void k1_tile_copy_vec(const K1Ctx& c, const K1Tile& t
   const int g0 = it.grid_off[0] + it.grid_sign[0] * o0;
   const int g1 = it.grid_off[1] + it.grid_sign[1] * o1;
   const int g2 = it.grid_off[2] + it.grid_sign[2] * (rev ? o2 + 3 : o2);  // lowest address of the quad
-  const int64_t sstep = 8 * it.grid_sign[0] * it.src_stride[0], dstep = 8 * it.dst_stride[0];
-  const float4* sp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(it.src) + g0 * it.src_stride[0] +
-                                                      g1 * it.src_stride[1] + g2 * it.src_stride[2]);
-  float4* dp = reinterpret_cast<float4*>(it.dst + o0 * it.dst_stride[0] + o1 * it.dst_stride[1] + o2);
-  const bool two = o0 + 8 < O0 && di + 8 < K1_T;
-  float4 qa = __ldg(sp);
-  float4 qb = qa;
-  if (two) qb = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sp) + sstep));
-  auto fix = [&](float4 q) {
-    if (rev) { float t = q.x; q.x = q.w; q.w = t; t = q.y; q.y = q.z; q.z = t; }
-    if (plain) return q;
+  const int64_t sstep = 4 * it.grid_sign[0] * it.src_stride[0], dstep = 4 * it.dst_stride[0];
+  const float* sp = reinterpret_cast<const float*>(it.src) + g0 * it.src_stride[0] + g1 * it.src_stride[1] + g2 * it.src_stride[2];
+  float* dp = it.dst + o0 * it.dst_stride[0] + o1 * it.dst_stride[1] + o2;
+  const int nrow = min(8, (O0 - o0 + 3) >> 2);  // rows o0 + 4r of this thread inside the volume
+  float4 v[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+    if (r < nrow) v[r] = __ldcs(reinterpret_cast<const float4*>(sp + r * sstep));
+  auto fix = [&](float4 x) {
+    if (rev) { float t = x.x; x.x = x.w; x.w = t; t = x.y; x.y = x.z; x.z = t; }
+    if (plain) return x;
     if (clip) {
-      q.x = fmaf(k1_premap(q.x, pre_s, pre_o, true, clo, chi), post_s, post_o);
-      q.y = fmaf(k1_premap(q.y, pre_s, pre_o, true, clo, chi), post_s, post_o);
-      q.z = fmaf(k1_premap(q.z, pre_s, pre_o, true, clo, chi), post_s, post_o);
-      q.w = fmaf(k1_premap(q.w, pre_s, pre_o, true, clo, chi), post_s, post_o);
+      x.x = fmaf(k1_premap(x.x, pre_s, pre_o, true, clo, chi), post_s, post_o);
+      x.y = fmaf(k1_premap(x.y, pre_s, pre_o, true, clo, chi), post_s, post_o);
+      x.z = fmaf(k1_premap(x.z, pre_s, pre_o, true, clo, chi), post_s, post_o);
+      x.w = fmaf(k1_premap(x.w, pre_s, pre_o, true, clo, chi), post_s, post_o);
     } else {
-      q.x = fmaf(q.x, gain, bias); q.y = fmaf(q.y, gain, bias); q.z = fmaf(q.z, gain, bias); q.w = fmaf(q.w, gain, bias);
+      x.x = fmaf(x.x, gain, bias); x.y = fmaf(x.y, gain, bias); x.z = fmaf(x.z, gain, bias); x.w = fmaf(x.w, gain, bias);
     }
-    return q;
+    return x;
   };
-  *dp = fix(qa);
-  if (two) *reinterpret_cast<float4*>(reinterpret_cast<float*>(dp) + dstep) = fix(qb);
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+    if (r < nrow) __stcs(reinterpret_cast<float4*>(dp + r * dstep), fix(v[r]));
 }
 
 // ------------------------------------------------------------------------- per-tile set-up
-__device__ void k1_tile_setup(const K1Ctx& c, K1Tile& tl, int b0, int b1, int b2) {
+struct K1Slot {
+  K1Ctx ctx;
+  K1Tile tl;
+  K1Fast fast;
+};
+
+// Warp-parallel: lanes 0..2 own one source axis each (footprint, padding fold, box placement,
+// fast coordinates), lane 3 fills the scalar part of the consumers' register image.  Everything
+// per-item (the fp64 coordinate of output voxel 0 and its derivative, the footprint of a full
+// tile) was computed on the host by adell_aug_prepare.
+__device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0, int b1, int b2, int lane) {
   const adell_item& it = c.it;
-  tl.o0[0] = b0 * K1_T; tl.o0[1] = b1 * K1_T; tl.o0[2] = b2 * K1_T;
-  tl.mode = MODE_DIRECT;
-  tl.rmask = 0;
-  tl.all_valid = 0;
-  if (it.flags & ADELL_F_IDENTITY) {
-    if (c.copy_ok) tl.mode = MODE_COPY;
+  K1Tile& tl = sl.tl;
+  const unsigned FULL = 0xffffffffu;
+  const bool ax = lane < 3;
+  const int a = ax ? lane : 0;
+  const int o00 = b0 * it.tile_dim[0], o01 = b1 * it.tile_dim[1], o02 = b2 * it.tile_dim[2];
+  const int o0a = a == 0 ? o00 : (a == 1 ? o01 : o02);
+  if (ax) { tl.o0[a] = o0a; tl.T[a] = it.tile_dim[a]; }
+  if (it.kind != ADELL_KIND_STAGED) {
+    if (lane == 0) tl.mode = it.kind == ADELL_KIND_VCOPY ? MODE_COPY : MODE_DIRECT;
     return;
   }
-  if (!(it.flags & ADELL_F_TMAP)) return;
-  // affine map of the tile in double: u_a(d) = U0_a + sum_b D_ab d_b   (t-space, before padding)
-  double U0[3], D[3][3];
-  double cc[3];
-  for (int b = 0; b < 3; ++b) cc[b] = static_cast<double>(it.grid_off[b] + it.grid_sign[b] * tl.o0[b]) - static_cast<double>(c.cg[b]);
-  bool finite = true;
-  for (int a = 0; a < 3; ++a) {
-    const double K = static_cast<double>(it.nrm[a]) * it.src_shape[a] * 0.5;
-    const float* A = it.A + 4 * a;
-    U0[a] = (A[0] * cc[0] + A[1] * cc[1] + A[2] * cc[2] + A[3]) * K + (it.src_shape[a] - 1) * 0.5;
-    for (int b = 0; b < 3; ++b) D[a][b] = static_cast<double>(A[b]) * K * it.grid_sign[b];
-    double umin = U0[a], umax = U0[a];
-    for (int b = 0; b < 3; ++b) {
-      const double span = D[a][b] * (min(K1_T, it.out_shape[b] - tl.o0[b]) - 1);
-      if (span < 0) umin += span; else umax += span;
-    }
-    finite = finite && (umin > -1.0e6) && (umax < 1.0e6);
-    if (!finite) break;
-    tl.lo_t[a] = static_cast<int>(floor(umin - K1_EPS));
-    tl.hi_t[a] = static_cast<int>(floor(umax + K1_EPS)) + 1;
-  }
-  if (!finite) return;
-  bool all_valid = true, any_valid = true;
-  int blo[3], bhi[3];  // source index interval the box must hold
-  tl.rmask = 0;
-  for (int a = 0; a < 3; ++a) {
-    const int S = it.src_shape[a], lo = tl.lo_t[a], hi = tl.hi_t[a];
-    blo[a] = lo; bhi[a] = hi;
-    if (it.padding == ADELL_PAD_ZEROS) {
-      if (hi < c.tlo[a] || lo >= c.thi[a]) any_valid = false;
-    } else if (lo < 0 || hi > S - 1) {
-      // coordinates leave [0,S): the voxel loop clamps / reflects them (ATen semantics), so the box
-      // only has to hold the covering interval of the clamped / reflected indices (+1 for the hi tap)
-      tl.rmask |= 1 << a;
-      int rlo, rhi;
-      if (it.padding == ADELL_PAD_BORDER) {
-        rlo = min(max(lo, 0), S - 1); rhi = min(max(hi, 0), S - 1);
-      } else if (lo >= -S && hi < 0) {            // inside the first mirrored period below
-        rlo = -1 - hi; rhi = -1 - lo;
-      } else if (lo >= S && hi <= 2 * S - 1) {    // inside the first mirrored period above
-        rlo = 2 * S - 1 - hi; rhi = 2 * S - 1 - lo;
-      } else if (lo < 0 && lo >= -S && hi <= S - 1) {   // straddles the lower edge
-        rlo = 0; rhi = max(-1 - lo, hi);
-      } else if (lo >= 0 && hi >= S && hi <= 2 * S - 1) {  // straddles the upper edge
-        rlo = min(2 * S - 1 - hi, lo); rhi = S - 1;
-      } else {
-        rlo = 0; rhi = S - 1;
-      }
-      blo[a] = rlo; bhi[a] = rhi + 1;  // the hi tap of u' == S-1 reads cell S: TMA zero fill, weight 0
-    }
-    if (bhi[a] - blo[a] + 1 + (a == 2 ? 3 : 0) > it.tmap_box[a]) return;  // larger than the encoded box: direct path
-    all_valid = all_valid && lo >= c.tlo[a] && hi < c.thi[a];
-  }
-  if (!any_valid) { tl.mode = MODE_ZERO; return; }
-  // a pre offset must not leak into zero-filled (invalid) taps: such tiles use the exact path
-  tl.all_valid = (all_valid && tl.rmask == 0) ? 1 : 0;
-  if (tl.rmask != 0) {
-    tl.all_valid = 1;
-    for (int a = 0; a < 3; ++a) tl.all_valid = tl.all_valid && c.tlo[a] <= 0 && c.thi[a] >= it.src_shape[a];
-  }
-  for (int a = 0; a < 3; ++a) {
-    tl.box[a] = it.tmap_box[a];
-    tl.msign[a] = it.tmap_sign[a];
-    int mo = tl.msign[a] > 0 ? blo[a] + it.tmap_off[a] : -bhi[a] + it.tmap_off[a];
-    // TMA needs a 16-byte aligned start along the contiguous axis: round the box origin down to a
-    // multiple of 4 elements (the encoded inner extent carries 3 spare elements for this)
-    if (a == 2) mo = (mo >> 2) << 2;
-    tl.mconst[a] = it.tmap_off[a] - mo;
-    if (tl.rmask & (1 << a)) {
-      tl.V0[a] = static_cast<float>(U0[a]);
-      for (int b = 0; b < 3; ++b) tl.Dm[a][b] = static_cast<float>(D[a][b]);
-      tl.rA[a] = static_cast<float>(tl.msign[a]);
-      tl.rB[a] = static_cast<float>(tl.mconst[a]);
+  // un-padded source coordinate of the tile-origin voxel along axis a, and the tile's footprint
+  const double U0 = fma(it.fp_D[3 * a + 2], static_cast<double>(o02),
+                        fma(it.fp_D[3 * a + 1], static_cast<double>(o01),
+                            fma(it.fp_D[3 * a + 0], static_cast<double>(o00), it.fp_U0[a])));
+  const double umin = U0 + static_cast<double>(it.fp_smin[a]), umax = U0 + static_cast<double>(it.fp_smax[a]);
+  const bool finite = (umin > -1.0e6) && (umax < 1.0e6);
+  if (!__all_sync(FULL, finite)) { if (lane == 0) tl.mode = MODE_DIRECT; return; }
+  const int S = it.src_shape[a];
+  const int lo = static_cast<int>(floor(umin - K1_EPS)), hi = static_cast<int>(floor(umax + K1_EPS)) + 1;
+  int blo = lo, bhi = hi;  // source index interval the box must hold
+  bool rm = false, anyv = true;
+  if (it.padding == ADELL_PAD_ZEROS) {
+    if (hi < c.tlo[a] || lo >= c.thi[a]) anyv = false;
+  } else if (lo < 0 || hi > S - 1) {
+    // coordinates leave [0,S): the voxel loop clamps / reflects them (ATen semantics), so the box
+    // only has to hold the covering interval of the clamped / reflected indices (+1 for the hi tap)
+    rm = true;
+    int rlo, rhi;
+    if (it.padding == ADELL_PAD_BORDER) {
+      rlo = min(max(lo, 0), S - 1); rhi = min(max(hi, 0), S - 1);
+    } else if (lo >= -S && hi < 0) {            // inside the first mirrored period below
+      rlo = -1 - hi; rhi = -1 - lo;
+    } else if (lo >= S && hi <= 2 * S - 1) {    // inside the first mirrored period above
+      rlo = 2 * S - 1 - hi; rhi = 2 * S - 1 - lo;
+    } else if (lo < 0 && lo >= -S && hi <= S - 1) {   // straddles the lower edge
+      rlo = 0; rhi = max(-1 - lo, hi);
+    } else if (lo >= 0 && hi >= S && hi <= 2 * S - 1) {  // straddles the upper edge
+      rlo = min(2 * S - 1 - hi, lo); rhi = S - 1;
     } else {
-      tl.V0[a] = static_cast<float>(tl.msign[a] * U0[a] + tl.mconst[a]);
-      for (int b = 0; b < 3; ++b) tl.Dm[a][b] = static_cast<float>(tl.msign[a] * D[a][b]);
-      tl.rA[a] = 1.0f; tl.rB[a] = 0.0f;
+      rlo = 0; rhi = S - 1;
+    }
+    blo = rlo; bhi = rhi + 1;  // the hi tap of u' == S-1 reads cell S: TMA zero fill, weight 0
+  }
+  const bool fits = bhi - blo + 1 + (a == 2 ? 3 : 0) <= it.tmap_box[a];  // else larger than the encoded box
+  const bool allv = lo >= c.tlo[a] && hi < c.thi[a];
+  const bool win_full = c.tlo[a] <= 0 && c.thi[a] >= S;
+  if (!__all_sync(FULL, fits)) { if (lane == 0) tl.mode = MODE_DIRECT; return; }
+  if (!__all_sync(FULL, anyv)) { if (lane == 0) tl.mode = MODE_ZERO; return; }
+  const int rmask = static_cast<int>(__ballot_sync(FULL, ax && rm) & 7u);
+  const bool allv_all = __all_sync(FULL, allv), win_all = __all_sync(FULL, win_full);
+  // a pre offset must not leak into zero-filled (invalid) taps: such tiles use the exact path
+  const int all_valid = rmask ? (win_all ? 1 : 0) : (allv_all ? 1 : 0);
+  const int msign = it.tmap_sign[a];
+  int mo = msign > 0 ? blo + it.tmap_off[a] : -bhi + it.tmap_off[a];
+  // TMA needs a 16-byte aligned start along the contiguous axis: round the box origin down to a
+  // multiple of 4 elements (the encoded inner extent carries 3 spare elements for this)
+  if (a == 2) mo = (mo >> 2) << 2;
+  const int mconst = it.tmap_off[a] - mo;
+  float V0, Dm0, Dm1, Dm2, rA, rB;
+  if (rm) {
+    V0 = static_cast<float>(U0);
+    Dm0 = static_cast<float>(it.fp_D[3 * a + 0]); Dm1 = static_cast<float>(it.fp_D[3 * a + 1]); Dm2 = static_cast<float>(it.fp_D[3 * a + 2]);
+    rA = static_cast<float>(msign); rB = static_cast<float>(mconst);
+  } else {
+    V0 = static_cast<float>(msign * U0 + mconst);
+    Dm0 = static_cast<float>(msign * it.fp_D[3 * a + 0]); Dm1 = static_cast<float>(msign * it.fp_D[3 * a + 1]);
+    Dm2 = static_cast<float>(msign * it.fp_D[3 * a + 2]);
+    rA = 1.0f; rB = 0.0f;
+  }
+  K1Fast& f = sl.fast;
+  const int na = min(static_cast<int>(it.tile_dim[a]), it.out_shape[a] - o0a);
+  const int vlo = it.out_vlo[a] - o0a, vhi = it.out_vhi[a] - o0a;
+  const bool padded_a = vlo > 0 || vhi < na;
+  const bool padded = __any_sync(FULL, ax && padded_a);
+  if (ax) {
+    tl.lo_t[a] = lo; tl.hi_t[a] = hi;
+    tl.box[a] = it.tmap_box[a]; tl.msign[a] = msign; tl.mconst[a] = mconst;
+    tl.V0[a] = V0; tl.Dm[a][0] = Dm0; tl.Dm[a][1] = Dm1; tl.Dm[a][2] = Dm2; tl.rA[a] = rA; tl.rB[a] = rB;
+    f.V0[a] = V0; f.D0[a] = Dm0; f.D1[a] = Dm1; f.D2[a] = Dm2;
+    f.Sf[a] = c.Sf[a]; f.Sm1[a] = c.Sm1[a]; f.rA[a] = rA; f.rB[a] = rB;
+    f.vlo[a] = vlo; f.vhi[a] = vhi;
+    if (a == 0) f.n0 = na; else if (a == 1) f.n1 = na; else f.n2 = na;
+    if (a == 2) {  // alignment slack columns of the tensor map that fall inside this box
+      tl.fix_lo = max(0, -mo);
+      tl.fix_hi = it.fp_fix > 0 ? min(it.tmap_box[2], it.fp_fix - mo) : 0;
     }
   }
-  tl.mode = MODE_STAGED;
+  if (lane == 3) {
+    tl.mode = MODE_STAGED;
+    tl.rmask = rmask; tl.all_valid = all_valid;
+    f.p1 = it.tmap_box[2]; f.p0 = it.tmap_box[1] * it.tmap_box[2];
+    f.p1f = static_cast<float>(f.p1); f.p0f = static_cast<float>(f.p0);
+    f.gain = c.pre_s * it.post_scale;
+    f.bias = fmaf(c.pre_o, it.post_scale, it.post_offset);
+    f.post_o = it.post_offset;
+    f.noise_std = it.noise_std;
+    f.kw = it.tile_dim[2];
+    f.padded = padded ? 1 : 0;
+    f.ds0 = it.dst_stride[0]; f.ds1 = it.dst_stride[1]; f.ds2 = it.dst_stride[2];
+    f.dst = it.dst + o00 * it.dst_stride[0] + o01 * it.dst_stride[1] + o02 * it.dst_stride[2];
+    f.ns1 = it.out_shape[2]; f.ns0 = static_cast<int64_t>(it.out_shape[1]) * it.out_shape[2];
+    f.olin0 = (static_cast<uint64_t>(o00) * it.out_shape[1] + o01) * it.out_shape[2] + o02;
+    f.noise = it.noise ? it.noise + f.olin0 : nullptr;
+    f.philox = (it.flags & ADELL_F_PHILOX) ? 1 : 0;
+    f.philox_seed = it.philox_seed; f.philox_offset = it.philox_offset;
+    f.rmask = rmask; f.pad = it.padding;
+  }
 }
 
 #ifdef K1_PROFILE
@@ -610,24 +642,19 @@ __device__ unsigned long long k1_prof[8];
 #define K1_PROF_ADD(i)
 #endif
 
-struct K1Slot {
-  K1Ctx ctx;
-  K1Tile tl;
-  K1Fast fast;
-};
-
 // Producer: derive the tile state (and the consumers' register image) in the given slot.  The
-// item itself is fetched from global memory only when the tile sequence moves on to a new item
-// (tiles of one item are consecutive); otherwise it is copied from the producer's private copy.
+// item itself is fetched from global memory only when the tile sequence moves on to a new item.
 __device__ __forceinline__ void k1_prepare(const adell_item* __restrict__ items, const int32_t* __restrict__ tile_start,
                                            int tile, int& item, int& cur_start, int& next_start, int& cached_item,
                                            K1Ctx& priv, K1Slot& sl, int lane) {
   while (tile >= next_start) { ++item; cur_start = next_start; next_start = __ldg(tile_start + item + 1); }
+  constexpr int kItemWords = (sizeof(adell_item) - 128) / 4;  // without the tensor map
   uint32_t* pw = reinterpret_cast<uint32_t*>(&priv) + 32;
   if (item != cached_item) {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(items + item) + 32;  // skip the tensor map
-    uint32_t w0 = __ldg(src + lane), w1 = __ldg(src + lane + 32), w2 = __ldg(src + lane + 64);
-    pw[lane] = w0; pw[lane + 32] = w1; pw[lane + 64] = w2;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(items + item) + 32;
+#pragma unroll
+    for (int w = 0; w < (kItemWords + 31) / 32; ++w)
+      if (w * 32 + lane < kItemWords) pw[w * 32 + lane] = __ldg(src + w * 32 + lane);
     __syncwarp();
     if (lane == 0) k1_ctx_finish(priv);
     __syncwarp();
@@ -637,43 +664,51 @@ __device__ __forceinline__ void k1_prepare(const adell_item* __restrict__ items,
     // whole K1Ctx (item image + derived constants), minus the unused tensor-map bytes
     constexpr int kWords = (sizeof(K1Ctx) - 128) / 4;
     uint32_t* dw = reinterpret_cast<uint32_t*>(&sl.ctx) + 32;
-    for (int w = lane; w < kWords; w += 32) dw[w] = pw[w];
+#pragma unroll
+    for (int w = 0; w < (kWords + 31) / 32; ++w)
+      if (w * 32 + lane < kWords) dw[w * 32 + lane] = pw[w * 32 + lane];
   }
   __syncwarp();
-  if (lane == 0) {
-    int n0, n1, n2;
-    k1_tile_counts(sl.ctx.it.out_shape, n0, n1, n2);
-    int local = tile - cur_start;
-    const int b2 = local % n2; local /= n2;
-    const int b1 = local % n1;
-    const int b0 = local / n1;
-    k1_tile_setup(sl.ctx, sl.tl, b0, b1, b2);
-    sl.tl.item = item;
-    if (sl.tl.mode == MODE_STAGED) k1_fast_fill(sl.ctx, sl.tl, sl.fast);
-  }
+  const int n1 = priv.it.n_tiles[1], n2 = priv.it.n_tiles[2];
+  int local = tile - cur_start;
+  const int b2 = local % n2; local /= n2;
+  const int b1 = local % n1;
+  const int b0 = local / n1;
+  k1_tile_setup(sl.ctx, sl, b0, b1, b2, lane);
+  if (lane == 0) sl.tl.item = item;
+  __syncwarp();
+}
+
+// Producer, after the TMA load of a tile whose box contains alignment-slack columns completed:
+// zero them (they hold bytes that precede the valid source box) and hand the stage to the consumers.
+__device__ __forceinline__ void k1_fix_columns(float* box, const K1Tile& tl, int lane) {
+  const int w = tl.fix_hi - tl.fix_lo, p1 = tl.box[2];
+  const int rows = tl.box[0] * tl.box[1];
+  for (int e = lane; e < rows * w; e += 32) box[(e / w) * p1 + tl.fix_lo + e % w] = 0.0f;
+  fence_proxy_async_smem();
   __syncwarp();
 }
 
 // Persistent, warp-specialised: one CTA per SM walks tiles blockIdx.x, +gridDim.x, ...  The
 // producer warp prepares tile k+1 (item fetch + set-up) while the TMA box load of tile k is in
 // flight, and issues each load the moment its ring stage is released; the 16 consumer warps
-// interpolate the oldest full stage.  Rings: n_stages boxes (full/empty mbarrier pair each) and
+// work on the oldest full stage.  Rings: n_stages boxes (full/empty mbarrier pair each) and
 // n_stages+1 tile-state slots, so set-up never waits for shared-memory space.
 __global__ void __launch_bounds__(K1_THREADS, 1)
 k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile_start, int n_items, int total_tiles,
           int n_stages, int stage_bytes) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int n_slots = n_stages + K1_PWARPS;
+  const int n_slots = n_stages + 1;
   K1Slot* slots = reinterpret_cast<K1Slot*>(smem + static_cast<size_t>(n_stages) * stage_bytes);
-  K1Ctx* privs = reinterpret_cast<K1Ctx*>(slots + n_slots);   // one private item copy per producer warp
-  uint64_t* full = reinterpret_cast<uint64_t*>(privs + K1_PWARPS);
+  K1Ctx* priv = reinterpret_cast<K1Ctx*>(slots + n_slots);   // the producer's private item copy
+  uint64_t* full = reinterpret_cast<uint64_t*>(priv + 1);
   uint64_t* empty = full + n_stages;
-  volatile int* issued = reinterpret_cast<volatile int*>(empty + n_stages);  // tiles issued so far (in order)
+  uint64_t* landed = empty + n_stages;   // TMA completion of tiles that need the column fix-up first
   if (threadIdx.x == 0) {
-    *issued = 0;
     for (int s = 0; s < n_stages; ++s) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(full + s)), "r"(1));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(empty + s)), "r"(K1_CWARPS));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(landed + s)), "r"(1));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -682,52 +717,59 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
   int stage = 0, phase = 0, slot = 0;
 
   if (threadIdx.x >= K1_CTHREADS) {
-    // ------------------------------------------------------------------ producer warps
-    // warp p owns tiles k = p, p+P, ... of this CTA's sequence; ring positions follow k
-    const int pw = (threadIdx.x - K1_CTHREADS) >> 5;
-    K1Ctx& priv = privs[pw];
+    // ------------------------------------------------------------------ producer warp
     int item = 0, cached_item = -1, cur_start = 0;
     int next_start = __ldg(tile_start + 1);
-    int tile = blockIdx.x + pw * gridDim.x;
-    int seq = pw;  // position of `tile` in this CTA's tile sequence
-    for (int j = 0; j < pw; ++j) {
-      if (++stage == n_stages) { stage = 0; phase ^= 1; }
-      if (++slot == n_slots) slot = 0;
-    }
-    while (tile < total_tiles) {
+    uint32_t landed_phase = 0;          // bit s = parity to wait for on landed[s]
+    int pend_stage = -1, pend_slot = 0; // tile whose column fix-up is still due
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       K1_PROF_T0
-      // safe to overwrite: the slot's previous tile (k - n_slots) was released before this warp's
-      // previous issue (tile k - P waited for the stage of tile k - P - n_stages = k - n_slots)
-      k1_prepare(items, tile_start, tile, item, cur_start, next_start, cached_item, priv, slots[slot], lane);
+      // safe to overwrite: the slot's previous tile (k - n_slots) was released before the previous
+      // iteration's issue (tile k-1 waited for the stage of tile k-1-n_stages = k - n_slots)
+      k1_prepare(items, tile_start, tile, item, cur_start, next_start, cached_item, *priv, slots[slot], lane);
       K1_PROF_ADD(2)
-      // issues happen strictly in tile order (the parity wait below is only meaningful for the
-      // warp that is at most one ring revolution behind the consumers)
-      if (lane == 0) { while (*issued != seq) { __nanosleep(20); } }
-      __syncwarp();
       mbar_wait(empty + stage, phase ^ 1);
       K1_PROF_ADD(0)
+      const K1Slot& sl = slots[slot];
+      const bool staged = sl.tl.mode == MODE_STAGED;
+      const bool fix = staged && sl.tl.fix_hi > sl.tl.fix_lo;
       if (lane == 0) {
-        const K1Slot& sl = slots[slot];
-        if (sl.tl.mode == MODE_STAGED) {
+        if (staged) {
           const int mo0 = sl.ctx.it.tmap_off[0] - sl.tl.mconst[0], mo1 = sl.ctx.it.tmap_off[1] - sl.tl.mconst[1],
                     mo2 = sl.ctx.it.tmap_off[2] - sl.tl.mconst[2];
+          uint64_t* bar = fix ? landed + stage : full + stage;
           tmap_acquire(items[sl.tl.item].tmap);
-          mbar_expect_tx(full + stage, static_cast<uint32_t>(sl.tl.box[0] * sl.tl.box[1] * sl.tl.box[2] * 4));
-          tma_load_3d(smem + static_cast<size_t>(stage) * stage_bytes, items[sl.tl.item].tmap, full + stage, mo2, mo1, mo0);
+          mbar_expect_tx(bar, static_cast<uint32_t>(sl.tl.box[0] * sl.tl.box[1] * sl.tl.box[2] * 4));
+          tma_load_3d(smem + static_cast<size_t>(stage) * stage_bytes, items[sl.tl.item].tmap, bar, mo2, mo1, mo0);
         } else {
           mbar_arrive(full + stage);
         }
-        __threadfence_block();
-        *issued = seq + 1;
       }
       __syncwarp();
-      K1_PROF_ADD(1)
-      seq += K1_PWARPS;
-      for (int j = 0; j < K1_PWARPS; ++j) {
-        if (++stage == n_stages) { stage = 0; phase ^= 1; }
-        if (++slot == n_slots) slot = 0;
+      // complete the previous tile's fix-up now that this tile's load is in flight as well
+      if (pend_stage >= 0) {
+        mbar_wait(landed + pend_stage, (landed_phase >> pend_stage) & 1u);
+        landed_phase ^= 1u << pend_stage;
+        k1_fix_columns(reinterpret_cast<float*>(smem + static_cast<size_t>(pend_stage) * stage_bytes), slots[pend_slot].tl, lane);
+        if (lane == 0) mbar_arrive(full + pend_stage);
+        pend_stage = -1;
       }
-      tile += K1_PWARPS * gridDim.x;
+      if (fix) { pend_stage = stage; pend_slot = slot; }
+      if (fix && n_stages < 2) {  // a one-stage ring cannot defer: the next issue waits on this very tile
+        mbar_wait(landed + pend_stage, (landed_phase >> pend_stage) & 1u);
+        landed_phase ^= 1u << pend_stage;
+        k1_fix_columns(reinterpret_cast<float*>(smem + static_cast<size_t>(pend_stage) * stage_bytes), slots[pend_slot].tl, lane);
+        if (lane == 0) mbar_arrive(full + pend_stage);
+        pend_stage = -1;
+      }
+      K1_PROF_ADD(1)
+      if (++stage == n_stages) { stage = 0; phase ^= 1; }
+      if (++slot == n_slots) slot = 0;
+    }
+    if (pend_stage >= 0) {
+      mbar_wait(landed + pend_stage, (landed_phase >> pend_stage) & 1u);
+      k1_fix_columns(reinterpret_cast<float*>(smem + static_cast<size_t>(pend_stage) * stage_bytes), slots[pend_slot].tl, lane);
+      if (lane == 0) mbar_arrive(full + pend_stage);
     }
     return;
   }
@@ -751,7 +793,7 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
       const bool exact = (it.flags & (ADELL_F_STRICT | ADELL_F_CLIP)) != 0 || (ctx.pre_o != 0.0f && !tl.all_valid);
       if (exact) k1_tile_exact_dispatch<SmemTaps, false>(ctx, tl, box);
       else if (it.interp == ADELL_NEAREST) k1_tile_staged_nearest(ctx, tl, slots[slot].fast, box);
-      else k1_tile_staged_trilinear(ctx, tl, slots[slot].fast, box);
+      else k1_tile_staged_trilinear<K1_NV>(slots[slot].fast, box);
     } else if (it.flags & ADELL_F_IDENTITY) {
       k1_tile_exact_dispatch<GlobalTaps, true>(ctx, tl, nullptr);
     } else {
@@ -776,7 +818,7 @@ int k1_validate(const adell_item& it) {
   return ADELL_OK;
 }
 
-// ---- host: tensor-map encoding -------------------------------------------------------------
+// ---- host: per-item policy -------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -793,21 +835,51 @@ EncodeTiledFn k1_get_encode() {
   return cached;
 }
 
-// Decides staged-path eligibility for one item and, when eligible, encodes its tensor map over
-// the valid source box in memory order.  Returns the box bytes (0 = not staged).
-int k1_encode_item(adell_item& it, EncodeTiledFn enc) {
-  it.flags &= static_cast<uint8_t>(~ADELL_F_TMAP);
-  if (it.flags & ADELL_F_IDENTITY) return 0;
-  if (it.src_dtype != ADELL_F32) return 0;
-  if (it.src_stride[2] != 1 && it.src_stride[2] != -1) return 0;
-  int box[3];
-  int64_t cells = 1;
+// Identity item eligible for the 128-bit vector copy: fp32, unit step along axis 2, 16-byte
+// aligned rows on both sides, nothing invalid, no noise, no strict-order post map.
+bool k1_vcopy_ok(const adell_item& it) {
+  if (!(it.flags & ADELL_F_IDENTITY) || it.src_dtype != ADELL_F32) return false;
+  if ((it.src_stride[2] != 1 && it.src_stride[2] != -1) || it.dst_stride[2] != 1 || it.noise != nullptr) return false;
+  if ((it.flags & (ADELL_F_PHILOX | ADELL_F_STRICT)) || (it.out_shape[2] & 3) != 0) return false;
+  const bool rev = it.grid_sign[2] * it.src_stride[2] < 0;
+  for (int a = 0; a < 3; ++a) {
+    if (it.out_vlo[a] > 0 || it.out_vhi[a] < it.out_shape[a]) return false;
+    const int tlo = it.src_vlo[a] > 0 ? it.src_vlo[a] : 0;
+    const int thi = it.src_vhi[a] < it.src_shape[a] ? it.src_vhi[a] : it.src_shape[a];
+    const int ga = it.grid_off[a], gb = it.grid_off[a] + it.grid_sign[a] * (it.out_shape[a] - 1);
+    if ((ga < gb ? ga : gb) < tlo || (ga > gb ? ga : gb) >= thi) return false;
+  }
+  const int g2 = it.grid_off[2] + it.grid_sign[2] * (rev ? 3 : 0);
+  const int64_t e0 = g2 * it.src_stride[2];
+  const uintptr_t sp = reinterpret_cast<uintptr_t>(it.src);
+  if ((sp & 3u) != 0 || (((sp >> 2) + static_cast<uint64_t>(e0)) & 3u) != 0) return false;
+  if ((it.src_stride[0] & 3) || (it.src_stride[1] & 3) || (reinterpret_cast<uintptr_t>(it.dst) & 15u)) return false;
+  if ((it.dst_stride[0] & 3) || (it.dst_stride[1] & 3)) return false;
+  return true;
+}
+
+// fp64 coordinate of output voxel (0,0,0) and its derivative (same expressions the device used to
+// evaluate per tile): u_a(o) = (A_a . (g(o) - cg) + A_a3) * nrm_a*S_a/2 + (S_a-1)/2, g = off + sign*o.
+void k1_item_map(adell_item& it) {
+  double cc[3];
+  for (int b = 0; b < 3; ++b)
+    cc[b] = static_cast<double>(it.grid_off[b]) - static_cast<double>(static_cast<float>(it.grid_shape[b] - 1) * 0.5f);
   for (int a = 0; a < 3; ++a) {
     const double K = static_cast<double>(it.nrm[a]) * it.src_shape[a] * 0.5;
+    const float* A = it.A + 4 * a;
+    it.fp_U0[a] = (A[0] * cc[0] + A[1] * cc[1] + A[2] * cc[2] + A[3]) * K + (it.src_shape[a] - 1) * 0.5;
+    for (int b = 0; b < 3; ++b) it.fp_D[3 * a + b] = static_cast<double>(A[b]) * K * it.grid_sign[b];
+  }
+}
+
+// Footprint box of one T-shaped output tile; returns its bytes (0: not stageable).
+int64_t k1_box_for_tile(const adell_item& it, const int* T, int* box) {
+  int64_t cells = 1;
+  for (int a = 0; a < 3; ++a) {
     double span = 0.0;
     for (int b = 0; b < 3; ++b) {
-      const int tb = it.out_shape[b] < K1_T ? it.out_shape[b] : K1_T;
-      span += fabs(static_cast<double>(it.A[4 * a + b]) * K) * (tb - 1);
+      const int tb = it.out_shape[b] < T[b] ? it.out_shape[b] : T[b];
+      span += fabs(it.fp_D[3 * a + b]) * (tb - 1);
     }
     if (!(span < 4096.0)) return 0;
     box[a] = static_cast<int>(floor(span + 2 * K1_EPS)) + 3;
@@ -821,7 +893,35 @@ int k1_encode_item(adell_item& it, EncodeTiledFn enc) {
     if (box[a] > 256) return 0;
     cells *= box[a];
   }
-  if (cells * 4 > K1_MAX_BOX_BYTES) return 0;
+  return cells * 4;
+}
+
+// Decides staged-path eligibility for one item and, when eligible, picks its tile shape, encodes
+// its tensor map over the valid source box in memory order and fills the derived fields.
+// Returns the box bytes (0 = not staged, -1 = no driver).
+int k1_encode_item(adell_item& it, EncodeTiledFn enc, int tile_pref) {
+  it.flags &= static_cast<uint8_t>(~ADELL_F_TMAP);
+  if (it.flags & ADELL_F_IDENTITY) return 0;
+  if (it.src_dtype != ADELL_F32) return 0;
+  if (it.src_stride[2] != 1 && it.src_stride[2] != -1) return 0;
+  k1_item_map(it);
+  // tile shapes, most voxels per consumer thread first; a larger shape is taken only if its box
+  // leaves room for three ring stages, the base shape up to the two-stage limit
+  static const int kShapes[3][3] = {{16, 16, 32}, {16, 32, 16}, {16, 16, 16}};
+  int box[3] = {0, 0, 0}, T[3] = {16, 16, 16};
+  int64_t bytes = 0;
+  for (int s = 0; s < 3; ++s) {
+    if (tile_pref >= 0 && s != 2 && s != tile_pref) continue;
+    if (s == 0 && it.out_shape[2] <= 16) continue;
+    if (s == 1 && it.out_shape[1] <= 16) continue;
+    int bx[3];
+    const int64_t b = k1_box_for_tile(it, kShapes[s], bx);
+    if (b == 0 || b > (s == 2 ? K1_MAX_BOX_BYTES : K1_PREF_BOX_BYTES)) continue;
+    bytes = b;
+    for (int a = 0; a < 3; ++a) { box[a] = bx[a]; T[a] = kShapes[s][a]; }
+    break;
+  }
+  if (bytes == 0) return 0;
   // valid source box in t-space and its origin in memory order
   cuuint64_t gdim[3], gstride[2];
   int64_t base_off = 0;
@@ -839,11 +939,18 @@ int k1_encode_item(adell_item& it, EncodeTiledFn enc) {
     gdim[2 - a] = static_cast<cuuint64_t>(thi - tlo);     // tensor-map dims are innermost first
     it.tmap_box[a] = box[a];
   }
-  const uintptr_t base = reinterpret_cast<uintptr_t>(it.src) + static_cast<uintptr_t>(base_off * 4);
+  uintptr_t base = reinterpret_cast<uintptr_t>(it.src) + static_cast<uintptr_t>(base_off * 4);
   gstride[0] = static_cast<cuuint64_t>(astride[1]) * 4;
   gstride[1] = static_cast<cuuint64_t>(astride[0]) * 4;
-  if ((base & 15u) || (gstride[0] & 15u) || (gstride[1] & 15u)) return 0;
+  if ((base & 3u) || (gstride[0] & 15u) || (gstride[1] & 15u)) return 0;
   if (gstride[0] < gdim[0] * 4 || gstride[1] < gstride[0]) return 0;  // rows must not overlap
+  // a crop window may start anywhere in a row: align the tensor-map base down to 16 bytes; the
+  // 1..3 elements this prepends to every row are zeroed in shared memory after each load (fp_fix)
+  const int slack = static_cast<int>((base & 15u) >> 2);
+  base -= static_cast<uintptr_t>(slack) * 4;
+  gdim[0] += static_cast<cuuint64_t>(slack);
+  it.tmap_off[2] += slack;
+  it.fp_fix = slack;
   const cuuint32_t bdim[3] = {static_cast<cuuint32_t>(box[2]), static_cast<cuuint32_t>(box[1]), static_cast<cuuint32_t>(box[0])};
   const cuuint32_t estr[3] = {1, 1, 1};
   if (enc == nullptr) return -1;
@@ -851,9 +958,22 @@ int k1_encode_item(adell_item& it, EncodeTiledFn enc) {
                    reinterpret_cast<void*>(base), gdim, gstride, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return 0;
+  for (int a = 0; a < 3; ++a) {
+    it.tile_dim[a] = static_cast<uint8_t>(T[a]);
+    double smin = 0.0, smax = 0.0;
+    for (int b = 0; b < 3; ++b) {
+      const int tb = it.out_shape[b] < T[b] ? it.out_shape[b] : T[b];
+      const double span = it.fp_D[3 * a + b] * (tb - 1);
+      if (span < 0) smin += span; else smax += span;
+    }
+    // rounded outwards so the fp32 copies never under-estimate the footprint
+    it.fp_smin[a] = nextafterf(static_cast<float>(smin), -INFINITY);
+    it.fp_smax[a] = nextafterf(static_cast<float>(smax), INFINITY);
+  }
   it.tmap_base = reinterpret_cast<const void*>(base);
   it.flags |= ADELL_F_TMAP;
-  return static_cast<int>(cells * 4);
+  it.kind = ADELL_KIND_STAGED;
+  return static_cast<int>(bytes);
 }
 
 }  // namespace
@@ -866,19 +986,35 @@ extern "C" int adell_aug_prepare(adell_item* items_host, int n_items, int32_t* t
   bool enc_tried = false;
   const char* dis = getenv("ADELL_DISABLE_STAGED");  // debugging aid: force the direct path
   const bool no_staged = dis != nullptr && dis[0] == '1';
+  const char* tp = getenv("ADELL_K1_TILE");          // tuning aid: 0 = 16x16x32, 1 = 16x32x16, 2 = 16x16x16 only
+  const int tile_pref = (tp != nullptr && tp[0] >= '0' && tp[0] <= '2') ? tp[0] - '0' : -1;
   for (int i = 0; i < n_items; ++i) {
-    int st = k1_validate(items_host[i]);
+    adell_item& it = items_host[i];
+    int st = k1_validate(it);
     if (st != ADELL_OK) return st;
     if (!enc_tried && !no_staged) { enc = k1_get_encode(); enc_tried = true; }
+    it.kind = ADELL_KIND_GENERIC;
+    it.tile_dim[0] = it.tile_dim[1] = it.tile_dim[2] = K1_T;
+    it.fp_fix = 0;
     int bytes = 0;
-    if (no_staged) items_host[i].flags &= static_cast<uint8_t>(~ADELL_F_TMAP);
-    else bytes = k1_encode_item(items_host[i], enc);
+    if (k1_vcopy_ok(it)) {
+      it.flags &= static_cast<uint8_t>(~ADELL_F_TMAP);
+      it.kind = ADELL_KIND_VCOPY;
+      it.tile_dim[0] = 32; it.tile_dim[1] = 16; it.tile_dim[2] = 32;
+    } else if (no_staged) {
+      it.flags &= static_cast<uint8_t>(~ADELL_F_TMAP);
+    } else {
+      bytes = k1_encode_item(it, enc, tile_pref);
+    }
     if (bytes < 0) return ADELL_ERR_NO_DRIVER;
     if (bytes > 0) { ++staged; if (bytes > smem) smem = bytes; }
-    int n0, n1, n2;
-    k1_tile_counts(items_host[i].out_shape, n0, n1, n2);
+    int64_t n = 1;
+    for (int a = 0; a < 3; ++a) {
+      it.n_tiles[a] = (it.out_shape[a] + it.tile_dim[a] - 1) / it.tile_dim[a];
+      n *= it.n_tiles[a];
+    }
     tile_start_host[i] = static_cast<int32_t>(acc);
-    acc += static_cast<int64_t>(n0) * n1 * n2;
+    acc += n;
     if (acc > 0x7fffffffLL) return ADELL_ERR_BAD_ARG;
   }
   tile_start_host[n_items] = static_cast<int32_t>(acc);
@@ -903,8 +1039,8 @@ extern "C" int adell_aug_gather(const adell_item* items_dev, const int32_t* tile
   if (e != cudaSuccess) { (void)cudaGetLastError(); return adell_map_cuda_error(e); }
   // ring of staged boxes: as many stages as fit next to the per-stage tile state
   const int stage_bytes = (info->smem_bytes + 127) & ~127;
-  const int per_stage = stage_bytes + static_cast<int>(sizeof(K1Slot)) + 16;  // box + tile state + 2 mbarriers
-  const int fixed = static_cast<int>(K1_PWARPS * (sizeof(K1Slot) + sizeof(K1Ctx))) + 16;
+  const int per_stage = stage_bytes + static_cast<int>(sizeof(K1Slot)) + 24;  // box + tile state + 3 mbarriers
+  const int fixed = static_cast<int>(sizeof(K1Slot) + sizeof(K1Ctx)) + 64;
   int n_stages = (K1_SMEM_BUDGET - fixed) / per_stage;
   if (n_stages > K1_MAX_STAGES) n_stages = K1_MAX_STAGES;
   if (n_stages < 1) return ADELL_ERR_BAD_ARG;

@@ -18,11 +18,11 @@ struct K1Ctx {
   int tlo[3];     // max(0, src_vlo)
   int thi[3];     // min(S, src_vhi)
   float pre_s, pre_o;
-  int copy_ok;    // identity item eligible for the 128-bit vector copy (decided once per item)
 };
 
 __device__ __forceinline__ void k1_ctx_finish(K1Ctx& c) {
-  // called by one thread after the raw item has been copied into c.it
+  // called by one thread after the raw item has been copied into c.it (the vector-copy
+  // eligibility that used to be decided here is now adell_item.kind, set by adell_aug_prepare)
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     c.cg[a] = static_cast<float>(c.it.grid_shape[a] - 1) * 0.5f;
@@ -30,29 +30,6 @@ __device__ __forceinline__ void k1_ctx_finish(K1Ctx& c) {
     c.Sm1[a] = static_cast<float>(c.it.src_shape[a] - 1);
     c.tlo[a] = max(0, c.it.src_vlo[a]);
     c.thi[a] = min(c.it.src_shape[a], c.it.src_vhi[a]);
-  }
-  {
-    // vector copy needs: identity, fp32, unit step along axis 2, 16-byte aligned rows, nothing
-    // invalid, no noise, no strict-order post map
-    const adell_item& it = c.it;
-    bool ok = (it.flags & ADELL_F_IDENTITY) && it.src_dtype == ADELL_F32 &&
-              (it.src_stride[2] == 1 || it.src_stride[2] == -1) && it.dst_stride[2] == 1 && it.noise == nullptr &&
-              !(it.flags & (ADELL_F_PHILOX | ADELL_F_STRICT)) && (it.out_shape[2] & 3) == 0;
-    const bool rev = it.grid_sign[2] * it.src_stride[2] < 0;
-    for (int a = 0; a < 3 && ok; ++a) {
-      ok = ok && it.out_vlo[a] <= 0 && it.out_vhi[a] >= it.out_shape[a];
-      const int ga = it.grid_off[a], gb = it.grid_off[a] + it.grid_sign[a] * (it.out_shape[a] - 1);
-      ok = ok && min(ga, gb) >= c.tlo[a] && max(ga, gb) < c.thi[a];
-    }
-    if (ok) {
-      const int g2 = it.grid_off[2] + it.grid_sign[2] * (rev ? 3 : 0);
-      const int64_t e0 = g2 * it.src_stride[2];
-      ok = ((reinterpret_cast<uintptr_t>(it.src) & 3u) == 0) &&
-           (((reinterpret_cast<uintptr_t>(it.src) >> 2) + static_cast<uint64_t>(e0)) & 3u) == 0 &&
-           (it.src_stride[0] & 3) == 0 && (it.src_stride[1] & 3) == 0 && (reinterpret_cast<uintptr_t>(it.dst) & 15u) == 0 &&
-           (it.dst_stride[0] & 3) == 0 && (it.dst_stride[1] & 3) == 0;
-    }
-    c.copy_ok = ok ? 1 : 0;
   }
   if (c.it.flags & ADELL_F_PRE_DEV) {
     c.pre_s = c.it.pre_dev[0];

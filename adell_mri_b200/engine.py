@@ -18,6 +18,8 @@ import torch
 from . import _lib
 from .plan import ITEM_DTYPE, BatchPlan
 
+ISZ = _lib.ITEM_SIZE
+
 #: number of K1 launches issued so far in this process (bench.py reports the delta per step)
 launch_count = 0
 
@@ -70,14 +72,14 @@ def _require_cuda(device: torch.device):
 
 def pack_launch(items: np.ndarray):
     """Host-side preparation of one launch: encodes the TMA descriptors of the eligible items
-    (``adell_aug_prepare``) and packs ``items (512 B each) + int32 tile prefix (n+1)`` into one
+    (``adell_aug_prepare``) and packs ``items (640 B each) + int32 tile prefix (n+1)`` into one
     buffer.  Returns ``(uint8 buffer, n_items, LaunchInfo)``."""
     lib = _lib.load()
     n = items.shape[0]
-    buf = np.empty(n * 512 + 4 * (n + 1), np.uint8)
-    it = buf[: n * 512].view(ITEM_DTYPE)
+    buf = np.empty(n * ISZ + 4 * (n + 1), np.uint8)
+    it = buf[: n * ISZ].view(ITEM_DTYPE)
     it[:] = items
-    tiles = buf[n * 512 :].view(np.int32)
+    tiles = buf[n * ISZ :].view(np.int32)
     info = _lib.LaunchInfo()
     _lib.check(lib.adell_aug_prepare(it.ctypes.data, n, tiles.ctypes.data, C.byref(info)), "adell_aug_prepare")
     return buf, n, info
@@ -90,7 +92,7 @@ def launch_packed(buf_dev: torch.Tensor, n: int, info, stream: int | None = None
     if stream is None:
         stream = torch.cuda.current_stream(buf_dev.device).cuda_stream
     base = buf_dev.data_ptr()
-    _lib.check(lib.adell_aug_gather(base, base + n * 512, n, C.byref(info), C.c_void_p(stream)), "adell_aug_gather")
+    _lib.check(lib.adell_aug_gather(base, base + n * ISZ, n, C.byref(info), C.c_void_p(stream)), "adell_aug_gather")
     launch_count += lib.adell_aug_gather_launches()
 
 
@@ -158,22 +160,22 @@ def prepare_steps(plan: BatchPlan, dst_ptr: np.ndarray, dst_stride: np.ndarray, 
     sizes = [int(x) for x in step_sizes]
     if sum(sizes) != items.shape[0]:
         raise ValueError("step_sizes must add up to the number of volumes")
-    # layout per step: items (512 B each) + int32 prefix, padded to 512 B so every slice stays aligned
+    # layout per step: items (640 B each) + int32 prefix, padded to 128 B so every slice stays aligned
     offs, total = [], 0
     for n in sizes:
         offs.append(total)
-        total += n * 512 + ((4 * (n + 1) + 511) // 512) * 512
+        total += n * ISZ + ((4 * (n + 1) + 127) // 128) * 128
     buf = np.zeros(total, np.uint8)
     infos, start = [], 0
     for n, o in zip(sizes, offs):
-        it = buf[o : o + n * 512].view(ITEM_DTYPE)
+        it = buf[o : o + n * ISZ].view(ITEM_DTYPE)
         it[:] = items[start : start + n]
-        tiles = buf[o + n * 512 : o + n * 512 + 4 * (n + 1)].view(np.int32)
+        tiles = buf[o + n * ISZ : o + n * ISZ + 4 * (n + 1)].view(np.int32)
         info = _lib.LaunchInfo()
         _lib.check(lib.adell_aug_prepare(it.ctypes.data, n, tiles.ctypes.data, C.byref(info)), "adell_aug_prepare")
         infos.append(info)
         start += n
     with torch.cuda.device(plan.device):
         dev = _stage(buf, plan.device)
-    launches = [(dev[o : o + n * 512 + 4 * (n + 1)], n, info) for n, o, info in zip(sizes, offs, infos)]
+    launches = [(dev[o : o + n * ISZ + 4 * (n + 1)], n, info) for n, o, info in zip(sizes, offs, infos)]
     return PreparedSteps(launches, [dev, plan] + list(keep or []))

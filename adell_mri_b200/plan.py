@@ -30,7 +30,7 @@ from . import _lib
 from ._lib import Item
 
 ITEM_DTYPE = np.dtype(Item)
-assert ITEM_DTYPE.itemsize == 512
+assert ITEM_DTYPE.itemsize == _lib.ITEM_SIZE
 
 _TORCH_TO_ADELL = {torch.float32: _lib.F32, torch.int16: _lib.I16, torch.uint8: _lib.U8}
 _ELSIZE = {_lib.F32: 4, _lib.I16: 2, _lib.U8: 1}

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define ADELL_ABI_VERSION 1
+#define ADELL_ABI_VERSION 2
 
 /* status codes */
 #define ADELL_OK 0
@@ -122,8 +122,24 @@ typedef struct __attribute__((aligned(64))) adell_item {
   float post_scale, post_offset, noise_std;
   uint64_t philox_seed, philox_offset;
   uint8_t src_dtype, interp, padding, flags;
-  uint8_t reserved[44]; /* pads the struct to 512 bytes */
+  /* ---- derived by adell_aug_prepare; callers leave these zero ------------------------------ */
+  uint8_t tile_dim[3];     /* output tile extents of this item along axes 0,1,2                     */
+  uint8_t kind;            /* ADELL_KIND_*: which K1 path the item's tiles take                     */
+  int32_t n_tiles[3];      /* ceil(out_shape / tile_dim)                                            */
+  float fp_smin[3];        /* staged path: footprint of a full tile relative to its origin voxel,   */
+  float fp_smax[3];        /*   per source axis (sum of negative / positive D*(tile_dim-1) terms)    */
+  int32_t fp_fix;          /* staged path: leading columns (axis 2, box order) of the tensor map
+                              that lie before the valid source box (16-byte alignment slack); they
+                              are zeroed in shared memory after the TMA load                         */
+  double fp_U0[3];         /* un-padded source coordinate of output voxel (0,0,0), fp64             */
+  double fp_D[9];          /* d(source coordinate a)/d(output index b), row-major [a][b], fp64      */
+  uint8_t reserved[32];    /* pads the struct to 640 bytes */
 } adell_item;
+
+/* adell_item.kind */
+#define ADELL_KIND_GENERIC 0 /* bit-faithful per-voxel path, taps from global memory               */
+#define ADELL_KIND_STAGED 1  /* TMA-staged source footprint, taps from shared memory               */
+#define ADELL_KIND_VCOPY 2   /* identity item: 128-bit vectorised flip/crop copy                   */
 
 /* -- library / device ---------------------------------------------------------------- */
 int adell_abi_version(void);
@@ -139,7 +155,7 @@ int adell_mat4_chain(const float* mats, int batch, int k, float* out);
 /* -- K1: fused gather ----------------------------------------------------------------- */
 /* What the host learned while preparing one launch. */
 typedef struct adell_launch_info {
-  int64_t total_tiles; /* grid size (one CTA per 16x16x16 output tile)                         */
+  int64_t total_tiles; /* output tiles over all items (per-item tile extents: adell_item.tile_dim) */
   int32_t smem_bytes;  /* dynamic shared memory = largest staged source box among the items     */
   int32_t n_staged;    /* items eligible for the TMA-staged path                                */
 } adell_launch_info;

@@ -1,0 +1,164 @@
+"""K1 launch-time microbenchmark (device-resident parameters, CUDA events on the launching stream).
+
+  python tools/k1_micro.py [--prof] [workload ...]
+
+Workloads: seg (reference probabilities), seg_all_affine, seg_copy (no affine ever fires: pure
+flip copies), ssl (config C, two views, zeros padding), cls (config D, 208x208x64 -> 192x192x48).
+`--prof` loads libadell_b200_prof.so (built with -DK1_PROFILE) and prints its cycle counters.
+"""
+import ctypes
+import os
+import statistics
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from adell_mri_b200 import _lib
+
+PROF = "--prof" in sys.argv
+if PROF:
+    _lib.LIB_PATH = os.path.join(os.path.dirname(_lib.LIB_PATH), "libadell_b200_prof.so")
+from adell_mri_b200 import engine, geometry
+from adell_mri_b200.plan import BatchPlan
+
+dev = torch.device("cuda:0")
+PEAK = 6541.1
+
+
+def seg_items(R, prob, n_batches=4, B=8, shape=(256, 256, 32)):
+    g = torch.Generator(device=dev).manual_seed(0)
+    out_img = torch.empty((B, 3, *shape), device=dev)
+    out_mask = torch.empty((B, 1, *shape), device=dev)
+    launches = []
+    keep = [out_img, out_mask]
+    for _ in range(n_batches):
+        vols, mats, fired, flips, dsts = [], [], [], [], []
+        for b in range(B):
+            f = R.rand() < prob
+            ang = R.uniform(-1, 1, 3) * np.array([np.pi / 8, np.pi / 8, np.pi / 16])
+            A = geometry.compose_affine(rotate=ang[None])[0]
+            fl = R.rand(3) < 0.25
+            for k in range(4):
+                vols.append(torch.rand(shape, device=dev, generator=g))
+                mats.append(A); fired.append(f); flips.append(fl)
+                dsts.append(out_img[b, k] if k < 3 else out_mask[b, 0])
+        plan = BatchPlan(vols)
+        plan.affine(np.stack(mats), (["bilinear"] * 3 + ["nearest"]) * B, "reflection", where=np.array(fired))
+        plan.flip(np.stack(flips))
+        launches.append(pack(plan, dsts))
+        keep.append(vols)
+    return launches, B * 4 * int(np.prod(shape)), keep
+
+
+def ssl_items(R, n_batches=2, B=64, src=(160, 160, 40), roi=(128, 128, 32)):
+    g = torch.Generator(device=dev).manual_seed(0)
+    o1 = torch.empty((B, 1, *roi), device=dev)
+    o2 = torch.empty((B, 1, *roi), device=dev)
+    launches, keep = [], [o1, o2]
+    for _ in range(n_batches):
+        vols, mats, starts, dsts = [], [], [], []
+        for b in range(B):
+            v = torch.rand(src, device=dev, generator=g)
+            st = [R.randint(s - r + 1) for s, r in zip(src, roi)]
+            for view in range(2):
+                rot = np.zeros(3); rot[R.randint(3)] = R.uniform(-1, 1) * (np.pi / 12)
+                tr = np.zeros(3); tr[R.randint(3)] = R.uniform(-15, 15)
+                A = geometry.compose_affine(rotate=rot[None], translate=tr[None])[0]
+                vols.append(v); mats.append(A); starts.append(st)
+                dsts.append((o1 if view == 0 else o2)[b, 0])
+        plan = BatchPlan(vols)
+        plan.crop(np.array(starts), roi)
+        plan.affine(np.stack(mats), "bilinear", "zeros")
+        plan.intensity(scale=1.1, offset=0.05)
+        launches.append(pack(plan, dsts))
+        keep.append(vols)
+    return launches, B * 2 * int(np.prod(roi)), keep
+
+
+def cls_items(R, n_batches=2, B=32, src=(208, 208, 64), crop=(192, 192, 48), K=3):
+    g = torch.Generator(device=dev).manual_seed(0)
+    out = torch.empty((B, K + 1, *crop), device=dev)
+    launches, keep = [], [out]
+    for _ in range(n_batches):
+        vols, mats, flips, dsts, modes = [], [], [], [], []
+        for b in range(B):
+            rot = np.array([R.uniform(-1, 1) * np.pi / 16])
+            tr = R.uniform(-1, 1, 3) * np.array([4, 4, 1])
+            sc = 1 + R.uniform(-1, 1, 3) * np.array([0.1, 0.1, 0.05])
+            A = geometry.compose_affine(rotate=rot[None], translate=tr[None], scale=sc[None])[0]
+            fl = R.rand(3) < 0.3
+            for k in range(K + 1):
+                vols.append(torch.rand(src, device=dev, generator=g))
+                mats.append(A); flips.append(fl); dsts.append(out[b, k])
+                modes.append("bilinear" if k < K else "nearest")
+        plan = BatchPlan(vols)
+        plan.flip(np.stack(flips))
+        plan.affine(np.stack(mats), modes, "zeros")
+        plan.center_crop(crop)
+        launches.append(pack(plan, dsts))
+        keep.append(vols)
+    return launches, B * (K + 1) * int(np.prod(crop)), keep
+
+
+def pack(plan, dsts):
+    dst_ptr = np.array([d.data_ptr() for d in dsts], np.uint64)
+    dst_stride = np.array([d.stride() for d in dsts], np.int64)
+    items = plan.build_launches(dst_ptr, dst_stride, None)[-1]
+    buf, n, info = engine.pack_launch(items)
+    return torch.from_numpy(buf).to(dev), n, info, plan
+
+
+def time_launches(launches, reps=5):
+    st = torch.cuda.current_stream()
+    for (buf, n, info, _) in launches:
+        engine.launch_packed(buf, n, info)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        for (buf, n, info, _) in launches:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(st); engine.launch_packed(buf, n, info); b.record(st)
+            ts.append((a, b))
+    torch.cuda.synchronize()
+    return [a.elapsed_time(b) for a, b in ts]
+
+
+def main():
+    names = [a for a in sys.argv[1:] if not a.startswith("--")] or ["seg", "seg_all_affine", "seg_copy", "ssl", "cls"]
+    lib = _lib.load()
+    if PROF:
+        lib.adell_debug_prof.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    for name in names:
+        R = np.random.RandomState(7)
+        if name == "seg":
+            L, vox, keep = seg_items(R, 0.2)
+        elif name == "seg_all_affine":
+            L, vox, keep = seg_items(R, 1.0)
+        elif name == "seg_copy":
+            L, vox, keep = seg_items(R, 0.0)
+        elif name == "ssl":
+            L, vox, keep = ssl_items(R)
+        elif name == "cls":
+            L, vox, keep = cls_items(R)
+        else:
+            raise SystemExit(name)
+        if PROF:
+            out = (ctypes.c_ulonglong * 8)()
+            lib.adell_debug_prof(out, 1)
+        ts = time_launches(L)
+        ms = statistics.mean(ts)
+        gbs = 8.0 * vox / (ms * 1e-3) / 1e9
+        print(f"{name}: {ms:.4f} ms/launch (min {min(ts):.4f}), {vox/ms/1e6:.1f} Gvox/s, {gbs:.0f} GB/s algorithmic = {gbs/PEAK:.3f} of measured peak; "
+              f"staged items {L[0][2].n_staged}/{L[0][1]}, smem {L[0][2].smem_bytes}")
+        if PROF:
+            lib.adell_debug_prof(out, 1)
+            v = list(out)
+            print("   cycles summed over warps: prod wait-empty %d, issue %d, prepare %d | cons wait-full %d, compute %d" % tuple(v[:5]))
+        del L, keep
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
