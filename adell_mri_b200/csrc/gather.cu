@@ -260,23 +260,22 @@ __device__ __noinline__ void k1_tile_exact_dispatch(const K1Ctx& c, const K1Tile
 }
 
 // ------------------------------------------------------------------------- staged fast paths
-// Tile-local incremental coordinates: v_a = V0_a + Dm_a0*di + Dm_a1*dj + Dm_a2*dk is the
-// box-local (memory order) source coordinate; floor/frac/lerp directly on it.  Everything the
-// inner loop needs is copied into registers first: the output stores go through a generic
-// pointer, so the compiler would otherwise reload every shared-memory field per voxel.
+// Tile-local incremental coordinates: v_a = V0_a + D0_a*di + D1_a*dj + D2_a*dk is the box-local
+// (memory order) source coordinate; floor/frac/lerp directly on it.  The producer lays the
+// consumers' register image out in 16-byte groups, so a consumer thread fetches it with a
+// handful of broadcast LDS.128 per tile.
 struct __align__(16) K1Fast {
-  float V0[3], D0[3], D1[3], D2[3];
-  float Sf[3], Sm1[3], rA[3], rB[3];
-  int vlo[3], vhi[3];    // valid output range, tile-local
-  float p0f, p1f, gain, bias, post_o, noise_std;
-  int p0, p1;
-  int n0, n1, n2;        // voxels of the tile along each axis
-  int kw;                // tile extent along axis 2 (16 or 32): lanes of a warp along that axis
-  int rmask, pad;        // per-voxel border / reflection handling (axes in rmask)
-  int philox, padded;
+  float4 ax[3];          // per source axis a: {V0_a, D0_a, D1_a, D2_a}
+  float4 gb;             // gain, bias, post_offset, noise_std
+  int4 n;                // n0, n1, n2 (voxels of the tile along each axis), kw (16 or 32 lanes along axis 2)
+  int4 m;                // p0, p1 (box pitches in elements), rmask | padding mode << 8, cbase: tap byte address =
+                         // cbase + 4*(bits0*p0 + bits1*p1 + bits2), bits = float bits of coordinate + MAGIC
+  int4 fl;               // cold (padded | noise | philox), padded, philox, -
+  float4 rf[3];          // per source axis a: {S_a, S_a-1, rA_a, rB_a} (axes in rmask)
+  int4 vlo, vhi;         // valid output range, tile-local
   float* dst;            // tile origin in the destination
   const float* noise;    // tile origin in the noise tensor (or null)
-  int64_t ds0, ds1, ds2;
+  int64_t ds0, ds1, ds2; // destination strides (elements)
   int64_t ns0, ns1;      // noise strides (contiguous [O0,O1,O2])
   uint64_t olin0;        // linear output index of the tile origin (Philox counter)
   uint64_t philox_seed, philox_offset;
@@ -292,7 +291,10 @@ __device__ __noinline__ float k1_fast_reflect_far(float x, float Sf) {
 __device__ __forceinline__ float k1_fast_pad(float u, int pad, float Sf, float Sm1) {
   if (pad == ADELL_PAD_REFLECTION) {
     float x = fabsf(u + 0.5f);
-    if (x >= Sf) x = k1_fast_reflect_far(x, Sf);
+    if (x >= Sf) {              // beyond the upper edge: first mirrored period inline, the rest out of line
+      x = 2.0f * Sf - x;
+      if (x < 0.0f) x = k1_fast_reflect_far(2.0f * Sf - x, Sf);
+    }
     u = x - 0.5f;
   }
   return fminf(Sm1, fmaxf(u, 0.0f));
@@ -313,95 +315,47 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
   return v;
 }
 
-// Hot register image of a staged tile (everything else stays in the shared-memory K1Fast and is
-// only touched on the rare padded / noise paths).
+// Per-thread register image of a staged tile.
+template <bool RMASK>
 struct K1Hot {
-  float D1[3], P[3];
-  float Sf[3], Sm1[3], rA[3], rB[3];
+  float D1[3], P[3];      // coordinate along dj: v_a = P_a + D1_a * dj
   float gain, bias;
-  uint32_t p0, p1, cbase;   // tap address = cbase + 4*(bits0*p0 + bits1*p1 + bits2), bits = float bits of x + MAGIC
-  int rmask, pad, n1;
-  int64_t ds1;
-  float* drow;
-  bool cold;  // padded output region or noise: take the slow store
+  uint32_t p0, p1, cbase; // tap address = cbase + 4*(bits0*p0 + bits1*p1 + bits2), bits = float bits of x + MAGIC
+  float Sf[3], Sm1[3], rA[3], rB[3];
+  int rmask, pad;
 };
 
-__device__ __forceinline__ K1Hot k1_hot_load(const K1Fast& f, int di, int dk, uint32_t box_addr) {
-  K1Hot h;
+template <bool RMASK>
+__device__ __forceinline__ void k1_hot_load(K1Hot<RMASK>& h, const K1Fast& f, int di, int dk) {
   const float fk = static_cast<float>(dk), fi = static_cast<float>(di);
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    h.D1[a] = f.D1[a];
-    h.P[a] = fmaf(f.D0[a], fi, fmaf(f.D2[a], fk, f.V0[a]));
-    h.Sf[a] = f.Sf[a]; h.Sm1[a] = f.Sm1[a]; h.rA[a] = f.rA[a]; h.rB[a] = f.rB[a];
+    const float4 q = f.ax[a];
+    h.D1[a] = q.z;
+    h.P[a] = fmaf(q.y, fi, fmaf(q.w, fk, q.x));
   }
-  h.gain = f.gain; h.bias = f.bias;
-  h.p0 = static_cast<uint32_t>(f.p0); h.p1 = static_cast<uint32_t>(f.p1);
-  h.cbase = box_addr - 4u * (K1_MAGIC_BITS * (h.p0 + h.p1 + 1u));  // modulo 2^32 on purpose
-  h.rmask = f.rmask; h.pad = f.pad; h.n1 = f.n1;
-  h.ds1 = f.ds1;
-  h.drow = f.dst + di * f.ds0 + dk * f.ds2;
-  h.cold = f.padded || f.noise != nullptr || f.philox;
-  return h;
+  const float4 gb = f.gb;
+  const int4 m = f.m;
+  h.gain = gb.x; h.bias = gb.y;
+  h.p0 = static_cast<uint32_t>(m.x); h.p1 = static_cast<uint32_t>(m.y);
+  h.cbase = static_cast<uint32_t>(m.w);  // computed by the producer (modulo 2^32 on purpose)
+  if (RMASK) {
+    h.rmask = m.z & 0xff; h.pad = m.z >> 8;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float4 q = f.rf[a];
+      h.Sf[a] = q.x; h.Sm1[a] = q.y; h.rA[a] = q.z; h.rB[a] = q.w;
+    }
+  }
 }
 
-__device__ __forceinline__ void k1_fast_coords(const K1Hot& h, int dj, float& v0, float& v1, float& v2) {
-  const float fj = static_cast<float>(dj);
+template <bool RMASK>
+__device__ __forceinline__ void k1_fast_coords(const K1Hot<RMASK>& h, float fj, float& v0, float& v1, float& v2) {
   v0 = fmaf(h.D1[0], fj, h.P[0]); v1 = fmaf(h.D1[1], fj, h.P[1]); v2 = fmaf(h.D1[2], fj, h.P[2]);
-  if (h.rmask) {  // block-uniform: some axis leaves [0,S) inside this tile
+  if (RMASK) {  // block-uniform: some axis leaves [0,S) inside this tile
     if (h.rmask & 1) v0 = fmaf(h.rA[0], k1_fast_pad(v0, h.pad, h.Sf[0], h.Sm1[0]), h.rB[0]);
     if (h.rmask & 2) v1 = fmaf(h.rA[1], k1_fast_pad(v1, h.pad, h.Sf[1], h.Sm1[1]), h.rB[1]);
     if (h.rmask & 4) v2 = fmaf(h.rA[2], k1_fast_pad(v2, h.pad, h.Sf[2], h.Sm1[2]), h.rB[2]);
-  }
-}
-
-// rare: output pad band (SpatialPadd after the resample), injected or Philox noise
-__device__ __noinline__ void k1_cold_store(const K1Fast& f, float* p, int di, int dj, int dk, float val) {
-  if (f.padded) {
-    const bool ov = (di >= f.vlo[0]) & (di < f.vhi[0]) & (dj >= f.vlo[1]) & (dj < f.vhi[1]) & (dk >= f.vlo[2]) & (dk < f.vhi[2]);
-    if (!ov) val = f.post_o;
-  }
-  const int64_t rel = di * f.ns0 + dj * f.ns1 + dk;
-  if (f.noise != nullptr) val = __fadd_rn(val, __ldg(f.noise + rel));
-  if (f.philox) val = fmaf(f.noise_std, adell_philox_normal(f.philox_seed, f.philox_offset + f.olin0 + rel), val);
-  *p = val;
-}
-
-__device__ __forceinline__ void k1_fast_store(const K1Fast& f, const K1Hot& h, int di, int dj, int dk, float val) {
-  float* p = h.drow + dj * h.ds1;
-  if (h.cold) k1_cold_store(f, p, di, dj, dk, val);
-  else *p = val;
-}
-
-// lane -> (dk, first dj, dj step): 32 lanes along axis 2 for 32-wide tiles, else 16 x 2 rows
-__device__ __forceinline__ void k1_lane_map(const K1Fast& f, int& dk, int& jj, int& jstep) {
-  const int lane = threadIdx.x & 31;
-  if (f.kw == 32) { dk = lane; jj = 0; jstep = 1; }
-  else { dk = lane & 15; jj = lane >> 4; jstep = 2; }
-}
-
-__device__ __forceinline__ void k1_tile_staged_nearest(const K1Ctx& c, const K1Tile& tl, const K1Fast& f, const float* __restrict__ box) {
-  int dk, jj, jstep;
-  k1_lane_map(f, dk, jj, jstep);
-  const int di = threadIdx.x >> 5;
-  if (dk >= f.n2 || di >= f.n0) return;
-  const K1Hot h = k1_hot_load(f, di, dk, smem_u32(box));
-  const float tie = 0.5f - static_cast<float>(K1_EPS);
-#pragma unroll 2
-  for (int dj = jj; dj < h.n1; dj += jstep) {
-    float v0, v1, v2;
-    k1_fast_coords(h, dj, v0, v1, v2);
-    // rint (ties to even) on the FMA pipe: x + 1.5*2^23 rounds to the nearest integer
-    const float t0 = __fadd_rn(v0, K1_MAGIC), t1 = __fadd_rn(v1, K1_MAGIC), t2 = __fadd_rn(v2, K1_MAGIC);
-    const float n0 = t0 - K1_MAGIC, n1 = t1 - K1_MAGIC, n2 = t2 - K1_MAGIC;
-    float val;
-    if (fabsf(v0 - n0) > tie || fabsf(v1 - n1) > tie || fabsf(v2 - n2) > tie) {
-      val = k1_exact_nearest_smem(c, tl, box, di, dj, dk);  // within 1e-3 of a rounding tie
-    } else {
-      const uint32_t a = h.cbase + 4u * (__float_as_uint(t0) * h.p0 + __float_as_uint(t1) * h.p1 + __float_as_uint(t2));
-      val = fmaf(lds_f32(a), h.gain, h.bias);
-    }
-    k1_fast_store(f, h, di, dj, dk, val);
   }
 }
 
@@ -410,9 +364,10 @@ struct K1Vox {
   uint32_t a;  // shared-memory byte address of tap (0,0,0)
 };
 
-__device__ __forceinline__ K1Vox k1_fast_vox(const K1Hot& h, int dj) {
+template <bool RMASK>
+__device__ __forceinline__ K1Vox k1_fast_vox(const K1Hot<RMASK>& h, float fj) {
   float v0, v1, v2;
-  k1_fast_coords(h, dj, v0, v1, v2);
+  k1_fast_coords<RMASK>(h, fj, v0, v1, v2);
   // floor on the FMA pipe: round-down add of 1.5*2^23 leaves floor(x) in the low mantissa bits
   const float t0 = __fadd_rd(v0, K1_MAGIC), t1 = __fadd_rd(v1, K1_MAGIC), t2 = __fadd_rd(v2, K1_MAGIC);
   K1Vox x;
@@ -428,25 +383,39 @@ __device__ __forceinline__ float k1_lerp8(const K1Vox& x, const float* t) {
   return fmaf(x.r0, y1 - y0, y0);
 }
 
-// NV voxels per iteration, all their shared-memory taps issued before any arithmetic that
-// depends on them (the loads are volatile asm so ptxas keeps them batched).
-template <int NV>
-__device__ __forceinline__ void k1_tile_staged_trilinear(const K1Fast& f, const float* __restrict__ box) {
+// lane -> (dk, first dj, dj step): 32 lanes along axis 2 for 32-wide tiles, else 16 x 2 rows
+__device__ __forceinline__ void k1_lane_map(int kw, int& dk, int& jj, int& jstep) {
+  const int lane = threadIdx.x & 31;
+  if (kw == 32) { dk = lane; jj = 0; jstep = 1; }
+  else { dk = lane & 15; jj = lane >> 4; jstep = 2; }
+}
+
+// Trilinear, plain tiles (no output pad band, no noise): NV voxels per iteration, all their
+// shared-memory taps issued before any arithmetic that depends on them (the loads are volatile
+// asm so ptxas keeps them batched); no per-voxel bounds checks — a thread's voxel count is split
+// into full groups and a one-at-a-time tail.
+template <int NV, bool RMASK>
+__device__ __forceinline__ void k1_tile_staged_trilinear(const K1Fast& f) {
+  const int4 n = f.n;
   int dk, jj, jstep;
-  k1_lane_map(f, dk, jj, jstep);
+  k1_lane_map(n.w, dk, jj, jstep);
   const int di = threadIdx.x >> 5;
-  if (dk >= f.n2 || di >= f.n0) return;
-  const K1Hot h = k1_hot_load(f, di, dk, smem_u32(box));
+  if (dk >= n.z || di >= n.x) return;
+  K1Hot<RMASK> h;
+  k1_hot_load<RMASK>(h, f, di, dk);
   const uint32_t o1 = 4u * h.p1, o0 = 4u * h.p0;
+  const int64_t ds1 = f.ds1;
+  float* p = f.dst + di * f.ds0 + dk * f.ds2 + jj * ds1;
+  const int64_t pstep = jstep * ds1;
+  const float fstep = static_cast<float>(jstep);
+  float fj = static_cast<float>(jj);
+  int cnt = (n.y - jj + jstep - 1) / jstep;  // voxels of this thread
 #pragma unroll 1
-  for (int dj0 = jj; dj0 < h.n1; dj0 += NV * jstep) {
+  for (; cnt >= NV; cnt -= NV) {
     K1Vox x[NV];
     float t[NV][8];
 #pragma unroll
-    for (int u = 0; u < NV; ++u) {
-      const int dj = dj0 + u * jstep;
-      x[u] = k1_fast_vox(h, dj < h.n1 ? dj : dj0);
-    }
+    for (int u = 0; u < NV; ++u) x[u] = k1_fast_vox<RMASK>(h, fj + static_cast<float>(u) * fstep);
 #pragma unroll
     for (int u = 0; u < NV; ++u) {
       t[u][0] = lds_f32(x[u].a); t[u][1] = lds_f32(x[u].a + 4);
@@ -458,11 +427,95 @@ __device__ __forceinline__ void k1_tile_staged_trilinear(const K1Fast& f, const 
       t[u][6] = lds_f32(x[u].a + o0 + o1); t[u][7] = lds_f32(x[u].a + o0 + o1 + 4);
     }
 #pragma unroll
-    for (int u = 0; u < NV; ++u) {
-      const int dj = dj0 + u * jstep;
-      const float val = fmaf(k1_lerp8(x[u], t[u]), h.gain, h.bias);
-      if (dj < h.n1) k1_fast_store(f, h, di, dj, dk, val);
+    for (int u = 0; u < NV; ++u) p[u * pstep] = fmaf(k1_lerp8(x[u], t[u]), h.gain, h.bias);
+    p += NV * pstep;
+    fj += static_cast<float>(NV) * fstep;
+  }
+#pragma unroll 1
+  for (; cnt > 0; --cnt) {
+    const K1Vox x = k1_fast_vox<RMASK>(h, fj);
+    float t[8];
+    t[0] = lds_f32(x.a); t[1] = lds_f32(x.a + 4); t[2] = lds_f32(x.a + o1); t[3] = lds_f32(x.a + o1 + 4);
+    t[4] = lds_f32(x.a + o0); t[5] = lds_f32(x.a + o0 + 4); t[6] = lds_f32(x.a + o0 + o1); t[7] = lds_f32(x.a + o0 + o1 + 4);
+    *p = fmaf(k1_lerp8(x, t), h.gain, h.bias);
+    p += pstep;
+    fj += fstep;
+  }
+}
+
+// Nearest, plain tiles: fast coordinates, exact replay inside the tie window.
+template <bool RMASK>
+__device__ __forceinline__ void k1_tile_staged_nearest(const K1Ctx& c, const K1Tile& tl, const K1Fast& f, const float* __restrict__ box) {
+  const int4 n = f.n;
+  int dk, jj, jstep;
+  k1_lane_map(n.w, dk, jj, jstep);
+  const int di = threadIdx.x >> 5;
+  if (dk >= n.z || di >= n.x) return;
+  K1Hot<RMASK> h;
+  k1_hot_load<RMASK>(h, f, di, dk);
+  const float tie = 0.5f - static_cast<float>(K1_EPS);
+  const int64_t ds1 = f.ds1;
+  float* p = f.dst + di * f.ds0 + dk * f.ds2 + jj * ds1;
+  const int64_t pstep = jstep * ds1;
+#pragma unroll 2
+  for (int dj = jj; dj < n.y; dj += jstep) {
+    float v0, v1, v2;
+    k1_fast_coords<RMASK>(h, static_cast<float>(dj), v0, v1, v2);
+    // rint (ties to even) on the FMA pipe: x + 1.5*2^23 rounds to the nearest integer
+    const float t0 = __fadd_rn(v0, K1_MAGIC), t1 = __fadd_rn(v1, K1_MAGIC), t2 = __fadd_rn(v2, K1_MAGIC);
+    const float n0 = t0 - K1_MAGIC, n1 = t1 - K1_MAGIC, n2 = t2 - K1_MAGIC;
+    float val;
+    if (fabsf(v0 - n0) > tie || fabsf(v1 - n1) > tie || fabsf(v2 - n2) > tie) {
+      val = k1_exact_nearest_smem(c, tl, box, di, dj, dk);  // within 1e-3 of a rounding tie
+    } else {
+      const uint32_t a = h.cbase + 4u * (__float_as_uint(t0) * h.p0 + __float_as_uint(t1) * h.p1 + __float_as_uint(t2));
+      val = fmaf(lds_f32(a), h.gain, h.bias);
     }
+    *p = val;
+    p += pstep;
+  }
+}
+
+// Rare tiles: output pad band (SpatialPadd after the resample), injected or Philox noise.  Same
+// arithmetic as the plain loops, one voxel at a time, out of line.
+__device__ __noinline__ void k1_tile_staged_cold(const K1Ctx& c, const K1Tile& tl, const K1Fast& f, const float* __restrict__ box) {
+  const int4 n = f.n;
+  int dk, jj, jstep;
+  k1_lane_map(n.w, dk, jj, jstep);
+  const int di = threadIdx.x >> 5;
+  if (dk >= n.z || di >= n.x) return;
+  K1Hot<true> h;
+  k1_hot_load<true>(h, f, di, dk);
+  const bool nearest = c.it.interp == ADELL_NEAREST;
+  const float tie = 0.5f - static_cast<float>(K1_EPS);
+  const uint32_t o1 = 4u * h.p1, o0 = 4u * h.p0;
+  const int4 vlo = f.vlo, vhi = f.vhi, fl = f.fl;
+  const float4 gb = f.gb;
+  for (int dj = jj; dj < n.y; dj += jstep) {
+    float val;
+    if (nearest) {
+      float v0, v1, v2;
+      k1_fast_coords<true>(h, static_cast<float>(dj), v0, v1, v2);
+      const float t0 = __fadd_rn(v0, K1_MAGIC), t1 = __fadd_rn(v1, K1_MAGIC), t2 = __fadd_rn(v2, K1_MAGIC);
+      if (fabsf(v0 - (t0 - K1_MAGIC)) > tie || fabsf(v1 - (t1 - K1_MAGIC)) > tie || fabsf(v2 - (t2 - K1_MAGIC)) > tie)
+        val = k1_exact_nearest_smem(c, tl, box, di, dj, dk);
+      else
+        val = fmaf(lds_f32(h.cbase + 4u * (__float_as_uint(t0) * h.p0 + __float_as_uint(t1) * h.p1 + __float_as_uint(t2))), h.gain, h.bias);
+    } else {
+      const K1Vox x = k1_fast_vox<true>(h, static_cast<float>(dj));
+      float t[8];
+      t[0] = lds_f32(x.a); t[1] = lds_f32(x.a + 4); t[2] = lds_f32(x.a + o1); t[3] = lds_f32(x.a + o1 + 4);
+      t[4] = lds_f32(x.a + o0); t[5] = lds_f32(x.a + o0 + 4); t[6] = lds_f32(x.a + o0 + o1); t[7] = lds_f32(x.a + o0 + o1 + 4);
+      val = fmaf(k1_lerp8(x, t), h.gain, h.bias);
+    }
+    if (fl.y) {
+      const bool ov = (di >= vlo.x) & (di < vhi.x) & (dj >= vlo.y) & (dj < vhi.y) & (dk >= vlo.z) & (dk < vhi.z);
+      if (!ov) val = gb.z;
+    }
+    const int64_t rel = di * f.ns0 + dj * f.ns1 + dk;
+    if (f.noise != nullptr) val = __fadd_rn(val, __ldg(f.noise + rel));
+    if (fl.z) val = fmaf(gb.w, adell_philox_normal(f.philox_seed, f.philox_offset + f.olin0 + rel), val);
+    f.dst[di * f.ds0 + dj * f.ds1 + dk * f.ds2] = val;
   }
 }
 
@@ -521,7 +574,7 @@ struct K1Slot {
 // fast coordinates), lane 3 fills the scalar part of the consumers' register image.  Everything
 // per-item (the fp64 coordinate of output voxel 0 and its derivative, the footprint of a full
 // tile) was computed on the host by adell_aug_prepare.
-__device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0, int b1, int b2, int lane) {
+__device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0, int b1, int b2, uint32_t box_addr, int lane) {
   const adell_item& it = c.it;
   K1Tile& tl = sl.tl;
   const unsigned FULL = 0xffffffffu;
@@ -598,14 +651,15 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
   const int vlo = it.out_vlo[a] - o0a, vhi = it.out_vhi[a] - o0a;
   const bool padded_a = vlo > 0 || vhi < na;
   const bool padded = __any_sync(FULL, ax && padded_a);
+  const int n0 = __shfl_sync(FULL, na, 0), n1 = __shfl_sync(FULL, na, 1), n2 = __shfl_sync(FULL, na, 2);
+  const int vl0 = __shfl_sync(FULL, vlo, 0), vl1 = __shfl_sync(FULL, vlo, 1), vl2 = __shfl_sync(FULL, vlo, 2);
+  const int vh0 = __shfl_sync(FULL, vhi, 0), vh1 = __shfl_sync(FULL, vhi, 1), vh2 = __shfl_sync(FULL, vhi, 2);
   if (ax) {
     tl.lo_t[a] = lo; tl.hi_t[a] = hi;
     tl.box[a] = it.tmap_box[a]; tl.msign[a] = msign; tl.mconst[a] = mconst;
     tl.V0[a] = V0; tl.Dm[a][0] = Dm0; tl.Dm[a][1] = Dm1; tl.Dm[a][2] = Dm2; tl.rA[a] = rA; tl.rB[a] = rB;
-    f.V0[a] = V0; f.D0[a] = Dm0; f.D1[a] = Dm1; f.D2[a] = Dm2;
-    f.Sf[a] = c.Sf[a]; f.Sm1[a] = c.Sm1[a]; f.rA[a] = rA; f.rB[a] = rB;
-    f.vlo[a] = vlo; f.vhi[a] = vhi;
-    if (a == 0) f.n0 = na; else if (a == 1) f.n1 = na; else f.n2 = na;
+    f.ax[a] = make_float4(V0, Dm0, Dm1, Dm2);
+    f.rf[a] = make_float4(c.Sf[a], c.Sm1[a], rA, rB);
     if (a == 2) {  // alignment slack columns of the tensor map that fall inside this box
       tl.fix_lo = max(0, -mo);
       tl.fix_hi = it.fp_fix > 0 ? min(it.tmap_box[2], it.fp_fix - mo) : 0;
@@ -614,22 +668,21 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
   if (lane == 3) {
     tl.mode = MODE_STAGED;
     tl.rmask = rmask; tl.all_valid = all_valid;
-    f.p1 = it.tmap_box[2]; f.p0 = it.tmap_box[1] * it.tmap_box[2];
-    f.p1f = static_cast<float>(f.p1); f.p0f = static_cast<float>(f.p0);
-    f.gain = c.pre_s * it.post_scale;
-    f.bias = fmaf(c.pre_o, it.post_scale, it.post_offset);
-    f.post_o = it.post_offset;
-    f.noise_std = it.noise_std;
-    f.kw = it.tile_dim[2];
-    f.padded = padded ? 1 : 0;
+    const int philox = (it.flags & ADELL_F_PHILOX) ? 1 : 0;
+    f.gb = make_float4(c.pre_s * it.post_scale, fmaf(c.pre_o, it.post_scale, it.post_offset), it.post_offset, it.noise_std);
+    f.n = make_int4(n0, n1, n2, it.tile_dim[2]);
+    const uint32_t p0 = static_cast<uint32_t>(it.tmap_box[1] * it.tmap_box[2]), p1 = static_cast<uint32_t>(it.tmap_box[2]);
+    f.m = make_int4(static_cast<int>(p0), static_cast<int>(p1), rmask | (it.padding << 8),
+                    static_cast<int>(box_addr - 4u * (K1_MAGIC_BITS * (p0 + p1 + 1u))));
+    f.fl = make_int4((padded || it.noise != nullptr || philox) ? 1 : 0, padded ? 1 : 0, philox, 0);
+    f.vlo = make_int4(vl0, vl1, vl2, 0);
+    f.vhi = make_int4(vh0, vh1, vh2, 0);
     f.ds0 = it.dst_stride[0]; f.ds1 = it.dst_stride[1]; f.ds2 = it.dst_stride[2];
     f.dst = it.dst + o00 * it.dst_stride[0] + o01 * it.dst_stride[1] + o02 * it.dst_stride[2];
     f.ns1 = it.out_shape[2]; f.ns0 = static_cast<int64_t>(it.out_shape[1]) * it.out_shape[2];
     f.olin0 = (static_cast<uint64_t>(o00) * it.out_shape[1] + o01) * it.out_shape[2] + o02;
     f.noise = it.noise ? it.noise + f.olin0 : nullptr;
-    f.philox = (it.flags & ADELL_F_PHILOX) ? 1 : 0;
     f.philox_seed = it.philox_seed; f.philox_offset = it.philox_offset;
-    f.rmask = rmask; f.pad = it.padding;
   }
 }
 
@@ -646,7 +699,7 @@ __device__ unsigned long long k1_prof[8];
 // item itself is fetched from global memory only when the tile sequence moves on to a new item.
 __device__ __forceinline__ void k1_prepare(const adell_item* __restrict__ items, const int32_t* __restrict__ tile_start,
                                            int tile, int& item, int& cur_start, int& next_start, int& cached_item,
-                                           K1Ctx& priv, K1Slot& sl, int lane) {
+                                           K1Ctx& priv, K1Slot& sl, uint32_t box_addr, int lane) {
   while (tile >= next_start) { ++item; cur_start = next_start; next_start = __ldg(tile_start + item + 1); }
   constexpr int kItemWords = (sizeof(adell_item) - 128) / 4;  // without the tensor map
   uint32_t* pw = reinterpret_cast<uint32_t*>(&priv) + 32;
@@ -674,7 +727,7 @@ __device__ __forceinline__ void k1_prepare(const adell_item* __restrict__ items,
   const int b2 = local % n2; local /= n2;
   const int b1 = local % n1;
   const int b0 = local / n1;
-  k1_tile_setup(sl.ctx, sl, b0, b1, b2, lane);
+  k1_tile_setup(sl.ctx, sl, b0, b1, b2, box_addr, lane);
   if (lane == 0) sl.tl.item = item;
   __syncwarp();
 }
@@ -726,7 +779,8 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
       K1_PROF_T0
       // safe to overwrite: the slot's previous tile (k - n_slots) was released before the previous
       // iteration's issue (tile k-1 waited for the stage of tile k-1-n_stages = k - n_slots)
-      k1_prepare(items, tile_start, tile, item, cur_start, next_start, cached_item, *priv, slots[slot], lane);
+      k1_prepare(items, tile_start, tile, item, cur_start, next_start, cached_item, *priv, slots[slot],
+                 smem_u32(smem + static_cast<size_t>(stage) * stage_bytes), lane);
       K1_PROF_ADD(2)
       mbar_wait(empty + stage, phase ^ 1);
       K1_PROF_ADD(0)
@@ -791,9 +845,16 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
       k1_for_each_voxel(tl, it, [&](int, int, int, int o0, int o1, int o2) { k1_finish(it, 0.0f, o0, o1, o2, strict); });
     } else if (mode == MODE_STAGED) {
       const bool exact = (it.flags & (ADELL_F_STRICT | ADELL_F_CLIP)) != 0 || (ctx.pre_o != 0.0f && !tl.all_valid);
+      const K1Fast& f = slots[slot].fast;
       if (exact) k1_tile_exact_dispatch<SmemTaps, false>(ctx, tl, box);
-      else if (it.interp == ADELL_NEAREST) k1_tile_staged_nearest(ctx, tl, slots[slot].fast, box);
-      else k1_tile_staged_trilinear<K1_NV>(slots[slot].fast, box);
+      else if (f.fl.x) k1_tile_staged_cold(ctx, tl, f, box);
+      else if (it.interp == ADELL_NEAREST) {
+        if (tl.rmask) k1_tile_staged_nearest<true>(ctx, tl, f, box);
+        else k1_tile_staged_nearest<false>(ctx, tl, f, box);
+      } else {
+        if (tl.rmask) k1_tile_staged_trilinear<K1_NV, true>(f);
+        else k1_tile_staged_trilinear<K1_NV, false>(f);
+      }
     } else if (it.flags & ADELL_F_IDENTITY) {
       k1_tile_exact_dispatch<GlobalTaps, true>(ctx, tl, nullptr);
     } else {
@@ -905,11 +966,12 @@ int k1_encode_item(adell_item& it, EncodeTiledFn enc, int tile_pref) {
   if (it.src_dtype != ADELL_F32) return 0;
   if (it.src_stride[2] != 1 && it.src_stride[2] != -1) return 0;
   k1_item_map(it);
-  // tile shapes, most voxels per consumer thread first; a larger shape is taken only if its box
-  // leaves room for three ring stages, the base shape up to the two-stage limit
+  // tile shapes: among those whose box fits (a larger shape only if it leaves room for three ring
+  // stages, the base shape up to the two-stage limit) take the one that pads the output least;
+  // ties go to the shape listed first (32 lanes along the contiguous axis = 128-byte row stores)
   static const int kShapes[3][3] = {{16, 16, 32}, {16, 32, 16}, {16, 16, 16}};
   int box[3] = {0, 0, 0}, T[3] = {16, 16, 16};
-  int64_t bytes = 0;
+  int64_t bytes = 0, best_cover = -1;
   for (int s = 0; s < 3; ++s) {
     if (tile_pref >= 0 && s != 2 && s != tile_pref) continue;
     if (s == 0 && it.out_shape[2] <= 16) continue;
@@ -917,9 +979,12 @@ int k1_encode_item(adell_item& it, EncodeTiledFn enc, int tile_pref) {
     int bx[3];
     const int64_t b = k1_box_for_tile(it, kShapes[s], bx);
     if (b == 0 || b > (s == 2 ? K1_MAX_BOX_BYTES : K1_PREF_BOX_BYTES)) continue;
+    int64_t cover = 1;  // voxels of all tiles, padding included
+    for (int a = 0; a < 3; ++a) cover *= static_cast<int64_t>((it.out_shape[a] + kShapes[s][a] - 1) / kShapes[s][a]) * kShapes[s][a];
+    if (best_cover >= 0 && (tile_pref >= 0 || cover >= best_cover)) continue;
+    best_cover = cover;
     bytes = b;
     for (int a = 0; a < 3; ++a) { box[a] = bx[a]; T[a] = kShapes[s][a]; }
-    break;
   }
   if (bytes == 0) return 0;
   // valid source box in t-space and its origin in memory order
