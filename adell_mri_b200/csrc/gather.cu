@@ -519,32 +519,36 @@ __device__ __noinline__ void k1_tile_staged_cold(const K1Ctx& c, const K1Tile& t
   }
 }
 
-// 128-bit vectorised identity copy (flip / crop only, everything valid and aligned): one 32x16x32
-// tile = 64 KiB; each consumer thread moves eight float4 (rows di0 + 4r of column quad q), all
-// eight loads issued before the first store so that ~64 KiB per SM are in flight.
-__device__ __forceinline__ void k1_tile_copy_vec(const K1Ctx& c, const K1Tile& tl) {
+// Identity items (flip / crop only, everything valid): the producer brings the tile's source box
+// in with one TMA load like any staged tile — the load latency is carried by the TMA queue, several
+// tiles deep, instead of by the consumer threads — and the consumers move it out with 128-bit
+// shared loads and 128-bit streaming global stores.  One 32x16x32 tile = 64 KiB; each thread
+// moves eight float4 (rows di0 + 4r of column quad q).  A flip is a sign in the box index; a flip
+// along the contiguous axis reverses the quad in registers.
+__device__ __forceinline__ void k1_tile_copy_box(const K1Ctx& c, const K1Tile& tl, const float* __restrict__ box) {
   const adell_item& it = c.it;
   const int q = threadIdx.x & 7, dj = (threadIdx.x >> 3) & 15, di0 = threadIdx.x >> 7;
   const int o0 = tl.o0[0] + di0, o1 = tl.o0[1] + dj, o2 = tl.o0[2] + 4 * q;
   const int O0 = it.out_shape[0];
   if (o1 >= it.out_shape[1] || o2 >= it.out_shape[2] || o0 >= O0) return;
-  const bool rev = it.grid_sign[2] * it.src_stride[2] < 0;
+  // box index of output voxel o along axis a: s_a*o_a + M_a
+  const int s0 = tl.msign[0] * it.grid_sign[0], s1 = tl.msign[1] * it.grid_sign[1], s2 = tl.msign[2] * it.grid_sign[2];
+  const int M0 = tl.msign[0] * it.grid_off[0] + tl.mconst[0], M1 = tl.msign[1] * it.grid_off[1] + tl.mconst[1],
+            M2 = tl.msign[2] * it.grid_off[2] + tl.mconst[2];
+  const bool rev = s2 < 0;
+  const int m2 = rev ? M2 - (o2 + 3) : M2 + o2;  // lowest box column of the quad
+  const int p1 = tl.box[2], p0 = tl.box[1] * tl.box[2];
+  const float* sp = box + (s0 * o0 + M0) * p0 + (s1 * o1 + M1) * p1 + m2;
+  const int sstep = 4 * s0 * p0;
+  const bool vec = (m2 & 3) == 0;  // block-uniform: the same for every quad of every tile of an item
   const bool clip = (it.flags & ADELL_F_CLIP) != 0;
   const float pre_s = c.pre_s, pre_o = c.pre_o, post_s = it.post_scale, post_o = it.post_offset;
   const float clo = it.clip_lo, chi = it.clip_hi;
   const float gain = pre_s * post_s, bias = fmaf(pre_o, post_s, post_o);
   const bool plain = !clip && gain == 1.0f && bias == 0.0f;
-  const int g0 = it.grid_off[0] + it.grid_sign[0] * o0;
-  const int g1 = it.grid_off[1] + it.grid_sign[1] * o1;
-  const int g2 = it.grid_off[2] + it.grid_sign[2] * (rev ? o2 + 3 : o2);  // lowest address of the quad
-  const int64_t sstep = 4 * it.grid_sign[0] * it.src_stride[0], dstep = 4 * it.dst_stride[0];
-  const float* sp = reinterpret_cast<const float*>(it.src) + g0 * it.src_stride[0] + g1 * it.src_stride[1] + g2 * it.src_stride[2];
+  const int64_t dstep = 4 * it.dst_stride[0];
   float* dp = it.dst + o0 * it.dst_stride[0] + o1 * it.dst_stride[1] + o2;
-  const int nrow = min(8, (O0 - o0 + 3) >> 2);  // rows o0 + 4r of this thread inside the volume
-  float4 v[8];
-#pragma unroll
-  for (int r = 0; r < 8; ++r)
-    if (r < nrow) v[r] = __ldcs(reinterpret_cast<const float4*>(sp + r * sstep));
+  const int nrow = min(8, (min(O0 - o0, tl.T[0] - di0) + 3) >> 2);  // rows o0 + 4r of this thread inside the tile
   auto fix = [&](float4 x) {
     if (rev) { float t = x.x; x.x = x.w; x.w = t; t = x.y; x.y = x.z; x.z = t; }
     if (plain) return x;
@@ -558,9 +562,17 @@ __device__ __forceinline__ void k1_tile_copy_vec(const K1Ctx& c, const K1Tile& t
     }
     return x;
   };
+  if (vec) {
 #pragma unroll
-  for (int r = 0; r < 8; ++r)
-    if (r < nrow) __stcs(reinterpret_cast<float4*>(dp + r * dstep), fix(v[r]));
+    for (int r = 0; r < 8; ++r)
+      if (r < nrow) __stcs(reinterpret_cast<float4*>(dp + r * dstep), fix(*reinterpret_cast<const float4*>(sp + r * sstep)));
+  } else {
+#pragma unroll 2
+    for (int r = 0; r < nrow; ++r) {
+      const float* p = sp + r * sstep;
+      __stcs(reinterpret_cast<float4*>(dp + r * dstep), fix(make_float4(p[0], p[1], p[2], p[3])));
+    }
+  }
 }
 
 // ------------------------------------------------------------------------- per-tile set-up
@@ -583,8 +595,22 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
   const int o00 = b0 * it.tile_dim[0], o01 = b1 * it.tile_dim[1], o02 = b2 * it.tile_dim[2];
   const int o0a = a == 0 ? o00 : (a == 1 ? o01 : o02);
   if (ax) { tl.o0[a] = o0a; tl.T[a] = it.tile_dim[a]; }
+  if (it.kind == ADELL_KIND_VCOPY) {
+    // source box of the tile = its voxels, in memory order (integer flip / crop only)
+    if (ax) {
+      const int na = min(static_cast<int>(it.tile_dim[a]), it.out_shape[a] - o0a);
+      const int g0 = it.grid_off[a] + it.grid_sign[a] * o0a, g1 = it.grid_off[a] + it.grid_sign[a] * (o0a + na - 1);
+      const int msign = it.tmap_sign[a];
+      int mo = msign > 0 ? min(g0, g1) + it.tmap_off[a] : -max(g0, g1) + it.tmap_off[a];
+      if (a == 2) mo = (mo >> 2) << 2;  // 16-byte aligned start along the contiguous axis
+      tl.box[a] = it.tmap_box[a]; tl.msign[a] = msign; tl.mconst[a] = it.tmap_off[a] - mo;
+      if (a == 2) { tl.fix_lo = 0; tl.fix_hi = 0; }
+    }
+    if (lane == 0) tl.mode = MODE_COPY;
+    return;
+  }
   if (it.kind != ADELL_KIND_STAGED) {
-    if (lane == 0) tl.mode = it.kind == ADELL_KIND_VCOPY ? MODE_COPY : MODE_DIRECT;
+    if (lane == 0) tl.mode = MODE_DIRECT;
     return;
   }
   // un-padded source coordinate of the tile-origin voxel along axis a, and the tile's footprint
@@ -785,8 +811,8 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
       mbar_wait(empty + stage, phase ^ 1);
       K1_PROF_ADD(0)
       const K1Slot& sl = slots[slot];
-      const bool staged = sl.tl.mode == MODE_STAGED;
-      const bool fix = staged && sl.tl.fix_hi > sl.tl.fix_lo;
+      const bool staged = sl.tl.mode == MODE_STAGED || sl.tl.mode == MODE_COPY;  // tiles with a TMA box load
+      const bool fix = sl.tl.mode == MODE_STAGED && sl.tl.fix_hi > sl.tl.fix_lo;
       if (lane == 0) {
         if (staged) {
           const int mo0 = sl.ctx.it.tmap_off[0] - sl.tl.mconst[0], mo1 = sl.ctx.it.tmap_off[1] - sl.tl.mconst[1],
@@ -839,7 +865,7 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
     const adell_item& it = ctx.it;
     const int mode = tl.mode;
     if (mode == MODE_COPY) {
-      k1_tile_copy_vec(ctx, tl);
+      k1_tile_copy_box(ctx, tl, box);
     } else if (mode == MODE_ZERO) {
       const bool strict = (it.flags & ADELL_F_STRICT) != 0;
       k1_for_each_voxel(tl, it, [&](int, int, int, int o0, int o1, int o2) { k1_finish(it, 0.0f, o0, o1, o2, strict); });
@@ -896,13 +922,13 @@ EncodeTiledFn k1_get_encode() {
   return cached;
 }
 
-// Identity item eligible for the 128-bit vector copy: fp32, unit step along axis 2, 16-byte
-// aligned rows on both sides, nothing invalid, no noise, no strict-order post map.
+// Identity item eligible for the box copy: fp32, unit step along axis 2, 16-byte aligned
+// destination rows, nothing invalid, no noise, no strict-order post map.  (The source needs no
+// alignment: it arrives through a TMA box whose origin is rounded down to 16 bytes.)
 bool k1_vcopy_ok(const adell_item& it) {
   if (!(it.flags & ADELL_F_IDENTITY) || it.src_dtype != ADELL_F32) return false;
   if ((it.src_stride[2] != 1 && it.src_stride[2] != -1) || it.dst_stride[2] != 1 || it.noise != nullptr) return false;
   if ((it.flags & (ADELL_F_PHILOX | ADELL_F_STRICT)) || (it.out_shape[2] & 3) != 0) return false;
-  const bool rev = it.grid_sign[2] * it.src_stride[2] < 0;
   for (int a = 0; a < 3; ++a) {
     if (it.out_vlo[a] > 0 || it.out_vhi[a] < it.out_shape[a]) return false;
     const int tlo = it.src_vlo[a] > 0 ? it.src_vlo[a] : 0;
@@ -910,12 +936,7 @@ bool k1_vcopy_ok(const adell_item& it) {
     const int ga = it.grid_off[a], gb = it.grid_off[a] + it.grid_sign[a] * (it.out_shape[a] - 1);
     if ((ga < gb ? ga : gb) < tlo || (ga > gb ? ga : gb) >= thi) return false;
   }
-  const int g2 = it.grid_off[2] + it.grid_sign[2] * (rev ? 3 : 0);
-  const int64_t e0 = g2 * it.src_stride[2];
-  const uintptr_t sp = reinterpret_cast<uintptr_t>(it.src);
-  if ((sp & 3u) != 0 || (((sp >> 2) + static_cast<uint64_t>(e0)) & 3u) != 0) return false;
-  if ((it.src_stride[0] & 3) || (it.src_stride[1] & 3) || (reinterpret_cast<uintptr_t>(it.dst) & 15u)) return false;
-  if ((it.dst_stride[0] & 3) || (it.dst_stride[1] & 3)) return false;
+  if ((reinterpret_cast<uintptr_t>(it.dst) & 15u) || (it.dst_stride[0] & 3) || (it.dst_stride[1] & 3)) return false;
   return true;
 }
 
@@ -957,36 +978,10 @@ int64_t k1_box_for_tile(const adell_item& it, const int* T, int* box) {
   return cells * 4;
 }
 
-// Decides staged-path eligibility for one item and, when eligible, picks its tile shape, encodes
-// its tensor map over the valid source box in memory order and fills the derived fields.
-// Returns the box bytes (0 = not staged, -1 = no driver).
-int k1_encode_item(adell_item& it, EncodeTiledFn enc, int tile_pref) {
+// Encodes the tensor map of the item's valid source box (memory order) for a staged box of the
+// given extents (axes 0,1,2).  Returns 1, 0 (layout not expressible) or -1 (no driver).
+int k1_encode_tmap(adell_item& it, const int* box, EncodeTiledFn enc) {
   it.flags &= static_cast<uint8_t>(~ADELL_F_TMAP);
-  if (it.flags & ADELL_F_IDENTITY) return 0;
-  if (it.src_dtype != ADELL_F32) return 0;
-  if (it.src_stride[2] != 1 && it.src_stride[2] != -1) return 0;
-  k1_item_map(it);
-  // tile shapes: among those whose box fits (a larger shape only if it leaves room for three ring
-  // stages, the base shape up to the two-stage limit) take the one that pads the output least;
-  // ties go to the shape listed first (32 lanes along the contiguous axis = 128-byte row stores)
-  static const int kShapes[3][3] = {{16, 16, 32}, {16, 32, 16}, {16, 16, 16}};
-  int box[3] = {0, 0, 0}, T[3] = {16, 16, 16};
-  int64_t bytes = 0, best_cover = -1;
-  for (int s = 0; s < 3; ++s) {
-    if (tile_pref >= 0 && s != 2 && s != tile_pref) continue;
-    if (s == 0 && it.out_shape[2] <= 16) continue;
-    if (s == 1 && it.out_shape[1] <= 16) continue;
-    int bx[3];
-    const int64_t b = k1_box_for_tile(it, kShapes[s], bx);
-    if (b == 0 || b > (s == 2 ? K1_MAX_BOX_BYTES : K1_PREF_BOX_BYTES)) continue;
-    int64_t cover = 1;  // voxels of all tiles, padding included
-    for (int a = 0; a < 3; ++a) cover *= static_cast<int64_t>((it.out_shape[a] + kShapes[s][a] - 1) / kShapes[s][a]) * kShapes[s][a];
-    if (best_cover >= 0 && (tile_pref >= 0 || cover >= best_cover)) continue;
-    best_cover = cover;
-    bytes = b;
-    for (int a = 0; a < 3; ++a) { box[a] = bx[a]; T[a] = kShapes[s][a]; }
-  }
-  if (bytes == 0) return 0;
   // valid source box in t-space and its origin in memory order
   cuuint64_t gdim[3], gstride[2];
   int64_t base_off = 0;
@@ -1023,6 +1018,65 @@ int k1_encode_item(adell_item& it, EncodeTiledFn enc, int tile_pref) {
                    reinterpret_cast<void*>(base), gdim, gstride, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return 0;
+  it.tmap_base = reinterpret_cast<const void*>(base);
+  it.flags |= ADELL_F_TMAP;
+  return 1;
+}
+
+// Identity item: tensor map for the 32x16x32 box copy.  Returns the box bytes (0 = not eligible).
+int k1_encode_copy(adell_item& it, EncodeTiledFn enc) {
+  if (!k1_vcopy_ok(it)) return 0;
+  static const int T[3] = {32, 16, 32};
+  int box[3] = {T[0], T[1], T[2]};
+  int r = k1_encode_tmap(it, box, enc);
+  if (r <= 0) return r;
+  // tensor coordinate of the first tile's lowest element along axis 2: if it is not a multiple of
+  // four the box origin is rounded down per tile and the box needs four more columns
+  const int n2 = it.out_shape[2] < T[2] ? it.out_shape[2] : T[2];
+  const int g0 = it.grid_off[2], g1 = it.grid_off[2] + it.grid_sign[2] * (n2 - 1);
+  const int lo = it.tmap_sign[2] > 0 ? (g0 < g1 ? g0 : g1) + it.tmap_off[2] : -(g0 > g1 ? g0 : g1) + it.tmap_off[2];
+  if (lo & 3) {
+    box[2] += 4;
+    r = k1_encode_tmap(it, box, enc);
+    if (r <= 0) return r;
+  }
+  for (int a = 0; a < 3; ++a) it.tile_dim[a] = static_cast<uint8_t>(T[a]);
+  it.kind = ADELL_KIND_VCOPY;
+  return box[0] * box[1] * box[2] * 4;
+}
+
+// Decides staged-path eligibility for one item and, when eligible, picks its tile shape, encodes
+// its tensor map over the valid source box in memory order and fills the derived fields.
+// Returns the box bytes (0 = not staged, -1 = no driver).
+int k1_encode_item(adell_item& it, EncodeTiledFn enc, int tile_pref) {
+  it.flags &= static_cast<uint8_t>(~ADELL_F_TMAP);
+  if (it.flags & ADELL_F_IDENTITY) return 0;
+  if (it.src_dtype != ADELL_F32) return 0;
+  if (it.src_stride[2] != 1 && it.src_stride[2] != -1) return 0;
+  k1_item_map(it);
+  // tile shapes: among those whose box fits (a larger shape only if it leaves room for three ring
+  // stages, the base shape up to the two-stage limit) take the one that pads the output least;
+  // ties go to the shape listed first (32 lanes along the contiguous axis = 128-byte row stores)
+  static const int kShapes[3][3] = {{16, 16, 32}, {16, 32, 16}, {16, 16, 16}};
+  int box[3] = {0, 0, 0}, T[3] = {16, 16, 16};
+  int64_t bytes = 0, best_cover = -1;
+  for (int s = 0; s < 3; ++s) {
+    if (tile_pref >= 0 && s != 2 && s != tile_pref) continue;
+    if (s == 0 && it.out_shape[2] <= 16) continue;
+    if (s == 1 && it.out_shape[1] <= 16) continue;
+    int bx[3];
+    const int64_t b = k1_box_for_tile(it, kShapes[s], bx);
+    if (b == 0 || b > (s == 2 ? K1_MAX_BOX_BYTES : K1_PREF_BOX_BYTES)) continue;
+    int64_t cover = 1;  // voxels of all tiles, padding included
+    for (int a = 0; a < 3; ++a) cover *= static_cast<int64_t>((it.out_shape[a] + kShapes[s][a] - 1) / kShapes[s][a]) * kShapes[s][a];
+    if (best_cover >= 0 && (tile_pref >= 0 || cover >= best_cover)) continue;
+    best_cover = cover;
+    bytes = b;
+    for (int a = 0; a < 3; ++a) { box[a] = bx[a]; T[a] = kShapes[s][a]; }
+  }
+  if (bytes == 0) return 0;
+  const int r = k1_encode_tmap(it, box, enc);
+  if (r <= 0) return r;
   for (int a = 0; a < 3; ++a) {
     it.tile_dim[a] = static_cast<uint8_t>(T[a]);
     double smin = 0.0, smax = 0.0;
@@ -1035,8 +1089,6 @@ int k1_encode_item(adell_item& it, EncodeTiledFn enc, int tile_pref) {
     it.fp_smin[a] = nextafterf(static_cast<float>(smin), -INFINITY);
     it.fp_smax[a] = nextafterf(static_cast<float>(smax), INFINITY);
   }
-  it.tmap_base = reinterpret_cast<const void*>(base);
-  it.flags |= ADELL_F_TMAP;
   it.kind = ADELL_KIND_STAGED;
   return static_cast<int>(bytes);
 }
@@ -1062,14 +1114,15 @@ extern "C" int adell_aug_prepare(adell_item* items_host, int n_items, int32_t* t
     it.tile_dim[0] = it.tile_dim[1] = it.tile_dim[2] = K1_T;
     it.fp_fix = 0;
     int bytes = 0;
-    if (k1_vcopy_ok(it)) {
-      it.flags &= static_cast<uint8_t>(~ADELL_F_TMAP);
-      it.kind = ADELL_KIND_VCOPY;
-      it.tile_dim[0] = 32; it.tile_dim[1] = 16; it.tile_dim[2] = 32;
-    } else if (no_staged) {
-      it.flags &= static_cast<uint8_t>(~ADELL_F_TMAP);
-    } else {
-      bytes = k1_encode_item(it, enc, tile_pref);
+    it.flags &= static_cast<uint8_t>(~ADELL_F_TMAP);
+    if (!no_staged) {
+      bytes = (it.flags & ADELL_F_IDENTITY) ? k1_encode_copy(it, enc) : k1_encode_item(it, enc, tile_pref);
+      if (bytes == 0) {  // not staged after all: generic 16^3 tiles
+        it.flags &= static_cast<uint8_t>(~ADELL_F_TMAP);
+        it.kind = ADELL_KIND_GENERIC;
+        it.tile_dim[0] = it.tile_dim[1] = it.tile_dim[2] = K1_T;
+        it.fp_fix = 0;
+      }
     }
     if (bytes < 0) return ADELL_ERR_NO_DRIVER;
     if (bytes > 0) { ++staged; if (bytes > smem) smem = bytes; }
