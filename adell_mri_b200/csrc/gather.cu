@@ -33,12 +33,13 @@ namespace {
 
 constexpr int K1_CWARPS = 16;                  // consumer warps per CTA
 constexpr int K1_CTHREADS = 32 * K1_CWARPS;    // consumer threads
-constexpr int K1_THREADS = K1_CTHREADS + 32;   // + one producer warp
+constexpr int K1_THREADS = K1_CTHREADS + 64;   // + one producer warp + one hand-over warp
 constexpr int K1_T = 16;                       // base tile edge
 constexpr int K1_MAX_STAGES = 6;
 constexpr int K1_SMEM_BUDGET = 224 * 1024;     // dynamic shared memory per persistent CTA (1 CTA per SM)
 constexpr int K1_MAX_BOX_BYTES = 100 * 1024;   // staged footprint limit (two stages)
 constexpr int K1_PREF_BOX_BYTES = 68 * 1024;   // preferred limit for the larger tile shapes (three stages)
+constexpr int K1_TS_CACHE = 2048;               // tile-prefix entries cached in shared memory (else read from global)
 constexpr double K1_EPS = 1e-3;                // coordinate slack of the fast path / tie window
 constexpr float K1_MAGIC = 12582912.0f;        // 1.5 * 2^23: x + MAGIC has ulp 1 for |x| < 2^22
 constexpr uint32_t K1_MAGIC_BITS = 0x4B400000u;
@@ -723,10 +724,20 @@ __device__ unsigned long long k1_prof[8];
 
 // Producer: derive the tile state (and the consumers' register image) in the given slot.  The
 // item itself is fetched from global memory only when the tile sequence moves on to a new item.
-__device__ __forceinline__ void k1_prepare(const adell_item* __restrict__ items, const int32_t* __restrict__ tile_start,
+__device__ __forceinline__ void k1_prepare(const adell_item* __restrict__ items, const int32_t* ts, int n_items,
                                            int tile, int& item, int& cur_start, int& next_start, int& cached_item,
                                            K1Ctx& priv, K1Slot& sl, uint32_t box_addr, int lane) {
-  while (tile >= next_start) { ++item; cur_start = next_start; next_start = __ldg(tile_start + item + 1); }
+  // monotone walk over the per-item tile prefix, 32 entries per step (one load latency per step,
+  // not one per item skipped); `ts` is the shared-memory copy of the prefix when it fits
+  while (tile >= next_start) {
+    const int idx = item + 1 + lane;
+    const int v = idx <= n_items ? ts[idx] : 0x7fffffff;
+    const int adv = __popc(__ballot_sync(0xffffffffu, tile >= v));  // prefix is non-decreasing: a run of leading lanes
+    item += adv;
+    cur_start = __shfl_sync(0xffffffffu, v, adv - 1);
+    const int nxt = __shfl_sync(0xffffffffu, v, adv & 31);
+    next_start = adv < 32 ? nxt : (item + 1 <= n_items ? ts[item + 1] : 0x7fffffff);
+  }
   constexpr int kItemWords = (sizeof(adell_item) - 128) / 4;  // without the tensor map
   uint32_t* pw = reinterpret_cast<uint32_t*>(&priv) + 32;
   if (item != cached_item) {
@@ -775,7 +786,7 @@ __device__ __forceinline__ void k1_fix_columns(float* box, const K1Tile& tl, int
 // n_stages+1 tile-state slots, so set-up never waits for shared-memory space.
 __global__ void __launch_bounds__(K1_THREADS, 1)
 k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile_start, int n_items, int total_tiles,
-          int n_stages, int stage_bytes) {
+          int n_stages, int stage_bytes, int chunk) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int n_slots = n_stages + 1;
   K1Slot* slots = reinterpret_cast<K1Slot*>(smem + static_cast<size_t>(n_stages) * stage_bytes);
@@ -783,6 +794,11 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
   uint64_t* full = reinterpret_cast<uint64_t*>(priv + 1);
   uint64_t* empty = full + n_stages;
   uint64_t* landed = empty + n_stages;   // TMA completion of tiles that need the column fix-up first
+  int32_t* ts_s = reinterpret_cast<int32_t*>(landed + n_stages);
+  const bool ts_cached = n_items + 1 <= K1_TS_CACHE;
+  if (ts_cached)
+    for (int i = threadIdx.x; i <= n_items; i += K1_THREADS) ts_s[i] = __ldg(tile_start + i);
+  const int32_t* ts = ts_cached ? ts_s : tile_start;
   if (threadIdx.x == 0) {
     for (int s = 0; s < n_stages; ++s) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(full + s)), "r"(1));
@@ -795,67 +811,65 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
   const int lane = threadIdx.x & 31;
   int stage = 0, phase = 0, slot = 0;
 
-  if (threadIdx.x >= K1_CTHREADS) {
+  if (threadIdx.x >= K1_CTHREADS + 32) {
     // ------------------------------------------------------------------ producer warp
     int item = 0, cached_item = -1, cur_start = 0;
-    int next_start = __ldg(tile_start + 1);
-    uint32_t landed_phase = 0;          // bit s = parity to wait for on landed[s]
-    int pend_stage = -1, pend_slot = 0; // tile whose column fix-up is still due
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    int next_start = ts[1];
+    int acq_item = -1;                  // item whose tensor map this CTA acquired last
+    // chunks of `chunk` consecutive tiles go round-robin over the CTAs: consecutive tiles share
+    // their item (one item fetch / tensor-map acquire per chunk) and neighbouring source boxes
+    for (int t0 = blockIdx.x * chunk; t0 < total_tiles; t0 += gridDim.x * chunk)
+    for (int tile = t0; tile < min(t0 + chunk, total_tiles); ++tile) {
       K1_PROF_T0
       // safe to overwrite: the slot's previous tile (k - n_slots) was released before the previous
       // iteration's issue (tile k-1 waited for the stage of tile k-1-n_stages = k - n_slots)
-      k1_prepare(items, tile_start, tile, item, cur_start, next_start, cached_item, *priv, slots[slot],
+      k1_prepare(items, ts, n_items, tile, item, cur_start, next_start, cached_item, *priv, slots[slot],
                  smem_u32(smem + static_cast<size_t>(stage) * stage_bytes), lane);
       K1_PROF_ADD(2)
       mbar_wait(empty + stage, phase ^ 1);
       K1_PROF_ADD(0)
-      const K1Slot& sl = slots[slot];
-      const bool staged = sl.tl.mode == MODE_STAGED || sl.tl.mode == MODE_COPY;  // tiles with a TMA box load
-      const bool fix = sl.tl.mode == MODE_STAGED && sl.tl.fix_hi > sl.tl.fix_lo;
       if (lane == 0) {
-        if (staged) {
+        const K1Slot& sl = slots[slot];
+        if (sl.tl.mode == MODE_STAGED || sl.tl.mode == MODE_COPY) {  // tiles with a TMA box load
           const int mo0 = sl.ctx.it.tmap_off[0] - sl.tl.mconst[0], mo1 = sl.ctx.it.tmap_off[1] - sl.tl.mconst[1],
                     mo2 = sl.ctx.it.tmap_off[2] - sl.tl.mconst[2];
-          uint64_t* bar = fix ? landed + stage : full + stage;
-          tmap_acquire(items[sl.tl.item].tmap);
-          mbar_expect_tx(bar, static_cast<uint32_t>(sl.tl.box[0] * sl.tl.box[1] * sl.tl.box[2] * 4));
-          tma_load_3d(smem + static_cast<size_t>(stage) * stage_bytes, items[sl.tl.item].tmap, bar, mo2, mo1, mo0);
+          if (sl.tl.item != acq_item) { tmap_acquire(items[sl.tl.item].tmap); acq_item = sl.tl.item; }
+          mbar_expect_tx(landed + stage, static_cast<uint32_t>(sl.tl.box[0] * sl.tl.box[1] * sl.tl.box[2] * 4));
+          tma_load_3d(smem + static_cast<size_t>(stage) * stage_bytes, items[sl.tl.item].tmap, landed + stage, mo2, mo1, mo0);
         } else {
-          mbar_arrive(full + stage);
+          mbar_arrive(landed + stage);
         }
       }
       __syncwarp();
-      // complete the previous tile's fix-up now that this tile's load is in flight as well
-      if (pend_stage >= 0) {
-        mbar_wait(landed + pend_stage, (landed_phase >> pend_stage) & 1u);
-        landed_phase ^= 1u << pend_stage;
-        k1_fix_columns(reinterpret_cast<float*>(smem + static_cast<size_t>(pend_stage) * stage_bytes), slots[pend_slot].tl, lane);
-        if (lane == 0) mbar_arrive(full + pend_stage);
-        pend_stage = -1;
-      }
-      if (fix) { pend_stage = stage; pend_slot = slot; }
-      if (fix && n_stages < 2) {  // a one-stage ring cannot defer: the next issue waits on this very tile
-        mbar_wait(landed + pend_stage, (landed_phase >> pend_stage) & 1u);
-        landed_phase ^= 1u << pend_stage;
-        k1_fix_columns(reinterpret_cast<float*>(smem + static_cast<size_t>(pend_stage) * stage_bytes), slots[pend_slot].tl, lane);
-        if (lane == 0) mbar_arrive(full + pend_stage);
-        pend_stage = -1;
-      }
       K1_PROF_ADD(1)
       if (++stage == n_stages) { stage = 0; phase ^= 1; }
       if (++slot == n_slots) slot = 0;
     }
-    if (pend_stage >= 0) {
-      mbar_wait(landed + pend_stage, (landed_phase >> pend_stage) & 1u);
-      k1_fix_columns(reinterpret_cast<float*>(smem + static_cast<size_t>(pend_stage) * stage_bytes), slots[pend_slot].tl, lane);
-      if (lane == 0) mbar_arrive(full + pend_stage);
+    return;
+  }
+
+  if (threadIdx.x >= K1_CTHREADS) {
+    // ------------------------------------------------------------------ hand-over warp
+    // Sits between the TMA completion (landed) and the consumers (full): zeroes the alignment-slack
+    // columns of boxes that have any (crop windows that start mid-row), off the producer's path, so
+    // that the producer never waits for a load to land.
+    for (int t0 = blockIdx.x * chunk; t0 < total_tiles; t0 += gridDim.x * chunk)
+    for (int tile = t0; tile < min(t0 + chunk, total_tiles); ++tile) {
+      mbar_wait(landed + stage, phase);
+      const K1Tile& tl = slots[slot].tl;
+      if (tl.mode == MODE_STAGED && tl.fix_hi > tl.fix_lo)
+        k1_fix_columns(reinterpret_cast<float*>(smem + static_cast<size_t>(stage) * stage_bytes), tl, lane);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full + stage);
+      if (++stage == n_stages) { stage = 0; phase ^= 1; }
+      if (++slot == n_slots) slot = 0;
     }
     return;
   }
 
   // -------------------------------------------------------------------- consumer warps
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+  for (int t0 = blockIdx.x * chunk; t0 < total_tiles; t0 += gridDim.x * chunk)
+  for (int tile = t0; tile < min(t0 + chunk, total_tiles); ++tile) {
     K1_PROF_T0
     mbar_wait(full + stage, phase);
     K1_PROF_ADD(3)
@@ -1158,16 +1172,21 @@ extern "C" int adell_aug_gather(const adell_item* items_dev, const int32_t* tile
   // ring of staged boxes: as many stages as fit next to the per-stage tile state
   const int stage_bytes = (info->smem_bytes + 127) & ~127;
   const int per_stage = stage_bytes + static_cast<int>(sizeof(K1Slot)) + 24;  // box + tile state + 3 mbarriers
-  const int fixed = static_cast<int>(sizeof(K1Slot) + sizeof(K1Ctx)) + 64;
+  const int fixed = static_cast<int>(sizeof(K1Slot) + sizeof(K1Ctx)) + 64 + K1_TS_CACHE * 4;
   int n_stages = (K1_SMEM_BUDGET - fixed) / per_stage;
   if (n_stages > K1_MAX_STAGES) n_stages = K1_MAX_STAGES;
   if (n_stages < 1) return ADELL_ERR_BAD_ARG;
   const int smem = n_stages * per_stage + fixed;
   e = cudaFuncSetAttribute(k1_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BUDGET);
   if (e != cudaSuccess) { (void)cudaGetLastError(); return adell_map_cuda_error(e); }
-  const int64_t grid = info->total_tiles < sms ? info->total_tiles : sms;
+  // consecutive tiles per CTA turn: small enough that the last round stays balanced
+  int chunk = 4;
+  if (const char* ce = getenv("ADELL_K1_CHUNK")) { const int v = atoi(ce); if (v >= 1 && v <= 64) chunk = v; }
+  while (chunk > 1 && info->total_tiles < static_cast<int64_t>(sms) * chunk * 8) chunk >>= 1;
+  const int64_t n_chunks = (info->total_tiles + chunk - 1) / chunk;
+  const int64_t grid = n_chunks < sms ? n_chunks : sms;
   k1_gather<<<static_cast<unsigned>(grid), K1_THREADS, static_cast<size_t>(smem), static_cast<cudaStream_t>(stream)>>>(
-      items_dev, tile_start_dev, n_items, static_cast<int>(info->total_tiles), n_stages, stage_bytes);
+      items_dev, tile_start_dev, n_items, static_cast<int>(info->total_tiles), n_stages, stage_bytes, chunk);
   ADELL_CUDA_CHECK_LAUNCH();
   return ADELL_OK;
 }

@@ -62,6 +62,8 @@ def ssl_items(R, n_batches=2, B=64, src=(160, 160, 40), roi=(128, 128, 32)):
         for b in range(B):
             v = torch.rand(src, device=dev, generator=g)
             st = [R.randint(s - r + 1) for s, r in zip(src, roi)]
+            if os.environ.get('SSL_ALIGNED'):
+                st[2] &= ~3
             for view in range(2):
                 rot = np.zeros(3); rot[R.randint(3)] = R.uniform(-1, 1) * (np.pi / 12)
                 tr = np.zeros(3); tr[R.randint(3)] = R.uniform(-15, 15)
