@@ -1,0 +1,79 @@
+"""Collation of the reference's loaders with the fused launch behind it.
+
+``safe_collate`` / ``safe_collate_crops`` keep the reference's contract
+(/root/reference/adell_mri/utils/utils.py:308-377: per key ``torch.stack`` of the samples, the
+plain list when stacking is impossible; the crops variant flattens ``list[list[dict]]`` first).
+Entries that are still :class:`~adell_mri_b200.transforms.Pending` — i.e. everything the lazy
+dictionary transforms touched — are executed here: the recorded chains of every sample and every
+key are concatenated and run as ONE K1 launch per resample pass, each volume written straight
+into its slot of the collated ``[B, C, H, W, D]`` tensor (no per-sample tensors, no stack copy).
+"""
+
+from __future__ import annotations
+
+from typing import Sequence
+
+import torch
+
+from . import engine
+from .plan import BatchPlan
+from .transforms import Pending
+
+
+def _cat(x):
+    try:
+        x = [torch.as_tensor(y) for y in x]
+    except Exception:
+        return x
+    try:
+        return torch.stack(x)
+    except Exception:
+        return x
+
+
+def execute_pending(groups: Sequence[Sequence[Pending]]) -> list[torch.Tensor]:
+    """``groups[g]`` = the entries of one key over the batch (same output shape): returns one
+    ``[B, C, H, W, D]`` float32 tensor per group, all produced by the same fused launch(es)."""
+    plans, dsts, outs = [], [], []
+    for entries in groups:
+        first = entries[0]
+        out = torch.empty((len(entries), *first.shape), dtype=torch.float32, device=first.device)
+        outs.append(out)
+        for b, e in enumerate(entries):
+            plans.append(e.plan)
+            dsts.extend(out[b, c] for c in range(e.n_channels))
+    if plans:
+        engine.execute(BatchPlan.concat(plans), dsts)
+    return outs
+
+
+def safe_collate(X):
+    """Mirror of ``adell_mri.utils.safe_collate`` with fused execution of pending entries."""
+    example = X[0]
+    if isinstance(example, list):
+        return [_cat(e) for e in zip(*X)]
+    keys = list(example.keys())
+    out, groups, group_keys = {}, [], []
+    for k in keys:
+        vals = [x[k] if k in x else None for x in X]
+        if all(isinstance(v, Pending) for v in vals):
+            if len({(v.shape, str(v.device)) for v in vals}) == 1:
+                groups.append(vals)
+                group_keys.append(k)
+                continue
+            # ragged shapes: the reference returns the list of per-sample tensors
+            out[k] = [v.tensor() for v in vals]
+            continue
+        vals = [v.tensor() if isinstance(v, Pending) else v for v in vals]
+        out[k] = _cat(vals)
+    for k, t in zip(group_keys, execute_pending(groups)):
+        out[k] = t
+    return {k: out[k] for k in keys}
+
+
+def safe_collate_crops(X):
+    """Mirror of ``adell_mri.utils.safe_collate_crops`` (lists of crops are flattened first)."""
+    flat = []
+    for x in X:
+        flat.extend(x)
+    return safe_collate(flat)

@@ -1,0 +1,537 @@
+"""Mirror of ``adell_mri/transform_factory`` for the fused GPU hot path.
+
+Same names, keys and argument meaning as the reference's pipeline builders
+(/root/reference/adell_mri/transform_factory/transforms.py:53-67,70-263,367-557,706-820;
+/root/reference/adell_mri/transform_factory/augmentations.py:19-178,181-320,391-516;
+/root/reference/adell_mri/modules/augmentations.py:10-256), built from the lazy dictionary
+transforms of :mod:`adell_mri_b200.transforms`, so an entrypoint can swap
+
+    from adell_mri.transform_factory import SegmentationTransforms, get_augmentations_unet
+    from adell_mri.utils.utils import safe_collate
+
+for the same names from this package.  What differs by design:
+
+* samples enter as channel-first device tensors (the device-resident analogue of what
+  ``LoadImaged`` + ``Orientationd`` hand on); file loading, re-orientation, ``Spacingd`` and
+  ``Resized`` are outside the hot path and raise if requested;
+* members of the augmentation vocabulary that are not gathers / pointwise maps raise
+  ``NotImplementedError`` instead of silently doing something else.
+"""
+
+from __future__ import annotations
+
+import itertools
+from dataclasses import dataclass
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, stats
+from . import transforms as T
+from .transforms import Pending
+
+ADC_FACTOR = -2 / 3  # transforms.py:25
+IMAGE_INTERPOLATION = "bilinear"
+
+
+# --------------------------------------------------------------------------- custom transforms
+class _DeviceIntensity(T.MapTransform):
+    """Cached-stage intensity op evaluated by the exact intensity-program kernel
+    (``y = ((x*m0 - a)/d)*m1*m2 + b``, every step rounded to fp32, identity steps skipped)."""
+
+    def coefs(self, mm: torch.Tensor) -> torch.Tensor:
+        raise NotImplementedError
+
+    def __call__(self, data):
+        d = dict(data)
+        for k in self.key_iterator(d):
+            x = d[k].tensor() if isinstance(d[k], Pending) else d[k]
+            flat = [x.contiguous().reshape(-1)]
+            mm = stats.minmax(flat)
+            d[k] = stats.intensity_map(flat, self.coefs(mm))[0].reshape(x.shape)
+        return d
+
+
+class ConditionalRescalingd(_DeviceIntensity):
+    """/root/reference/adell_mri/utils/monai_transforms/image_intensity_ops.py:49-103:
+    ``if X.max() > max_value: X = X * scale``."""
+
+    def __init__(self, keys, max_value: float, scale: float):
+        super().__init__(keys, allow_missing_keys=True)
+        self.max_value, self.scale = max_value, scale
+
+    def coefs(self, mm):
+        c = torch.tensor([[1.0, 0.0, 1.0, 1.0, 1.0, 0.0]], dtype=torch.float32, device=mm.device).repeat(mm.shape[0], 1)
+        c[:, 0] = torch.where(mm[:, 1] > self.max_value, float(np.float32(self.scale)), 1.0)
+        return c
+
+
+class Offsetd(_DeviceIntensity):
+    """image_intensity_ops.py:106-143: ``X - offset`` (the array minimum when ``offset`` is None)."""
+
+    def __init__(self, keys, offset: float | None = None):
+        super().__init__(keys, allow_missing_keys=False)
+        self.offset = offset
+
+    def coefs(self, mm):
+        c = torch.tensor([[1.0, 0.0, 1.0, 1.0, 1.0, 0.0]], dtype=torch.float32, device=mm.device).repeat(mm.shape[0], 1)
+        c[:, 1] = mm[:, 0] if self.offset is None else float(np.float32(self.offset))
+        return c
+
+
+class CopyEntryd(T.Transform):
+    """/root/reference/adell_mri/utils/monai_transforms/generic_data_ops.py:7-26 (``out_keys`` is
+    an ``input_key -> output_key`` dict); the recorded chain is cloned, the voxels are shared."""
+
+    def __init__(self, keys, out_keys):
+        self.keys = list(keys)
+        self.out_keys = dict(out_keys) if isinstance(out_keys, dict) else dict(zip(keys, out_keys))
+
+    def __call__(self, data):
+        d = dict(data)
+        for k in list(d.keys()):
+            if k in self.keys and k in self.out_keys:
+                d[k] = T.as_pending(d[k])
+                d[self.out_keys[k]] = d[k].clone()
+        return d
+
+
+class AdjustSizesd(T.MapTransform):
+    """/root/reference/adell_mri/utils/monai_transforms/image_ops.py:368-438, ``mode="crop"``:
+    centre-crop every key to the per-axis minimum size over the keys."""
+
+    def __init__(self, keys, ndim: int = 3, mode: str = "pad"):
+        super().__init__(keys)
+        if mode != "crop":
+            raise NotImplementedError("AdjustSizesd: only mode='crop' is used on the hot path")
+        self.ndim = ndim
+
+    def __call__(self, data):
+        d = dict(data)
+        for k in self.key_iterator(d):
+            d[k] = T.as_pending(d[k])
+        target = np.min(np.array([d[k].spatial_shape for k in self.keys]), axis=0)
+        for k in self.keys:
+            d[k].plan.center_crop([int(x) for x in target])
+        return d
+
+
+# --------------------------------------------------------------------------- workhorse (SSL)
+generic_augments = ["gaussian_noise", "shift_intensity", "scale_intensity", "contrast", "gaussian_smooth_x",
+                    "gaussian_smooth_y", "gaussian_smooth_z", "gaussian_sharpen_x", "gaussian_sharpen_y",
+                    "gaussian_sharpen_z", "coarse_dropout"]
+mri_specific_augments = ["rbf", "gibbs_noise", "spike_noise", "rician_noise"]
+spatial_augments = ["rotate_x", "rotate_y", "rotate_z", "translate_x", "translate_y", "translate_z",
+                    "shear_x", "shear_y", "shear_z", "scale_x", "scale_y", "scale_z"]
+#: members of the reference vocabulary that the fused path implements
+FUSED_AUGMENTS = ["gaussian_noise", "shift_intensity", "scale_intensity", *spatial_augments]
+
+
+def _aug_param_dict():
+    """modules/augmentations.py:103-129 (a fresh copy: the reference mutates its dict in place)."""
+    d = {"gaussian_noise": {"std": 1}, "shift_intensity": {"offsets": 0.5}, "scale_intensity": {"factors": 0.5}}
+    for c in ["x", "y", "z"]:
+        t = 30 if c != "z" else 5
+        a = np.pi / 6 if c != "z" else np.pi / 16
+        d["rotate_" + c] = {"rotate_range": a}
+        d["translate_" + c] = {"translate_range": t}
+        d["shear_" + c] = {"shear_range": 0.5}
+        d["scale_" + c] = {"scale_range": 0.3}
+    return d
+
+
+def _axis_tuple(c: str, value):
+    i = "xyz".index(c)
+    out = [0, 0, 0]
+    out[i] = value
+    return tuple(out)
+
+
+def _param_correction(name: str, x):
+    """modules/augmentations.py:131-162."""
+    kind, _, c = name.partition("_")
+    if kind in ("rotate", "translate") and c in "xyz" and c:
+        return _axis_tuple(c, (-x, x))
+    if kind in ("shear", "scale") and c in "xyz" and c and name not in ("scale_intensity",):
+        return _axis_tuple(c, (1 - x, 1 + x))
+    return x
+
+
+def get_transform_d(keys, transform_str: str, params: dict, mask_keys=()):
+    """modules/augmentations.py:165-186 for the fused members (``prob=1.0`` each)."""
+    if transform_str not in FUSED_AUGMENTS:
+        raise NotImplementedError(f"workhorse member '{transform_str}' is outside the fused GPU hot path")
+    params = {k: (_param_correction(transform_str, v) if transform_str in spatial_augments else v) for k, v in params.items()}
+    if transform_str == "gaussian_noise":
+        return T.RandGaussianNoised(keys, prob=1.0, **params)
+    if transform_str == "shift_intensity":
+        return T.RandShiftIntensityd(keys, prob=1.0, **params)
+    if transform_str == "scale_intensity":
+        return T.RandScaleIntensityd(keys, prob=1.0, **params)
+    mode = ["bilinear" if k not in mask_keys else "nearest" for k in keys]
+    return T.RandAffined(keys, prob=1.0, mode=mode, padding_mode="zeros", **params)
+
+
+class AugmentationWorkhorsed(T.RandomizableTransform):
+    """modules/augmentations.py:189-256: ``np.random.choice(augmentations, N, replace=False)`` on
+    the GLOBAL numpy stream (as the reference does), then the chosen members in that order.  The
+    members' own streams are seeded from this transform's ``set_random_state`` (the reference
+    leaves them unseeded, i.e. not reproducible; seeding them is a superset of that behaviour)."""
+
+    def __init__(self, augmentations, keys=None, mask_keys=(), max_mult: float = 1.0, N: int = 5,
+                 aug_param_dict=None, dropout_size=(32, 32, 2)):
+        super().__init__(1.0)
+        self.augmentations = list(augmentations)
+        self.keys, self.mask_keys, self.max_mult, self.N = keys, list(mask_keys), max_mult, N
+        base = aug_param_dict if aug_param_dict is not None else _aug_param_dict()
+        self.param_dict = {k: {kk: base[k][kk] * max_mult for kk in base[k]} for k in self.augmentations}
+        self.transforms = {k: get_transform_d(keys, k, self.param_dict[k], self.mask_keys) for k in self.param_dict}
+
+    def set_random_state(self, seed=None, state=None):
+        super().set_random_state(seed, state)
+        for k in self.augmentations:
+            self.transforms[k].set_random_state(seed=int(self.R.randint(T.MAX_SEED, dtype="uint32")))
+        return self
+
+    def __call__(self, X):
+        t_list = np.random.choice(self.augmentations, self.N, replace=False)
+        self.last_choice = [str(t) for t in t_list]
+        for t in t_list:
+            X = self.transforms[t](X)
+        return X
+
+
+# --------------------------------------------------------------------------- augmentation builders
+_UNET_VALID = ["intensity", "noise", "rbf", "affine", "shear", "flip", "blur", "distort", "lowres", "trivial"]
+_CLASS_VALID = ["intensity", "noise", "rbf", "affine", "shear", "flip", "blur", "lowres", "distort", "trivial"]
+_FUSED_TOKENS = {"affine", "shear", "flip", "trivial"}
+
+
+def _check_tokens(augment, valid):
+    for a in augment:
+        if a not in valid:
+            raise NotImplementedError("augment can only contain {}".format(valid))
+    bad = [a for a in augment if a not in _FUSED_TOKENS]
+    if bad:
+        raise NotImplementedError(f"augmentations {bad} are outside the fused GPU hot path (DESIGN.md, out of scope)")
+
+
+def get_augmentations_unet(augment, all_keys, image_keys, t2_keys, random_crop_size: list[int] = None,
+                           has_label: bool = True, n_crops: int = 1, flip_axis: list[int] = [0, 1]):
+    """augmentations.py:19-178."""
+    _check_tokens(augment, _UNET_VALID)
+    interpolation = ["bilinear" if k in image_keys else "nearest" for k in all_keys]
+    augments = []
+    prob = 0.2
+    if "trivial" in augment:
+        augments.append(T.Identityd(image_keys))
+        prob = 1.0
+    if "affine" in augment:
+        augments.append(T.RandAffined(all_keys, rotate_range=[np.pi / 8, np.pi / 8, np.pi / 16], prob=prob, mode=interpolation))
+    if "shear" in augment:
+        augments.append(T.RandAffined(all_keys, shear_range=((0.9, 1.1), (0.9, 1.1), (0.9, 1.1)), prob=prob, mode=interpolation))
+    flip_transform = [T.RandFlipd(all_keys, spatial_axis=[axis], prob=0.25) for axis in flip_axis] if "flip" in augment else []
+    if "trivial" in augment:
+        augments = T.Compose([T.OneOf(augments), *flip_transform])
+    else:
+        augments = T.Compose([*augments, *flip_transform])
+    if random_crop_size is not None:
+        pre_final_size = [int(i * 1.10) for i in random_crop_size]
+        new_augments = []
+        if has_label is True:
+            new_augments.append(T.RandCropByPosNegLabeld(
+                [*image_keys, "mask"], "mask", pre_final_size, allow_smaller=True, num_samples=n_crops,
+                fg_indices_key="mask_fg_indices", bg_indices_key="mask_bg_indices"))
+        else:
+            new_augments.append(T.RandSpatialCropd(image_keys, pre_final_size))
+        augments = T.Compose([*new_augments, augments,
+                              T.CenterSpatialCropd([*image_keys, "mask"] if has_label else image_keys, random_crop_size)])
+    return augments
+
+
+def get_augmentations_class(augment, image_keys, mask_key, t2_keys, flip_axis: list[int] = [0, 1], prob: float = 0.1,
+                            n_transforms_trivial: int = 1):
+    """augmentations.py:181-320."""
+    _check_tokens(augment, _CLASS_VALID)
+    all_keys_with_mask = [k for k in image_keys]
+    if mask_key is not None:
+        all_keys_with_mask.append(mask_key)
+    intp = ["bilinear" if k != mask_key else "nearest" for k in all_keys_with_mask]
+    augments = []
+    if "trivial" in augment:
+        augments.append(T.Identityd(image_keys))
+        prob = 1.0
+    if "flip" in augment:
+        if isinstance(flip_axis, int):
+            flip_axis = [flip_axis]
+        flips = []
+        for i in range(len(flip_axis)):
+            for axis_to_flip in itertools.combinations(flip_axis, i + 1):
+                flips.append(T.RandFlipd(all_keys_with_mask, prob=prob, spatial_axis=axis_to_flip))
+        augments.append(T.OneOf(flips))
+    if "affine" in augment:
+        augments.append(T.RandAffined(all_keys_with_mask, translate_range=[4, 4, 1], rotate_range=[np.pi / 16],
+                                      scale_range=[0.1, 0.1, 0.05], prob=prob, mode=intp, padding_mode="zeros"))
+    if "shear" in augment:
+        augments.append(T.RandAffined(all_keys_with_mask, shear_range=((0.9, 1.1), (0.9, 1.1), (0.9, 1.1)), prob=prob,
+                                      mode=intp, padding_mode="zeros"))
+    if "trivial" in augment:
+        return T.SomeOf(augments, num_transforms=n_transforms_trivial)
+    return T.Compose(augments)
+
+
+def flatten_box(box, roi_size):
+    """augmentations.py:402-406."""
+    box1 = np.array(box[::2])
+    box2 = np.array(roi_size) - np.array(box[1::2])
+    return np.concatenate([box1, box2]).astype(np.float32)
+
+
+def get_augmentations_ssl(all_keys, copied_keys, scaled_crop_size, roi_size, vicregl: bool, different_crop: bool,
+                          n_transforms=3, n_dim: int = 3, skip_augmentations: bool = False, aug_list=None):
+    """augmentations.py:391-516.  ``aug_list`` defaults to the fused members of the reference's
+    list (after its own removals); passing the full reference list raises for the first member
+    that is not on the fused path."""
+    roi_size = tuple(int(x) for x in roi_size)
+    all_keys, copied_keys = list(all_keys), list(copied_keys)
+    transforms_to_remove = []
+    if vicregl is True:
+        transforms_to_remove.extend(spatial_augments)
+    if n_dim == 2:
+        transforms_to_remove.extend(["rotate_z", "translate_z", "shear_z", "scale_z"])
+    else:
+        transforms_to_remove.extend(["gaussian_sharpen_x", "gaussian_sharpen_y", "gaussian_sharpen_z"])
+    if aug_list is None:
+        aug_list = [x for x in generic_augments + mri_specific_augments + spatial_augments if x in FUSED_AUGMENTS]
+    aug_list = [x for x in aug_list if x not in transforms_to_remove]
+    cropping_strategy = []
+    if scaled_crop_size is not None:
+        raise NotImplementedError("scaled_crop_size uses Resized (area interpolation): outside the fused hot path")
+    if skip_augmentations is True:
+        return cropping_strategy
+    if vicregl is True:
+        cropping_strategy.extend([
+            T.RandSpatialCropd(all_keys, roi_size=roi_size, random_size=False),
+            T.RandSpatialCropd(copied_keys, roi_size=roi_size, random_size=False),
+            T.ExposeTransformKeyMetad(all_keys[0], "RandSpatialCrop", ["extra_info", "cropped"], "box_1"),
+            T.ExposeTransformKeyMetad(copied_keys[0], "RandSpatialCrop", ["extra_info", "cropped"], "box_2"),
+            T.Lambdad(["box_1", "box_2"], lambda box: flatten_box(box, roi_size)),
+        ])
+    elif different_crop is True:
+        cropping_strategy.extend([
+            T.RandSpatialCropd(all_keys, roi_size=roi_size, random_size=False),
+            T.RandSpatialCropd(copied_keys, roi_size=roi_size, random_size=False),
+        ])
+    else:
+        cropping_strategy.append(T.RandSpatialCropd(all_keys + copied_keys, roi_size=roi_size, random_size=False))
+    dropout_size = tuple(x // 10 for x in roi_size)
+    out = [*cropping_strategy,
+           AugmentationWorkhorsed(augmentations=aug_list, keys=all_keys, mask_keys=[], max_mult=0.5, N=n_transforms,
+                                  dropout_size=dropout_size)]
+    if len(copied_keys) > 0:
+        out.append(AugmentationWorkhorsed(augmentations=aug_list, keys=copied_keys, mask_keys=[], max_mult=0.5,
+                                          N=n_transforms, dropout_size=dropout_size))
+    return out
+
+
+# --------------------------------------------------------------------------- pipeline builders
+@dataclass
+class TransformMixin:
+    """transforms.py:45-67."""
+
+    def pre_transforms(self):
+        raise NotImplementedError("pre_transform must be implemented")
+
+    def post_transforms(self):
+        raise NotImplementedError("post_transform must be implemented")
+
+    def transforms(self, augmentations=None, final_transforms=None):
+        transforms = [*self.pre_transforms()]
+        if augmentations:
+            if isinstance(augmentations, T.Transform):
+                transforms.append(augmentations)
+            else:
+                transforms.extend(augmentations)
+        transforms.extend(self.post_transforms())
+        if final_transforms is not None:
+            transforms.extend(final_transforms)
+        return T.Compose(transforms)
+
+
+def _reject(name, value):
+    if value is not None and value is not False and value != []:
+        raise NotImplementedError(f"{name} belongs to the cached loading stage (file IO / Spacingd / Resized): outside the fused hot path")
+
+
+def _intensity_stage(non_adc_keys, adc_keys, offset_adc: bool):
+    """transforms.py:143-155 (seg), 430-443 (class, with Offsetd), 772-786 (ssl)."""
+    out = []
+    if len(non_adc_keys) > 0:
+        out.append(T.ScaleIntensityd(list(non_adc_keys), minv=0.0, maxv=1.0))
+    if len(adc_keys) > 0:
+        out.append(ConditionalRescalingd(list(adc_keys), 500, 0.001))
+        if offset_adc:
+            out.append(Offsetd(list(adc_keys), None))
+        out.append(T.ScaleIntensityd(list(adc_keys), None, None, ADC_FACTOR))
+    return out
+
+
+@dataclass
+class SegmentationTransforms(TransformMixin):
+    """transforms.py:70-263 (in-scope fields; the others must stay at their defaults)."""
+
+    all_keys: Sequence[str]
+    image_keys: Sequence[str]
+    label_keys: Sequence[str] | None
+    non_adc_keys: Sequence[str]
+    adc_keys: Sequence[str]
+    target_spacing: Sequence[float] | None = None
+    intp: Sequence[str] | None = None
+    intp_resampling_augmentations: Sequence[str] | None = None
+    output_image_key: str = "image"
+    possible_labels: Sequence[int] = (0, 1)
+    positive_labels: Sequence[int] = (1,)
+    all_aux_keys: Sequence[str] = ()
+    resize_keys: Sequence[str] = ()
+    feature_keys: Sequence[str] = ()
+    aux_key_net: str | None = None
+    feature_key_net: str | None = None
+    resize_size: Sequence[int] | None = None
+    crop_size: Sequence[int] | None = None
+    pad_size: Sequence[int] | None = None
+    random_crop_size: Sequence[int] | None = None
+    label_mode: str | None = None
+    fill_missing: bool = False
+    brunet: bool = False
+    track_meta: bool = False
+    convert_to_tensor: bool = True
+
+    def __post_init__(self):
+        _reject("target_spacing", self.target_spacing)
+        _reject("resize_size", self.resize_size)
+        _reject("fill_missing", self.fill_missing)
+        _reject("brunet", self.brunet)
+        _reject("all_aux_keys", list(self.all_aux_keys))
+        _reject("feature_keys", list(self.feature_keys))
+        self.all_keys, self.image_keys = list(self.all_keys), list(self.image_keys)
+        self.transform_keys = [self.output_image_key]
+        self.mask_key = ["mask"] if self.label_keys is not None else []
+        if self.label_keys is not None and list(self.label_keys) != ["mask"]:
+            raise NotImplementedError("label combination (CombineBinaryLabelsd) runs in the cached loading stage: "
+                                      "hand the combined 0/1 label in under the key 'mask'")
+
+    def pre_transforms(self):
+        keys = self.all_keys + ([] if self.label_keys is None or "mask" in self.all_keys else ["mask"])
+        transforms = _intensity_stage(self.non_adc_keys, self.adc_keys, offset_adc=False)
+        if self.pad_size is not None:
+            transforms.append(T.SpatialPadd(keys, self.pad_size))
+        if self.crop_size is not None:
+            transforms.append(T.CenterSpatialCropd(keys, self.crop_size))
+        transforms.append(T.EnsureTyped(keys, dtype=torch.float32))
+        if self.random_crop_size is not None:
+            if self.label_keys is not None:
+                transforms.append(AdjustSizesd([*self.image_keys, "mask"], mode="crop"))
+                transforms.append(T.FgBgToIndicesd("mask"))
+            else:
+                transforms.append(AdjustSizesd(self.image_keys, mode="crop"))
+        return transforms
+
+    def post_transforms(self):
+        transforms = [T.ConcatItemsd(self.image_keys, self.output_image_key)]
+        if self.convert_to_tensor is True:
+            transforms.append(T.ToTensord([self.output_image_key] + self.mask_key, track_meta=self.track_meta, dtype=torch.float32))
+        if not self.track_meta:
+            transforms.append(T.SelectItemsd(self.transform_keys + self.mask_key))
+        return transforms
+
+
+@dataclass
+class ClassificationTransforms(TransformMixin):
+    """transforms.py:367-557 (image part; label / tabular / confounder entries pass through)."""
+
+    keys: Sequence[str]
+    adc_keys: Sequence[str]
+    clinical_feature_keys: Sequence[str] = ()
+    target_spacing: Sequence[float] | None = None
+    crop_size: Sequence[int] | None = None
+    pad_size: Sequence[int] | None = None
+    image_masking: bool = False
+    image_crop_from_mask: bool = False
+    mask_key: str | None = None
+    branched: bool = False
+    target_size: Sequence[int] | None = None
+
+    def __post_init__(self):
+        _reject("target_spacing", self.target_spacing)
+        _reject("target_size", self.target_size)
+        _reject("image_masking", self.image_masking)
+        _reject("image_crop_from_mask", self.image_crop_from_mask)
+        self.keys = list(self.keys)
+        self.non_adc_keys = [k for k in self.keys if k not in self.adc_keys]
+        self.all_keys = [k for k in self.keys]
+        if self.mask_key is not None:
+            self.all_keys.append(self.mask_key)
+        self.crop_size_with_margin = [int(j) + 16 for j in self.crop_size] if self.crop_size is not None else None
+        self.crop_size_final = [int(j) for j in self.crop_size] if self.crop_size is not None else None
+
+    def pre_transforms(self):
+        transforms = _intensity_stage(self.non_adc_keys, self.adc_keys, offset_adc=True)
+        if self.pad_size is not None:
+            transforms.append(T.SpatialPadd(self.all_keys, self.crop_size_with_margin))
+        if self.crop_size is not None:
+            transforms.append(T.CenterSpatialCropd(self.all_keys, self.crop_size_with_margin))
+        transforms.append(T.EnsureTyped(self.all_keys))
+        return transforms
+
+    def post_transforms(self):
+        transforms = []
+        if self.crop_size is not None:
+            transforms.append(T.CenterSpatialCropd(self.all_keys, self.crop_size_final))
+        if self.branched is not True:
+            transforms.append(T.ConcatItemsd(self.all_keys, "image"))
+        return transforms
+
+
+@dataclass
+class SSLTransforms(TransformMixin):
+    """transforms.py:706-820."""
+
+    all_keys: Sequence[str]
+    copied_keys: Sequence[str]
+    adc_keys: Sequence[str]
+    non_adc_keys: Sequence[str]
+    target_spacing: Sequence[float] | None = None
+    crop_size: Sequence[int] | None = None
+    pad_size: Sequence[int] | None = None
+    resize_size: Sequence[int] | None = None
+    in_channels: int = 1
+    n_dim: int = 3
+    skip_augmentations: bool = False
+    jpeg_dataset: bool = False
+
+    def __post_init__(self):
+        _reject("target_spacing", self.target_spacing)
+        _reject("resize_size", self.resize_size)
+        _reject("jpeg_dataset", self.jpeg_dataset)
+        if self.n_dim != 3:
+            raise NotImplementedError("the fused hot path is volumetric (n_dim=3)")
+        self.all_keys, self.copied_keys = list(self.all_keys), list(self.copied_keys)
+        self.output_keys = ["image"] if self.skip_augmentations else ["augmented_image_1", "augmented_image_2"]
+        self.concat_keys = [self.all_keys] if self.skip_augmentations else [self.all_keys, self.copied_keys]
+
+    def pre_transforms(self):
+        transforms = _intensity_stage(self.non_adc_keys, self.adc_keys, offset_adc=False)
+        if self.crop_size is not None:
+            transforms.append(T.CenterSpatialCropd(self.all_keys, [int(j) for j in self.crop_size]))
+        if self.pad_size is not None:
+            transforms.append(T.SpatialPadd(self.all_keys, [int(j) for j in self.pad_size]))
+        transforms.append(T.EnsureTyped(self.all_keys))
+        if self.skip_augmentations is False:
+            transforms.append(CopyEntryd(self.all_keys, {k: kk for k, kk in zip(self.all_keys, self.copied_keys)}))
+        return transforms
+
+    def post_transforms(self):
+        transforms = [T.ConcatItemsd(keys, output_key) for keys, output_key in zip(self.concat_keys, self.output_keys)]
+        transforms.append(T.ToTensord(self.output_keys, track_meta=False))
+        return transforms

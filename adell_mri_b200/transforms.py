@@ -1,0 +1,761 @@
+"""Dictionary transforms with the MONAI calling convention, executed lazily on the GPU.
+
+The reference wires ``monai.transforms.*`` dictionary transforms into ``Compose`` pipelines
+(/root/reference/adell_mri/transform_factory/augmentations.py:19-178,181-320,391-516;
+/root/reference/adell_mri/transform_factory/transforms.py:53-67) that DataLoader workers run
+eagerly on the CPU, one full-volume copy per op.  The classes here obey the same protocol
+(callable ``dict -> dict | list[dict]``, ``.R`` / ``set_random_state`` / ``randomize`` on the
+random ones, the same constructor arguments and the same RandomState draw order †) but do not
+touch voxels: every op is *recorded* on a :class:`Pending` entry (a one-sample
+:class:`~adell_mri_b200.plan.BatchPlan`).  :func:`adell_mri_b200.collate.safe_collate` then
+concatenates the recorded chains of the whole batch and runs them as ONE fused K1 launch per
+resample pass, writing straight into the collated ``[B, C, H, W, D]`` tensors.
+
+† draw orders restated from MONAI 1.3-1.6 (not importable here): see oracle/monai_restated.py.
+Transforms of the reference vocabulary that are not gathers / pointwise maps (blur, bias field,
+Gibbs, grid distortion, low-res, coarse dropout ...) raise ``NotImplementedError`` — they are
+outside the fused hot path (out of scope).
+"""
+
+from __future__ import annotations
+
+import itertools
+from typing import Callable, Hashable, Sequence
+
+import numpy as np
+import torch
+
+from . import geometry
+from .plan import BatchPlan
+from .sampling import MAX_SEED, RandAffineSampler, rand_param
+
+# --------------------------------------------------------------------------- execution mode
+_MODE = {"strict": False, "fast": False, "noise": "injected"}
+
+
+def set_mode(strict: bool | None = None, fast: bool | None = None, noise: str | None = None):
+    """Global execution mode of newly created :class:`Pending` entries.
+
+    ``strict``: bit-faithful ATen operation order for trilinear resampling (parity mode);
+    ``fast``: consecutive resamples are composed into one matrix (documented deviation);
+    ``noise``: ``"injected"`` (host RandomState.normal tensor, as the reference draws it) or
+    ``"philox"`` (device-side counter-based normal with the host-drawn sigma)."""
+    if strict is not None:
+        _MODE["strict"] = bool(strict)
+    if fast is not None:
+        _MODE["fast"] = bool(fast)
+    if noise is not None:
+        if noise not in ("injected", "philox"):
+            raise ValueError("noise must be 'injected' or 'philox'")
+        _MODE["noise"] = noise
+    return dict(_MODE)
+
+
+class Pending:
+    """One dict entry ``[C, H, W, D]`` whose transform chain is recorded, not yet executed."""
+
+    def __init__(self, tensor: torch.Tensor | None = None, plan: BatchPlan | None = None, meta: dict | None = None):
+        if plan is None:
+            if tensor.dim() != 4:
+                raise ValueError("expected a channel-first [C, H, W, D] volume")
+            plan = BatchPlan([tensor[c] for c in range(tensor.shape[0])], fast=_MODE["fast"], strict=_MODE["strict"])
+        self.plan = plan
+        self.meta = meta if meta is not None else {}
+
+    @property
+    def n_channels(self) -> int:
+        return self.plan.n
+
+    @property
+    def spatial_shape(self) -> tuple:
+        return tuple(int(x) for x in self.plan.shape[0])
+
+    @property
+    def shape(self) -> tuple:
+        return (self.plan.n, *self.spatial_shape)
+
+    @property
+    def device(self):
+        return self.plan.device
+
+    def clone(self) -> "Pending":
+        return Pending(plan=BatchPlan.concat([self.plan]), meta={k: (list(v) if isinstance(v, list) else v) for k, v in self.meta.items()})
+
+    @staticmethod
+    def cat(entries: Sequence["Pending"]) -> "Pending":
+        return Pending(plan=BatchPlan.concat([e.plan for e in entries]))
+
+    def tensor(self) -> torch.Tensor:
+        """Materialise this entry alone (one launch per pass)."""
+        from . import engine
+
+        out = torch.empty(self.shape, dtype=torch.float32, device=self.device)
+        engine.execute(self.plan, [out[c] for c in range(self.plan.n)])
+        return out
+
+
+def as_pending(x) -> Pending:
+    if isinstance(x, Pending):
+        return x
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(x)
+    if not isinstance(x, torch.Tensor):
+        raise TypeError(f"cannot record transforms on {type(x)}")
+    return Pending(x)
+
+
+def _shape_of(x) -> tuple:
+    return tuple(x.shape)
+
+
+# --------------------------------------------------------------------------- protocol
+class Transform:
+    def __call__(self, data):
+        raise NotImplementedError
+
+
+class Randomizable:
+    """MONAI ``Randomizable``: own ``np.random.RandomState`` in ``self.R`` †."""
+
+    R: np.random.RandomState = np.random.RandomState()
+
+    def set_random_state(self, seed: int | None = None, state: np.random.RandomState | None = None):
+        if seed is not None:
+            self.R = np.random.RandomState(int(seed) % MAX_SEED)
+            return self
+        if state is not None:
+            if not isinstance(state, np.random.RandomState):
+                raise TypeError(f"state must be None or a np.random.RandomState but is {type(state).__name__}.")
+            self.R = state
+            return self
+        self.R = np.random.RandomState()
+        return self
+
+    def randomize(self, data=None) -> None:
+        raise NotImplementedError
+
+
+class MapTransform(Transform):
+    def __init__(self, keys, allow_missing_keys: bool = False):
+        self.keys = tuple(keys) if isinstance(keys, (list, tuple)) else (keys,)
+        if not self.keys:
+            raise ValueError("keys must be non empty.")
+        self.allow_missing_keys = allow_missing_keys
+
+    def key_iterator(self, data: dict):
+        for k in self.keys:
+            if k in data:
+                yield k
+            elif not self.allow_missing_keys:
+                raise KeyError(f"Key `{k}` of transform `{type(self).__name__}` was missing in the data")
+
+    def first_key(self, data: dict):
+        for k in self.key_iterator(data):
+            return k
+        return ()
+
+
+class RandomizableTransform(Randomizable, Transform):
+    def __init__(self, prob: float = 1.0, do_transform: bool = True):
+        self._do_transform = do_transform
+        self.prob = min(max(prob, 0.0), 1.0)
+
+    def randomize(self, data=None) -> None:
+        self._do_transform = self.R.rand() < self.prob
+
+
+def _per_key(value, keys, name="mode"):
+    if isinstance(value, (list, tuple)):
+        if len(value) != len(keys):
+            raise ValueError(f"{name} must have one entry per key")
+        return list(value)
+    return [value] * len(keys)
+
+
+def apply_transform(t: Callable, data):
+    """``monai.transforms.apply_transform``: a list input maps the transform over its items."""
+    if isinstance(data, (list, tuple)):
+        return [apply_transform(t, d) for d in data]
+    return t(data)
+
+
+class Compose(Randomizable, Transform):
+    """``monai.transforms.Compose`` †: sequential application, list outputs fan out, and
+    ``set_random_state(seed)`` hands every Randomizable child ``R.randint(2**32)`` in order."""
+
+    def __init__(self, transforms=None):
+        if transforms is None:
+            transforms = []
+        if not isinstance(transforms, (list, tuple)):
+            transforms = [transforms]
+        self.transforms = tuple(transforms)
+        self.set_random_state()  # fresh entropy, like MONAI without set_determinism (no draw from the global stream)
+
+    def set_random_state(self, seed=None, state=None):
+        super().set_random_state(seed=seed, state=state)
+        for t in self.transforms:
+            if isinstance(t, Randomizable):
+                t.set_random_state(seed=int(self.R.randint(MAX_SEED, dtype="uint32")))
+        return self
+
+    def randomize(self, data=None) -> None:
+        for t in self.transforms:
+            if isinstance(t, Randomizable):
+                try:
+                    t.randomize(data)
+                except TypeError:
+                    pass
+
+    def flatten(self):
+        out = []
+        for t in self.transforms:
+            if type(t) is Compose:
+                out.extend(t.flatten().transforms)
+            else:
+                out.append(t)
+        return Compose(out)
+
+    def __len__(self):
+        return len(self.flatten().transforms) if self.transforms else 0
+
+    def __call__(self, data):
+        for t in self.transforms:
+            data = apply_transform(t, data)
+        return data
+
+
+class OneOf(Compose):
+    """``monai.transforms.OneOf`` †: ``R.multinomial(1, weights).argmax()`` picks the member."""
+
+    def __init__(self, transforms=None, weights=None):
+        super().__init__(transforms)
+        n = len(self.transforms)
+        if n == 0:
+            self.weights = []
+        elif weights is None:
+            self.weights = [1.0 / n] * n
+        else:
+            w = np.asarray(weights, dtype=float)
+            if len(w) != n or (w < 0).any() or w.sum() <= 0:
+                raise ValueError("weights must be non-negative, one per transform, and not all zero")
+            self.weights = list(w / w.sum())
+
+    def __call__(self, data):
+        if len(self.transforms) == 0:
+            return data
+        index = int(self.R.multinomial(1, self.weights).argmax())
+        return apply_transform(self.transforms[index], data)
+
+
+class SomeOf(Compose):
+    """``monai.transforms.SomeOf`` †: ``R.randint(min, max+1)`` members chosen by ``R.choice``."""
+
+    def __init__(self, transforms=None, num_transforms=None, replace: bool = False, weights=None):
+        super().__init__(transforms)
+        n = len(self.transforms)
+        if num_transforms is None:
+            self.min_num_transforms = self.max_num_transforms = n
+        elif isinstance(num_transforms, (tuple, list)):
+            self.min_num_transforms, self.max_num_transforms = (int(x) for x in num_transforms)
+        else:
+            self.min_num_transforms = self.max_num_transforms = int(num_transforms)
+        if self.max_num_transforms > n and not replace:
+            raise ValueError("num_transforms cannot exceed the number of transforms without replacement")
+        self.replace = replace
+        self.weights = None if weights is None else list(np.asarray(weights, float) / np.sum(weights))
+
+    def __call__(self, data):
+        if len(self.transforms) == 0:
+            return data
+        sample_size = self.R.randint(self.min_num_transforms, self.max_num_transforms + 1)
+        order = self.R.choice(len(self.transforms), sample_size, replace=self.replace, p=self.weights).tolist()
+        for i in order:
+            data = apply_transform(self.transforms[i], data)
+        return data
+
+
+# --------------------------------------------------------------------------- bookkeeping transforms
+class Identityd(MapTransform):
+    def __call__(self, data):
+        return dict(data)
+
+
+class EnsureTyped(MapTransform):
+    """Outputs of the fused path are always float32 device tensors: recorded as a no-op."""
+
+    def __init__(self, keys, dtype=None, track_meta=None, allow_missing_keys: bool = False, **_):
+        super().__init__(keys, allow_missing_keys)
+
+    def __call__(self, data):
+        return dict(data)
+
+
+ToTensord = EnsureTyped
+
+
+class SelectItemsd(MapTransform):
+    def __call__(self, data):
+        return {k: data[k] for k in self.key_iterator(data)}
+
+
+class Lambdad(MapTransform):
+    def __init__(self, keys, func, allow_missing_keys: bool = False):
+        super().__init__(keys, allow_missing_keys)
+        self.func = func
+
+    def __call__(self, data):
+        d = dict(data)
+        for k in self.key_iterator(d):
+            d[k] = self.func(d[k])
+        return d
+
+
+class CopyEntryd(MapTransform):
+    """/root/reference/adell_mri/utils/monai_transforms/generic_data_ops.py:7-26 — the reference
+    deep-copies the voxels; here the *recorded chain* is cloned (both views share the source)."""
+
+    def __init__(self, keys, new_keys):
+        super().__init__(keys)
+        self.new_keys = list(new_keys)
+
+    def __call__(self, data):
+        d = dict(data)
+        for k, nk in zip(self.keys, self.new_keys):
+            d[k] = as_pending(d[k])
+            d[nk] = d[k].clone()
+        return d
+
+
+class ConcatItemsd(MapTransform):
+    """Channel concatenation: the recorded chains are concatenated, voxels are written once."""
+
+    def __init__(self, keys, name: str, dim: int = 0, allow_missing_keys: bool = False):
+        super().__init__(keys, allow_missing_keys)
+        if dim != 0:
+            raise NotImplementedError("ConcatItemsd: only channel concatenation (dim=0) is on the fused path")
+        self.name = name
+
+    def __call__(self, data):
+        d = dict(data)
+        entries = [as_pending(d[k]) for k in self.key_iterator(d)]
+        if not entries:
+            return d
+        shapes = {e.spatial_shape for e in entries}
+        if len(shapes) != 1:
+            raise ValueError(f"ConcatItemsd: spatial shapes differ: {shapes}")
+        d[self.name] = Pending.cat(entries)
+        return d
+
+
+class ExposeTransformKeyMetad(Transform):
+    """/root/reference/adell_mri/utils/monai_transforms/generic_data_ops.py:75-119: exposes a value
+    recorded by an applied transform (here: ``extra_info.cropped`` of the last RandSpatialCrop)."""
+
+    def __init__(self, key: str, transform_class: str, nested_pattern: Sequence[str], output_key: str | None = None):
+        self.key, self.transform_class, self.nested_pattern = key, transform_class, list(nested_pattern)
+        self.output_key = output_key if output_key is not None else "_".join([key, transform_class])
+
+    def __call__(self, data):
+        d = dict(data)
+        ops = d[self.key].meta.get("applied_operations", []) if isinstance(d[self.key], Pending) else []
+        for op in ops:
+            if op["class"] == self.transform_class:
+                v = op
+                for p in self.nested_pattern:
+                    v = v[p]
+                d[self.output_key] = v
+        return d
+
+
+# --------------------------------------------------------------------------- integer geometry
+class SpatialPadd(MapTransform):
+    """``monai.transforms.SpatialPadd`` (method symmetric, constant 0) †."""
+
+    def __init__(self, keys, spatial_size, allow_missing_keys: bool = False, **_):
+        super().__init__(keys, allow_missing_keys)
+        self.spatial_size = [int(x) for x in spatial_size]
+
+    def __call__(self, data):
+        d = dict(data)
+        for k in self.key_iterator(d):
+            d[k] = as_pending(d[k])
+            d[k].plan.spatial_pad(self.spatial_size)
+        return d
+
+
+class CenterSpatialCropd(MapTransform):
+    def __init__(self, keys, roi_size, allow_missing_keys: bool = False):
+        super().__init__(keys, allow_missing_keys)
+        self.roi_size = [int(x) for x in roi_size]
+
+    def __call__(self, data):
+        d = dict(data)
+        for k in self.key_iterator(d):
+            d[k] = as_pending(d[k])
+            d[k].plan.center_crop(self.roi_size)
+        return d
+
+
+class SpatialCropd(MapTransform):
+    def __init__(self, keys, roi_start, roi_size, allow_missing_keys: bool = False):
+        super().__init__(keys, allow_missing_keys)
+        self.roi_start, self.roi_size = [int(x) for x in roi_start], [int(x) for x in roi_size]
+
+    def __call__(self, data):
+        d = dict(data)
+        for k in self.key_iterator(d):
+            d[k] = as_pending(d[k])
+            d[k].plan.crop(self.roi_start, self.roi_size)
+        return d
+
+
+class RandSpatialCropd(Randomizable, MapTransform):
+    """``monai.transforms.RandSpatialCropd`` †: randomised once on the first key's shape, the same
+    window for every key; records ``extra_info.cropped = [start0, size0-end0, start1, ...]``."""
+
+    def __init__(self, keys, roi_size, max_roi_size=None, random_center: bool = True, random_size: bool = False,
+                 allow_missing_keys: bool = False):
+        MapTransform.__init__(self, keys, allow_missing_keys)
+        self.roi_size = list(roi_size) if isinstance(roi_size, (list, tuple)) else [roi_size] * 3
+        self.max_roi_size = max_roi_size
+        self.random_center, self.random_size = random_center, random_size
+        self._size, self._start = None, None
+
+    def randomize(self, img_size) -> None:
+        size = [d if (r is None or r <= 0) else min(int(r), d) for d, r in zip(img_size, self.roi_size)]
+        if self.random_size:
+            mx = list(img_size) if self.max_roi_size is None else [min(int(m), d) for m, d in zip(self.max_roi_size, img_size)]
+            if any(a > b for a, b in zip(size, mx)):
+                raise ValueError(f"min ROI size: {size} is larger than max ROI size: {mx}.")
+            size = [int(self.R.randint(low=size[i], high=mx[i] + 1)) for i in range(len(img_size))]
+        self._size = size
+        if self.random_center:
+            self._start = [int(self.R.randint(low=0, high=d - s + 1)) if d > s else 0 for d, s in zip(img_size, size)]
+        else:
+            self._start = [max(d // 2 - s // 2, 0) for d, s in zip(img_size, size)]
+
+    def __call__(self, data):
+        d = dict(data)
+        first = self.first_key(d)
+        if first == ():
+            return d
+        d[first] = as_pending(d[first])
+        self.randomize(d[first].spatial_shape)
+        for k in self.key_iterator(d):
+            d[k] = as_pending(d[k])
+            shape = d[k].spatial_shape
+            d[k].plan.crop(self._start, self._size)
+            cropped = []
+            for dim, s, z in zip(shape, self._start, self._size):
+                cropped += [int(s), int(dim - min(s + z, dim))]
+            d[k].meta.setdefault("applied_operations", []).append(
+                {"class": "RandSpatialCrop", "extra_info": {"cropped": cropped}})
+        return d
+
+
+class FgBgToIndicesd(MapTransform):
+    """``monai.transforms.FgBgToIndicesd`` †: flat indices of foreground (>0) and background
+    voxels of a (materialised, cached) label volume, kept on the host for the crop draws."""
+
+    def __init__(self, keys, fg_postfix: str = "_fg_indices", bg_postfix: str = "_bg_indices", allow_missing_keys: bool = False):
+        super().__init__(keys, allow_missing_keys)
+        self.fg_postfix, self.bg_postfix = fg_postfix, bg_postfix
+
+    def __call__(self, data):
+        d = dict(data)
+        for k in self.key_iterator(d):
+            lab = d[k].tensor() if isinstance(d[k], Pending) else torch.as_tensor(d[k])
+            flat = (lab > 0).any(dim=0).reshape(-1)
+            d[k + self.fg_postfix] = torch.nonzero(flat).reshape(-1).cpu().numpy()
+            d[k + self.bg_postfix] = torch.nonzero(~flat).reshape(-1).cpu().numpy()
+        return d
+
+
+class RandCropByPosNegLabeld(Randomizable, MapTransform):
+    """``monai.transforms.RandCropByPosNegLabeld`` († generate_pos_neg_label_crop_centers +
+    correct_crop_centers(allow_smaller=True)): returns a LIST of ``num_samples`` dicts."""
+
+    def __init__(self, keys, label_key, spatial_size, pos: float = 1.0, neg: float = 1.0, num_samples: int = 1,
+                 fg_indices_key=None, bg_indices_key=None, allow_smaller: bool = False, allow_missing_keys: bool = False):
+        MapTransform.__init__(self, keys, allow_missing_keys)
+        if pos < 0 or neg < 0 or pos + neg == 0:
+            raise ValueError("pos and neg must be non-negative and not both zero")
+        self.label_key, self.spatial_size = label_key, [int(x) for x in spatial_size]
+        self.pos_ratio = pos / (pos + neg)
+        self.num_samples = num_samples
+        self.fg_indices_key, self.bg_indices_key = fg_indices_key, bg_indices_key
+        self.allow_smaller = allow_smaller
+        self.centers = None
+
+    def randomize(self, label_shape, fg_indices, bg_indices) -> None:
+        size = [min(int(s), int(d)) if s > 0 else int(d) for s, d in zip(self.spatial_size, label_shape)]
+        fg_indices, bg_indices = np.asarray(fg_indices), np.asarray(bg_indices)
+        pos_ratio = self.pos_ratio
+        if len(fg_indices) == 0 or len(bg_indices) == 0:
+            if len(fg_indices) == 0 and len(bg_indices) == 0:
+                raise ValueError("No sampling location available.")
+            pos_ratio = 0 if len(fg_indices) == 0 else 1
+        centers = []
+        for _ in range(self.num_samples):
+            indices_to_use = fg_indices if self.R.rand() < pos_ratio else bg_indices
+            idx = indices_to_use[self.R.randint(len(indices_to_use))]
+            center = np.unravel_index(idx, label_shape)
+            valid_start = np.floor_divide(size, 2)
+            valid_end = np.subtract(np.array(label_shape) + 1, np.array(size) / 2).astype(np.uint16)
+            for i, vs in enumerate(valid_start):
+                if vs == valid_end[i]:
+                    valid_end[i] += 1
+            centers.append([int(min(max(c, vs), ve - 1)) for c, vs, ve in zip(center, valid_start, valid_end)])
+        self.centers, self._size = centers, size
+
+    def __call__(self, data):
+        d = dict(data)
+        lab = as_pending(d[self.label_key])
+        fg = d.get(self.fg_indices_key) if self.fg_indices_key else None
+        bg = d.get(self.bg_indices_key) if self.bg_indices_key else None
+        if fg is None or bg is None:
+            t = lab.tensor()
+            flat = (t > 0).any(dim=0).reshape(-1)
+            fg, bg = torch.nonzero(flat).reshape(-1).cpu().numpy(), torch.nonzero(~flat).reshape(-1).cpu().numpy()
+        self.randomize(lab.spatial_shape, fg, bg)
+        out = []
+        for center in self.centers:
+            r = dict(d)
+            for k in self.key_iterator(d):
+                e = as_pending(d[k]).clone()
+                starts = [max(int(c) - int(s) // 2, 0) for c, s in zip(center, self._size)]
+                e.plan.crop(starts, self._size)
+                r[k] = e
+            out.append(r)
+        return out
+
+
+class RandFlipd(RandomizableTransform, MapTransform):
+    """``monai.transforms.RandFlipd`` †: one ``R.rand() < prob`` per call; ``torch.flip``."""
+
+    def __init__(self, keys, prob: float = 0.1, spatial_axis=None, allow_missing_keys: bool = False):
+        MapTransform.__init__(self, keys, allow_missing_keys)
+        RandomizableTransform.__init__(self, prob)
+        if spatial_axis is None:
+            spatial_axis = (0, 1, 2)
+        self.spatial_axis = [spatial_axis] if isinstance(spatial_axis, (int, np.integer)) else list(spatial_axis)
+
+    def __call__(self, data):
+        d = dict(data)
+        self.randomize(None)
+        if not self._do_transform:
+            return d
+        mask = np.array([a in self.spatial_axis for a in range(3)])
+        for k in self.key_iterator(d):
+            d[k] = as_pending(d[k])
+            d[k].plan.flip(mask)
+        return d
+
+
+# --------------------------------------------------------------------------- resampling
+class RandAffined(RandomizableTransform, MapTransform):
+    """``monai.transforms.RandAffined`` †: same constructor vocabulary as the reference uses
+    (rotate / shear / translate / scale ranges, per-key ``mode``, ``padding_mode`` — MONAI's
+    default "reflection" when the reference leaves it unset), three identically seeded streams,
+    one shared grid for every key (see :class:`~adell_mri_b200.sampling.RandAffineSampler`)."""
+
+    def __init__(self, keys, spatial_size=None, prob: float = 0.1, rotate_range=None, shear_range=None,
+                 translate_range=None, scale_range=None, mode="bilinear", padding_mode="reflection",
+                 cache_grid: bool = False, device=None, allow_missing_keys: bool = False):
+        MapTransform.__init__(self, keys, allow_missing_keys)
+        RandomizableTransform.__init__(self, prob)
+        if spatial_size is not None:
+            raise NotImplementedError("RandAffined(spatial_size=...) is not used by the reference and not on the fused path")
+        self.sampler = RandAffineSampler(prob, rotate_range, shear_range, translate_range, scale_range)
+        self.mode = _per_key(mode, self.keys, "mode")
+        self.padding_mode = _per_key(padding_mode, self.keys, "padding_mode")
+        self.last_affine = None
+
+    def set_random_state(self, seed=None, state=None):
+        super().set_random_state(seed, state)
+        self.sampler.set_random_state(seed, state)
+        self.R = self.sampler.R
+        return self
+
+    def __call__(self, data):
+        d = dict(data)
+        keys = list(self.key_iterator(d))
+        fired, p = self.sampler.draw(n_keys=len(keys))
+        self._do_transform = bool(fired)
+        if not fired:
+            self.last_affine = None
+            return d
+        A = geometry.compose_affine(p["rotate"], p["shear"], p["translate"], p["scale"])[0]
+        self.last_affine = A
+        for k, mode, pad in zip(self.keys, self.mode, self.padding_mode):
+            if k not in d:
+                continue
+            d[k] = as_pending(d[k])
+            d[k].plan.affine(A, mode, pad)
+        return d
+
+
+# --------------------------------------------------------------------------- intensity
+class _RandIntensityd(RandomizableTransform, MapTransform):
+    """Shared draw order of the Rand*Intensityd family †: the dict transform's own ``R.rand()``
+    gate, then the wrapped array transform's ``R.rand()`` (prob 1.0) and its parameter draw from
+    an identically seeded second stream."""
+
+    def __init__(self, keys, prob, allow_missing_keys=False):
+        MapTransform.__init__(self, keys, allow_missing_keys)
+        RandomizableTransform.__init__(self, prob)
+        self.R_inner = np.random.RandomState()
+
+    def set_random_state(self, seed=None, state=None):
+        super().set_random_state(seed, state)
+        if state is not None:
+            self.R_inner = state
+        else:
+            self.R_inner = np.random.RandomState(seed)
+        return self
+
+
+class RandScaleIntensityd(_RandIntensityd):
+    """``v * (1 + factor)``, ``factor ~ U(-factors, factors)`` †."""
+
+    def __init__(self, keys, factors, prob: float = 0.1, allow_missing_keys: bool = False, **_):
+        super().__init__(keys, prob, allow_missing_keys)
+        self.factors = (min(-factors, factors), max(-factors, factors)) if not isinstance(factors, (tuple, list)) else (min(factors), max(factors))
+        self.factor = None
+
+    def __call__(self, data):
+        d = dict(data)
+        self.randomize(None)
+        if not self._do_transform:
+            return d
+        self.R_inner.rand()
+        self.factor = self.R_inner.uniform(low=self.factors[0], high=self.factors[1])
+        for k in self.key_iterator(d):
+            d[k] = as_pending(d[k])
+            d[k].plan.intensity(scale=float(np.float32(1 + self.factor)))
+        return d
+
+
+class RandShiftIntensityd(_RandIntensityd):
+    """``v + offset``, ``offset ~ U(-offsets, offsets)`` †."""
+
+    def __init__(self, keys, offsets, prob: float = 0.1, allow_missing_keys: bool = False, **_):
+        super().__init__(keys, prob, allow_missing_keys)
+        self.offsets = (min(-offsets, offsets), max(-offsets, offsets)) if not isinstance(offsets, (tuple, list)) else (min(offsets), max(offsets))
+        self.offset = None
+
+    def __call__(self, data):
+        d = dict(data)
+        self.randomize(None)
+        if not self._do_transform:
+            return d
+        self.R_inner.rand()
+        self.offset = self.R_inner.uniform(low=self.offsets[0], high=self.offsets[1])
+        for k in self.key_iterator(d):
+            d[k] = as_pending(d[k])
+            d[k].plan.intensity(offset=float(np.float32(self.offset)))
+        return d
+
+
+class RandGaussianNoised(_RandIntensityd):
+    """``monai.transforms.RandGaussianNoised`` †: sigma ~ U(0, std) (``sample_std``), ONE noise
+    volume of the first key's shape drawn from ``R.normal`` on the host (float64 -> float32) and
+    added to every key.  In ``noise="philox"`` mode only sigma is drawn on the host and the
+    normal deviates come from the device-side Philox generator (not stream-comparable)."""
+
+    def __init__(self, keys, prob: float = 0.1, mean: float = 0.0, std: float = 0.1, sample_std: bool = True,
+                 allow_missing_keys: bool = False, **_):
+        super().__init__(keys, prob, allow_missing_keys)
+        self.mean, self.std, self.sample_std = mean, std, sample_std
+        self.noise = None
+        self._philox_calls = 0
+
+    def __call__(self, data):
+        d = dict(data)
+        self.randomize(None)
+        if not self._do_transform:
+            return d
+        first = self.first_key(d)
+        if first == ():
+            return d
+        d[first] = as_pending(d[first])
+        shape = d[first].shape
+        self.R_inner.rand()
+        std = self.R_inner.uniform(0, self.std) if self.sample_std else self.std
+        if _MODE["noise"] == "philox":
+            if self.mean != 0.0:
+                raise NotImplementedError("philox noise supports mean=0 only")
+            self._philox_calls += 1
+            seed = int(self.R_inner.randint(MAX_SEED, dtype="uint32"))
+            offs = np.arange(shape[0], dtype=np.uint64) * np.uint64(int(np.prod(shape[1:])))
+            for k in self.key_iterator(d):
+                d[k] = as_pending(d[k])
+                d[k].plan.add_philox_noise(np.float32(std), seed=seed, offset=offs)
+            return d
+        noise = self.R_inner.normal(self.mean, std, size=shape).astype(np.float32)
+        self.noise = noise
+        for k in self.key_iterator(d):
+            d[k] = as_pending(d[k])
+            if d[k].shape != shape:
+                raise ValueError("RandGaussianNoised: all keys must share the first key's shape")
+            dev = d[k].device
+            nz = torch.from_numpy(noise)
+            nz = nz.pin_memory().to(dev, non_blocking=True) if dev.type == "cuda" else nz
+            d[k].plan.add_noise([nz[c] for c in range(shape[0])])
+        return d
+
+
+class ScaleIntensityd(MapTransform):
+    """``monai.transforms.ScaleIntensityd`` († min-max to [minv, maxv], or ``v*(1+factor)``) on the
+    device statistics kernels, bit-exact fp32 operation order.  A cached-stage transform: it
+    materialises its input (the reference runs it before the CacheDataset cut as well)."""
+
+    def __init__(self, keys, minv=0.0, maxv=1.0, factor=None, allow_missing_keys: bool = False, **_):
+        super().__init__(keys, allow_missing_keys)
+        self.minv, self.maxv, self.factor = minv, maxv, factor
+
+    def __call__(self, data):
+        from . import _lib, stats
+
+        d = dict(data)
+        for k in self.key_iterator(d):
+            x = d[k].tensor() if isinstance(d[k], Pending) else d[k]
+            vols = [x[c].contiguous() for c in range(x.shape[0])]
+            flat = [x.contiguous().reshape(-1)]  # MONAI scales over the whole array (channel_wise=False)
+            if self.minv is not None or self.maxv is not None:
+                mm = stats.minmax(flat)
+                coefs = stats.scaler_coefs(mm, _lib.SCALER_MINMAX, self.minv, self.maxv)
+                out = stats.intensity_map(flat, coefs)[0].reshape(x.shape)
+            elif self.factor is not None:
+                out = (x.to(torch.float32) * np.float32(1 + self.factor)).to(torch.float32)
+            else:
+                raise ValueError("Incompatible values: minv=None or maxv=None and factor=None.")
+            d[k] = out
+            del vols
+        return d
+
+
+def not_on_fused_path(name: str):
+    def ctor(*args, **kwargs):
+        raise NotImplementedError(
+            f"{name} is outside the fused GPU hot path (stencil / FFT / polynomial field / non-affine warp; "
+            "see DESIGN.md, out of scope)")
+    return ctor
+
+
+RandAdjustContrastd = not_on_fused_path("RandAdjustContrastd")
+RandStdShiftIntensityd = not_on_fused_path("RandStdShiftIntensityd")
+RandRicianNoised = not_on_fused_path("RandRicianNoised")
+RandGibbsNoised = not_on_fused_path("RandGibbsNoised")
+RandBiasFieldd = not_on_fused_path("RandBiasFieldd")
+RandGaussianSmoothd = not_on_fused_path("RandGaussianSmoothd")
+RandGridDistortiond = not_on_fused_path("RandGridDistortiond")
+RandSimulateLowResolutiond = not_on_fused_path("RandSimulateLowResolutiond")
+Resized = not_on_fused_path("Resized")
+
+
+def all_flip_combinations(flip_axis):
+    out = []
+    for i in range(len(flip_axis)):
+        out.extend(itertools.combinations(flip_axis, i + 1))
+    return out

@@ -40,3 +40,14 @@ def rand_affine_matrix(R: np.random.RandomState, rotate=(0.4, 0.4, 0.2), shear=N
 
 def mismatch(a: torch.Tensor, b: torch.Tensor) -> int:
     return int((a != b).sum())
+
+
+def cref_execute(plan: BatchPlan, dsts) -> None:
+    """Stand-in for ``engine.execute`` on CPU-resident plans: every pass runs through the C
+    restatement (oracle/gather_ref.c).  Lets the lazy dictionary transforms / collation be
+    tested without a GPU; the GPU tests run the same pipelines through the CUDA path."""
+    dst_ptr = np.array([d.data_ptr() for d in dsts], np.uint64)
+    dst_stride = np.array([d.stride() for d in dsts], np.int64)
+    launches = plan.build_launches(dst_ptr, dst_stride, lambda n: torch.empty(max(n, 1), dtype=torch.float32))
+    for items in launches:
+        cref.gather(items)

@@ -1,0 +1,156 @@
+"""The lazy dictionary transforms + fused collation (adell_mri_b200.transforms / transform_factory
+/ collate) against the eager oracle restatement of the reference's pipelines
+(oracle/pipelines_ref.py) on identical seeds.  CPU: plans execute through the C restatement;
+GPU (marked): the same pipelines through the CUDA path."""
+
+import numpy as np
+import pytest
+import torch
+
+from adell_mri_b200 import collate, engine, transform_factory as F, transforms as T
+from oracle import pipelines_ref as P
+from tests.helpers import cref_execute
+
+
+@pytest.fixture(params=["cpu", pytest.param("cuda:0", marks=pytest.mark.gpu)])
+def dev(request, monkeypatch):
+    if request.param == "cpu":
+        monkeypatch.setattr(engine, "execute", cref_execute)
+    T.set_mode(strict=True, fast=False, noise="injected")
+    yield request.param
+    T.set_mode(strict=False)
+
+
+def _samples(R, n, keys, shape, mask=True):
+    out = []
+    for _ in range(n):
+        s = {k: torch.from_numpy(R.rand(1, *shape).astype(np.float32)) for k in keys}
+        if mask:
+            s["mask"] = torch.from_numpy((R.rand(1, *shape) > 0.7).astype(np.float32))
+        out.append(s)
+    return out
+
+
+def _to(s, dev):
+    return {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in s.items()}
+
+
+@pytest.mark.parametrize("augment", [["affine", "flip"], ["affine", "shear", "flip"], ["trivial", "affine", "shear", "flip"]])
+def test_unet_pipeline_matches_eager_reference(dev, augment):
+    R = np.random.RandomState(0)
+    keys, shape = ["t2", "adc", "dwi"], (28, 24, 12)
+    samples = _samples(R, 6, keys, shape)
+    lazy = T.Compose([F.get_augmentations_unet(augment, keys + ["mask"], keys, [], flip_axis=[0, 1, 2]),
+                      T.ConcatItemsd(keys, "image"), T.SelectItemsd(["image", "mask"])]).set_random_state(11)
+    ref = P.Chain([P.unet(augment, keys + ["mask"], keys, flip_axis=(0, 1, 2)), P.ConcatD(keys, "image")]).seed(11)
+    batch = collate.safe_collate([lazy(_to(s, dev)) for s in samples])
+    want = [ref(s) for s in samples]
+    assert batch["image"].shape == (6, 3, *shape) and batch["mask"].shape == (6, 1, *shape)
+    for b, w in enumerate(want):
+        assert torch.equal(batch["image"][b].cpu(), w["image"])
+        assert torch.equal(batch["mask"][b].cpu(), w["mask"].to(torch.float32))
+
+
+def test_unet_all_fire_and_crop_sandwich(dev):
+    """prob forced to 1 so every sample resamples twice (parity mode = two passes) inside the
+    RandSpatialCropd -> augment -> CenterSpatialCropd sandwich (has_label=False)."""
+    R = np.random.RandomState(1)
+    keys, shape, rc = ["t2", "dwi"], (30, 28, 14), [20, 18, 10]
+    samples = _samples(R, 4, keys, shape, mask=False)
+    lazy_aug = F.get_augmentations_unet(["affine", "shear", "flip"], keys, keys, [], random_crop_size=rc, has_label=False, flip_axis=[0, 1])
+    ref_aug = P.unet(["affine", "shear", "flip"], keys, keys, random_crop_size=rc, has_label=False, flip_axis=(0, 1))
+    for t in lazy_aug.flatten().transforms:
+        if isinstance(t, T.RandAffined):
+            t.sampler.prob = 1.0
+    for t in ref_aug.ts[1].ts:
+        if isinstance(t, P.AffineD):
+            t.draws.prob = 1.0
+    lazy = T.Compose([lazy_aug, T.ConcatItemsd(keys, "image")]).set_random_state(5)
+    ref = P.Chain([ref_aug, P.ConcatD(keys, "image")]).seed(5)
+    batch = collate.safe_collate([lazy(_to(s, dev)) for s in samples])
+    for b, s in enumerate(samples):
+        assert torch.equal(batch["image"][b].cpu(), ref(s)["image"])
+
+
+def test_unet_pos_neg_crops(dev):
+    R = np.random.RandomState(2)
+    keys, shape, rc = ["t2"], (32, 32, 12), [16, 16, 8]
+    samples = _samples(R, 3, keys, shape)
+    for s in samples:
+        flat = (s["mask"] > 0).reshape(-1).numpy()
+        s["mask_fg_indices"], s["mask_bg_indices"] = np.nonzero(flat)[0], np.nonzero(~flat)[0]
+    lazy = T.Compose([F.get_augmentations_unet(["affine", "flip"], keys + ["mask"], keys, [], random_crop_size=rc, n_crops=2),
+                      T.ConcatItemsd(keys, "image"), T.SelectItemsd(["image", "mask"])]).set_random_state(3)
+    ref = P.Chain([P.unet(["affine", "flip"], keys + ["mask"], keys, random_crop_size=rc, n_crops=2), P.ConcatD(keys, "image")]).seed(3)
+    got = collate.safe_collate_crops([lazy(_to(s, dev)) for s in samples])
+    want = [c for s in samples for c in ref(s)]
+    assert got["image"].shape == (6, 1, *rc)
+    for b, w in enumerate(want):
+        assert torch.equal(got["image"][b].cpu(), w["image"])
+        assert torch.equal(got["mask"][b].cpu(), w["mask"])
+
+
+@pytest.mark.parametrize("augment", [["flip", "affine"], ["flip", "affine", "shear"], ["trivial", "flip", "affine", "shear"]])
+def test_classification_pipeline_matches_eager_reference(dev, augment):
+    R = np.random.RandomState(4)
+    keys, shape, crop = ["t2", "adc"], (40, 40, 24), [24, 24, 8]
+    samples = _samples(R, 5, keys, shape)
+    tf = F.ClassificationTransforms(keys, adc_keys=[], crop_size=crop, mask_key="mask")
+    lazy_aug = F.get_augmentations_class(augment, keys, "mask", [], flip_axis=[0, 1, 2], prob=0.6)
+    lazy = T.Compose([*tf.pre_transforms()[-2:], lazy_aug, *tf.post_transforms()]).set_random_state(9)
+    m = [c + 16 for c in crop]
+    ref = P.Chain([P.CenterCropD(keys + ["mask"], m), P.classification(augment, keys, "mask", flip_axis=(0, 1, 2), prob=0.6),
+                   P.CenterCropD(keys + ["mask"], crop), P.ConcatD(keys + ["mask"], "image")]).seed(9)
+    batch = collate.safe_collate([lazy(_to(s, dev)) for s in samples])
+    assert batch["image"].shape == (5, 3, *crop)
+    for b, s in enumerate(samples):
+        assert torch.equal(batch["image"][b].cpu(), ref(s)["image"])
+
+
+@pytest.mark.parametrize("different_crop,vicregl", [(False, False), (True, False), (False, True)])
+def test_ssl_two_view_pipeline_matches_eager_reference(dev, different_crop, vicregl):
+    R = np.random.RandomState(6)
+    keys, copied, shape, roi = ["image"], ["image_copy"], (36, 32, 16), [24, 24, 12]
+    samples = _samples(R, 5, keys, shape, mask=False)
+    names = F.FUSED_AUGMENTS
+    tf = F.SSLTransforms(keys, copied, adc_keys=[], non_adc_keys=[])
+    lazy = tf.transforms(F.get_augmentations_ssl(keys, copied, None, roi, vicregl, different_crop, n_transforms=3)).set_random_state(21)
+    ref = P.Chain(P.ssl(keys, copied, roi, vicregl, different_crop, names, 3)).seed(21)
+    np.random.seed(123)
+    got = collate.safe_collate([lazy(_to(s, dev)) for s in samples])
+    np.random.seed(123)
+    for b, s in enumerate(samples):
+        d = dict(s)
+        d["image_copy"] = s["image"].clone()
+        w = ref(d)
+        for gk, wk in (("augmented_image_1", "image"), ("augmented_image_2", "image_copy")):
+            g, r = got[gk][b].cpu(), w[wk].to(torch.float32)
+            # consecutive intensity members collapse into one {scale, offset} pair: rounding-level differences
+            assert torch.allclose(g, r, rtol=2e-6, atol=2e-6), (gk, float((g - r).abs().max()))
+        if vicregl:
+            for bk, wk in (("box_1", "image"), ("box_2", "image_copy")):
+                assert np.array_equal(np.asarray(got[bk][b]), P.M.flatten_box(w["_cropped"][wk], roi))
+
+
+def test_ssl_pre_transforms_intensity_and_copy(dev):
+    """SSLTransforms.pre_transforms: min-max scaling (exact), centre crop then pad, CopyEntryd."""
+    if dev == "cpu":
+        pytest.skip("the statistics kernels need a CUDA device")
+    R = np.random.RandomState(7)
+    x = torch.from_numpy((R.rand(1, 20, 18, 10) * 900 + 30).astype(np.float32))
+    tf = F.SSLTransforms(["image"], ["image_copy"], adc_keys=[], non_adc_keys=["image"], crop_size=[16, 16, 16], pad_size=[24, 24, 12])
+    d = T.Compose(tf.pre_transforms())({"image": x.to(dev)})
+    want = P.M.spatial_pad(P.M.center_spatial_crop(P.M.scale_intensity(x, 0.0, 1.0), [16, 16, 16]), [24, 24, 12])
+    assert torch.equal(d["image"].tensor().cpu(), want)
+    assert torch.equal(d["image_copy"].tensor().cpu(), want)
+
+
+def test_unknown_and_out_of_scope_tokens_raise():
+    with pytest.raises(NotImplementedError):
+        F.get_augmentations_unet(["bogus"], ["a"], ["a"], [])
+    with pytest.raises(NotImplementedError):
+        F.get_augmentations_unet(["blur"], ["a"], ["a"], [])
+    with pytest.raises(NotImplementedError):
+        F.get_augmentations_class(["noise"], ["a"], None, [])
+    with pytest.raises(NotImplementedError):
+        F.get_augmentations_ssl(["a"], ["b"], [8, 8, 8], [8, 8, 8], False, False)
