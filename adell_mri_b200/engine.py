@@ -42,7 +42,14 @@ class _PinnedRing:
         if self.events[k] is not None:
             self.events[k].synchronize()  # normally long complete
         if self.slots[k] is None or self.slots[k].numel() < n:
-            self.slots[k] = torch.empty(max(n, 1 << 16), dtype=torch.uint8).pin_memory()
+            # cudaHostAlloc costs milliseconds: (re)size every slot in one go, with headroom, so a
+            # steady-state loop never pins memory again
+            cap = max(2 * n, 1 << 16)
+            for j in range(len(self.slots)):
+                if self.slots[j] is None or self.slots[j].numel() < cap:
+                    if self.events[j] is not None:
+                        self.events[j].synchronize()
+                    self.slots[j] = torch.empty(cap, dtype=torch.uint8).pin_memory()
         host = self.slots[k][:n]
         host.numpy()[:] = buf
         dev = host.to(device, non_blocking=True)
