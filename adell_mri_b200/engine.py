@@ -44,7 +44,7 @@ class _PinnedRing:
         if self.slots[k] is None or self.slots[k].numel() < n:
             # cudaHostAlloc costs milliseconds: (re)size every slot in one go, with headroom, so a
             # steady-state loop never pins memory again
-            cap = max(2 * n, 1 << 16)
+            cap = max(2 * n, 1 << 20)
             for j in range(len(self.slots)):
                 if self.slots[j] is None or self.slots[j].numel() < cap:
                     if self.events[j] is not None:
