@@ -386,7 +386,7 @@ def main():
                 host_out2[j][k].copy_(out2[j][k], non_blocking=True)
             ev_out[j].record(s_out)
 
-    e2e_steps = max(4, min(args.steps, 10))
+    e2e_steps = max(4, min(args.steps, 40))
     for i in range(2):
         e2e_step(i)
     barrier()
