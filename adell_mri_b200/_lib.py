@@ -18,7 +18,7 @@ F32, I16, U8 = 0, 1, 2
 NEAREST, TRILINEAR = 0, 1
 PAD_ZEROS, PAD_BORDER, PAD_REFLECTION = 0, 1, 2
 F_IDENTITY, F_CLIP, F_STRICT, F_PHILOX, F_PRE_DEV, F_TMAP, F_FASTCOORD = 0x01, 0x02, 0x04, 0x08, 0x10, 0x20, 0x40
-SCALER_MINMAX, SCALER_ADC_SEG, SCALER_ADC_CLASS, SCALER_RANGE = 0, 1, 2, 3
+SCALER_MINMAX, SCALER_ADC_SEG, SCALER_ADC_CLASS, SCALER_RANGE, SCALER_ZSCORE = 0, 1, 2, 3, 4
 
 PADDING_MODES = {"zeros": PAD_ZEROS, "border": PAD_BORDER, "reflection": PAD_REFLECTION}
 INTERP_MODES = {"nearest": NEAREST, "bilinear": TRILINEAR, "trilinear": TRILINEAR, "linear": TRILINEAR}
@@ -104,6 +104,7 @@ _SIGNATURES = {
     "adell_aug_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "adell_aug_gather_launches": (C.c_int, []),
     "adell_minmax": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
+    "adell_meanstd": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "adell_intensity_map": (
         C.c_int,
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_void_p],

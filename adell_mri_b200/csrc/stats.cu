@@ -99,6 +99,51 @@ __global__ void st_minmax_fin(uint32_t* out, int n_vols) {
   if (i < 2 * n_vols) reinterpret_cast<float*>(out)[i] = adell_unkey_f32(out[i]);
 }
 
+// ---------------------------------------------------------------- mean / std --------------
+// NormalizeIntensityd: per-volume mean and population standard deviation.  Accumulated in fp64
+// (sum, sum of squares, count) so that the result is the correctly rounded fp32 statistic; with
+// nonzero != 0 only elements != 0 take part (MONAI `nonzero=True`).  acc_dev: 3 doubles / volume.
+__global__ void __launch_bounds__(ST_THREADS) st_meanstd(const adell_vol* __restrict__ vols, int nonzero, double* acc) {
+  const adell_vol v = vols[blockIdx.y];
+  double s = 0.0, q = 0.0, c = 0.0;
+  st_for_each(v, [&](float x, int64_t) {
+    if (!nonzero || x != 0.0f) {
+      const double d = static_cast<double>(x);
+      s += d; q = fma(d, d, q); c += 1.0;
+    }
+  });
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  __shared__ double ss[ST_THREADS / 32], sq[ST_THREADS / 32], sc[ST_THREADS / 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { ss[warp] = s; sq[warp] = q; sc[warp] = c; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < ST_THREADS / 32; ++w) { s += ss[w]; q += sq[w]; c += sc[w]; }
+    atomicAdd(acc + 3 * blockIdx.y + 0, s);
+    atomicAdd(acc + 3 * blockIdx.y + 1, q);
+    atomicAdd(acc + 3 * blockIdx.y + 2, c);
+  }
+}
+
+// out[2v] = mean, out[2v+1] = std (population; 1 when it is 0, as MONAI substitutes)
+__global__ void st_meanstd_fin(const double* __restrict__ acc, int n_vols, float* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_vols) return;
+  const double s = acc[3 * i], q = acc[3 * i + 1], c = acc[3 * i + 2];
+  double mean = 0.0, var = 0.0;
+  if (c > 0.0) { mean = s / c; var = q / c - mean * mean; }
+  if (var < 0.0) var = 0.0;
+  float sd = static_cast<float>(sqrt(var));
+  if (sd == 0.0f) sd = 1.0f;
+  out[2 * i] = static_cast<float>(mean);
+  out[2 * i + 1] = sd;
+}
+
 // ---------------------------------------------------------------- intensity program -------
 // y = ((x*m0 - a)/d)*m1*m2 + b, each op rounded to fp32 (IEEE division).
 __device__ __forceinline__ float st_program(float x, const float* __restrict__ c) {
@@ -170,6 +215,9 @@ __global__ void st_scaler_coefs(const float* __restrict__ stats, int n_vols, int
     if (hi > static_cast<float>(p0)) m0 = static_cast<float>(p1);
     a = __fmul_rn(lo, m0);  // Offsetd(None): minus the minimum of the (rescaled) array
     m1 = adc_mult;
+  } else if (scaler == ADELL_SCALER_ZSCORE) {
+    a = lo;   // mean
+    d = hi;   // std (already 1 when the volume is constant)
   } else {  // ADELL_SCALER_RANGE
     a = lo;
     if (__fsub_rn(hi, lo) != 0.0f) {
@@ -344,6 +392,20 @@ extern "C" int adell_minmax(const adell_vol* vols_dev, int n_vols, int64_t max_n
   return ADELL_OK;
 }
 
+extern "C" int adell_meanstd(const adell_vol* vols_dev, int n_vols, int64_t max_n, int nonzero, double* acc_dev,
+                             float* out_dev, void* stream) {
+  if (n_vols == 0) return ADELL_OK;
+  if (vols_dev == nullptr || out_dev == nullptr || acc_dev == nullptr || n_vols < 0 || max_n < 0) return ADELL_ERR_BAD_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(acc_dev, 0, sizeof(double) * 3 * static_cast<size_t>(n_vols), st);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return adell_map_cuda_error(e); }
+  dim3 grid(st_blocks_per_vol(max_n, n_vols, 32), n_vols);
+  st_meanstd<<<grid, ST_THREADS, 0, st>>>(vols_dev, nonzero, acc_dev);
+  st_meanstd_fin<<<(n_vols + 127) / 128, 128, 0, st>>>(acc_dev, n_vols, out_dev);
+  ADELL_CUDA_CHECK_LAUNCH();
+  return ADELL_OK;
+}
+
 extern "C" int adell_intensity_map(const adell_vol* vols_dev, float* const* dst_dev, const float* coef_dev,
                                    int n_vols, int64_t max_n, int clip, float clip_lo, float clip_hi,
                                    void* stream) {
@@ -360,7 +422,7 @@ extern "C" int adell_intensity_map(const adell_vol* vols_dev, float* const* dst_
 extern "C" int adell_scaler_coefs(const float* stats_dev, int n_vols, int scaler, double p0, double p1,
                                   float* coef_dev, void* stream) {
   if (n_vols == 0) return ADELL_OK;
-  if (stats_dev == nullptr || coef_dev == nullptr || n_vols < 0 || scaler < 0 || scaler > ADELL_SCALER_RANGE)
+  if (stats_dev == nullptr || coef_dev == nullptr || n_vols < 0 || scaler < 0 || scaler > ADELL_SCALER_ZSCORE)
     return ADELL_ERR_BAD_ARG;
   st_scaler_coefs<<<(n_vols + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(stats_dev, n_vols, scaler, p0,
                                                                                        p1, coef_dev);

@@ -60,6 +60,17 @@ def minmax(vols: Sequence[torch.Tensor], desc=None) -> torch.Tensor:
     return out
 
 
+def meanstd(vols: Sequence[torch.Tensor], nonzero: bool = False, desc=None) -> torch.Tensor:
+    """``[n, 2]`` fp32 (mean, population std; std 0 -> 1) per volume — monai NormalizeIntensity."""
+    dev = _check_vols(vols)
+    d, max_n = desc if desc is not None else vol_descriptors(vols)
+    out = torch.empty(len(vols), 2, dtype=torch.float32, device=dev)
+    acc = torch.empty(len(vols), 3, dtype=torch.float64, device=dev)
+    _lib.check(_lib.load().adell_meanstd(d.data_ptr(), len(vols), max_n, int(nonzero), acc.data_ptr(), out.data_ptr(),
+                                         _stream(dev)), "adell_meanstd")
+    return out
+
+
 def scaler_coefs(stats: torch.Tensor, scaler: int, p0: float, p1: float) -> torch.Tensor:
     """``[n, 6]`` coefficients of ``y = ((x*m0 - a)/d)*m1*m2 + b`` for one of the reference scalers."""
     n = stats.shape[0]

@@ -735,6 +735,63 @@ class ScaleIntensityd(MapTransform):
         return d
 
 
+class NormalizeIntensityd(MapTransform):
+    """``monai.transforms.NormalizeIntensityd`` († ``(x - mean) / std``, population std, a zero std
+    replaced by 1; ``nonzero`` restricts the statistics — and the update — to voxels != 0) on the
+    device statistics kernels (fp64 accumulation: within 1e-6 of torch's fp32 reduction).  Named by
+    the north star; the reference's own pipelines use min-max scaling."""
+
+    def __init__(self, keys, subtrahend=None, divisor=None, nonzero: bool = False, channel_wise: bool = False,
+                 allow_missing_keys: bool = False, **_):
+        super().__init__(keys, allow_missing_keys)
+        if subtrahend is not None or divisor is not None:
+            raise NotImplementedError("NormalizeIntensityd: explicit subtrahend / divisor are not on the device path")
+        self.nonzero, self.channel_wise = nonzero, channel_wise
+
+    def __call__(self, data):
+        from . import _lib, stats
+
+        d = dict(data)
+        for k in self.key_iterator(d):
+            x = d[k].tensor() if isinstance(d[k], Pending) else d[k]
+            x = x.contiguous()
+            vols = [x[c].reshape(-1) for c in range(x.shape[0])] if self.channel_wise else [x.reshape(-1)]
+            ms = stats.meanstd(vols, nonzero=self.nonzero)
+            out = torch.stack([o for o in stats.intensity_map(vols, stats.scaler_coefs(ms, _lib.SCALER_ZSCORE, 0.0, 0.0))]).reshape(x.shape)
+            if self.nonzero:
+                out = torch.where(x != 0, out, x.to(torch.float32))
+            d[k] = out
+        return d
+
+
+class ScaleIntensityRangePercentilesd(MapTransform):
+    """``monai.transforms.ScaleIntensityRangePercentilesd`` †: ``a_min/a_max = np.percentile(x, q)``
+    ('linear' method, exact via the radix-select kernels), then ScaleIntensityRange."""
+
+    def __init__(self, keys, lower: float, upper: float, b_min, b_max, clip: bool = False, relative: bool = False,
+                 channel_wise: bool = False, allow_missing_keys: bool = False, **_):
+        super().__init__(keys, allow_missing_keys)
+        if relative or b_min is None or b_max is None:
+            raise NotImplementedError("ScaleIntensityRangePercentilesd: relative / open output ranges are not on the device path")
+        if not (0 <= lower <= 100 and 0 <= upper <= 100):
+            raise ValueError("Percentiles must be in the range [0, 100]")
+        self.lower, self.upper, self.b_min, self.b_max, self.clip, self.channel_wise = lower, upper, b_min, b_max, clip, channel_wise
+
+    def __call__(self, data):
+        from . import _lib, stats
+
+        d = dict(data)
+        for k in self.key_iterator(d):
+            x = d[k].tensor() if isinstance(d[k], Pending) else d[k]
+            x = x.contiguous()
+            vols = [x[c].reshape(-1) for c in range(x.shape[0])] if self.channel_wise else [x.reshape(-1)]
+            pct = stats.percentiles(vols, [self.lower, self.upper])
+            coefs = stats.scaler_coefs(pct, _lib.SCALER_RANGE, self.b_min, self.b_max)
+            outs = stats.intensity_map(vols, coefs, clip=(self.b_min, self.b_max) if self.clip else None)
+            d[k] = torch.stack(outs).reshape(x.shape)
+        return d
+
+
 def not_on_fused_path(name: str):
     def ctor(*args, **kwargs):
         raise NotImplementedError(

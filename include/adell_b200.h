@@ -188,6 +188,13 @@ typedef struct adell_vol {
  * pre-initialised by the call itself (it is: +inf/-inf written by a first tiny kernel). */
 int adell_minmax(const adell_vol* vols_dev, int n_vols, int64_t max_n, float* out_dev, void* stream);
 
+/* out_dev[2*v+0] = mean, out_dev[2*v+1] = population standard deviation of volume v (1 when it
+ * is 0), as monai NormalizeIntensityd computes them (named by BASELINE.json north_star; the
+ * reference itself never calls it).  fp64 accumulation in acc_dev (3 doubles per volume, scratch,
+ * zeroed by the call); nonzero != 0 restricts the statistics to elements != 0. */
+int adell_meanstd(const adell_vol* vols_dev, int n_vols, int64_t max_n, int nonzero, double* acc_dev,
+                  float* out_dev, void* stream);
+
 /* Exact elementwise intensity program  y = ((x*m0 - a)/d)*m1*m2 + b  with every op rounded to
  * fp32 in that order and no-op steps skipped bit-exactly (m0=1, a=0, d=1, m1=1, m2=1, b=0); the
  * six coefficients are read from coef_dev[6*v ..] so they can come from device statistics.
@@ -201,6 +208,7 @@ int adell_intensity_map(const adell_vol* vols_dev, float* const* dst_dev, const 
 #define ADELL_SCALER_ADC_CLASS 2 /* ConditionalRescalingd -> Offsetd(None) -> ScaleIntensityd(factor) */
 #define ADELL_SCALER_RANGE 3     /* ScaleIntensityRange(a_min=lo,a_max=hi,b_min=p0,b_max=p1) as used by
                                     ScaleIntensityRangePercentilesd; stats = the two percentiles     */
+#define ADELL_SCALER_ZSCORE 4     /* NormalizeIntensityd: (x - mean) / std; stats = {mean, std}           */
 /* stats_dev holds {lo, hi} per volume (min/max from adell_minmax, or two percentiles).
  * MINMAX: p0=minv, p1=maxv.  ADC_*: p0=max_value (500), p1=scale (0.001); factor fixed at -2/3
  * (ADC_FACTOR, transforms.py:25). */

@@ -113,3 +113,52 @@ def test_percentile_scaler_fused_and_exact():
     plan = BatchPlan([dv]).intensity_from_device(stats.coefs_to_affine(coefs)).clip(0.0, 1.0)
     fused = run_plan_cuda(plan)[0]
     assert torch.allclose(fused.cpu(), ref, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("nonzero,channel_wise", [(False, False), (True, False), (False, True)])
+def test_normalize_intensity_transform(nonzero, channel_wise):
+    """NormalizeIntensityd (north-star name; z-score) vs the oracle: fp64-accumulated statistics,
+    tolerance 1e-5 relative to the dynamic range (torch reduces in fp32)."""
+    from adell_mri_b200 import transforms as T
+
+    R = np.random.RandomState(3)
+    x = torch.from_numpy(R.gamma(2.0, 300.0, size=(2, 40, 36, 20)).astype(np.float32))
+    x[R.rand(*x.shape) < 0.3] = 0.0
+    got = T.NormalizeIntensityd(["image"], nonzero=nonzero, channel_wise=channel_wise)({"image": x.to(DEV)})["image"].cpu()
+    want = M.normalize_intensity(x, nonzero=nonzero, channel_wise=channel_wise)
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-5 * float(want.abs().max()))
+    ms = stats.meanstd([x[0].contiguous().to(DEV)])
+    assert abs(float(ms[0, 0]) - float(x[0].double().mean())) <= 1e-6 * abs(float(x[0].double().mean()))
+    assert abs(float(ms[0, 1]) - float(x[0].double().std(unbiased=False))) <= 1e-6 * float(x[0].double().std(unbiased=False))
+    # constant volume: std 0 -> 1
+    c = torch.full((1, 8, 8, 8), 2.5)
+    assert torch.equal(T.NormalizeIntensityd(["i"])({"i": c.to(DEV)})["i"].cpu(), torch.zeros_like(c))
+
+
+@pytest.mark.parametrize("clip", [False, True])
+def test_percentile_scaler_transform_then_classification_chain(clip):
+    """Config D: ScaleIntensityRangePercentilesd(0.5, 99.5 -> [0,1]) on the cached volume (exact),
+    then the classification chain flip -> affine(zeros) -> centre crop through the lazy surface."""
+    from adell_mri_b200 import collate, transform_factory as F, transforms as T
+    from oracle import pipelines_ref as P
+
+    R = np.random.RandomState(8)
+    shape, crop = (56, 56, 40), [40, 40, 24]
+    raw = [torch.from_numpy(R.gamma(2.0, 300.0, size=(1, *shape)).astype(np.float32)) for _ in range(3)]
+    T.set_mode(strict=True)
+    try:
+        scaler = T.ScaleIntensityRangePercentilesd(["t2"], 0.5, 99.5, 0.0, 1.0, clip=clip)
+        tf = F.ClassificationTransforms(["t2"], adc_keys=[], crop_size=crop)
+        aug = F.get_augmentations_class(["flip", "affine"], ["t2"], None, [], flip_axis=[0, 1, 2], prob=0.7)
+        lazy = T.Compose([scaler, *tf.pre_transforms()[-2:], aug, *tf.post_transforms()]).set_random_state(4)
+        ref = P.Chain([P.CenterCropD(["t2"], [c + 16 for c in crop]), P.classification(["flip", "affine"], ["t2"], None, (0, 1, 2), 0.7),
+                       P.CenterCropD(["t2"], crop), P.ConcatD(["t2"], "image")]).seed(4)
+        got = collate.safe_collate([lazy({"t2": r.to(DEV)}) for r in raw])["image"].cpu()
+        for b, r in enumerate(raw):
+            scaled = M.scale_intensity_range_percentiles(r, 0.5, 99.5, 0.0, 1.0, clip=clip)
+            # volumes under 1e6 voxels: MONAI interpolates the percentile with torch.quantile in fp32, the
+            # device kernels with numpy's float64 'linear' rule (exact for the BASELINE sizes, which
+            # are above that threshold: test_percentile_scaler_fused_and_exact) -> 1-ulp level differences
+            assert torch.allclose(got[b], ref({"t2": scaled})["image"], rtol=1e-5, atol=1e-6)
+    finally:
+        T.set_mode(strict=False)
