@@ -92,6 +92,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "WAIT_DONE:\n"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// Same, for the producer / hand-over warps: a long suspend-time hint, so that a warp that is merely
+// waiting for its turn does not take issue slots from the consumer warps on its scheduler.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "RWAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra RWAIT_DONE;\n"
+      "bra RWAIT_LOOP;\n"
+      "RWAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+}
 // The descriptor lives in global memory and was written by a host copy: the tensormap proxy
 // must acquire it before the TMA unit reads it (CUDA programming guide, "tensor map in global
 // memory").
@@ -826,7 +839,7 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
       k1_prepare(items, ts, n_items, tile, item, cur_start, next_start, cached_item, *priv, slots[slot],
                  smem_u32(smem + static_cast<size_t>(stage) * stage_bytes), lane);
       K1_PROF_ADD(2)
-      mbar_wait(empty + stage, phase ^ 1);
+      mbar_wait_relaxed(empty + stage, phase ^ 1);
       K1_PROF_ADD(0)
       if (lane == 0) {
         const K1Slot& sl = slots[slot];
@@ -855,7 +868,7 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
     // that the producer never waits for a load to land.
     for (int t0 = blockIdx.x * chunk; t0 < total_tiles; t0 += gridDim.x * chunk)
     for (int tile = t0; tile < min(t0 + chunk, total_tiles); ++tile) {
-      mbar_wait(landed + stage, phase);
+      mbar_wait_relaxed(landed + stage, phase);
       const K1Tile& tl = slots[slot].tl;
       if (tl.mode == MODE_STAGED && tl.fix_hi > tl.fix_lo)
         k1_fix_columns(reinterpret_cast<float*>(smem + static_cast<size_t>(stage) * stage_bytes), tl, lane);
