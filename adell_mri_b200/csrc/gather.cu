@@ -43,6 +43,14 @@ constexpr int K1_TS_CACHE = 2048;               // tile-prefix entries cached in
 constexpr double K1_EPS = 1e-3;                // coordinate slack of the fast path / tie window
 constexpr float K1_MAGIC = 12582912.0f;        // 1.5 * 2^23: x + MAGIC has ulp 1 for |x| < 2^22
 constexpr uint32_t K1_MAGIC_BITS = 0x4B400000u;
+#ifndef K1_L2_PROMO
+#define K1_L2_PROMO CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+#endif
+#ifndef K1_STORE
+#define K1_STORE __stcs
+#endif
+__device__ __forceinline__ void k1_plain_store(float4* p, float4 v) { *p = v; }
+__device__ __forceinline__ void k1_wt_store(float4* p, float4 v) { __stwt(p, v); }
 #ifndef K1_NV
 #define K1_NV 4                                 // trilinear voxels interleaved per consumer-thread iteration
 #endif
@@ -579,12 +587,12 @@ __device__ __forceinline__ void k1_tile_copy_box(const K1Ctx& c, const K1Tile& t
   if (vec) {
 #pragma unroll
     for (int r = 0; r < 8; ++r)
-      if (r < nrow) __stcs(reinterpret_cast<float4*>(dp + r * dstep), fix(*reinterpret_cast<const float4*>(sp + r * sstep)));
+      if (r < nrow) K1_STORE(reinterpret_cast<float4*>(dp + r * dstep), fix(*reinterpret_cast<const float4*>(sp + r * sstep)));
   } else {
 #pragma unroll 2
     for (int r = 0; r < nrow; ++r) {
       const float* p = sp + r * sstep;
-      __stcs(reinterpret_cast<float4*>(dp + r * dstep), fix(make_float4(p[0], p[1], p[2], p[3])));
+      K1_STORE(reinterpret_cast<float4*>(dp + r * dstep), fix(make_float4(p[0], p[1], p[2], p[3])));
     }
   }
 }
@@ -1043,7 +1051,7 @@ int k1_encode_tmap(adell_item& it, const int* box, EncodeTiledFn enc) {
   if (enc == nullptr) return -1;
   CUresult r = enc(reinterpret_cast<CUtensorMap*>(it.tmap), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
                    reinterpret_cast<void*>(base), gdim, gstride, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_SWIZZLE_NONE, K1_L2_PROMO, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return 0;
   it.tmap_base = reinterpret_cast<const void*>(base);
   it.flags |= ADELL_F_TMAP;
@@ -1053,7 +1061,8 @@ int k1_encode_tmap(adell_item& it, const int* box, EncodeTiledFn enc) {
 // Identity item: tensor map for the 32x16x32 box copy.  Returns the box bytes (0 = not eligible).
 int k1_encode_copy(adell_item& it, EncodeTiledFn enc) {
   if (!k1_vcopy_ok(it)) return 0;
-  static const int T[3] = {32, 16, 32};
+  int T[3] = {32, 16, 32};
+  if (const char* e = getenv("ADELL_K1_COPY_T0")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32) T[0] = v; }  // tuning aid
   int box[3] = {T[0], T[1], T[2]};
   int r = k1_encode_tmap(it, box, enc);
   if (r <= 0) return r;

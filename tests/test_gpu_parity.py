@@ -197,3 +197,45 @@ def test_c_abi_rejects_bad_items():
     info.total_tiles = 1
     assert lib.adell_aug_gather(8, 8, 1, C.byref(info), None) == -3  # misaligned items pointer
     assert lib.adell_aug_gather(None, None, 0, C.byref(info), None) == 0  # empty batch is a no-op
+
+
+def test_many_small_items_and_mixed_kinds_in_one_launch():
+    """More items than the kernel's shared-memory tile-prefix cache holds (2048), of every kind in
+    one launch: TMA-staged resamples, box copies (aligned and unaligned crop windows), and the
+    generic path (int16 source, strict), written into one collated tensor."""
+    from adell_mri_b200 import engine
+
+    R = np.random.RandomState(11)
+    n, shape = 2300, (12, 10, 8)
+    base = torch.from_numpy(R.rand(n, *shape).astype(np.float32))
+    base_i16 = torch.from_numpy(R.randint(-100, 3000, size=(n, *shape)).astype(np.int16))
+    dev_f, dev_i = base.to(DEV), base_i16.to(DEV)
+    out = torch.zeros(n, 8, 8, 8, device=DEV)
+    plans, refs = [], []
+    A = rand_affine_matrix(R, rotate=(0.3, 0.2, 0.1), translate=(1, 1, 1), scale=(0.05, 0.05, 0.05))
+    for i in range(n):
+        kind = i % 4
+        start = (int(R.randint(5)), int(R.randint(3)), int(R.randint(1)) if kind != 2 else 1 - (i % 2) * 0)
+        if kind == 0:      # staged resample, then crop
+            p = BatchPlan([dev_f[i]]).affine(A.numpy(), "bilinear", "zeros").crop(start, (8, 8, 8))
+            r = M.crop(M.affine_resample(base[i][None], A, "bilinear", "zeros"), start, (8, 8, 8))[0]
+        elif kind == 1:    # aligned box copy with flips
+            p = BatchPlan([dev_f[i]]).flip(np.array([True, False, True])).crop((start[0], start[1], 0), (8, 8, 8))
+            r = M.crop(M.flip(base[i][None], [0, 2]), (start[0], start[1], 0), (8, 8, 8))[0]
+        elif kind == 2:    # box copy of a window that starts mid-row (unaligned)
+            p = BatchPlan([dev_f[i, :, :, 1:]]).crop((start[0], start[1], 0), (8, 8, 4)).spatial_pad((8, 8, 8))
+            r = M.spatial_pad(M.crop(base[i, :, :, 1:][None], (start[0], start[1], 0), (8, 8, 4)), (8, 8, 8))[0]
+        else:              # generic path: int16 source, nearest
+            p = BatchPlan([dev_i[i]], strict=True).affine(A.numpy(), "nearest", "border").center_crop((8, 8, 8))
+            r = M.center_spatial_crop(M.affine_resample(base_i16[i][None], A, "nearest", "border"), (8, 8, 8))[0]
+        plans.append(p); refs.append(r)
+    before = engine.launch_count
+    engine.execute(BatchPlan.concat(plans), [out[i] for i in range(n)])
+    torch.cuda.synchronize()
+    assert engine.launch_count - before == 1
+    got = out.cpu()
+    for i in range(n):
+        if i % 4 == 0:
+            assert torch.allclose(got[i], refs[i], rtol=1e-4, atol=1e-4), i
+        else:
+            assert torch.equal(got[i], refs[i]), (i, i % 4)
