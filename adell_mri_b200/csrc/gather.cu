@@ -1178,6 +1178,19 @@ extern "C" int adell_aug_prepare(adell_item* items_host, int n_items, int32_t* t
   return ADELL_OK;
 }
 
+extern "C" int adell_aug_prepare_steps(void* buf_host, int n_steps, const int32_t* n_items, const int64_t* item_off,
+                                       const int64_t* tile_off, adell_launch_info* infos) {
+  if (buf_host == nullptr || n_items == nullptr || item_off == nullptr || tile_off == nullptr || infos == nullptr || n_steps < 0)
+    return ADELL_ERR_BAD_ARG;
+  uint8_t* base = static_cast<uint8_t*>(buf_host);
+  for (int k = 0; k < n_steps; ++k) {
+    const int st = adell_aug_prepare(reinterpret_cast<adell_item*>(base + item_off[k]), n_items[k],
+                                     reinterpret_cast<int32_t*>(base + tile_off[k]), infos + k);
+    if (st != ADELL_OK) return st;
+  }
+  return ADELL_OK;
+}
+
 extern "C" int adell_aug_gather(const adell_item* items_dev, const int32_t* tile_start_dev, int n_items,
                                 const adell_launch_info* info, void* stream) {
   if (n_items == 0) return ADELL_OK;

@@ -169,6 +169,11 @@ typedef struct adell_launch_info {
  * then uploads items + prefix and calls adell_aug_gather. */
 int adell_aug_prepare(adell_item* items_host, int n_items, int32_t* tile_start_host,
                       adell_launch_info* info);
+/* Host-only convenience for several launches packed in one buffer (one upload for many steps):
+ * step k has n_items[k] items at buf_host + item_off[k] (64-byte aligned) and its tile prefix
+ * (n_items[k] + 1 int32) at buf_host + tile_off[k]; runs adell_aug_prepare on each, filling infos[k]. */
+int adell_aug_prepare_steps(void* buf_host, int n_steps, const int32_t* n_items, const int64_t* item_off,
+                            const int64_t* tile_off, adell_launch_info* infos);
 /* Enqueue the fused gather over all items: ONE kernel launch per call. */
 int adell_aug_gather(const adell_item* items_dev, const int32_t* tile_start_dev, int n_items,
                      const adell_launch_info* info, void* stream);
