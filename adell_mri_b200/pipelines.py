@@ -226,3 +226,376 @@ class SegmentationBatchAugmenter:
         nk = len(self.keys)
         return engine.prepare_steps(plan, np.concatenate(ptrs), np.concatenate(strides), [len(b) * nk for b in batches],
                                     keep=[t for o in outs for t in o.values()])
+
+
+class _BatchBase:
+    """Shared plumbing of the batch augmenters: per-sample metadata cache, destination pointers."""
+
+    def __init__(self):
+        self._meta = {}
+
+    def _sample_meta(self, s: dict, keys):
+        m = self._meta.get(id(s))
+        if m is None or m[0] is not s:
+            vols = [s[k][c] for k in keys for c in range(s[k].shape[0])]
+            plan = BatchPlan(vols)
+            m = (s, plan.parent_ptr, plan.parent_stride, plan.parent_dtype, plan.shape, vols)
+            self._meta[id(s)] = m
+        return m
+
+    def _base_plan(self, samples, keys, repeat: int = 1):
+        """One volume per (sample, [view,] key-channel); ``repeat`` > 1 lists each sample's volumes
+        that many times (the SSL views share their source)."""
+        metas = [self._sample_meta(s, keys) for s in samples]
+        cat = lambda i: np.concatenate([np.tile(m[i], (repeat,) + (1,) * (m[i].ndim - 1)) for m in metas])
+        return BatchPlan.from_arrays(cat(1), cat(2), cat(3), cat(4), metas[0][5][0].device, [m[5] for m in metas],
+                                     fast=self.fast, strict=self.strict), metas
+
+    @staticmethod
+    def _dst_of(out: torch.Tensor):
+        """Pointers / strides of every [b, c] volume of a collated ``[B, C, H, W, D]`` tensor."""
+        B, Cn = out.shape[:2]
+        bi = np.arange(B, dtype=np.int64)[:, None]
+        ci = np.arange(Cn, dtype=np.int64)[None, :]
+        ptr = (out.data_ptr() + 4 * (bi * out.stride(0) + ci * out.stride(1))).astype(np.uint64)
+        stride = np.broadcast_to(np.asarray(out.stride()[2:], np.int64), (B, Cn, 3))
+        return ptr, stride
+
+
+class ClassificationBatchAugmenter(_BatchBase):
+    """``get_augmentations_class`` chain (+ the final ``CenterSpatialCropd`` / ``ConcatItemsd`` of
+    ``ClassificationTransforms.post_transforms``) for a batch of cached samples
+    (/root/reference/adell_mri/transform_factory/augmentations.py:181-320,
+    /root/reference/adell_mri/transform_factory/transforms.py:492-509): ``OneOf`` over the flip
+    combinations FIRST (a flip before the resample is a negative source stride), then
+    ``RandAffined(translate, rotate x, scale; zeros)``, optionally the shear one, centre crop, and
+    every key (mask last) concatenated into ``"image"``.  ``set_random_state(seed)`` seeds exactly
+    like ``get_augmentations_class(...).set_random_state(seed)``."""
+
+    def __init__(self, augment: Sequence[str], image_keys: Sequence[str], mask_key: str | None = None,
+                 flip_axis: Sequence[int] = (0, 1), prob: float = 0.1, crop_size: Sequence[int] | None = None,
+                 strict: bool = False, fast: bool = False):
+        super().__init__()
+        valid = ["intensity", "noise", "rbf", "affine", "shear", "flip", "blur", "lowres", "distort", "trivial"]
+        _check_augment(augment, valid)
+        if "trivial" in augment:
+            raise NotImplementedError("'trivial' (SomeOf) is handled by the dict-transform surface, not the batch fast path")
+        self.keys = list(image_keys) + ([mask_key] if mask_key is not None else [])
+        self.modes = ["bilinear" if k != mask_key else "nearest" for k in self.keys]
+        self.prob, self.crop_size = prob, None if crop_size is None else [int(x) for x in crop_size]
+        self.strict, self.fast = strict, fast
+        flip_axis = [flip_axis] if isinstance(flip_axis, int) else list(flip_axis)
+        self.flip_combos = [c for i in range(len(flip_axis)) for c in itertools.combinations(flip_axis, i + 1)] if "flip" in augment else []
+        self.oneof_R = np.random.RandomState()
+        self.flip_R = [np.random.RandomState() for _ in self.flip_combos]
+        self.samplers = []
+        if "affine" in augment:
+            self.samplers.append(RandAffineSampler(prob=prob, translate_range=[4, 4, 1], rotate_range=[np.pi / 16],
+                                                   scale_range=[0.1, 0.1, 0.05]))
+        if "shear" in augment:
+            self.samplers.append(RandAffineSampler(prob=prob, shear_range=((0.9, 1.1), (0.9, 1.1), (0.9, 1.1))))
+        self.set_random_state(None)
+
+    def set_random_state(self, seed=None):
+        n = (1 if self.flip_combos else 0) + len(self.samplers)
+        seeds = child_seeds(seed, n) if seed is not None else [None] * n
+        i = 0
+        if self.flip_combos:
+            self.oneof_R = np.random.RandomState(seeds[i]); i += 1
+            fs = [int(self.oneof_R.randint(2 ** 32, dtype="uint32")) for _ in self.flip_combos] if seed is not None else [None] * len(self.flip_combos)
+            self.flip_R = [np.random.RandomState(f) for f in fs]
+        for smp in self.samplers:
+            smp.set_random_state(seeds[i]); i += 1
+        return self
+
+    def draw(self, batch: int):
+        nk = len(self.keys)
+        flips = np.zeros((batch, 3), bool)
+        if self.flip_combos:
+            w = [1.0 / len(self.flip_combos)] * len(self.flip_combos)
+            idx = self.oneof_R.multinomial(1, w, size=batch).argmax(1)      # == one OneOf.__call__ per sample
+            for j, combo in enumerate(self.flip_combos):
+                use = np.nonzero(idx == j)[0]
+                fire = self.flip_R[j].random_sample(use.size) < self.prob   # that member's own stream, in sample order
+                for a in combo:
+                    flips[use[fire], a] = True
+        fired = np.zeros((len(self.samplers), batch), bool)
+        mats = np.tile(np.eye(4, dtype=np.float32), (len(self.samplers), batch, 1, 1))
+        for si, smp in enumerate(self.samplers):
+            f, p = smp.draw_batch(batch, n_keys=nk)
+            fired[si] = f
+            if f.any():
+                mats[si, f] = geometry.compose_affine(p["rotate"], p["shear"], p["translate"], p["scale"], batch=int(f.sum()))
+        return dict(flips=flips, fired=fired, mats=mats)
+
+    def plan(self, samples: Sequence[dict], params=None) -> BatchPlan:
+        B = len(samples)
+        if params is None:
+            params = self.draw(B)
+        plan, metas = self._base_plan(samples, self.keys)
+        per = plan.n // B                      # volumes per sample (keys x channels)
+        modes = []
+        for k, m in zip(self.keys, self.modes):
+            modes += [m] * samples[0][k].shape[0]
+        rep = lambda x: np.repeat(x, per, axis=0)
+        plan.flip(rep(params["flips"]))
+        for si in range(len(self.samplers)):
+            plan.affine(rep(params["mats"][si]), modes * B, "zeros", where=rep(params["fired"][si]))
+        if self.crop_size is not None:
+            plan.center_crop(self.crop_size)
+        return plan
+
+    def __call__(self, samples: Sequence[dict], params=None, out: dict | None = None) -> dict:
+        plan = self.plan(samples, params)
+        B = len(samples)
+        per = plan.n // B
+        if out is None:
+            out = {"image": torch.empty((B, per, *(int(x) for x in plan.shape[0])), dtype=torch.float32, device=plan.device)}
+        ptr, stride = self._dst_of(out["image"])
+        engine.execute_ptrs(plan, ptr.reshape(-1), stride.reshape(-1, 3), keep=[out["image"]])
+        return out
+
+
+#: workhorse members the fused path implements, in the reference's list order
+#: (/root/reference/adell_mri/modules/augmentations.py:10-37)
+SSL_FUSED_MEMBERS = ["gaussian_noise", "shift_intensity", "scale_intensity",
+                     "rotate_x", "rotate_y", "rotate_z", "translate_x", "translate_y", "translate_z",
+                     "shear_x", "shear_y", "shear_z", "scale_x", "scale_y", "scale_z"]
+
+
+def _ssl_member_ranges(name: str, max_mult: float):
+    """Parameter range of one spatial member after ``max_mult`` and AUG_PARAM_CORRECTION
+    (modules/augmentations.py:103-162): a per-axis tuple with the active axis a (lo, hi) pair."""
+    kind, c = name.rsplit("_", 1)
+    i = "xyz".index(c)
+    rng = [0, 0, 0]
+    if kind == "rotate":
+        a = (np.pi / 6 if c != "z" else np.pi / 16) * max_mult
+        rng[i] = (-a, a)
+        return dict(rotate_range=tuple(rng))
+    if kind == "translate":
+        t = (30 if c != "z" else 5) * max_mult
+        rng[i] = (-t, t)
+        return dict(translate_range=tuple(rng))
+    x = (0.5 if kind == "shear" else 0.3) * max_mult
+    rng[i] = (1 - x, 1 + x)
+    return dict(shear_range=tuple(rng)) if kind == "shear" else dict(scale_range=tuple(rng))
+
+
+class _WorkhorseDraws:
+    """Vectorised draws of one ``AugmentationWorkhorsed`` over a batch: which members each sample
+    applies (in which order) and every member's parameters from ITS OWN streams, consumed in
+    sample order — the same values the per-sample transform objects would draw."""
+
+    def __init__(self, members, n_keys: int, N: int, max_mult: float = 0.5):
+        self.members, self.n_keys, self.N = list(members), n_keys, N
+        self.R = np.random.RandomState()
+        self.samplers, self.R_outer, self.R_inner = {}, {}, {}
+        for m in self.members:
+            if m in ("gaussian_noise", "shift_intensity", "scale_intensity"):
+                self.R_outer[m], self.R_inner[m] = np.random.RandomState(), np.random.RandomState()
+            else:
+                self.samplers[m] = RandAffineSampler(prob=1.0, **_ssl_member_ranges(m, max_mult))
+        self.noise_std = 1 * max_mult
+        self.shift, self.scale = 0.5 * max_mult, 0.5 * max_mult
+
+    def set_random_state(self, seed):
+        self.R = np.random.RandomState(seed)
+        for m in self.members:  # AugmentationWorkhorsed.set_random_state fan-out (transform_factory.py)
+            s = int(self.R.randint(2 ** 32, dtype="uint32")) if seed is not None else None
+            if m in self.samplers:
+                self.samplers[m].set_random_state(s)
+            else:
+                self.R_outer[m], self.R_inner[m] = np.random.RandomState(s), np.random.RandomState(s)
+        return self
+
+    def draw_members(self, choice: np.ndarray, shape, philox: bool):
+        """``choice``: [B, N] member indices.  Returns per member the samples using it and its
+        parameters (matrices / factors / offsets / noise)."""
+        out = {}
+        for mi, m in enumerate(self.members):
+            use = np.nonzero((choice == mi).any(axis=1))[0]
+            if use.size == 0:
+                continue
+            if m in self.samplers:
+                _, p = self.samplers[m].draw_batch(use.size, n_keys=self.n_keys)
+                out[m] = (use, geometry.compose_affine(p["rotate"], p["shear"], p["translate"], p["scale"], batch=use.size))
+            elif m == "gaussian_noise":
+                self.R_outer[m].random_sample(use.size)
+                vals = []
+                for _ in range(use.size):   # the noise volume itself is drawn per use (host float64 normal)
+                    self.R_inner[m].random_sample()
+                    std = self.R_inner[m].uniform(0, self.noise_std)
+                    if philox:
+                        vals.append((np.float32(std), int(self.R_inner[m].randint(2 ** 32, dtype="uint32"))))
+                    else:
+                        vals.append(self.R_inner[m].normal(0.0, std, size=shape).astype(np.float32))
+                out[m] = (use, vals)
+            else:
+                self.R_outer[m].random_sample(use.size)
+                u = self.R_inner[m].random_sample(2 * use.size).reshape(-1, 2)[:, 1]   # gate, then uniform(lo, hi)
+                f = self.shift if m == "shift_intensity" else self.scale
+                out[m] = (use, -f + (f - (-f)) * u)
+        return out
+
+
+class SSLBatchAugmenter(_BatchBase):
+    """``get_augmentations_ssl`` two-view chain for a batch (augmentations.py:391-516;
+    modules/augmentations.py:189-256): the crop window(s), then per view ``n_transforms`` of the
+    fused workhorse members in the drawn order.  ``choice="global"`` draws the member subsets with
+    ``np.random.choice`` on the global stream, sample by sample, exactly like the reference (whose
+    global stream is unseeded, so nothing reproducible is lost by ``choice="vectorised"``, which
+    draws all subsets at once from this object's own stream).  ``noise="philox"`` replaces the
+    host-drawn noise volumes by the device generator (sigma still drawn on the host)."""
+
+    def __init__(self, all_keys: Sequence[str], roi_size: Sequence[int], n_transforms: int = 3, different_crop: bool = False,
+                 vicregl: bool = False, members: Sequence[str] | None = None, choice: str = "global", noise: str = "injected",
+                 strict: bool = False, fast: bool = False):
+        super().__init__()
+        self.keys = list(all_keys)
+        self.roi = [int(x) for x in roi_size]
+        self.N, self.different_crop, self.vicregl = n_transforms, different_crop or vicregl, vicregl
+        members = list(SSL_FUSED_MEMBERS if members is None else members)
+        if vicregl:
+            members = [m for m in members if m in ("gaussian_noise", "shift_intensity", "scale_intensity")]
+        bad = [m for m in members if m not in SSL_FUSED_MEMBERS]
+        if bad:
+            raise NotImplementedError(f"workhorse members {bad} are outside the fused GPU hot path")
+        self.members = members
+        self.choice, self.noise, self.strict, self.fast = choice, noise, strict, fast
+        self.crop_R = [np.random.RandomState(), np.random.RandomState()]
+        self.views = None
+        self.choice_R = np.random.RandomState()
+        self.set_random_state(None)
+
+    def _n_channels(self, sample):
+        return sum(sample[k].shape[0] for k in self.keys)
+
+    def set_random_state(self, seed=None):
+        n = (2 if self.different_crop else 1) + 2
+        seeds = child_seeds(seed, n) if seed is not None else [None] * n
+        i = 0
+        self.crop_R[0] = np.random.RandomState(seeds[i]); i += 1
+        if self.different_crop:
+            self.crop_R[1] = np.random.RandomState(seeds[i]); i += 1
+        self._view_seeds = seeds[i:i + 2]
+        self.views = None
+        self.choice_R = np.random.RandomState(None if seed is None else seed + 1)
+        return self
+
+    def _ensure_views(self, n_keys):
+        if self.views is None:
+            self.views = [_WorkhorseDraws(self.members, n_keys, self.N).set_random_state(s) for s in self._view_seeds]
+
+    def draw(self, batch: int, shape, n_keys: int):
+        self._ensure_views(n_keys)
+        nm = len(self.members)
+        starts = np.zeros((2, batch, 3), np.int64)
+        for b in range(batch):   # RandSpatialCropd(random_size=False): a randint per axis that can move
+            starts[0, b] = [int(self.crop_R[0].randint(low=0, high=d - r + 1)) if d > r else 0 for d, r in zip(shape, self.roi)]
+            if self.different_crop:
+                starts[1, b] = [int(self.crop_R[1].randint(low=0, high=d - r + 1)) if d > r else 0 for d, r in zip(shape, self.roi)]
+        if not self.different_crop:
+            starts[1] = starts[0]
+        choice = np.zeros((2, batch, self.N), np.int64)
+        if self.choice == "global":
+            for b in range(batch):
+                for v in range(2):   # per sample: view 1's workhorse, then view 2's
+                    choice[v, b] = np.random.choice(nm, self.N, replace=False)
+        else:
+            for v in range(2):
+                choice[v] = np.argsort(self.choice_R.random_sample((batch, nm)), axis=1)[:, : self.N]
+        roi_shape = tuple(min(r, d) for r, d in zip(self.roi, shape))
+        draws = [self.views[v].draw_members(choice[v], (n_keys, *roi_shape), self.noise == "philox") for v in range(2)]
+        return dict(starts=starts, choice=choice, draws=draws)
+
+    def plan(self, samples: Sequence[dict], params=None):
+        B = len(samples)
+        nc = self._n_channels(samples[0])
+        plan, metas = self._base_plan(samples, self.keys, repeat=2)      # volume order: [b, view, channel]
+        shape = tuple(int(x) for x in metas[0][4][0])
+        if params is None:
+            params = self.draw(B, shape, nc)
+        n = plan.n
+        vol_b = np.repeat(np.arange(B), 2 * nc)
+        vol_v = np.tile(np.repeat(np.arange(2), nc), B)
+        plan.crop(params["starts"][vol_v, vol_b], self.roi)
+        dev = plan.device
+        for v in range(2):
+            choice, draws = params["choice"][v], params["draws"][v]
+            for s in range(self.N):                 # slot s of every sample, member by member
+                for mi, m in enumerate(self.members):
+                    sel = np.nonzero(choice[:, s] == mi)[0]
+                    if sel.size == 0:
+                        continue
+                    use, vals = draws[m]
+                    pos = np.searchsorted(use, sel)   # index of each selected sample in the member's use list
+                    where = np.zeros(n, bool)
+                    where[(vol_v == v) & np.isin(vol_b, sel)] = True
+                    if m in self.views[v].samplers:
+                        A = np.tile(np.eye(4, dtype=np.float32), (n, 1, 1))
+                        for b, q in zip(sel, pos):
+                            A[(vol_b == b) & (vol_v == v)] = vals[q]
+                        plan.affine(A, "bilinear", "zeros", where=where)
+                    elif m == "scale_intensity":
+                        sc = np.ones(n)
+                        for b, q in zip(sel, pos):
+                            sc[(vol_b == b) & (vol_v == v)] = float(np.float32(1 + vals[q]))
+                        plan.intensity(scale=sc, where=where)
+                    elif m == "shift_intensity":
+                        of = np.zeros(n)
+                        for b, q in zip(sel, pos):
+                            of[(vol_b == b) & (vol_v == v)] = float(np.float32(vals[q]))
+                        plan.intensity(offset=of, where=where)
+                    else:  # gaussian_noise
+                        if self.noise == "philox":
+                            std, seed, off = np.zeros(n, np.float32), np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+                            vox = int(np.prod(plan.shape[0]))
+                            for b, q in zip(sel, pos):
+                                idx = np.nonzero((vol_b == b) & (vol_v == v))[0]
+                                std[idx], seed[idx] = vals[q][0], vals[q][1]
+                                off[idx] = np.arange(idx.size, dtype=np.uint64) * np.uint64(vox)
+                            plan._close(where & plan._has_noise())
+                            st = plan.st
+                            st.philox_std = np.where(where, std, st.philox_std).astype(np.float32)
+                            st.philox_seed = np.where(where, seed, st.philox_seed).astype(np.uint64)
+                            st.philox_off = np.where(where, off, st.philox_off).astype(np.uint64)
+                        else:
+                            noise = [None] * n
+                            for b, q in zip(sel, pos):
+                                idx = np.nonzero((vol_b == b) & (vol_v == v))[0]
+                                t = torch.from_numpy(vals[q])
+                                t = t.pin_memory().to(dev, non_blocking=True) if dev.type == "cuda" else t
+                                for c, i in enumerate(idx):
+                                    noise[i] = t[c]
+                            plan.add_noise(noise)
+        return plan, params
+
+    def boxes(self, params, shape):
+        """``box_1`` / ``box_2`` of the VICRegL variant: ``flatten_box(extra_info.cropped)``
+        (augmentations.py:402-406)."""
+        out = []
+        for v in range(2):
+            st = params["starts"][v]
+            size = np.minimum(np.asarray(self.roi), np.asarray(shape))
+            end_gap = np.asarray(shape)[None, :] - (st + size[None, :])
+            out.append(np.concatenate([st, np.asarray(self.roi)[None, :] - end_gap], axis=1).astype(np.float32))
+        return out
+
+    def __call__(self, samples: Sequence[dict], params=None, out: dict | None = None) -> dict:
+        plan, params = self.plan(samples, params)
+        B, nc = len(samples), self._n_channels(samples[0])
+        oshape = tuple(int(x) for x in plan.shape[0])
+        if out is None:
+            out = {k: torch.empty((B, nc, *oshape), dtype=torch.float32, device=plan.device)
+                   for k in ("augmented_image_1", "augmented_image_2")}
+        p1, s1 = self._dst_of(out["augmented_image_1"])
+        p2, s2 = self._dst_of(out["augmented_image_2"])
+        ptr = np.stack([p1, p2], axis=1).reshape(-1)          # [b, view, channel]
+        stride = np.stack([s1, s2], axis=1).reshape(-1, 3)
+        engine.execute_ptrs(plan, ptr, stride, keep=[out["augmented_image_1"], out["augmented_image_2"]])
+        if self.vicregl:
+            shape = tuple(int(x) for x in self._meta[id(samples[0])][4][0])
+            b1, b2 = self.boxes(params, shape)
+            out["box_1"], out["box_2"] = torch.from_numpy(b1), torch.from_numpy(b2)
+        return out

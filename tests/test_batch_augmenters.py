@@ -1,0 +1,83 @@
+"""Batch fast paths (adell_mri_b200.pipelines.ClassificationBatchAugmenter / SSLBatchAugmenter)
+against the dictionary-transform surface on identical seeds: the vectorised draws must consume the
+very same RandomState streams as one transform call per sample does.  (The dictionary surface is
+itself pinned against the eager oracle pipelines in tests/test_lazy_pipelines.py.)  CPU: plans run
+through the C restatement; GPU (marked): through CUDA."""
+
+import numpy as np
+import pytest
+import torch
+
+from adell_mri_b200 import collate, engine, transform_factory as F, transforms as T
+from adell_mri_b200.pipelines import ClassificationBatchAugmenter, SSLBatchAugmenter
+from oracle import cref
+
+
+def _cref_execute_ptrs(plan, dst_ptr, dst_stride, keep=None):
+    launches = plan.build_launches(dst_ptr, dst_stride, lambda n: torch.empty(max(n, 1), dtype=torch.float32))
+    for items in launches:
+        cref.gather(items)
+
+
+@pytest.fixture(params=["cpu", pytest.param("cuda:0", marks=pytest.mark.gpu)])
+def dev(request, monkeypatch):
+    if request.param == "cpu":
+        from tests.helpers import cref_execute
+        monkeypatch.setattr(engine, "execute", cref_execute)
+        monkeypatch.setattr(engine, "execute_ptrs", _cref_execute_ptrs)
+    T.set_mode(strict=True, fast=False, noise="injected")
+    yield request.param
+    T.set_mode(strict=False)
+
+
+def _apply(chain, d):
+    for t in chain:
+        d = t(d)
+    return d
+
+
+def _samples(R, n, keys, shape, dev, mask=True):
+    out = []
+    for _ in range(n):
+        s = {k: torch.from_numpy(R.rand(1, *shape).astype(np.float32)).to(dev) for k in keys}
+        if mask:
+            s["mask"] = torch.from_numpy((R.rand(1, *shape) > 0.7).astype(np.float32)).to(dev)
+        out.append(s)
+    return out
+
+
+@pytest.mark.parametrize("augment", [["flip", "affine"], ["flip", "affine", "shear"], ["affine"]])
+def test_classification_batch_equals_dictionary_surface(dev, augment):
+    R = np.random.RandomState(3)
+    keys, shape, crop = ["t2", "adc"], (40, 36, 24), [24, 20, 8]
+    samples = _samples(R, 7, keys, shape, dev)
+    # (an outer Compose would re-seed its children on construction, like MONAI's: chain by hand)
+    chain = [F.get_augmentations_class(augment, keys, "mask", [], flip_axis=[0, 1, 2], prob=0.6).set_random_state(17),
+             T.CenterSpatialCropd(keys + ["mask"], crop), T.ConcatItemsd(keys + ["mask"], "image")]
+    want = collate.safe_collate([_apply(chain, dict(s)) for s in samples])["image"]
+    aug = ClassificationBatchAugmenter(augment, keys, "mask", flip_axis=[0, 1, 2], prob=0.6, crop_size=crop, strict=True)
+    got = aug.set_random_state(17)(samples)["image"]
+    assert got.shape == (7, 3, *crop)
+    assert torch.equal(got.cpu(), want.cpu())
+
+
+@pytest.mark.parametrize("different_crop,vicregl", [(False, False), (True, False), (False, True)])
+def test_ssl_batch_equals_dictionary_surface(dev, different_crop, vicregl):
+    R = np.random.RandomState(5)
+    keys, copied, shape, roi = ["image"], ["image_copy"], (36, 32, 16), [24, 24, 12]
+    samples = _samples(R, 6, keys, shape, dev, mask=False)
+    tf = F.SSLTransforms(keys, copied, adc_keys=[], non_adc_keys=[])
+    chain = [tf.pre_transforms()[-1],   # CopyEntryd
+             T.Compose(F.get_augmentations_ssl(keys, copied, None, roi, vicregl, different_crop, n_transforms=3)).set_random_state(23),
+             *tf.post_transforms()]
+    np.random.seed(77)
+    want = collate.safe_collate([_apply(chain, dict(s)) for s in samples])
+    aug = SSLBatchAugmenter(keys, roi, n_transforms=3, different_crop=different_crop, vicregl=vicregl, strict=True)
+    np.random.seed(77)
+    got = aug.set_random_state(23)(samples)
+    for k in ("augmented_image_1", "augmented_image_2"):
+        assert got[k].shape == (6, 1, *roi)
+        assert torch.allclose(got[k].cpu(), want[k].cpu(), rtol=2e-6, atol=2e-6), (k, float((got[k].cpu() - want[k].cpu()).abs().max()))
+    if vicregl:
+        for k in ("box_1", "box_2"):
+            assert np.array_equal(np.asarray(got[k]), np.asarray(want[k]))
