@@ -72,7 +72,7 @@ class Item(C.Structure):
         ("fp_fix", C.c_int32),
         ("fp_U0", C.c_double * 3),
         ("fp_D", C.c_double * 9),
-        ("reserved", C.c_uint8 * 32),
+        ("shear", C.c_int8 * 32),
     ]
 
 

@@ -2,7 +2,7 @@
 # Builds libadell_b200.so in-tree for sm_100a (B200).  No other architecture is targeted.
 set -euo pipefail
 here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
-out="${here}/../libadell_b200.so"
+out="${OUT:-${here}/../libadell_b200.so}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 "${NVCC}" -shared -Xcompiler -fPIC -O3 -std=c++17 -lineinfo \
   -gencode arch=compute_100a,code=sm_100a \

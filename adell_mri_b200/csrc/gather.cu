@@ -26,6 +26,7 @@
 #include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "k1_math.cuh"
 
@@ -33,13 +34,20 @@ namespace {
 
 constexpr int K1_CWARPS = 16;                  // consumer warps per CTA
 constexpr int K1_CTHREADS = 32 * K1_CWARPS;    // consumer threads
-constexpr int K1_THREADS = K1_CTHREADS + 64;   // + one producer warp + one hand-over warp
+#ifndef K1_NPROD
+#define K1_NPROD 2                              // producer warps: warp p prepares / issues tiles seq = p (mod K1_NPROD)
+#endif
+constexpr int K1_THREADS = K1_CTHREADS + 32 + 32 * K1_NPROD;   // + one hand-over warp + the producer warps
+#ifndef K1_GROUPS
+#define K1_GROUPS 2                             // consumer groups: each works on its own tile (ring stage)
+#endif
+constexpr int K1_GWARPS = K1_CWARPS / K1_GROUPS;   // warps per group; a warp takes planes di = w, w + K1_GWARPS, ...
+constexpr int K1_GTHREADS = 32 * K1_GWARPS;
 constexpr int K1_T = 16;                       // base tile edge
 constexpr int K1_MAX_STAGES = 6;
-constexpr int K1_SMEM_BUDGET = 224 * 1024;     // dynamic shared memory per persistent CTA (1 CTA per SM)
+constexpr int K1_SMEM_BUDGET = 227 * 1024;     // dynamic shared memory per persistent CTA (1 CTA per SM): the sm_100 opt-in maximum
 constexpr int K1_MAX_BOX_BYTES = 100 * 1024;   // staged footprint limit (two stages)
-constexpr int K1_PREF_BOX_BYTES = 68 * 1024;   // preferred limit for the larger tile shapes (three stages)
-constexpr int K1_TS_CACHE = 2048;               // tile-prefix entries cached in shared memory (else read from global)
+constexpr int K1_TS_CACHE = 1024;               // tile-prefix entries cached in shared memory (else read from global)
 constexpr double K1_EPS = 1e-3;                // coordinate slack of the fast path / tie window
 constexpr float K1_MAGIC = 12582912.0f;        // 1.5 * 2^23: x + MAGIC has ulp 1 for |x| < 2^22
 constexpr uint32_t K1_MAGIC_BITS = 0x4B400000u;
@@ -241,10 +249,12 @@ template <class F>
 __device__ __forceinline__ void k1_for_each_voxel(const K1Tile& tl, const adell_item& it, F&& body) {
   const int s2 = __ffs(tl.T[2]) - 1, s1 = __ffs(tl.T[1]) - 1;
   const int nvox = tl.T[0] << (s1 + s2);
-  for (int v = threadIdx.x; v < nvox; v += K1_CTHREADS) {
+  for (int v = threadIdx.x % K1_GTHREADS; v < nvox; v += K1_GTHREADS) {
     const int dk = v & (tl.T[2] - 1), dj = (v >> s2) & (tl.T[1] - 1), di = v >> (s1 + s2);
-    const int o0 = tl.o0[0] + di, o1 = tl.o0[1] + dj, o2 = tl.o0[2] + dk;
-    if (o0 >= it.out_shape[0] || o1 >= it.out_shape[1] || o2 >= it.out_shape[2]) continue;
+    const int o2 = tl.o0[2] + dk;
+    const int G = (o2 >> 3) & 15;  // column group: its shift of the tile window (all zero without shear)
+    const int o0 = tl.o0[0] + di - it.shear[0][G], o1 = tl.o0[1] + dj - it.shear[1][G];
+    if (o0 < 0 || o1 < 0 || o0 >= it.out_shape[0] || o1 >= it.out_shape[1] || o2 >= it.out_shape[2]) continue;
     body(di, dj, dk, o0, o1, o2);
   }
 }
@@ -289,11 +299,15 @@ __device__ __noinline__ void k1_tile_exact_dispatch(const K1Ctx& c, const K1Tile
 struct __align__(16) K1Fast {
   float4 ax[3];          // per source axis a: {V0_a, D0_a, D1_a, D2_a}
   float4 gb;             // gain, bias, post_offset, noise_std
-  int4 n;                // n0, n1, n2 (voxels of the tile along each axis), kw (16 or 32 lanes along axis 2)
+  int4 n;                // T0, T1 (tile extents), n2 (voxels of the tile along axis 2), kw (16 or 32 lanes along axis 2)
+  int4 lim;              // valid window of (di - s0) and (dj - s1): {-o0, O0 - o0, -o1, O1 - o1} (o = tile origin)
+  float eg[4][4];        // per column group g = dk >> 3: {e_0, e_1, e_2} added to the fast coordinates,
+                         // [3] = bits s0 | s1 << 16: the group's shift of the tile window (k1_item_shear)
   int4 m;                // p0, p1 (box pitches in elements), rmask | padding mode << 8, cbase: tap byte address =
                          // cbase + 4*(bits0*p0 + bits1*p1 + bits2), bits = float bits of coordinate + MAGIC
   int4 fl;               // cold (padded | noise | philox), padded, philox, -
-  float4 rf[3];          // per source axis a: {S_a, S_a-1, rA_a, rB_a} (axes in rmask)
+  float4 rf[3];          // per source axis a: {1/(2 S_a), 2 S_a, S_a-1, rA_a} (axes in rmask)
+  float4 rb;             // rB_0, rB_1, rB_2: box-local index = rA*u' + rB for the axes in rmask
   int4 vlo, vhi;         // valid output range, tile-local
   float* dst;            // tile origin in the destination
   const float* noise;    // tile origin in the noise tensor (or null)
@@ -303,23 +317,16 @@ struct __align__(16) K1Fast {
   uint64_t philox_seed, philox_offset;
 };
 
-// ATen compute_coordinates on the fast coordinate (same formulas as k1_pad_coord, plain fp32).
-__device__ __noinline__ float k1_fast_reflect_far(float x, float Sf) {
-  const float n = floorf(x / Sf);
-  x = fmaf(-n, Sf, x);
-  if (static_cast<int>(n) & 1) x = Sf - x;
-  return x;
-}
-__device__ __forceinline__ float k1_fast_pad(float u, int pad, float Sf, float Sm1) {
-  if (pad == ADELL_PAD_REFLECTION) {
-    float x = fabsf(u + 0.5f);
-    if (x >= Sf) {              // beyond the upper edge: first mirrored period inline, the rest out of line
-      x = 2.0f * Sf - x;
-      if (x < 0.0f) x = k1_fast_reflect_far(2.0f * Sf - x, Sf);
-    }
-    u = x - 0.5f;
-  }
-  return fminf(Sm1, fmaxf(u, 0.0f));
+// ATen compute_coordinates on the fast coordinate, branch-free.  Reflection about -0.5 and S-0.5 is a
+// triangle wave of period 2S: with y = (u + 0.5) / 2S and f = y - rint(y) in [-0.5, 0.5], the
+// reflected coordinate is |f| * 2S - 0.5 (then the clamp to [0, S-1] ATen applies as well).  The
+// producer shifts the tile's coordinates by a whole number of periods so that |y| stays small
+// (error of the fold: a few 1e-6 voxel).  rint is the round-to-nearest add of 1.5 * 2^23.
+__device__ __forceinline__ float k1_fold_reflect(float u, float inv2S, float hinv, float twoS, float Sm1) {
+  const float y = fmaf(u, inv2S, hinv);
+  const float n = __fadd_rn(y, K1_MAGIC) - K1_MAGIC;
+  const float x = fmaf(fabsf(y - n), twoS, -0.5f);
+  return fminf(Sm1, fmaxf(x, 0.0f));
 }
 
 // bit-faithful replay for one nearest voxel (tie window of the fast path); cold
@@ -337,47 +344,99 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
   return v;
 }
 
-// Per-thread register image of a staged tile.
-template <bool RMASK>
+// Per-thread register image of a staged tile.  RM: 0 = every coordinate of the tile stays inside
+// [0,S); 1 = only source axis 2 leaves it and the padding is reflection (the common case of a thin,
+// rotated volume); 2 = any axes, border or reflection (block-uniform branches per axis).
+template <int RM>
 struct K1Hot {
   float D1[3], P[3];      // coordinate along dj: v_a = P_a + D1_a * dj
   float gain, bias;
   uint32_t p0, p1, cbase; // tap address = cbase + 4*(bits0*p0 + bits1*p1 + bits2), bits = float bits of x + MAGIC
-  float Sf[3], Sm1[3], rA[3], rB[3];
+  float inv2S[3], hinv[3], twoS[3], Sm1[3], rA[3], rB[3];
   int rmask, pad;
 };
 
-template <bool RMASK>
-__device__ __forceinline__ void k1_hot_load(K1Hot<RMASK>& h, const K1Fast& f, int di, int dk) {
+template <int RM>
+__device__ __forceinline__ void k1_hot_plane(K1Hot<RM>& h, const K1Fast& f, int di, int dk, const float4 e) {
   const float fk = static_cast<float>(dk), fi = static_cast<float>(di);
+  const float eg[3] = {e.x, e.y, e.z};
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     const float4 q = f.ax[a];
     h.D1[a] = q.z;
-    h.P[a] = fmaf(q.y, fi, fmaf(q.w, fk, q.x));
+    h.P[a] = fmaf(q.y, fi, fmaf(q.w, fk, q.x)) + eg[a];
   }
+}
+template <int RM>
+__device__ __forceinline__ void k1_hot_load(K1Hot<RM>& h, const K1Fast& f) {
   const float4 gb = f.gb;
   const int4 m = f.m;
   h.gain = gb.x; h.bias = gb.y;
   h.p0 = static_cast<uint32_t>(m.x); h.p1 = static_cast<uint32_t>(m.y);
   h.cbase = static_cast<uint32_t>(m.w);  // computed by the producer (modulo 2^32 on purpose)
-  if (RMASK) {
+  if (RM) {
     h.rmask = m.z & 0xff; h.pad = m.z >> 8;
+    const float4 rb = f.rb;
+    h.rB[0] = rb.x; h.rB[1] = rb.y; h.rB[2] = rb.z;
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
+    for (int a = (RM == 1 ? 2 : 0); a < 3; ++a) {
       const float4 q = f.rf[a];
-      h.Sf[a] = q.x; h.Sm1[a] = q.y; h.rA[a] = q.z; h.rB[a] = q.w;
+      h.inv2S[a] = q.x; h.hinv[a] = 0.5f * q.x; h.twoS[a] = q.y; h.Sm1[a] = q.z; h.rA[a] = q.w;
     }
   }
 }
 
-template <bool RMASK>
-__device__ __forceinline__ void k1_fast_coords(const K1Hot<RMASK>& h, float fj, float& v0, float& v1, float& v2) {
+// Thread -> voxels of a staged tile: warp = plane di, lanes along axis 2 (32, or 16 x 2 rows), loop
+// over dj.  The thread's column group g = dk >> 3 shifts the tile window by (s0, s1) (k1_item_shear):
+// output voxel (o0 + di - s0, o1 + dj - s1, o2 + dk).
+struct K1Map {
+  int dk, s0, s1;        // lane's column along axis 2 and its group's shifts
+  int jj, jstep;         // lane's first row and row step (32 lanes along axis 2, or 16 x 2 rows)
+  int jlo, jhi;          // window of dj that falls inside the output
+  int ii;                // current plane: di - s0
+  int j0, cnt;           // first dj of this thread and its number of voxels in the current plane
+  float4 e;
+};
+// per tile: false when the lane has no voxels at all
+__device__ __forceinline__ bool k1_lane_map(const K1Fast& f, K1Map& m) {
+  const int4 n = f.n;
+  const int lane = threadIdx.x & 31;
+  if (n.w == 32) { m.dk = lane; m.jj = 0; m.jstep = 1; }
+  else { m.dk = lane & 15; m.jj = lane >> 4; m.jstep = 2; }
+  if (m.dk >= n.z) return false;
+  m.e = *reinterpret_cast<const float4*>(f.eg[m.dk >> 3]);
+  const int sh = __float_as_int(m.e.w);
+  m.s0 = sh & 0xffff;
+  m.s1 = sh >> 16;
+  const int4 lim = f.lim;
+  m.jlo = max(0, lim.z + m.s1); m.jhi = min(n.y, lim.w + m.s1);
+  m.j0 = m.jlo + ((m.jj - m.jlo) & (m.jstep - 1));
+  m.cnt = m.jhi > m.j0 ? (m.jhi - m.j0 + m.jstep - 1) / m.jstep : 0;
+  return m.cnt > 0;
+}
+// per plane di: false when the plane's row of this lane lies outside the output
+__device__ __forceinline__ bool k1_plane_map(const K1Fast& f, K1Map& m, int di) {
+  m.ii = di - m.s0;
+  return m.ii >= f.lim.x && m.ii < f.lim.y;
+}
+
+template <int RM>
+__device__ __forceinline__ float k1_fast_pad_axis(const K1Hot<RM>& h, int a, float v) {
+  float x;
+  if (RM == 1 || h.pad == ADELL_PAD_REFLECTION) x = k1_fold_reflect(v, h.inv2S[a], h.hinv[a], h.twoS[a], h.Sm1[a]);
+  else x = fminf(h.Sm1[a], fmaxf(v, 0.0f));
+  return fmaf(h.rA[a], x, h.rB[a]);
+}
+
+template <int RM>
+__device__ __forceinline__ void k1_fast_coords(const K1Hot<RM>& h, float fj, float& v0, float& v1, float& v2) {
   v0 = fmaf(h.D1[0], fj, h.P[0]); v1 = fmaf(h.D1[1], fj, h.P[1]); v2 = fmaf(h.D1[2], fj, h.P[2]);
-  if (RMASK) {  // block-uniform: some axis leaves [0,S) inside this tile
-    if (h.rmask & 1) v0 = fmaf(h.rA[0], k1_fast_pad(v0, h.pad, h.Sf[0], h.Sm1[0]), h.rB[0]);
-    if (h.rmask & 2) v1 = fmaf(h.rA[1], k1_fast_pad(v1, h.pad, h.Sf[1], h.Sm1[1]), h.rB[1]);
-    if (h.rmask & 4) v2 = fmaf(h.rA[2], k1_fast_pad(v2, h.pad, h.Sf[2], h.Sm1[2]), h.rB[2]);
+  if (RM == 1) {
+    v2 = k1_fast_pad_axis<RM>(h, 2, v2);
+  } else if (RM == 2) {  // block-uniform: some axis leaves [0,S) inside this tile
+    if (h.rmask & 1) v0 = k1_fast_pad_axis<RM>(h, 0, v0);
+    if (h.rmask & 2) v1 = k1_fast_pad_axis<RM>(h, 1, v1);
+    if (h.rmask & 4) v2 = k1_fast_pad_axis<RM>(h, 2, v2);
   }
 }
 
@@ -386,10 +445,10 @@ struct K1Vox {
   uint32_t a;  // shared-memory byte address of tap (0,0,0)
 };
 
-template <bool RMASK>
-__device__ __forceinline__ K1Vox k1_fast_vox(const K1Hot<RMASK>& h, float fj) {
+template <int RM>
+__device__ __forceinline__ K1Vox k1_fast_vox(const K1Hot<RM>& h, float fj) {
   float v0, v1, v2;
-  k1_fast_coords<RMASK>(h, fj, v0, v1, v2);
+  k1_fast_coords<RM>(h, fj, v0, v1, v2);
   // floor on the FMA pipe: round-down add of 1.5*2^23 leaves floor(x) in the low mantissa bits
   const float t0 = __fadd_rd(v0, K1_MAGIC), t1 = __fadd_rd(v1, K1_MAGIC), t2 = __fadd_rd(v2, K1_MAGIC);
   K1Vox x;
@@ -405,139 +464,144 @@ __device__ __forceinline__ float k1_lerp8(const K1Vox& x, const float* t) {
   return fmaf(x.r0, y1 - y0, y0);
 }
 
-// lane -> (dk, first dj, dj step): 32 lanes along axis 2 for 32-wide tiles, else 16 x 2 rows
-__device__ __forceinline__ void k1_lane_map(int kw, int& dk, int& jj, int& jstep) {
-  const int lane = threadIdx.x & 31;
-  if (kw == 32) { dk = lane; jj = 0; jstep = 1; }
-  else { dk = lane & 15; jj = lane >> 4; jstep = 2; }
-}
-
 // Trilinear, plain tiles (no output pad band, no noise): NV voxels per iteration, all their
 // shared-memory taps issued before any arithmetic that depends on them (the loads are volatile
 // asm so ptxas keeps them batched); no per-voxel bounds checks — a thread's voxel count is split
 // into full groups and a one-at-a-time tail.
-template <int NV, bool RMASK>
+template <int NV, int RMASK>
 __device__ __forceinline__ void k1_tile_staged_trilinear(const K1Fast& f) {
-  const int4 n = f.n;
-  int dk, jj, jstep;
-  k1_lane_map(n.w, dk, jj, jstep);
-  const int di = threadIdx.x >> 5;
-  if (dk >= n.z || di >= n.x) return;
+  K1Map m;
+  if (!k1_lane_map(f, m)) return;
   K1Hot<RMASK> h;
-  k1_hot_load<RMASK>(h, f, di, dk);
+  k1_hot_load<RMASK>(h, f);
   const uint32_t o1 = 4u * h.p1, o0 = 4u * h.p0;
   const int64_t ds1 = f.ds1;
-  float* p = f.dst + di * f.ds0 + dk * f.ds2 + jj * ds1;
-  const int64_t pstep = jstep * ds1;
-  const float fstep = static_cast<float>(jstep);
-  float fj = static_cast<float>(jj);
-  int cnt = (n.y - jj + jstep - 1) / jstep;  // voxels of this thread
+  const int64_t pstep = m.jstep * ds1;
+  const float fstep = static_cast<float>(m.jstep);
+  const int T0 = f.n.x;
 #pragma unroll 1
-  for (; cnt >= NV; cnt -= NV) {
-    K1Vox x[NV];
-    float t[NV][8];
-#pragma unroll
-    for (int u = 0; u < NV; ++u) x[u] = k1_fast_vox<RMASK>(h, fj + static_cast<float>(u) * fstep);
-#pragma unroll
-    for (int u = 0; u < NV; ++u) {
-      t[u][0] = lds_f32(x[u].a); t[u][1] = lds_f32(x[u].a + 4);
-      t[u][2] = lds_f32(x[u].a + o1); t[u][3] = lds_f32(x[u].a + o1 + 4);
-    }
-#pragma unroll
-    for (int u = 0; u < NV; ++u) {
-      t[u][4] = lds_f32(x[u].a + o0); t[u][5] = lds_f32(x[u].a + o0 + 4);
-      t[u][6] = lds_f32(x[u].a + o0 + o1); t[u][7] = lds_f32(x[u].a + o0 + o1 + 4);
-    }
-#pragma unroll
-    for (int u = 0; u < NV; ++u) p[u * pstep] = fmaf(k1_lerp8(x[u], t[u]), h.gain, h.bias);
-    p += NV * pstep;
-    fj += static_cast<float>(NV) * fstep;
-  }
+  for (int di = (threadIdx.x >> 5) % K1_GWARPS; di < T0; di += K1_GWARPS) {
+    if (!k1_plane_map(f, m, di)) continue;
+    k1_hot_plane<RMASK>(h, f, di, m.dk, m.e);
+    float* p = f.dst + m.ii * f.ds0 + m.dk * f.ds2 + (m.j0 - m.s1) * ds1;
+    float fj = static_cast<float>(m.j0);
+    int cnt = m.cnt;
 #pragma unroll 1
-  for (; cnt > 0; --cnt) {
-    const K1Vox x = k1_fast_vox<RMASK>(h, fj);
-    float t[8];
-    t[0] = lds_f32(x.a); t[1] = lds_f32(x.a + 4); t[2] = lds_f32(x.a + o1); t[3] = lds_f32(x.a + o1 + 4);
-    t[4] = lds_f32(x.a + o0); t[5] = lds_f32(x.a + o0 + 4); t[6] = lds_f32(x.a + o0 + o1); t[7] = lds_f32(x.a + o0 + o1 + 4);
-    *p = fmaf(k1_lerp8(x, t), h.gain, h.bias);
-    p += pstep;
-    fj += fstep;
+    for (; cnt >= NV; cnt -= NV) {
+      K1Vox x[NV];
+      float t[NV][8];
+#pragma unroll
+      for (int u = 0; u < NV; ++u) x[u] = k1_fast_vox<RMASK>(h, fj + static_cast<float>(u) * fstep);
+#pragma unroll
+      for (int u = 0; u < NV; ++u) {
+        t[u][0] = lds_f32(x[u].a); t[u][1] = lds_f32(x[u].a + 4);
+        t[u][2] = lds_f32(x[u].a + o1); t[u][3] = lds_f32(x[u].a + o1 + 4);
+      }
+#pragma unroll
+      for (int u = 0; u < NV; ++u) {
+        t[u][4] = lds_f32(x[u].a + o0); t[u][5] = lds_f32(x[u].a + o0 + 4);
+        t[u][6] = lds_f32(x[u].a + o0 + o1); t[u][7] = lds_f32(x[u].a + o0 + o1 + 4);
+      }
+#pragma unroll
+      for (int u = 0; u < NV; ++u) p[u * pstep] = fmaf(k1_lerp8(x[u], t[u]), h.gain, h.bias);
+      p += NV * pstep;
+      fj += static_cast<float>(NV) * fstep;
+    }
+#pragma unroll 1
+    for (; cnt > 0; --cnt) {
+      const K1Vox x = k1_fast_vox<RMASK>(h, fj);
+      float t[8];
+      t[0] = lds_f32(x.a); t[1] = lds_f32(x.a + 4); t[2] = lds_f32(x.a + o1); t[3] = lds_f32(x.a + o1 + 4);
+      t[4] = lds_f32(x.a + o0); t[5] = lds_f32(x.a + o0 + 4); t[6] = lds_f32(x.a + o0 + o1); t[7] = lds_f32(x.a + o0 + o1 + 4);
+      *p = fmaf(k1_lerp8(x, t), h.gain, h.bias);
+      p += pstep;
+      fj += fstep;
+    }
   }
 }
 
 // Nearest, plain tiles: fast coordinates, exact replay inside the tie window.
-template <bool RMASK>
+template <int RMASK>
 __device__ __forceinline__ void k1_tile_staged_nearest(const K1Ctx& c, const K1Tile& tl, const K1Fast& f, const float* __restrict__ box) {
-  const int4 n = f.n;
-  int dk, jj, jstep;
-  k1_lane_map(n.w, dk, jj, jstep);
-  const int di = threadIdx.x >> 5;
-  if (dk >= n.z || di >= n.x) return;
+  K1Map m;
+  if (!k1_lane_map(f, m)) return;
   K1Hot<RMASK> h;
-  k1_hot_load<RMASK>(h, f, di, dk);
+  k1_hot_load<RMASK>(h, f);
   const float tie = 0.5f - static_cast<float>(K1_EPS);
   const int64_t ds1 = f.ds1;
-  float* p = f.dst + di * f.ds0 + dk * f.ds2 + jj * ds1;
-  const int64_t pstep = jstep * ds1;
+  const int64_t pstep = m.jstep * ds1;
+  const int T0 = f.n.x;
+#pragma unroll 1
+  for (int di = (threadIdx.x >> 5) % K1_GWARPS; di < T0; di += K1_GWARPS) {
+    if (!k1_plane_map(f, m, di)) continue;
+    k1_hot_plane<RMASK>(h, f, di, m.dk, m.e);
+    float* p = f.dst + m.ii * f.ds0 + m.dk * f.ds2 + (m.j0 - m.s1) * ds1;
+    int dj = m.j0;
 #pragma unroll 2
-  for (int dj = jj; dj < n.y; dj += jstep) {
-    float v0, v1, v2;
-    k1_fast_coords<RMASK>(h, static_cast<float>(dj), v0, v1, v2);
-    // rint (ties to even) on the FMA pipe: x + 1.5*2^23 rounds to the nearest integer
-    const float t0 = __fadd_rn(v0, K1_MAGIC), t1 = __fadd_rn(v1, K1_MAGIC), t2 = __fadd_rn(v2, K1_MAGIC);
-    const float n0 = t0 - K1_MAGIC, n1 = t1 - K1_MAGIC, n2 = t2 - K1_MAGIC;
-    float val;
-    if (fabsf(v0 - n0) > tie || fabsf(v1 - n1) > tie || fabsf(v2 - n2) > tie) {
-      val = k1_exact_nearest_smem(c, tl, box, di, dj, dk);  // within 1e-3 of a rounding tie
-    } else {
-      const uint32_t a = h.cbase + 4u * (__float_as_uint(t0) * h.p0 + __float_as_uint(t1) * h.p1 + __float_as_uint(t2));
-      val = fmaf(lds_f32(a), h.gain, h.bias);
+    for (int cnt = m.cnt; cnt > 0; --cnt, dj += m.jstep) {
+      float v0, v1, v2;
+      k1_fast_coords<RMASK>(h, static_cast<float>(dj), v0, v1, v2);
+      // rint (ties to even) on the FMA pipe: x + 1.5*2^23 rounds to the nearest integer
+      const float t0 = __fadd_rn(v0, K1_MAGIC), t1 = __fadd_rn(v1, K1_MAGIC), t2 = __fadd_rn(v2, K1_MAGIC);
+      const float n0 = t0 - K1_MAGIC, n1 = t1 - K1_MAGIC, n2 = t2 - K1_MAGIC;
+      float val;
+      if (fabsf(v0 - n0) > tie || fabsf(v1 - n1) > tie || fabsf(v2 - n2) > tie) {
+        val = k1_exact_nearest_smem(c, tl, box, m.ii, dj - m.s1, m.dk);  // within 1e-3 of a rounding tie
+      } else {
+        const uint32_t a = h.cbase + 4u * (__float_as_uint(t0) * h.p0 + __float_as_uint(t1) * h.p1 + __float_as_uint(t2));
+        val = fmaf(lds_f32(a), h.gain, h.bias);
+      }
+      *p = val;
+      p += pstep;
     }
-    *p = val;
-    p += pstep;
   }
 }
 
 // Rare tiles: output pad band (SpatialPadd after the resample), injected or Philox noise.  Same
 // arithmetic as the plain loops, one voxel at a time, out of line.
 __device__ __noinline__ void k1_tile_staged_cold(const K1Ctx& c, const K1Tile& tl, const K1Fast& f, const float* __restrict__ box) {
-  const int4 n = f.n;
-  int dk, jj, jstep;
-  k1_lane_map(n.w, dk, jj, jstep);
-  const int di = threadIdx.x >> 5;
-  if (dk >= n.z || di >= n.x) return;
-  K1Hot<true> h;
-  k1_hot_load<true>(h, f, di, dk);
+  K1Map m;
+  if (!k1_lane_map(f, m)) return;
+  const int dk = m.dk;
+  K1Hot<2> h;
+  k1_hot_load<2>(h, f);
   const bool nearest = c.it.interp == ADELL_NEAREST;
   const float tie = 0.5f - static_cast<float>(K1_EPS);
   const uint32_t o1 = 4u * h.p1, o0 = 4u * h.p0;
   const int4 vlo = f.vlo, vhi = f.vhi, fl = f.fl;
   const float4 gb = f.gb;
-  for (int dj = jj; dj < n.y; dj += jstep) {
-    float val;
-    if (nearest) {
-      float v0, v1, v2;
-      k1_fast_coords<true>(h, static_cast<float>(dj), v0, v1, v2);
-      const float t0 = __fadd_rn(v0, K1_MAGIC), t1 = __fadd_rn(v1, K1_MAGIC), t2 = __fadd_rn(v2, K1_MAGIC);
-      if (fabsf(v0 - (t0 - K1_MAGIC)) > tie || fabsf(v1 - (t1 - K1_MAGIC)) > tie || fabsf(v2 - (t2 - K1_MAGIC)) > tie)
-        val = k1_exact_nearest_smem(c, tl, box, di, dj, dk);
-      else
-        val = fmaf(lds_f32(h.cbase + 4u * (__float_as_uint(t0) * h.p0 + __float_as_uint(t1) * h.p1 + __float_as_uint(t2))), h.gain, h.bias);
-    } else {
-      const K1Vox x = k1_fast_vox<true>(h, static_cast<float>(dj));
-      float t[8];
-      t[0] = lds_f32(x.a); t[1] = lds_f32(x.a + 4); t[2] = lds_f32(x.a + o1); t[3] = lds_f32(x.a + o1 + 4);
-      t[4] = lds_f32(x.a + o0); t[5] = lds_f32(x.a + o0 + 4); t[6] = lds_f32(x.a + o0 + o1); t[7] = lds_f32(x.a + o0 + o1 + 4);
-      val = fmaf(k1_lerp8(x, t), h.gain, h.bias);
+  const int T0 = f.n.x;
+  for (int di = (threadIdx.x >> 5) % K1_GWARPS; di < T0; di += K1_GWARPS) {
+    if (!k1_plane_map(f, m, di)) continue;
+    k1_hot_plane<2>(h, f, di, dk, m.e);
+    int dj = m.j0;
+    for (int cnt = m.cnt; cnt > 0; --cnt, dj += m.jstep) {
+      const int jo = dj - m.s1;  // tile-local output position (ii, jo, dk)
+      float val;
+      if (nearest) {
+        float v0, v1, v2;
+        k1_fast_coords<2>(h, static_cast<float>(dj), v0, v1, v2);
+        const float t0 = __fadd_rn(v0, K1_MAGIC), t1 = __fadd_rn(v1, K1_MAGIC), t2 = __fadd_rn(v2, K1_MAGIC);
+        if (fabsf(v0 - (t0 - K1_MAGIC)) > tie || fabsf(v1 - (t1 - K1_MAGIC)) > tie || fabsf(v2 - (t2 - K1_MAGIC)) > tie)
+          val = k1_exact_nearest_smem(c, tl, box, m.ii, jo, dk);
+        else
+          val = fmaf(lds_f32(h.cbase + 4u * (__float_as_uint(t0) * h.p0 + __float_as_uint(t1) * h.p1 + __float_as_uint(t2))), h.gain, h.bias);
+      } else {
+        const K1Vox x = k1_fast_vox<2>(h, static_cast<float>(dj));
+        float t[8];
+        t[0] = lds_f32(x.a); t[1] = lds_f32(x.a + 4); t[2] = lds_f32(x.a + o1); t[3] = lds_f32(x.a + o1 + 4);
+        t[4] = lds_f32(x.a + o0); t[5] = lds_f32(x.a + o0 + 4); t[6] = lds_f32(x.a + o0 + o1); t[7] = lds_f32(x.a + o0 + o1 + 4);
+        val = fmaf(k1_lerp8(x, t), h.gain, h.bias);
+      }
+      if (fl.y) {
+        const bool ov = (m.ii >= vlo.x) & (m.ii < vhi.x) & (jo >= vlo.y) & (jo < vhi.y) & (dk >= vlo.z) & (dk < vhi.z);
+        if (!ov) val = gb.z;
+      }
+      const int64_t rel = m.ii * f.ns0 + jo * f.ns1 + dk;
+      if (f.noise != nullptr) val = __fadd_rn(val, __ldg(f.noise + rel));
+      if (fl.z) val = fmaf(gb.w, adell_philox_normal(f.philox_seed, f.philox_offset + f.olin0 + rel), val);
+      f.dst[m.ii * f.ds0 + jo * f.ds1 + dk * f.ds2] = val;
     }
-    if (fl.y) {
-      const bool ov = (di >= vlo.x) & (di < vhi.x) & (dj >= vlo.y) & (dj < vhi.y) & (dk >= vlo.z) & (dk < vhi.z);
-      if (!ov) val = gb.z;
-    }
-    const int64_t rel = di * f.ns0 + dj * f.ns1 + dk;
-    if (f.noise != nullptr) val = __fadd_rn(val, __ldg(f.noise + rel));
-    if (fl.z) val = fmaf(gb.w, adell_philox_normal(f.philox_seed, f.philox_offset + f.olin0 + rel), val);
-    f.dst[di * f.ds0 + dj * f.ds1 + dk * f.ds2] = val;
   }
 }
 
@@ -549,7 +613,9 @@ __device__ __noinline__ void k1_tile_staged_cold(const K1Ctx& c, const K1Tile& t
 // along the contiguous axis reverses the quad in registers.
 __device__ __forceinline__ void k1_tile_copy_box(const K1Ctx& c, const K1Tile& tl, const float* __restrict__ box) {
   const adell_item& it = c.it;
-  const int q = threadIdx.x & 7, dj = (threadIdx.x >> 3) & 15, di0 = threadIdx.x >> 7;
+  constexpr int PS = K1_GTHREADS / 128;  // planes a group covers per step (a plane = 16 rows x 8 quads)
+  const int gtid = threadIdx.x % K1_GTHREADS;
+  const int q = gtid & 7, dj = (gtid >> 3) & 15, di0 = gtid >> 7;
   const int o0 = tl.o0[0] + di0, o1 = tl.o0[1] + dj, o2 = tl.o0[2] + 4 * q;
   const int O0 = it.out_shape[0];
   if (o1 >= it.out_shape[1] || o2 >= it.out_shape[2] || o0 >= O0) return;
@@ -561,16 +627,16 @@ __device__ __forceinline__ void k1_tile_copy_box(const K1Ctx& c, const K1Tile& t
   const int m2 = rev ? M2 - (o2 + 3) : M2 + o2;  // lowest box column of the quad
   const int p1 = tl.box[2], p0 = tl.box[1] * tl.box[2];
   const float* sp = box + (s0 * o0 + M0) * p0 + (s1 * o1 + M1) * p1 + m2;
-  const int sstep = 4 * s0 * p0;
+  const int sstep = PS * s0 * p0;
   const bool vec = (m2 & 3) == 0;  // block-uniform: the same for every quad of every tile of an item
   const bool clip = (it.flags & ADELL_F_CLIP) != 0;
   const float pre_s = c.pre_s, pre_o = c.pre_o, post_s = it.post_scale, post_o = it.post_offset;
   const float clo = it.clip_lo, chi = it.clip_hi;
   const float gain = pre_s * post_s, bias = fmaf(pre_o, post_s, post_o);
   const bool plain = !clip && gain == 1.0f && bias == 0.0f;
-  const int64_t dstep = 4 * it.dst_stride[0];
+  const int64_t dstep = PS * it.dst_stride[0];
   float* dp = it.dst + o0 * it.dst_stride[0] + o1 * it.dst_stride[1] + o2;
-  const int nrow = min(8, (min(O0 - o0, tl.T[0] - di0) + 3) >> 2);  // rows o0 + 4r of this thread inside the tile
+  const int nrow = (min(O0 - o0, tl.T[0] - di0) + PS - 1) / PS;  // rows o0 + PS*r of this thread inside the tile
   auto fix = [&](float4 x) {
     if (rev) { float t = x.x; x.x = x.w; x.w = t; t = x.y; x.y = x.z; x.z = t; }
     if (plain) return x;
@@ -585,9 +651,14 @@ __device__ __forceinline__ void k1_tile_copy_box(const K1Ctx& c, const K1Tile& t
     return x;
   };
   if (vec) {
+    // eight independent 128-bit loads in flight per thread, then their stores
+#pragma unroll 1
+    for (int r0 = 0; r0 < nrow; r0 += 8) {
 #pragma unroll
-    for (int r = 0; r < 8; ++r)
-      if (r < nrow) K1_STORE(reinterpret_cast<float4*>(dp + r * dstep), fix(*reinterpret_cast<const float4*>(sp + r * sstep)));
+      for (int r = 0; r < 8; ++r)
+        if (r0 + r < nrow)
+          K1_STORE(reinterpret_cast<float4*>(dp + (r0 + r) * dstep), fix(*reinterpret_cast<const float4*>(sp + (r0 + r) * sstep)));
+    }
   } else {
 #pragma unroll 2
     for (int r = 0; r < nrow; ++r) {
@@ -639,7 +710,28 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
   const double U0 = fma(it.fp_D[3 * a + 2], static_cast<double>(o02),
                         fma(it.fp_D[3 * a + 1], static_cast<double>(o01),
                             fma(it.fp_D[3 * a + 0], static_cast<double>(o00), it.fp_U0[a])));
-  const double umin = U0 + static_cast<double>(it.fp_smin[a]), umax = U0 + static_cast<double>(it.fp_smax[a]);
+  // column groups of this tile: group term e(g) = D_a2*8g - D_a0*s0(G) - D_a1*s1(G) (see k1_item_shear);
+  // fp_smin/fp_smax hold the footprint of ONE group (di, dj over the tile, 8 voxels along axis 2)
+  const int G0 = o02 >> 3;
+  const int ng = min(static_cast<int>(it.tile_dim[2]) >> 3, (it.out_shape[2] - o02 + 7) >> 3);
+  double emin = 0.0, emax = 0.0;
+  float egv[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // -D_a0*s0(G) - D_a1*s1(G): added to the group's fast coordinates
+  int shv[4] = {0, 0, 0, 0};
+  int sa_max = 0;  // largest shift of this tile's groups along output axis a (axes 0, 1)
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    if (g < ng) {
+      const int s0 = it.shear[0][(G0 + g) & 15], s1 = it.shear[1][(G0 + g) & 15];
+      sa_max = max(sa_max, a == 0 ? s0 : (a == 1 ? s1 : 0));
+      const double sh = -(it.fp_D[3 * a + 0] * s0 + it.fp_D[3 * a + 1] * s1);
+      const double ev = fma(it.fp_D[3 * a + 2], 8.0 * g, sh);
+      emin = g == 0 ? ev : fmin(emin, ev);
+      emax = g == 0 ? ev : fmax(emax, ev);
+      egv[g] = static_cast<float>(sh);
+      shv[g] = s0 | (s1 << 16);
+    }
+  }
+  const double umin = U0 + emin + static_cast<double>(it.fp_smin[a]), umax = U0 + emax + static_cast<double>(it.fp_smax[a]);
   const bool finite = (umin > -1.0e6) && (umax < 1.0e6);
   if (!__all_sync(FULL, finite)) { if (lane == 0) tl.mode = MODE_DIRECT; return; }
   const int S = it.src_shape[a];
@@ -666,9 +758,13 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
     } else {
       rlo = 0; rhi = S - 1;
     }
-    blo = rlo; bhi = rhi + 1;  // the hi tap of u' == S-1 reads cell S: TMA zero fill, weight 0
+    // the fast path clamps u' just below S-1: the hi tap never reads cell S, and the lo tap of a
+    // coordinate clamped at the upper edge is S-2
+    blo = min(rlo, max(S - 2, 0)); bhi = rhi + (S == 1 ? 1 : 0);
   }
-  const bool fits = bhi - blo + 1 + (a == 2 ? 3 : 0) <= it.tmap_box[a];  // else larger than the encoded box
+  // cells [blo, bhi] plus, along the contiguous axis, those lost to aligning the box origin down to 16 bytes
+  const int mo_raw = it.tmap_sign[a] > 0 ? blo + it.tmap_off[a] : -bhi + it.tmap_off[a];
+  const bool fits = bhi - blo + 1 + (a == 2 ? (mo_raw & 3) : 0) <= it.tmap_box[a];  // else larger than the encoded box
   const bool allv = lo >= c.tlo[a] && hi < c.thi[a];
   const bool win_full = c.tlo[a] <= 0 && c.thi[a] >= S;
   if (!__all_sync(FULL, fits)) { if (lane == 0) tl.mode = MODE_DIRECT; return; }
@@ -685,11 +781,17 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
   const int mconst = it.tmap_off[a] - mo;
   float V0, Dm0, Dm1, Dm2, rA, rB;
   if (rm) {
-    V0 = static_cast<float>(U0);
+    // reflection is periodic in 2S: move the tile's coordinates next to the origin (whole periods,
+    // exact in fp64) so that the fold's fp32 arithmetic keeps its precision far from the volume
+    double sh = 0.0;
+    if (it.padding == ADELL_PAD_REFLECTION) sh = 2.0 * S * rint((0.5 * (umin + umax) + 0.5) / (2.0 * S));
+    V0 = static_cast<float>(U0 - sh);  // (group terms egv stay in source orientation, like Dm)
     Dm0 = static_cast<float>(it.fp_D[3 * a + 0]); Dm1 = static_cast<float>(it.fp_D[3 * a + 1]); Dm2 = static_cast<float>(it.fp_D[3 * a + 2]);
     rA = static_cast<float>(msign); rB = static_cast<float>(mconst);
   } else {
     V0 = static_cast<float>(msign * U0 + mconst);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) egv[g] *= static_cast<float>(msign);
     Dm0 = static_cast<float>(msign * it.fp_D[3 * a + 0]); Dm1 = static_cast<float>(msign * it.fp_D[3 * a + 1]);
     Dm2 = static_cast<float>(msign * it.fp_D[3 * a + 2]);
     rA = 1.0f; rB = 0.0f;
@@ -697,9 +799,11 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
   K1Fast& f = sl.fast;
   const int na = min(static_cast<int>(it.tile_dim[a]), it.out_shape[a] - o0a);
   const int vlo = it.out_vlo[a] - o0a, vhi = it.out_vhi[a] - o0a;
-  const bool padded_a = vlo > 0 || vhi < na;
+  // does any voxel of the tile (its window may be shifted down by up to sa_max) lie in an output pad band?
+  const bool padded_a = it.out_vlo[a] > max(0, o0a - sa_max) || it.out_vhi[a] < min(it.out_shape[a], o0a + static_cast<int>(it.tile_dim[a]));
   const bool padded = __any_sync(FULL, ax && padded_a);
   const int n0 = __shfl_sync(FULL, na, 0), n1 = __shfl_sync(FULL, na, 1), n2 = __shfl_sync(FULL, na, 2);
+  const float rB0 = __shfl_sync(FULL, rB, 0), rB1 = __shfl_sync(FULL, rB, 1), rB2 = __shfl_sync(FULL, rB, 2);
   const int vl0 = __shfl_sync(FULL, vlo, 0), vl1 = __shfl_sync(FULL, vlo, 1), vl2 = __shfl_sync(FULL, vlo, 2);
   const int vh0 = __shfl_sync(FULL, vhi, 0), vh1 = __shfl_sync(FULL, vhi, 1), vh2 = __shfl_sync(FULL, vhi, 2);
   if (ax) {
@@ -707,7 +811,10 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
     tl.box[a] = it.tmap_box[a]; tl.msign[a] = msign; tl.mconst[a] = mconst;
     tl.V0[a] = V0; tl.Dm[a][0] = Dm0; tl.Dm[a][1] = Dm1; tl.Dm[a][2] = Dm2; tl.rA[a] = rA; tl.rB[a] = rB;
     f.ax[a] = make_float4(V0, Dm0, Dm1, Dm2);
-    f.rf[a] = make_float4(c.Sf[a], c.Sm1[a], rA, rB);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) f.eg[g][a] = egv[g];
+    // clamp just below S-1 (one ulp): floor(u') + 1 <= S-1, the lerp error is <= 2^-23 of the step
+    f.rf[a] = make_float4(0.5f / c.Sf[a], 2.0f * c.Sf[a], c.Sm1[a] > 0.0f ? __uint_as_float(__float_as_uint(c.Sm1[a]) - 1u) : 0.0f, rA);
     if (a == 2) {  // alignment slack columns of the tensor map that fall inside this box
       tl.fix_lo = max(0, -mo);
       tl.fix_hi = it.fp_fix > 0 ? min(it.tmap_box[2], it.fp_fix - mo) : 0;
@@ -718,10 +825,14 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
     tl.rmask = rmask; tl.all_valid = all_valid;
     const int philox = (it.flags & ADELL_F_PHILOX) ? 1 : 0;
     f.gb = make_float4(c.pre_s * it.post_scale, fmaf(c.pre_o, it.post_scale, it.post_offset), it.post_offset, it.noise_std);
-    f.n = make_int4(n0, n1, n2, it.tile_dim[2]);
+    f.n = make_int4(it.tile_dim[0], it.tile_dim[1], n2, it.tile_dim[2]);
+    f.lim = make_int4(-o00, it.out_shape[0] - o00, -o01, it.out_shape[1] - o01);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) f.eg[g][3] = __int_as_float(shv[g]);
     const uint32_t p0 = static_cast<uint32_t>(it.tmap_box[1] * it.tmap_box[2]), p1 = static_cast<uint32_t>(it.tmap_box[2]);
     f.m = make_int4(static_cast<int>(p0), static_cast<int>(p1), rmask | (it.padding << 8),
                     static_cast<int>(box_addr - 4u * (K1_MAGIC_BITS * (p0 + p1 + 1u))));
+    f.rb = make_float4(rB0, rB1, rB2, 0.0f);
     f.fl = make_int4((padded || it.noise != nullptr || philox) ? 1 : 0, padded ? 1 : 0, philox, 0);
     f.vlo = make_int4(vl0, vl1, vl2, 0);
     f.vhi = make_int4(vh0, vh1, vh2, 0);
@@ -736,11 +847,16 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
 
 #ifdef K1_PROFILE
 __device__ unsigned long long k1_prof[8];
+// cycle counters accumulate in registers and are flushed once per warp (low perturbation)
+#define K1_PROF_DECL long long _acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define K1_PROF_T0 long long _t0 = clock64();
-#define K1_PROF_ADD(i) { long long _t1 = clock64(); if ((threadIdx.x & 31) == 0) atomicAdd(&k1_prof[i], (unsigned long long)(_t1 - _t0)); _t0 = _t1; }
+#define K1_PROF_ADD(i) { long long _t1 = clock64(); _acc[i] += _t1 - _t0; _t0 = _t1; }
+#define K1_PROF_FLUSH if ((threadIdx.x & 31) == 0) { for (int _i = 0; _i < 8; ++_i) if (_acc[_i]) atomicAdd(&k1_prof[_i], (unsigned long long)_acc[_i]); }
 #else
+#define K1_PROF_DECL
 #define K1_PROF_T0
 #define K1_PROF_ADD(i)
+#define K1_PROF_FLUSH
 #endif
 
 // Producer: derive the tile state (and the consumers' register image) in the given slot.  The
@@ -809,13 +925,14 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
 k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile_start, int n_items, int total_tiles,
           int n_stages, int stage_bytes, int chunk) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int n_slots = n_stages + 1;
+  const int n_slots = n_stages + K1_NPROD;
   K1Slot* slots = reinterpret_cast<K1Slot*>(smem + static_cast<size_t>(n_stages) * stage_bytes);
-  K1Ctx* priv = reinterpret_cast<K1Ctx*>(slots + n_slots);   // the producer's private item copy
-  uint64_t* full = reinterpret_cast<uint64_t*>(priv + 1);
+  K1Ctx* priv = reinterpret_cast<K1Ctx*>(slots + n_slots);   // the producers' private item copies
+  uint64_t* full = reinterpret_cast<uint64_t*>(priv + K1_NPROD);
   uint64_t* empty = full + n_stages;
   uint64_t* landed = empty + n_stages;   // TMA completion of tiles that need the column fix-up first
-  int32_t* ts_s = reinterpret_cast<int32_t*>(landed + n_stages);
+  uint64_t* turn = landed + n_stages;    // producers issue in tile order: turn[p] = "warp p may issue its next tile"
+  int32_t* ts_s = reinterpret_cast<int32_t*>(turn + K1_NPROD);
   const bool ts_cached = n_items + 1 <= K1_TS_CACHE;
   if (ts_cached)
     for (int i = threadIdx.x; i <= n_items; i += K1_THREADS) ts_s[i] = __ldg(tile_start + i);
@@ -823,9 +940,11 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
   if (threadIdx.x == 0) {
     for (int s = 0; s < n_stages; ++s) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(full + s)), "r"(1));
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(empty + s)), "r"(K1_CWARPS));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(empty + s)), "r"(K1_GWARPS));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(landed + s)), "r"(1));
     }
+    for (int q = 0; q < K1_NPROD; ++q)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(turn + q)), "r"(1));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -833,20 +952,30 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
   int stage = 0, phase = 0, slot = 0;
 
   if (threadIdx.x >= K1_CTHREADS + 32) {
-    // ------------------------------------------------------------------ producer warp
+    // ------------------------------------------------------------------ producer warps
+    // Producer p owns the tiles seq = p, p + K1_NPROD, ... of this CTA (seq numbers the CTA's tiles:
+    // chunks of `chunk` consecutive tiles go round-robin over the CTAs, so consecutive tiles share
+    // their item and neighbouring source boxes).  The producers are independent: each tile has its
+    // own ring stage (seq % n_stages) and tile-state slot (seq % n_slots).
+    const int prod = (threadIdx.x - K1_CTHREADS - 32) >> 5;
     int item = 0, cached_item = -1, cur_start = 0;
     int next_start = ts[1];
-    int acq_item = -1;                  // item whose tensor map this CTA acquired last
-    // chunks of `chunk` consecutive tiles go round-robin over the CTAs: consecutive tiles share
-    // their item (one item fetch / tensor-map acquire per chunk) and neighbouring source boxes
-    for (int t0 = blockIdx.x * chunk; t0 < total_tiles; t0 += gridDim.x * chunk)
-    for (int tile = t0; tile < min(t0 + chunk, total_tiles); ++tile) {
+    int acq_item = -1;                  // item whose tensor map this warp acquired last
+    K1_PROF_DECL
+    for (int seq = prod;; seq += K1_NPROD) {
+      const int64_t tile64 = (static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(seq / chunk) * gridDim.x) * chunk + seq % chunk;
+      if (tile64 >= total_tiles) break;
+      const int tile = static_cast<int>(tile64);
+      stage = seq % n_stages; phase = (seq / n_stages) & 1; slot = seq % n_slots;
       K1_PROF_T0
-      // safe to overwrite: the slot's previous tile (k - n_slots) was released before the previous
-      // iteration's issue (tile k-1 waited for the stage of tile k-1-n_stages = k - n_slots)
-      k1_prepare(items, ts, n_items, tile, item, cur_start, next_start, cached_item, *priv, slots[slot],
+      // safe to overwrite: the slot's previous tile (seq - n_slots = seq - K1_NPROD - n_stages) was
+      // released before this warp's previous issue (tile seq - K1_NPROD waited for that very stage)
+      k1_prepare(items, ts, n_items, tile, item, cur_start, next_start, cached_item, priv[prod], slots[slot],
                  smem_u32(smem + static_cast<size_t>(stage) * stage_bytes), lane);
       K1_PROF_ADD(2)
+      // issue strictly in tile order (preparation above overlaps freely): a stage's empty barrier has
+      // only two phases, so a warp must not wait for a release more than one use ahead of the others
+      if (K1_NPROD > 1 && seq > 0) mbar_wait_relaxed(turn + prod, ((seq - 1) / K1_NPROD) & 1);
       mbar_wait_relaxed(empty + stage, phase ^ 1);
       K1_PROF_ADD(0)
       if (lane == 0) {
@@ -860,12 +989,12 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
         } else {
           mbar_arrive(landed + stage);
         }
+        if (K1_NPROD > 1) mbar_arrive(turn + (prod + 1) % K1_NPROD);
       }
       __syncwarp();
       K1_PROF_ADD(1)
-      if (++stage == n_stages) { stage = 0; phase ^= 1; }
-      if (++slot == n_slots) slot = 0;
     }
+    K1_PROF_FLUSH
     return;
   }
 
@@ -889,8 +1018,15 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
   }
 
   // -------------------------------------------------------------------- consumer warps
-  for (int t0 = blockIdx.x * chunk; t0 < total_tiles; t0 += gridDim.x * chunk)
-  for (int tile = t0; tile < min(t0 + chunk, total_tiles); ++tile) {
+  // K1_GROUPS groups of K1_GWARPS warps; the CTA's tiles (in the producer's order) go round-robin
+  // over the groups, so several ring stages are being consumed at once and a thread's per-tile
+  // set-up is amortised over more voxels.
+  const int grp = threadIdx.x / K1_GTHREADS;
+  K1_PROF_DECL
+  for (int seq = grp;; seq += K1_GROUPS) {
+    const int64_t tile64 = (static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(seq / chunk) * gridDim.x) * chunk + seq % chunk;
+    if (tile64 >= total_tiles) break;
+    stage = seq % n_stages; phase = (seq / n_stages) & 1; slot = seq % n_slots;
     K1_PROF_T0
     mbar_wait(full + stage, phase);
     K1_PROF_ADD(3)
@@ -909,12 +1045,18 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
       const K1Fast& f = slots[slot].fast;
       if (exact) k1_tile_exact_dispatch<SmemTaps, false>(ctx, tl, box);
       else if (f.fl.x) k1_tile_staged_cold(ctx, tl, f, box);
-      else if (it.interp == ADELL_NEAREST) {
-        if (tl.rmask) k1_tile_staged_nearest<true>(ctx, tl, f, box);
-        else k1_tile_staged_nearest<false>(ctx, tl, f, box);
-      } else {
-        if (tl.rmask) k1_tile_staged_trilinear<K1_NV, true>(f);
-        else k1_tile_staged_trilinear<K1_NV, false>(f);
+      else {
+        // block-uniform variant: 0 = no padding arithmetic, 1 = reflection on the thin axis only, 2 = general
+        const int rm = tl.rmask == 0 ? 0 : ((tl.rmask == 4 && it.padding == ADELL_PAD_REFLECTION) ? 1 : 2);
+        if (it.interp == ADELL_NEAREST) {
+          if (rm == 0) k1_tile_staged_nearest<0>(ctx, tl, f, box);
+          else if (rm == 1) k1_tile_staged_nearest<1>(ctx, tl, f, box);
+          else k1_tile_staged_nearest<2>(ctx, tl, f, box);
+        } else {
+          if (rm == 0) k1_tile_staged_trilinear<K1_NV, 0>(f);
+          else if (rm == 1) k1_tile_staged_trilinear<K1_NV, 1>(f);
+          else k1_tile_staged_trilinear<K1_NV, 2>(f);
+        }
       }
     } else if (it.flags & ADELL_F_IDENTITY) {
       k1_tile_exact_dispatch<GlobalTaps, true>(ctx, tl, nullptr);
@@ -922,11 +1064,22 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
       k1_tile_exact_dispatch<GlobalTaps, false>(ctx, tl, nullptr);
     }
     __syncwarp();
-    K1_PROF_ADD(4)
+#ifdef K1_PROFILE
+    { long long _t1 = clock64(); _acc[mode == MODE_DIRECT ? 5 : 4] += _t1 - _t0; if (threadIdx.x % K1_GTHREADS == 0) _acc[7] += 1; }
+#endif
     if (lane == 0) mbar_arrive(empty + stage);
-    if (++stage == n_stages) { stage = 0; phase ^= 1; }
-    if (++slot == n_slots) slot = 0;
   }
+  K1_PROF_FLUSH
+}
+
+// Shared-memory plan of the persistent CTA: ring stages (box + tile state + 3 mbarriers each) next to
+// the fixed part (extra tile-state slots and item copies of the producers, barriers, tile prefix).
+int k1_smem_fixed() { return K1_NPROD * static_cast<int>(sizeof(K1Slot) + sizeof(K1Ctx) + 8) + 64 + K1_TS_CACHE * 4; }
+int k1_smem_per_stage(int stage_bytes) { return stage_bytes + static_cast<int>(sizeof(K1Slot)) + 24; }
+// largest box that still leaves room for three ring stages
+int k1_pref_box_bytes() {
+  const int b = ((K1_SMEM_BUDGET - k1_smem_fixed()) / 3 - static_cast<int>(sizeof(K1Slot)) - 24) & ~127;
+  return b < K1_MAX_BOX_BYTES ? b : K1_MAX_BOX_BYTES;
 }
 
 int k1_validate(const adell_item& it) {
@@ -989,71 +1142,154 @@ void k1_item_map(adell_item& it) {
   }
 }
 
-// Footprint box of one T-shaped output tile; returns its bytes (0: not stageable).
-int64_t k1_box_for_tile(const adell_item& it, const int* T, int* box) {
+// Column-group shear of the tile grid.  A tile spans 16 or 32 voxels of axis 2 (the lanes); under a
+// rotation that couples axis 2 into source axes 0/1 (a thin volume tilted about an in-plane axis)
+// the footprint of such a column is slanted and its bounding box mostly empty.  Shifting the
+// tile's (axis 0, axis 1) window per group of 8 voxels along axis 2 (8 fp32 = one 32-byte sector:
+// row stores stay sector-complete) straightens the footprint: the shifts s(G) solve
+//   [D00 D01; D10 D11] s = (D02, D12) * 8G   (rounded to integers, made non-negative).
+// Any integer shifts give a valid partition of the output (each column group is tiled by its own
+// shifted grid).  Returns true when a non-trivial shear was written to it.shear.
+bool k1_item_shear(adell_item& it) {
+  memset(it.shear, 0, sizeof(it.shear));
+  const char* e = getenv("ADELL_K1_NO_SHEAR");  // tuning / debugging aid
+  if (e != nullptr && e[0] == '1') return false;
+  const int nG = (it.out_shape[2] + 7) >> 3;
+  if (nG < 2 || nG > 16) return false;
+  const double* D = it.fp_D;
+  const double det = D[0] * D[4] - D[1] * D[3];
+  if (!(fabs(det) > 0.25)) return false;
+  const double a0 = (D[4] * D[2] - D[1] * D[5]) / det * 8.0;
+  const double a1 = (-D[3] * D[2] + D[0] * D[5]) / det * 8.0;
+  long s[2][16], mn[2] = {0, 0}, mx[2] = {0, 0};
+  for (int G = 0; G < nG; ++G) {
+    s[0][G] = lrint(a0 * G);
+    s[1][G] = lrint(a1 * G);
+    for (int b = 0; b < 2; ++b) {
+      if (s[b][G] < mn[b]) mn[b] = s[b][G];
+      if (s[b][G] > mx[b]) mx[b] = s[b][G];
+    }
+  }
+  if (mx[0] - mn[0] > 127 || mx[1] - mn[1] > 127) return false;
+  if (mx[0] == mn[0] && mx[1] == mn[1]) return false;
+  for (int G = 0; G < nG; ++G)
+    for (int b = 0; b < 2; ++b) it.shear[b][G] = static_cast<int8_t>(s[b][G] - mn[b]);
+  return true;
+}
+
+int k1_max_shear(const adell_item& it, int b) {
+  int m = 0;
+  for (int G = 0; G < 16; ++G) if (it.shear[b][G] > m) m = it.shear[b][G];
+  return m;
+}
+
+// Extent along source axis a of the group terms e_a(G) = D_a2*8g - D_a0*s0(G) - D_a1*s1(G) over the
+// column groups g of one tile (g = G - first group of the tile), maximised over the tile rows.
+double k1_group_range(const adell_item& it, int a, int T2) {
+  const int nG = (it.out_shape[2] + 7) >> 3, ng = T2 >> 3;
+  double range = 0.0;
+  for (int G0 = 0; G0 < nG; G0 += (ng > 0 ? ng : 1)) {
+    double lo = 0.0, hi = 0.0;
+    for (int g = 0; g < ng && G0 + g < nG; ++g) {
+      const int G = (G0 + g) & 15;
+      const double ev = it.fp_D[3 * a + 2] * 8.0 * g - it.fp_D[3 * a + 0] * it.shear[0][G] - it.fp_D[3 * a + 1] * it.shear[1][G];
+      if (g == 0 || ev < lo) lo = ev;
+      if (g == 0 || ev > hi) hi = ev;
+    }
+    if (hi - lo > range) range = hi - lo;
+  }
+  return range;
+}
+
+// Extent of the tile along output axis b that the footprint has to cover.
+int k1_tile_extent(const adell_item& it, const int* T, int b, bool sheared) {
+  if (b == 2) return it.out_shape[2] < 8 ? it.out_shape[2] : 8;  // one column group (staged tiles span 16 or 32)
+  if (sheared) return T[b];  // a shifted window can hold a full tile even where out_shape < T
+  return it.out_shape[b] < T[b] ? it.out_shape[b] : T[b];
+}
+
+// Footprint box of one T-shaped output tile; returns its bytes (0: not stageable).  Needs
+// tmap_sign / tmap_off (k1_tmap_layout).
+int64_t k1_box_for_tile(const adell_item& it, const int* T, int* box, bool sheared) {
   int64_t cells = 1;
   for (int a = 0; a < 3; ++a) {
-    double span = 0.0;
-    for (int b = 0; b < 3; ++b) {
-      const int tb = it.out_shape[b] < T[b] ? it.out_shape[b] : T[b];
-      span += fabs(it.fp_D[3 * a + b]) * (tb - 1);
-    }
+    double span = k1_group_range(it, a, T[2]);
+    for (int b = 0; b < 3; ++b) span += fabs(it.fp_D[3 * a + b]) * (k1_tile_extent(it, T, b, sheared) - 1);
     if (!(span < 4096.0)) return 0;
     box[a] = static_cast<int>(floor(span + 2 * K1_EPS)) + 3;
+    bool whole = false;
     if (it.padding != ADELL_PAD_ZEROS) {
-      // border / reflection fold the footprint back into [0,S): one spare cell for the hi tap, and a
-      // thin axis is simply staged whole so that multiply-reflected tiles stay on this path
-      box[a] += 1;
-      if (it.src_shape[a] <= 64 && box[a] < it.src_shape[a] + 1) box[a] = it.src_shape[a] + 1;
+      // border / reflection fold the coordinates back into [0, S-1) (the fast path clamps just below
+      // S-1, so the hi tap never leaves the volume), and a thin axis is simply staged whole so that
+      // multiply-reflected tiles stay on this path
+      if (it.src_shape[a] <= 64 || box[a] >= it.src_shape[a]) { box[a] = it.src_shape[a] > 1 ? it.src_shape[a] : 2; whole = true; }
     }
-    if (a == 2) box[a] = (box[a] + 3 + 3) & ~3;  // inner extent: 16-byte multiple + slack to align the origin
+    if (a == 2) {
+      // inner extent: a 16-byte multiple, plus the cells lost to aligning the box origin down to 16 bytes
+      // (known exactly when the axis is staged whole)
+      int lead = 3;
+      if (whole) {
+        const int mo = it.tmap_sign[2] > 0 ? it.tmap_off[2] : -(it.src_shape[2] - 1) + it.tmap_off[2];
+        lead = mo & 3;
+      }
+      box[a] = (box[a] + lead + 3) & ~3;
+    }
     if (box[a] > 256) return 0;
     cells *= box[a];
   }
   return cells * 4;
 }
 
-// Encodes the tensor map of the item's valid source box (memory order) for a staged box of the
-// given extents (axes 0,1,2).  Returns 1, 0 (layout not expressible) or -1 (no driver).
-int k1_encode_tmap(adell_item& it, const int* box, EncodeTiledFn enc) {
-  it.flags &= static_cast<uint8_t>(~ADELL_F_TMAP);
-  // valid source box in t-space and its origin in memory order
+// Memory-order layout of the item's valid source box: fills tmap_sign / tmap_off / fp_fix and the
+// tensor-map geometry.  Returns false when the layout cannot be expressed as a tensor map.
+struct K1Layout {
   cuuint64_t gdim[3], gstride[2];
+  uintptr_t base;
+};
+bool k1_tmap_layout(adell_item& it, K1Layout& L) {
   int64_t base_off = 0;
   int64_t astride[3];
   for (int a = 0; a < 3; ++a) {
     const int tlo = it.src_vlo[a] > 0 ? it.src_vlo[a] : 0;
     const int thi = it.src_vhi[a] < it.src_shape[a] ? it.src_vhi[a] : it.src_shape[a];
-    if (thi <= tlo) return 0;
+    if (thi <= tlo) return false;
     const int sign = it.src_stride[a] >= 0 ? 1 : -1;
     astride[a] = it.src_stride[a] * sign;
-    if (astride[a] == 0) return 0;
+    if (astride[a] == 0) return false;
     it.tmap_sign[a] = sign;
     it.tmap_off[a] = sign > 0 ? -tlo : thi - 1;           // m = sign*t + off, m = 0 at the lowest address
     base_off += static_cast<int64_t>(sign > 0 ? tlo : thi - 1) * it.src_stride[a];
-    gdim[2 - a] = static_cast<cuuint64_t>(thi - tlo);     // tensor-map dims are innermost first
-    it.tmap_box[a] = box[a];
+    L.gdim[2 - a] = static_cast<cuuint64_t>(thi - tlo);   // tensor-map dims are innermost first
   }
   uintptr_t base = reinterpret_cast<uintptr_t>(it.src) + static_cast<uintptr_t>(base_off * 4);
-  gstride[0] = static_cast<cuuint64_t>(astride[1]) * 4;
-  gstride[1] = static_cast<cuuint64_t>(astride[0]) * 4;
-  if ((base & 3u) || (gstride[0] & 15u) || (gstride[1] & 15u)) return 0;
-  if (gstride[0] < gdim[0] * 4 || gstride[1] < gstride[0]) return 0;  // rows must not overlap
+  L.gstride[0] = static_cast<cuuint64_t>(astride[1]) * 4;
+  L.gstride[1] = static_cast<cuuint64_t>(astride[0]) * 4;
+  if ((base & 3u) || (L.gstride[0] & 15u) || (L.gstride[1] & 15u)) return false;
+  if (L.gstride[0] < L.gdim[0] * 4 || L.gstride[1] < L.gstride[0]) return false;  // rows must not overlap
   // a crop window may start anywhere in a row: align the tensor-map base down to 16 bytes; the
   // 1..3 elements this prepends to every row are zeroed in shared memory after each load (fp_fix)
   const int slack = static_cast<int>((base & 15u) >> 2);
   base -= static_cast<uintptr_t>(slack) * 4;
-  gdim[0] += static_cast<cuuint64_t>(slack);
+  L.gdim[0] += static_cast<cuuint64_t>(slack);
   it.tmap_off[2] += slack;
   it.fp_fix = slack;
+  L.base = base;
+  return true;
+}
+
+// Encodes the tensor map for a staged box of the given extents (axes 0,1,2).  Returns 1, 0 (the
+// driver refused the layout) or -1 (no driver).
+int k1_encode_tmap(adell_item& it, const K1Layout& L, const int* box, EncodeTiledFn enc) {
+  it.flags &= static_cast<uint8_t>(~ADELL_F_TMAP);
+  for (int a = 0; a < 3; ++a) it.tmap_box[a] = box[a];
   const cuuint32_t bdim[3] = {static_cast<cuuint32_t>(box[2]), static_cast<cuuint32_t>(box[1]), static_cast<cuuint32_t>(box[0])};
   const cuuint32_t estr[3] = {1, 1, 1};
   if (enc == nullptr) return -1;
   CUresult r = enc(reinterpret_cast<CUtensorMap*>(it.tmap), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
-                   reinterpret_cast<void*>(base), gdim, gstride, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   reinterpret_cast<void*>(L.base), L.gdim, L.gstride, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, K1_L2_PROMO, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return 0;
-  it.tmap_base = reinterpret_cast<const void*>(base);
+  it.tmap_base = reinterpret_cast<const void*>(L.base);
   it.flags |= ADELL_F_TMAP;
   return 1;
 }
@@ -1064,7 +1300,9 @@ int k1_encode_copy(adell_item& it, EncodeTiledFn enc) {
   int T[3] = {32, 16, 32};
   if (const char* e = getenv("ADELL_K1_COPY_T0")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32) T[0] = v; }  // tuning aid
   int box[3] = {T[0], T[1], T[2]};
-  int r = k1_encode_tmap(it, box, enc);
+  K1Layout L;
+  if (!k1_tmap_layout(it, L)) return 0;
+  int r = k1_encode_tmap(it, L, box, enc);
   if (r <= 0) return r;
   // tensor coordinate of the first tile's lowest element along axis 2: if it is not a multiple of
   // four the box origin is rounded down per tile and the box needs four more columns
@@ -1073,7 +1311,7 @@ int k1_encode_copy(adell_item& it, EncodeTiledFn enc) {
   const int lo = it.tmap_sign[2] > 0 ? (g0 < g1 ? g0 : g1) + it.tmap_off[2] : -(g0 > g1 ? g0 : g1) + it.tmap_off[2];
   if (lo & 3) {
     box[2] += 4;
-    r = k1_encode_tmap(it, box, enc);
+    r = k1_encode_tmap(it, L, box, enc);
     if (r <= 0) return r;
   }
   for (int a = 0; a < 3; ++a) it.tile_dim[a] = static_cast<uint8_t>(T[a]);
@@ -1090,35 +1328,53 @@ int k1_encode_item(adell_item& it, EncodeTiledFn enc, int tile_pref) {
   if (it.src_dtype != ADELL_F32) return 0;
   if (it.src_stride[2] != 1 && it.src_stride[2] != -1) return 0;
   k1_item_map(it);
-  // tile shapes: among those whose box fits (a larger shape only if it leaves room for three ring
-  // stages, the base shape up to the two-stage limit) take the one that pads the output least;
-  // ties go to the shape listed first (32 lanes along the contiguous axis = 128-byte row stores)
-  static const int kShapes[3][3] = {{16, 16, 32}, {16, 32, 16}, {16, 16, 16}};
+  const bool sheared = k1_item_shear(it);
+  const int smx[2] = {k1_max_shear(it, 0), k1_max_shear(it, 1)};
+  K1Layout L;
+  if (!k1_tmap_layout(it, L)) { memset(it.shear, 0, sizeof(it.shear)); return 0; }
+  // tile shapes: among those whose box leaves room for three ring stages (two consumer groups at
+  // work + one load in flight) take the cheapest one: voxels of all its tiles, padding included (idle
+  // lanes cost as much as busy ones), plus a fixed cost per tile (producer set-up, consumer prologue:
+  // worth ~3000 voxels, measured); ties go to the shape listed first.  Only when none fits, the same
+  // choice among the boxes that fit twice.
+  static const int kShapes[4][3] = {{16, 16, 32}, {16, 32, 16}, {8, 16, 32}, {16, 16, 16}};
+  int pref_bytes = k1_pref_box_bytes();
+  if (const char* pe = getenv("ADELL_K1_PREF_BOX")) { const int v = atoi(pe); if (v >= 1024 && v <= K1_MAX_BOX_BYTES) pref_bytes = v; }
   int box[3] = {0, 0, 0}, T[3] = {16, 16, 16};
-  int64_t bytes = 0, best_cover = -1;
-  for (int s = 0; s < 3; ++s) {
-    if (tile_pref >= 0 && s != 2 && s != tile_pref) continue;
-    if (s == 0 && it.out_shape[2] <= 16) continue;
-    if (s == 1 && it.out_shape[1] <= 16) continue;
-    int bx[3];
-    const int64_t b = k1_box_for_tile(it, kShapes[s], bx);
-    if (b == 0 || b > (s == 2 ? K1_MAX_BOX_BYTES : K1_PREF_BOX_BYTES)) continue;
-    int64_t cover = 1;  // voxels of all tiles, padding included
-    for (int a = 0; a < 3; ++a) cover *= static_cast<int64_t>((it.out_shape[a] + kShapes[s][a] - 1) / kShapes[s][a]) * kShapes[s][a];
-    if (best_cover >= 0 && (tile_pref >= 0 || cover >= best_cover)) continue;
-    best_cover = cover;
-    bytes = b;
-    for (int a = 0; a < 3; ++a) { box[a] = bx[a]; T[a] = kShapes[s][a]; }
+  int64_t bytes = 0;
+  int64_t tile_cost = 3072;
+  if (const char* ce = getenv("ADELL_K1_TILE_COST")) { const int v = atoi(ce); if (v >= 0) tile_cost = v; }  // tuning aid
+  for (int pass = 0; pass < 2 && bytes == 0; ++pass) {
+    const int limit = pass == 0 ? pref_bytes : K1_MAX_BOX_BYTES;
+    int64_t best_cover = -1;
+    for (int s = 0; s < 4; ++s) {
+      if (tile_pref >= 0 && s != tile_pref) continue;
+      if ((s == 0 || s == 2) && it.out_shape[2] <= 16) continue;
+      if (s == 1 && it.out_shape[1] <= 16) continue;
+      int bx[3];
+      const int64_t b = k1_box_for_tile(it, kShapes[s], bx, sheared);
+      if (b == 0 || b > limit) continue;
+      int64_t cover = 1, tiles = 1;
+      for (int a = 0; a < 3; ++a) {
+        const int64_t nt = (it.out_shape[a] + (a < 2 ? smx[a] : 0) + kShapes[s][a] - 1) / kShapes[s][a];
+        tiles *= nt;
+        cover *= nt * kShapes[s][a];
+      }
+      cover += tiles * tile_cost;
+      if (best_cover >= 0 && cover >= best_cover) continue;
+      best_cover = cover;
+      bytes = b;
+      for (int a = 0; a < 3; ++a) { box[a] = bx[a]; T[a] = kShapes[s][a]; }
+    }
   }
-  if (bytes == 0) return 0;
-  const int r = k1_encode_tmap(it, box, enc);
-  if (r <= 0) return r;
+  if (bytes == 0) { memset(it.shear, 0, sizeof(it.shear)); return 0; }
+  const int r = k1_encode_tmap(it, L, box, enc);
+  if (r <= 0) { memset(it.shear, 0, sizeof(it.shear)); return r; }
   for (int a = 0; a < 3; ++a) {
     it.tile_dim[a] = static_cast<uint8_t>(T[a]);
-    double smin = 0.0, smax = 0.0;
+    double smin = 0.0, smax = 0.0;  // footprint of one 8-voxel column group of a tile (di, dj, kk in [0,8))
     for (int b = 0; b < 3; ++b) {
-      const int tb = it.out_shape[b] < T[b] ? it.out_shape[b] : T[b];
-      const double span = it.fp_D[3 * a + b] * (tb - 1);
+      const double span = it.fp_D[3 * a + b] * (k1_tile_extent(it, T, b, sheared) - 1);
       if (span < 0) smin += span; else smax += span;
     }
     // rounded outwards so the fp32 copies never under-estimate the footprint
@@ -1139,8 +1395,8 @@ extern "C" int adell_aug_prepare(adell_item* items_host, int n_items, int32_t* t
   bool enc_tried = false;
   const char* dis = getenv("ADELL_DISABLE_STAGED");  // debugging aid: force the direct path
   const bool no_staged = dis != nullptr && dis[0] == '1';
-  const char* tp = getenv("ADELL_K1_TILE");          // tuning aid: 0 = 16x16x32, 1 = 16x32x16, 2 = 16x16x16 only
-  const int tile_pref = (tp != nullptr && tp[0] >= '0' && tp[0] <= '2') ? tp[0] - '0' : -1;
+  const char* tp = getenv("ADELL_K1_TILE");          // tuning aid: 0 = 16x16x32, 1 = 16x32x16, 2 = 8x16x32, 3 = 16x16x16 only
+  const int tile_pref = (tp != nullptr && tp[0] >= '0' && tp[0] <= '3') ? tp[0] - '0' : -1;
   for (int i = 0; i < n_items; ++i) {
     adell_item& it = items_host[i];
     int st = k1_validate(it);
@@ -1149,11 +1405,13 @@ extern "C" int adell_aug_prepare(adell_item* items_host, int n_items, int32_t* t
     it.kind = ADELL_KIND_GENERIC;
     it.tile_dim[0] = it.tile_dim[1] = it.tile_dim[2] = K1_T;
     it.fp_fix = 0;
+    memset(it.shear, 0, sizeof(it.shear));
     int bytes = 0;
     it.flags &= static_cast<uint8_t>(~ADELL_F_TMAP);
     if (!no_staged) {
       bytes = (it.flags & ADELL_F_IDENTITY) ? k1_encode_copy(it, enc) : k1_encode_item(it, enc, tile_pref);
       if (bytes == 0) {  // not staged after all: generic 16^3 tiles
+        memset(it.shear, 0, sizeof(it.shear));
         it.flags &= static_cast<uint8_t>(~ADELL_F_TMAP);
         it.kind = ADELL_KIND_GENERIC;
         it.tile_dim[0] = it.tile_dim[1] = it.tile_dim[2] = K1_T;
@@ -1164,7 +1422,8 @@ extern "C" int adell_aug_prepare(adell_item* items_host, int n_items, int32_t* t
     if (bytes > 0) { ++staged; if (bytes > smem) smem = bytes; }
     int64_t n = 1;
     for (int a = 0; a < 3; ++a) {
-      it.n_tiles[a] = (it.out_shape[a] + it.tile_dim[a] - 1) / it.tile_dim[a];
+      const int ext = it.out_shape[a] + ((a < 2 && it.kind == ADELL_KIND_STAGED) ? k1_max_shear(it, a) : 0);
+      it.n_tiles[a] = (ext + it.tile_dim[a] - 1) / it.tile_dim[a];
       n *= it.n_tiles[a];
     }
     tile_start_host[i] = static_cast<int32_t>(acc);
@@ -1206,8 +1465,8 @@ extern "C" int adell_aug_gather(const adell_item* items_dev, const int32_t* tile
   if (e != cudaSuccess) { (void)cudaGetLastError(); return adell_map_cuda_error(e); }
   // ring of staged boxes: as many stages as fit next to the per-stage tile state
   const int stage_bytes = (info->smem_bytes + 127) & ~127;
-  const int per_stage = stage_bytes + static_cast<int>(sizeof(K1Slot)) + 24;  // box + tile state + 3 mbarriers
-  const int fixed = static_cast<int>(sizeof(K1Slot) + sizeof(K1Ctx)) + 64 + K1_TS_CACHE * 4;
+  const int per_stage = k1_smem_per_stage(stage_bytes);
+  const int fixed = k1_smem_fixed();
   int n_stages = (K1_SMEM_BUDGET - fixed) / per_stage;
   if (n_stages > K1_MAX_STAGES) n_stages = K1_MAX_STAGES;
   if (n_stages < 1) return ADELL_ERR_BAD_ARG;

@@ -125,7 +125,7 @@ typedef struct __attribute__((aligned(64))) adell_item {
   /* ---- derived by adell_aug_prepare; callers leave these zero ------------------------------ */
   uint8_t tile_dim[3];     /* output tile extents of this item along axes 0,1,2                     */
   uint8_t kind;            /* ADELL_KIND_*: which K1 path the item's tiles take                     */
-  int32_t n_tiles[3];      /* ceil(out_shape / tile_dim)                                            */
+  int32_t n_tiles[3];      /* ceil((out_shape + max shear) / tile_dim)                              */
   float fp_smin[3];        /* staged path: footprint of a full tile relative to its origin voxel,   */
   float fp_smax[3];        /*   per source axis (sum of negative / positive D*(tile_dim-1) terms)    */
   int32_t fp_fix;          /* staged path: leading columns (axis 2, box order) of the tensor map
@@ -133,7 +133,12 @@ typedef struct __attribute__((aligned(64))) adell_item {
                               are zeroed in shared memory after the TMA load                         */
   double fp_U0[3];         /* un-padded source coordinate of output voxel (0,0,0), fp64             */
   double fp_D[9];          /* d(source coordinate a)/d(output index b), row-major [a][b], fp64      */
-  uint8_t reserved[32];    /* pads the struct to 640 bytes */
+  int8_t shear[2][16];     /* staged path: per 8-voxel column group G = o_2 >> 3 along axis 2, the shift
+                              (>= 0) of the output tile grid along axes 0 and 1: voxel o belongs to
+                              tile ((o_0 + shear[0][G]) / tile_dim[0], (o_1 + shear[1][G]) / tile_dim[1],
+                              o_2 / tile_dim[2]).  Chosen so that a column tile's source footprint
+                              stays compact under rotations that couple axis 2 into axes 0/1; all
+                              zero = plain tile grid.  (Completes the struct to 640 bytes.)          */
 } adell_item;
 
 /* adell_item.kind */

@@ -109,7 +109,29 @@ def pack(plan, dsts):
     dst_stride = np.array([d.stride() for d in dsts], np.int64)
     items = plan.build_launches(dst_ptr, dst_stride, None)[-1]
     buf, n, info = engine.pack_launch(items)
+    it = buf[: n * engine.ISZ].view(engine.ITEM_DTYPE)
+    STATS.append((it["tile_dim"].copy(), it["tmap_box"].copy(), it["n_tiles"].copy(), it["kind"].copy(), it["out_shape"].copy()))
     return torch.from_numpy(buf).to(dev), n, info, plan
+
+
+STATS = []
+
+
+def tile_stats():
+    """Host policy summary of the packed launches: tile shapes, staged bytes per output voxel."""
+    td = np.concatenate([s[0] for s in STATS]); box = np.concatenate([s[1] for s in STATS]).astype(np.int64)
+    nt = np.concatenate([s[2] for s in STATS]).astype(np.int64); kind = np.concatenate([s[3] for s in STATS])
+    osh = np.concatenate([s[4] for s in STATS]).astype(np.int64)
+    out = []
+    for k in np.unique(kind):
+        for shp in np.unique(td[kind == k], axis=0):
+            sel = (kind == k) & (td == shp).all(axis=1)
+            tiles = nt[sel].prod(axis=1).sum()
+            bb = (box[sel].prod(axis=1) * 4 * nt[sel].prod(axis=1)).sum()
+            out.append(f"kind {k} tile {tuple(int(x) for x in shp)}: {int(sel.sum())} items, {int(tiles)} tiles, mean box {bb / max(tiles, 1) / 1024:.1f} KiB, "
+                       f"{bb / osh[sel].prod(axis=1).sum():.1f} staged B/voxel")
+    STATS.clear()
+    return "; ".join(out)
 
 
 def time_launches(launches, reps=5):
@@ -146,6 +168,7 @@ def main():
             L, vox, keep = cls_items(R)
         else:
             raise SystemExit(name)
+        print("  ", tile_stats())
         if PROF:
             out = (ctypes.c_ulonglong * 8)()
             lib.adell_debug_prof(out, 1)
@@ -158,6 +181,9 @@ def main():
             lib.adell_debug_prof(out, 1)
             v = list(out)
             print("   cycles summed over warps: prod wait-empty %d, issue %d, prepare %d | cons wait-full %d, compute %d" % tuple(v[:5]))
+            nt = max(v[7], 1)
+            print("   per tile: producer prepare %.0f, wait-empty %.0f, issue %.0f cycles | per consumer warp: wait-full %.0f, compute %.0f (DIRECT %.0f) cycles; %d tiles"
+                  % (v[2] / nt, v[0] / nt, v[1] / nt, v[3] / nt / 8, v[4] / nt / 8, v[5] / nt / 8, nt))
         del L, keep
         torch.cuda.empty_cache()
 
