@@ -527,7 +527,7 @@ __device__ __forceinline__ void k1_tile_staged_nearest(const K1Ctx& c, const K1T
   if (!k1_lane_map(f, m)) return;
   K1Hot<RMASK> h;
   k1_hot_load<RMASK>(h, f);
-  const float tie = 0.5f - static_cast<float>(K1_EPS);
+  const float tie = f.rb.w;
   const int64_t ds1 = f.ds1;
   const int64_t pstep = m.jstep * ds1;
   const int T0 = f.n.x;
@@ -545,8 +545,8 @@ __device__ __forceinline__ void k1_tile_staged_nearest(const K1Ctx& c, const K1T
       const float t0 = __fadd_rn(v0, K1_MAGIC), t1 = __fadd_rn(v1, K1_MAGIC), t2 = __fadd_rn(v2, K1_MAGIC);
       const float n0 = t0 - K1_MAGIC, n1 = t1 - K1_MAGIC, n2 = t2 - K1_MAGIC;
       float val;
-      if (fabsf(v0 - n0) > tie || fabsf(v1 - n1) > tie || fabsf(v2 - n2) > tie) {
-        val = k1_exact_nearest_smem(c, tl, box, m.ii, dj - m.s1, m.dk);  // within 1e-3 of a rounding tie
+      if (fmaxf(fmaxf(fabsf(v0 - n0), fabsf(v1 - n1)), fabsf(v2 - n2)) > tie) {
+        val = k1_exact_nearest_smem(c, tl, box, m.ii, dj - m.s1, m.dk);  // inside the tie window of a rounding tie
       } else {
         const uint32_t a = h.cbase + 4u * (__float_as_uint(t0) * h.p0 + __float_as_uint(t1) * h.p1 + __float_as_uint(t2));
         val = fmaf(lds_f32(a), h.gain, h.bias);
@@ -566,7 +566,7 @@ __device__ __noinline__ void k1_tile_staged_cold(const K1Ctx& c, const K1Tile& t
   K1Hot<2> h;
   k1_hot_load<2>(h, f);
   const bool nearest = c.it.interp == ADELL_NEAREST;
-  const float tie = 0.5f - static_cast<float>(K1_EPS);
+  const float tie = f.rb.w;
   const uint32_t o1 = 4u * h.p1, o0 = 4u * h.p0;
   const int4 vlo = f.vlo, vhi = f.vhi, fl = f.fl;
   const float4 gb = f.gb;
@@ -804,6 +804,11 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
   const bool padded = __any_sync(FULL, ax && padded_a);
   const int n0 = __shfl_sync(FULL, na, 0), n1 = __shfl_sync(FULL, na, 1), n2 = __shfl_sync(FULL, na, 2);
   const float rB0 = __shfl_sync(FULL, rB, 0), rB1 = __shfl_sync(FULL, rB, 1), rB2 = __shfl_sync(FULL, rB, 2);
+  // tie window of the nearest fast path: grows with the magnitude of the tile's (un-padded) coordinates,
+  // where the reference's own fp32 chain is coarser (far translations under border / reflection)
+  const float mag_a = ax ? fmaxf(fabsf(static_cast<float>(umin)), fabsf(static_cast<float>(umax))) : 0.0f;
+  const float mag = fmaxf(fmaxf(__shfl_sync(FULL, mag_a, 0), __shfl_sync(FULL, mag_a, 1)), __shfl_sync(FULL, mag_a, 2));
+  const float tie = fminf(c.tie, 0.5f - 2.0e-6f * mag);
   const int vl0 = __shfl_sync(FULL, vlo, 0), vl1 = __shfl_sync(FULL, vlo, 1), vl2 = __shfl_sync(FULL, vlo, 2);
   const int vh0 = __shfl_sync(FULL, vhi, 0), vh1 = __shfl_sync(FULL, vhi, 1), vh2 = __shfl_sync(FULL, vhi, 2);
   if (ax) {
@@ -832,7 +837,7 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
     const uint32_t p0 = static_cast<uint32_t>(it.tmap_box[1] * it.tmap_box[2]), p1 = static_cast<uint32_t>(it.tmap_box[2]);
     f.m = make_int4(static_cast<int>(p0), static_cast<int>(p1), rmask | (it.padding << 8),
                     static_cast<int>(box_addr - 4u * (K1_MAGIC_BITS * (p0 + p1 + 1u))));
-    f.rb = make_float4(rB0, rB1, rB2, 0.0f);
+    f.rb = make_float4(rB0, rB1, rB2, tie);
     f.fl = make_int4((padded || it.noise != nullptr || philox) ? 1 : 0, padded ? 1 : 0, philox, 0);
     f.vlo = make_int4(vl0, vl1, vl2, 0);
     f.vhi = make_int4(vh0, vh1, vh2, 0);
@@ -916,6 +921,32 @@ __device__ __forceinline__ void k1_fix_columns(float* box, const K1Tile& tl, int
   __syncwarp();
 }
 
+// Position of a warp in the CTA's tile sequence seq = first, first + step, ...: the tile (chunks of
+// `chunk` consecutive tiles go round-robin over the CTAs), its ring stage / phase and tile-state
+// slot — advanced incrementally (no divisions on the per-tile path).
+struct K1Seq {
+  int c, within;      // chunk number of this CTA, position inside the chunk
+  int stage, phase, slot;
+  int round;          // number of advances so far
+  __device__ __forceinline__ void init(int first, int chunk, int n_stages, int n_slots) {
+    c = first / chunk; within = first % chunk;
+    stage = first % n_stages; phase = (first / n_stages) & 1; slot = first % n_slots;
+    round = 0;
+  }
+  __device__ __forceinline__ int64_t tile(int chunk) const {
+    return (static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(c) * gridDim.x) * chunk + within;
+  }
+  __device__ __forceinline__ void advance(int step, int chunk, int n_stages, int n_slots) {
+    within += step;
+    while (within >= chunk) { within -= chunk; ++c; }
+    stage += step;
+    while (stage >= n_stages) { stage -= n_stages; phase ^= 1; }
+    slot += step;
+    while (slot >= n_slots) slot -= n_slots;
+    ++round;
+  }
+};
+
 // Persistent, warp-specialised: one CTA per SM walks tiles blockIdx.x, +gridDim.x, ...  The
 // producer warp prepares tile k+1 (item fetch + set-up) while the TMA box load of tile k is in
 // flight, and issues each load the moment its ring stage is released; the 16 consumer warps
@@ -962,11 +993,13 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
     int next_start = ts[1];
     int acq_item = -1;                  // item whose tensor map this warp acquired last
     K1_PROF_DECL
+    K1Seq sq;
+    sq.init(prod, chunk, n_stages, n_slots);
     for (int seq = prod;; seq += K1_NPROD) {
-      const int64_t tile64 = (static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(seq / chunk) * gridDim.x) * chunk + seq % chunk;
+      const int64_t tile64 = sq.tile(chunk);
       if (tile64 >= total_tiles) break;
       const int tile = static_cast<int>(tile64);
-      stage = seq % n_stages; phase = (seq / n_stages) & 1; slot = seq % n_slots;
+      stage = sq.stage; phase = sq.phase; slot = sq.slot;
       K1_PROF_T0
       // safe to overwrite: the slot's previous tile (seq - n_slots = seq - K1_NPROD - n_stages) was
       // released before this warp's previous issue (tile seq - K1_NPROD waited for that very stage)
@@ -975,7 +1008,7 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
       K1_PROF_ADD(2)
       // issue strictly in tile order (preparation above overlaps freely): a stage's empty barrier has
       // only two phases, so a warp must not wait for a release more than one use ahead of the others
-      if (K1_NPROD > 1 && seq > 0) mbar_wait_relaxed(turn + prod, ((seq - 1) / K1_NPROD) & 1);
+      if (K1_NPROD > 1 && seq > 0) mbar_wait_relaxed(turn + prod, (sq.round - (prod == 0 ? 1 : 0)) & 1);
       mbar_wait_relaxed(empty + stage, phase ^ 1);
       K1_PROF_ADD(0)
       if (lane == 0) {
@@ -993,6 +1026,7 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
       }
       __syncwarp();
       K1_PROF_ADD(1)
+      sq.advance(K1_NPROD, chunk, n_stages, n_slots);
     }
     K1_PROF_FLUSH
     return;
@@ -1023,10 +1057,11 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
   // set-up is amortised over more voxels.
   const int grp = threadIdx.x / K1_GTHREADS;
   K1_PROF_DECL
-  for (int seq = grp;; seq += K1_GROUPS) {
-    const int64_t tile64 = (static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(seq / chunk) * gridDim.x) * chunk + seq % chunk;
-    if (tile64 >= total_tiles) break;
-    stage = seq % n_stages; phase = (seq / n_stages) & 1; slot = seq % n_slots;
+  K1Seq sq;
+  sq.init(grp, chunk, n_stages, n_slots);
+  for (;; sq.advance(K1_GROUPS, chunk, n_stages, n_slots)) {
+    if (sq.tile(chunk) >= total_tiles) break;
+    stage = sq.stage; phase = sq.phase; slot = sq.slot;
     K1_PROF_T0
     mbar_wait(full + stage, phase);
     K1_PROF_ADD(3)

@@ -18,6 +18,7 @@ struct K1Ctx {
   int tlo[3];     // max(0, src_vlo)
   int thi[3];     // min(S, src_vhi)
   float pre_s, pre_o;
+  float tie;      // nearest fast path: |fast coordinate - rint| above this => bit-faithful replay (0.5 - window)
 };
 
 __device__ __forceinline__ void k1_ctx_finish(K1Ctx& c) {
@@ -30,6 +31,15 @@ __device__ __forceinline__ void k1_ctx_finish(K1Ctx& c) {
     c.Sm1[a] = static_cast<float>(c.it.src_shape[a] - 1);
     c.tlo[a] = max(0, c.it.src_vlo[a]);
     c.thi[a] = min(c.it.src_shape[a], c.it.src_vhi[a]);
+  }
+  // The fast (tile-local fp32) coordinate and the reference's own fp32 chain each stay within
+  // ~3e-7 * extent of the real coordinate (a handful of roundings at magnitude <= extent), so they
+  // disagree by <= ~6e-7 * extent; the tie window is 2e-6 * extent, at least 2e-4 voxel.
+  {
+    int ext = 1;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) ext = max(ext, max(c.it.src_shape[a], c.it.grid_shape[a]));
+    c.tie = 0.5f - fmaxf(2.0e-4f, 2.0e-6f * static_cast<float>(ext));
   }
   if (c.it.flags & ADELL_F_PRE_DEV) {
     c.pre_s = c.it.pre_dev[0];
