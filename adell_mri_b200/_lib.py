@@ -122,7 +122,7 @@ _SIGNATURES = {
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 _lib = None
 
 

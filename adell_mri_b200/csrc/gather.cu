@@ -34,16 +34,15 @@ namespace {
 
 constexpr int K1_CWARPS = 16;                  // consumer warps per CTA
 constexpr int K1_CTHREADS = 32 * K1_CWARPS;    // consumer threads
-#ifndef K1_NPROD
-#define K1_NPROD 2                              // producer warps: warp p prepares / issues tiles seq = p (mod K1_NPROD)
-#endif
-constexpr int K1_THREADS = K1_CTHREADS + 32 + 32 * K1_NPROD;   // + one hand-over warp + the producer warps
-#ifndef K1_GROUPS
-#define K1_GROUPS 2                             // consumer groups: each works on its own tile (ring stage)
-#endif
+// The CTA runs K1_GROUPS independent streams: stream p = one producer warp, one hand-over warp and
+// one group of consumer warps, with its own ring stages (p, p + K1_GROUPS, ...) and tile-state slots.
+#define K1_GROUPS 2
+#define K1_NPROD K1_GROUPS
+constexpr int K1_THREADS = K1_CTHREADS + 64 * K1_GROUPS;   // consumers + per stream a hand-over and a producer warp
 constexpr int K1_GWARPS = K1_CWARPS / K1_GROUPS;   // warps per group; a warp takes planes di = w, w + K1_GWARPS, ...
 constexpr int K1_GTHREADS = 32 * K1_GWARPS;
 constexpr int K1_T = 16;                       // base tile edge
+constexpr int K1_COPY_T0 = 16;                 // identity items: 16x16x32 box copies (32 KiB: three ring stages per stream)
 constexpr int K1_MAX_STAGES = 6;
 constexpr int K1_SMEM_BUDGET = 227 * 1024;     // dynamic shared memory per persistent CTA (1 CTA per SM): the sm_100 opt-in maximum
 constexpr int K1_MAX_BOX_BYTES = 100 * 1024;   // staged footprint limit (two stages)
@@ -59,11 +58,14 @@ constexpr uint32_t K1_MAGIC_BITS = 0x4B400000u;
 #endif
 __device__ __forceinline__ void k1_plain_store(float4* p, float4 v) { *p = v; }
 __device__ __forceinline__ void k1_wt_store(float4* p, float4 v) { __stwt(p, v); }
+#ifndef K1_NP
+#define K1_NP 2                                 // trilinear voxel PAIRS (packed fp32) interleaved per consumer-thread iteration
+#endif
 #ifndef K1_NV
 #define K1_NV 4                                 // trilinear voxels interleaved per consumer-thread iteration
 #endif
 
-enum { MODE_DIRECT = 0, MODE_STAGED = 1, MODE_ZERO = 2, MODE_COPY = 3 };
+enum { MODE_DIRECT = 0, MODE_STAGED = 1, MODE_ZERO = 2, MODE_COPY = 3, MODE_DONE = 4 };
 
 struct K1Tile {
   int mode;
@@ -469,7 +471,7 @@ __device__ __forceinline__ float k1_lerp8(const K1Vox& x, const float* t) {
 // asm so ptxas keeps them batched); no per-voxel bounds checks — a thread's voxel count is split
 // into full groups and a one-at-a-time tail.
 template <int NV, int RMASK>
-__device__ __forceinline__ void k1_tile_staged_trilinear(const K1Fast& f) {
+__device__ __forceinline__ void k1_tile_staged_trilinear_scalar(const K1Fast& f) {
   K1Map m;
   if (!k1_lane_map(f, m)) return;
   K1Hot<RMASK> h;
@@ -506,6 +508,131 @@ __device__ __forceinline__ void k1_tile_staged_trilinear(const K1Fast& f) {
       for (int u = 0; u < NV; ++u) p[u * pstep] = fmaf(k1_lerp8(x[u], t[u]), h.gain, h.bias);
       p += NV * pstep;
       fj += static_cast<float>(NV) * fstep;
+    }
+#pragma unroll 1
+    for (; cnt > 0; --cnt) {
+      const K1Vox x = k1_fast_vox<RMASK>(h, fj);
+      float t[8];
+      t[0] = lds_f32(x.a); t[1] = lds_f32(x.a + 4); t[2] = lds_f32(x.a + o1); t[3] = lds_f32(x.a + o1 + 4);
+      t[4] = lds_f32(x.a + o0); t[5] = lds_f32(x.a + o0 + 4); t[6] = lds_f32(x.a + o0 + o1); t[7] = lds_f32(x.a + o0 + o1 + 4);
+      *p = fmaf(k1_lerp8(x, t), h.gain, h.bias);
+      p += pstep;
+      fj += fstep;
+    }
+  }
+}
+
+// ---- packed fp32 (Blackwell FFMA2 / FADD2: two fp32 lanes per instruction in a 64-bit register pair).
+// The trilinear loop is bound by instruction issue, not by the FMA pipe: doing the coordinate, floor /
+// fraction and lerp arithmetic of two voxels per instruction removes about a quarter of its issue slots.
+typedef unsigned long long k1_f2;
+__device__ __forceinline__ k1_f2 f2_pack(float lo, float hi) { k1_f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ k1_f2 f2_dup(float v) { return f2_pack(v, v); }
+__device__ __forceinline__ void f2_unpack(k1_f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ k1_f2 f2_fma(k1_f2 a, k1_f2 b, k1_f2 c) { k1_f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ k1_f2 f2_add(k1_f2 a, k1_f2 b) { k1_f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ k1_f2 f2_sub(k1_f2 a, k1_f2 b) { k1_f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ k1_f2 f2_add_rd(k1_f2 a, k1_f2 b) { k1_f2 r; asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ k1_f2 f2_abs(k1_f2 a) { return a & 0x7fffffff7fffffffull; }
+
+// Two voxels (rows dj and dj + jstep of the thread) at a time.
+struct K1Vox2 {
+  k1_f2 r0, r1, r2;
+  uint32_t aA, aB;  // shared-memory byte addresses of tap (0,0,0) of the two voxels
+};
+template <int RM>
+struct K1Hot2 {
+  k1_f2 D1[3], P[3];
+  k1_f2 inv2S, hinv, twoS, rA, rB;   // RM == 1: reflection fold of source axis 2
+  float Sm1;
+};
+template <int RM>
+__device__ __forceinline__ K1Vox2 k1_fast_vox2(const K1Hot<RM>& h, const K1Hot2<RM>& q, k1_f2 fj2) {
+  const k1_f2 M = f2_dup(K1_MAGIC), NM = f2_dup(-K1_MAGIC);
+  k1_f2 v0 = f2_fma(q.D1[0], fj2, q.P[0]), v1 = f2_fma(q.D1[1], fj2, q.P[1]), v2 = f2_fma(q.D1[2], fj2, q.P[2]);
+  if (RM == 1) {  // k1_fold_reflect, two lanes at a time; the clamp has no packed form
+    const k1_f2 y = f2_fma(v2, q.inv2S, q.hinv);
+    const k1_f2 n = f2_add(f2_add(y, M), NM);
+    const k1_f2 x = f2_fma(f2_abs(f2_sub(y, n)), q.twoS, f2_dup(-0.5f));
+    float xa, xb;
+    f2_unpack(x, xa, xb);
+    xa = fminf(q.Sm1, fmaxf(xa, 0.0f)); xb = fminf(q.Sm1, fmaxf(xb, 0.0f));
+    v2 = f2_fma(q.rA, f2_pack(xa, xb), q.rB);
+  }
+  // floor on the FMA pipe: round-down add of 1.5*2^23 leaves floor(x) in the low mantissa bits
+  const k1_f2 t0 = f2_add_rd(v0, M), t1 = f2_add_rd(v1, M), t2 = f2_add_rd(v2, M);
+  K1Vox2 x;
+  x.r0 = f2_sub(v0, f2_add(t0, NM)); x.r1 = f2_sub(v1, f2_add(t1, NM)); x.r2 = f2_sub(v2, f2_add(t2, NM));
+  float t0a, t0b, t1a, t1b, t2a, t2b;
+  f2_unpack(t0, t0a, t0b); f2_unpack(t1, t1a, t1b); f2_unpack(t2, t2a, t2b);
+  x.aA = h.cbase + 4u * (__float_as_uint(t0a) * h.p0 + __float_as_uint(t1a) * h.p1 + __float_as_uint(t2a));
+  x.aB = h.cbase + 4u * (__float_as_uint(t0b) * h.p0 + __float_as_uint(t1b) * h.p1 + __float_as_uint(t2b));
+  return x;
+}
+__device__ __forceinline__ k1_f2 k1_lerp8x2(const K1Vox2& x, const k1_f2* t) {
+  const k1_f2 x00 = f2_fma(x.r2, f2_sub(t[1], t[0]), t[0]), x01 = f2_fma(x.r2, f2_sub(t[3], t[2]), t[2]);
+  const k1_f2 x10 = f2_fma(x.r2, f2_sub(t[5], t[4]), t[4]), x11 = f2_fma(x.r2, f2_sub(t[7], t[6]), t[6]);
+  const k1_f2 y0 = f2_fma(x.r1, f2_sub(x01, x00), x00), y1 = f2_fma(x.r1, f2_sub(x11, x10), x10);
+  return f2_fma(x.r0, f2_sub(y1, y0), y0);
+}
+
+// Trilinear, plain tiles, RM = 0 / 1: NP pairs of voxels per iteration with packed arithmetic, a
+// one-voxel-at-a-time tail.  Same operations (and roundings) per voxel as the scalar loop.
+template <int NP, int RMASK>
+__device__ __forceinline__ void k1_tile_staged_trilinear(const K1Fast& f) {
+  K1Map m;
+  if (!k1_lane_map(f, m)) return;
+  K1Hot<RMASK> h;
+  k1_hot_load<RMASK>(h, f);
+  const uint32_t o1 = 4u * h.p1, o0 = 4u * h.p0;
+  const int64_t ds1 = f.ds1;
+  const int64_t pstep = m.jstep * ds1;
+  const float fstep = static_cast<float>(m.jstep);
+  const int T0 = f.n.x;
+  const k1_f2 G2 = f2_dup(h.gain), B2 = f2_dup(h.bias);
+  K1Hot2<RMASK> q;
+  if (RMASK == 1) {
+    q.inv2S = f2_dup(h.inv2S[2]); q.hinv = f2_dup(h.hinv[2]); q.twoS = f2_dup(h.twoS[2]);
+    q.rA = f2_dup(h.rA[2]); q.rB = f2_dup(h.rB[2]); q.Sm1 = h.Sm1[2];
+  }
+#pragma unroll 1
+  for (int di = (threadIdx.x >> 5) % K1_GWARPS; di < T0; di += K1_GWARPS) {
+    if (!k1_plane_map(f, m, di)) continue;
+    k1_hot_plane<RMASK>(h, f, di, m.dk, m.e);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { q.D1[a] = f2_dup(h.D1[a]); q.P[a] = f2_dup(h.P[a]); }
+    float* p = f.dst + m.ii * f.ds0 + m.dk * f.ds2 + (m.j0 - m.s1) * ds1;
+    float fj = static_cast<float>(m.j0);
+    int cnt = m.cnt;
+#pragma unroll 1
+    for (; cnt >= 2 * NP; cnt -= 2 * NP) {
+      K1Vox2 x[NP];
+      k1_f2 t[NP][8];
+#pragma unroll
+      for (int u = 0; u < NP; ++u) {
+        const float fa = fj + static_cast<float>(2 * u) * fstep;
+        x[u] = k1_fast_vox2<RMASK>(h, q, f2_pack(fa, fa + fstep));
+      }
+#pragma unroll
+      for (int u = 0; u < NP; ++u) {
+        t[u][0] = f2_pack(lds_f32(x[u].aA), lds_f32(x[u].aB)); t[u][1] = f2_pack(lds_f32(x[u].aA + 4), lds_f32(x[u].aB + 4));
+        t[u][2] = f2_pack(lds_f32(x[u].aA + o1), lds_f32(x[u].aB + o1)); t[u][3] = f2_pack(lds_f32(x[u].aA + o1 + 4), lds_f32(x[u].aB + o1 + 4));
+      }
+#pragma unroll
+      for (int u = 0; u < NP; ++u) {
+        t[u][4] = f2_pack(lds_f32(x[u].aA + o0), lds_f32(x[u].aB + o0)); t[u][5] = f2_pack(lds_f32(x[u].aA + o0 + 4), lds_f32(x[u].aB + o0 + 4));
+        t[u][6] = f2_pack(lds_f32(x[u].aA + o0 + o1), lds_f32(x[u].aB + o0 + o1));
+        t[u][7] = f2_pack(lds_f32(x[u].aA + o0 + o1 + 4), lds_f32(x[u].aB + o0 + o1 + 4));
+      }
+#pragma unroll
+      for (int u = 0; u < NP; ++u) {
+        float za, zb;
+        f2_unpack(f2_fma(k1_lerp8x2(x[u], t[u]), G2, B2), za, zb);
+        p[(2 * u) * pstep] = za;
+        p[(2 * u + 1) * pstep] = zb;
+      }
+      p += 2 * NP * pstep;
+      fj += static_cast<float>(2 * NP) * fstep;
     }
 #pragma unroll 1
     for (; cnt > 0; --cnt) {
@@ -921,49 +1048,32 @@ __device__ __forceinline__ void k1_fix_columns(float* box, const K1Tile& tl, int
   __syncwarp();
 }
 
-// Position of a warp in the CTA's tile sequence seq = first, first + step, ...: the tile (chunks of
-// `chunk` consecutive tiles go round-robin over the CTAs), its ring stage / phase and tile-state
-// slot — advanced incrementally (no divisions on the per-tile path).
-struct K1Seq {
-  int c, within;      // chunk number of this CTA, position inside the chunk
-  int stage, phase, slot;
-  int round;          // number of advances so far
-  __device__ __forceinline__ void init(int first, int chunk, int n_stages, int n_slots) {
-    c = first / chunk; within = first % chunk;
-    stage = first % n_stages; phase = (first / n_stages) & 1; slot = first % n_slots;
-    round = 0;
-  }
-  __device__ __forceinline__ int64_t tile(int chunk) const {
-    return (static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(c) * gridDim.x) * chunk + within;
-  }
-  __device__ __forceinline__ void advance(int step, int chunk, int n_stages, int n_slots) {
-    within += step;
-    while (within >= chunk) { within -= chunk; ++c; }
-    stage += step;
-    while (stage >= n_stages) { stage -= n_stages; phase ^= 1; }
-    slot += step;
-    while (slot >= n_slots) slot -= n_slots;
-    ++round;
-  }
+// Persistent, warp-specialised, dynamically scheduled.  One CTA per SM runs K1_GROUPS independent
+// streams.  Stream p: its producer warp pulls chunks of `chunk` consecutive tiles from a global queue
+// (an atomic counter in the caller's launch buffer: SMs that run faster simply take more chunks, so
+// no SM idles at the tail), prepares the tile state and issues one TMA box load per tile into the
+// stream's next free ring stage; its hand-over warp sits between the TMA completion and the
+// consumers (alignment-slack columns); its K1_GWARPS consumer warps produce the voxels.  Per stream:
+// n_stages / K1_GROUPS ring stages (full / empty / landed mbarriers each) and one more tile-state
+// slot than stages, so set-up never waits for shared-memory space.  A tile with mode MODE_DONE ends
+// the stream.
+struct K1Ring {
+  int n, i, phase;   // stages (or slots) of the stream, position, phase bit of the current lap
+  __device__ __forceinline__ void init(int n_) { n = n_; i = 0; phase = 0; }
+  __device__ __forceinline__ void next() { if (++i == n) { i = 0; phase ^= 1; } }
 };
 
-// Persistent, warp-specialised: one CTA per SM walks tiles blockIdx.x, +gridDim.x, ...  The
-// producer warp prepares tile k+1 (item fetch + set-up) while the TMA box load of tile k is in
-// flight, and issues each load the moment its ring stage is released; the 16 consumer warps
-// work on the oldest full stage.  Rings: n_stages boxes (full/empty mbarrier pair each) and
-// n_stages+1 tile-state slots, so set-up never waits for shared-memory space.
 __global__ void __launch_bounds__(K1_THREADS, 1)
 k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile_start, int n_items, int total_tiles,
-          int n_stages, int stage_bytes, int chunk) {
+          int n_stages, int stage_bytes, int chunk, int n_big, unsigned int* __restrict__ sched) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int n_slots = n_stages + K1_NPROD;
+  const int n_slots = n_stages + K1_GROUPS;
   K1Slot* slots = reinterpret_cast<K1Slot*>(smem + static_cast<size_t>(n_stages) * stage_bytes);
   K1Ctx* priv = reinterpret_cast<K1Ctx*>(slots + n_slots);   // the producers' private item copies
-  uint64_t* full = reinterpret_cast<uint64_t*>(priv + K1_NPROD);
+  uint64_t* full = reinterpret_cast<uint64_t*>(priv + K1_GROUPS);
   uint64_t* empty = full + n_stages;
-  uint64_t* landed = empty + n_stages;   // TMA completion of tiles that need the column fix-up first
-  uint64_t* turn = landed + n_stages;    // producers issue in tile order: turn[p] = "warp p may issue its next tile"
-  int32_t* ts_s = reinterpret_cast<int32_t*>(turn + K1_NPROD);
+  uint64_t* landed = empty + n_stages;   // TMA completion, seen by the hand-over warp first
+  int32_t* ts_s = reinterpret_cast<int32_t*>(landed + n_stages);
   const bool ts_cached = n_items + 1 <= K1_TS_CACHE;
   if (ts_cached)
     for (int i = threadIdx.x; i <= n_items; i += K1_THREADS) ts_s[i] = __ldg(tile_start + i);
@@ -974,42 +1084,50 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(empty + s)), "r"(K1_GWARPS));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(landed + s)), "r"(1));
     }
-    for (int q = 0; q < K1_NPROD; ++q)
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(turn + q)), "r"(1));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  int stage = 0, phase = 0, slot = 0;
+  const int warp = threadIdx.x >> 5;
+  // stream of this warp, its stages p, p + K1_GROUPS, ... and slots p, p + K1_GROUPS, ...
+  const int strm = warp < K1_CWARPS ? warp / K1_GWARPS : (warp - K1_CWARPS) % K1_GROUPS;
+  K1Ring rs, rl;
+  rs.init(n_stages / K1_GROUPS);
+  rl.init(n_slots / K1_GROUPS);
 
-  if (threadIdx.x >= K1_CTHREADS + 32) {
-    // ------------------------------------------------------------------ producer warps
-    // Producer p owns the tiles seq = p, p + K1_NPROD, ... of this CTA (seq numbers the CTA's tiles:
-    // chunks of `chunk` consecutive tiles go round-robin over the CTAs, so consecutive tiles share
-    // their item and neighbouring source boxes).  The producers are independent: each tile has its
-    // own ring stage (seq % n_stages) and tile-state slot (seq % n_slots).
-    const int prod = (threadIdx.x - K1_CTHREADS - 32) >> 5;
+  if (warp >= K1_CWARPS + K1_GROUPS) {
+    // ------------------------------------------------------------------ producer warp of stream `strm`
     int item = 0, cached_item = -1, cur_start = 0;
     int next_start = ts[1];
     int acq_item = -1;                  // item whose tensor map this warp acquired last
+    int64_t cur = 0, cur_end = 0;       // tiles left of the current chunk
     K1_PROF_DECL
-    K1Seq sq;
-    sq.init(prod, chunk, n_stages, n_slots);
-    for (int seq = prod;; seq += K1_NPROD) {
-      const int64_t tile64 = sq.tile(chunk);
-      if (tile64 >= total_tiles) break;
-      const int tile = static_cast<int>(tile64);
-      stage = sq.stage; phase = sq.phase; slot = sq.slot;
+    for (;; rs.next(), rl.next()) {
+      const int stage = strm + K1_GROUPS * rs.i, slot = strm + K1_GROUPS * rl.i;
       K1_PROF_T0
-      // safe to overwrite: the slot's previous tile (seq - n_slots = seq - K1_NPROD - n_stages) was
-      // released before this warp's previous issue (tile seq - K1_NPROD waited for that very stage)
-      k1_prepare(items, ts, n_items, tile, item, cur_start, next_start, cached_item, priv[prod], slots[slot],
+      if (cur >= cur_end) {             // next chunk from the global queue
+        unsigned int c = 0;
+        if (lane == 0) c = atomicAdd(sched, 1u);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        // the first n_big queue entries are chunks of `chunk` tiles, the rest single tiles (balanced tail)
+        if (c < static_cast<unsigned int>(n_big)) { cur = static_cast<int64_t>(c) * chunk; cur_end = cur + chunk; }
+        else { cur = static_cast<int64_t>(n_big) * chunk + (c - static_cast<unsigned int>(n_big)); cur_end = cur + 1; }
+        cur_end = min(cur_end, static_cast<int64_t>(total_tiles));
+      }
+      if (cur >= total_tiles) {         // queue drained: end-of-stream marker
+        if (lane == 0) slots[slot].tl.mode = MODE_DONE;
+        __syncwarp();
+        mbar_wait_relaxed(empty + stage, rs.phase ^ 1);
+        if (lane == 0) mbar_arrive(landed + stage);
+        break;
+      }
+      const int tile = static_cast<int>(cur++);
+      // safe to overwrite: the stream has one more slot than stages, and this warp's previous issue
+      // waited for the release of the stage of the slot's previous tile
+      k1_prepare(items, ts, n_items, tile, item, cur_start, next_start, cached_item, priv[strm], slots[slot],
                  smem_u32(smem + static_cast<size_t>(stage) * stage_bytes), lane);
       K1_PROF_ADD(2)
-      // issue strictly in tile order (preparation above overlaps freely): a stage's empty barrier has
-      // only two phases, so a warp must not wait for a release more than one use ahead of the others
-      if (K1_NPROD > 1 && seq > 0) mbar_wait_relaxed(turn + prod, (sq.round - (prod == 0 ? 1 : 0)) & 1);
-      mbar_wait_relaxed(empty + stage, phase ^ 1);
+      mbar_wait_relaxed(empty + stage, rs.phase ^ 1);
       K1_PROF_ADD(0)
       if (lane == 0) {
         const K1Slot& sl = slots[slot];
@@ -1022,54 +1140,54 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
         } else {
           mbar_arrive(landed + stage);
         }
-        if (K1_NPROD > 1) mbar_arrive(turn + (prod + 1) % K1_NPROD);
       }
       __syncwarp();
       K1_PROF_ADD(1)
-      sq.advance(K1_NPROD, chunk, n_stages, n_slots);
+    }
+    // the last producer of the grid to drain the queue re-arms it for the next launch of this buffer
+    if (lane == 0) {
+      const unsigned int done = atomicAdd(sched + 1, 1u);
+      if (done == K1_GROUPS * gridDim.x - 1) { sched[0] = 0u; sched[1] = 0u; }
     }
     K1_PROF_FLUSH
     return;
   }
 
-  if (threadIdx.x >= K1_CTHREADS) {
-    // ------------------------------------------------------------------ hand-over warp
+  if (warp >= K1_CWARPS) {
+    // ------------------------------------------------------------------ hand-over warp of stream `strm`
     // Sits between the TMA completion (landed) and the consumers (full): zeroes the alignment-slack
     // columns of boxes that have any (crop windows that start mid-row), off the producer's path, so
     // that the producer never waits for a load to land.
-    for (int t0 = blockIdx.x * chunk; t0 < total_tiles; t0 += gridDim.x * chunk)
-    for (int tile = t0; tile < min(t0 + chunk, total_tiles); ++tile) {
-      mbar_wait_relaxed(landed + stage, phase);
+    for (;; rs.next(), rl.next()) {
+      const int stage = strm + K1_GROUPS * rs.i, slot = strm + K1_GROUPS * rl.i;
+      mbar_wait_relaxed(landed + stage, rs.phase);
       const K1Tile& tl = slots[slot].tl;
-      if (tl.mode == MODE_STAGED && tl.fix_hi > tl.fix_lo)
+      const int mode = tl.mode;
+      if (mode == MODE_STAGED && tl.fix_hi > tl.fix_lo)
         k1_fix_columns(reinterpret_cast<float*>(smem + static_cast<size_t>(stage) * stage_bytes), tl, lane);
       __syncwarp();
       if (lane == 0) mbar_arrive(full + stage);
-      if (++stage == n_stages) { stage = 0; phase ^= 1; }
-      if (++slot == n_slots) slot = 0;
+      if (mode == MODE_DONE) break;
     }
     return;
   }
 
-  // -------------------------------------------------------------------- consumer warps
-  // K1_GROUPS groups of K1_GWARPS warps; the CTA's tiles (in the producer's order) go round-robin
-  // over the groups, so several ring stages are being consumed at once and a thread's per-tile
-  // set-up is amortised over more voxels.
-  const int grp = threadIdx.x / K1_GTHREADS;
+  // -------------------------------------------------------------------- consumer warps of stream `strm`
   K1_PROF_DECL
-  K1Seq sq;
-  sq.init(grp, chunk, n_stages, n_slots);
-  for (;; sq.advance(K1_GROUPS, chunk, n_stages, n_slots)) {
-    if (sq.tile(chunk) >= total_tiles) break;
-    stage = sq.stage; phase = sq.phase; slot = sq.slot;
+#ifdef K1_PROFILE
+  const long long _tstart = clock64();
+#endif
+  for (;; rs.next(), rl.next()) {
+    const int stage = strm + K1_GROUPS * rs.i, slot = strm + K1_GROUPS * rl.i;
     K1_PROF_T0
-    mbar_wait(full + stage, phase);
+    mbar_wait(full + stage, rs.phase);
     K1_PROF_ADD(3)
     const K1Ctx& ctx = slots[slot].ctx;
     const K1Tile& tl = slots[slot].tl;
     const float* box = reinterpret_cast<const float*>(smem + static_cast<size_t>(stage) * stage_bytes);
     const adell_item& it = ctx.it;
     const int mode = tl.mode;
+    if (mode == MODE_DONE) break;
     if (mode == MODE_COPY) {
       k1_tile_copy_box(ctx, tl, box);
     } else if (mode == MODE_ZERO) {
@@ -1088,9 +1206,9 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
           else if (rm == 1) k1_tile_staged_nearest<1>(ctx, tl, f, box);
           else k1_tile_staged_nearest<2>(ctx, tl, f, box);
         } else {
-          if (rm == 0) k1_tile_staged_trilinear<K1_NV, 0>(f);
-          else if (rm == 1) k1_tile_staged_trilinear<K1_NV, 1>(f);
-          else k1_tile_staged_trilinear<K1_NV, 2>(f);
+          if (rm == 0) k1_tile_staged_trilinear<K1_NP, 0>(f);
+          else if (rm == 1) k1_tile_staged_trilinear<K1_NP, 1>(f);
+          else k1_tile_staged_trilinear_scalar<K1_NV, 2>(f);
         }
       }
     } else if (it.flags & ADELL_F_IDENTITY) {
@@ -1100,20 +1218,27 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
     }
     __syncwarp();
 #ifdef K1_PROFILE
-    { long long _t1 = clock64(); _acc[mode == MODE_DIRECT ? 5 : 4] += _t1 - _t0; if (threadIdx.x % K1_GTHREADS == 0) _acc[7] += 1; }
+    { long long _t1 = clock64(); _acc[4] += _t1 - _t0; if (threadIdx.x % K1_GTHREADS == 0) _acc[7] += 1; }
 #endif
     if (lane == 0) mbar_arrive(empty + stage);
   }
+#ifdef K1_PROFILE
+  if (threadIdx.x % K1_GTHREADS == 0) {  // whole-kernel time of this consumer group: sum and max over groups
+    const unsigned long long dt = static_cast<unsigned long long>(clock64() - _tstart);
+    atomicAdd(&k1_prof[5], dt);
+    atomicMax(&k1_prof[6], dt);
+  }
+#endif
   K1_PROF_FLUSH
 }
 
 // Shared-memory plan of the persistent CTA: ring stages (box + tile state + 3 mbarriers each) next to
 // the fixed part (extra tile-state slots and item copies of the producers, barriers, tile prefix).
-int k1_smem_fixed() { return K1_NPROD * static_cast<int>(sizeof(K1Slot) + sizeof(K1Ctx) + 8) + 64 + K1_TS_CACHE * 4; }
+int k1_smem_fixed() { return K1_GROUPS * static_cast<int>(sizeof(K1Slot) + sizeof(K1Ctx)) + 64 + K1_TS_CACHE * 4; }
 int k1_smem_per_stage(int stage_bytes) { return stage_bytes + static_cast<int>(sizeof(K1Slot)) + 24; }
-// largest box that still leaves room for three ring stages
+// largest box that still leaves room for four ring stages (two per stream: one at work, one in flight)
 int k1_pref_box_bytes() {
-  const int b = ((K1_SMEM_BUDGET - k1_smem_fixed()) / 3 - static_cast<int>(sizeof(K1Slot)) - 24) & ~127;
+  const int b = ((K1_SMEM_BUDGET - k1_smem_fixed()) / 4 - static_cast<int>(sizeof(K1Slot)) - 24) & ~127;
   return b < K1_MAX_BOX_BYTES ? b : K1_MAX_BOX_BYTES;
 }
 
@@ -1332,7 +1457,7 @@ int k1_encode_tmap(adell_item& it, const K1Layout& L, const int* box, EncodeTile
 // Identity item: tensor map for the 32x16x32 box copy.  Returns the box bytes (0 = not eligible).
 int k1_encode_copy(adell_item& it, EncodeTiledFn enc) {
   if (!k1_vcopy_ok(it)) return 0;
-  int T[3] = {32, 16, 32};
+  int T[3] = {K1_COPY_T0, 16, 32};
   if (const char* e = getenv("ADELL_K1_COPY_T0")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32) T[0] = v; }  // tuning aid
   int box[3] = {T[0], T[1], T[2]};
   K1Layout L;
@@ -1466,6 +1591,8 @@ extern "C" int adell_aug_prepare(adell_item* items_host, int n_items, int32_t* t
     if (acc > 0x7fffffffLL) return ADELL_ERR_BAD_ARG;
   }
   tile_start_host[n_items] = static_cast<int32_t>(acc);
+  tile_start_host[n_items + 1] = 0;  // chunk queue of the launch (see adell_aug_gather)
+  tile_start_host[n_items + 2] = 0;
   info->total_tiles = acc;
   info->smem_bytes = smem;
   info->n_staged = staged;
@@ -1504,18 +1631,28 @@ extern "C" int adell_aug_gather(const adell_item* items_dev, const int32_t* tile
   const int fixed = k1_smem_fixed();
   int n_stages = (K1_SMEM_BUDGET - fixed) / per_stage;
   if (n_stages > K1_MAX_STAGES) n_stages = K1_MAX_STAGES;
-  if (n_stages < 1) return ADELL_ERR_BAD_ARG;
+  n_stages -= n_stages % K1_GROUPS;  // the same number of stages for every stream
+  if (n_stages < K1_GROUPS) return ADELL_ERR_BAD_ARG;
   const int smem = n_stages * per_stage + fixed;
   e = cudaFuncSetAttribute(k1_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BUDGET);
   if (e != cudaSuccess) { (void)cudaGetLastError(); return adell_map_cuda_error(e); }
-  // consecutive tiles per CTA turn: small enough that the last round stays balanced
+  // consecutive tiles a producer takes from the queue at a time (they share the item and neighbouring
+  // source boxes): small enough that the tail of the launch stays balanced
   int chunk = 4;
   if (const char* ce = getenv("ADELL_K1_CHUNK")) { const int v = atoi(ce); if (v >= 1 && v <= 64) chunk = v; }
-  while (chunk > 1 && info->total_tiles < static_cast<int64_t>(sms) * chunk * 8) chunk >>= 1;
-  const int64_t n_chunks = (info->total_tiles + chunk - 1) / chunk;
-  const int64_t grid = n_chunks < sms ? n_chunks : sms;
+  // the last ~3 tiles per stream are handed out one by one
+  const int64_t streams = static_cast<int64_t>(sms) * K1_GROUPS;
+  int64_t tail = 3 * streams;
+  if (const char* te = getenv("ADELL_K1_TAIL")) { const int v = atoi(te); if (v >= 0 && v <= 64) tail = v * streams; }
+  const int64_t n_big = info->total_tiles > tail ? (info->total_tiles - tail) / chunk : 0;
+  const int64_t n_units = n_big + (info->total_tiles - n_big * chunk);
+  const int64_t n_ctas = (n_units + K1_GROUPS - 1) / K1_GROUPS;
+  const int64_t grid = n_ctas < sms ? n_ctas : sms;
+  // the two words after the tile prefix are the launch's chunk queue {next chunk, drained producers}:
+  // zero on upload (adell_aug_prepare), re-armed by the kernel itself when it finishes
+  unsigned int* sched = reinterpret_cast<unsigned int*>(const_cast<int32_t*>(tile_start_dev) + n_items + 1);
   k1_gather<<<static_cast<unsigned>(grid), K1_THREADS, static_cast<size_t>(smem), static_cast<cudaStream_t>(stream)>>>(
-      items_dev, tile_start_dev, n_items, static_cast<int>(info->total_tiles), n_stages, stage_bytes, chunk);
+      items_dev, tile_start_dev, n_items, static_cast<int>(info->total_tiles), n_stages, stage_bytes, chunk, static_cast<int>(n_big), sched);
   ADELL_CUDA_CHECK_LAUNCH();
   return ADELL_OK;
 }

@@ -60,6 +60,20 @@ def test_default_mode_nearest_is_bit_exact(shape, padding):
         assert mismatch(run_plan_cuda(plan)[0].cpu(), ref) == 0
 
 
+@pytest.mark.parametrize("shape", [(256, 256, 32), (208, 208, 64), (320, 288, 40)])
+@pytest.mark.parametrize("padding", ["zeros", "border", "reflection"])
+def test_default_mode_nearest_is_bit_exact_at_benchmark_sizes(shape, padding):
+    """Masks at the BASELINE volume sizes: sheared column tiles, wide coordinate ranges (the tie
+    window of the fast coordinates scales with the extent), thin reflected axis."""
+    R = np.random.RandomState(15)
+    img = torch.from_numpy((R.rand(1, *shape) * 5).astype(np.int32).astype(np.float32))
+    for i in range(4):
+        A = rand_affine_matrix(R, rotate=(np.pi / 8, np.pi / 8, np.pi / 16), translate=(6, 6, 2), scale=(0.1, 0.1, 0.05))
+        ref = M.affine_resample(img, A, "nearest", padding)[0]
+        out = run_plan_cuda(BatchPlan([img[0].to(DEV)]).affine(A.numpy(), "nearest", padding))[0].cpu()
+        assert mismatch(out, ref) == 0, (shape, padding, i)
+
+
 @pytest.mark.parametrize("padding", ["zeros", "border", "reflection"])
 def test_default_mode_trilinear_tolerance_large(padding):
     R = np.random.RandomState(6)

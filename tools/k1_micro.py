@@ -182,8 +182,11 @@ def main():
             v = list(out)
             print("   cycles summed over warps: prod wait-empty %d, issue %d, prepare %d | cons wait-full %d, compute %d" % tuple(v[:5]))
             nt = max(v[7], 1)
-            print("   per tile: producer prepare %.0f, wait-empty %.0f, issue %.0f cycles | per consumer warp: wait-full %.0f, compute %.0f (DIRECT %.0f) cycles; %d tiles"
-                  % (v[2] / nt, v[0] / nt, v[1] / nt, v[3] / nt / 8, v[4] / nt / 8, v[5] / nt / 8, nt))
+            print("   per tile: producer prepare %.0f, wait-empty %.0f, issue %.0f cycles | per consumer warp: wait-full %.0f, compute %.0f cycles; %d tiles"
+                  % (v[2] / nt, v[0] / nt, v[1] / nt, v[3] / nt / 8, v[4] / nt / 8, nt))
+            nl = len(ts)
+            print("   consumer-group kernel time: mean %.0f cycles per launch, max over groups and launches %d cycles; event time %.0f cycles at 1965 MHz"
+                  % (v[5] / (nl * 148 * 2), v[6], ms * 1e-3 * 1965e6))
         del L, keep
         torch.cuda.empty_cache()
 
