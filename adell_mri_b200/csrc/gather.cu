@@ -58,8 +58,11 @@ constexpr uint32_t K1_MAGIC_BITS = 0x4B400000u;
 #endif
 __device__ __forceinline__ void k1_plain_store(float4* p, float4 v) { *p = v; }
 __device__ __forceinline__ void k1_wt_store(float4* p, float4 v) { __stwt(p, v); }
+#ifndef K1_WAIT_NS
+#define K1_WAIT_NS 128u                         // back-off of the producer / hand-over polling loops
+#endif
 #ifndef K1_NP
-#define K1_NP 2                                 // trilinear voxel PAIRS (packed fp32) interleaved per consumer-thread iteration
+#define K1_NP 1                                 // trilinear voxel PAIRS (packed fp32) per consumer-thread iteration (1 measured best: smaller loop body)
 #endif
 #ifndef K1_NV
 #define K1_NV 4                                 // trilinear voxels interleaved per consumer-thread iteration
@@ -110,18 +113,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "WAIT_DONE:\n"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-// Same, for the producer / hand-over warps: a long suspend-time hint, so that a warp that is merely
-// waiting for its turn does not take issue slots from the consumer warps on its scheduler.
+// Same, for the producer / hand-over warps, which wait for thousands of cycles at a time: back off
+// with nanosleep between polls, so that a warp that is merely waiting for its turn does not take
+// issue slots from the consumer warps on its scheduler (the polling loops were ~8 % of all issued
+// instructions).
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "RWAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       "@p bra RWAIT_DONE;\n"
+      "nanosleep.u32 %2;\n"
       "bra RWAIT_LOOP;\n"
       "RWAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(K1_WAIT_NS) : "memory");
 }
 // The descriptor lives in global memory and was written by a host copy: the tensormap proxy
 // must acquire it before the TMA unit reads it (CUDA programming guide, "tensor map in global
