@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(ST_THREADS) st_meanstd(const adell_vol* __rest
 }
 
 // out[2v] = mean, out[2v+1] = std (population; 1 when it is 0, as MONAI substitutes)
-__global__ void st_meanstd_fin(const double* __restrict__ acc, int n_vols, float* out) {
+__global__ void st_meanstd_fin(const double* __restrict__ acc, int n_vols, float* out, int raw_std) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_vols) return;
   const double s = acc[3 * i], q = acc[3 * i + 1], c = acc[3 * i + 2];
@@ -139,7 +139,7 @@ __global__ void st_meanstd_fin(const double* __restrict__ acc, int n_vols, float
   if (c > 0.0) { mean = s / c; var = q / c - mean * mean; }
   if (var < 0.0) var = 0.0;
   float sd = static_cast<float>(sqrt(var));
-  if (sd == 0.0f) sd = 1.0f;
+  if (sd == 0.0f && !raw_std) sd = 1.0f;
   out[2 * i] = static_cast<float>(mean);
   out[2 * i + 1] = sd;
 }
@@ -189,6 +189,23 @@ st_intensity_map(const adell_vol* __restrict__ vols, float* const* __restrict__ 
       float y = st_program(adell_load_src(v.data, i, v.dtype), c);
       dst[i] = clip ? fminf(hi, fmaxf(y, lo)) : y;
     }
+  }
+}
+
+// monai AdjustContrast: ((x - min) / (range + eps)) ** gamma * range + min, fp32 op by op.
+__global__ void __launch_bounds__(ST_THREADS)
+st_gamma_map(const adell_vol* __restrict__ vols, float* const* __restrict__ dsts, const float* __restrict__ minmax,
+             const float* __restrict__ gammas) {
+  const adell_vol v = vols[blockIdx.y];
+  float* __restrict__ dst = dsts[blockIdx.y];
+  const float lo = __ldg(minmax + 2 * blockIdx.y), hi = __ldg(minmax + 2 * blockIdx.y + 1);
+  const float range = __fsub_rn(hi, lo), den = __fadd_rn(range, 1e-7f), gamma = __ldg(gammas + blockIdx.y);
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nthr = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = tid; i < v.n; i += nthr) {
+    const float x = adell_load_src(v.data, i, v.dtype);
+    const float t = powf(__fdiv_rn(__fsub_rn(x, lo), den), gamma);
+    dst[i] = __fadd_rn(__fmul_rn(t, range), lo);
   }
 }
 
@@ -400,8 +417,8 @@ extern "C" int adell_meanstd(const adell_vol* vols_dev, int n_vols, int64_t max_
   cudaError_t e = cudaMemsetAsync(acc_dev, 0, sizeof(double) * 3 * static_cast<size_t>(n_vols), st);
   if (e != cudaSuccess) { (void)cudaGetLastError(); return adell_map_cuda_error(e); }
   dim3 grid(st_blocks_per_vol(max_n, n_vols, 32), n_vols);
-  st_meanstd<<<grid, ST_THREADS, 0, st>>>(vols_dev, nonzero, acc_dev);
-  st_meanstd_fin<<<(n_vols + 127) / 128, 128, 0, st>>>(acc_dev, n_vols, out_dev);
+  st_meanstd<<<grid, ST_THREADS, 0, st>>>(vols_dev, nonzero & ADELL_MEANSTD_NONZERO, acc_dev);
+  st_meanstd_fin<<<(n_vols + 127) / 128, 128, 0, st>>>(acc_dev, n_vols, out_dev, (nonzero & ADELL_MEANSTD_RAW_STD) != 0);
   ADELL_CUDA_CHECK_LAUNCH();
   return ADELL_OK;
 }
@@ -415,6 +432,17 @@ extern "C" int adell_intensity_map(const adell_vol* vols_dev, float* const* dst_
   dim3 grid(st_blocks_per_vol(max_n, n_vols, 16), n_vols);
   st_intensity_map<<<grid, ST_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(vols_dev, dst_dev, coef_dev, clip,
                                                                                 clip_lo, clip_hi);
+  ADELL_CUDA_CHECK_LAUNCH();
+  return ADELL_OK;
+}
+
+extern "C" int adell_gamma_map(const adell_vol* vols_dev, float* const* dst_dev, const float* minmax_dev,
+                               const float* gamma_dev, int n_vols, int64_t max_n, void* stream) {
+  if (n_vols == 0) return ADELL_OK;
+  if (vols_dev == nullptr || dst_dev == nullptr || minmax_dev == nullptr || gamma_dev == nullptr || n_vols < 0 || max_n < 0)
+    return ADELL_ERR_BAD_ARG;
+  dim3 grid(st_blocks_per_vol(max_n, n_vols, 16), n_vols);
+  st_gamma_map<<<grid, ST_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(vols_dev, dst_dev, minmax_dev, gamma_dev);
   ADELL_CUDA_CHECK_LAUNCH();
   return ADELL_OK;
 }

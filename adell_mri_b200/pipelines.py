@@ -43,7 +43,8 @@ def _check_augment(augment, valid):
     out_of_scope = [a for a in augment if a not in _GPU_AUGMENTS and a != "trivial"]
     if out_of_scope:
         raise NotImplementedError(
-            f"augmentations {out_of_scope} are outside the fused GPU hot path (see DESIGN.md, out of scope)"
+            f"augmentations {out_of_scope} are not on the batch fast path ('intensity' is served by the "
+            "dictionary-transform surface; the others are out of scope, see DESIGN.md)"
         )
 
 

@@ -365,7 +365,7 @@ class BatchPlan:
         self._close(w & (st.has_affine | self._has_noise()))
         # a pending post map precedes this resample: fold it into the per-tap pre map
         foldable = w & ((st.post_s != 1) | (st.post_o != 0))
-        bad = foldable & st.pre.has_invalid() & (st.post_o != 0)
+        bad = foldable & ((st.pre.has_invalid() & (st.post_o != 0)) | (st.pre_dev != 0))
         self._close(bad)
         foldable &= ~bad
         st.pre_o = np.where(foldable, st.pre_o * st.post_s + st.post_o, st.pre_o)
@@ -387,7 +387,9 @@ class BatchPlan:
         w = _where(where, self.n)
         scale = np.broadcast_to(np.asarray(scale, np.float64), (self.n,))
         offset = np.broadcast_to(np.asarray(offset, np.float64), (self.n,))
-        self._close(w & self._has_noise())
+        # a device-side pre map ({scale, offset} read from pre_dev by the kernel) cannot absorb a
+        # host-side one: materialise that pass first
+        self._close(w & (self._has_noise() | (self.st.pre_dev != 0)))
         st = self.st
         to_post = w & (st.has_affine | st.pre.has_invalid() | st.clip)
         to_pre = w & ~to_post

@@ -60,15 +60,32 @@ def minmax(vols: Sequence[torch.Tensor], desc=None) -> torch.Tensor:
     return out
 
 
-def meanstd(vols: Sequence[torch.Tensor], nonzero: bool = False, desc=None) -> torch.Tensor:
-    """``[n, 2]`` fp32 (mean, population std; std 0 -> 1) per volume — monai NormalizeIntensity."""
+def meanstd(vols: Sequence[torch.Tensor], nonzero: bool = False, desc=None, raw_std: bool = False) -> torch.Tensor:
+    """``[n, 2]`` fp32 (mean, population std) per volume.  A zero std is reported as 1 (monai
+    NormalizeIntensity) unless ``raw_std`` (monai StdShiftIntensity: ``offset = factor * std``)."""
     dev = _check_vols(vols)
     d, max_n = desc if desc is not None else vol_descriptors(vols)
     out = torch.empty(len(vols), 2, dtype=torch.float32, device=dev)
     acc = torch.empty(len(vols), 3, dtype=torch.float64, device=dev)
-    _lib.check(_lib.load().adell_meanstd(d.data_ptr(), len(vols), max_n, int(nonzero), acc.data_ptr(), out.data_ptr(),
+    flags = (1 if nonzero else 0) | (2 if raw_std else 0)
+    _lib.check(_lib.load().adell_meanstd(d.data_ptr(), len(vols), max_n, flags, acc.data_ptr(), out.data_ptr(),
                                          _stream(dev)), "adell_meanstd")
     return out
+
+
+def gamma_map(vols: Sequence[torch.Tensor], minmax_dev: torch.Tensor, gammas, desc=None) -> list[torch.Tensor]:
+    """monai AdjustContrast per volume: ``((x - min) / (range + 1e-7)) ** gamma * range + min`` with
+    ``{min, max}`` read from ``minmax_dev`` (``[n, 2]`` fp32 on the device); returns new fp32 volumes."""
+    dev = _check_vols(vols)
+    d, max_n = desc if desc is not None else vol_descriptors(vols)
+    outs = [torch.empty(v.shape, dtype=torch.float32, device=dev) for v in vols]
+    ptrs = torch.tensor([o.data_ptr() for o in outs], dtype=torch.int64).pin_memory().to(dev, non_blocking=True)
+    g = torch.tensor(np.broadcast_to(np.asarray(gammas, np.float32), (len(vols),)).copy()).pin_memory().to(dev, non_blocking=True)
+    if minmax_dev.shape != (len(vols), 2) or minmax_dev.dtype != torch.float32 or not minmax_dev.is_contiguous():
+        raise ValueError("minmax_dev must be a contiguous [n, 2] float32 tensor")
+    _lib.check(_lib.load().adell_gamma_map(d.data_ptr(), ptrs.data_ptr(), minmax_dev.data_ptr(), g.data_ptr(), len(vols), max_n,
+                                           _stream(dev)), "adell_gamma_map")
+    return outs
 
 
 def scaler_coefs(stats: torch.Tensor, scaler: int, p0: float, p1: float) -> torch.Tensor:

@@ -205,7 +205,7 @@ class AugmentationWorkhorsed(T.RandomizableTransform):
 # --------------------------------------------------------------------------- augmentation builders
 _UNET_VALID = ["intensity", "noise", "rbf", "affine", "shear", "flip", "blur", "distort", "lowres", "trivial"]
 _CLASS_VALID = ["intensity", "noise", "rbf", "affine", "shear", "flip", "blur", "lowres", "distort", "trivial"]
-_FUSED_TOKENS = {"affine", "shear", "flip", "trivial"}
+_FUSED_TOKENS = {"affine", "shear", "flip", "trivial", "intensity"}
 
 
 def _check_tokens(augment, valid):
@@ -227,6 +227,9 @@ def get_augmentations_unet(augment, all_keys, image_keys, t2_keys, random_crop_s
     if "trivial" in augment:
         augments.append(T.Identityd(image_keys))
         prob = 1.0
+    if "intensity" in augment:   # augmentations.py:66-76 (listed before the spatial members)
+        augments.extend([T.RandAdjustContrastd(image_keys, gamma=(0.5, 1.5), prob=prob),
+                         T.RandStdShiftIntensityd(image_keys, factors=0.1, prob=prob)])
     if "affine" in augment:
         augments.append(T.RandAffined(all_keys, rotate_range=[np.pi / 8, np.pi / 8, np.pi / 16], prob=prob, mode=interpolation))
     if "shear" in augment:
@@ -262,6 +265,10 @@ def get_augmentations_class(augment, image_keys, mask_key, t2_keys, flip_axis: l
     if "trivial" in augment:
         augments.append(T.Identityd(image_keys))
         prob = 1.0
+    if "intensity" in augment:   # augmentations.py:219-232
+        augments.extend([T.RandAdjustContrastd(image_keys, gamma=(0.5, 1.5), prob=prob),
+                         T.RandStdShiftIntensityd(image_keys, factors=0.1, prob=prob),
+                         T.RandShiftIntensityd(image_keys, offsets=0.1, prob=prob)])
     if "flip" in augment:
         if isinstance(flip_axis, int):
             flip_axis = [flip_axis]

@@ -657,6 +657,80 @@ class RandShiftIntensityd(_RandIntensityd):
         return d
 
 
+class RandStdShiftIntensityd(_RandIntensityd):
+    """``monai.transforms.RandStdShiftIntensityd`` †: ``v + factor * std(v)``, ``factor ~ U(-factors,
+    factors)``, the same factor for every key, ``std`` = population standard deviation of each key's
+    whole array (``torch.std(unbiased=False)``), computed by the device statistics kernel (fp64
+    accumulation) and applied through the fused ``{scale, offset}`` pre map.  The input is
+    materialised first (the statistic is taken over the current volume)
+    (/root/reference/adell_mri/transform_factory/augmentations.py:66-76,219-232)."""
+
+    def __init__(self, keys, factors, prob: float = 0.1, nonzero: bool = False, channel_wise: bool = False,
+                 allow_missing_keys: bool = False, **_):
+        super().__init__(keys, prob, allow_missing_keys)
+        if nonzero or channel_wise:
+            raise NotImplementedError("RandStdShiftIntensityd: nonzero / channel_wise are not used by the reference")
+        self.factors = (min(-factors, factors), max(-factors, factors)) if not isinstance(factors, (tuple, list)) else (min(factors), max(factors))
+        self.factor = None
+
+    def __call__(self, data):
+        from . import stats
+
+        d = dict(data)
+        self.randomize(None)
+        if not self._do_transform:
+            return d
+        self.R_inner.rand()
+        self.factor = self.R_inner.uniform(low=self.factors[0], high=self.factors[1])
+        for k in self.key_iterator(d):
+            x = d[k].tensor() if isinstance(d[k], Pending) else d[k]
+            x = x.contiguous()
+            ms = stats.meanstd([x.reshape(-1)], raw_std=True)            # [1, 2] on the device
+            pre = torch.ones(x.shape[0], 2, dtype=torch.float32, device=x.device)
+            pre[:, 1] = ms[0, 1] * self.factor                           # fp32 tensor * python scalar, like MONAI
+            p = as_pending(x.to(torch.float32) if x.dtype != torch.float32 else x)
+            p.plan.intensity_from_device(pre)
+            d[k] = p
+        return d
+
+
+class RandAdjustContrastd(_RandIntensityd):
+    """``monai.transforms.RandAdjustContrastd`` †: ``((v - min) / (range + 1e-7)) ** gamma * range +
+    min`` with ``gamma ~ U(gamma)`` shared by every key and ``min`` / ``range`` of each key's whole
+    array.  The power law is not linear, so it cannot ride in the gather's intensity map: it runs
+    as one pointwise device pass (``adell_minmax`` + ``adell_gamma_map``) over the materialised
+    input (/root/reference/adell_mri/transform_factory/augmentations.py:66-76,219-232)."""
+
+    def __init__(self, keys, prob: float = 0.1, gamma=(0.5, 4.5), invert_image: bool = False, retain_stats: bool = False,
+                 allow_missing_keys: bool = False, **_):
+        super().__init__(keys, prob, allow_missing_keys)
+        if invert_image or retain_stats:
+            raise NotImplementedError("RandAdjustContrastd: invert_image / retain_stats are not used by the reference")
+        if isinstance(gamma, (int, float)):
+            if gamma <= 0.5:
+                raise ValueError("if gamma is a number, must greater than 0.5 and value is picked from (0.5, gamma)")
+            self.gamma = (0.5, gamma)
+        else:
+            self.gamma = (min(gamma), max(gamma))
+        self.gamma_value = None
+
+    def __call__(self, data):
+        from . import stats
+
+        d = dict(data)
+        self.randomize(None)
+        if not self._do_transform:
+            return d
+        self.R_inner.rand()
+        self.gamma_value = self.R_inner.uniform(low=self.gamma[0], high=self.gamma[1])
+        for k in self.key_iterator(d):
+            x = d[k].tensor() if isinstance(d[k], Pending) else d[k]
+            flat = [x.contiguous().reshape(-1)]
+            mm = stats.minmax(flat)
+            d[k] = stats.gamma_map(flat, mm, self.gamma_value)[0].reshape(x.shape)
+        return d
+
+
 class RandGaussianNoised(_RandIntensityd):
     """``monai.transforms.RandGaussianNoised`` †: sigma ~ U(0, std) (``sample_std``), ONE noise
     volume of the first key's shape drawn from ``R.normal`` on the host (float64 -> float32) and
@@ -800,8 +874,6 @@ def not_on_fused_path(name: str):
     return ctor
 
 
-RandAdjustContrastd = not_on_fused_path("RandAdjustContrastd")
-RandStdShiftIntensityd = not_on_fused_path("RandStdShiftIntensityd")
 RandRicianNoised = not_on_fused_path("RandRicianNoised")
 RandGibbsNoised = not_on_fused_path("RandGibbsNoised")
 RandBiasFieldd = not_on_fused_path("RandBiasFieldd")

@@ -207,6 +207,17 @@ int adell_minmax(const adell_vol* vols_dev, int n_vols, int64_t max_n, float* ou
  * zeroed by the call); nonzero != 0 restricts the statistics to elements != 0. */
 int adell_meanstd(const adell_vol* vols_dev, int n_vols, int64_t max_n, int nonzero, double* acc_dev,
                   float* out_dev, void* stream);
+#define ADELL_MEANSTD_NONZERO 1 /* bit 0 of `nonzero`: statistics over elements != 0                  */
+#define ADELL_MEANSTD_RAW_STD 2 /* bit 1 of `nonzero`: report a zero std as 0 (RandStdShiftIntensityd:
+                                   offset = factor * std), not as NormalizeIntensityd's 1             */
+
+/* monai AdjustContrast (RandAdjustContrastd, --augment intensity;
+ * /root/reference/adell_mri/transform_factory/augmentations.py:66-76,219-232):
+ *   y = pow((x - min) / (range + 1e-7f), gamma) * range + min,  range = max - min,
+ * every op rounded to fp32 in that order; {min, max} per volume are read from minmax_dev[2*v..]
+ * (adell_minmax), the exponent from gamma_dev[v].  dst is fp32, contiguous. */
+int adell_gamma_map(const adell_vol* vols_dev, float* const* dst_dev, const float* minmax_dev,
+                    const float* gamma_dev, int n_vols, int64_t max_n, void* stream);
 
 /* Exact elementwise intensity program  y = ((x*m0 - a)/d)*m1*m2 + b  with every op rounded to
  * fp32 in that order and no-op steps skipped bit-exactly (m0=1, a=0, d=1, m1=1, m2=1, b=0); the

@@ -513,3 +513,23 @@ def all_flip_combinations(flip_axis):
     for i in range(len(flip_axis)):
         out.extend(itertools.combinations(flip_axis, i + 1))
     return out
+
+
+# --------------------------------------------------------------------------- --augment intensity
+def adjust_contrast(img: torch.Tensor, gamma: float) -> torch.Tensor:
+    """monai AdjustContrast.__call__ † (invert_image=False, retain_stats=False):
+    ``((img - min) / float(range + 1e-7)) ** gamma * range + min`` over the whole array
+    (/root/reference/adell_mri/transform_factory/augmentations.py:66-76,219-232)."""
+    img = img.to(torch.float32)
+    epsilon = 1e-7
+    img_min = img.min()
+    img_range = img.max() - img_min
+    return ((img - img_min) / float(img_range + epsilon)) ** gamma * img_range + img_min
+
+
+def std_shift_intensity(img: torch.Tensor, factor: float) -> torch.Tensor:
+    """monai StdShiftIntensity._stdshift † (nonzero=False, channel_wise=False): ``img + factor *
+    std(img)`` with the population standard deviation of the whole array."""
+    img = img.to(torch.float32)
+    offset = factor * torch.std(img, unbiased=False)
+    return img + offset

@@ -214,6 +214,61 @@ class ShiftD(ScaleD):
         return d
 
 
+class ContrastD(ScaleD):
+    """RandAdjustContrastd †: dict-level gate, then the array transform's gate (prob 1.0) and
+    ``gamma ~ U(lo, hi)`` on the identically seeded second stream; one gamma for every key."""
+
+    def __init__(self, keys, prob, gamma):
+        super().__init__(keys, None)
+        self.prob, self.gamma = prob, gamma
+
+    def __call__(self, d):
+        d = dict(d)
+        if not self.R.rand() < self.prob:
+            return d
+        self.R2.rand()
+        g = self.R2.uniform(low=self.gamma[0], high=self.gamma[1])
+        for k in self.keys:
+            d[k] = M.adjust_contrast(d[k], g)
+        return d
+
+
+class StdShiftD(ScaleD):
+    """RandStdShiftIntensityd †."""
+
+    def __init__(self, keys, prob, factors):
+        super().__init__(keys, factors)
+        self.prob = prob
+
+    def __call__(self, d):
+        d = dict(d)
+        if not self.R.rand() < self.prob:
+            return d
+        self.R2.rand()
+        f = self.R2.uniform(low=-self.f, high=self.f)
+        for k in self.keys:
+            d[k] = M.std_shift_intensity(d[k], f)
+        return d
+
+
+class ProbShiftD(ScaleD):
+    """RandShiftIntensityd † with a gate probability (the --augment intensity member)."""
+
+    def __init__(self, keys, prob, offsets):
+        super().__init__(keys, offsets)
+        self.prob = prob
+
+    def __call__(self, d):
+        d = dict(d)
+        if not self.R.rand() < self.prob:
+            return d
+        self.R2.rand()
+        o = self.R2.uniform(low=-self.f, high=self.f)
+        for k in self.keys:
+            d[k] = (d[k] + o).to(torch.float32)
+        return d
+
+
 class NoiseD(ScaleD):
     """RandGaussianNoised †: one float64 normal draw of the first key's shape, cast to fp32."""
 
@@ -293,6 +348,8 @@ def unet(augment, all_keys, image_keys, random_crop_size=None, has_label=True, n
     modes = ["bilinear" if k in image_keys else "nearest" for k in all_keys]
     prob = 1.0 if "trivial" in augment else 0.2
     aug = [Same()] if "trivial" in augment else []
+    if "intensity" in augment:
+        aug += [ContrastD(image_keys, prob, (0.5, 1.5)), StdShiftD(image_keys, prob, 0.1)]
     if "affine" in augment:
         aug.append(AffineD(all_keys, prob, modes, rotate_range=[np.pi / 8, np.pi / 8, np.pi / 16]))
     if "shear" in augment:
@@ -313,6 +370,8 @@ def classification(augment, image_keys, mask_key, flip_axis=(0, 1), prob=0.1, n_
     if "trivial" in augment:
         aug.append(Same())
         prob = 1.0
+    if "intensity" in augment:
+        aug += [ContrastD(image_keys, prob, (0.5, 1.5)), StdShiftD(image_keys, prob, 0.1), ProbShiftD(image_keys, prob, 0.1)]
     if "flip" in augment:
         combos = [c for i in range(len(flip_axis)) for c in itertools.combinations(flip_axis, i + 1)]
         aug.append(PickOne([FlipD(keys, prob, c) for c in combos]))

@@ -145,6 +145,63 @@ def test_ssl_pre_transforms_intensity_and_copy(dev):
     assert torch.equal(d["image_copy"].tensor().cpu(), want)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("augment", [["intensity"], ["intensity", "affine", "flip"], ["trivial", "intensity", "affine"]])
+def test_unet_intensity_token_matches_eager_reference(augment):
+    """--augment intensity (RandAdjustContrastd + RandStdShiftIntensityd before the spatial members):
+    same draws as the eager oracle chain; values within fp32 pow / reduction-order tolerance; the mask
+    (untouched by the intensity members) stays bit-exact."""
+    dev = "cuda:0"
+    T.set_mode(strict=True, fast=False, noise="injected")
+    try:
+        R = np.random.RandomState(8)
+        keys, shape = ["t2", "adc"], (28, 24, 12)
+        samples = _samples(R, 8, keys, shape)
+        lazy_aug = F.get_augmentations_unet(augment, keys + ["mask"], keys, [], flip_axis=[0, 1, 2])
+        ref_aug = P.unet(augment, keys + ["mask"], keys, flip_axis=(0, 1, 2))
+        if "trivial" not in augment:   # make the members fire often enough to be exercised
+            for t in lazy_aug.flatten().transforms:
+                if isinstance(t, (T.RandAdjustContrastd, T.RandStdShiftIntensityd)):
+                    t.prob = 0.7
+            for t in ref_aug.ts:
+                if isinstance(t, (P.ContrastD, P.StdShiftD)):
+                    t.prob = 0.7
+        lazy = T.Compose([lazy_aug, T.ConcatItemsd(keys, "image"), T.SelectItemsd(["image", "mask"])]).set_random_state(13)
+        ref = P.Chain([ref_aug, P.ConcatD(keys, "image")]).seed(13)
+        batch = collate.safe_collate([lazy(_to(s, dev)) for s in samples])
+        fired = 0
+        for b, s in enumerate(samples):
+            w = ref(s)
+            g, r = batch["image"][b].cpu(), w["image"]
+            assert torch.allclose(g, r, rtol=2e-5, atol=2e-6), (b, float((g - r).abs().max()))
+            assert torch.equal(batch["mask"][b].cpu(), w["mask"].to(torch.float32))
+            fired += int(not torch.equal(r, torch.cat([s[k] for k in keys], 0)))
+        assert fired >= 3
+    finally:
+        T.set_mode(strict=False)
+
+
+@pytest.mark.gpu
+def test_classification_intensity_token_matches_eager_reference():
+    dev = "cuda:0"
+    T.set_mode(strict=True, fast=False, noise="injected")
+    try:
+        R = np.random.RandomState(9)
+        keys, shape = ["t2", "adc"], (30, 28, 14)
+        samples = _samples(R, 8, keys, shape)
+        augment = ["intensity", "flip", "affine"]
+        lazy = T.Compose([F.get_augmentations_class(augment, keys, "mask", [], flip_axis=[0, 1], prob=0.6),
+                          T.ConcatItemsd(keys + ["mask"], "image")]).set_random_state(31)
+        ref = P.Chain([P.classification(augment, keys, "mask", flip_axis=(0, 1), prob=0.6), P.ConcatD(keys + ["mask"], "image")]).seed(31)
+        batch = collate.safe_collate([lazy(_to(s, dev)) for s in samples])
+        for b, s in enumerate(samples):
+            g, r = batch["image"][b].cpu(), ref(s)["image"]
+            assert torch.allclose(g[:2], r[:2], rtol=2e-5, atol=2e-6), (b, float((g - r).abs().max()))
+            assert torch.equal(g[2], r[2])   # the mask channel
+    finally:
+        T.set_mode(strict=False)
+
+
 def test_unknown_and_out_of_scope_tokens_raise():
     with pytest.raises(NotImplementedError):
         F.get_augmentations_unet(["bogus"], ["a"], ["a"], [])

@@ -61,3 +61,20 @@ def test_flatten_box_formula():
     assert cropped == [3, 13, 5, 11, 1, 3]
     box = M.flatten_box(cropped, roi)
     assert box.dtype == np.float32 and box.tolist() == [3, 5, 1, 3, 5, 5]
+
+
+def test_intensity_token_known_answers():
+    """--augment intensity members († MONAI AdjustContrast / StdShiftIntensity): closed forms on a ramp."""
+    import numpy as np
+    import torch
+
+    from oracle import monai_restated as M
+
+    x = torch.arange(5, dtype=torch.float32).reshape(1, 5, 1, 1) + 2.0          # 2..6: min 2, range 4
+    y = M.adjust_contrast(x, 2.0).reshape(-1).numpy()
+    want = ((np.arange(5, dtype=np.float32) / np.float32(np.float32(4) + np.float32(1e-7))) ** 2 * np.float32(4) + np.float32(2))
+    assert np.allclose(y, want, rtol=1e-6) and y[0] == 2.0 and abs(y[-1] - 6.0) < 1e-5
+    z = M.std_shift_intensity(x, 0.5).reshape(-1).numpy()
+    assert np.allclose(z, (np.arange(5) + 2.0) + 0.5 * np.sqrt(2.0), rtol=1e-6)   # population std of 5 consecutive ints = sqrt(2)
+    c = M.std_shift_intensity(torch.full((1, 3, 3, 3), 7.0), 0.5)
+    assert torch.equal(c, torch.full((1, 3, 3, 3), 7.0))                            # zero std: no shift
