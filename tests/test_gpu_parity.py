@@ -74,6 +74,22 @@ def test_default_mode_nearest_is_bit_exact_at_benchmark_sizes(shape, padding):
         assert mismatch(out, ref) == 0, (shape, padding, i)
 
 
+@pytest.mark.parametrize("padding,mode", [("zeros", "nearest"), ("reflection", "nearest"), ("border", "bilinear"), ("zeros", "bilinear")])
+def test_config_e_volume_against_oracle(padding, mode):
+    """Config E size (512x512x128, 134 MB): 16 column groups of sheared tiles, coordinates up to 512
+    (widest tie window); nearest bit-exact, trilinear within 1e-4 of the oracle."""
+    R = np.random.RandomState(21)
+    shape = (512, 512, 128)
+    img = torch.from_numpy((R.rand(1, *shape) * 5).astype(np.int32).astype(np.float32))
+    A = rand_affine_matrix(R, rotate=(np.pi / 8, np.pi / 8, np.pi / 16), translate=(8, 8, 3), scale=(0.1, 0.1, 0.05))
+    ref = M.affine_resample(img, A, mode, padding)[0]
+    out = run_plan_cuda(BatchPlan([img[0].to(DEV)]).affine(A.numpy(), mode, padding))[0].cpu()
+    if mode == "nearest":
+        assert mismatch(out, ref) == 0
+    else:
+        assert float((out - ref).abs().max()) <= 1e-4 * float(ref.abs().max())
+
+
 @pytest.mark.parametrize("padding", ["zeros", "border", "reflection"])
 def test_default_mode_trilinear_tolerance_large(padding):
     R = np.random.RandomState(6)
