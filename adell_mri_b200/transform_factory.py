@@ -128,6 +128,71 @@ spatial_augments = ["rotate_x", "rotate_y", "rotate_z", "translate_x", "translat
 FUSED_AUGMENTS = ["gaussian_noise", "shift_intensity", "scale_intensity", *spatial_augments]
 
 
+class GetAllCrops:
+    """``adell_mri.utils.monai_transforms.GetAllCrops``
+    (/root/reference/adell_mri/utils/monai_transforms/image_ops.py:257-331): every ``size``-shaped crop
+    of a volume on the regular grid, after a symmetric zero pad of the axes whose missing remainder is
+    smaller than half a crop.  Literal reference quirks kept: the loops run over the UN-padded extent
+    and a crop is emitted only if it ends inside it, so the pad never creates an extra crop.  Here each
+    crop is a recorded integer pad + crop on a :class:`Pending` entry: nothing is copied until
+    ``safe_collate_crops`` gathers all crops of the batch in one K1 launch of box copies."""
+
+    def __init__(self, size):
+        self.size = None if size is None else [int(x) for x in size]
+        self.ndim = None if size is None else len(self.size)
+
+    def get_pad_size(self, sh):
+        remainder = [(y - (x % y)) if x > y else 0 for x, y in zip(sh[1:], self.size)]
+        remainder = [x if x < (y // 2) else 0 for x, y in zip(remainder, self.size)]
+        return [(0, 0), *[(x // 2, x - x // 2) for x in remainder]]
+
+    def crop_windows(self, sh):
+        """``(pad_before, pad_after, [start, ...])`` for a ``[C, H, W, D]`` shape."""
+        if self.ndim != 3:
+            raise NotImplementedError("GetAllCrops: the fused path handles 3-D volumes")
+        pads = self.get_pad_size(sh)[1:]
+        ext = list(sh[1:])
+        starts = [(i, j, k)
+                  for i in range(0, ext[0], self.size[0]) for j in range(0, ext[1], self.size[1]) for k in range(0, ext[2], self.size[2])
+                  if i + self.size[0] < ext[0] + 1 and j + self.size[1] < ext[1] + 1 and k + self.size[2] < ext[2] + 1]
+        return [p[0] for p in pads], [p[1] for p in pads], starts
+
+    def __call__(self, X):
+        if self.size is None:
+            return X
+        base = T.as_pending(X)
+        before, after, starts = self.crop_windows(base.shape)
+        out = []
+        for st in starts:
+            p = base.clone()
+            p.plan.pad(before, after)
+            p.plan.crop(st, self.size)
+            out.append(p)
+        return out
+
+
+class GetAllCropsd(T.MapTransform):
+    """Dictionary version (image_ops.py:334-365): a list with one dict per crop, the other entries
+    shared.  Used by the validation pipelines of the segmentation entrypoints
+    (/root/reference/adell_mri/entrypoints/segmentation/train.py:359-371)."""
+
+    def __init__(self, keys, size):
+        super().__init__(keys)
+        self.size = size
+        self.tr = GetAllCrops(self.size)
+
+    def __call__(self, X):
+        crops = {k: list(self.tr(X[k])) for k in self.keys}
+        outputs = []
+        for elements in zip(*[crops[k] for k in self.keys]):
+            output = {k: e for k, e in zip(self.keys, elements)}
+            for k in X:
+                if k not in output:
+                    output[k] = X[k]
+            outputs.append(output)
+        return outputs
+
+
 def _aug_param_dict():
     """modules/augmentations.py:103-129 (a fresh copy: the reference mutates its dict in place)."""
     d = {"gaussian_noise": {"std": 1}, "shift_intensity": {"offsets": 0.5}, "scale_intensity": {"factors": 0.5}}
