@@ -266,6 +266,16 @@ int adell_hist_select(const uint64_t* bins_dev, int n_hist, int n_sel, int pass_
 int adell_percentile_finalize(const uint32_t* keys_dev, const double* frac_dev, int n_vols, int n_q,
                               int dtype, float* out_dev, void* stream);
 
+/* -- K4: batch-level mixing after collation ------------------------------------------------ */
+/* (partial) mixup of a collated fp32 batch [batch, per_sample] in one pass
+ * (/root/reference/adell_mri/utils/batch_preprocessing.py:31-118):
+ *   out[b] = x[b] * factor[b] + x[perm[b]] * (1 - factor[b])     (fp32: mul, mul, add, as torch)
+ * for the samples with sel[b] != 0 (sel_dev == NULL: all of them); the others are copied.
+ * out_dev must not alias x_dev.  HBM-bound: 8 B per element algorithmically (12 B when the partner
+ * sample is no longer in L2). */
+int adell_mixup(const float* x_dev, float* out_dev, const float* factor_dev, const int32_t* perm_dev,
+                const uint8_t* sel_dev, int batch, int64_t per_sample, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
