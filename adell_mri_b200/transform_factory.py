@@ -98,22 +98,34 @@ class CopyEntryd(T.Transform):
 
 
 class AdjustSizesd(T.MapTransform):
-    """/root/reference/adell_mri/utils/monai_transforms/image_ops.py:368-438, ``mode="crop"``:
-    centre-crop every key to the per-axis minimum size over the keys."""
+    """/root/reference/adell_mri/utils/monai_transforms/image_ops.py:368-438: ``mode="crop"`` crops every
+    key to the per-axis minimum size over the keys, window start ``(size - target) // 2`` (NOT MONAI's
+    ``CenterSpatialCrop`` start ``size // 2 - target // 2``: they differ when ``size`` is even and
+    ``target`` odd — pinned by tests/golden/custom_transforms.npz); ``mode="pad"`` pads to the per-axis
+    maximum with ``pad // 2`` zeros before and the rest after."""
 
     def __init__(self, keys, ndim: int = 3, mode: str = "pad"):
         super().__init__(keys)
-        if mode != "crop":
-            raise NotImplementedError("AdjustSizesd: only mode='crop' is used on the hot path")
-        self.ndim = ndim
+        if ndim != 3:
+            raise NotImplementedError("AdjustSizesd: the fused path handles 3-D volumes")
+        self.ndim, self.mode = ndim, mode
 
     def __call__(self, data):
         d = dict(data)
         for k in self.key_iterator(d):
             d[k] = T.as_pending(d[k])
-        target = np.min(np.array([d[k].spatial_shape for k in self.keys]), axis=0)
-        for k in self.keys:
-            d[k].plan.center_crop([int(x) for x in target])
+        sizes = np.array([d[k].spatial_shape for k in self.keys])
+        if self.mode == "pad":
+            target = np.max(sizes, axis=0)
+            for k in self.keys:
+                pad = [int(t - s) for t, s in zip(target, d[k].spatial_shape)]
+                before = [p // 2 for p in pad]
+                d[k].plan.pad(before, [p - b for p, b in zip(pad, before)])
+        else:
+            target = np.min(sizes, axis=0)
+            for k in self.keys:
+                start = [int(s - t) // 2 for s, t in zip(d[k].spatial_shape, target)]
+                d[k].plan.crop(start, [int(t) for t in target])
         return d
 
 
@@ -132,7 +144,8 @@ class GetAllCrops:
     """``adell_mri.utils.monai_transforms.GetAllCrops``
     (/root/reference/adell_mri/utils/monai_transforms/image_ops.py:257-331): every ``size``-shaped crop
     of a volume on the regular grid, after a symmetric zero pad of the axes whose missing remainder is
-    smaller than half a crop.  Literal reference quirks kept: the loops run over the UN-padded extent
+    smaller than half a crop.  Literal reference quirks kept: the pad amounts are derived from the
+    shape shifted by the channel axis (see ``get_pad_size``), the loops run over the UN-padded extent
     and a crop is emitted only if it ends inside it, so the pad never creates an extra crop.  Here each
     crop is a recorded integer pad + crop on a :class:`Pending` entry: nothing is copied until
     ``safe_collate_crops`` gathers all crops of the batch in one K1 launch of box copies."""
@@ -142,7 +155,10 @@ class GetAllCrops:
         self.ndim = None if size is None else len(self.size)
 
     def get_pad_size(self, sh):
-        remainder = [(y - (x % y)) if x > y else 0 for x, y in zip(sh[1:], self.size)]
+        # literal reference behaviour (image_ops.py:275-284): ``sh`` is the FULL shape, channel axis
+        # included, so the remainders are taken from (C, H, W) against size[0..2] but applied to
+        # (H, W, D) — pinned by tests/golden/custom_transforms.npz, produced by the reference itself
+        remainder = [(y - (x % y)) if x > y else 0 for x, y in zip(sh, self.size)]
         remainder = [x if x < (y // 2) else 0 for x, y in zip(remainder, self.size)]
         return [(0, 0), *[(x // 2, x - x // 2) for x in remainder]]
 

@@ -1,0 +1,144 @@
+"""Generates tests/golden/builder_wiring.json by RUNNING THE REFERENCE's own augmentation builders
+(/root/reference/adell_mri/transform_factory/augmentations.py: get_augmentations_unet / _class / _ssl,
+/root/reference/adell_mri/modules/augmentations.py: AugmentationWorkhorsed, get_transform_d) in the
+build container.  MONAI is not installed: `monai.transforms` is replaced by a RECORDER whose classes
+only remember their name and constructor arguments, so what is captured is exactly which MONAI
+transform the reference constructs, with which arguments, in which order — the wiring rows a7-a10 of
+SURVEY.md §8 — produced by the reference's code, not restated.  The nested `flatten_box` of
+get_augmentations_ssl is captured as the live function object and evaluated on sample boxes.
+
+    python tests/golden/make_golden_wiring.py        # needs /root/reference; not run on the GPU box
+"""
+import importlib.util
+import json
+import os
+import sys
+import types
+
+import numpy as np
+
+ROOT = "/root/reference/adell_mri"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class Rec:
+    """Stand-in for any `monai.transforms.X`: remembers the class name and constructor arguments."""
+
+    _name = "?"
+
+    def __init__(self, *args, **kwargs):
+        self.args, self.kwargs = args, kwargs
+
+
+class _Base:  # base classes the reference subclasses
+    def __init__(self, *a, **k):
+        pass
+
+
+def _recorder_module(name):
+    mod = types.ModuleType(name)
+    cache = {}
+
+    def getattr_(attr):
+        if attr.startswith("__"):
+            raise AttributeError(attr)
+        if attr in ("Transform", "MapTransform", "RandomizableTransform", "InvertibleTransform", "Randomizable"):
+            return _Base
+        if attr not in cache:
+            cache[attr] = type(attr, (Rec,), {"_name": attr})
+        return cache[attr]
+
+    mod.__getattr__ = getattr_
+    return mod
+
+
+def load_reference():
+    monai = types.ModuleType("monai")
+    monai.transforms = _recorder_module("monai.transforms")
+    sys.modules["monai"], sys.modules["monai.transforms"] = monai, monai.transforms
+    for name in ("adell_mri", "adell_mri.utils", "adell_mri.modules", "adell_mri.transform_factory"):
+        m = types.ModuleType(name)
+        m.__path__ = []
+        sys.modules[name] = m
+    sys.modules["adell_mri.utils.monai_transforms"] = _recorder_module("adell_mri.utils.monai_transforms")
+    mods = {}
+    for name, path in (("adell_mri.custom_types", "custom_types.py"),
+                       ("adell_mri.modules.augmentations", "modules/augmentations.py"),
+                       ("adell_mri.transform_factory.augmentations", "transform_factory/augmentations.py")):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, path))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+        mods[name] = mod
+    return mods["adell_mri.modules.augmentations"], mods["adell_mri.transform_factory.augmentations"]
+
+
+FLATTEN_BOX_INPUTS = [[3, 5, 0, 8, 2, 2], [0, 0, 0, 0, 0, 0], [10, 4, 7, 1, 3, 9]]
+
+
+def to_json(x, workhorse_cls):
+    if isinstance(x, Rec):
+        return {"cls": x._name, "args": [to_json(a, workhorse_cls) for a in x.args],
+                "kwargs": {k: to_json(v, workhorse_cls) for k, v in sorted(x.kwargs.items())}}
+    if isinstance(x, workhorse_cls):
+        return {"cls": "AugmentationWorkhorsed", "augmentations": list(x.augmentations), "keys": list(x.keys),
+                "mask_keys": list(x.mask_keys), "max_mult": x.max_mult, "N": x.N,
+                "transforms": {k: to_json(v, workhorse_cls) for k, v in x.transforms.items()}}
+    if callable(x) and getattr(x, "__name__", "") == "flatten_box":
+        return {"fn": "flatten_box", "outputs": [[float(v) for v in x(b)] for b in FLATTEN_BOX_INPUTS]}
+    if isinstance(x, (list, tuple)):
+        return [to_json(v, workhorse_cls) for v in x]
+    if isinstance(x, dict):
+        return {str(k): to_json(v, workhorse_cls) for k, v in x.items()}
+    if isinstance(x, (np.floating, float)):
+        return float(x)
+    if isinstance(x, (np.integer, int)) and not isinstance(x, bool):
+        return int(x)
+    if isinstance(x, np.ndarray):
+        return to_json(x.tolist(), workhorse_cls)
+    if x is None or isinstance(x, (bool, str)):
+        return x
+    return repr(x)
+
+
+KEYS, ALL = ["t2", "adc", "dwi"], ["t2", "adc", "dwi", "mask"]
+UNET_CASES = {
+    "affine_flip": dict(augment=["affine", "flip"], all_keys=ALL, image_keys=KEYS, t2_keys=[], flip_axis=[0, 1, 2]),
+    "affine_shear_flip": dict(augment=["affine", "shear", "flip"], all_keys=ALL, image_keys=KEYS, t2_keys=[], flip_axis=[0, 1, 2]),
+    "trivial": dict(augment=["trivial", "affine", "shear", "flip"], all_keys=ALL, image_keys=KEYS, t2_keys=[], flip_axis=[0, 1]),
+    "intensity": dict(augment=["intensity", "affine", "flip"], all_keys=ALL, image_keys=KEYS, t2_keys=[], flip_axis=[0, 1, 2]),
+    "posneg_crops": dict(augment=["affine", "flip"], all_keys=ALL, image_keys=KEYS, t2_keys=[], random_crop_size=[128, 128, 24],
+                         n_crops=2, flip_axis=[0, 1, 2]),
+    "random_crops_no_label": dict(augment=["affine", "shear", "flip"], all_keys=KEYS, image_keys=KEYS, t2_keys=[],
+                                  random_crop_size=[64, 64, 16], has_label=False, flip_axis=[0, 1]),
+}
+CLASS_CASES = {
+    "flip_affine": dict(augment=["flip", "affine"], image_keys=KEYS, mask_key="mask", t2_keys=[], flip_axis=[0, 1]),
+    "flip_affine_shear_p06": dict(augment=["flip", "affine", "shear"], image_keys=KEYS, mask_key="mask", t2_keys=[], flip_axis=[0, 1, 2], prob=0.6),
+    "trivial": dict(augment=["trivial", "flip", "affine", "shear"], image_keys=KEYS, mask_key=None, t2_keys=[], n_transforms_trivial=2),
+    "intensity": dict(augment=["intensity", "flip", "affine"], image_keys=KEYS, mask_key="mask", t2_keys=[]),
+}
+SSL_CASES = {
+    "shared_crop": dict(all_keys=["image"], copied_keys=["image_copy"], scaled_crop_size=None, roi_size=[128, 128, 32], vicregl=False, different_crop=False),
+    "different_crop": dict(all_keys=["image"], copied_keys=["image_copy"], scaled_crop_size=None, roi_size=[128, 128, 32], vicregl=False, different_crop=True, n_transforms=2),
+    "vicregl": dict(all_keys=["image"], copied_keys=["image_copy"], scaled_crop_size=None, roi_size=[96, 96, 24], vicregl=True, different_crop=False),
+}
+
+
+def main():
+    M, A = load_reference()
+    W = M.AugmentationWorkhorsed
+    out = {"unet": {}, "class": {}, "ssl": {}}
+    for name, kw in UNET_CASES.items():
+        out["unet"][name] = to_json(A.get_augmentations_unet(**kw), W)
+    for name, kw in CLASS_CASES.items():
+        out["class"][name] = to_json(A.get_augmentations_class(**kw), W)
+    for name, kw in SSL_CASES.items():
+        out["ssl"][name] = to_json(A.get_augmentations_ssl(**kw), W)
+    out["member_lists"] = {"generic": list(M.generic_augments), "mri_specific": list(M.mri_specific_augments), "spatial": list(M.spatial_augments)}
+    json.dump(out, open(os.path.join(HERE, "builder_wiring.json"), "w"), indent=1, sort_keys=True)
+    print("wrote builder_wiring.json:", {k: len(v) for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()

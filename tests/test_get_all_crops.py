@@ -26,7 +26,7 @@ def dev(request, monkeypatch):
 def reference_crops(X: np.ndarray, size):
     """Literal restatement of GetAllCrops.get_all_crops_3d (pad, loops over the un-padded extent)."""
     sh = list(X.shape[1:])
-    rem = [(y - (x % y)) if x > y else 0 for x, y in zip(sh, size)]
+    rem = [(y - (x % y)) if x > y else 0 for x, y in zip(X.shape, size)]   # full shape: the reference's own quirk
     rem = [x if x < (y // 2) else 0 for x, y in zip(rem, size)]
     Xp = np.pad(X, [(0, 0), *[(x // 2, x - x // 2) for x in rem]], "constant", constant_values=0)
     out = []

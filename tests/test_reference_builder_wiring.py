@@ -1,0 +1,175 @@
+"""Builder wiring pinned against the reference itself:
+tests/golden/builder_wiring.json was produced by RUNNING the reference's get_augmentations_unet /
+_class / _ssl and AugmentationWorkhorsed with a recorder in place of `monai.transforms`
+(tests/golden/make_golden_wiring.py), i.e. it lists which MONAI transform the reference constructs,
+with which arguments, in which order.  The product's builders must construct the same chain with the
+same effective parameters (for the members on the fused path; MONAI defaults spelled out)."""
+
+import json
+import os
+
+import numpy as np
+import pytest
+
+from adell_mri_b200 import transform_factory as F, transforms as T
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "builder_wiring.json")))
+import importlib.util
+
+_spec = importlib.util.spec_from_file_location("make_golden_wiring", os.path.join(HERE, "golden", "make_golden_wiring.py"))
+G = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(G)
+
+
+def _rng(x):
+    """Range arguments as nested lists of floats (tuples == lists, ints == floats)."""
+    if x is None:
+        return None
+    if isinstance(x, (list, tuple)):
+        return [_rng(v) for v in x]
+    return float(x)
+
+
+def _pair(x):
+    """MONAI's scalar-or-pair convention for offsets / factors: ``f -> (-f, f)`` sorted."""
+    if isinstance(x, (list, tuple)):
+        return [float(min(x)), float(max(x))]
+    return [float(min(-x, x)), float(max(-x, x))]
+
+
+# ------------------------------------------------------------------ reference records -> effective config
+def ref_cfg(r):
+    cls, a, k = r["cls"], r.get("args", []), r.get("kwargs", {})
+    if cls in ("Compose", "OneOf", "SomeOf"):
+        out = {"cls": cls, "children": [ref_cfg(c) for c in a[0]]}
+        if cls == "SomeOf":
+            out["num_transforms"] = k["num_transforms"]
+        return out
+    if cls == "AugmentationWorkhorsed":
+        fused = [m for m in r["augmentations"] if m in F.FUSED_AUGMENTS]
+        return {"cls": cls, "augmentations": fused, "keys": r["keys"], "max_mult": r["max_mult"], "N": r["N"],
+                "transforms": {m: ref_cfg(r["transforms"][m]) for m in fused}}
+    keys = list(a[0]) if isinstance(a[0], list) else [a[0]]
+    if cls == "Identityd":
+        return {"cls": cls, "keys": keys}
+    if cls == "RandAffined":
+        mode = k.get("mode", "bilinear")
+        return {"cls": cls, "keys": keys, "prob": k.get("prob", 0.1), "mode": mode if isinstance(mode, list) else [mode] * len(keys),
+                "padding_mode": k.get("padding_mode", "reflection"),   # MONAI default
+                "rotate_range": _rng(k.get("rotate_range")), "shear_range": _rng(k.get("shear_range")),
+                "translate_range": _rng(k.get("translate_range")), "scale_range": _rng(k.get("scale_range"))}
+    if cls == "RandFlipd":
+        return {"cls": cls, "keys": keys, "prob": k.get("prob", 0.1), "spatial_axis": list(k["spatial_axis"])}
+    if cls == "RandSpatialCropd":
+        roi = a[1] if len(a) > 1 else k["roi_size"]
+        return {"cls": cls, "keys": keys, "roi_size": [int(x) for x in roi], "random_size": k.get("random_size", False)}
+    if cls == "RandCropByPosNegLabeld":
+        return {"cls": cls, "keys": keys, "label_key": a[1], "spatial_size": [int(x) for x in a[2]], "num_samples": k["num_samples"],
+                "allow_smaller": k["allow_smaller"], "fg_indices_key": k["fg_indices_key"], "bg_indices_key": k["bg_indices_key"],
+                "pos_ratio": 0.5}   # MONAI defaults pos=neg=1
+    if cls == "CenterSpatialCropd":
+        return {"cls": cls, "keys": keys, "roi_size": [int(x) for x in a[1]]}
+    if cls == "ExposeTransformKeyMetad":
+        return {"cls": cls, "key": a[0], "transform_class": a[1], "nested_pattern": list(a[2]), "output_key": a[3]}
+    if cls == "Lambdad":
+        return {"cls": cls, "keys": keys, "flatten_box": a[1]["outputs"]}
+    if cls == "RandGaussianNoised":
+        return {"cls": cls, "keys": keys, "prob": k["prob"], "std": float(k["std"]), "mean": 0.0, "sample_std": True}
+    if cls == "RandShiftIntensityd":
+        return {"cls": cls, "keys": keys, "prob": k["prob"], "offsets": _pair(k["offsets"])}
+    if cls == "RandScaleIntensityd":
+        return {"cls": cls, "keys": keys, "prob": k["prob"], "factors": _pair(k["factors"])}
+    if cls == "RandStdShiftIntensityd":
+        return {"cls": cls, "keys": keys, "prob": k["prob"], "factors": _pair(k["factors"])}
+    if cls == "RandAdjustContrastd":
+        return {"cls": cls, "keys": keys, "prob": k["prob"], "gamma": [float(x) for x in k["gamma"]]}
+    raise AssertionError(f"unexpected reference transform {cls}")
+
+
+# ------------------------------------------------------------------ product objects -> effective config
+def our_cfg(t, roi_size=None):
+    if isinstance(t, F.AugmentationWorkhorsed):
+        return {"cls": "AugmentationWorkhorsed", "augmentations": list(t.augmentations), "keys": list(t.keys), "max_mult": t.max_mult,
+                "N": t.N, "transforms": {m: our_cfg(t.transforms[m]) for m in t.augmentations}}
+    if isinstance(t, T.SomeOf):
+        assert t.min_num_transforms == t.max_num_transforms
+        return {"cls": "SomeOf", "children": [our_cfg(c, roi_size) for c in t.transforms], "num_transforms": t.max_num_transforms}
+    if isinstance(t, T.OneOf):
+        return {"cls": "OneOf", "children": [our_cfg(c, roi_size) for c in t.transforms]}
+    if isinstance(t, T.Compose):
+        return {"cls": "Compose", "children": [our_cfg(c, roi_size) for c in t.transforms]}
+    cls = type(t).__name__
+    if cls == "ExposeTransformKeyMetad":
+        return {"cls": cls, "key": t.key, "transform_class": t.transform_class, "nested_pattern": t.nested_pattern, "output_key": t.output_key}
+    keys = list(t.keys)
+    if cls == "Identityd":
+        return {"cls": cls, "keys": keys}
+    if cls == "RandAffined":
+        pm = set(t.padding_mode)
+        assert len(pm) == 1
+        s = t.sampler
+        return {"cls": cls, "keys": keys, "prob": t.prob, "mode": list(t.mode), "padding_mode": pm.pop(),
+                "rotate_range": _rng(s.rotate_range), "shear_range": _rng(s.shear_range),
+                "translate_range": _rng(s.translate_range), "scale_range": _rng(s.scale_range)}
+    if cls == "RandFlipd":
+        return {"cls": cls, "keys": keys, "prob": t.prob, "spatial_axis": list(t.spatial_axis)}
+    if cls == "RandSpatialCropd":
+        return {"cls": cls, "keys": keys, "roi_size": [int(x) for x in t.roi_size], "random_size": t.random_size}
+    if cls == "RandCropByPosNegLabeld":
+        return {"cls": cls, "keys": keys, "label_key": t.label_key, "spatial_size": t.spatial_size, "num_samples": t.num_samples,
+                "allow_smaller": t.allow_smaller, "fg_indices_key": t.fg_indices_key, "bg_indices_key": t.bg_indices_key,
+                "pos_ratio": t.pos_ratio}
+    if cls == "CenterSpatialCropd":
+        return {"cls": cls, "keys": keys, "roi_size": t.roi_size}
+    if cls == "Lambdad":
+        return {"cls": cls, "keys": keys, "flatten_box": [[float(v) for v in t.func(b)] for b in G.FLATTEN_BOX_INPUTS]}
+    if cls == "RandGaussianNoised":
+        return {"cls": cls, "keys": keys, "prob": t.prob, "std": float(t.std), "mean": float(t.mean), "sample_std": t.sample_std}
+    if cls == "RandShiftIntensityd":
+        return {"cls": cls, "keys": keys, "prob": t.prob, "offsets": [float(x) for x in t.offsets]}
+    if cls in ("RandScaleIntensityd", "RandStdShiftIntensityd"):
+        return {"cls": cls, "keys": keys, "prob": t.prob, "factors": [float(x) for x in t.factors]}
+    if cls == "RandAdjustContrastd":
+        return {"cls": cls, "keys": keys, "prob": t.prob, "gamma": [float(x) for x in t.gamma]}
+    raise AssertionError(f"unexpected product transform {cls}")
+
+
+def _assert_same(ours, ref, path="root"):
+    if isinstance(ref, dict):
+        assert isinstance(ours, dict) and sorted(ours) == sorted(ref), (path, sorted(ours) if isinstance(ours, dict) else ours, sorted(ref))
+        for k in ref:
+            _assert_same(ours[k], ref[k], f"{path}.{k}")
+    elif isinstance(ref, list):
+        assert isinstance(ours, (list, tuple)) and len(ours) == len(ref), (path, ours, ref)
+        for i, (o, r) in enumerate(zip(ours, ref)):
+            _assert_same(o, r, f"{path}[{i}]")
+    elif isinstance(ref, float):
+        assert ours == pytest.approx(ref, rel=1e-12, abs=0), (path, ours, ref)
+    else:
+        assert ours == ref, (path, ours, ref)
+
+
+@pytest.mark.parametrize("name", sorted(G.UNET_CASES))
+def test_unet_builder_constructs_what_the_reference_constructs(name):
+    ours = our_cfg(F.get_augmentations_unet(**G.UNET_CASES[name]))
+    _assert_same(ours, ref_cfg(GOLD["unet"][name]))
+
+
+@pytest.mark.parametrize("name", sorted(G.CLASS_CASES))
+def test_classification_builder_constructs_what_the_reference_constructs(name):
+    ours = our_cfg(F.get_augmentations_class(**G.CLASS_CASES[name]))
+    _assert_same(ours, ref_cfg(GOLD["class"][name]))
+
+
+@pytest.mark.parametrize("name", sorted(G.SSL_CASES))
+def test_ssl_builder_constructs_what_the_reference_constructs(name):
+    ours = [our_cfg(t) for t in F.get_augmentations_ssl(**G.SSL_CASES[name])]
+    ref = [ref_cfg(r) for r in GOLD["ssl"][name]]
+    _assert_same(ours, ref)
+
+
+def test_member_vocabulary_matches_reference():
+    assert F.generic_augments == GOLD["member_lists"]["generic"]
+    assert F.mri_specific_augments == GOLD["member_lists"]["mri_specific"]
+    assert F.spatial_augments == GOLD["member_lists"]["spatial"]
