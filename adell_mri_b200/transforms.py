@@ -290,7 +290,9 @@ class EnsureTyped(MapTransform):
         return dict(data)
 
 
-ToTensord = EnsureTyped
+class ToTensord(EnsureTyped):
+    """``monai.transforms.ToTensord`` † (same conversion as :class:`EnsureTyped` here)."""
+
 
 
 class SelectItemsd(MapTransform):

@@ -64,13 +64,15 @@ def load_reference():
     mods = {}
     for name, path in (("adell_mri.custom_types", "custom_types.py"),
                        ("adell_mri.modules.augmentations", "modules/augmentations.py"),
-                       ("adell_mri.transform_factory.augmentations", "transform_factory/augmentations.py")):
+                       ("adell_mri.transform_factory.augmentations", "transform_factory/augmentations.py"),
+                       ("adell_mri.transform_factory.transforms", "transform_factory/transforms.py")):
         spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, path))
         mod = importlib.util.module_from_spec(spec)
         sys.modules[name] = mod
         spec.loader.exec_module(mod)
         mods[name] = mod
-    return mods["adell_mri.modules.augmentations"], mods["adell_mri.transform_factory.augmentations"]
+    return (mods["adell_mri.modules.augmentations"], mods["adell_mri.transform_factory.augmentations"],
+            mods["adell_mri.transform_factory.transforms"])
 
 
 FLATTEN_BOX_INPUTS = [[3, 5, 0, 8, 2, 2], [0, 0, 0, 0, 0, 0], [10, 4, 7, 1, 3, 9]]
@@ -125,8 +127,40 @@ SSL_CASES = {
 }
 
 
+SEG_COMMON = dict(all_keys=ALL, image_keys=KEYS, label_keys=["mask"], non_adc_keys=["t2", "dwi"], adc_keys=["adc"],
+                  target_spacing=None, intp=["area", "area", "area", "nearest"],
+                  intp_resampling_augmentations=["bilinear", "bilinear", "bilinear", "nearest"], possible_labels=[0, 1],
+                  positive_labels=[1], all_aux_keys=[], resize_keys=[], feature_keys=[], aux_key_net=None, feature_key_net=None,
+                  resize_size=None, label_mode="binary", fill_missing=False, brunet=False)
+FACTORY_CASES = {
+    "seg_plain": ("SegmentationTransforms", dict(SEG_COMMON, crop_size=None, pad_size=None, random_crop_size=None)),
+    "seg_pad_crop_randomcrop": ("SegmentationTransforms", dict(SEG_COMMON, crop_size=[256, 256, 32], pad_size=[256, 256, 32], random_crop_size=[128, 128, 24])),
+    "seg_unlabelled_randomcrop": ("SegmentationTransforms", dict(SEG_COMMON, all_keys=KEYS, label_keys=None, intp=["area"] * 3,
+                                                                  intp_resampling_augmentations=["bilinear"] * 3, crop_size=None,
+                                                                  pad_size=[64, 64, 16], random_crop_size=[32, 32, 8])),
+    "class_crop_mask": ("ClassificationTransforms", dict(keys=KEYS, adc_keys=["adc"], clinical_feature_keys=[], target_spacing=None,
+                                                          crop_size=[192, 192, 48], pad_size=[192, 192, 48], image_masking=False,
+                                                          image_crop_from_mask=False, mask_key="mask", branched=False,
+                                                          possible_labels=[0, 1], positive_labels=[1], label_groups=None, label_key=None,
+                                                          target_size=None, label_mode="binary", cat_confounder_keys=None,
+                                                          cont_confounder_keys=None)),
+    "class_plain_branched": ("ClassificationTransforms", dict(keys=["t2"], adc_keys=[], clinical_feature_keys=[], target_spacing=None,
+                                                               crop_size=None, pad_size=None, image_masking=False,
+                                                               image_crop_from_mask=False, mask_key=None, branched=True,
+                                                               possible_labels=[0, 1], positive_labels=[1], label_groups=None, label_key=None,
+                                                               target_size=None, label_mode="binary", cat_confounder_keys=None,
+                                                               cont_confounder_keys=None)),
+    "ssl_crop_pad": ("SSLTransforms", dict(all_keys=["image"], copied_keys=["image_copy"], adc_keys=[], non_adc_keys=["image"],
+                                            target_spacing=None, crop_size=[160, 160, 40], pad_size=[160, 160, 40], resize_size=None,
+                                            in_channels=1, n_dim=3, skip_augmentations=False, jpeg_dataset=False)),
+    "ssl_adc": ("SSLTransforms", dict(all_keys=["t2", "adc"], copied_keys=["t2_copy", "adc_copy"], adc_keys=["adc"], non_adc_keys=["t2"],
+                                       target_spacing=None, crop_size=None, pad_size=None, resize_size=None, in_channels=2, n_dim=3,
+                                       skip_augmentations=False, jpeg_dataset=False)),
+}
+
+
 def main():
-    M, A = load_reference()
+    M, A, TF = load_reference()
     W = M.AugmentationWorkhorsed
     out = {"unet": {}, "class": {}, "ssl": {}}
     for name, kw in UNET_CASES.items():
@@ -135,9 +169,14 @@ def main():
         out["class"][name] = to_json(A.get_augmentations_class(**kw), W)
     for name, kw in SSL_CASES.items():
         out["ssl"][name] = to_json(A.get_augmentations_ssl(**kw), W)
+    out["factories"] = {}
+    for name, (cls, kw) in FACTORY_CASES.items():
+        obj = getattr(TF, cls)(**kw)
+        out["factories"][name] = {"pre": to_json(obj.pre_transforms(), W), "post": to_json(obj.post_transforms(), W)}
+    out["ADC_FACTOR"] = TF.ADC_FACTOR
     out["member_lists"] = {"generic": list(M.generic_augments), "mri_specific": list(M.mri_specific_augments), "spatial": list(M.spatial_augments)}
     json.dump(out, open(os.path.join(HERE, "builder_wiring.json"), "w"), indent=1, sort_keys=True)
-    print("wrote builder_wiring.json:", {k: len(v) for k, v in out.items()})
+    print("wrote builder_wiring.json:", {k: len(v) for k, v in out.items() if hasattr(v, "__len__")})
 
 
 if __name__ == "__main__":

@@ -173,3 +173,90 @@ def test_member_vocabulary_matches_reference():
     assert F.generic_augments == GOLD["member_lists"]["generic"]
     assert F.mri_specific_augments == GOLD["member_lists"]["mri_specific"]
     assert F.spatial_augments == GOLD["member_lists"]["spatial"]
+
+
+# ------------------------------------------------------------------ *Transforms factories (rows a1-a6)
+#: reference entries that belong to the cached loading stage (disk IO, orientation, label
+#: construction): out of the hot path, the product's factories do not emit them
+LOADING_STAGE = {"LoadImaged", "Orientationd", "Spacingd", "ResampleToMatchd", "SampleChannelDimd", "CombineBinaryLabelsd",
+                 "LabelOperatorSegmentationd", "CreateImageAndWeightsd"}
+
+
+def ref_stage_cfg(r):
+    cls, a, k = r["cls"], r["args"], r["kwargs"]
+    keys = list(a[0]) if isinstance(a[0], list) else [a[0]]
+    if cls == "ScaleIntensityd":
+        pos = list(a[1:]) + [None] * 3
+        return {"cls": cls, "keys": keys, "minv": k.get("minv", pos[0] if len(a) > 1 else 0.0), "maxv": k.get("maxv", pos[1] if len(a) > 2 else 1.0),
+                "factor": k.get("factor", pos[2] if len(a) > 3 else None)}
+    if cls == "ConditionalRescalingd":
+        return {"cls": cls, "keys": keys, "max_value": a[1], "scale": a[2]}
+    if cls == "Offsetd":
+        return {"cls": cls, "keys": keys, "offset": a[1] if len(a) > 1 else k.get("offset")}
+    if cls == "SpatialPadd":
+        return {"cls": cls, "keys": keys, "spatial_size": [int(x) for x in a[1]]}
+    if cls == "CenterSpatialCropd":
+        return {"cls": cls, "keys": keys, "roi_size": [int(x) for x in a[1]]}
+    if cls == "EnsureTyped":
+        return {"cls": cls, "keys": keys}
+    if cls == "AdjustSizesd":
+        return {"cls": cls, "keys": keys, "mode": k["mode"]}
+    if cls == "FgBgToIndicesd":
+        return {"cls": cls, "keys": keys}
+    if cls == "ConcatItemsd":
+        return {"cls": cls, "keys": keys, "name": a[1]}
+    if cls == "SelectItemsd":
+        return {"cls": cls, "keys": keys}
+    if cls == "ToTensord":
+        return {"cls": cls, "keys": keys}
+    if cls == "CopyEntryd":
+        return {"cls": cls, "keys": keys, "out_keys": a[1]}
+    raise AssertionError(f"unexpected reference stage transform {cls}")
+
+
+def our_stage_cfg(t):
+    cls = type(t).__name__
+    keys = list(t.keys)
+    if cls == "ScaleIntensityd":
+        return {"cls": cls, "keys": keys, "minv": t.minv, "maxv": t.maxv, "factor": t.factor}
+    if cls == "ConditionalRescalingd":
+        return {"cls": cls, "keys": keys, "max_value": t.max_value, "scale": t.scale}
+    if cls == "Offsetd":
+        return {"cls": cls, "keys": keys, "offset": t.offset}
+    if cls == "SpatialPadd":
+        return {"cls": cls, "keys": keys, "spatial_size": [int(x) for x in t.spatial_size]}
+    if cls == "CenterSpatialCropd":
+        return {"cls": cls, "keys": keys, "roi_size": [int(x) for x in t.roi_size]}
+    if cls in ("EnsureTyped", "FgBgToIndicesd", "SelectItemsd", "ToTensord"):
+        return {"cls": cls, "keys": keys}
+    if cls == "AdjustSizesd":
+        return {"cls": cls, "keys": keys, "mode": t.mode}
+    if cls == "ConcatItemsd":
+        return {"cls": cls, "keys": keys, "name": t.name}
+    if cls == "CopyEntryd":
+        return {"cls": cls, "keys": keys, "out_keys": dict(t.out_keys)}
+    raise AssertionError(f"unexpected product stage transform {cls}")
+
+
+#: arguments of the reference dataclasses that only steer the loading stage / label handling
+_DROP = {"SegmentationTransforms": (),
+         "ClassificationTransforms": ("possible_labels", "positive_labels", "label_groups", "label_key", "label_mode",
+                                      "cat_confounder_keys", "cont_confounder_keys"),
+         "SSLTransforms": ()}
+
+
+@pytest.mark.parametrize("name", sorted(G.FACTORY_CASES))
+def test_factories_emit_the_reference_chain_on_the_hot_path(name):
+    cls, kw = G.FACTORY_CASES[name]
+    kw = {k: v for k, v in kw.items() if k not in _DROP[cls]}
+    if cls == "SegmentationTransforms" and kw.get("label_keys") is not None:
+        kw["all_keys"] = [k for k in kw["all_keys"]]   # the combined label arrives under "mask" (cached stage)
+    obj = getattr(F, cls)(**kw)
+    for stage in ("pre", "post"):
+        ref = [ref_stage_cfg(r) for r in GOLD["factories"][name][stage] if r["cls"] not in LOADING_STAGE]
+        ours = [our_stage_cfg(t) for t in getattr(obj, stage + "_transforms")()]
+        _assert_same(ours, ref, f"{name}.{stage}")
+
+
+def test_adc_factor_matches_reference():
+    assert F.ADC_FACTOR == GOLD["ADC_FACTOR"]
