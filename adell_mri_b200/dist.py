@@ -9,12 +9,41 @@ summed over NCCL after every radix pass, then every rank runs the identical sele
 
 from __future__ import annotations
 
+import os
+import random
 from typing import Sequence
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
 from . import stats
+
+
+def get_global_rank() -> int:
+    """/root/reference/adell_mri/utils/torch_utils.py:304-323: launcher environment first
+    (``RANK``, ``LOCAL_RANK``, ``SLURM_PROCID``, ``SLURM_LOCALID``), then ``torch.distributed``."""
+    for var in ("RANK", "LOCAL_RANK", "SLURM_PROCID", "SLURM_LOCALID"):
+        value = os.environ.get(var)
+        if value is not None:
+            return int(value)
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank()
+    return 0
+
+
+def get_generator_and_rng(seed: int) -> tuple[torch.Generator, np.random.Generator]:
+    """/root/reference/adell_mri/utils/torch_utils.py:326-354: the global torch /
+    random / numpy streams and the numpy Generator are seeded identically on every rank (dataset
+    construction stays consistent), the sampler's torch Generator with ``seed + global rank`` (each
+    rank draws different samples: sharding by sample without a collective)."""
+    torch.manual_seed(seed)
+    random.seed(seed)
+    np.random.seed(seed)
+    g = torch.Generator()
+    g.manual_seed(seed + get_global_rank())
+    rng = np.random.default_rng(seed)
+    return g, rng
 
 
 def rank_world(group=None) -> tuple[int, int]:
