@@ -192,6 +192,46 @@ st_intensity_map(const adell_vol* __restrict__ vols, float* const* __restrict__ 
   }
 }
 
+// Bounding box of the non-zero voxels of a [S0,S1,S2] volume: out = {lo0, hi0, lo1, hi1, lo2, hi2}
+// (hi exclusive; empty mask: lo = INT_MAX, hi = 0).  One read of the mask, warp-shuffle reductions,
+// six atomics per warp that saw a non-zero voxel.
+__global__ void st_bbox_init(int32_t* out, int n_vols) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 6 * n_vols) out[i] = (i & 1) ? 0 : 0x7fffffff;
+}
+__global__ void __launch_bounds__(ST_THREADS)
+st_mask_bbox(const adell_vol* __restrict__ vols, const int32_t* __restrict__ shapes, int32_t* __restrict__ out) {
+  const adell_vol v = vols[blockIdx.y];
+  const int S1 = shapes[3 * blockIdx.y + 1], S2 = shapes[3 * blockIdx.y + 2];
+  const int64_t plane = static_cast<int64_t>(S1) * S2;
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nthr = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  int lo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, hi[3] = {0, 0, 0};
+  for (int64_t i = tid; i < v.n; i += nthr) {
+    if (adell_load_src(v.data, i, v.dtype) != 0.0f) {
+      const int c0 = static_cast<int>(i / plane);
+      const int64_t r = i - c0 * plane;
+      const int c1 = static_cast<int>(r / S2), c2 = static_cast<int>(r - static_cast<int64_t>(c1) * S2);
+      lo[0] = min(lo[0], c0); hi[0] = max(hi[0], c0 + 1);
+      lo[1] = min(lo[1], c1); hi[1] = max(hi[1], c1 + 1);
+      lo[2] = min(lo[2], c2); hi[2] = max(hi[2], c2 + 1);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[a] = min(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+      hi[a] = max(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+    }
+  }
+  if ((threadIdx.x & 31) == 0 && hi[0] > 0) {
+    int32_t* o = out + 6 * blockIdx.y;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { atomicMin(o + 2 * a, lo[a]); atomicMax(o + 2 * a + 1, hi[a]); }
+  }
+}
+
 // monai AdjustContrast: ((x - min) / (range + eps)) ** gamma * range + min, fp32 op by op.
 __global__ void __launch_bounds__(ST_THREADS)
 st_gamma_map(const adell_vol* __restrict__ vols, float* const* __restrict__ dsts, const float* __restrict__ minmax,
@@ -432,6 +472,18 @@ extern "C" int adell_intensity_map(const adell_vol* vols_dev, float* const* dst_
   dim3 grid(st_blocks_per_vol(max_n, n_vols, 16), n_vols);
   st_intensity_map<<<grid, ST_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(vols_dev, dst_dev, coef_dev, clip,
                                                                                 clip_lo, clip_hi);
+  ADELL_CUDA_CHECK_LAUNCH();
+  return ADELL_OK;
+}
+
+extern "C" int adell_mask_bbox(const adell_vol* vols_dev, const int32_t* shapes_dev, int n_vols, int64_t max_n,
+                               int32_t* out_dev, void* stream) {
+  if (n_vols == 0) return ADELL_OK;
+  if (vols_dev == nullptr || shapes_dev == nullptr || out_dev == nullptr || n_vols < 0 || max_n < 0) return ADELL_ERR_BAD_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  st_bbox_init<<<(6 * n_vols + 127) / 128, 128, 0, st>>>(out_dev, n_vols);
+  dim3 grid(st_blocks_per_vol(max_n, n_vols, 32), n_vols);
+  st_mask_bbox<<<grid, ST_THREADS, 0, st>>>(vols_dev, shapes_dev, out_dev);
   ADELL_CUDA_CHECK_LAUNCH();
   return ADELL_OK;
 }

@@ -73,6 +73,20 @@ def meanstd(vols: Sequence[torch.Tensor], nonzero: bool = False, desc=None, raw_
     return out
 
 
+def mask_bbox(vols: Sequence[torch.Tensor]) -> torch.Tensor:
+    """``[n, 6]`` int32 ``{lo0, hi0, lo1, hi1, lo2, hi2}`` (hi exclusive) of the non-zero voxels of each
+    contiguous ``[S0, S1, S2]`` volume; an empty mask gives ``lo = INT32_MAX, hi = 0``."""
+    dev = _check_vols(vols)
+    if any(v.dim() != 3 for v in vols):
+        raise ValueError("mask_bbox expects [S0, S1, S2] volumes")
+    d, max_n = vol_descriptors(vols)
+    shapes = torch.tensor([list(v.shape) for v in vols], dtype=torch.int32).pin_memory().to(dev, non_blocking=True)
+    out = torch.empty(len(vols), 6, dtype=torch.int32, device=dev)
+    _lib.check(_lib.load().adell_mask_bbox(d.data_ptr(), shapes.data_ptr(), len(vols), max_n, out.data_ptr(), _stream(dev)),
+               "adell_mask_bbox")
+    return out
+
+
 def gamma_map(vols: Sequence[torch.Tensor], minmax_dev: torch.Tensor, gammas, desc=None) -> list[torch.Tensor]:
     """monai AdjustContrast per volume: ``((x - min) / (range + 1e-7)) ** gamma * range + min`` with
     ``{min, max}`` read from ``minmax_dev`` (``[n, 2]`` fp32 on the device); returns new fp32 volumes."""

@@ -140,6 +140,87 @@ spatial_augments = ["rotate_x", "rotate_y", "rotate_z", "translate_x", "translat
 FUSED_AUGMENTS = ["gaussian_noise", "shift_intensity", "scale_intensity", *spatial_augments]
 
 
+class CropFromMask:
+    """``adell_mri.utils.monai_transforms.CropFromMask``
+    (/root/reference/adell_mri/utils/monai_transforms/labels.py:412-477): the window is either the
+    bounding box of the mask's non-zero voxels or, when ``output_size`` is given (or the mask is empty),
+    an ``output_size`` box centred on the bounding box (on the volume centre for an empty mask) and
+    shifted back inside the volume.  The bounding box is one reduction on the device
+    (``adell_mask_bbox``); the crop itself is a recorded integer window."""
+
+    def __init__(self, output_size=None, lazy: bool = False):
+        self.output_size = None if output_size is None else [int(x) for x in output_size]
+
+    def get_centre_extremes(self, mask):
+        from . import stats
+
+        m = mask.tensor() if isinstance(mask, T.Pending) else mask
+        if m.shape[0] != 1:
+            raise NotImplementedError("CropFromMask: the mask must have one channel (the reference's slicing fails otherwise)")
+        box = stats.mask_bbox([m[0].contiguous()])[0].tolist()          # cached-stage transform: one small D2H
+        if box[1] > 0:
+            extremes = [(box[2 * a], box[2 * a + 1]) for a in range(3)]
+            centre = [(e[1] + e[0]) // 2 for e in extremes]
+        else:
+            centre = [int(c) // 2 for c in m.shape[1:]]
+            extremes = None
+        return centre, extremes
+
+    def compute_slices(self, shape, mask):
+        centres, extremes = self.get_centre_extremes(mask)
+        min_shape = [int(x) for x in shape[1:]]
+        if (self.output_size is not None) or (extremes is None):
+            if self.output_size is None:
+                raise TypeError("CropFromMask: an empty mask needs output_size (as in the reference)")
+            if any(o > s for o, s in zip(self.output_size, min_shape)):
+                raise NotImplementedError("CropFromMask: output_size larger than the volume (pad first, as the reference pipelines do)")
+            half_size = [x // 2 for x in self.output_size]
+            extremes = [(c - h, c + (o - h)) for c, h, o in zip(centres, half_size, self.output_size)]
+            for i in range(len(extremes)):
+                if extremes[i][0] < 0:
+                    extremes[i] = (0, self.output_size[i])
+                if extremes[i][1] > min_shape[i]:
+                    extremes[i] = (min_shape[i] - self.output_size[i], min_shape[i])
+        return [slice(int(e[0]), int(e[1])) for e in extremes]
+
+
+class CropFromMaskd(T.MapTransform):
+    """Dictionary version (labels.py:480-522; used by ``ClassificationTransforms(image_crop_from_mask=True)``,
+    transform_factory/transforms.py:474-481).  ``inverse`` zero-pads the entries back to their size
+    before the crop (MONAI ``Cropd.inverse`` †)."""
+
+    def __init__(self, keys, mask_key: str, output_size=None, lazy: bool = False):
+        super().__init__([keys] if isinstance(keys, str) else keys)
+        self.mask_key, self.output_size = mask_key, output_size
+        self.cropper = CropFromMask(output_size=output_size)
+
+    def __call__(self, data, lazy: bool = False):
+        d = dict(data)
+        mask = d[self.mask_key]
+        for k in self.keys:
+            p = T.as_pending(d[k]).clone() if isinstance(d[k], T.Pending) else T.as_pending(d[k])
+            full = p.spatial_shape
+            sl = self.cropper.compute_slices(p.shape, mask)
+            start = [s.start for s in sl]
+            size = [s.stop - s.start for s in sl]
+            p.plan.crop(start, size)
+            p.meta.setdefault("crop_from_mask", []).append((start, size, full))
+            d[k] = p
+        return d
+
+    def inverse(self, data):
+        d = dict(data)
+        for k in self.keys:
+            p = d[k]
+            if not isinstance(p, T.Pending) or not p.meta.get("crop_from_mask"):
+                raise RuntimeError(f"CropFromMaskd.inverse: no crop recorded for key {k}")
+            p = p.clone()
+            start, size, full = p.meta["crop_from_mask"].pop()
+            p.plan.pad(start, [f - s - z for f, s, z in zip(full, start, size)])
+            d[k] = p
+        return d
+
+
 class GetAllCrops:
     """``adell_mri.utils.monai_transforms.GetAllCrops``
     (/root/reference/adell_mri/utils/monai_transforms/image_ops.py:257-331): every ``size``-shaped crop
@@ -554,7 +635,6 @@ class ClassificationTransforms(TransformMixin):
         _reject("target_spacing", self.target_spacing)
         _reject("target_size", self.target_size)
         _reject("image_masking", self.image_masking)
-        _reject("image_crop_from_mask", self.image_crop_from_mask)
         self.keys = list(self.keys)
         self.non_adc_keys = [k for k in self.keys if k not in self.adc_keys]
         self.all_keys = [k for k in self.keys]
@@ -567,7 +647,9 @@ class ClassificationTransforms(TransformMixin):
         transforms = _intensity_stage(self.non_adc_keys, self.adc_keys, offset_adc=True)
         if self.pad_size is not None:
             transforms.append(T.SpatialPadd(self.all_keys, self.crop_size_with_margin))
-        if self.crop_size is not None:
+        if self.image_crop_from_mask is True:
+            transforms.append(CropFromMaskd(self.all_keys, mask_key=self.mask_key, output_size=self.crop_size_with_margin))
+        elif self.crop_size is not None:
             transforms.append(T.CenterSpatialCropd(self.all_keys, self.crop_size_with_margin))
         transforms.append(T.EnsureTyped(self.all_keys))
         return transforms

@@ -211,6 +211,13 @@ int adell_meanstd(const adell_vol* vols_dev, int n_vols, int64_t max_n, int nonz
 #define ADELL_MEANSTD_RAW_STD 2 /* bit 1 of `nonzero`: report a zero std as 0 (RandStdShiftIntensityd:
                                    offset = factor * std), not as NormalizeIntensityd's 1             */
 
+/* Bounding box of the non-zero voxels of each [S0,S1,S2] volume (shapes_dev: 3 int32 per volume):
+ * out_dev[6*v ..] = {lo0, hi0, lo1, hi1, lo2, hi2}, hi exclusive; an empty mask yields lo = INT32_MAX,
+ * hi = 0.  The reduction behind CropFromMaskd
+ * (/root/reference/adell_mri/utils/monai_transforms/labels.py:412-522: `torch.where(mask)` + min/max). */
+int adell_mask_bbox(const adell_vol* vols_dev, const int32_t* shapes_dev, int n_vols, int64_t max_n,
+                    int32_t* out_dev, void* stream);
+
 /* monai AdjustContrast (RandAdjustContrastd, --augment intensity;
  * /root/reference/adell_mri/transform_factory/augmentations.py:66-76,219-232):
  *   y = pow((x - min) / (range + 1e-7f), gamma) * range + min,  range = max - min,

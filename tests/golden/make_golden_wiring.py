@@ -144,6 +144,12 @@ FACTORY_CASES = {
                                                           possible_labels=[0, 1], positive_labels=[1], label_groups=None, label_key=None,
                                                           target_size=None, label_mode="binary", cat_confounder_keys=None,
                                                           cont_confounder_keys=None)),
+    "class_crop_from_mask": ("ClassificationTransforms", dict(keys=KEYS, adc_keys=["adc"], clinical_feature_keys=[], target_spacing=None,
+                                                               crop_size=[64, 64, 16], pad_size=[64, 64, 16], image_masking=False,
+                                                               image_crop_from_mask=True, mask_key="mask", branched=False,
+                                                               possible_labels=[0, 1], positive_labels=[1], label_groups=None, label_key=None,
+                                                               target_size=None, label_mode="binary", cat_confounder_keys=None,
+                                                               cont_confounder_keys=None)),
     "class_plain_branched": ("ClassificationTransforms", dict(keys=["t2"], adc_keys=[], clinical_feature_keys=[], target_spacing=None,
                                                                crop_size=None, pad_size=None, image_masking=False,
                                                                image_crop_from_mask=False, mask_key=None, branched=True,

@@ -211,6 +211,8 @@ def ref_stage_cfg(r):
         return {"cls": cls, "keys": keys}
     if cls == "CopyEntryd":
         return {"cls": cls, "keys": keys, "out_keys": a[1]}
+    if cls == "CropFromMaskd":
+        return {"cls": cls, "keys": keys, "mask_key": k["mask_key"], "output_size": [int(x) for x in k["output_size"]]}
     raise AssertionError(f"unexpected reference stage transform {cls}")
 
 
@@ -235,6 +237,8 @@ def our_stage_cfg(t):
         return {"cls": cls, "keys": keys, "name": t.name}
     if cls == "CopyEntryd":
         return {"cls": cls, "keys": keys, "out_keys": dict(t.out_keys)}
+    if cls == "CropFromMaskd":
+        return {"cls": cls, "keys": keys, "mask_key": t.mask_key, "output_size": [int(x) for x in t.output_size]}
     raise AssertionError(f"unexpected product stage transform {cls}")
 
 
