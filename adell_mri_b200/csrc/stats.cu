@@ -315,8 +315,7 @@ st_hist_first(const adell_vol* __restrict__ vols, int shared_bins, int bits, uns
   if (v.dtype == ADELL_F32 && (reinterpret_cast<uintptr_t>(v.data) & 15u) == 0) {
     const float4* p4 = reinterpret_cast<const float4*>(v.data);
     const int64_t n4 = v.n >> 2;
-    for (int64_t i = tid; i < n4; i += nthr) {
-      float4 q = __ldg(p4 + i);
+    auto count4 = [&](const float4 q) {
       uint32_t b0 = adell_key_f32(q.x) >> shift, b1 = adell_key_f32(q.y) >> shift;
       uint32_t b2 = adell_key_f32(q.z) >> shift, b3 = adell_key_f32(q.w) >> shift;
       if (b0 == b1 && b1 == b2 && b2 == b3) {
@@ -325,7 +324,13 @@ st_hist_first(const adell_vol* __restrict__ vols, int shared_bins, int bits, uns
         atomicAdd(&sh[b0 * HIST_REPL + copy], 1u); atomicAdd(&sh[b1 * HIST_REPL + copy], 1u);
         atomicAdd(&sh[b2 * HIST_REPL + copy], 1u); atomicAdd(&sh[b3 * HIST_REPL + copy], 1u);
       }
+    };
+    int64_t i = tid;
+    for (; i + 3 * nthr < n4; i += 4 * nthr) {  // four independent 128-bit loads in flight per thread
+      const float4 q0 = __ldcs(p4 + i), q1 = __ldcs(p4 + i + nthr), q2 = __ldcs(p4 + i + 2 * nthr), q3 = __ldcs(p4 + i + 3 * nthr);
+      count4(q0); count4(q1); count4(q2); count4(q3);
     }
+    for (; i < n4; i += nthr) count4(__ldcs(p4 + i));
     const float* p = reinterpret_cast<const float*>(v.data);
     for (int64_t i = (n4 << 2) + tid; i < v.n; i += nthr)
       atomicAdd(&sh[(adell_key_f32(__ldg(p + i)) >> shift) * HIST_REPL + copy], 1u);
@@ -343,43 +348,99 @@ st_hist_first(const adell_vol* __restrict__ vols, int shared_bins, int bits, uns
   }
 }
 
+constexpr int NEXT_REPL = 2;  // shared-memory copies of the later passes' histograms
+
 __global__ void __launch_bounds__(ST_THREADS)
 st_hist_next(const adell_vol* __restrict__ vols, int n_sel, int shared_bins, const uint32_t* __restrict__ prefix,
              int shift, int bits, unsigned long long* __restrict__ bins) {
-  extern __shared__ uint32_t sh[];  // [n_sel][nb]
-  __shared__ uint32_t spre[8];
+  extern __shared__ uint32_t sh[];  // [n_uniq][nb]: one histogram per DISTINCT selected prefix
+  __shared__ uint32_t spre[8];      // distinct prefixes (high bits)
+  __shared__ int s_uniq[8];         // selection -> index of its prefix in spre
+  __shared__ int s_nu;
   const int nb = 1 << bits;
-  for (int i = threadIdx.x; i < nb * n_sel; i += blockDim.x) sh[i] = 0u;
   const int h = shared_bins ? 0 : blockIdx.y;
   const int hi_shift = shift + bits;  // < 32 here
-  if (threadIdx.x < n_sel) spre[threadIdx.x] = __ldg(prefix + h * n_sel + threadIdx.x) >> hi_shift;
+  if (threadIdx.x == 0) {
+    // the lo / hi order statistics of one percentile (and neighbouring percentiles of flat data)
+    // usually share their prefix: such selections see the very same elements, count them once
+    int nu = 0;
+    for (int s = 0; s < n_sel; ++s) {
+      const uint32_t p = __ldg(prefix + h * n_sel + s) >> hi_shift;
+      int u = 0;
+      while (u < nu && spre[u] != p) ++u;
+      if (u == nu) spre[nu++] = p;
+      s_uniq[s] = u;
+    }
+    s_nu = nu;
+  }
+  __syncthreads();
+  const int nu = s_nu;
+  for (int i = threadIdx.x; i < nb * nu * NEXT_REPL; i += blockDim.x) sh[i] = 0u;
   __syncthreads();
   const adell_vol v = vols[blockIdx.y];
   const uint32_t mask = static_cast<uint32_t>(nb - 1);
   const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t nthr = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  // whole warps iterate together so that __match_any_sync sees a full mask
-  const int64_t n_round = ((v.n + nthr - 1) / nthr) * nthr;
-  for (int64_t i = tid; i < n_round; i += nthr) {
-    const bool live = i < v.n;
-    uint32_t key = live ? adell_key(v.data, i, v.dtype) : 0u;
+  const int copy = threadIdx.x & (NEXT_REPL - 1);   // lane-interleaved copies: equal keys of a warp collide 32/REPL-way
+  // `w` elements with this key under distinct prefix `u`: plain shared-memory atomic (a prefix holds
+  // 2^-11 .. 2^-22 of the keys, hits are rare and spread over the bins — no warp votes)
+  auto add = [&](int u, uint32_t key, uint32_t w) {
+    atomicAdd(&sh[((u << bits) + ((key >> shift) & mask)) * NEXT_REPL + copy], w);
+  };
+  auto count = [&](uint32_t key, uint32_t w) {   // generic: any dtype, any number of distinct prefixes
     const uint32_t khi = key >> hi_shift;
-    for (int s = 0; s < n_sel; ++s) {
-      const bool m = live && khi == spre[s];
-      const unsigned ballot = __ballot_sync(0xffffffffu, m);
-      if (ballot == 0u) continue;
-      if (m) {
-        const uint32_t bin = (key >> shift) & mask;
-        const unsigned peers = __match_any_sync(ballot, bin);
-        if ((threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&sh[s * nb + bin], __popc(peers));
-      }
+#pragma unroll 1
+    for (int u = 0; u < nu; ++u)
+      if (khi == spre[u]) add(u, key, w);
+  };
+  // fp32 fast test on the RAW bits (no key transform per element): the order-preserving key is
+  // u | 0x80000000 for non-negative floats and ~u for negative ones, so "key >> hi_shift == p" is
+  // "u >> hi_shift == p ^ top" resp. "u >> hi_shift == ~p" — two registers for the common case of
+  // two distinct prefixes (lo / hi statistics of a percentile share theirs), the generic loop otherwise
+  const uint32_t top = 1u << (31 - hi_shift), himask = 0xffffffffu >> hi_shift;
+  auto raw_of = [&](uint32_t p) { return (p & top) ? (p ^ top) : (~p & himask); };
+  const uint32_t r0 = raw_of(spre[0]), r1 = nu > 1 ? raw_of(spre[1]) : r0;
+  const bool two = nu <= 2;
+  auto count_raw = [&](uint32_t u, uint32_t w) {
+    const uint32_t uh = u >> hi_shift;
+    if (two) {
+      if (uh == r0) add(0, adell_key_f32(__uint_as_float(u)), w);
+      else if (uh == r1 && nu > 1) add(1, adell_key_f32(__uint_as_float(u)), w);
+    } else {
+      count(adell_key_f32(__uint_as_float(u)), w);
     }
+  };
+  auto count4 = [&](const float4 q) {
+    const uint32_t u0 = __float_as_uint(q.x), u1 = __float_as_uint(q.y), u2 = __float_as_uint(q.z), u3 = __float_as_uint(q.w);
+    if (u0 == u1 && u1 == u2 && u2 == u3) {  // runs of equal voxels (background): one atomic for the four
+      count_raw(u0, 4u);
+    } else {
+      count_raw(u0, 1u); count_raw(u1, 1u); count_raw(u2, 1u); count_raw(u3, 1u);
+    }
+  };
+  if (v.dtype == ADELL_F32 && (reinterpret_cast<uintptr_t>(v.data) & 15u) == 0) {
+    // fp32: four independent 128-bit loads in flight per thread, like the first pass
+    const float4* p4 = reinterpret_cast<const float4*>(v.data);
+    const int64_t n4 = v.n >> 2;
+    int64_t i = tid;
+    for (; i + 3 * nthr < n4; i += 4 * nthr) {
+      const float4 q0 = __ldcs(p4 + i), q1 = __ldcs(p4 + i + nthr), q2 = __ldcs(p4 + i + 2 * nthr), q3 = __ldcs(p4 + i + 3 * nthr);
+      count4(q0); count4(q1); count4(q2); count4(q3);
+    }
+    for (; i < n4; i += nthr) count4(__ldcs(p4 + i));
+    const float* p = reinterpret_cast<const float*>(v.data);
+    for (int64_t j = (n4 << 2) + tid; j < v.n; j += nthr) count(adell_key_f32(__ldg(p + j)), 1u);
+  } else {
+    for (int64_t i = tid; i < v.n; i += nthr) count(adell_key(v.data, i, v.dtype), 1u);
   }
   __syncthreads();
   unsigned long long* out = bins + ((static_cast<size_t>(h) * n_sel) << bits);
   for (int b = threadIdx.x; b < nb * n_sel; b += blockDim.x) {
-    uint32_t s = sh[b];
-    if (s) atomicAdd(out + b, static_cast<unsigned long long>(s));
+    const int s_ = b >> bits, bin = b & (nb - 1);
+    uint32_t c = 0;
+#pragma unroll
+    for (int r = 0; r < NEXT_REPL; ++r) c += sh[((s_uniq[s_] << bits) + bin) * NEXT_REPL + r];
+    if (c) atomicAdd(out + b, static_cast<unsigned long long>(c));
   }
 }
 
@@ -538,7 +599,7 @@ extern "C" int adell_hist_pass(const adell_vol* vols_dev, int n_vols, int64_t ma
   } else {
     if (prefix_dev == nullptr) return ADELL_ERR_BAD_ARG;
     dim3 grid(st_blocks_per_vol(max_n, n_vols, 64), n_vols);
-    size_t smem = (static_cast<size_t>(1) << pass_bits) * n_sel * sizeof(uint32_t);
+    size_t smem = (static_cast<size_t>(1) << pass_bits) * n_sel * NEXT_REPL * sizeof(uint32_t);
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(st_hist_next, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     st_hist_next<<<grid, ST_THREADS, smem, st>>>(vols_dev, n_sel, shared, prefix_dev, pass_shift, pass_bits, bins);

@@ -3,7 +3,9 @@
   python tools/k1_micro.py [--prof] [workload ...]
 
 Workloads: seg (reference probabilities), seg_all_affine, seg_copy (no affine ever fires: pure
-flip copies), ssl (config C, two views, zeros padding), cls (config D, 208x208x64 -> 192x192x48).
+flip copies), ssl (config C, two views, zeros padding), cls (config D, 208x208x64 -> 192x192x48),
+a (config A: 512 x 1x128x128x32, the reference micro-benchmark's affine), e (config E: 4 x 512x512x128 with
+device percentiles).
 `--prof` loads libadell_b200_prof.so (built with -DK1_PROFILE) and prints its cycle counters.
 """
 import ctypes
@@ -104,6 +106,65 @@ def cls_items(R, n_batches=2, B=32, src=(208, 208, 64), crop=(192, 192, 48), K=3
     return launches, B * (K + 1) * int(np.prod(crop)), keep
 
 
+def a_items(R, n_batches=2, N=512, shape=(128, 128, 32)):
+    """Config A (the reference's benchmarks/benchmark-random-affine.py case, batched): RandAffined prob 1,
+    rotate +-pi/6 x3, translate [10,10,3], scale +-0.1, trilinear, reflection."""
+    g = torch.Generator(device=dev).manual_seed(0)
+    out = torch.empty((N, 1, *shape), device=dev)
+    src = [torch.rand(shape, device=dev, generator=g) for _ in range(64)]
+    launches, keep = [], [out, src]
+    for _ in range(n_batches):
+        vols, mats, dsts = [], [], []
+        for b in range(N):
+            rot = R.uniform(-1, 1, 3) * (np.pi / 6)
+            tr = R.uniform(-1, 1, 3) * np.array([10, 10, 3])
+            sc = 1 + R.uniform(-0.1, 0.1, 3)
+            vols.append(src[b % 64]); dsts.append(out[b, 0])
+            mats.append(geometry.compose_affine(rotate=rot[None], translate=tr[None], scale=sc[None])[0])
+        plan = BatchPlan(vols)
+        plan.affine(np.stack(mats), "bilinear", "reflection")
+        launches.append(pack(plan, dsts))
+    return launches, N * int(np.prod(shape)), keep
+
+
+def e_items(R, n_batches=2, M=4, shape=(512, 512, 128)):
+    """Config E (large volumes): M volumes of 512x512x128 lognormal fp32, percentile (1, 99) scaling read
+    from the device ({scale, offset} through pre_dev) + affine gather.  The statistics are timed apart."""
+    from adell_mri_b200 import _lib, stats
+    g = torch.Generator(device=dev).manual_seed(0)
+    vols = [torch.empty(shape, device=dev).log_normal_(0, 1, generator=g) for _ in range(M)]
+    out = torch.empty((M, 1, *shape), device=dev)
+    flat = [v.reshape(-1) for v in vols]
+
+    def pre():
+        pct = stats.percentiles(flat, [1.0, 99.0])
+        return stats.coefs_to_affine(stats.scaler_coefs(pct, _lib.SCALER_RANGE, 0.0, 1.0))
+
+    for _ in range(2):
+        pre_dev = pre()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(5):
+        pre_dev = pre()
+    b.record(); torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 5
+    nvox = M * int(np.prod(shape))
+    print(f"   config E statistics (K2/K3 exact percentiles 1/99 of {M} x {shape}): {ms:.3f} ms = {4.0 * nvox / ms / 1e6:.0f} GB/s "
+          f"(4 B per voxel credited once) = {4.0 * nvox / ms / 1e6 / PEAK:.3f} of measured peak")
+    launches, keep = [], [out, vols, pre_dev]
+    for _ in range(n_batches):
+        mats = []
+        for b in range(M):
+            rot = R.uniform(-1, 1, 3) * np.array([np.pi / 8, np.pi / 8, np.pi / 16])
+            mats.append(geometry.compose_affine(rotate=rot[None])[0])
+        plan = BatchPlan(vols)
+        plan.intensity_from_device(pre_dev)
+        plan.affine(np.stack(mats), "bilinear", "zeros")
+        launches.append(pack(plan, [out[b, 0] for b in range(M)]))
+    return launches, nvox, keep
+
+
 def pack(plan, dsts):
     dst_ptr = np.array([d.data_ptr() for d in dsts], np.uint64)
     dst_stride = np.array([d.stride() for d in dsts], np.int64)
@@ -166,6 +227,10 @@ def main():
             L, vox, keep = ssl_items(R)
         elif name == "cls":
             L, vox, keep = cls_items(R)
+        elif name == "a":
+            L, vox, keep = a_items(R)
+        elif name == "e":
+            L, vox, keep = e_items(R)
         else:
             raise SystemExit(name)
         print("  ", tile_stats())
