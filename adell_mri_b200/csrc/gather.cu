@@ -315,7 +315,9 @@ struct __align__(16) K1Fast {
                          // cbase + 4*(bits0*p0 + bits1*p1 + bits2), bits = float bits of coordinate + MAGIC
   int4 fl;               // cold (padded | noise | philox), padded, philox, -
   float4 rf[3];          // per source axis a: {1/(2 S_a), 2 S_a, S_a-1, rA_a} (axes in rmask)
-  float4 rb;             // rB_0, rB_1, rB_2: box-local index = rA*u' + rB for the axes in rmask
+  float4 rb;             // rB_0, rB_1, rB_2: box-local index = rA*u' + rB for the axes in rmask; [3] = tie threshold
+  float4 ws;             // valid-weight variant (RM 3): {pre_o * post_s, post_o, -, -}; rf[a] = {lo_a - 1, hi_a + 1} then holds
+                         // the box-local interval of valid taps along axis a
   int4 vlo, vhi;         // valid output range, tile-local
   float* dst;            // tile origin in the destination
   const float* noise;    // tile origin in the noise tensor (or null)
@@ -362,6 +364,8 @@ struct K1Hot {
   uint32_t p0, p1, cbase; // tap address = cbase + 4*(bits0*p0 + bits1*p1 + bits2), bits = float bits of x + MAGIC
   float inv2S[3], hinv[3], twoS[3], Sm1[3], rA[3], rB[3];
   int rmask, pad;
+  float vl[3], vh[3];     // RM 3: valid taps lie strictly between vl and vh (box-local)
+  float wb, po;           // RM 3: pre_o * post_s (scaled by the valid weight), post_o
 };
 
 template <int RM>
@@ -382,7 +386,12 @@ __device__ __forceinline__ void k1_hot_load(K1Hot<RM>& h, const K1Fast& f) {
   h.gain = gb.x; h.bias = gb.y;
   h.p0 = static_cast<uint32_t>(m.x); h.p1 = static_cast<uint32_t>(m.y);
   h.cbase = static_cast<uint32_t>(m.w);  // computed by the producer (modulo 2^32 on purpose)
-  if (RM) {
+  if (RM == 3) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { const float4 q = f.rf[a]; h.vl[a] = q.x; h.vh[a] = q.y; }
+    const float4 ws = f.ws;
+    h.wb = ws.x; h.po = ws.y;
+  } else if (RM) {
     h.rmask = m.z & 0xff; h.pad = m.z >> 8;
     const float4 rb = f.rb;
     h.rB[0] = rb.x; h.rB[1] = rb.y; h.rB[2] = rb.z;
@@ -451,7 +460,15 @@ __device__ __forceinline__ void k1_fast_coords(const K1Hot<RM>& h, float fj, flo
 struct K1Vox {
   float r0, r1, r2;
   uint32_t a;  // shared-memory byte address of tap (0,0,0)
+  float w;     // RM 3: sum of the trilinear weights of the valid taps
 };
+
+// Sum of the two tap weights along one axis that fall on valid cells: 1 inside, a linear ramp over
+// the first / last cell, 0 outside — a trapezoid of the coordinate (the valid region is a box, so
+// the 3-D sum is the product of the three).
+__device__ __forceinline__ float k1_valid_weight(float v, float vl, float vh) {
+  return fminf(1.0f, fmaxf(fminf(v - vl, vh - v), 0.0f));
+}
 
 template <int RM>
 __device__ __forceinline__ K1Vox k1_fast_vox(const K1Hot<RM>& h, float fj) {
@@ -462,6 +479,7 @@ __device__ __forceinline__ K1Vox k1_fast_vox(const K1Hot<RM>& h, float fj) {
   K1Vox x;
   x.r0 = v0 - (t0 - K1_MAGIC); x.r1 = v1 - (t1 - K1_MAGIC); x.r2 = v2 - (t2 - K1_MAGIC);
   x.a = h.cbase + 4u * (__float_as_uint(t0) * h.p0 + __float_as_uint(t1) * h.p1 + __float_as_uint(t2));
+  if (RM == 3) x.w = k1_valid_weight(v0, h.vl[0], h.vh[0]) * k1_valid_weight(v1, h.vl[1], h.vh[1]) * k1_valid_weight(v2, h.vl[2], h.vh[2]);
   return x;
 }
 
@@ -545,12 +563,14 @@ __device__ __forceinline__ k1_f2 f2_abs(k1_f2 a) { return a & 0x7fffffff7fffffff
 struct K1Vox2 {
   k1_f2 r0, r1, r2;
   uint32_t aA, aB;  // shared-memory byte addresses of tap (0,0,0) of the two voxels
+  k1_f2 w;          // RM 3: valid-weight sums of the two voxels
 };
 template <int RM>
 struct K1Hot2 {
   k1_f2 D1[3], P[3];
   k1_f2 inv2S, hinv, twoS, rA, rB;   // RM == 1: reflection fold of source axis 2
   float Sm1;
+  k1_f2 vl[3], vh[3];                // RM == 3: valid tap interval per axis
 };
 template <int RM>
 __device__ __forceinline__ K1Vox2 k1_fast_vox2(const K1Hot<RM>& h, const K1Hot2<RM>& q, k1_f2 fj2) {
@@ -573,6 +593,19 @@ __device__ __forceinline__ K1Vox2 k1_fast_vox2(const K1Hot<RM>& h, const K1Hot2<
   f2_unpack(t0, t0a, t0b); f2_unpack(t1, t1a, t1b); f2_unpack(t2, t2a, t2b);
   x.aA = h.cbase + 4u * (__float_as_uint(t0a) * h.p0 + __float_as_uint(t1a) * h.p1 + __float_as_uint(t2a));
   x.aB = h.cbase + 4u * (__float_as_uint(t0b) * h.p0 + __float_as_uint(t1b) * h.p1 + __float_as_uint(t2b));
+  if (RM == 3) {  // valid-weight product, the subtractions packed, min / max per lane
+    float wa = 1.0f, wb = 1.0f;
+    const k1_f2 vv[3] = {v0, v1, v2};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float la, lb, ha, hb;
+      f2_unpack(f2_sub(vv[a], q.vl[a]), la, lb);
+      f2_unpack(f2_sub(q.vh[a], vv[a]), ha, hb);
+      wa *= fminf(1.0f, fmaxf(fminf(la, ha), 0.0f));
+      wb *= fminf(1.0f, fmaxf(fminf(lb, hb), 0.0f));
+    }
+    x.w = f2_pack(wa, wb);
+  }
   return x;
 }
 __device__ __forceinline__ k1_f2 k1_lerp8x2(const K1Vox2& x, const k1_f2* t) {
@@ -600,6 +633,12 @@ __device__ __forceinline__ void k1_tile_staged_trilinear(const K1Fast& f) {
   if (RMASK == 1) {
     q.inv2S = f2_dup(h.inv2S[2]); q.hinv = f2_dup(h.hinv[2]); q.twoS = f2_dup(h.twoS[2]);
     q.rA = f2_dup(h.rA[2]); q.rB = f2_dup(h.rB[2]); q.Sm1 = h.Sm1[2];
+  }
+  k1_f2 WB2 = 0, PO2 = 0;
+  if (RMASK == 3) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { q.vl[a] = f2_dup(h.vl[a]); q.vh[a] = f2_dup(h.vh[a]); }
+    WB2 = f2_dup(h.wb); PO2 = f2_dup(h.po);
   }
 #pragma unroll 1
   for (int di = (threadIdx.x >> 5) % K1_GWARPS; di < T0; di += K1_GWARPS) {
@@ -633,7 +672,8 @@ __device__ __forceinline__ void k1_tile_staged_trilinear(const K1Fast& f) {
 #pragma unroll
       for (int u = 0; u < NP; ++u) {
         float za, zb;
-        f2_unpack(f2_fma(k1_lerp8x2(x[u], t[u]), G2, B2), za, zb);
+        // RM 3: gain * sum(w v) + (pre_o post_s) * sum(w valid) + post_o
+        f2_unpack(f2_fma(k1_lerp8x2(x[u], t[u]), G2, RMASK == 3 ? f2_fma(x[u].w, WB2, PO2) : B2), za, zb);
         p[(2 * u) * pstep] = za;
         p[(2 * u + 1) * pstep] = zb;
       }
@@ -646,7 +686,7 @@ __device__ __forceinline__ void k1_tile_staged_trilinear(const K1Fast& f) {
       float t[8];
       t[0] = lds_f32(x.a); t[1] = lds_f32(x.a + 4); t[2] = lds_f32(x.a + o1); t[3] = lds_f32(x.a + o1 + 4);
       t[4] = lds_f32(x.a + o0); t[5] = lds_f32(x.a + o0 + 4); t[6] = lds_f32(x.a + o0 + o1); t[7] = lds_f32(x.a + o0 + o1 + 4);
-      *p = fmaf(k1_lerp8(x, t), h.gain, h.bias);
+      *p = fmaf(k1_lerp8(x, t), h.gain, RMASK == 3 ? fmaf(x.w, h.wb, h.po) : h.bias);
       p += pstep;
       fj += fstep;
     }
@@ -683,6 +723,10 @@ __device__ __forceinline__ void k1_tile_staged_nearest(const K1Ctx& c, const K1T
       } else {
         const uint32_t a = h.cbase + 4u * (__float_as_uint(t0) * h.p0 + __float_as_uint(t1) * h.p1 + __float_as_uint(t2));
         val = fmaf(lds_f32(a), h.gain, h.bias);
+        if (RMASK == 3) {  // an invalid (zero-filled) tap is a literal 0 of the padded volume: no pre offset
+          const bool ok = (n0 > h.vl[0]) & (n0 < h.vh[0]) & (n1 > h.vl[1]) & (n1 < h.vh[1]) & (n2 > h.vl[2]) & (n2 < h.vh[2]);
+          if (!ok) val = h.po;
+        }
       }
       *p = val;
       p += pstep;
@@ -952,7 +996,13 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
 #pragma unroll
     for (int g = 0; g < 4; ++g) f.eg[g][a] = egv[g];
     // clamp just below S-1 (one ulp): floor(u') + 1 <= S-1, the lerp error is <= 2^-23 of the step
-    f.rf[a] = make_float4(0.5f / c.Sf[a], 2.0f * c.Sf[a], c.Sm1[a] > 0.0f ? __uint_as_float(__float_as_uint(c.Sm1[a]) - 1u) : 0.0f, rA);
+    if (rm) {
+      f.rf[a] = make_float4(0.5f / c.Sf[a], 2.0f * c.Sf[a], c.Sm1[a] > 0.0f ? __uint_as_float(__float_as_uint(c.Sm1[a]) - 1u) : 0.0f, rA);
+    } else {
+      // box-local interval [m_lo, m_hi] of the valid taps (m = msign * t + mconst, t in [tlo, thi - 1])
+      const int ma = msign * c.tlo[a] + mconst, mb = msign * (c.thi[a] - 1) + mconst;
+      f.rf[a] = make_float4(static_cast<float>(min(ma, mb) - 1), static_cast<float>(max(ma, mb) + 1), 0.0f, 0.0f);
+    }
     if (a == 2) {  // alignment slack columns of the tensor map that fall inside this box
       tl.fix_lo = max(0, -mo);
       tl.fix_hi = it.fp_fix > 0 ? min(it.tmap_box[2], it.fp_fix - mo) : 0;
@@ -971,6 +1021,7 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
     f.m = make_int4(static_cast<int>(p0), static_cast<int>(p1), rmask | (it.padding << 8),
                     static_cast<int>(box_addr - 4u * (K1_MAGIC_BITS * (p0 + p1 + 1u))));
     f.rb = make_float4(rB0, rB1, rB2, tie);
+    f.ws = make_float4(c.pre_o * it.post_scale, it.post_offset, 0.0f, 0.0f);
     f.fl = make_int4((padded || it.noise != nullptr || philox) ? 1 : 0, padded ? 1 : 0, philox, 0);
     f.vlo = make_int4(vl0, vl1, vl2, 0);
     f.vhi = make_int4(vh0, vh1, vh2, 0);
@@ -1200,20 +1251,26 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
       const bool strict = (it.flags & ADELL_F_STRICT) != 0;
       k1_for_each_voxel(tl, it, [&](int, int, int, int o0, int o1, int o2) { k1_finish(it, 0.0f, o0, o1, o2, strict); });
     } else if (mode == MODE_STAGED) {
-      const bool exact = (it.flags & (ADELL_F_STRICT | ADELL_F_CLIP)) != 0 || (ctx.pre_o != 0.0f && !tl.all_valid);
+      // a pre offset must not leak into zero-filled (invalid) taps: the fast loops then scale it by the
+      // sum of the valid tap weights (variant 3); where that is not available, the exact path
       const K1Fast& f = slots[slot].fast;
+      const bool leak = ctx.pre_o != 0.0f && !tl.all_valid;
+      const bool exact = (it.flags & (ADELL_F_STRICT | ADELL_F_CLIP)) != 0 || (leak && (tl.rmask != 0 || f.fl.x));
       if (exact) k1_tile_exact_dispatch<SmemTaps, false>(ctx, tl, box);
       else if (f.fl.x) k1_tile_staged_cold(ctx, tl, f, box);
       else {
-        // block-uniform variant: 0 = no padding arithmetic, 1 = reflection on the thin axis only, 2 = general
-        const int rm = tl.rmask == 0 ? 0 : ((tl.rmask == 4 && it.padding == ADELL_PAD_REFLECTION) ? 1 : 2);
+        // block-uniform variant: 0 = no padding arithmetic, 1 = reflection on the thin axis only, 2 = general,
+        // 3 = no padding arithmetic but invalid taps under a pre offset (valid-weight sum)
+        const int rm = tl.rmask == 0 ? (leak ? 3 : 0) : ((tl.rmask == 4 && it.padding == ADELL_PAD_REFLECTION) ? 1 : 2);
         if (it.interp == ADELL_NEAREST) {
           if (rm == 0) k1_tile_staged_nearest<0>(ctx, tl, f, box);
           else if (rm == 1) k1_tile_staged_nearest<1>(ctx, tl, f, box);
+          else if (rm == 3) k1_tile_staged_nearest<3>(ctx, tl, f, box);
           else k1_tile_staged_nearest<2>(ctx, tl, f, box);
         } else {
           if (rm == 0) k1_tile_staged_trilinear<K1_NP, 0>(f);
           else if (rm == 1) k1_tile_staged_trilinear<K1_NP, 1>(f);
+          else if (rm == 3) k1_tile_staged_trilinear<K1_NP, 3>(f);
           else k1_tile_staged_trilinear_scalar<K1_NV, 2>(f);
         }
       }

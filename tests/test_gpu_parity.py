@@ -74,6 +74,27 @@ def test_default_mode_nearest_is_bit_exact_at_benchmark_sizes(shape, padding):
         assert mismatch(out, ref) == 0, (shape, padding, i)
 
 
+@pytest.mark.parametrize("mode", ["nearest", "bilinear"])
+@pytest.mark.parametrize("shape", [(96, 80, 48), (64, 200, 32)])
+def test_pre_offset_does_not_leak_into_zero_padding(shape, mode):
+    """Intensity map with an offset BEFORE a zeros-padded resample (percentile / min-max scaling folded
+    into the gather): out-of-volume taps are literal zeros of the padded volume, so the offset only
+    counts with the weights of the valid taps.  Tiles that straddle the volume edge take the fast
+    loops' valid-weight variant; far translations make most tiles straddle or miss the volume."""
+    R = np.random.RandomState(17)
+    img = torch.from_numpy((R.rand(1, *shape) * 5).astype(np.int32).astype(np.float32))
+    for i in range(4):
+        A = rand_affine_matrix(R, rotate=(np.pi / 8, np.pi / 8, np.pi / 16), translate=(30, 25, 12), scale=(0.15, 0.15, 0.1))
+        pre = (img * np.float32(1.25) + np.float32(0.75)).to(torch.float32)
+        ref = M.affine_resample(pre, A, mode, "zeros")[0]
+        plan = BatchPlan([img[0].to(DEV)]).intensity(scale=1.25, offset=0.75).affine(A.numpy(), mode, "zeros")
+        out = run_plan_cuda(plan)[0].cpu()
+        if mode == "nearest":
+            assert mismatch(out, ref) == 0, (shape, i)
+        else:
+            assert float((out - ref).abs().max()) <= 1e-4 * float(ref.abs().max()), (shape, i)
+
+
 @pytest.mark.parametrize("padding,mode", [("zeros", "nearest"), ("reflection", "nearest"), ("border", "bilinear"), ("zeros", "bilinear")])
 def test_config_e_volume_against_oracle(padding, mode):
     """Config E size (512x512x128, 134 MB): 16 column groups of sheared tiles, coordinates up to 512
