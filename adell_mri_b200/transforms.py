@@ -355,7 +355,7 @@ class ExposeTransformKeyMetad(Transform):
 
     def __init__(self, key: str, transform_class: str, nested_pattern: Sequence[str], output_key: str | None = None):
         self.key, self.transform_class, self.nested_pattern = key, transform_class, list(nested_pattern)
-        self.output_key = output_key if output_key is not None else "_".join([key, transform_class])
+        self.output_key = output_key if output_key is not None else "box_" + key   # the reference's default
 
     def __call__(self, data):
         d = dict(data)

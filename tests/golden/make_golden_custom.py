@@ -67,6 +67,13 @@ def ramp(shape, mod=251):
     return (np.arange(int(np.prod(shape)), dtype=np.int64) % mod).astype(np.float32).reshape(shape)
 
 
+def expose_ops():
+    return [{"class": "SpatialPad", "extra_info": {"padded": [[0, 0], [1, 1]]}},
+            {"class": "RandSpatialCrop", "extra_info": {"cropped": [3, 5, 0, 8, 2, 2]}},
+            {"class": "RandFlip", "extra_info": {}},
+            {"class": "RandSpatialCrop", "extra_info": {"cropped": [1, 4, 2, 6, 0, 3]}}]
+
+
 def main():
     I, Gm, Im = load_reference()
     out = {}
@@ -82,6 +89,14 @@ def main():
     d = Gm.CopyEntryd(["x"], {"x": "x_copy"})({"x": torch.from_numpy(x.copy()), "other": 3})
     out["copy/x_copy"] = d["x_copy"].numpy()
     out["copy/keys"] = np.array(sorted(d.keys()))
+    # ExposeTransformKeyMetad on an object that carries MONAI-style applied_operations (two crops: the last wins)
+    ops = expose_ops()
+    holder = types.SimpleNamespace(applied_operations=ops)
+    d = Gm.ExposeTransformKeyMetad("image", "RandSpatialCrop", ["extra_info", "cropped"], "box_1")({"image": holder})
+    out["expose/named"] = np.asarray(d["box_1"])
+    d = Gm.ExposeTransformKeyMetad("image", "RandSpatialCrop", ["extra_info", "cropped"])({"image": holder})
+    out["expose/default_keys"] = np.array(sorted(d.keys()))
+    out["expose/default_value"] = np.asarray(d["box_image"])
     # AdjustSizesd, both modes
     for name, shapes in ADJUST_CASES:
         for mode in ("crop", "pad"):

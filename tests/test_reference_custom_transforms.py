@@ -61,6 +61,16 @@ def test_copy_entry(dev):
     assert np.array_equal(_mat(d["x_copy"]), GOLD["copy/x_copy"])
 
 
+def test_expose_transform_key_meta():
+    p = T.Pending(torch.zeros(1, 4, 4, 4))
+    p.meta["applied_operations"] = G.expose_ops()
+    d = T.ExposeTransformKeyMetad("image", "RandSpatialCrop", ["extra_info", "cropped"], "box_1")({"image": p})
+    assert np.array_equal(np.asarray(d["box_1"]), GOLD["expose/named"])
+    d = T.ExposeTransformKeyMetad("image", "RandSpatialCrop", ["extra_info", "cropped"])({"image": p})
+    assert sorted(d.keys()) == list(GOLD["expose/default_keys"])
+    assert np.array_equal(np.asarray(d["box_image"]), GOLD["expose/default_value"])
+
+
 def test_oracle_intensity_restatements_equal_reference_vectors():
     hi, lo = G.volume(1, (1, 12, 10, 6), 2000.0), G.volume(2, (1, 12, 10, 6), 400.0)
     assert np.array_equal(M.conditional_rescaling(torch.from_numpy(hi), 500, 0.001).numpy(), GOLD["condrescale/hi"])
