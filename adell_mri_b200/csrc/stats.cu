@@ -232,6 +232,39 @@ st_mask_bbox(const adell_vol* __restrict__ vols, const int32_t* __restrict__ sha
   }
 }
 
+// Label construction of the cached stage: combine K label maps voxel-wise (any: sum > 0, majority:
+// mean > 0.5, none: the single map as is) and map the values (binary: 1 where the value is one of
+// `table`, categorical: index of the value in `table`, 0 when absent, none: unchanged).
+struct st_label_args {
+  const void* src[8];
+  int32_t dtype[8];
+  float table[16];
+  int32_t n_src, combine, op, n_table;
+};
+__global__ void __launch_bounds__(ST_THREADS)
+st_label_map(const st_label_args a, float* __restrict__ dst, int64_t n) {
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nthr = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = tid; i < n; i += nthr) {
+    float x;
+    if (a.combine == ADELL_LABEL_COMBINE_NONE) {
+      x = adell_load_src(a.src[0], i, a.dtype[0]);
+    } else {
+      float sum = 0.0f;  // torch.stack(...).sum(-1) in fp32, key order
+      for (int k = 0; k < a.n_src; ++k) sum = __fadd_rn(sum, adell_load_src(a.src[k], i, a.dtype[k]));
+      if (a.combine == ADELL_LABEL_COMBINE_ANY) x = sum > 0.0f ? 1.0f : 0.0f;
+      else x = __fdiv_rn(sum, static_cast<float>(a.n_src)) > 0.5f ? 1.0f : 0.0f;
+    }
+    if (a.op != ADELL_LABEL_OP_NONE) {
+      float y = 0.0f;
+      for (int t = 0; t < a.n_table; ++t)
+        if (x == a.table[t]) { y = a.op == ADELL_LABEL_OP_BINARY ? 1.0f : static_cast<float>(t); break; }
+      x = y;
+    }
+    dst[i] = x;
+  }
+}
+
 // monai AdjustContrast: ((x - min) / (range + eps)) ** gamma * range + min, fp32 op by op.
 __global__ void __launch_bounds__(ST_THREADS)
 st_gamma_map(const adell_vol* __restrict__ vols, float* const* __restrict__ dsts, const float* __restrict__ minmax,
@@ -533,6 +566,27 @@ extern "C" int adell_intensity_map(const adell_vol* vols_dev, float* const* dst_
   dim3 grid(st_blocks_per_vol(max_n, n_vols, 16), n_vols);
   st_intensity_map<<<grid, ST_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(vols_dev, dst_dev, coef_dev, clip,
                                                                                 clip_lo, clip_hi);
+  ADELL_CUDA_CHECK_LAUNCH();
+  return ADELL_OK;
+}
+
+extern "C" int adell_label_map(const void* const* src_dev, const int32_t* dtypes, int n_src, int combine, int op,
+                               const float* table, int n_table, float* dst_dev, int64_t n, void* stream) {
+  if (n == 0) return ADELL_OK;
+  if (src_dev == nullptr || dtypes == nullptr || dst_dev == nullptr || n < 0 || n_src < 1 || n_src > 8 || n_table < 0 ||
+      n_table > 16 || combine < 0 || combine > ADELL_LABEL_COMBINE_MAJORITY || op < 0 || op > ADELL_LABEL_OP_CATEGORICAL ||
+      (n_table > 0 && table == nullptr) || (combine == ADELL_LABEL_COMBINE_NONE && n_src != 1))
+    return ADELL_ERR_BAD_ARG;
+  st_label_args a;
+  for (int k = 0; k < 8; ++k) {
+    a.src[k] = k < n_src ? src_dev[k] : nullptr;
+    a.dtype[k] = k < n_src ? dtypes[k] : 0;
+    if (k < n_src && (src_dev[k] == nullptr || dtypes[k] < 0 || dtypes[k] > ADELL_U8)) return ADELL_ERR_BAD_ARG;
+  }
+  for (int t = 0; t < 16; ++t) a.table[t] = t < n_table ? table[t] : 0.0f;
+  a.n_src = n_src; a.combine = combine; a.op = op; a.n_table = n_table;
+  const int blocks = st_blocks_per_vol(n, 1, 16);
+  st_label_map<<<blocks, ST_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(a, dst_dev, n);
   ADELL_CUDA_CHECK_LAUNCH();
   return ADELL_OK;
 }

@@ -73,6 +73,27 @@ def meanstd(vols: Sequence[torch.Tensor], nonzero: bool = False, desc=None, raw_
     return out
 
 
+LABEL_COMBINE = {None: 0, "none": 0, "any": 1, "majority": 2}
+LABEL_OP = {None: 0, "none": 0, "binary": 1, "cat": 2}
+
+
+def label_map(vols: Sequence[torch.Tensor], combine: str | None, op: str | None, table: Sequence[float]) -> torch.Tensor:
+    """Voxel-wise combination of up to 8 label maps (``"any"`` / ``"majority"``; ``None`` for a single
+    map) followed by the label operator (``"binary"``: 1 where the value is in ``table``; ``"cat"``:
+    index of the value in ``table``, else 0).  Returns a new fp32 tensor of the maps' shape."""
+    dev = _check_vols(vols)
+    if any(v.shape != vols[0].shape for v in vols):
+        raise ValueError("label maps must share their shape")
+    n_src = len(vols)
+    ptrs = (C.c_void_p * n_src)(*[v.data_ptr() for v in vols])
+    dts = (C.c_int32 * n_src)(*[_TORCH_TO_ADELL[v.dtype] for v in vols])
+    tab = (C.c_float * max(len(table), 1))(*[float(x) for x in table])
+    out = torch.empty(vols[0].shape, dtype=torch.float32, device=dev)
+    _lib.check(_lib.load().adell_label_map(ptrs, dts, n_src, LABEL_COMBINE[combine], LABEL_OP[op], tab, len(table),
+                                           out.data_ptr(), out.numel(), _stream(dev)), "adell_label_map")
+    return out
+
+
 def mask_bbox(vols: Sequence[torch.Tensor]) -> torch.Tensor:
     """``[n, 6]`` int32 ``{lo0, hi0, lo1, hi1, lo2, hi2}`` (hi exclusive) of the non-zero voxels of each
     contiguous ``[S0, S1, S2]`` volume; an empty mask gives ``lo = INT32_MAX, hi = 0``."""

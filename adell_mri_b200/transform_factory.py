@@ -140,6 +140,53 @@ spatial_augments = ["rotate_x", "rotate_y", "rotate_z", "translate_x", "translat
 FUSED_AUGMENTS = ["gaussian_noise", "shift_intensity", "scale_intensity", *spatial_augments]
 
 
+class CombineBinaryLabelsd(T.Transform):
+    """/root/reference/adell_mri/utils/monai_transforms/labels.py:189-220: voxel-wise ``any`` (sum > 0)
+    or ``majority`` (mean > 0.5) of the binary label maps under ``keys``, written as a float32 map to
+    ``output_key`` (default: the first key).  One pointwise device pass (``adell_label_map``); a
+    cached-stage transform: pending inputs are materialised."""
+
+    def __init__(self, keys, mode: str = "any", output_key: str | None = None):
+        self.keys, self.mode = list(keys), mode
+        self.output_key = self.keys[0] if output_key is None else output_key
+
+    def __call__(self, X):
+        from . import stats
+
+        d = dict(X)
+        vols = [(d[k].tensor() if isinstance(d[k], T.Pending) else d[k]).contiguous() for k in self.keys]
+        if self.mode in ("any", "majority"):
+            d[self.output_key] = stats.label_map(vols, self.mode, None, [])
+        else:   # the reference leaves the stacked maps untouched for other modes
+            d[self.output_key] = torch.stack(vols, -1)
+        return d
+
+
+class LabelOperatorSegmentationd(T.Transform):
+    """labels.py:123-186: ``mode="binary"``: 1 where the value is one of ``positive_labels``;
+    ``mode="cat"``: the index of the value in ``possible_labels`` (0 when absent); any other mode:
+    unchanged.  One pointwise device pass (``adell_label_map``)."""
+
+    def __init__(self, keys, possible_labels, mode: str = "cat", positive_labels=[1], output_keys={}):
+        self.keys, self.possible_labels, self.mode = list(keys), list(possible_labels), mode
+        self.positive_labels, self.output_keys = list(positive_labels), dict(output_keys)
+
+    def __call__(self, data):
+        from . import stats
+
+        d = dict(data)
+        for key in self.keys:
+            out_key = self.output_keys.get(key, key)
+            x = (d[key].tensor() if isinstance(d[key], T.Pending) else d[key]).contiguous()
+            if self.mode == "cat":
+                d[out_key] = stats.label_map([x], None, "cat", self.possible_labels)
+            elif self.mode == "binary":
+                d[out_key] = stats.label_map([x], None, "binary", self.positive_labels)
+            else:
+                d[out_key] = x
+        return d
+
+
 class CropFromMask:
     """``adell_mri.utils.monai_transforms.CropFromMask``
     (/root/reference/adell_mri/utils/monai_transforms/labels.py:412-477): the window is either the
@@ -586,18 +633,20 @@ class SegmentationTransforms(TransformMixin):
         self.all_keys, self.image_keys = list(self.all_keys), list(self.image_keys)
         self.transform_keys = [self.output_image_key]
         self.mask_key = ["mask"] if self.label_keys is not None else []
-        if self.label_keys is not None and list(self.label_keys) != ["mask"]:
-            raise NotImplementedError("label combination (CombineBinaryLabelsd) runs in the cached loading stage: "
-                                      "hand the combined 0/1 label in under the key 'mask'")
 
     def pre_transforms(self):
-        keys = self.all_keys + ([] if self.label_keys is None or "mask" in self.all_keys else ["mask"])
         transforms = _intensity_stage(self.non_adc_keys, self.adc_keys, offset_adc=False)
         if self.pad_size is not None:
-            transforms.append(T.SpatialPadd(keys, self.pad_size))
+            transforms.append(T.SpatialPadd(self.all_keys, self.pad_size))
         if self.crop_size is not None:
-            transforms.append(T.CenterSpatialCropd(keys, self.crop_size))
-        transforms.append(T.EnsureTyped(keys, dtype=torch.float32))
+            transforms.append(T.CenterSpatialCropd(self.all_keys, self.crop_size))
+        transforms.append(T.EnsureTyped(self.all_keys, dtype=torch.float32))
+        if self.label_keys is not None:   # transforms.py:181-194: the label maps become the 0/1 "mask"
+            transforms.extend([
+                CombineBinaryLabelsd(list(self.label_keys), "any", "mask"),
+                LabelOperatorSegmentationd(["mask"], list(self.possible_labels), mode=self.label_mode,
+                                           positive_labels=list(self.positive_labels)),
+            ])
         if self.random_crop_size is not None:
             if self.label_keys is not None:
                 transforms.append(AdjustSizesd([*self.image_keys, "mask"], mode="crop"))

@@ -211,6 +211,20 @@ int adell_meanstd(const adell_vol* vols_dev, int n_vols, int64_t max_n, int nonz
 #define ADELL_MEANSTD_RAW_STD 2 /* bit 1 of `nonzero`: report a zero std as 0 (RandStdShiftIntensityd:
                                    offset = factor * std), not as NormalizeIntensityd's 1             */
 
+/* Label construction of the cached stage (CombineBinaryLabelsd + LabelOperatorSegmentationd,
+ * /root/reference/adell_mri/utils/monai_transforms/labels.py:123-220, called from
+ * transform_factory/transforms.py:181-194): n_src (<= 8) label maps of n elements each
+ * (src_dev / dtypes are HOST arrays of device pointers / ADELL_* dtypes) are combined voxel-wise, then
+ * mapped through `table` (host array, <= 16 values).  dst is fp32. */
+#define ADELL_LABEL_COMBINE_NONE 0     /* one map, as is                                       */
+#define ADELL_LABEL_COMBINE_ANY 1      /* float(sum over the maps > 0)                         */
+#define ADELL_LABEL_COMBINE_MAJORITY 2 /* float(mean over the maps > 0.5)                      */
+#define ADELL_LABEL_OP_NONE 0          /* values unchanged                                     */
+#define ADELL_LABEL_OP_BINARY 1        /* 1 where the value is in table (positive labels)      */
+#define ADELL_LABEL_OP_CATEGORICAL 2   /* index of the value in table (possible labels), else 0 */
+int adell_label_map(const void* const* src_dev, const int32_t* dtypes, int n_src, int combine, int op,
+                    const float* table, int n_table, float* dst_dev, int64_t n, void* stream);
+
 /* Bounding box of the non-zero voxels of each [S0,S1,S2] volume (shapes_dev: 3 int32 per volume):
  * out_dev[6*v ..] = {lo0, hi0, lo1, hi1, lo2, hi2}, hi exclusive; an empty mask yields lo = INT32_MAX,
  * hi = 0.  The reduction behind CropFromMaskd

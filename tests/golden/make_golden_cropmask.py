@@ -81,9 +81,40 @@ def make_sample(spatial, box, n_channels=1):
     return img, mask
 
 
+def label_inputs():
+    """Three label maps with values in {0, 1, 2, 3} (uint8-valued floats), deterministic."""
+    import numpy as np
+    R = np.random.RandomState(4)
+    return [torch.from_numpy((R.rand(1, 9, 8, 7) * 4).astype(np.int64).astype(np.float32) * (R.rand(1, 9, 8, 7) > 0.5)) for _ in range(3)]
+
+
+LABEL_CASES = {  # name -> (combine mode, possible_labels, label mode, positive_labels)
+    "any_binary": ("any", [0, 1], "binary", [1]),
+    "majority_binary": ("majority", [0, 1], "binary", [1]),
+    "any_cat": ("any", [0, 1], "cat", [1]),
+}
+OPERATOR_CASES = {  # applied to the first raw map alone
+    "binary_2_3": ([0, 1, 2, 3], "binary", [2, 3]),
+    "cat_reordered": ([3, 1, 2], "cat", [1]),
+    "passthrough": ([0, 1], None, [1]),
+}
+
+
 def main():
     L = load_reference()
     out = {}
+    import numpy as np
+    lab = {}
+    for name, (comb, possible, mode, positive) in LABEL_CASES.items():
+        a, b, c = label_inputs()
+        d = L.CombineBinaryLabelsd(["a", "b", "c"], comb, "mask")({"a": (a > 0).float(), "b": (b > 0).float(), "c": (c > 0).float()})
+        d = L.LabelOperatorSegmentationd(["mask"], possible, mode=mode, positive_labels=positive)(d)
+        lab[name] = np.asarray(d["mask"], np.float32)
+    for name, (possible, mode, positive) in OPERATOR_CASES.items():
+        a, _, _ = label_inputs()
+        d = L.LabelOperatorSegmentationd(["a"], possible, mode=mode, positive_labels=positive)({"a": a.numpy()})
+        lab["op_" + name] = np.asarray(d["a"], np.float32)
+    np.savez_compressed(os.path.join(HERE, "label_ops.npz"), **lab)
     for name, (spatial, box, osize) in CASES.items():
         img, mask = make_sample(spatial, box)
         t = L.CropFromMaskd(keys=["image", "mask"], mask_key="mask", output_size=osize)

@@ -87,3 +87,42 @@ def test_classification_transforms_mask_crop():
     assert restored.shape == (2, 16, 16, 16)
     assert restored[0].min() >= 0.0 and restored[0].max() <= 1.0
     assert torch.all((restored[1] == 0) | (restored[1] == 1))
+
+
+# ------------------------------------------------------------------ label construction (labels.py:123-220)
+import numpy as np
+
+LAB = np.load(os.path.join(HERE, "golden", "label_ops.npz"))
+
+
+@pytest.mark.parametrize("name", sorted(G.LABEL_CASES))
+def test_combine_and_label_operator_equal_reference_classes(name):
+    comb, possible, mode, positive = G.LABEL_CASES[name]
+    a, b, c = G.label_inputs()
+    d = {"a": (a > 0).float().to(DEV), "b": (b > 0).float().to(DEV), "c": (c > 0).float().to(DEV)}
+    d = F.CombineBinaryLabelsd(["a", "b", "c"], comb, "mask")(d)
+    d = F.LabelOperatorSegmentationd(["mask"], possible, mode=mode, positive_labels=positive)(d)
+    assert np.array_equal(d["mask"].cpu().numpy(), LAB[name])
+
+
+@pytest.mark.parametrize("name", sorted(G.OPERATOR_CASES))
+def test_label_operator_equals_reference_class(name):
+    possible, mode, positive = G.OPERATOR_CASES[name]
+    a, _, _ = G.label_inputs()
+    d = F.LabelOperatorSegmentationd(["a"], possible, mode=mode, positive_labels=positive)({"a": a.to(DEV)})
+    assert np.array_equal(d["a"].cpu().numpy(), LAB["op_" + name])
+
+
+def test_segmentation_factory_builds_the_mask_from_label_keys():
+    """transforms.py:181-194: two label maps -> any -> binary "mask", then the image / mask batch."""
+    R = np.random.RandomState(3)
+    s = {"t2": torch.from_numpy(R.rand(1, 16, 12, 8).astype(np.float32) * 900).to(DEV),
+         "l1": torch.from_numpy((R.rand(1, 16, 12, 8) > 0.8).astype(np.float32)).to(DEV),
+         "l2": torch.from_numpy((R.rand(1, 16, 12, 8) > 0.8).astype(np.float32)).to(DEV)}
+    tf = F.SegmentationTransforms(all_keys=["t2", "l1", "l2"], image_keys=["t2"], label_keys=["l1", "l2"], non_adc_keys=["t2"],
+                                  adc_keys=[], possible_labels=[0, 1], positive_labels=[1], label_mode="binary")
+    out = collate.safe_collate([tf.transforms()(s)])
+    want = ((s["l1"] + s["l2"]) > 0).float()
+    assert sorted(out.keys()) == ["image", "mask"]
+    assert torch.equal(out["mask"][0], want)
+    assert float(out["image"].min()) == 0.0 and float(out["image"].max()) == 1.0

@@ -178,8 +178,7 @@ def test_member_vocabulary_matches_reference():
 # ------------------------------------------------------------------ *Transforms factories (rows a1-a6)
 #: reference entries that belong to the cached loading stage (disk IO, orientation, label
 #: construction): out of the hot path, the product's factories do not emit them
-LOADING_STAGE = {"LoadImaged", "Orientationd", "Spacingd", "ResampleToMatchd", "SampleChannelDimd", "CombineBinaryLabelsd",
-                 "LabelOperatorSegmentationd", "CreateImageAndWeightsd"}
+LOADING_STAGE = {"LoadImaged", "Orientationd", "Spacingd", "ResampleToMatchd", "SampleChannelDimd", "CreateImageAndWeightsd"}
 
 
 def ref_stage_cfg(r):
@@ -213,6 +212,10 @@ def ref_stage_cfg(r):
         return {"cls": cls, "keys": keys, "out_keys": a[1]}
     if cls == "CropFromMaskd":
         return {"cls": cls, "keys": keys, "mask_key": k["mask_key"], "output_size": [int(x) for x in k["output_size"]]}
+    if cls == "CombineBinaryLabelsd":
+        return {"cls": cls, "keys": keys, "mode": a[1], "output_key": a[2]}
+    if cls == "LabelOperatorSegmentationd":
+        return {"cls": cls, "keys": keys, "possible_labels": list(a[1]), "mode": k["mode"], "positive_labels": list(k["positive_labels"])}
     raise AssertionError(f"unexpected reference stage transform {cls}")
 
 
@@ -239,6 +242,10 @@ def our_stage_cfg(t):
         return {"cls": cls, "keys": keys, "out_keys": dict(t.out_keys)}
     if cls == "CropFromMaskd":
         return {"cls": cls, "keys": keys, "mask_key": t.mask_key, "output_size": [int(x) for x in t.output_size]}
+    if cls == "CombineBinaryLabelsd":
+        return {"cls": cls, "keys": keys, "mode": t.mode, "output_key": t.output_key}
+    if cls == "LabelOperatorSegmentationd":
+        return {"cls": cls, "keys": keys, "possible_labels": list(t.possible_labels), "mode": t.mode, "positive_labels": list(t.positive_labels)}
     raise AssertionError(f"unexpected product stage transform {cls}")
 
 
