@@ -1365,6 +1365,37 @@ void k1_item_map(adell_item& it) {
   }
 }
 
+// Tuning / debugging knobs from the environment, read once per process (getenv walks the whole
+// environment: per item it cost more than the policy itself).
+struct K1Tuning {
+  bool no_shear, no_staged;
+  int copy_t0, pref_box, tile_pref, chunk, tail;
+  int64_t tile_cost;
+  K1Tuning() {
+    auto num = [](const char* name, int lo, int hi, int dflt) {
+      const char* e = getenv(name);
+      if (e == nullptr) return dflt;
+      const int v = atoi(e);
+      return (v >= lo && v <= hi) ? v : dflt;
+    };
+    const char* e = getenv("ADELL_K1_NO_SHEAR");
+    no_shear = e != nullptr && e[0] == '1';
+    e = getenv("ADELL_DISABLE_STAGED");                       // debugging aid: force the direct path
+    no_staged = e != nullptr && e[0] == '1';
+    copy_t0 = num("ADELL_K1_COPY_T0", 8, 32, K1_COPY_T0);
+    if (copy_t0 != 8 && copy_t0 != 16 && copy_t0 != 32) copy_t0 = K1_COPY_T0;
+    pref_box = num("ADELL_K1_PREF_BOX", 1024, K1_MAX_BOX_BYTES, -1);
+    tile_pref = num("ADELL_K1_TILE", 0, 3, -1);               // 0 = 16x16x32, 1 = 16x32x16, 2 = 8x16x32, 3 = 16x16x16 only
+    chunk = num("ADELL_K1_CHUNK", 1, 64, 4);
+    tail = num("ADELL_K1_TAIL", 0, 64, 3);
+    tile_cost = num("ADELL_K1_TILE_COST", 0, 1 << 30, 3072);
+  }
+};
+const K1Tuning& k1_tuning() {
+  static const K1Tuning t;
+  return t;
+}
+
 // Column-group shear of the tile grid.  A tile spans 16 or 32 voxels of axis 2 (the lanes); under a
 // rotation that couples axis 2 into source axes 0/1 (a thin volume tilted about an in-plane axis)
 // the footprint of such a column is slanted and its bounding box mostly empty.  Shifting the
@@ -1375,8 +1406,7 @@ void k1_item_map(adell_item& it) {
 // shifted grid).  Returns true when a non-trivial shear was written to it.shear.
 bool k1_item_shear(adell_item& it) {
   memset(it.shear, 0, sizeof(it.shear));
-  const char* e = getenv("ADELL_K1_NO_SHEAR");  // tuning / debugging aid
-  if (e != nullptr && e[0] == '1') return false;
+  if (k1_tuning().no_shear) return false;
   const int nG = (it.out_shape[2] + 7) >> 3;
   if (nG < 2 || nG > 16) return false;
   const double* D = it.fp_D;
@@ -1508,10 +1538,37 @@ int k1_encode_tmap(adell_item& it, const K1Layout& L, const int* box, EncodeTile
   const cuuint32_t bdim[3] = {static_cast<cuuint32_t>(box[2]), static_cast<cuuint32_t>(box[1]), static_cast<cuuint32_t>(box[0])};
   const cuuint32_t estr[3] = {1, 1, 1};
   if (enc == nullptr) return -1;
+  // A device-resident cache hands the same volumes back every epoch, and the map only depends on the
+  // memory-order layout of the valid source box (flips are signs in the box index): remember the last
+  // encodings per host thread instead of asking the driver again (~0.4 us each, 32 per step).
+  struct Entry { uintptr_t base; cuuint64_t gdim[3], gstride[2]; cuuint32_t box[3]; bool valid; uint8_t map[128]; };
+  constexpr int kEntries = 2048;
+  static thread_local Entry* cache = nullptr;
+  if (cache == nullptr) cache = static_cast<Entry*>(calloc(kEntries, sizeof(Entry)));
+  Entry* e = nullptr;
+  if (cache != nullptr) {
+    uint64_t h = (L.base >> 4) * 0x9E3779B97F4A7C15ull ^ (L.gdim[0] * 31 + L.gdim[1] * 131 + L.gdim[2] * 1031 + bdim[0] * 7 + bdim[1] * 11 + bdim[2] * 13);
+    e = cache + (h >> 40) % kEntries;
+    if (e->valid && e->base == L.base && e->gdim[0] == L.gdim[0] && e->gdim[1] == L.gdim[1] && e->gdim[2] == L.gdim[2] &&
+        e->gstride[0] == L.gstride[0] && e->gstride[1] == L.gstride[1] && e->box[0] == bdim[0] && e->box[1] == bdim[1] &&
+        e->box[2] == bdim[2]) {
+      memcpy(it.tmap, e->map, 128);
+      it.tmap_base = reinterpret_cast<const void*>(L.base);
+      it.flags |= ADELL_F_TMAP;
+      return 1;
+    }
+  }
   CUresult r = enc(reinterpret_cast<CUtensorMap*>(it.tmap), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
                    reinterpret_cast<void*>(L.base), L.gdim, L.gstride, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, K1_L2_PROMO, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return 0;
+  if (e != nullptr) {
+    e->base = L.base;
+    for (int i = 0; i < 3; ++i) { e->gdim[i] = L.gdim[i]; e->box[i] = bdim[i]; }
+    e->gstride[0] = L.gstride[0]; e->gstride[1] = L.gstride[1];
+    memcpy(e->map, it.tmap, 128);
+    e->valid = true;
+  }
   it.tmap_base = reinterpret_cast<const void*>(L.base);
   it.flags |= ADELL_F_TMAP;
   return 1;
@@ -1520,8 +1577,7 @@ int k1_encode_tmap(adell_item& it, const K1Layout& L, const int* box, EncodeTile
 // Identity item: tensor map for the 32x16x32 box copy.  Returns the box bytes (0 = not eligible).
 int k1_encode_copy(adell_item& it, EncodeTiledFn enc) {
   if (!k1_vcopy_ok(it)) return 0;
-  int T[3] = {K1_COPY_T0, 16, 32};
-  if (const char* e = getenv("ADELL_K1_COPY_T0")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32) T[0] = v; }  // tuning aid
+  int T[3] = {k1_tuning().copy_t0, 16, 32};
   int box[3] = {T[0], T[1], T[2]};
   K1Layout L;
   if (!k1_tmap_layout(it, L)) return 0;
@@ -1561,12 +1617,10 @@ int k1_encode_item(adell_item& it, EncodeTiledFn enc, int tile_pref) {
   // worth ~3000 voxels, measured); ties go to the shape listed first.  Only when none fits, the same
   // choice among the boxes that fit twice.
   static const int kShapes[4][3] = {{16, 16, 32}, {16, 32, 16}, {8, 16, 32}, {16, 16, 16}};
-  int pref_bytes = k1_pref_box_bytes();
-  if (const char* pe = getenv("ADELL_K1_PREF_BOX")) { const int v = atoi(pe); if (v >= 1024 && v <= K1_MAX_BOX_BYTES) pref_bytes = v; }
+  const int pref_bytes = k1_tuning().pref_box > 0 ? k1_tuning().pref_box : k1_pref_box_bytes();
   int box[3] = {0, 0, 0}, T[3] = {16, 16, 16};
   int64_t bytes = 0;
-  int64_t tile_cost = 3072;
-  if (const char* ce = getenv("ADELL_K1_TILE_COST")) { const int v = atoi(ce); if (v >= 0) tile_cost = v; }  // tuning aid
+  const int64_t tile_cost = k1_tuning().tile_cost;
   for (int pass = 0; pass < 2 && bytes == 0; ++pass) {
     const int limit = pass == 0 ? pref_bytes : K1_MAX_BOX_BYTES;
     int64_t best_cover = -1;
@@ -1616,10 +1670,8 @@ extern "C" int adell_aug_prepare(adell_item* items_host, int n_items, int32_t* t
   int smem = 0, staged = 0;
   EncodeTiledFn enc = nullptr;
   bool enc_tried = false;
-  const char* dis = getenv("ADELL_DISABLE_STAGED");  // debugging aid: force the direct path
-  const bool no_staged = dis != nullptr && dis[0] == '1';
-  const char* tp = getenv("ADELL_K1_TILE");          // tuning aid: 0 = 16x16x32, 1 = 16x32x16, 2 = 8x16x32, 3 = 16x16x16 only
-  const int tile_pref = (tp != nullptr && tp[0] >= '0' && tp[0] <= '3') ? tp[0] - '0' : -1;
+  const bool no_staged = k1_tuning().no_staged;
+  const int tile_pref = k1_tuning().tile_pref;
   for (int i = 0; i < n_items; ++i) {
     adell_item& it = items_host[i];
     int st = k1_validate(it);
@@ -1701,12 +1753,10 @@ extern "C" int adell_aug_gather(const adell_item* items_dev, const int32_t* tile
   if (e != cudaSuccess) { (void)cudaGetLastError(); return adell_map_cuda_error(e); }
   // consecutive tiles a producer takes from the queue at a time (they share the item and neighbouring
   // source boxes): small enough that the tail of the launch stays balanced
-  int chunk = 4;
-  if (const char* ce = getenv("ADELL_K1_CHUNK")) { const int v = atoi(ce); if (v >= 1 && v <= 64) chunk = v; }
+  const int chunk = k1_tuning().chunk;
   // the last ~3 tiles per stream are handed out one by one
   const int64_t streams = static_cast<int64_t>(sms) * K1_GROUPS;
-  int64_t tail = 3 * streams;
-  if (const char* te = getenv("ADELL_K1_TAIL")) { const int v = atoi(te); if (v >= 0 && v <= 64) tail = v * streams; }
+  const int64_t tail = k1_tuning().tail * streams;
   const int64_t n_big = info->total_tiles > tail ? (info->total_tiles - tail) / chunk : 0;
   const int64_t n_units = n_big + (info->total_tiles - n_big * chunk);
   const int64_t n_ctas = (n_units + K1_GROUPS - 1) / K1_GROUPS;
