@@ -201,7 +201,7 @@ class CpuReference:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=None, help="default: 1000 (b200 arm), 40 (reference arm: ~0.3 s of host work per step)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="seg", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -210,6 +210,8 @@ def main():
     ap.add_argument("--cache-samples", type=int, default=32)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.steps is None:
+        args.steps = 40 if args.impl == "reference" else 1000
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
