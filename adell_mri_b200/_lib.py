@@ -83,7 +83,7 @@ assert ITEM_SIZE == 640, ITEM_SIZE
 class LaunchInfo(C.Structure):
     """Mirror of ``adell_launch_info``."""
 
-    _fields_ = [("total_tiles", C.c_int64), ("smem_bytes", C.c_int32), ("n_staged", C.c_int32)]
+    _fields_ = [("total_tiles", C.c_int64), ("smem_bytes", C.c_int32), ("n_staged", C.c_int32), ("first_copy_tile", C.c_int64)]
 
 
 class Vol(C.Structure):
@@ -126,7 +126,7 @@ _SIGNATURES = {
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 _lib = None
 
 

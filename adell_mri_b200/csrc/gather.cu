@@ -1122,7 +1122,8 @@ struct K1Ring {
 
 __global__ void __launch_bounds__(K1_THREADS, 1)
 k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile_start, int n_items, int total_tiles,
-          int n_stages, int stage_bytes, int chunk, int n_big, unsigned int* __restrict__ sched) {
+          int n_stages, int stage_bytes, int chunk, int n_big_r, int n_big_c, int first_copy,
+          unsigned int* __restrict__ sched) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int n_slots = n_stages + K1_GROUPS;
   K1Slot* slots = reinterpret_cast<K1Slot*>(smem + static_cast<size_t>(n_stages) * stage_bytes);
@@ -1158,20 +1159,34 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
     int next_start = ts[1];
     int acq_item = -1;                  // item whose tensor map this warp acquired last
     int64_t cur = 0, cur_end = 0;       // tiles left of the current chunk
+    // Two queues: 0 = tiles of resampled / generic items [0, first_copy), 1 = tiles of box-copy items
+    // [first_copy, total).  Stream 0 drains the resampled queue first, stream 1 the copy queue, each
+    // moving on to the other queue when its own is empty: most of the time an SM then works on a
+    // compute-bound and a memory-bound tile at once instead of all SMs going through the same phases.
+    int q = strm & 1;
+    bool switched = false;
     K1_PROF_DECL
     for (;; rs.next(), rl.next()) {
       const int stage = strm + K1_GROUPS * rs.i, slot = strm + K1_GROUPS * rl.i;
       K1_PROF_T0
-      if (cur >= cur_end) {             // next chunk from the global queue
+      while (cur >= cur_end) {          // next unit from the current queue, or from the other one
         unsigned int c = 0;
-        if (lane == 0) c = atomicAdd(sched, 1u);
+        if (lane == 0) c = atomicAdd(sched + q, 1u);
         c = __shfl_sync(0xffffffffu, c, 0);
-        // the first n_big queue entries are chunks of `chunk` tiles, the rest single tiles (balanced tail)
-        if (c < static_cast<unsigned int>(n_big)) { cur = static_cast<int64_t>(c) * chunk; cur_end = cur + chunk; }
-        else { cur = static_cast<int64_t>(n_big) * chunk + (c - static_cast<unsigned int>(n_big)); cur_end = cur + 1; }
-        cur_end = min(cur_end, static_cast<int64_t>(total_tiles));
+        const int64_t lo = q == 0 ? 0 : first_copy, hi = q == 0 ? first_copy : total_tiles;
+        const unsigned int nb = static_cast<unsigned int>(q == 0 ? n_big_r : n_big_c);
+        // the first nb units of a queue are chunks of `chunk` tiles, the rest single tiles (balanced tail)
+        if (c < nb) { cur = lo + static_cast<int64_t>(c) * chunk; cur_end = cur + chunk; }
+        else { cur = lo + static_cast<int64_t>(nb) * chunk + (c - nb); cur_end = cur + 1; }
+        cur_end = min(cur_end, hi);
+        if (cur < hi) break;
+        if (switched) { cur = cur_end = total_tiles; break; }   // both queues drained
+        switched = true;
+        q ^= 1;
+        item = 0; cur_start = 0; next_start = ts[1];            // the other queue's tiles may lie behind: restart the walk
+        cur = cur_end = 0;
       }
-      if (cur >= total_tiles) {         // queue drained: end-of-stream marker
+      if (cur >= total_tiles || cur >= cur_end) {         // queues drained: end-of-stream marker
         if (lane == 0) slots[slot].tl.mode = MODE_DONE;
         __syncwarp();
         mbar_wait_relaxed(empty + stage, rs.phase ^ 1);
@@ -1203,8 +1218,8 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
     }
     // the last producer of the grid to drain the queue re-arms it for the next launch of this buffer
     if (lane == 0) {
-      const unsigned int done = atomicAdd(sched + 1, 1u);
-      if (done == K1_GROUPS * gridDim.x - 1) { sched[0] = 0u; sched[1] = 0u; }
+      const unsigned int done = atomicAdd(sched + 2, 1u);
+      if (done == K1_GROUPS * gridDim.x - 1) { sched[0] = 0u; sched[1] = 0u; sched[2] = 0u; }
     }
     K1_PROF_FLUSH
     return;
@@ -1701,13 +1716,37 @@ extern "C" int adell_aug_prepare(adell_item* items_host, int n_items, int32_t* t
       it.n_tiles[a] = (ext + it.tile_dim[a] - 1) / it.tile_dim[a];
       n *= it.n_tiles[a];
     }
-    tile_start_host[i] = static_cast<int32_t>(acc);
+    tile_start_host[i] = static_cast<int32_t>(n);  // tile count for now; the prefix follows the reordering
     acc += n;
     if (acc > 0x7fffffffLL) return ADELL_ERR_BAD_ARG;
   }
+  // Identity (box-copy) items go behind the others (stable): tiles [0, first_copy) then feed the
+  // "resampled" queue and the rest the "copy" queue, so that every SM can keep a compute-bound and a
+  // memory-bound tile in flight at once.  Items are independent: their order does not matter.
+  int n_copy = 0;
+  for (int i = 0; i < n_items; ++i) n_copy += items_host[i].kind == ADELL_KIND_VCOPY;
+  if (n_copy > 0 && n_copy < n_items) {
+    adell_item* tmp = static_cast<adell_item*>(malloc(sizeof(adell_item) * static_cast<size_t>(n_items)));
+    int32_t* cnt = static_cast<int32_t*>(malloc(sizeof(int32_t) * static_cast<size_t>(n_items)));
+    if (tmp == nullptr || cnt == nullptr) { free(tmp); free(cnt); return ADELL_ERR_BAD_ARG; }
+    int w = 0;
+    for (int pass = 0; pass < 2; ++pass)
+      for (int i = 0; i < n_items; ++i)
+        if ((items_host[i].kind == ADELL_KIND_VCOPY) == (pass == 1)) { memcpy(tmp + w, items_host + i, sizeof(adell_item)); cnt[w++] = tile_start_host[i]; }
+    memcpy(items_host, tmp, sizeof(adell_item) * static_cast<size_t>(n_items));
+    memcpy(tile_start_host, cnt, sizeof(int32_t) * static_cast<size_t>(n_items));
+    free(tmp); free(cnt);
+  }
+  int64_t run = 0, first_copy = -1;
+  for (int i = 0; i < n_items; ++i) {
+    if (first_copy < 0 && items_host[i].kind == ADELL_KIND_VCOPY) first_copy = run;
+    const int32_t n = tile_start_host[i];
+    tile_start_host[i] = static_cast<int32_t>(run);
+    run += n;
+  }
   tile_start_host[n_items] = static_cast<int32_t>(acc);
-  tile_start_host[n_items + 1] = 0;  // chunk queue of the launch (see adell_aug_gather)
-  tile_start_host[n_items + 2] = 0;
+  for (int q = 1; q <= 4; ++q) tile_start_host[n_items + q] = 0;  // chunk queues of the launch (see adell_aug_gather)
+  info->first_copy_tile = first_copy < 0 ? acc : first_copy;
   info->total_tiles = acc;
   info->smem_bytes = smem;
   info->n_staged = staged;
@@ -1754,18 +1793,24 @@ extern "C" int adell_aug_gather(const adell_item* items_dev, const int32_t* tile
   // consecutive tiles a producer takes from the queue at a time (they share the item and neighbouring
   // source boxes): small enough that the tail of the launch stays balanced
   const int chunk = k1_tuning().chunk;
-  // the last ~3 tiles per stream are handed out one by one
+  // the last ~3 tiles per stream of each queue are handed out one by one
   const int64_t streams = static_cast<int64_t>(sms) * K1_GROUPS;
   const int64_t tail = k1_tuning().tail * streams;
-  const int64_t n_big = info->total_tiles > tail ? (info->total_tiles - tail) / chunk : 0;
-  const int64_t n_units = n_big + (info->total_tiles - n_big * chunk);
+  const int64_t first_copy = info->first_copy_tile < 0 || info->first_copy_tile > info->total_tiles ? info->total_tiles : info->first_copy_tile;
+  const int64_t tiles_q[2] = {first_copy, info->total_tiles - first_copy};
+  int64_t n_big[2], n_units = 0;
+  for (int q = 0; q < 2; ++q) {
+    n_big[q] = tiles_q[q] > tail ? (tiles_q[q] - tail) / chunk : 0;
+    n_units += n_big[q] + (tiles_q[q] - n_big[q] * chunk);
+  }
   const int64_t n_ctas = (n_units + K1_GROUPS - 1) / K1_GROUPS;
   const int64_t grid = n_ctas < sms ? n_ctas : sms;
-  // the two words after the tile prefix are the launch's chunk queue {next chunk, drained producers}:
-  // zero on upload (adell_aug_prepare), re-armed by the kernel itself when it finishes
+  // the words after the tile prefix are the launch's chunk queues {next resampled unit, next copy unit,
+  // drained producers}: zero on upload (adell_aug_prepare), re-armed by the kernel itself when it finishes
   unsigned int* sched = reinterpret_cast<unsigned int*>(const_cast<int32_t*>(tile_start_dev) + n_items + 1);
   k1_gather<<<static_cast<unsigned>(grid), K1_THREADS, static_cast<size_t>(smem), static_cast<cudaStream_t>(stream)>>>(
-      items_dev, tile_start_dev, n_items, static_cast<int>(info->total_tiles), n_stages, stage_bytes, chunk, static_cast<int>(n_big), sched);
+      items_dev, tile_start_dev, n_items, static_cast<int>(info->total_tiles), n_stages, stage_bytes, chunk,
+      static_cast<int>(n_big[0]), static_cast<int>(n_big[1]), static_cast<int>(first_copy), sched);
   ADELL_CUDA_CHECK_LAUNCH();
   return ADELL_OK;
 }

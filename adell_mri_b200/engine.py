@@ -83,7 +83,7 @@ def pack_launch(items: np.ndarray):
     buffer.  Returns ``(uint8 buffer, n_items, LaunchInfo)``."""
     lib = _lib.load()
     n = items.shape[0]
-    buf = np.empty(n * ISZ + 4 * (n + 3), np.uint8)  # items, tile prefix (n + 1), chunk queue (2)
+    buf = np.empty(n * ISZ + 4 * (n + 5), np.uint8)  # items, tile prefix (n + 1), chunk queues (4 words)
     it = buf[: n * ISZ].view(ITEM_DTYPE)
     it[:] = items
     tiles = buf[n * ISZ :].view(np.int32)
@@ -176,9 +176,9 @@ def prepare_steps(plan: BatchPlan, dst_ptr: np.ndarray, dst_stride: np.ndarray, 
     sizes = [int(x) for x in step_sizes]
     if sum(sizes) != items.shape[0]:
         raise ValueError("step_sizes must add up to the number of volumes")
-    # layout per step: items (640 B each) + int32 prefix + 2 chunk-queue words, padded to 128 B so every slice stays aligned
+    # layout per step: items (640 B each) + int32 prefix + 4 chunk-queue words, padded to 128 B so every slice stays aligned
     ns = np.asarray(sizes, np.int64)
-    step_bytes = ns * ISZ + ((4 * (ns + 3) + 127) // 128) * 128
+    step_bytes = ns * ISZ + ((4 * (ns + 5) + 127) // 128) * 128
     offs = np.concatenate([[0], np.cumsum(step_bytes)[:-1]]).astype(np.int64)
     total = int(step_bytes.sum())
     buf = np.zeros(total, np.uint8)
@@ -200,5 +200,5 @@ def prepare_steps(plan: BatchPlan, dst_ptr: np.ndarray, dst_stride: np.ndarray, 
     offs = [int(o) for o in offs]
     with torch.cuda.device(plan.device):
         dev = _stage(buf, plan.device)
-    launches = [(dev[o : o + n * ISZ + 4 * (n + 3)], n, info) for n, o, info in zip(sizes, offs, infos)]
+    launches = [(dev[o : o + n * ISZ + 4 * (n + 5)], n, info) for n, o, info in zip(sizes, offs, infos)]
     return PreparedSteps(launches, [dev, plan, infos_arr] + list(keep or []))

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define ADELL_ABI_VERSION 3
+#define ADELL_ABI_VERSION 4
 
 /* status codes */
 #define ADELL_OK 0
@@ -163,6 +163,10 @@ typedef struct adell_launch_info {
   int64_t total_tiles; /* output tiles over all items (per-item tile extents: adell_item.tile_dim) */
   int32_t smem_bytes;  /* dynamic shared memory = largest staged source box among the items     */
   int32_t n_staged;    /* items eligible for the TMA-staged path                                */
+  int64_t first_copy_tile; /* tiles [0, first_copy_tile) belong to resampled / generic items, the rest to
+                              identity (box-copy) items: adell_aug_prepare moves the copy items behind the
+                              others so that the kernel can run a memory-bound copy tile and a compute-bound
+                              resampled tile side by side on every SM                                   */
 } adell_launch_info;
 
 /* Host-only, no GPU work: validates the items, decides per item whether its source footprint
@@ -170,16 +174,17 @@ typedef struct adell_launch_info {
  * rows, footprint box <= 100 KiB) and if so encodes the CUtensorMap into items_host[i].tmap
  * (+ tmap_off/tmap_sign/tmap_box, ADELL_F_TMAP) via the driver entry point
  * cuTensorMapEncodeTiled (ADELL_ERR_NO_DRIVER if libcuda is unavailable), and fills
- * tile_start_host[0..n_items] with the exclusive prefix of per-item tile counts, followed by two
- * zero words (tile_start_host must hold n_items + 3 entries): the launch's chunk queue, from which
- * the SMs draw their tiles at run time.  The caller then uploads items + prefix + queue words and
+ * tile_start_host[0..n_items] with the exclusive prefix of per-item tile counts, followed by four
+ * zero words (tile_start_host must hold n_items + 5 entries): the launch's two chunk queues
+ * (resampled tiles, copy tiles) from which the SMs draw their tiles at run time.  The items may be
+ * REORDERED in place (identity items last); they are independent, so the result does not change.  The caller then uploads items + prefix + queue words and
  * calls adell_aug_gather; the kernel leaves the queue words zero again, so a buffer can be
  * launched repeatedly (not concurrently with itself). */
 int adell_aug_prepare(adell_item* items_host, int n_items, int32_t* tile_start_host,
                       adell_launch_info* info);
 /* Host-only convenience for several launches packed in one buffer (one upload for many steps):
  * step k has n_items[k] items at buf_host + item_off[k] (64-byte aligned) and its tile prefix
- * (n_items[k] + 3 int32, see adell_aug_prepare) at buf_host + tile_off[k]; runs adell_aug_prepare on each, filling infos[k]. */
+ * (n_items[k] + 5 int32, see adell_aug_prepare) at buf_host + tile_off[k]; runs adell_aug_prepare on each, filling infos[k]. */
 int adell_aug_prepare_steps(void* buf_host, int n_steps, const int32_t* n_items, const int64_t* item_off,
                             const int64_t* tile_off, adell_launch_info* infos);
 /* Enqueue the fused gather over all items: ONE kernel launch per call. */

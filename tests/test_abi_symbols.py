@@ -28,7 +28,7 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 def test_item_layout_and_status_strings():
     lib = _lib.load()
-    assert lib.adell_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.adell_abi_version() == _lib.ABI_VERSION == 4
     assert lib.adell_item_size() == C.sizeof(_lib.Item) == 640
     assert b"no CUDA device" in lib.adell_status_string(-5)
     assert lib.adell_status_string(0) == b"ok"
@@ -51,7 +51,7 @@ def test_mat4_chain_matches_torch_cpu_products():
 def test_prepare_validates_and_never_falls_back():
     lib = _lib.load()
     items = np.zeros(2, np.dtype(_lib.Item))
-    tiles = np.full(5, -1, np.int32)   # tile prefix (n + 1) + the launch's two chunk-queue words
+    tiles = np.full(7, -1, np.int32)   # tile prefix (n + 1) + the launch's four chunk-queue words
     info = _lib.LaunchInfo()
     assert lib.adell_aug_prepare(items.ctypes.data, 2, tiles.ctypes.data, C.byref(info)) == -1  # zero shapes
     # identity items need no TMA descriptor, hence no driver: preparation succeeds on a CPU-only box
@@ -63,4 +63,4 @@ def test_prepare_validates_and_never_falls_back():
         it["grid_sign"] = (1, 1, 1)
         it["flags"] = _lib.F_IDENTITY
     assert lib.adell_aug_prepare(items.ctypes.data, 2, tiles.ctypes.data, C.byref(info)) == 0
-    assert info.total_tiles == 2 * 2 * 3 * 3 and list(tiles) == [0, 18, 36, 0, 0] and info.n_staged == 0
+    assert info.total_tiles == 2 * 2 * 3 * 3 and list(tiles) == [0, 18, 36, 0, 0, 0, 0] and info.n_staged == 0

@@ -34,7 +34,7 @@ for rep in range(REPS + 2):
     for k in range(16):
         o = k * (n * 640 + 256)
         it = buf[o:o + n * 640].view(ITEM_DTYPE); it[:] = items[k * n:(k + 1) * n]
-        tiles = buf[o + n * 640:o + n * 640 + 4 * (n + 3)].view(np.int32)
+        tiles = buf[o + n * 640:o + n * 640 + 4 * (n + 5)].view(np.int32)
         info = _lib.LaunchInfo()
         lib.adell_aug_prepare(it.ctypes.data, n, tiles.ctypes.data, C.byref(info)); infos.append(info)
     tick("aug_prepare (tensor maps)", t)
@@ -42,7 +42,7 @@ for rep in range(REPS + 2):
     t = time.perf_counter()
     for k in range(16):
         o = k * (n * 640 + 256)
-        engine.launch_packed(d[o:o + n * 640 + 4 * (n + 3)], n, infos[k])
+        engine.launch_packed(d[o:o + n * 640 + 4 * (n + 5)], n, infos[k])
     tick("16 launches", t)
     torch.cuda.synchronize()
 for k, v in T.items():
