@@ -101,6 +101,7 @@ _SIGNATURES = {
     "adell_device_sm_count": (C.c_int, [C.POINTER(C.c_int)]),
     "adell_mat4_chain": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "adell_aug_prepare": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "adell_aug_plan": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "adell_aug_prepare_steps": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "adell_aug_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "adell_aug_gather_launches": (C.c_int, []),

@@ -1348,6 +1348,11 @@ EncodeTiledFn k1_get_encode() {
   return cached;
 }
 
+// stands in for cuTensorMapEncodeTiled in adell_aug_plan: accepts every layout, encodes nothing
+CUresult k1_encode_nothing(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                           const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                           CUtensorMapL2promotion, CUtensorMapFloatOOBfill) { return CUDA_SUCCESS; }
+
 // Identity item eligible for the box copy: fp32, unit step along axis 2, 16-byte aligned
 // destination rows, nothing invalid, no noise, no strict-order post map.  (The source needs no
 // alignment: it arrives through a TMA box whose origin is rounded down to 16 bytes.)
@@ -1561,7 +1566,7 @@ int k1_encode_tmap(adell_item& it, const K1Layout& L, const int* box, EncodeTile
   static thread_local Entry* cache = nullptr;
   if (cache == nullptr) cache = static_cast<Entry*>(calloc(kEntries, sizeof(Entry)));
   Entry* e = nullptr;
-  if (cache != nullptr) {
+  if (cache != nullptr && enc != &k1_encode_nothing) {
     uint64_t h = (L.base >> 4) * 0x9E3779B97F4A7C15ull ^ (L.gdim[0] * 31 + L.gdim[1] * 131 + L.gdim[2] * 1031 + bdim[0] * 7 + bdim[1] * 11 + bdim[2] * 13);
     e = cache + (h >> 40) % kEntries;
     if (e->valid && e->base == L.base && e->gdim[0] == L.gdim[0] && e->gdim[1] == L.gdim[1] && e->gdim[2] == L.gdim[2] &&
@@ -1679,12 +1684,30 @@ int k1_encode_item(adell_item& it, EncodeTiledFn enc, int tile_pref) {
 
 }  // namespace
 
+namespace {
+int k1_prepare_impl(adell_item* items_host, int n_items, int32_t* tile_start_host, adell_launch_info* info, bool plan_only);
+}  // namespace
+
 extern "C" int adell_aug_prepare(adell_item* items_host, int n_items, int32_t* tile_start_host, adell_launch_info* info) {
+  return k1_prepare_impl(items_host, n_items, tile_start_host, info, false);
+}
+
+extern "C" int adell_aug_plan(adell_item* items_host, int n_items, int32_t* tile_start_host, adell_launch_info* info) {
+  const int st = k1_prepare_impl(items_host, n_items, tile_start_host, info, true);
+  if (st == ADELL_OK) {
+    for (int i = 0; i < n_items; ++i) items_host[i].flags &= static_cast<uint8_t>(~ADELL_F_TMAP);  // nothing was encoded
+    info->n_staged = -1 - info->n_staged;   // marks the plan as not launchable (adell_aug_gather refuses it)
+  }
+  return st;
+}
+
+namespace {
+int k1_prepare_impl(adell_item* items_host, int n_items, int32_t* tile_start_host, adell_launch_info* info, bool plan_only) {
   if (items_host == nullptr || tile_start_host == nullptr || info == nullptr || n_items < 0) return ADELL_ERR_BAD_ARG;
   int64_t acc = 0;
   int smem = 0, staged = 0;
-  EncodeTiledFn enc = nullptr;
-  bool enc_tried = false;
+  EncodeTiledFn enc = plan_only ? &k1_encode_nothing : nullptr;
+  bool enc_tried = plan_only;
   const bool no_staged = k1_tuning().no_staged;
   const int tile_pref = k1_tuning().tile_pref;
   for (int i = 0; i < n_items; ++i) {
@@ -1752,6 +1775,7 @@ extern "C" int adell_aug_prepare(adell_item* items_host, int n_items, int32_t* t
   info->n_staged = staged;
   return ADELL_OK;
 }
+}  // namespace
 
 extern "C" int adell_aug_prepare_steps(void* buf_host, int n_steps, const int32_t* n_items, const int64_t* item_off,
                                        const int64_t* tile_off, adell_launch_info* infos) {
@@ -1772,7 +1796,7 @@ extern "C" int adell_aug_gather(const adell_item* items_dev, const int32_t* tile
   if (info == nullptr) return ADELL_ERR_BAD_ARG;
   if (info->total_tiles == 0) return ADELL_OK;
   if (items_dev == nullptr || tile_start_dev == nullptr || n_items < 0 || info->total_tiles < 0 ||
-      info->total_tiles > 0x7fffffffLL || info->smem_bytes < 0 || info->smem_bytes > K1_MAX_BOX_BYTES)
+      info->total_tiles > 0x7fffffffLL || info->smem_bytes < 0 || info->smem_bytes > K1_MAX_BOX_BYTES || info->n_staged < 0)
     return ADELL_ERR_BAD_ARG;
   if ((reinterpret_cast<uintptr_t>(items_dev) & 63u) != 0) return ADELL_ERR_ALIGN;
   int dev = 0, sms = 0;

@@ -182,6 +182,11 @@ typedef struct adell_launch_info {
  * launched repeatedly (not concurrently with itself). */
 int adell_aug_prepare(adell_item* items_host, int n_items, int32_t* tile_start_host,
                       adell_launch_info* info);
+/* Host-only, needs neither a GPU nor a driver: the same decisions as adell_aug_prepare (item order,
+ * per-item path, tile shape, column-group shear, staged box, tile prefix) without encoding any tensor
+ * map.  For inspection and for tests of the host policy; the result is NOT launchable (info->n_staged
+ * comes back as -1 - count and adell_aug_gather refuses it). */
+int adell_aug_plan(adell_item* items_host, int n_items, int32_t* tile_start_host, adell_launch_info* info);
 /* Host-only convenience for several launches packed in one buffer (one upload for many steps):
  * step k has n_items[k] items at buf_host + item_off[k] (64-byte aligned) and its tile prefix
  * (n_items[k] + 5 int32, see adell_aug_prepare) at buf_host + tile_off[k]; runs adell_aug_prepare on each, filling infos[k]. */
