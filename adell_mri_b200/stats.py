@@ -123,6 +123,21 @@ def gamma_map(vols: Sequence[torch.Tensor], minmax_dev: torch.Tensor, gammas, de
     return outs
 
 
+def rician_map(x: torch.Tensor, noise1: torch.Tensor, noise2: torch.Tensor) -> torch.Tensor:
+    """monai RandRicianNoise: ``sqrt((x + noise1)**2 + noise2**2)`` in fp32, one streaming device pass
+    (``adell_rician_map``); returns a new tensor of ``x``'s shape."""
+    if noise1.shape != x.shape or noise2.shape != x.shape:
+        raise ValueError("rician_map: the noise volumes must have the shape of the input")
+    if any(t.dtype != torch.float32 for t in (x, noise1, noise2)):
+        raise ValueError("rician_map expects float32 tensors")
+    x, noise1, noise2 = x.contiguous(), noise1.contiguous(), noise2.contiguous()
+    dev = _check_vols([x, noise1, noise2])
+    out = torch.empty_like(x)
+    _lib.check(_lib.load().adell_rician_map(x.data_ptr(), noise1.data_ptr(), noise2.data_ptr(), out.data_ptr(), x.numel(),
+                                            _stream(dev)), "adell_rician_map")
+    return out
+
+
 def scaler_coefs(stats: torch.Tensor, scaler: int, p0: float, p1: float) -> torch.Tensor:
     """``[n, 6]`` coefficients of ``y = ((x*m0 - a)/d)*m1*m2 + b`` for one of the reference scalers."""
     n = stats.shape[0]

@@ -137,7 +137,7 @@ mri_specific_augments = ["rbf", "gibbs_noise", "spike_noise", "rician_noise"]
 spatial_augments = ["rotate_x", "rotate_y", "rotate_z", "translate_x", "translate_y", "translate_z",
                     "shear_x", "shear_y", "shear_z", "scale_x", "scale_y", "scale_z"]
 #: members of the reference vocabulary that the fused path implements
-FUSED_AUGMENTS = ["gaussian_noise", "shift_intensity", "scale_intensity", *spatial_augments]
+FUSED_AUGMENTS = ["gaussian_noise", "shift_intensity", "scale_intensity", "contrast", "rician_noise", *spatial_augments]
 
 
 class CombineBinaryLabelsd(T.Transform):
@@ -339,7 +339,8 @@ class GetAllCropsd(T.MapTransform):
 
 def _aug_param_dict():
     """modules/augmentations.py:103-129 (a fresh copy: the reference mutates its dict in place)."""
-    d = {"gaussian_noise": {"std": 1}, "shift_intensity": {"offsets": 0.5}, "scale_intensity": {"factors": 0.5}}
+    d = {"gaussian_noise": {"std": 1}, "shift_intensity": {"offsets": 0.5}, "scale_intensity": {"factors": 0.5},
+         "contrast": {"gamma": 3}, "rician_noise": {"std": 0.2}}
     for c in ["x", "y", "z"]:
         t = 30 if c != "z" else 5
         a = np.pi / 6 if c != "z" else np.pi / 16
@@ -378,6 +379,10 @@ def get_transform_d(keys, transform_str: str, params: dict, mask_keys=()):
         return T.RandShiftIntensityd(keys, prob=1.0, **params)
     if transform_str == "scale_intensity":
         return T.RandScaleIntensityd(keys, prob=1.0, **params)
+    if transform_str == "contrast":       # AUG_PARAM_CORRECTION["contrast"]: x + 0.51, gamma ~ U(0.5, x + 0.51)
+        return T.RandAdjustContrastd(keys, prob=1.0, **{k: v + 0.51 for k, v in params.items()})
+    if transform_str == "rician_noise":
+        return T.RandRicianNoised(keys, prob=1.0, **params)
     mode = ["bilinear" if k not in mask_keys else "nearest" for k in keys]
     return T.RandAffined(keys, prob=1.0, mode=mode, padding_mode="zeros", **params)
 

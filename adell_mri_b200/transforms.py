@@ -733,6 +733,43 @@ class RandAdjustContrastd(_RandIntensityd):
         return d
 
 
+class RandRicianNoised(_RandIntensityd):
+    """``monai.transforms.RandRicianNoised`` †: the dict transform's ``R.rand()`` gate, then PER KEY the
+    wrapped ``RandRicianNoise(prob=1.0)``: its own ``R.rand()``, ``sigma ~ U(0, std)`` (``sample_std``)
+    and two ``R.normal(mean, sigma, size=shape)`` volumes (float64 -> float32) from the identically
+    seeded second stream; ``out = sqrt((v + n1)**2 + n2**2)``.  Not linear, so it cannot ride in the
+    gather's intensity map: one streaming device pass (``adell_rician_map``) over the materialised
+    input (/root/reference/adell_mri/modules/augmentations.py:53,86,117 ``rician_noise``;
+    /root/reference/adell_mri/transform_factory/augmentations.py:81-91)."""
+
+    def __init__(self, keys, prob: float = 0.1, mean: float = 0.0, std: float = 1.0, channel_wise: bool = False,
+                 relative: bool = False, sample_std: bool = True, allow_missing_keys: bool = False, **_):
+        super().__init__(keys, prob, allow_missing_keys)
+        if channel_wise or relative:
+            raise NotImplementedError("RandRicianNoised: channel_wise / relative are not used by the reference")
+        self.mean, self.std, self.sample_std = mean, std, sample_std
+        self.noise = {}
+
+    def __call__(self, data):
+        from . import stats
+
+        d = dict(data)
+        self.randomize(None)
+        if not self._do_transform:
+            return d
+        self.noise = {}
+        for k in self.key_iterator(d):
+            x = d[k].tensor() if isinstance(d[k], Pending) else d[k]
+            self.R_inner.rand()
+            std = self.R_inner.uniform(0, self.std) if self.sample_std else self.std
+            n1 = self.R_inner.normal(self.mean, std, size=tuple(x.shape)).astype(np.float32)
+            n2 = self.R_inner.normal(self.mean, std, size=tuple(x.shape)).astype(np.float32)
+            self.noise[k] = (n1, n2)
+            up = [torch.from_numpy(n).pin_memory().to(x.device, non_blocking=True) for n in (n1, n2)]
+            d[k] = stats.rician_map(x.to(torch.float32), up[0], up[1])
+        return d
+
+
 class RandGaussianNoised(_RandIntensityd):
     """``monai.transforms.RandGaussianNoised`` †: sigma ~ U(0, std) (``sample_std``), ONE noise
     volume of the first key's shape drawn from ``R.normal`` on the host (float64 -> float32) and
@@ -876,7 +913,6 @@ def not_on_fused_path(name: str):
     return ctor
 
 
-RandRicianNoised = not_on_fused_path("RandRicianNoised")
 RandGibbsNoised = not_on_fused_path("RandGibbsNoised")
 RandBiasFieldd = not_on_fused_path("RandBiasFieldd")
 RandGaussianSmoothd = not_on_fused_path("RandGaussianSmoothd")

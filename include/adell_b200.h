@@ -250,6 +250,16 @@ int adell_mask_bbox(const adell_vol* vols_dev, const int32_t* shapes_dev, int n_
 int adell_gamma_map(const adell_vol* vols_dev, float* const* dst_dev, const float* minmax_dev,
                     const float* gamma_dev, int n_vols, int64_t max_n, void* stream);
 
+/* monai RandRicianNoise (the SSL workhorse's `rician_noise` member,
+ * /root/reference/adell_mri/modules/augmentations.py:53,86,117; RandRicianNoised of --augment noise,
+ * /root/reference/adell_mri/transform_factory/augmentations.py:81-91):
+ *   y = sqrt((x + n1)^2 + n2^2)
+ * with the two host-drawn normal volumes n1, n2 (RandomState.normal, float64 -> fp32) resident on the
+ * device; add, squares, add and square root each rounded to fp32 in that order.  All four buffers
+ * are contiguous fp32 of n elements; dst may alias x. */
+int adell_rician_map(const float* x_dev, const float* noise1_dev, const float* noise2_dev, float* dst_dev,
+                     int64_t n, void* stream);
+
 /* Exact elementwise intensity program  y = ((x*m0 - a)/d)*m1*m2 + b  with every op rounded to
  * fp32 in that order and no-op steps skipped bit-exactly (m0=1, a=0, d=1, m1=1, m2=1, b=0); the
  * six coefficients are read from coef_dev[6*v ..] so they can come from device statistics.

@@ -527,6 +527,20 @@ def adjust_contrast(img: torch.Tensor, gamma: float) -> torch.Tensor:
     return ((img - img_min) / float(img_range + epsilon)) ** gamma * img_range + img_min
 
 
+def rand_rician_noise(img: torch.Tensor, R, std: float, mean: float = 0.0, sample_std: bool = True):
+    """monai RandRicianNoise.__call__ † (prob 1.0, channel_wise=False, relative=False): its own
+    ``R.rand()`` gate, ``sigma = R.uniform(0, std)``, two ``R.normal(mean, sigma, size=img.shape)``
+    volumes cast to the image dtype, ``sqrt((img + n1)**2 + n2**2)``
+    (/root/reference/adell_mri/modules/augmentations.py:53,86,117).  Returns (out, n1, n2).
+    torch's CPU sqrt is MKL VML's (within 1 ulp of the IEEE square root, not always equal to it)."""
+    img = img.to(torch.float32)
+    R.rand()
+    s = R.uniform(0, std) if sample_std else std
+    n1 = torch.as_tensor(R.normal(mean, s, size=tuple(img.shape)).astype(np.float32))
+    n2 = torch.as_tensor(R.normal(mean, s, size=tuple(img.shape)).astype(np.float32))
+    return torch.sqrt((img + n1) ** 2 + n2 ** 2), n1, n2
+
+
 def std_shift_intensity(img: torch.Tensor, factor: float) -> torch.Tensor:
     """monai StdShiftIntensity._stdshift † (nonzero=False, channel_wise=False): ``img + factor *
     std(img)`` with the population standard deviation of the whole array."""

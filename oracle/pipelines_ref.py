@@ -233,6 +233,23 @@ class ContrastD(ScaleD):
         return d
 
 
+class RicianD(ScaleD):
+    """RandRicianNoised †: dict-level gate, then per key the array transform (prob 1.0) drawing its own
+    sigma and two normal volumes from the identically seeded second stream."""
+
+    def __init__(self, keys, prob, std):
+        super().__init__(keys, std)
+        self.prob = prob
+
+    def __call__(self, d):
+        d = dict(d)
+        if not self.R.rand() < self.prob:
+            return d
+        for k in self.keys:
+            d[k], _, _ = M.rand_rician_noise(d[k], self.R2, self.f)
+        return d
+
+
 class StdShiftD(ScaleD):
     """RandStdShiftIntensityd †."""
 
@@ -292,6 +309,10 @@ def _member(keys, name, mult=0.5):
         return ShiftD(keys, 0.5 * mult)
     if name == "scale_intensity":
         return ScaleD(keys, 0.5 * mult)
+    if name == "contrast":        # AUG_PARAM_CORRECTION: gamma = 3 * mult + 0.51, a scalar: U(0.5, gamma)
+        return ContrastD(keys, 1.0, (0.5, 3 * mult + 0.51))
+    if name == "rician_noise":
+        return RicianD(keys, 1.0, 0.2 * mult)
     kind, c = name.rsplit("_", 1)
     rng = [0, 0, 0]
     if kind == "rotate":

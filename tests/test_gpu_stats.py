@@ -162,3 +162,22 @@ def test_percentile_scaler_transform_then_classification_chain(clip):
             assert torch.allclose(got[b], ref({"t2": scaled})["image"], rtol=1e-5, atol=1e-6)
     finally:
         T.set_mode(strict=False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,offset", [(0, 0), (1, 0), (7, 1), (4096, 0), (40 * 36 * 20 + 3, 0), (40 * 36 * 20 + 3, 3), (1 << 22, 0)])
+def test_rician_map_is_bit_exact(n, offset):
+    """adell_rician_map = sqrt((x + n1) ** 2 + n2 ** 2) with every op IEEE-rounded to fp32 (vectorised body,
+    scalar tail, unaligned views): bit-exact against numpy op by op; torch's CPU sqrt goes through MKL VML,
+    which is within 1 ulp but not correctly rounded (0.7 % of the elements differ by one ulp)."""
+    R = np.random.RandomState(n % 1000 + offset)
+    x = torch.from_numpy(R.gamma(2.0, 0.3, size=n + offset).astype(np.float32))[offset:]
+    want, n1, n2 = M.rand_rician_noise(x, np.random.RandomState(4), 0.1)
+    xd = torch.empty(n + offset, dtype=torch.float32, device=DEV)[offset:]   # offset: a view that is not 16-byte aligned
+    xd.copy_(x)
+    got = stats.rician_map(xd, n1.to(DEV), n2.to(DEV))
+    a = x.numpy() + n1.numpy()
+    ieee = np.sqrt(a * a + n2.numpy() * n2.numpy())
+    assert ieee.dtype == np.float32
+    assert got.shape == x.shape and np.array_equal(got.cpu().numpy(), ieee)
+    assert torch.allclose(got.cpu(), want, rtol=2e-7, atol=0)

@@ -83,7 +83,10 @@ def ref_cfg(r):
     if cls == "RandStdShiftIntensityd":
         return {"cls": cls, "keys": keys, "prob": k["prob"], "factors": _pair(k["factors"])}
     if cls == "RandAdjustContrastd":
-        return {"cls": cls, "keys": keys, "prob": k["prob"], "gamma": [float(x) for x in k["gamma"]]}
+        g = k["gamma"]   # MONAI: a number means U(0.5, gamma)
+        return {"cls": cls, "keys": keys, "prob": k["prob"], "gamma": [0.5, float(g)] if isinstance(g, (int, float)) else [float(x) for x in g]}
+    if cls == "RandRicianNoised":   # MONAI defaults: mean 0, sample_std True
+        return {"cls": cls, "keys": keys, "prob": k["prob"], "std": float(k["std"]), "mean": 0.0, "sample_std": True}
     raise AssertionError(f"unexpected reference transform {cls}")
 
 
@@ -124,7 +127,7 @@ def our_cfg(t, roi_size=None):
         return {"cls": cls, "keys": keys, "roi_size": t.roi_size}
     if cls == "Lambdad":
         return {"cls": cls, "keys": keys, "flatten_box": [[float(v) for v in t.func(b)] for b in G.FLATTEN_BOX_INPUTS]}
-    if cls == "RandGaussianNoised":
+    if cls in ("RandGaussianNoised", "RandRicianNoised"):
         return {"cls": cls, "keys": keys, "prob": t.prob, "std": float(t.std), "mean": float(t.mean), "sample_std": t.sample_std}
     if cls == "RandShiftIntensityd":
         return {"cls": cls, "keys": keys, "prob": t.prob, "offsets": [float(x) for x in t.offsets]}
