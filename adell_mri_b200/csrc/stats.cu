@@ -265,7 +265,16 @@ st_label_map(const st_label_args a, float* __restrict__ dst, int64_t n) {
   }
 }
 
-// monai AdjustContrast: ((x - min) / (range + eps)) ** gamma * range + min, fp32 op by op.
+// monai AdjustContrast: ((x - min) / (range + eps)) ** gamma * range + min.  Subtraction, division,
+// multiplication and addition are fp32 op by op; the power is exp2(gamma * log2(t)) on the SFU
+// (t in [0, 1], gamma in (0.5, 4.5]: the absolute error stays below 1e-6 of the range, far inside the
+// 1e-4 the intensity maps are held to; powf's ~50 instructions per voxel kept the pass at 0.2 of the
+// HBM peak).  t = 0 gives log2 = -inf and exp2 = 0 like pow.
+__device__ __forceinline__ float st_gamma_one(float x, float lo, float den, float range, float gamma) {
+  const float t = __fdiv_rn(__fsub_rn(x, lo), den);
+  const float p = exp2f(__fmul_rn(gamma, __log2f(t)));
+  return __fadd_rn(__fmul_rn(p, range), lo);
+}
 __global__ void __launch_bounds__(ST_THREADS)
 st_gamma_map(const adell_vol* __restrict__ vols, float* const* __restrict__ dsts, const float* __restrict__ minmax,
              const float* __restrict__ gammas) {
@@ -275,11 +284,20 @@ st_gamma_map(const adell_vol* __restrict__ vols, float* const* __restrict__ dsts
   const float range = __fsub_rn(hi, lo), den = __fadd_rn(range, 1e-7f), gamma = __ldg(gammas + blockIdx.y);
   const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t nthr = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t i = tid; i < v.n; i += nthr) {
-    const float x = adell_load_src(v.data, i, v.dtype);
-    const float t = powf(__fdiv_rn(__fsub_rn(x, lo), den), gamma);
-    dst[i] = __fadd_rn(__fmul_rn(t, range), lo);
+  int64_t done = 0;
+  if (v.dtype == ADELL_F32 && ((reinterpret_cast<uintptr_t>(v.data) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0) {
+    const float4* __restrict__ src4 = reinterpret_cast<const float4*>(v.data);
+    const int64_t n4 = v.n >> 2;
+    for (int64_t i = tid; i < n4; i += nthr) {
+      const float4 x = __ldcs(src4 + i);
+      float4 y;
+      y.x = st_gamma_one(x.x, lo, den, range, gamma); y.y = st_gamma_one(x.y, lo, den, range, gamma);
+      y.z = st_gamma_one(x.z, lo, den, range, gamma); y.w = st_gamma_one(x.w, lo, den, range, gamma);
+      __stcs(reinterpret_cast<float4*>(dst) + i, y);
+    }
+    done = n4 << 2;
   }
+  for (int64_t i = done + tid; i < v.n; i += nthr) dst[i] = st_gamma_one(adell_load_src(v.data, i, v.dtype), lo, den, range, gamma);
 }
 
 // monai RandRicianNoise: sqrt((x + n1)^2 + n2^2), fp32 op by op (torch: add, pow(2) = mul, add, sqrt).

@@ -181,3 +181,32 @@ def test_rician_map_is_bit_exact(n, offset):
     assert ieee.dtype == np.float32
     assert got.shape == x.shape and np.array_equal(got.cpu().numpy(), ieee)
     assert torch.allclose(got.cpu(), want, rtol=2e-7, atol=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gamma", [0.5, 0.77, 1.0, 2.01, 4.5])
+@pytest.mark.parametrize("kind", ["f32", "f32_unaligned", "i16"])
+def test_gamma_map_error_is_bounded_by_1e6_of_the_range(gamma, kind):
+    """adell_gamma_map vs monai AdjustContrast restated in float64 and in torch fp32: the SFU power keeps
+    the absolute error below 2e-6 of the intensity range (the path is held to 1e-4); min and max map to
+    themselves (pow(0) = 0, pow(1 - eps) ~ 1)."""
+    R = np.random.RandomState(int(gamma * 100))
+    n = 50_003
+    if kind == "i16":
+        x = torch.from_numpy(R.randint(-200, 4000, size=n).astype(np.int16))
+    else:
+        x = torch.from_numpy(np.concatenate([R.gamma(2.0, 300.0, size=n - 3), [0.0, 1e-3, 5e3]]).astype(np.float32))
+    xd = x.to(DEV)
+    if kind == "f32_unaligned":
+        buf = torch.empty(n + 1, dtype=torch.float32, device=DEV)
+        buf[1:].copy_(x)
+        xd = buf[1:]
+    mm = stats.minmax([xd])
+    got = stats.gamma_map([xd], mm, gamma)[0].cpu()
+    xf = x.to(torch.float64)
+    lo, rng = xf.min(), xf.max() - xf.min()
+    want64 = ((xf - lo) / (rng + 1e-7)) ** gamma * rng + lo
+    assert float((got.to(torch.float64) - want64).abs().max()) <= 2e-6 * float(rng)
+    want32 = M.adjust_contrast(x.to(torch.float32), gamma)
+    assert torch.allclose(got, want32, rtol=2e-5, atol=2e-6 * float(rng))
+    assert got[x.argmin()] == float(lo)
