@@ -25,7 +25,7 @@ INTERP_MODES = {"nearest": NEAREST, "bilinear": TRILINEAR, "trilinear": TRILINEA
 
 
 class Item(C.Structure):
-    """Mirror of ``adell_item`` (640 bytes, 64-byte aligned)."""
+    """Mirror of ``adell_item`` (768 bytes, 64-byte aligned)."""
 
     _fields_ = [
         ("tmap", C.c_uint8 * 128),
@@ -73,11 +73,12 @@ class Item(C.Structure):
         ("fp_U0", C.c_double * 3),
         ("fp_D", C.c_double * 9),
         ("shear", C.c_int8 * 32),
+        ("dmap", C.c_uint8 * 128),
     ]
 
 
 ITEM_SIZE = C.sizeof(Item)
-assert ITEM_SIZE == 640, ITEM_SIZE
+assert ITEM_SIZE == 768, ITEM_SIZE
 
 
 class LaunchInfo(C.Structure):
@@ -128,7 +129,7 @@ _SIGNATURES = {
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 _lib = None
 
 

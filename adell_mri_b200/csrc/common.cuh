@@ -5,7 +5,7 @@
 
 #include "../../include/adell_b200.h"
 
-static_assert(sizeof(adell_item) == 640, "adell_item must stay 640 bytes (ABI v2)");
+static_assert(sizeof(adell_item) == 768, "adell_item must stay 768 bytes (ABI v5)");
 
 #define ADELL_CUDA_CHECK_LAUNCH()                         \
   do {                                                    \

@@ -68,7 +68,7 @@ __device__ __forceinline__ void k1_wt_store(float4* p, float4 v) { __stwt(p, v);
 #define K1_NV 4                                 // trilinear voxels interleaved per consumer-thread iteration
 #endif
 
-enum { MODE_DIRECT = 0, MODE_STAGED = 1, MODE_ZERO = 2, MODE_COPY = 3, MODE_DONE = 4 };
+enum { MODE_DIRECT = 0, MODE_STAGED = 1, MODE_ZERO = 2, MODE_COPY = 3, MODE_DONE = 4, MODE_TSTORE = 5 };
 
 struct K1Tile {
   int mode;
@@ -141,6 +141,17 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const void* tmap, uint64_
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+
+// Shared -> global box store through the destination tensor map (bulk async group of the issuing thread).
+__device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the committed stores of this thread have finished READING shared memory (the stage may be refilled)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -865,7 +876,7 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
   const int o00 = b0 * it.tile_dim[0], o01 = b1 * it.tile_dim[1], o02 = b2 * it.tile_dim[2];
   const int o0a = a == 0 ? o00 : (a == 1 ? o01 : o02);
   if (ax) { tl.o0[a] = o0a; tl.T[a] = it.tile_dim[a]; }
-  if (it.kind == ADELL_KIND_VCOPY) {
+  if (it.kind >= ADELL_KIND_VCOPY) {
     // source box of the tile = its voxels, in memory order (integer flip / crop only)
     if (ax) {
       const int na = min(static_cast<int>(it.tile_dim[a]), it.out_shape[a] - o0a);
@@ -876,7 +887,7 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
       tl.box[a] = it.tmap_box[a]; tl.msign[a] = msign; tl.mconst[a] = it.tmap_off[a] - mo;
       if (a == 2) { tl.fix_lo = 0; tl.fix_hi = 0; }
     }
-    if (lane == 0) tl.mode = MODE_COPY;
+    if (lane == 0) tl.mode = it.kind == ADELL_KIND_VCOPY ? MODE_COPY : MODE_TSTORE;
     return;
   }
   if (it.kind != ADELL_KIND_STAGED) {
@@ -1035,12 +1046,12 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
 }
 
 #ifdef K1_PROFILE
-__device__ unsigned long long k1_prof[8];
+__device__ unsigned long long k1_prof[16];
 // cycle counters accumulate in registers and are flushed once per warp (low perturbation)
-#define K1_PROF_DECL long long _acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define K1_PROF_DECL long long _acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #define K1_PROF_T0 long long _t0 = clock64();
 #define K1_PROF_ADD(i) { long long _t1 = clock64(); _acc[i] += _t1 - _t0; _t0 = _t1; }
-#define K1_PROF_FLUSH if ((threadIdx.x & 31) == 0) { for (int _i = 0; _i < 8; ++_i) if (_acc[_i]) atomicAdd(&k1_prof[_i], (unsigned long long)_acc[_i]); }
+#define K1_PROF_FLUSH if ((threadIdx.x & 31) == 0) { for (int _i = 0; _i < 16; ++_i) if (_acc[_i]) atomicAdd(&k1_prof[_i], (unsigned long long)_acc[_i]); }
 #else
 #define K1_PROF_DECL
 #define K1_PROF_T0
@@ -1165,11 +1176,14 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
     // compute-bound and a memory-bound tile at once instead of all SMs going through the same phases.
     int q = strm & 1;
     bool switched = false;
+    const bool idle = (chunk >> 16) == strm + 1;   // measurement aid (ADELL_K1_IDLE_STREAM)
+    chunk &= 0xffff;
     K1_PROF_DECL
     for (;; rs.next(), rl.next()) {
       const int stage = strm + K1_GROUPS * rs.i, slot = strm + K1_GROUPS * rl.i;
       K1_PROF_T0
       while (cur >= cur_end) {          // next unit from the current queue, or from the other one
+        if (idle) { cur = cur_end = total_tiles; break; }
         unsigned int c = 0;
         if (lane == 0) c = atomicAdd(sched + q, 1u);
         c = __shfl_sync(0xffffffffu, c, 0);
@@ -1203,7 +1217,7 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
       K1_PROF_ADD(0)
       if (lane == 0) {
         const K1Slot& sl = slots[slot];
-        if (sl.tl.mode == MODE_STAGED || sl.tl.mode == MODE_COPY) {  // tiles with a TMA box load
+        if (sl.tl.mode == MODE_STAGED || sl.tl.mode == MODE_COPY || sl.tl.mode == MODE_TSTORE) {  // tiles with a TMA box load
           const int mo0 = sl.ctx.it.tmap_off[0] - sl.tl.mconst[0], mo1 = sl.ctx.it.tmap_off[1] - sl.tl.mconst[1],
                     mo2 = sl.ctx.it.tmap_off[2] - sl.tl.mconst[2];
           if (sl.tl.item != acq_item) { tmap_acquire(items[sl.tl.item].tmap); acq_item = sl.tl.item; }
@@ -1230,6 +1244,7 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
     // Sits between the TMA completion (landed) and the consumers (full): zeroes the alignment-slack
     // columns of boxes that have any (crop windows that start mid-row), off the producer's path, so
     // that the producer never waits for a load to land.
+    int acq_dst = -1;   // item whose destination tensor map this warp acquired last
     for (;; rs.next(), rl.next()) {
       const int stage = strm + K1_GROUPS * rs.i, slot = strm + K1_GROUPS * rl.i;
       mbar_wait_relaxed(landed + stage, rs.phase);
@@ -1237,10 +1252,43 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
       const int mode = tl.mode;
       if (mode == MODE_STAGED && tl.fix_hi > tl.fix_lo)
         k1_fix_columns(reinterpret_cast<float*>(smem + static_cast<size_t>(stage) * stage_bytes), tl, lane);
+      if (mode == MODE_TSTORE) {
+        // Plain copy tile: the box that just landed goes straight back out through the destination tensor
+        // map — no consumer instructions, no LSU traffic.  The box is in SOURCE memory order: an axis whose
+        // net direction is reversed (a flip) is stored slice by slice to the mirrored coordinate (planes for
+        // axis 0, rows for axis 1; the item's map was encoded with that box shape: kind - ADELL_KIND_TSTORE).
+        const adell_item& it = slots[slot].ctx.it;
+        if (tl.item != acq_dst) { tmap_acquire(items[tl.item].dmap); acq_dst = tl.item; }
+        const void* dmap = items[tl.item].dmap;
+        const uint32_t base = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+        const int split = it.kind - ADELL_KIND_TSTORE;
+        const int n0 = min(tl.T[0], it.out_shape[0] - tl.o0[0]), n1 = min(tl.T[1], it.out_shape[1] - tl.o0[1]);
+        const bool r0 = tl.msign[0] * it.grid_sign[0] < 0, r1 = tl.msign[1] * it.grid_sign[1] < 0;
+        const uint32_t row = static_cast<uint32_t>(tl.box[2]) * 4u, plane = row * static_cast<uint32_t>(tl.box[1]);
+        bool issued = false;
+        if (split == 0) {
+          if (lane == 0) { tma_store_3d(dmap, base, tl.o0[2], tl.o0[1], tl.o0[0]); issued = true; }
+        } else if (split == 1) {
+          if (lane < n0) {
+            const int b0 = r0 ? n0 - 1 - lane : lane;
+            tma_store_3d(dmap, base + b0 * plane, tl.o0[2], tl.o0[1], tl.o0[0] + lane);
+            issued = true;
+          }
+        } else {
+          for (int idx = lane; idx < n0 * n1; idx += 32) {
+            const int d0 = idx / n1, d1 = idx - d0 * n1;
+            const int b0 = r0 ? n0 - 1 - d0 : d0, b1 = r1 ? n1 - 1 - d1 : d1;
+            tma_store_3d(dmap, base + b0 * plane + b1 * row, tl.o0[2], tl.o0[1] + d1, tl.o0[0] + d0);
+            issued = true;
+          }
+        }
+        if (issued) { tma_store_commit(); tma_store_wait_read(); }
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(full + stage);
       if (mode == MODE_DONE) break;
     }
+    tma_store_wait_all();   // every store of this warp is complete before the kernel ends
     return;
   }
 
@@ -1262,6 +1310,8 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
     if (mode == MODE_DONE) break;
     if (mode == MODE_COPY) {
       k1_tile_copy_box(ctx, tl, box);
+    } else if (mode == MODE_TSTORE) {
+      // stored by the hand-over warp (TMA): the consumers only pass the stage on
     } else if (mode == MODE_ZERO) {
       const bool strict = (it.flags & ADELL_F_STRICT) != 0;
       k1_for_each_voxel(tl, it, [&](int, int, int, int o0, int o1, int o2) { k1_finish(it, 0.0f, o0, o1, o2, strict); });
@@ -1296,7 +1346,9 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
     }
     __syncwarp();
 #ifdef K1_PROFILE
-    { long long _t1 = clock64(); _acc[4] += _t1 - _t0; if (threadIdx.x % K1_GTHREADS == 0) _acc[7] += 1; }
+    { long long _t1 = clock64(); _acc[4] += _t1 - _t0; if (threadIdx.x % K1_GTHREADS == 0) _acc[7] += 1;
+      // per tile kind (first warp of each group): cycles and tiles of resampled [8,9] / consumer-copy [10,11] / TMA-store [12,13] tiles
+      if (threadIdx.x % K1_GTHREADS == 0) { const int _k = mode == MODE_STAGED ? 8 : (mode == MODE_COPY ? 10 : (mode == MODE_TSTORE ? 12 : 14)); _acc[_k] += _t1 - _t0; _acc[_k + 1] += 1; } }
 #endif
     if (lane == 0) mbar_arrive(empty + stage);
   }
@@ -1388,8 +1440,8 @@ void k1_item_map(adell_item& it) {
 // Tuning / debugging knobs from the environment, read once per process (getenv walks the whole
 // environment: per item it cost more than the policy itself).
 struct K1Tuning {
-  bool no_shear, no_staged;
-  int copy_t0, pref_box, tile_pref, chunk, tail;
+  bool no_shear, no_staged, no_tstore;
+  int copy_t0, pref_box, tile_pref, chunk, tail, idle_stream, tstore_split;
   int64_t tile_cost;
   K1Tuning() {
     auto num = [](const char* name, int lo, int hi, int dflt) {
@@ -1402,12 +1454,16 @@ struct K1Tuning {
     no_shear = e != nullptr && e[0] == '1';
     e = getenv("ADELL_DISABLE_STAGED");                       // debugging aid: force the direct path
     no_staged = e != nullptr && e[0] == '1';
+    e = getenv("ADELL_K1_NO_TSTORE");                         // measurement aid: copy tiles through the consumer warps
+    no_tstore = e != nullptr && e[0] == '1';
+    tstore_split = num("ADELL_K1_TSTORE_SPLIT", 0, 2, 1);    // finest split that still takes the TMA-store path
     copy_t0 = num("ADELL_K1_COPY_T0", 8, 32, K1_COPY_T0);
     if (copy_t0 != 8 && copy_t0 != 16 && copy_t0 != 32) copy_t0 = K1_COPY_T0;
     pref_box = num("ADELL_K1_PREF_BOX", 1024, K1_MAX_BOX_BYTES, -1);
     tile_pref = num("ADELL_K1_TILE", 0, 3, -1);               // 0 = 16x16x32, 1 = 16x32x16, 2 = 8x16x32, 3 = 16x16x16 only
     chunk = num("ADELL_K1_CHUNK", 1, 64, 4);
     tail = num("ADELL_K1_TAIL", 0, 64, 3);
+    idle_stream = num("ADELL_K1_IDLE_STREAM", 0, K1_GROUPS - 1, -1);   // measurement aid: that stream of every CTA takes no tiles
     tile_cost = num("ADELL_K1_TILE_COST", 0, 1 << 30, 3072);
   }
 };
@@ -1550,17 +1606,14 @@ bool k1_tmap_layout(adell_item& it, K1Layout& L) {
   return true;
 }
 
-// Encodes the tensor map for a staged box of the given extents (axes 0,1,2).  Returns 1, 0 (the
-// driver refused the layout) or -1 (no driver).
-int k1_encode_tmap(adell_item& it, const K1Layout& L, const int* box, EncodeTiledFn enc) {
-  it.flags &= static_cast<uint8_t>(~ADELL_F_TMAP);
-  for (int a = 0; a < 3; ++a) it.tmap_box[a] = box[a];
-  const cuuint32_t bdim[3] = {static_cast<cuuint32_t>(box[2]), static_cast<cuuint32_t>(box[1]), static_cast<cuuint32_t>(box[0])};
+// Encodes one 3-D fp32 tensor map (innermost dimension first) into out_map.  Returns 1, 0 (the driver
+// refused the layout) or -1 (no driver).
+// A device-resident cache hands the same volumes back every epoch and the outputs are written into the
+// same batch tensors, and a map only depends on the memory layout (flips are signs in the box index):
+// the last encodings are remembered per host thread instead of asking the driver again (~0.4 us each).
+int k1_encode_map(uint8_t* out_map, const K1Layout& L, const cuuint32_t* bdim, EncodeTiledFn enc) {
   const cuuint32_t estr[3] = {1, 1, 1};
   if (enc == nullptr) return -1;
-  // A device-resident cache hands the same volumes back every epoch, and the map only depends on the
-  // memory-order layout of the valid source box (flips are signs in the box index): remember the last
-  // encodings per host thread instead of asking the driver again (~0.4 us each, 32 per step).
   struct Entry { uintptr_t base; cuuint64_t gdim[3], gstride[2]; cuuint32_t box[3]; bool valid; uint8_t map[128]; };
   constexpr int kEntries = 2048;
   static thread_local Entry* cache = nullptr;
@@ -1572,13 +1625,11 @@ int k1_encode_tmap(adell_item& it, const K1Layout& L, const int* box, EncodeTile
     if (e->valid && e->base == L.base && e->gdim[0] == L.gdim[0] && e->gdim[1] == L.gdim[1] && e->gdim[2] == L.gdim[2] &&
         e->gstride[0] == L.gstride[0] && e->gstride[1] == L.gstride[1] && e->box[0] == bdim[0] && e->box[1] == bdim[1] &&
         e->box[2] == bdim[2]) {
-      memcpy(it.tmap, e->map, 128);
-      it.tmap_base = reinterpret_cast<const void*>(L.base);
-      it.flags |= ADELL_F_TMAP;
+      memcpy(out_map, e->map, 128);
       return 1;
     }
   }
-  CUresult r = enc(reinterpret_cast<CUtensorMap*>(it.tmap), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+  CUresult r = enc(reinterpret_cast<CUtensorMap*>(out_map), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
                    reinterpret_cast<void*>(L.base), L.gdim, L.gstride, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, K1_L2_PROMO, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return 0;
@@ -1586,12 +1637,55 @@ int k1_encode_tmap(adell_item& it, const K1Layout& L, const int* box, EncodeTile
     e->base = L.base;
     for (int i = 0; i < 3; ++i) { e->gdim[i] = L.gdim[i]; e->box[i] = bdim[i]; }
     e->gstride[0] = L.gstride[0]; e->gstride[1] = L.gstride[1];
-    memcpy(e->map, it.tmap, 128);
+    memcpy(e->map, out_map, 128);
     e->valid = true;
   }
+  return 1;
+}
+
+// Encodes the source tensor map for a staged box of the given extents (axes 0,1,2).
+int k1_encode_tmap(adell_item& it, const K1Layout& L, const int* box, EncodeTiledFn enc) {
+  it.flags &= static_cast<uint8_t>(~ADELL_F_TMAP);
+  for (int a = 0; a < 3; ++a) it.tmap_box[a] = box[a];
+  const cuuint32_t bdim[3] = {static_cast<cuuint32_t>(box[2]), static_cast<cuuint32_t>(box[1]), static_cast<cuuint32_t>(box[0])};
+  const int r = k1_encode_map(it.tmap, L, bdim, enc);
+  if (r <= 0) return r;
   it.tmap_base = reinterpret_cast<const void*>(L.base);
   it.flags |= ADELL_F_TMAP;
   return 1;
+}
+
+// Plain copy item (nothing but integer flips / crops, no intensity map, contiguous axis not reversed,
+// 16-byte aligned rows on both sides): its tiles can leave through a destination tensor map (TMA
+// store) without touching the consumer warps.  Fills it.dmap and returns the split (0: whole boxes,
+// 1: plane by plane — axis 0 reversed, 2: row by row — axis 1 reversed), -1 when not eligible, -2 without
+// a driver.  Needs tmap_sign (k1_tmap_layout) and the encoded source box.
+int k1_encode_dst(adell_item& it, const int* T, const int* box, EncodeTiledFn enc) {
+  if (k1_tuning().no_tstore) return -1;
+  if (it.flags & (ADELL_F_CLIP | ADELL_F_PRE_DEV)) return -1;
+  if (it.pre_scale != 1.0f || it.pre_offset != 0.0f || it.post_scale != 1.0f || it.post_offset != 0.0f) return -1;
+  if (it.tmap_sign[2] * it.grid_sign[2] < 0) return -1;          // a flip along the contiguous axis reverses elements
+  if (box[2] != T[2] || box[1] != T[1] || box[0] != T[0]) return -1;  // unaligned window: the box carries slack columns
+  if (it.fp_fix != 0) return -1;
+  K1Layout L;
+  L.base = reinterpret_cast<uintptr_t>(it.dst);
+  if (L.base & 15u) return -1;
+  if (it.dst_stride[2] != 1 || it.dst_stride[1] < it.out_shape[2] || it.dst_stride[0] < it.dst_stride[1] * it.out_shape[1]) return -1;
+  L.gdim[0] = static_cast<cuuint64_t>(it.out_shape[2]);
+  L.gdim[1] = static_cast<cuuint64_t>(it.out_shape[1]);
+  L.gdim[2] = static_cast<cuuint64_t>(it.out_shape[0]);
+  L.gstride[0] = static_cast<cuuint64_t>(it.dst_stride[1]) * 4;
+  L.gstride[1] = static_cast<cuuint64_t>(it.dst_stride[0]) * 4;
+  if ((L.gstride[0] & 15u) || (L.gstride[1] & 15u)) return -1;
+  const bool r0 = it.tmap_sign[0] * it.grid_sign[0] < 0, r1 = it.tmap_sign[1] * it.grid_sign[1] < 0;
+  const int split = r1 ? 2 : (r0 ? 1 : 0);
+  // row-by-row stores (128 B each, 256 per tile) are slower than the consumer copy: measured
+  if (split > k1_tuning().tstore_split) return -1;
+  const cuuint32_t bdim[3] = {static_cast<cuuint32_t>(T[2]), static_cast<cuuint32_t>(split == 2 ? 1 : T[1]),
+                              static_cast<cuuint32_t>(split == 0 ? T[0] : 1)};
+  const int r = k1_encode_map(it.dmap, L, bdim, enc);
+  if (r < 0) return -2;
+  return r == 0 ? -1 : split;
 }
 
 // Identity item: tensor map for the 32x16x32 box copy.  Returns the box bytes (0 = not eligible).
@@ -1614,7 +1708,9 @@ int k1_encode_copy(adell_item& it, EncodeTiledFn enc) {
     if (r <= 0) return r;
   }
   for (int a = 0; a < 3; ++a) it.tile_dim[a] = static_cast<uint8_t>(T[a]);
-  it.kind = ADELL_KIND_VCOPY;
+  const int split = k1_encode_dst(it, T, box, enc);
+  if (split == -2) return -1;
+  it.kind = static_cast<uint8_t>(split < 0 ? ADELL_KIND_VCOPY : ADELL_KIND_TSTORE + split);
   return box[0] * box[1] * box[2] * 4;
 }
 
@@ -1747,7 +1843,7 @@ int k1_prepare_impl(adell_item* items_host, int n_items, int32_t* tile_start_hos
   // "resampled" queue and the rest the "copy" queue, so that every SM can keep a compute-bound and a
   // memory-bound tile in flight at once.  Items are independent: their order does not matter.
   int n_copy = 0;
-  for (int i = 0; i < n_items; ++i) n_copy += items_host[i].kind == ADELL_KIND_VCOPY;
+  for (int i = 0; i < n_items; ++i) n_copy += items_host[i].kind >= ADELL_KIND_VCOPY;
   if (n_copy > 0 && n_copy < n_items) {
     adell_item* tmp = static_cast<adell_item*>(malloc(sizeof(adell_item) * static_cast<size_t>(n_items)));
     int32_t* cnt = static_cast<int32_t*>(malloc(sizeof(int32_t) * static_cast<size_t>(n_items)));
@@ -1755,14 +1851,14 @@ int k1_prepare_impl(adell_item* items_host, int n_items, int32_t* tile_start_hos
     int w = 0;
     for (int pass = 0; pass < 2; ++pass)
       for (int i = 0; i < n_items; ++i)
-        if ((items_host[i].kind == ADELL_KIND_VCOPY) == (pass == 1)) { memcpy(tmp + w, items_host + i, sizeof(adell_item)); cnt[w++] = tile_start_host[i]; }
+        if ((items_host[i].kind >= ADELL_KIND_VCOPY) == (pass == 1)) { memcpy(tmp + w, items_host + i, sizeof(adell_item)); cnt[w++] = tile_start_host[i]; }
     memcpy(items_host, tmp, sizeof(adell_item) * static_cast<size_t>(n_items));
     memcpy(tile_start_host, cnt, sizeof(int32_t) * static_cast<size_t>(n_items));
     free(tmp); free(cnt);
   }
   int64_t run = 0, first_copy = -1;
   for (int i = 0; i < n_items; ++i) {
-    if (first_copy < 0 && items_host[i].kind == ADELL_KIND_VCOPY) first_copy = run;
+    if (first_copy < 0 && items_host[i].kind >= ADELL_KIND_VCOPY) first_copy = run;
     const int32_t n = tile_start_host[i];
     tile_start_host[i] = static_cast<int32_t>(run);
     run += n;
@@ -1816,7 +1912,7 @@ extern "C" int adell_aug_gather(const adell_item* items_dev, const int32_t* tile
   if (e != cudaSuccess) { (void)cudaGetLastError(); return adell_map_cuda_error(e); }
   // consecutive tiles a producer takes from the queue at a time (they share the item and neighbouring
   // source boxes): small enough that the tail of the launch stays balanced
-  const int chunk = k1_tuning().chunk;
+  const int chunk = k1_tuning().chunk | ((k1_tuning().idle_stream + 1) << 16);
   // the last ~3 tiles per stream of each queue are handed out one by one
   const int64_t streams = static_cast<int64_t>(sms) * K1_GROUPS;
   const int64_t tail = k1_tuning().tail * streams;
@@ -1824,8 +1920,8 @@ extern "C" int adell_aug_gather(const adell_item* items_dev, const int32_t* tile
   const int64_t tiles_q[2] = {first_copy, info->total_tiles - first_copy};
   int64_t n_big[2], n_units = 0;
   for (int q = 0; q < 2; ++q) {
-    n_big[q] = tiles_q[q] > tail ? (tiles_q[q] - tail) / chunk : 0;
-    n_units += n_big[q] + (tiles_q[q] - n_big[q] * chunk);
+    n_big[q] = tiles_q[q] > tail ? (tiles_q[q] - tail) / (chunk & 0xffff) : 0;
+    n_units += n_big[q] + (tiles_q[q] - n_big[q] * (chunk & 0xffff));
   }
   const int64_t n_ctas = (n_units + K1_GROUPS - 1) / K1_GROUPS;
   const int64_t grid = n_ctas < sms ? n_ctas : sms;
@@ -1843,9 +1939,9 @@ extern "C" int adell_aug_gather_launches(void) { return 1; }
 
 #ifdef K1_PROFILE
 // debug builds only: cumulative cycle counters {producer wait-empty, issue, prepare, consumer wait-full, compute}
-extern "C" int adell_debug_prof(unsigned long long* out8, int reset) {
-  cudaMemcpyFromSymbol(out8, k1_prof, sizeof(unsigned long long) * 8);
-  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(k1_prof, z, sizeof(z)); }
+extern "C" int adell_debug_prof(unsigned long long* out16, int reset) {
+  cudaMemcpyFromSymbol(out16, k1_prof, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(k1_prof, z, sizeof(z)); }
   return 0;
 }
 #endif

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define ADELL_ABI_VERSION 4
+#define ADELL_ABI_VERSION 5
 
 /* status codes */
 #define ADELL_OK 0
@@ -138,13 +138,19 @@ typedef struct __attribute__((aligned(64))) adell_item {
                               tile ((o_0 + shear[0][G]) / tile_dim[0], (o_1 + shear[1][G]) / tile_dim[1],
                               o_2 / tile_dim[2]).  Chosen so that a column tile's source footprint
                               stays compact under rotations that couple axis 2 into axes 0/1; all
-                              zero = plain tile grid.  (Completes the struct to 640 bytes.)          */
+                              zero = plain tile grid.                                                */
+  uint8_t dmap[128];       /* opaque CUtensorMap of the destination volume (ADELL_KIND_TSTORE items: their
+                              tiles are written by TMA stores).  Completes the struct to 768 bytes.    */
 } adell_item;
 
 /* adell_item.kind */
 #define ADELL_KIND_GENERIC 0 /* bit-faithful per-voxel path, taps from global memory               */
 #define ADELL_KIND_STAGED 1  /* TMA-staged source footprint, taps from shared memory               */
 #define ADELL_KIND_VCOPY 2   /* identity item: 128-bit vectorised flip/crop copy                   */
+#define ADELL_KIND_TSTORE 3  /* plain identity item (no intensity map, contiguous axis not reversed, aligned
+                                rows): TMA box load -> TMA box store, no consumer instructions.  kind =
+                                ADELL_KIND_TSTORE + split: 3 whole boxes, 4 plane by plane (axis 0 flipped),
+                                5 row by row (axis 1 flipped)                                          */
 
 /* -- library / device ---------------------------------------------------------------- */
 int adell_abi_version(void);

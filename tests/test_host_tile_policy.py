@@ -112,3 +112,34 @@ def test_a_plan_cannot_be_launched():
     plan = BatchPlan([torch.zeros(16, 16, 16)])
     it, tiles, info, _ = plan_items(plan, [(16, 16, 16)])
     assert _lib.load().adell_aug_gather(64, 64, 1, C.byref(info), None) == -1
+
+
+def test_plain_copy_items_leave_through_the_destination_tensor_map():
+    """Identity items without an intensity map and without a flip along the contiguous axis become
+    ADELL_KIND_TSTORE + split (0 whole boxes, 1 plane by plane: axis 0 flipped, 2 row by row: axis 1 flipped);
+    everything else keeps the vectorised consumer copy (ADELL_KIND_VCOPY)."""
+    shape = (48, 40, 32)
+    flips = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0], [0, 0, 1], [1, 1, 1], [0, 0, 0], [0, 0, 0]], bool)
+    vols = [torch.zeros(shape) for _ in range(len(flips))]
+    plan = BatchPlan(vols)
+    plan.flip(flips)
+    scale = np.ones(len(flips)); scale[6] = 1.25
+    plan.intensity(scale=scale, offset=0.0)
+    outs_shapes = [shape] * len(flips)
+    it, tiles, info, outs = plan_items(plan, outs_shapes)
+    by_dst = {int(p): int(k) for p, k in zip(it["dst"], it["kind"])}
+    kinds = [by_dst[o.data_ptr()] for o in outs]
+    assert kinds[:6] == [3, 4, 5, 5, 2, 2]
+    assert kinds[6] == 2            # an intensity map needs the consumers
+    assert kinds[7] == 3
+    assert info.first_copy_tile == 0 and info.total_tiles == int(tiles[len(flips)])   # all of them feed the copy queue
+
+
+def test_unaligned_crop_windows_keep_the_consumer_copy():
+    shape, roi = (40, 40, 40), (32, 32, 32)
+    vols = [torch.zeros(shape) for _ in range(3)]
+    plan = BatchPlan(vols)
+    plan.crop(np.array([[3, 5, 0], [3, 5, 4], [3, 5, 2]]), roi)
+    it, tiles, info, outs = plan_items(plan, [roi] * 3)
+    by_dst = {int(p): int(k) for p, k in zip(it["dst"], it["kind"])}
+    assert [by_dst[o.data_ptr()] for o in outs] == [3, 3, 2]   # a window start that is not 16-byte aligned carries slack columns

@@ -29,20 +29,20 @@ for rep in range(REPS + 2):
     tick("fill items", t)
     t = time.perf_counter()
     n = 32
-    buf = np.zeros(16 * (n * 640 + 256), np.uint8)
+    buf = np.zeros(16 * (n * ISZ + 256), np.uint8)
     infos = []
     for k in range(16):
-        o = k * (n * 640 + 256)
-        it = buf[o:o + n * 640].view(ITEM_DTYPE); it[:] = items[k * n:(k + 1) * n]
-        tiles = buf[o + n * 640:o + n * 640 + 4 * (n + 5)].view(np.int32)
+        o = k * (n * ISZ + 256)
+        it = buf[o:o + n * ISZ].view(ITEM_DTYPE); it[:] = items[k * n:(k + 1) * n]
+        tiles = buf[o + n * ISZ:o + n * ISZ + 4 * (n + 5)].view(np.int32)
         info = _lib.LaunchInfo()
         lib.adell_aug_prepare(it.ctypes.data, n, tiles.ctypes.data, C.byref(info)); infos.append(info)
     tick("aug_prepare (tensor maps)", t)
     t = time.perf_counter(); d = engine._stage(buf, dev); tick("stage+upload", t)
     t = time.perf_counter()
     for k in range(16):
-        o = k * (n * 640 + 256)
-        engine.launch_packed(d[o:o + n * 640 + 4 * (n + 5)], n, infos[k])
+        o = k * (n * ISZ + 256)
+        engine.launch_packed(d[o:o + n * ISZ + 4 * (n + 5)], n, infos[k])
     tick("16 launches", t)
     torch.cuda.synchronize()
 for k, v in T.items():

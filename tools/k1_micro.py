@@ -235,7 +235,7 @@ def main():
             raise SystemExit(name)
         print("  ", tile_stats())
         if PROF:
-            out = (ctypes.c_ulonglong * 8)()
+            out = (ctypes.c_ulonglong * 16)()
             lib.adell_debug_prof(out, 1)
         ts = time_launches(L)
         ms = statistics.mean(ts)
@@ -249,6 +249,9 @@ def main():
             nt = max(v[7], 1)
             print("   per tile: producer prepare %.0f, wait-empty %.0f, issue %.0f cycles | per consumer warp: wait-full %.0f, compute %.0f cycles; %d tiles"
                   % (v[2] / nt, v[0] / nt, v[1] / nt, v[3] / nt / 8, v[4] / nt / 8, nt))
+            for lbl, k in (("resampled", 8), ("consumer-copy", 10), ("TMA-store", 12), ("other", 14)):
+                if v[k + 1]:
+                    print("   %s tiles: %d, %.0f cycles per tile (first warp of the group)" % (lbl, v[k + 1], v[k] / v[k + 1]))
             nl = len(ts)
             print("   consumer-group kernel time: mean %.0f cycles per launch, max over groups and launches %d cycles; event time %.0f cycles at 1965 MHz"
                   % (v[5] / (nl * 148 * 2), v[6], ms * 1e-3 * 1965e6))
