@@ -79,7 +79,7 @@ def _require_cuda(device: torch.device):
 
 def pack_launch(items: np.ndarray):
     """Host-side preparation of one launch: encodes the TMA descriptors of the eligible items
-    (``adell_aug_prepare``) and packs ``items (640 B each) + int32 tile prefix (n+1)`` into one
+    (``adell_aug_prepare``) and packs ``items (768 B each) + int32 tile prefix (n+1)`` into one
     buffer.  Returns ``(uint8 buffer, n_items, LaunchInfo)``."""
     lib = _lib.load()
     n = items.shape[0]
@@ -176,7 +176,7 @@ def prepare_steps(plan: BatchPlan, dst_ptr: np.ndarray, dst_stride: np.ndarray, 
     sizes = [int(x) for x in step_sizes]
     if sum(sizes) != items.shape[0]:
         raise ValueError("step_sizes must add up to the number of volumes")
-    # layout per step: items (640 B each) + int32 prefix + 4 chunk-queue words, padded to 128 B so every slice stays aligned
+    # layout per step: items (768 B each) + int32 prefix + 4 chunk-queue words, padded to 128 B so every slice stays aligned
     ns = np.asarray(sizes, np.int64)
     step_bytes = ns * ISZ + ((4 * (ns + 5) + 127) // 128) * 128
     offs = np.concatenate([[0], np.cumsum(step_bytes)[:-1]]).astype(np.int64)
