@@ -138,6 +138,31 @@ def rician_map(x: torch.Tensor, noise1: torch.Tensor, noise2: torch.Tensor) -> t
     return out
 
 
+def resize(vols: Sequence[torch.Tensor], out_shape: Sequence[int], mode: str = "area") -> list[torch.Tensor]:
+    """``F.interpolate(mode="area" | "nearest")`` of each contiguous fp32 ``[I0, I1, I2]`` volume to
+    ``out_shape`` (``adell_resize``; area = ATen adaptive_avg_pool3d op for op, bit-identical)."""
+    if mode not in ("area", "nearest"):
+        raise NotImplementedError(f"resize mode '{mode}' is not on the device path (area / nearest are)")
+    vols = [v.contiguous() for v in vols]
+    dev = _check_vols(vols)
+    if any(v.dim() != 3 or v.dtype != torch.float32 for v in vols):
+        raise ValueError("resize expects float32 [I0, I1, I2] volumes")
+    out_shape = [int(x) for x in out_shape]
+    outs = [torch.empty(out_shape, dtype=torch.float32, device=dev) for _ in vols]
+    n = len(vols)
+
+    def up(a):
+        return torch.from_numpy(a).pin_memory().to(dev, non_blocking=True)
+
+    d_src = up(np.array([v.data_ptr() for v in vols], np.int64))
+    d_dst = up(np.array([o.data_ptr() for o in outs], np.int64))
+    d_shp = up(np.array([list(v.shape) for v in vols], np.int32))
+    oshape = (C.c_int32 * 3)(*out_shape)
+    _lib.check(_lib.load().adell_resize(d_src.data_ptr(), d_shp.data_ptr(), d_dst.data_ptr(), n, oshape,
+                                        0 if mode == "area" else 1, _stream(dev)), "adell_resize")
+    return outs
+
+
 def scaler_coefs(stats: torch.Tensor, scaler: int, p0: float, p1: float) -> torch.Tensor:
     """``[n, 6]`` coefficients of ``y = ((x*m0 - a)/d)*m1*m2 + b`` for one of the reference scalers."""
     n = stats.shape[0]

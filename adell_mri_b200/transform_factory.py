@@ -12,8 +12,8 @@ transforms of :mod:`adell_mri_b200.transforms`, so an entrypoint can swap
 for the same names from this package.  What differs by design:
 
 * samples enter as channel-first device tensors (the device-resident analogue of what
-  ``LoadImaged`` + ``Orientationd`` hand on); file loading, re-orientation, ``Spacingd`` and
-  ``Resized`` are outside the hot path (SURVEY.md §8(f) row 3) and raise if requested;
+  ``LoadImaged`` + ``Orientationd`` hand on); file loading, re-orientation and ``Spacingd``
+  are outside the hot path (SURVEY.md §8(f) row 3) and raise if requested (``Resized`` runs on the device: K5);
 * members of the augmentation vocabulary that are not gathers / pointwise maps raise
   ``NotImplementedError`` instead of silently doing something else.
 """
@@ -398,6 +398,9 @@ class AugmentationWorkhorsed(T.RandomizableTransform):
         super().__init__(1.0)
         self.augmentations = list(augmentations)
         self.keys, self.mask_keys, self.max_mult, self.N = keys, list(mask_keys), max_mult, N
+        bad = [k for k in self.augmentations if k not in FUSED_AUGMENTS]
+        if bad:
+            raise NotImplementedError(f"workhorse members {bad} are outside the fused GPU hot path")
         base = aug_param_dict if aug_param_dict is not None else _aug_param_dict()
         self.param_dict = {k: {kk: base[k][kk] * max_mult for kk in base[k]} for k in self.augmentations}
         self.transforms = {k: get_transform_d(keys, k, self.param_dict[k], self.mask_keys) for k in self.param_dict}
@@ -527,8 +530,14 @@ def get_augmentations_ssl(all_keys, copied_keys, scaled_crop_size, roi_size, vic
         aug_list = [x for x in generic_augments + mri_specific_augments + spatial_augments if x in FUSED_AUGMENTS]
     aug_list = [x for x in aug_list if x not in transforms_to_remove]
     cropping_strategy = []
-    if scaled_crop_size is not None:
-        raise NotImplementedError("scaled_crop_size uses Resized (area interpolation): outside the fused hot path")
+    if scaled_crop_size is not None:   # augmentations.py:427-444
+        scaled_crop_size = tuple(int(x) for x in scaled_crop_size)
+        small_crop_size = [x // 2 for x in scaled_crop_size]
+        cropping_strategy.extend([
+            T.SpatialPadd(all_keys + copied_keys, small_crop_size),
+            T.RandSpatialCropd(all_keys + copied_keys, roi_size=small_crop_size, random_size=True),
+            T.Resized(all_keys + copied_keys, scaled_crop_size),
+        ])
     if skip_augmentations is True:
         return cropping_strategy
     if vicregl is True:
@@ -582,7 +591,7 @@ class TransformMixin:
 
 def _reject(name, value):
     if value is not None and value is not False and value != []:
-        raise NotImplementedError(f"{name} belongs to the cached loading stage (file IO / Spacingd / Resized): outside the fused hot path")
+        raise NotImplementedError(f"{name} belongs to the cached loading stage (file IO / Spacingd): outside the fused hot path")
 
 
 def _intensity_stage(non_adc_keys, adc_keys, offset_adc: bool):
@@ -630,7 +639,6 @@ class SegmentationTransforms(TransformMixin):
 
     def __post_init__(self):
         _reject("target_spacing", self.target_spacing)
-        _reject("resize_size", self.resize_size)
         _reject("fill_missing", self.fill_missing)
         _reject("brunet", self.brunet)
         _reject("all_aux_keys", list(self.all_aux_keys))
@@ -641,6 +649,9 @@ class SegmentationTransforms(TransformMixin):
 
     def pre_transforms(self):
         transforms = _intensity_stage(self.non_adc_keys, self.adc_keys, offset_adc=False)
+        if self.resize_size is not None and self.resize_keys:   # transforms.py:157-167
+            intp_ = [k for k, kk in zip(self.intp, self.all_keys) if kk in self.resize_keys]
+            transforms.append(T.Resized(list(self.resize_keys), tuple(self.resize_size), mode=intp_))
         if self.pad_size is not None:
             transforms.append(T.SpatialPadd(self.all_keys, self.pad_size))
         if self.crop_size is not None:
@@ -736,7 +747,6 @@ class SSLTransforms(TransformMixin):
 
     def __post_init__(self):
         _reject("target_spacing", self.target_spacing)
-        _reject("resize_size", self.resize_size)
         _reject("jpeg_dataset", self.jpeg_dataset)
         if self.n_dim != 3:
             raise NotImplementedError("the fused hot path is volumetric (n_dim=3)")
@@ -750,6 +760,8 @@ class SSLTransforms(TransformMixin):
             transforms.append(T.CenterSpatialCropd(self.all_keys, [int(j) for j in self.crop_size]))
         if self.pad_size is not None:
             transforms.append(T.SpatialPadd(self.all_keys, [int(j) for j in self.pad_size]))
+        if self.resize_size is not None:   # transforms.py:799-804 (MONAI's default mode: "area")
+            transforms.append(T.Resized(self.all_keys, [int(j) for j in self.resize_size]))
         transforms.append(T.EnsureTyped(self.all_keys))
         if self.skip_augmentations is False:
             transforms.append(CopyEntryd(self.all_keys, {k: kk for k, kk in zip(self.all_keys, self.copied_keys)}))

@@ -733,6 +733,45 @@ class RandAdjustContrastd(_RandIntensityd):
         return d
 
 
+class Resized(MapTransform):
+    """``monai.transforms.Resized`` † (``size_mode="all"``, no anti-aliasing): ``F.interpolate`` with
+    MONAI's default ``mode="area"`` (adaptive average pooling) or ``"nearest"``, per key; a no-op when
+    the shape already matches.  Runs on the device (``adell_resize``, bit-identical to ATen's CPU
+    kernel) over the materialised input and hands a fresh entry on
+    (/root/reference/adell_mri/transform_factory/augmentations.py:427-444: the SSL scaled crop;
+    /root/reference/adell_mri/transform_factory/transforms.py:157-167,455-462: ``resize_size``)."""
+
+    def __init__(self, keys, spatial_size, size_mode: str = "all", mode="area", align_corners=None,
+                 anti_aliasing: bool = False, allow_missing_keys: bool = False, **_):
+        super().__init__(keys, allow_missing_keys)
+        if size_mode != "all" or anti_aliasing:
+            raise NotImplementedError("Resized: only size_mode='all' without anti-aliasing is used by the reference")
+        self.spatial_size = [int(x) for x in spatial_size]
+        n = len(self.keys)
+        self.mode = [mode] * n if isinstance(mode, str) else list(mode)
+        for m in self.mode:
+            if m not in ("area", "nearest"):
+                raise NotImplementedError(f"Resized mode '{m}' is not on the device path (area / nearest are)")
+
+    def __call__(self, data):
+        from . import stats
+
+        d = dict(data)
+        for k, m in zip(self.keys, self.mode):
+            if k not in d:
+                if self.allow_missing_keys:
+                    continue
+                raise KeyError(k)
+            x = d[k]
+            shape = tuple(x.shape[1:])
+            if shape == tuple(self.spatial_size):
+                continue
+            t = (x.tensor() if isinstance(x, Pending) else x).to(torch.float32)
+            outs = stats.resize([t[c] for c in range(t.shape[0])], self.spatial_size, m)
+            d[k] = torch.stack(outs, 0) if len(outs) > 1 else outs[0][None]
+        return d
+
+
 class RandRicianNoised(_RandIntensityd):
     """``monai.transforms.RandRicianNoised`` †: the dict transform's ``R.rand()`` gate, then PER KEY the
     wrapped ``RandRicianNoise(prob=1.0)``: its own ``R.rand()``, ``sigma ~ U(0, std)`` (``sample_std``)
@@ -918,7 +957,6 @@ RandBiasFieldd = not_on_fused_path("RandBiasFieldd")
 RandGaussianSmoothd = not_on_fused_path("RandGaussianSmoothd")
 RandGridDistortiond = not_on_fused_path("RandGridDistortiond")
 RandSimulateLowResolutiond = not_on_fused_path("RandSimulateLowResolutiond")
-Resized = not_on_fused_path("Resized")
 
 
 def all_flip_combinations(flip_axis):

@@ -256,6 +256,17 @@ int adell_mask_bbox(const adell_vol* vols_dev, const int32_t* shapes_dev, int n_
 int adell_gamma_map(const adell_vol* vols_dev, float* const* dst_dev, const float* minmax_dev,
                     const float* gamma_dev, int n_vols, int64_t max_n, void* stream);
 
+/* -- K5: Resized ------------------------------------------------------------------------- */
+#define ADELL_RESIZE_AREA 0     /* F.interpolate(mode="area") = ATen adaptive_avg_pool3d, op for op (bit-identical) */
+#define ADELL_RESIZE_NEAREST 1  /* F.interpolate(mode="nearest") (legacy index rule)                               */
+/* monai.transforms.Resized of the reference's scaled crop
+ * (/root/reference/adell_mri/transform_factory/augmentations.py:427-444) and of its cached stage
+ * (/root/reference/adell_mri/transform_factory/transforms.py:157-167,455-462): volume v, contiguous fp32
+ * [I0,I1,I2] = in_shapes_dev[3v..] at src_dev[v], is resized to the contiguous fp32 [O0,O1,O2] =
+ * out_shape (HOST array of 3) at dst_dev[v].  src_dev / dst_dev are DEVICE arrays of device pointers. */
+int adell_resize(const float* const* src_dev, const int32_t* in_shapes_dev, float* const* dst_dev, int n_vols,
+                 const int32_t* out_shape, int mode, void* stream);
+
 /* monai RandRicianNoise (the SSL workhorse's `rician_noise` member,
  * /root/reference/adell_mri/modules/augmentations.py:53,86,117; RandRicianNoised of --augment noise,
  * /root/reference/adell_mri/transform_factory/augmentations.py:81-91):

@@ -541,6 +541,17 @@ def rand_rician_noise(img: torch.Tensor, R, std: float, mean: float = 0.0, sampl
     return torch.sqrt((img + n1) ** 2 + n2 ** 2), n1, n2
 
 
+def resized(img: torch.Tensor, spatial_size: Sequence[int], mode: str = "area") -> torch.Tensor:
+    """monai Resize.__call__ † (size_mode="all", anti_aliasing=False): a no-op when the shape already
+    matches, else ``F.interpolate(img[None].float(), size, mode)`` — "area" is ATen's
+    adaptive_avg_pool3d (/root/reference/adell_mri/transform_factory/augmentations.py:427-444 uses MONAI's
+    default mode "area"; transforms.py:157-167 passes "area" / "nearest" per key)."""
+    size = tuple(int(x) for x in spatial_size)
+    if tuple(img.shape[1:]) == size:
+        return img
+    return torch.nn.functional.interpolate(img[None].to(torch.float32), size=size, mode=mode)[0]
+
+
 def std_shift_intensity(img: torch.Tensor, factor: float) -> torch.Tensor:
     """monai StdShiftIntensity._stdshift † (nonzero=False, channel_wise=False): ``img + factor *
     std(img)`` with the population standard deviation of the whole array."""

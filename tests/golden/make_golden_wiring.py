@@ -124,6 +124,7 @@ SSL_CASES = {
     "shared_crop": dict(all_keys=["image"], copied_keys=["image_copy"], scaled_crop_size=None, roi_size=[128, 128, 32], vicregl=False, different_crop=False),
     "different_crop": dict(all_keys=["image"], copied_keys=["image_copy"], scaled_crop_size=None, roi_size=[128, 128, 32], vicregl=False, different_crop=True, n_transforms=2),
     "vicregl": dict(all_keys=["image"], copied_keys=["image_copy"], scaled_crop_size=None, roi_size=[96, 96, 24], vicregl=True, different_crop=False),
+    "scaled_crop": dict(all_keys=["image"], copied_keys=["image_copy"], scaled_crop_size=[160, 160, 40], roi_size=[128, 128, 32], vicregl=False, different_crop=False),
 }
 
 
@@ -159,6 +160,11 @@ FACTORY_CASES = {
     "ssl_crop_pad": ("SSLTransforms", dict(all_keys=["image"], copied_keys=["image_copy"], adc_keys=[], non_adc_keys=["image"],
                                             target_spacing=None, crop_size=[160, 160, 40], pad_size=[160, 160, 40], resize_size=None,
                                             in_channels=1, n_dim=3, skip_augmentations=False, jpeg_dataset=False)),
+    "seg_resize": ("SegmentationTransforms", dict(SEG_COMMON, resize_keys=["t2", "adc", "dwi", "mask"], resize_size=[128, 128, 24],
+                                                   crop_size=None, pad_size=[128, 128, 32], random_crop_size=None)),
+    "ssl_resize": ("SSLTransforms", dict(all_keys=["image"], copied_keys=["image_copy"], adc_keys=[], non_adc_keys=["image"],
+                                          target_spacing=None, crop_size=[160, 160, 40], pad_size=[160, 160, 40], resize_size=[96, 96, 24],
+                                          in_channels=1, n_dim=3, skip_augmentations=False, jpeg_dataset=False)),
     "ssl_adc": ("SSLTransforms", dict(all_keys=["t2", "adc"], copied_keys=["t2_copy", "adc_copy"], adc_keys=["adc"], non_adc_keys=["t2"],
                                        target_spacing=None, crop_size=None, pad_size=None, resize_size=None, in_channels=2, n_dim=3,
                                        skip_augmentations=False, jpeg_dataset=False)),

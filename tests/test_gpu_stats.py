@@ -210,3 +210,32 @@ def test_gamma_map_error_is_bounded_by_1e6_of_the_range(gamma, kind):
     want32 = M.adjust_contrast(x.to(torch.float32), gamma)
     assert torch.allclose(got, want32, rtol=2e-5, atol=2e-6 * float(rng))
     assert got[x.argmin()] == float(lo)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["area", "nearest"])
+def test_resize_is_bit_identical_to_torch_interpolate(mode):
+    """adell_resize vs F.interpolate on the CPU (area = ATen adaptive_avg_pool3d): shrinking, growing, mixed,
+    exact halves / doubles, identity, volumes of different input shapes in one call."""
+    R = np.random.RandomState(3)
+    cases = [((80, 72, 20), (64, 64, 16)), ((41, 37, 11), (64, 48, 16)), ((33, 80, 20), (48, 40, 24)), ((32, 32, 8), (64, 64, 16)),
+             ((64, 64, 16), (32, 32, 8)), ((24, 20, 12), (24, 20, 12)), ((97, 101, 37), (80, 80, 20)), ((5, 3, 2), (7, 9, 4))]
+    for out in sorted({o for _, o in cases}):
+        ins = [i for i, o in cases if o == out] + [tuple(int(x) for x in R.randint(out[a] // 2 + 1, 2 * out[a] + 2, 1)[0] for a in range(3)) for _ in range(2)]
+        ins = [tuple(int(v) for v in np.atleast_1d(i)) for i in ins]
+        vols = [torch.from_numpy((R.rand(*i) * 1000 - 200).astype(np.float32)) for i in ins]
+        got = stats.resize([v.to(DEV) for v in vols], out, mode)
+        for v, g in zip(vols, got):
+            want = torch.nn.functional.interpolate(v[None, None], size=out, mode=mode)[0, 0]
+            assert g.shape == want.shape and torch.equal(g.cpu(), want), (tuple(v.shape), out, mode)
+
+
+@pytest.mark.gpu
+def test_resize_full_size_volume_matches_torch():
+    """Config-E sized input (512x512x128 -> 256x256x64, exact 2x2x2 means; and -> 300x300x80, ragged windows)."""
+    g = torch.Generator().manual_seed(0)
+    v = torch.rand((512, 512, 128), generator=g)
+    for out in [(256, 256, 64), (300, 300, 80)]:
+        got = stats.resize([v.to(DEV)], out, "area")[0].cpu()
+        want = torch.nn.functional.interpolate(v[None, None], size=out, mode="area")[0, 0]
+        assert torch.equal(got, want)

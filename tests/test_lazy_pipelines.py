@@ -213,8 +213,10 @@ def test_unknown_and_out_of_scope_tokens_raise():
         F.get_augmentations_unet(["blur"], ["a"], ["a"], [])
     with pytest.raises(NotImplementedError):
         F.get_augmentations_class(["noise"], ["a"], None, [])
+    with pytest.raises(NotImplementedError):   # a workhorse member outside the fused path
+        F.get_augmentations_ssl(["a"], ["b"], None, [8, 8, 8], False, False, aug_list=["gaussian_noise", "gibbs_noise", "rotate_x"])
     with pytest.raises(NotImplementedError):
-        F.get_augmentations_ssl(["a"], ["b"], [8, 8, 8], [8, 8, 8], False, False)
+        T.Resized(["a"], [8, 8, 8], mode="trilinear")
 
 
 @pytest.mark.gpu
@@ -241,3 +243,33 @@ def test_workhorse_pointwise_members_match_eager_reference(members):
             assert not torch.equal(r, s["image"])
     finally:
         T.set_mode(strict=False)
+
+
+@pytest.mark.gpu
+def test_ssl_scaled_crop_matches_eager_reference():
+    """get_augmentations_ssl(scaled_crop_size=s): SpatialPadd(s/2) -> RandSpatialCropd(s/2, random_size=True) ->
+    Resized(s, "area") -> shared RandSpatialCropd(roi) (augmentations.py:427-444,487-492; skip_augmentations keeps the
+    chain deterministic after the crops); the resized volumes are bit-identical to ATen's."""
+    dev = "cuda:0"
+    R = np.random.RandomState(14)
+    keys, copied, shape, scaled, roi = ["image"], ["image_copy"], (44, 30, 18), [40, 40, 16], [40, 40, 16]
+    samples = _samples(R, 6, keys, shape, mask=False)
+    small = [x // 2 for x in scaled]
+    crop_only = F.get_augmentations_ssl(keys, copied, scaled, roi, False, False, skip_augmentations=True)
+    assert [type(t).__name__ for t in crop_only] == ["SpatialPadd", "RandSpatialCropd", "Resized"]
+    lazy = T.Compose(crop_only).set_random_state(33)
+    seeds = P.M.compose_set_random_state(33, 1)
+    Rc = np.random.RandomState(seeds[0])
+    sizes = set()
+    for s in samples:
+        d = {"image": s["image"].to(dev), "image_copy": s["image"].clone().to(dev)}
+        out = lazy(d)
+        x = P.M.spatial_pad(s["image"], small)
+        starts, size = P.M.rand_spatial_crop_draw(Rc, tuple(x.shape[1:]), small, random_size=True)
+        sizes.add(tuple(size))
+        want = P.M.resized(P.M.crop(x, starts, size), scaled, "area")
+        for k in ("image", "image_copy"):
+            g = out[k].tensor() if isinstance(out[k], T.Pending) else out[k]
+            assert tuple(g.shape) == (1, *scaled)
+            assert torch.equal(g.cpu(), want), k
+    assert len(sizes) > 1    # random window sizes were drawn

@@ -70,6 +70,12 @@ def ref_cfg(r):
                 "pos_ratio": 0.5}   # MONAI defaults pos=neg=1
     if cls == "CenterSpatialCropd":
         return {"cls": cls, "keys": keys, "roi_size": [int(x) for x in a[1]]}
+    if cls == "SpatialPadd":
+        return {"cls": cls, "keys": keys, "spatial_size": [int(x) for x in a[1]]}
+    if cls == "Resized":   # MONAI default mode: "area"
+        mode = k.get("mode", "area")
+        return {"cls": cls, "keys": keys, "spatial_size": [int(x) for x in (a[1] if len(a) > 1 else k["spatial_size"])],
+                "mode": [mode] * len(keys) if isinstance(mode, str) else list(mode)}
     if cls == "ExposeTransformKeyMetad":
         return {"cls": cls, "key": a[0], "transform_class": a[1], "nested_pattern": list(a[2]), "output_key": a[3]}
     if cls == "Lambdad":
@@ -125,6 +131,10 @@ def our_cfg(t, roi_size=None):
                 "pos_ratio": t.pos_ratio}
     if cls == "CenterSpatialCropd":
         return {"cls": cls, "keys": keys, "roi_size": t.roi_size}
+    if cls == "SpatialPadd":
+        return {"cls": cls, "keys": keys, "spatial_size": [int(x) for x in t.spatial_size]}
+    if cls == "Resized":
+        return {"cls": cls, "keys": keys, "spatial_size": [int(x) for x in t.spatial_size], "mode": list(t.mode)}
     if cls == "Lambdad":
         return {"cls": cls, "keys": keys, "flatten_box": [[float(v) for v in t.func(b)] for b in G.FLATTEN_BOX_INPUTS]}
     if cls in ("RandGaussianNoised", "RandRicianNoised"):
@@ -201,6 +211,8 @@ def ref_stage_cfg(r):
         return {"cls": cls, "keys": keys, "roi_size": [int(x) for x in a[1]]}
     if cls == "EnsureTyped":
         return {"cls": cls, "keys": keys}
+    if cls == "Resized":
+        return ref_cfg(r)
     if cls == "AdjustSizesd":
         return {"cls": cls, "keys": keys, "mode": k["mode"]}
     if cls == "FgBgToIndicesd":
@@ -239,6 +251,8 @@ def our_stage_cfg(t):
         return {"cls": cls, "keys": keys}
     if cls == "AdjustSizesd":
         return {"cls": cls, "keys": keys, "mode": t.mode}
+    if cls == "Resized":
+        return our_cfg(t)
     if cls == "ConcatItemsd":
         return {"cls": cls, "keys": keys, "name": t.name}
     if cls == "CopyEntryd":
