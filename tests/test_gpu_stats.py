@@ -221,8 +221,9 @@ def test_resize_is_bit_identical_to_torch_interpolate(mode):
     cases = [((80, 72, 20), (64, 64, 16)), ((41, 37, 11), (64, 48, 16)), ((33, 80, 20), (48, 40, 24)), ((32, 32, 8), (64, 64, 16)),
              ((64, 64, 16), (32, 32, 8)), ((24, 20, 12), (24, 20, 12)), ((97, 101, 37), (80, 80, 20)), ((5, 3, 2), (7, 9, 4))]
     for out in sorted({o for _, o in cases}):
-        ins = [i for i, o in cases if o == out] + [tuple(int(x) for x in R.randint(out[a] // 2 + 1, 2 * out[a] + 2, 1)[0] for a in range(3)) for _ in range(2)]
-        ins = [tuple(int(v) for v in np.atleast_1d(i)) for i in ins]
+        ins = [i for i, o in cases if o == out]
+        for _ in range(2):   # two more inputs of random extents between half and twice the output
+            ins.append(tuple(int(R.randint(out[ax] // 2 + 1, 2 * out[ax] + 2)) for ax in range(3)))
         vols = [torch.from_numpy((R.rand(*i) * 1000 - 200).astype(np.float32)) for i in ins]
         got = stats.resize([v.to(DEV) for v in vols], out, mode)
         for v, g in zip(vols, got):
