@@ -33,37 +33,73 @@ __device__ __forceinline__ int rs_nearest(int o, int O, int I) {
   return min(static_cast<int>(floorf(__fmul_rn(static_cast<float>(o), scale))), I - 1);
 }
 
-// src: contiguous [I0, I1, I2] fp32 per volume (in_shapes: 3 int32 per volume), dst: contiguous [O0, O1, O2]
+// src: contiguous [I0, I1, I2] fp32 per volume (in_shapes: 3 int32 per volume), dst: contiguous [O0, O1, O2].
+// Every block first tabulates the window bounds (area) or source indices (nearest) of the three output
+// axes for its volume in shared memory — O0 + O1 + O2 entries instead of six IEEE divisions per voxel —
+// then walks its voxels with 32-bit index arithmetic.
 template <bool AREA>
 __global__ void __launch_bounds__(RS_THREADS)
 rs_resize(const float* const* __restrict__ srcs, const int32_t* __restrict__ in_shapes, float* const* __restrict__ dsts,
           int O0, int O1, int O2) {
+  extern __shared__ int2 rs_tab[];   // [O0 | O1 | O2] -> {start, end} (area) or {index, -} (nearest)
   const int v = blockIdx.y;
   const float* __restrict__ src = srcs[v];
   float* __restrict__ dst = dsts[v];
   const int I0 = __ldg(in_shapes + 3 * v), I1 = __ldg(in_shapes + 3 * v + 1), I2 = __ldg(in_shapes + 3 * v + 2);
-  const int64_t n = static_cast<int64_t>(O0) * O1 * O2;
-  const int64_t nthr = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += nthr) {
-    const int ow = static_cast<int>(i % O2);
-    const int64_t r = i / O2;
-    const int oh = static_cast<int>(r % O1), od = static_cast<int>(r / O1);
+  for (int t = threadIdx.x; t < O0 + O1 + O2; t += RS_THREADS) {
+    const int ax = t < O0 ? 0 : (t < O0 + O1 ? 1 : 2);
+    const int o = ax == 0 ? t : (ax == 1 ? t - O0 : t - O0 - O1);
+    const int O = ax == 0 ? O0 : (ax == 1 ? O1 : O2), I = ax == 0 ? I0 : (ax == 1 ? I1 : I2);
+    rs_tab[t] = AREA ? make_int2(rs_start(o, O, I), rs_end(o, O, I)) : make_int2(rs_nearest(o, O, I), 0);
+  }
+  __syncthreads();
+  const int2* __restrict__ t0 = rs_tab, *t1 = rs_tab + O0, *t2 = rs_tab + O0 + O1;
+  const unsigned n = static_cast<unsigned>(O0) * O1 * O2;   // < 2^31 (checked by the host)
+  const unsigned nthr = gridDim.x * blockDim.x;
+  const unsigned uO2 = O2, uO1 = O1;
+  // (od, oh, ow) of the thread's first voxel and of the grid stride, then carried additions: no
+  // division inside the loop
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned r = i / uO2, ow = i - r * uO2, od = r / uO1, oh = r - od * uO1;
+  const unsigned sr = nthr / uO2, sw = nthr - sr * uO2, sd = sr / uO1, sh = sr - sd * uO1;
+  for (; i < n; i += nthr, ow += sw, oh += sh, od += sd) {
+    if (ow >= uO2) { ow -= uO2; ++oh; }
+    if (oh >= uO1) { oh -= uO1; ++od; }
     if (AREA) {
-      const int d0 = rs_start(od, O0, I0), d1 = rs_end(od, O0, I0);
-      const int h0 = rs_start(oh, O1, I1), h1 = rs_end(oh, O1, I1);
-      const int w0 = rs_start(ow, O2, I2), w1 = rs_end(ow, O2, I2);
+      const int2 d = t0[od], h = t1[oh], w = t2[ow];
+      const int kd = d.y - d.x, kh = h.y - h.x, kw = w.y - w.x;
       float sum = 0.0f;
-      for (int a = d0; a < d1; ++a)
-        for (int b = h0; b < h1; ++b) {
-          const float* __restrict__ row = src + (static_cast<int64_t>(a) * I1 + b) * I2;
-          for (int c = w0; c < w1; ++c) sum = __fadd_rn(sum, __ldg(row + c));
+      if (kd <= 2 && kh <= 2 && kw <= 2) {
+        // the common case (scale factors between 1/2 and 2): all taps in flight at once, then ATen's
+        // summation order (d, h, w); absent taps are not added
+        const float* __restrict__ p = src + (static_cast<int64_t>(d.x) * I1 + h.x) * I2 + w.x;
+        const int64_t sd = kd > 1 ? static_cast<int64_t>(I1) * I2 : 0, sh = kh > 1 ? I2 : 0;
+        const int sw = kw > 1 ? 1 : 0;
+        const float v000 = __ldg(p), v001 = __ldg(p + sw), v010 = __ldg(p + sh), v011 = __ldg(p + sh + sw);
+        const float v100 = __ldg(p + sd), v101 = __ldg(p + sd + sw), v110 = __ldg(p + sd + sh), v111 = __ldg(p + sd + sh + sw);
+        sum = __fadd_rn(sum, v000);
+        if (kw > 1) sum = __fadd_rn(sum, v001);
+        if (kh > 1) { sum = __fadd_rn(sum, v010); if (kw > 1) sum = __fadd_rn(sum, v011); }
+        if (kd > 1) {
+          sum = __fadd_rn(sum, v100);
+          if (kw > 1) sum = __fadd_rn(sum, v101);
+          if (kh > 1) { sum = __fadd_rn(sum, v110); if (kw > 1) sum = __fadd_rn(sum, v111); }
         }
-      const float q = __fdiv_rn(__fdiv_rn(__fdiv_rn(sum, static_cast<float>(d1 - d0)), static_cast<float>(h1 - h0)),
-                                static_cast<float>(w1 - w0));
+      } else {
+        for (int a = d.x; a < d.y; ++a)
+          for (int b = h.x; b < h.y; ++b) {
+            const float* __restrict__ row = src + (static_cast<int64_t>(a) * I1 + b) * I2;
+            for (int c = w.x; c < w.y; ++c) sum = __fadd_rn(sum, __ldg(row + c));
+          }
+      }
+      // sum / kd / kh / kw, one IEEE division after the other (by 1: nothing, by 2: an exact halving)
+      float q = sum;
+      q = kd == 1 ? q : (kd == 2 ? __fmul_rn(q, 0.5f) : __fdiv_rn(q, static_cast<float>(kd)));
+      q = kh == 1 ? q : (kh == 2 ? __fmul_rn(q, 0.5f) : __fdiv_rn(q, static_cast<float>(kh)));
+      q = kw == 1 ? q : (kw == 2 ? __fmul_rn(q, 0.5f) : __fdiv_rn(q, static_cast<float>(kw)));
       __stcs(dst + i, q);
     } else {
-      const int a = rs_nearest(od, O0, I0), b = rs_nearest(oh, O1, I1), c = rs_nearest(ow, O2, I2);
-      __stcs(dst + i, __ldg(src + (static_cast<int64_t>(a) * I1 + b) * I2 + c));
+      __stcs(dst + i, __ldg(src + (static_cast<int64_t>(t0[od].x) * I1 + t1[oh].x) * I2 + t2[ow].x));
     }
   }
 }
@@ -78,21 +114,24 @@ extern "C" int adell_resize(const float* const* src_dev, const int32_t* in_shape
   const int O0 = out_shape[0], O1 = out_shape[1], O2 = out_shape[2];
   if (O0 <= 0 || O1 <= 0 || O2 <= 0 || n_vols > 65535) return ADELL_ERR_BAD_ARG;
   const int64_t n = static_cast<int64_t>(O0) * O1 * O2;
+  if (n > 0x7fffffffLL) return ADELL_ERR_BAD_ARG;
+  const size_t tab = sizeof(int2) * (static_cast<size_t>(O0) + O1 + O2);
+  if (tab > 48 * 1024) return ADELL_ERR_BAD_ARG;
   int dev = 0, sms = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (e != cudaSuccess) { (void)cudaGetLastError(); return adell_map_cuda_error(e); }
-  // whole waves of the SM count, about eight voxels per thread
-  int64_t blocks = (n + RS_THREADS * 8 - 1) / (RS_THREADS * 8);
+  // a block amortises its tables over >= 16 voxels per thread; whole waves of the SM count
+  int64_t blocks = (n + RS_THREADS * 16 - 1) / (RS_THREADS * 16);
   const int64_t wave = (static_cast<int64_t>(sms) * 8 + n_vols - 1) / n_vols;
   if (blocks > wave) blocks = (blocks + wave - 1) / wave * wave;
-  if (blocks > 65535 * 16) blocks = 65535 * 16;
+  if (blocks > 65535) blocks = 65535;
   if (blocks < 1) blocks = 1;
   dim3 grid(static_cast<unsigned>(blocks), static_cast<unsigned>(n_vols));
   if (mode == ADELL_RESIZE_AREA)
-    rs_resize<true><<<grid, RS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(src_dev, in_shapes_dev, dst_dev, O0, O1, O2);
+    rs_resize<true><<<grid, RS_THREADS, tab, static_cast<cudaStream_t>(stream)>>>(src_dev, in_shapes_dev, dst_dev, O0, O1, O2);
   else
-    rs_resize<false><<<grid, RS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(src_dev, in_shapes_dev, dst_dev, O0, O1, O2);
+    rs_resize<false><<<grid, RS_THREADS, tab, static_cast<cudaStream_t>(stream)>>>(src_dev, in_shapes_dev, dst_dev, O0, O1, O2);
   ADELL_CUDA_CHECK_LAUNCH();
   return ADELL_OK;
 }

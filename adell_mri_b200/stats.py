@@ -148,15 +148,17 @@ def resize(vols: Sequence[torch.Tensor], out_shape: Sequence[int], mode: str = "
     if any(v.dim() != 3 or v.dtype != torch.float32 for v in vols):
         raise ValueError("resize expects float32 [I0, I1, I2] volumes")
     out_shape = [int(x) for x in out_shape]
-    outs = [torch.empty(out_shape, dtype=torch.float32, device=dev) for _ in vols]
     n = len(vols)
-
-    def up(a):
-        return torch.from_numpy(a).pin_memory().to(dev, non_blocking=True)
-
-    d_src = up(np.array([v.data_ptr() for v in vols], np.int64))
-    d_dst = up(np.array([o.data_ptr() for o in outs], np.int64))
-    d_shp = up(np.array([list(v.shape) for v in vols], np.int32))
+    block = torch.empty((n, *out_shape), dtype=torch.float32, device=dev)   # one allocation for all outputs
+    outs = list(block.unbind(0))
+    # one staging upload: source pointers, destination pointers, input extents
+    host = np.empty(5 * n, np.int64)
+    host[:n] = [v.data_ptr() for v in vols]
+    stride = block.stride(0) * 4
+    host[n:2 * n] = block.data_ptr() + stride * np.arange(n, dtype=np.int64)
+    host[2 * n:].view(np.int32)[:3 * n] = np.array([list(v.shape) for v in vols], np.int32).reshape(-1)
+    staged = torch.from_numpy(host).pin_memory().to(dev, non_blocking=True)
+    d_src, d_dst, d_shp = staged[:n], staged[n:2 * n], staged[2 * n:]
     oshape = (C.c_int32 * 3)(*out_shape)
     _lib.check(_lib.load().adell_resize(d_src.data_ptr(), d_shp.data_ptr(), d_dst.data_ptr(), n, oshape,
                                         0 if mode == "area" else 1, _stream(dev)), "adell_resize")
