@@ -1102,9 +1102,14 @@ __device__ unsigned long long k1_prof[16];
 
 // Producer: derive the tile state (and the consumers' register image) in the given slot.  The
 // item itself is fetched from global memory only when the tile sequence moves on to a new item.
+struct K1Walk {
+  int prev_tile = -2;      // last tile this producer prepared
+  int b0 = 0, b1 = 0, b2 = 0;  // its tile coordinates inside the item
+  int fresh = 0;           // slots of the stream's ring that already hold the current item's context
+};
 __device__ __forceinline__ void k1_prepare(const adell_item* __restrict__ items, const int32_t* ts, int n_items,
                                            int tile, int& item, int& cur_start, int& next_start, int& cached_item,
-                                           K1Ctx& priv, K1Slot& sl, uint32_t box_addr, int lane) {
+                                           K1Ctx& priv, K1Slot& sl, uint32_t box_addr, int lane, K1Walk& wk, int ring_slots) {
   // monotone walk over the per-item tile prefix, 32 entries per step (one load latency per step,
   // not one per item skipped); `ts` is the shared-memory copy of the prefix when it fits
   while (tile >= next_start) {
@@ -1118,7 +1123,8 @@ __device__ __forceinline__ void k1_prepare(const adell_item* __restrict__ items,
   }
   constexpr int kItemWords = (sizeof(adell_item) - 128) / 4;  // without the tensor map
   uint32_t* pw = reinterpret_cast<uint32_t*>(&priv) + 32;
-  if (item != cached_item) {
+  const bool new_item = item != cached_item;
+  if (new_item) {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(items + item) + 32;
 #pragma unroll
     for (int w = 0; w < (kItemWords + 31) / 32; ++w)
@@ -1127,22 +1133,31 @@ __device__ __forceinline__ void k1_prepare(const adell_item* __restrict__ items,
     if (lane == 0) k1_ctx_finish(priv);
     __syncwarp();
     cached_item = item;
+    wk.fresh = 0;
   }
-  {
-    // whole K1Ctx (item image + derived constants), minus the unused tensor-map bytes
+  // whole K1Ctx (item image + derived constants), minus the unused tensor-map bytes — only while some
+  // slot of the ring (visited round-robin) still holds another item's context: an item has hundreds of tiles
+  if (wk.fresh < ring_slots) {
     constexpr int kWords = (sizeof(K1Ctx) - 128) / 4;
     uint32_t* dw = reinterpret_cast<uint32_t*>(&sl.ctx) + 32;
 #pragma unroll
     for (int w = 0; w < (kWords + 31) / 32; ++w)
       if (w * 32 + lane < kWords) dw[w * 32 + lane] = pw[w * 32 + lane];
+    ++wk.fresh;
+    __syncwarp();
   }
-  __syncwarp();
+  // tile coordinates inside the item: the successor of the previous tile by carries, else two divisions
   const int n1 = priv.it.n_tiles[1], n2 = priv.it.n_tiles[2];
-  int local = tile - cur_start;
-  const int b2 = local % n2; local /= n2;
-  const int b1 = local % n1;
-  const int b0 = local / n1;
-  k1_tile_setup(sl.ctx, sl, b0, b1, b2, box_addr, lane);
+  if (!new_item && tile == wk.prev_tile + 1 && tile > cur_start) {
+    if (++wk.b2 == n2) { wk.b2 = 0; if (++wk.b1 == n1) { wk.b1 = 0; ++wk.b0; } }
+  } else {
+    int local = tile - cur_start;
+    wk.b2 = local % n2; local /= n2;
+    wk.b1 = local % n1;
+    wk.b0 = local / n1;
+  }
+  wk.prev_tile = tile;
+  k1_tile_setup(sl.ctx, sl, wk.b0, wk.b1, wk.b2, box_addr, lane);
   if (lane == 0) sl.tl.item = item;
   __syncwarp();
 }
@@ -1217,6 +1232,7 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
     // compute-bound and a memory-bound tile at once instead of all SMs going through the same phases.
     int q = strm & 1;
     bool switched = false;
+    K1Walk wk;
     const bool idle = (chunk >> 16) == strm + 1;   // measurement aid (ADELL_K1_IDLE_STREAM)
     chunk &= 0xffff;
     K1_PROF_DECL
@@ -1252,7 +1268,7 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
       // safe to overwrite: the stream has one more slot than stages, and this warp's previous issue
       // waited for the release of the stage of the slot's previous tile
       k1_prepare(items, ts, n_items, tile, item, cur_start, next_start, cached_item, priv[strm], slots[slot],
-                 smem_u32(smem + static_cast<size_t>(stage) * stage_bytes), lane);
+                 smem_u32(smem + static_cast<size_t>(stage) * stage_bytes), lane, wk, rl.n);
       K1_PROF_ADD(2)
       mbar_wait_relaxed(empty + stage, rs.phase ^ 1);
       K1_PROF_ADD(0)
