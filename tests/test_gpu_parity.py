@@ -336,3 +336,53 @@ def test_chunk_queues_rearm_on_relaunch(mix):
                 assert torch.equal(got[i], refs[i]), (mix, rep, i)
     q = dev_buf[cnt * engine.ISZ + 4 * (cnt + 1):].view(torch.int32).cpu()
     assert q.tolist()[:3] == [0, 0, 0]   # both queues and the drained-producer count are back to zero
+
+
+@pytest.mark.parametrize("shape,roi,start", [
+    ((48, 40, 32), (48, 40, 32), (0, 0, 0)),        # whole volumes, full tiles
+    ((50, 37, 24), (50, 37, 24), (0, 0, 0)),        # ragged along all axes, rows narrower than the 32-wide box
+    ((60, 52, 72), (41, 35, 40), (7, 9, 8)),        # crop window, 16-byte aligned start, two tiles + a ragged one along axis 2
+    ((33, 18, 8), (33, 18, 8), (0, 0, 0)),          # one column group only
+])
+def test_tma_store_copy_tiles_are_bit_exact(shape, roi, start):
+    """Plain copy items leave through the destination tensor map (ADELL_KIND_TSTORE): whole boxes, and plane by
+    plane to the mirrored plane under an axis-0 flip; stores that reach past the item's extents are clipped by
+    the map, never written into the neighbouring channel of the collated tensor.  Items that need the
+    consumers (axis-1 / axis-2 flips, an intensity map) share the launch."""
+    import ctypes as C
+
+    from adell_mri_b200 import _lib, engine
+    from adell_mri_b200.plan import ITEM_DTYPE
+
+    R = np.random.RandomState(sum(shape))
+    flips = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0], [0, 0, 1], [1, 0, 1], [0, 0, 0], [1, 0, 0]], bool)
+    n = len(flips)
+    scale = np.ones(n); scale[6] = 1.5
+    vols = [torch.from_numpy(R.rand(*shape).astype(np.float32)) for _ in range(n)]
+    plan = BatchPlan([v.to(DEV) for v in vols])
+    plan.crop(np.array([start] * n), roi)
+    plan.flip(flips)
+    plan.intensity(scale=scale, offset=0.0)
+    # destination: channel slices of one collated tensor, poisoned so that a stray store shows
+    out = torch.full((2, n // 2, *roi), float("nan"), device=DEV)
+    dsts = [out[i // (n // 2), i % (n // 2)] for i in range(n)]
+    dst_ptr = np.array([d.data_ptr() for d in dsts], np.uint64)
+    dst_stride = np.array([d.stride() for d in dsts], np.int64)
+    items = plan.build_launches(dst_ptr, dst_stride, None)[-1]
+    probe = np.zeros(n, ITEM_DTYPE); probe[:] = items
+    tiles = np.zeros(n + 5, np.int32)
+    info = _lib.LaunchInfo()
+    _lib.check(_lib.load().adell_aug_plan(probe.ctypes.data, n, tiles.ctypes.data, C.byref(info)), "adell_aug_plan")
+    kind = {int(p): int(k) for p, k in zip(probe["dst"], probe["kind"])}
+    assert [kind[int(p)] for p in dst_ptr] == [3, 4, 2, 2, 2, 2, 2, 4]
+    engine.execute(plan, dsts)
+    torch.cuda.synchronize()
+    got = out.cpu()
+    assert not torch.isnan(got).any()
+    for i, v in enumerate(vols):
+        r = M.crop(v[None], start, roi)
+        fl = [a for a in range(3) if flips[i, a]]
+        r = (M.flip(r, fl) if fl else r)[0]
+        if i == 6:
+            r = r * np.float32(1.5)
+        assert torch.equal(got[i // (n // 2), i % (n // 2)], r), i
