@@ -104,6 +104,86 @@ rs_resize(const float* const* __restrict__ srcs, const int32_t* __restrict__ in_
   }
 }
 
+// ATen's window average of one output voxel, any window size (sequential sum in (d, h, w) order).
+__device__ __forceinline__ float rs_area_one(const float* __restrict__ src, int I1, int I2, int2 d, int2 h, int2 w) {
+  float sum = 0.0f;
+  for (int a = d.x; a < d.y; ++a)
+    for (int b = h.x; b < h.y; ++b) {
+      const float* __restrict__ row = src + (static_cast<int64_t>(a) * I1 + b) * I2;
+      for (int c = w.x; c < w.y; ++c) sum = __fadd_rn(sum, __ldg(row + c));
+    }
+  return sum;
+}
+__device__ __forceinline__ float rs_div(float q, int k) {  // q / k: by 1 nothing, by 2 an exact halving
+  return k == 1 ? q : (k == 2 ? __fmul_rn(q, 0.5f) : __fdiv_rn(q, static_cast<float>(k)));
+}
+
+// Area, O2 a multiple of four: one thread produces four consecutive voxels of an output row.  The
+// (d, h) windows and the (at most four) source row pointers are shared by the four, the taps of a voxel
+// are in flight together, the result leaves as one 128-bit store.
+__global__ void __launch_bounds__(RS_THREADS)
+rs_area_quad(const float* const* __restrict__ srcs, const int32_t* __restrict__ in_shapes, float* const* __restrict__ dsts,
+             int O0, int O1, int O2) {
+  extern __shared__ int2 rs_tab[];
+  const int v = blockIdx.y;
+  const float* __restrict__ src = srcs[v];
+  float* __restrict__ dst = dsts[v];
+  const int I0 = __ldg(in_shapes + 3 * v), I1 = __ldg(in_shapes + 3 * v + 1), I2 = __ldg(in_shapes + 3 * v + 2);
+  for (int t = threadIdx.x; t < O0 + O1 + O2; t += RS_THREADS) {
+    const int ax = t < O0 ? 0 : (t < O0 + O1 ? 1 : 2);
+    const int o = ax == 0 ? t : (ax == 1 ? t - O0 : t - O0 - O1);
+    const int O = ax == 0 ? O0 : (ax == 1 ? O1 : O2), I = ax == 0 ? I0 : (ax == 1 ? I1 : I2);
+    rs_tab[t] = make_int2(rs_start(o, O, I), rs_end(o, O, I));
+  }
+  __syncthreads();
+  const int2* __restrict__ t0 = rs_tab, *t1 = rs_tab + O0, *t2 = rs_tab + O0 + O1;
+  const unsigned Q = static_cast<unsigned>(O2) >> 2, uO1 = O1;
+  const unsigned n = static_cast<unsigned>(O0) * O1 * Q;
+  const unsigned nthr = gridDim.x * blockDim.x;
+  const bool vec = (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;
+  const int64_t plane = static_cast<int64_t>(I1) * I2;
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned r = i / Q, oq = i - r * Q, od = r / uO1, oh = r - od * uO1;
+  const unsigned sr = nthr / Q, sq = nthr - sr * Q, sd = sr / uO1, sh = sr - sd * uO1;
+  for (; i < n; i += nthr, oq += sq, oh += sh, od += sd) {
+    if (oq >= Q) { oq -= Q; ++oh; }
+    if (oh >= uO1) { oh -= uO1; ++od; }
+    const int2 d = t0[od], h = t1[oh];
+    const int kd = d.y - d.x, kh = h.y - h.x;
+    const float* __restrict__ r00 = src + (static_cast<int64_t>(d.x) * I1 + h.x) * I2;
+    const float* __restrict__ r01 = r00 + (kh > 1 ? I2 : 0);
+    const float* __restrict__ r10 = r00 + (kd > 1 ? plane : 0);
+    const float* __restrict__ r11 = r10 + (kh > 1 ? I2 : 0);
+    const bool small = kd <= 2 && kh <= 2;
+    float q[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int2 w = t2[4 * oq + j];
+      const int kw = w.y - w.x;
+      float sum;
+      if (small && kw <= 2) {
+        const int c0 = w.x, c1 = w.x + (kw > 1 ? 1 : 0);
+        const float v000 = __ldg(r00 + c0), v001 = __ldg(r00 + c1), v010 = __ldg(r01 + c0), v011 = __ldg(r01 + c1);
+        const float v100 = __ldg(r10 + c0), v101 = __ldg(r10 + c1), v110 = __ldg(r11 + c0), v111 = __ldg(r11 + c1);
+        sum = __fadd_rn(0.0f, v000);
+        if (kw > 1) sum = __fadd_rn(sum, v001);
+        if (kh > 1) { sum = __fadd_rn(sum, v010); if (kw > 1) sum = __fadd_rn(sum, v011); }
+        if (kd > 1) {
+          sum = __fadd_rn(sum, v100);
+          if (kw > 1) sum = __fadd_rn(sum, v101);
+          if (kh > 1) { sum = __fadd_rn(sum, v110); if (kw > 1) sum = __fadd_rn(sum, v111); }
+        }
+      } else {
+        sum = rs_area_one(src, I1, I2, d, h, w);
+      }
+      q[j] = rs_div(rs_div(rs_div(sum, kd), kh), kw);
+    }
+    float* __restrict__ o = dst + (static_cast<int64_t>(od) * O1 + oh) * O2 + 4 * oq;
+    if (vec) __stcs(reinterpret_cast<float4*>(o), make_float4(q[0], q[1], q[2], q[3]));
+    else { o[0] = q[0]; o[1] = q[1]; o[2] = q[2]; o[3] = q[3]; }
+  }
+}
+
 }  // namespace
 
 extern "C" int adell_resize(const float* const* src_dev, const int32_t* in_shapes_dev, float* const* dst_dev, int n_vols,
@@ -128,7 +208,14 @@ extern "C" int adell_resize(const float* const* src_dev, const int32_t* in_shape
   if (blocks > 65535) blocks = 65535;
   if (blocks < 1) blocks = 1;
   dim3 grid(static_cast<unsigned>(blocks), static_cast<unsigned>(n_vols));
-  if (mode == ADELL_RESIZE_AREA)
+  if (mode == ADELL_RESIZE_AREA && (O2 & 3) == 0) {
+    int64_t qb = (n / 4 + RS_THREADS * 4 - 1) / (RS_THREADS * 4);   // four quads per thread
+    if (qb > wave) qb = (qb + wave - 1) / wave * wave;
+    if (qb > 65535) qb = 65535;
+    if (qb < 1) qb = 1;
+    rs_area_quad<<<dim3(static_cast<unsigned>(qb), static_cast<unsigned>(n_vols)), RS_THREADS, tab, static_cast<cudaStream_t>(stream)>>>(
+        src_dev, in_shapes_dev, dst_dev, O0, O1, O2);
+  } else if (mode == ADELL_RESIZE_AREA)
     rs_resize<true><<<grid, RS_THREADS, tab, static_cast<cudaStream_t>(stream)>>>(src_dev, in_shapes_dev, dst_dev, O0, O1, O2);
   else
     rs_resize<false><<<grid, RS_THREADS, tab, static_cast<cudaStream_t>(stream)>>>(src_dev, in_shapes_dev, dst_dev, O0, O1, O2);

@@ -219,7 +219,8 @@ def test_resize_is_bit_identical_to_torch_interpolate(mode):
     exact halves / doubles, identity, volumes of different input shapes in one call."""
     R = np.random.RandomState(3)
     cases = [((80, 72, 20), (64, 64, 16)), ((41, 37, 11), (64, 48, 16)), ((33, 80, 20), (48, 40, 24)), ((32, 32, 8), (64, 64, 16)),
-             ((64, 64, 16), (32, 32, 8)), ((24, 20, 12), (24, 20, 12)), ((97, 101, 37), (80, 80, 20)), ((5, 3, 2), (7, 9, 4))]
+             ((64, 64, 16), (32, 32, 8)), ((24, 20, 12), (24, 20, 12)), ((97, 101, 37), (80, 80, 20)), ((5, 3, 2), (7, 9, 4)),
+             ((41, 37, 11), (30, 30, 10)), ((20, 20, 9), (33, 17, 7)), ((90, 64, 50), (16, 16, 6))]   # rows that are not a multiple of four; 6-wide windows
     for out in sorted({o for _, o in cases}):
         ins = [i for i, o in cases if o == out]
         for _ in range(2):   # two more inputs of random extents between half and twice the output
