@@ -1502,7 +1502,7 @@ struct K1Tuning {
   K1Tuning() {
     auto num = [](const char* name, int lo, int hi, int dflt) {
       const char* e = getenv(name);
-      if (e == nullptr) return dflt;
+      if (e == nullptr || e[0] == '\0') return dflt;   // unset or empty
       const int v = atoi(e);
       return (v >= lo && v <= hi) ? v : dflt;
     };
