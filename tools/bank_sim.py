@@ -71,3 +71,33 @@ print("current (32 along k, pitch=box2): mean wavefronts/LDS", cur.mean().round(
 for name, rule in [("pitch 40", lambda b: 40 if b else 0), ("pitch 40, box1%4==0", lambda b: 40 if b else -1), ("pitch 36", lambda b: 36 if b else 0), ("pitch 32", lambda b: 32)]:
     new = sim(it, "patch", rule)
     print("4x8 patch,", name, new.mean().round(3), new.round(2))
+
+# TMA SWIZZLE_128B on the current mapping (row pitch 32 floats = 128 B): the 16-byte chunk index of a cell is
+# XORed with (row & 7); taps of lanes that share z but sit in different rows then fall into different banks.
+def sim_swizzle(items, n=4000, seed=0):
+    R = np.random.RandomState(seed)
+    res = []
+    for it in items:
+        if int(it["kind"]) != 1: continue
+        U0 = np.asarray(it["fp_U0"], float); D = np.asarray(it["fp_D"], float).reshape(3, 3)
+        sh = np.asarray(it["shear"]).reshape(2, 16).astype(int)
+        O = [int(x) for x in it["out_shape"]]; S = [int(x) for x in it["src_shape"]]
+        box = [int(x) for x in it["tmap_box"]]
+        if box[2] != 32: continue
+        i = R.randint(0, O[0], n); j = R.randint(0, O[1], n)
+        k = np.arange(32)[None, :] + np.zeros((n, 1), int)
+        G = (k >> 3) & 15
+        oi = i[:, None] - sh[0][G]; oj = j[:, None] - sh[1][G]
+        u = [U0[a] + D[a, 0] * oi + D[a, 1] * oj + D[a, 2] * k for a in range(3)]
+        u[2] = fold(u[2], S[2])
+        c = [np.floor(x).astype(int) for x in u]
+        row = c[0] * box[1] + c[1]
+        row -= row.min()
+        z = c[2]
+        chunk = (z >> 2) ^ (row & 7)
+        addr = row * 32 + chunk * 4 + (z & 3)
+        res.append(wavefronts(addr).mean())
+    return np.array(res)
+
+sw = sim_swizzle(it)
+print("32 along k, pitch 32, SWIZZLE_128B:", sw.mean().round(3), sw.round(2))
