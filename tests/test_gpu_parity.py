@@ -386,3 +386,19 @@ def test_tma_store_copy_tiles_are_bit_exact(shape, roi, start):
         if i == 6:
             r = r * np.float32(1.5)
         assert torch.equal(got[i // (n // 2), i % (n // 2)], r), i
+
+
+@pytest.mark.parametrize("n_batches,seed,big", [(140, 2, False), (60, 5, False), (16, 1, True)])
+def test_randomised_mixed_launches_against_the_oracle(n_batches, seed, big):
+    """tools/fuzz_parity.py as a test: launches of up to 40 random items (random shapes, flips / crops / pads before
+    and after, every mode x padding, intensity maps, plain copies) against the torch oracle.  Seed 2 holds the item
+    that exposed a tap read one cell past the staged box (an axis that runs backwards in memory under border /
+    reflection: the coordinate clamped onto the first cell put the hi tap outside; its weight is 0, but stale
+    shared memory may hold NaN)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import fuzz_parity
+
+    checked, bad = fuzz_parity.sweep(n_batches, seed, big, verbose=True)
+    assert checked > 100 and bad == 0

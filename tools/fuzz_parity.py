@@ -1,0 +1,109 @@
+"""Randomised parity sweep of K1 on the GPU against the torch oracle (oracle/monai_restated.py): batches of
+random items — random shapes, pre / post flips, crops, pads, affines of every mode x padding, intensity maps,
+plain copies (TMA-store and consumer paths), nearest masks — all in ONE launch per batch, so that item
+switches, queue order and tile kinds are mixed the way no hand-written case mixes them.
+
+    python tools/fuzz_parity.py [n_batches] [seed] [big]
+
+Exact items (integer work, nearest) must be bit-equal; trilinear items within rtol 1e-4 / atol 1e-4 (default
+fast-coordinate mode).  Test infrastructure: imports oracle/."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from adell_mri_b200 import engine
+from adell_mri_b200.plan import BatchPlan
+from oracle import monai_restated as M
+from tests.helpers import rand_affine_matrix
+
+DEV = "cuda:0"
+
+
+BIG = False
+
+
+def random_item(R):
+    if BIG:   # volumes of several tiles per axis: the staged (TMA) paths, sheared tile grids, ragged edges
+        shape = tuple(int(R.choice([64, 72, 80, 96, 112, 128, 160])) for _ in range(2)) + (int(R.choice([16, 24, 32, 48, 64])),)
+    else:
+        shape = tuple(int(R.choice([8, 12, 16, 20, 24, 32, 33, 40, 48, 56])) for _ in range(2)) + (int(R.choice([8, 12, 16, 24, 32, 40])),)
+    img = torch.from_numpy(R.rand(1, *shape).astype(np.float32))
+    plan = BatchPlan([img[0].to(DEV)])
+    ref = img
+    exact = True
+    cur = list(shape)
+    # integer ops before the resample
+    if R.rand() < 0.4:
+        ax = [a for a in range(3) if R.rand() < 0.4]
+        if ax:
+            plan.flip(np.array([a in ax for a in range(3)])); ref = M.flip(ref, ax)
+    if R.rand() < 0.3:
+        roi = [max(4, (c - int(R.randint(0, 9))) // 4 * 4 if a == 2 else c - int(R.randint(0, 9))) for a, c in enumerate(cur)]
+        roi = [min(r, c) for r, c in zip(roi, cur)]
+        st = [int(R.randint(0, c - r + 1)) for c, r in zip(cur, roi)]
+        plan.crop(st, roi); ref = M.crop(ref, st, roi); cur = roi
+    kind = R.rand()
+    if kind < 0.55:
+        mode = "nearest" if R.rand() < 0.35 else "bilinear"
+        padding = str(R.choice(["zeros", "border", "reflection"]))
+        A = rand_affine_matrix(R, rotate=(0.4, 0.4, 0.2), translate=(4, 4, 2), scale=(0.1, 0.1, 0.1))
+        plan.affine(A.numpy(), mode, padding); ref = M.affine_resample(ref, A, mode, padding)
+        exact = mode == "nearest"
+    # integer ops after it
+    if R.rand() < 0.4:
+        ax = [a for a in range(3) if R.rand() < 0.4]
+        if ax:
+            plan.flip(np.array([a in ax for a in range(3)])); ref = M.flip(ref, ax)
+    if R.rand() < 0.3:
+        size = [c + int(R.choice([0, 0, 3, 4, 8])) for c in cur]
+        size[2] = (size[2] + 3) // 4 * 4
+        plan.spatial_pad(size); ref = M.spatial_pad(ref, size); cur = list(ref.shape[1:])
+    if R.rand() < 0.3:
+        roi = [max(4, c - int(R.choice([0, 2, 4, 8]))) for c in cur]
+        plan.center_crop(roi); ref = M.center_spatial_crop(ref, roi); cur = list(ref.shape[1:])
+    if R.rand() < 0.3:
+        s, o = float(np.float32(R.uniform(0.5, 1.5))), float(np.float32(R.uniform(-0.2, 0.2)))
+        plan.intensity(scale=s, offset=o)
+        ref = ref * torch.tensor(s, dtype=torch.float32) + torch.tensor(o, dtype=torch.float32)
+        exact = False
+    return plan, ref[0], exact
+
+
+def sweep(n_batches, seed, big=False, verbose=True):
+    """Returns (items checked, mismatches)."""
+    global BIG
+    BIG = big
+    R = np.random.RandomState(seed)
+    bad = checked = 0
+    for b in range(n_batches):
+        items = [random_item(R) for _ in range(int(R.randint(1, 12 if BIG else 40)))]
+        outs = [torch.full(tuple(r.shape), float("nan"), device=DEV) for _, r, _ in items]
+        engine.execute(BatchPlan.concat([p for p, _, _ in items]), outs)
+        torch.cuda.synchronize()
+        for i, ((_, ref, exact), out) in enumerate(zip(items, outs)):
+            got = out.cpu()
+            ok = torch.equal(got, ref) if exact else torch.allclose(got, ref, rtol=1e-4, atol=1e-4)
+            checked += 1
+            if not ok:
+                bad += 1
+                d = (got - ref).abs()
+                if verbose:
+                    print(f"MISMATCH batch {b} item {i}: shape {tuple(ref.shape)} exact={exact} max|d|={float(d.max()):.3g} "
+                          f"n={int((got != ref).sum())} nan={int(torch.isnan(got).sum())}")
+    return checked, bad
+
+
+def main():
+    n_batches = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    big = len(sys.argv) > 3 and sys.argv[3] == "big"
+    checked, bad = sweep(n_batches, seed, big)
+    print(f"fuzz: {checked} items in {n_batches} launches, {bad} mismatches (seed {seed})")
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+    main()
