@@ -391,10 +391,8 @@ def test_tma_store_copy_tiles_are_bit_exact(shape, roi, start):
 @pytest.mark.parametrize("n_batches,seed,big", [(140, 2, False), (60, 5, False), (16, 1, True)])
 def test_randomised_mixed_launches_against_the_oracle(n_batches, seed, big):
     """tools/fuzz_parity.py as a test: launches of up to 40 random items (random shapes, flips / crops / pads before
-    and after, every mode x padding, intensity maps, plain copies) against the torch oracle.  Seed 2 holds the item
-    that exposed a tap read one cell past the staged box (an axis that runs backwards in memory under border /
-    reflection: the coordinate clamped onto the first cell put the hi tap outside; its weight is 0, but stale
-    shared memory may hold NaN)."""
+    and after, every mode x padding, strict and default plans, fp32 / int16 / uint8 sources, second resamples,
+    intensity maps, noise, plain copies) against the torch oracle."""
     import os
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
@@ -402,3 +400,37 @@ def test_randomised_mixed_launches_against_the_oracle(n_batches, seed, big):
 
     checked, bad = fuzz_parity.sweep(n_batches, seed, big, verbose=True)
     assert checked > 50 and bad == 0
+
+
+@pytest.mark.parametrize("padding", ["border", "reflection"])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_reversed_axis_hi_tap_stays_inside_the_staged_box(padding, seed):
+    """Found by the randomised sweep: on an axis that runs backwards in memory (a flip before the resample = a
+    negative source stride) a coordinate clamped / reflected onto the first cell put the lo tap on the last box
+    index and the hi tap one cell past the staged box.  Its weight is 0, but 0 * NaN = NaN: the stages are
+    poisoned first by running the same items on an all-NaN source."""
+    from adell_mri_b200 import engine
+
+    R = np.random.RandomState(100 + seed)
+    shape = (16, 40, 40)
+    vols = [torch.from_numpy(R.rand(*shape).astype(np.float32)) for _ in range(4)]
+    A = [rand_affine_matrix(R, rotate=(0.3, 0.3, 0.2), translate=(3, 6, 6), scale=(0.1, 0.1, 0.1)) for _ in vols]
+    flips = np.array([[1, 1, 1], [1, 0, 0], [0, 1, 1], [1, 1, 0]], bool)
+
+    def run(sources):
+        plan = BatchPlan([v.to(DEV) for v in sources])
+        plan.flip(flips)
+        plan.affine(np.stack([a.numpy() for a in A]), "bilinear", padding)
+        plan.spatial_pad((16, 44, 48))
+        outs = [torch.full((16, 44, 48), float("nan"), device=DEV) for _ in sources]
+        engine.execute(plan, outs)
+        torch.cuda.synchronize()
+        return [o.cpu() for o in outs]
+
+    run([torch.full(shape, float("nan")) for _ in vols])
+    got = run(vols)
+    for i, v in enumerate(vols):
+        fl = [a for a in range(3) if flips[i, a]]
+        ref = M.spatial_pad(M.affine_resample(M.flip(v[None], fl), A[i], "bilinear", padding), (16, 44, 48))[0]
+        assert not torch.isnan(got[i]).any(), (i, int(torch.isnan(got[i]).sum()))
+        assert torch.allclose(got[i], ref, rtol=1e-4, atol=1e-4), (i, float((got[i] - ref).abs().max()))

@@ -5,8 +5,9 @@ switches, queue order and tile kinds are mixed the way no hand-written case mixe
 
     python tools/fuzz_parity.py [n_batches] [seed] [big]
 
-Exact items (integer work, nearest) must be bit-equal; trilinear items within rtol 1e-4 / atol 1e-4 (default
-fast-coordinate mode).  Test infrastructure: imports oracle/."""
+Exact items (integer work, nearest, everything of a strict plan) must be bit-equal; trilinear items within
+rtol 1e-4 / atol 1e-4 of the value range (default fast-coordinate mode).  Sources are fp32, int16 or uint8; some
+items carry a second resample (one more pass) or an injected noise volume.  Test infrastructure: imports oracle/."""
 import os
 import sys
 
@@ -30,10 +31,18 @@ def random_item(R):
         shape = tuple(int(R.choice([64, 72, 80, 96, 112, 128, 160])) for _ in range(2)) + (int(R.choice([16, 24, 32, 48, 64])),)
     else:
         shape = tuple(int(R.choice([8, 12, 16, 20, 24, 32, 33, 40, 48, 56])) for _ in range(2)) + (int(R.choice([8, 12, 16, 24, 32, 40])),)
-    img = torch.from_numpy(R.rand(1, *shape).astype(np.float32))
-    plan = BatchPlan([img[0].to(DEV)])
+    dt = R.rand()
+    if dt < 0.12:
+        img = torch.from_numpy(R.randint(-200, 4096, size=(1, *shape)).astype(np.int16))
+    elif dt < 0.18:
+        img = torch.from_numpy(R.randint(0, 256, size=(1, *shape)).astype(np.uint8))
+    else:
+        img = torch.from_numpy(R.rand(1, *shape).astype(np.float32))
+    strict = R.rand() < 0.25     # ATen operation order: the trilinear sum is then bit-exact as well
+    plan = BatchPlan([img[0].to(DEV)], strict=strict)
     ref = img
     exact = True
+    scale_of_values = 4096.0 if dt < 0.12 else (255.0 if dt < 0.18 else 1.0)
     cur = list(shape)
     # integer ops before the resample
     if R.rand() < 0.4:
@@ -51,7 +60,10 @@ def random_item(R):
         padding = str(R.choice(["zeros", "border", "reflection"]))
         A = rand_affine_matrix(R, rotate=(0.4, 0.4, 0.2), translate=(4, 4, 2), scale=(0.1, 0.1, 0.1))
         plan.affine(A.numpy(), mode, padding); ref = M.affine_resample(ref, A, mode, padding)
-        exact = mode == "nearest"
+        exact = mode == "nearest" or strict
+        if R.rand() < 0.15:      # a second resample (the reference's shear after the affine): one more pass
+            A2 = rand_affine_matrix(R, rotate=(0.1, 0.1, 0.1), translate=(1, 1, 1), scale=(0.05, 0.05, 0.05))
+            plan.affine(A2.numpy(), mode, padding); ref = M.affine_resample(ref, A2, mode, padding)
     # integer ops after it
     if R.rand() < 0.4:
         ax = [a for a in range(3) if R.rand() < 0.4]
@@ -67,9 +79,13 @@ def random_item(R):
     if R.rand() < 0.3:
         s, o = float(np.float32(R.uniform(0.5, 1.5))), float(np.float32(R.uniform(-0.2, 0.2)))
         plan.intensity(scale=s, offset=o)
-        ref = ref * torch.tensor(s, dtype=torch.float32) + torch.tensor(o, dtype=torch.float32)
+        ref = ref.to(torch.float32) * torch.tensor(s, dtype=torch.float32) + torch.tensor(o, dtype=torch.float32)
         exact = False
-    return plan, ref[0], exact
+    if R.rand() < 0.1:           # injected noise (RandGaussianNoised parity path)
+        nz = torch.from_numpy(R.normal(0, 0.1, size=tuple(ref.shape[1:])).astype(np.float32))
+        plan.add_noise([nz.to(DEV)])
+        ref = ref.to(torch.float32) + nz
+    return plan, ref[0].to(torch.float32), exact, scale_of_values
 
 
 def sweep(n_batches, seed, big=False, verbose=True):
@@ -80,12 +96,12 @@ def sweep(n_batches, seed, big=False, verbose=True):
     bad = checked = 0
     for b in range(n_batches):
         items = [random_item(R) for _ in range(int(R.randint(1, 12 if BIG else 40)))]
-        outs = [torch.full(tuple(r.shape), float("nan"), device=DEV) for _, r, _ in items]
-        engine.execute(BatchPlan.concat([p for p, _, _ in items]), outs)
+        outs = [torch.full(tuple(it[1].shape), float("nan"), device=DEV) for it in items]
+        engine.execute(BatchPlan.concat([it[0] for it in items]), outs)
         torch.cuda.synchronize()
-        for i, ((_, ref, exact), out) in enumerate(zip(items, outs)):
+        for i, ((_, ref, exact, vs), out) in enumerate(zip(items, outs)):
             got = out.cpu()
-            ok = torch.equal(got, ref) if exact else torch.allclose(got, ref, rtol=1e-4, atol=1e-4)
+            ok = torch.equal(got, ref) if exact else torch.allclose(got, ref, rtol=1e-4, atol=1e-4 * vs)
             checked += 1
             if not ok:
                 bad += 1
