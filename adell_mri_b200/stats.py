@@ -210,10 +210,12 @@ def _pass_schedule(dtype: torch.dtype):
 
 
 def numpy_virtual_index(n: int, q: float):
-    """numpy ``_compute_virtual_index`` (method 'linear': alpha=beta=1) and ``_get_indexes`` /
-    ``_get_gamma`` in float64: returns (lo, hi, gamma)."""
+    """numpy's 'linear' quantile method in float64: virtual index ``(n - 1) * q`` (numpy evaluates exactly this
+    expression for 'linear', not the mathematically equivalent ``_compute_virtual_index(n, q, 1, 1)``: the two
+    round differently, and at a near-tie of the final float32 rounding the percentile moves by one ulp — found
+    by tools/fuzz_stats.py), then ``_get_indexes`` / ``_get_gamma``: returns (lo, hi, gamma)."""
     quant = np.true_divide(np.float64(q), 100.0)
-    vi = n * quant + (1.0 + quant * (1.0 - 1.0 - 1.0)) - 1.0
+    vi = (n - 1) * quant
     if vi >= n - 1:
         return n - 1, n - 1, 0.0
     if vi < 0:

@@ -116,3 +116,43 @@ def test_cpu_plans_are_refused_by_the_engine():
     img = torch.zeros(4, 4, 4)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         engine.execute(BatchPlan([img]), [torch.empty(4, 4, 4)])
+
+
+def test_percentile_positions_follow_numpys_linear_method_to_the_bit():
+    """`stats.numpy_virtual_index` against numpy itself: np.percentile of arange(n) (float64) IS the lerp of the
+    two order statistics lo, lo + 1 with numpy's own gamma, so its bits pin (lo, hi, gamma).  numpy evaluates
+    (n - 1) * q for 'linear'; the equivalent alpha = beta = 1 formula rounds differently (tools/fuzz_stats.py
+    found a percentile one ulp off at a near-tie of the final float32 rounding)."""
+    from adell_mri_b200 import stats
+
+    R = np.random.RandomState(0)
+    ns = [1, 2, 3, 7, 1000, 65536, 66538, 2_097_152, 33_554_432, 268_435_456 + 5]
+    qs = [0.0, 0.5, 1.0, 2.0, 25.0, 50.0, 75.0, 98.0, 99.0, 99.5, 100.0] + [float(x) for x in R.uniform(0, 100, 40)]
+    for n in ns:
+        a = np.arange(min(n, 70_000), dtype=np.float64) if n <= 70_000 else None
+        for q in qs:
+            lo, hi, g = stats.numpy_virtual_index(n, q)
+            vi = (n - 1) * (np.float64(q) / 100.0)     # numpy's expression
+            assert 0 <= lo <= hi <= n - 1 and hi - lo in (0, 1)
+            if hi > lo:
+                assert lo == int(np.floor(vi)) and g == vi - np.floor(vi)
+            if a is not None:
+                want = np.percentile(a, np.float64(q))
+                d = np.float64(hi - lo)
+                mine = np.float64(lo) + d * g if g < 0.5 else np.float64(hi) - d * (1 - g)
+                assert mine == want, (n, q, mine, want)
+
+
+def test_pooled_percentile_near_tie_matches_numpy():
+    """The literal case of the sweep: three pooled volumes (2 + 65536 + 1000 values), q = 98."""
+    from adell_mri_b200 import stats
+    from oracle.radix_select import NumpyKernels
+
+    R = np.random.RandomState(0)
+    for _ in range(200):
+        sizes = [int(R.choice([2, 17, 1000, 4097, 65536])) for _ in range(3)]
+        vols = [torch.from_numpy(R.normal(0, 100, size=s).astype(np.float32)) for s in sizes]
+        qs = [1.0, 98.0, float(R.uniform(0, 100))]
+        got = stats.percentiles(vols, qs, dataset_wide=True, kernels=NumpyKernels(vols)).numpy()[0]
+        ref = np.percentile(np.concatenate([v.numpy() for v in vols]), np.asarray(qs, np.float64)).astype(np.float32)
+        assert np.array_equal(got, ref), (sizes, qs, got, ref)
