@@ -241,3 +241,19 @@ def test_resize_full_size_volume_matches_torch():
         got = stats.resize([v.to(DEV)], out, "area")[0].cpu()
         want = torch.nn.functional.interpolate(v[None, None], size=out, mode="area")[0, 0]
         assert torch.equal(got, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [0, 7])
+def test_randomised_statistics_sweep_against_numpy(seed):
+    """tools/fuzz_stats.py as a test: exact percentiles (per volume and pooled) and min / max of adversarial volumes
+    — constants, two values, heavy ties, signed zeros, denormals, 60 decades of range, int16 / uint8, one element,
+    unaligned views, mixed sizes in one call.  Seed 0 holds the pooled near-tie that was one ulp off while the
+    percentile positions used the alpha = beta = 1 formula instead of numpy's (n - 1) * q."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import fuzz_stats
+
+    checked, bad = fuzz_stats.sweep(60, seed)
+    assert checked > 100 and bad == 0

@@ -45,9 +45,8 @@ def random_volume(R):
     return v, kind
 
 
-def main():
-    rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 60
-    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+def sweep(rounds, seed, verbose=True):
+    """Returns (checks, mismatches)."""
     R = np.random.RandomState(seed)
     bad = checked = 0
     for r in range(rounds):
@@ -74,17 +73,25 @@ def main():
             f = v.astype(np.float32)
             ref = np.percentile(f, np.asarray(qs, np.float64)).astype(np.float32)
             checked += 1
-            # bit-level comparison (signed zeros: numpy may return either zero of a tie of +0 / -0: compare by value there)
             ok = np.array_equal(got[i], ref) and mm[i, 0] == f.min() and mm[i, 1] == f.max()
             if not ok:
                 bad += 1
-                print(f"MISMATCH round {r} vol {i} kind {kind} n {v.size} qs {qs}: got {got[i]} ref {ref} minmax {mm[i]} vs {f.min()} {f.max()}")
+                if verbose:
+                    print(f"MISMATCH round {r} vol {i} kind {kind} n {v.size} qs {qs}: got {got[i]} ref {ref} minmax {mm[i]} vs {f.min()} {f.max()}")
         pooled = stats.percentiles(devs, qs, dataset_wide=True).cpu().numpy()[0]
         ref = np.percentile(np.concatenate([v.astype(np.float32) for v, _ in vols]), np.asarray(qs, np.float64)).astype(np.float32)
         checked += 1
         if not np.array_equal(pooled, ref):
             bad += 1
-            print(f"MISMATCH round {r} pooled kinds {[k for _, k in vols]} qs {qs}: got {pooled} ref {ref}")
+            if verbose:
+                print(f"MISMATCH round {r} pooled kinds {[k for _, k in vols]} qs {qs}: got {pooled} ref {ref}")
+    return checked, bad
+
+
+def main():
+    rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 60
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    checked, bad = sweep(rounds, seed)
     print(f"fuzz_stats: {checked} checks in {rounds} rounds, {bad} mismatches (seed {seed})")
     sys.exit(1 if bad else 0)
 
