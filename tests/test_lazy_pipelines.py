@@ -273,3 +273,20 @@ def test_ssl_scaled_crop_matches_eager_reference():
             assert tuple(g.shape) == (1, *scaled)
             assert torch.equal(g.cpu(), want), k
     assert len(sizes) > 1    # random window sizes were drawn
+
+
+@pytest.mark.parametrize("seed", [0, 3])
+def test_randomised_builder_configurations_match_the_eager_reference(seed):
+    """tools/fuzz_pipelines.py as a test (CPU, through the C restatement): random key sets, shapes, flip axes,
+    probabilities, crop sandwiches and augment lists of the unet / classification / SSL builders, lazy surface +
+    fused collation against the eager oracle chains on the same seeds."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    saved = engine.execute
+    try:
+        import fuzz_pipelines
+        n, bad = fuzz_pipelines.sweep(36, seed)
+    finally:
+        engine.execute = saved
+    assert n == 36 and bad == 0

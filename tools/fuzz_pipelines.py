@@ -1,0 +1,142 @@
+"""Randomised sweep of the lazy dictionary-transform surface (adell_mri_b200.transforms / transform_factory /
+collate) against the eager oracle restatement of the reference's pipelines (oracle/pipelines_ref.py): random
+seeds, shapes, key sets, flip axes, probabilities, crop sandwiches and augment lists for the unet, classification
+and SSL builders.  Runs on the CPU: plans execute through the C restatement (oracle/gather_ref.c), so this sweeps
+the HOST logic — draw orders, seed fan-out, chain composition, collation — not the CUDA kernels.  Test
+infrastructure (imports oracle/).
+
+    python tools/fuzz_pipelines.py [n_rounds] [seed]
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from adell_mri_b200 import collate, engine, transform_factory as F, transforms as T
+from oracle import pipelines_ref as P
+from tests.helpers import cref_execute
+
+engine.execute = cref_execute     # CPU stand-in for the launcher (test infrastructure)
+
+
+def samples_of(R, n, keys, shape, mask=True):
+    out = []
+    for _ in range(n):
+        s = {k: torch.from_numpy(R.rand(1, *shape).astype(np.float32)) for k in keys}
+        if mask:
+            s["mask"] = torch.from_numpy((R.rand(1, *shape) > 0.7).astype(np.float32))
+        out.append(s)
+    return out
+
+
+def shape_of(R):
+    return (int(R.choice([16, 20, 24, 28, 33])), int(R.choice([16, 18, 24, 30])), int(R.choice([8, 12, 16])))
+
+
+def unet_round(R):
+    keys = list(R.choice(["t2", "adc", "dwi", "hbv"], size=int(R.randint(1, 4)), replace=False))
+    shape = shape_of(R)
+    augment = [a for a in ["affine", "shear", "flip"] if R.rand() < 0.7] or ["flip"]
+    if R.rand() < 0.3:
+        augment = ["trivial"] + augment
+    flip_axis = sorted(int(a) for a in R.choice([0, 1, 2], size=int(R.randint(1, 4)), replace=False))
+    seed = int(R.randint(1 << 30))
+    has_label = bool(R.rand() < 0.7)
+    rc = None
+    if R.rand() < 0.4 and not has_label:
+        rc = [int(s * R.uniform(0.5, 0.8)) for s in shape]
+    all_keys = keys + (["mask"] if has_label else [])
+    samples = samples_of(R, 3, keys, shape, mask=has_label)
+    lazy = T.Compose([F.get_augmentations_unet(augment, all_keys, keys, [], random_crop_size=rc, has_label=has_label, flip_axis=flip_axis),
+                      T.ConcatItemsd(keys, "image")]).set_random_state(seed)
+    ref = P.Chain([P.unet(augment, all_keys, keys, random_crop_size=rc, has_label=has_label, flip_axis=tuple(flip_axis)),
+                   P.ConcatD(keys, "image")]).seed(seed)
+    got = collate.safe_collate([lazy(dict(s)) for s in samples])
+    desc = f"unet augment={augment} keys={keys} shape={shape} flip_axis={flip_axis} rc={rc} label={has_label} seed={seed}"
+    bad = 0
+    for b, s in enumerate(samples):
+        w = ref(s)
+        bad += int(not torch.equal(got["image"][b], w["image"]))
+        if has_label:
+            bad += int(not torch.equal(got["mask"][b], w["mask"].to(torch.float32)))
+    return bad, desc
+
+
+def class_round(R):
+    keys = list(R.choice(["t2", "adc", "dwi"], size=int(R.randint(1, 4)), replace=False))
+    shape = (int(R.choice([32, 36, 40])), int(R.choice([32, 40])), int(R.choice([20, 24])))
+    crop = [shape[0] - 16 - int(R.choice([0, 2])), shape[1] - 16, shape[2] - 16]
+    augment = [a for a in ["flip", "affine", "shear"] if R.rand() < 0.7] or ["affine"]
+    if R.rand() < 0.3:
+        augment = ["trivial"] + augment
+    flip_axis = sorted(int(a) for a in R.choice([0, 1, 2], size=int(R.randint(1, 4)), replace=False))
+    prob = float(R.choice([0.1, 0.5, 0.9]))
+    seed = int(R.randint(1 << 30))
+    samples = samples_of(R, 3, keys, shape)
+    tf = F.ClassificationTransforms(keys, adc_keys=[], crop_size=crop, mask_key="mask")
+    lazy = T.Compose([*tf.pre_transforms()[-2:], F.get_augmentations_class(augment, keys, "mask", [], flip_axis=flip_axis, prob=prob),
+                      *tf.post_transforms()]).set_random_state(seed)
+    m = [c + 16 for c in crop]
+    ref = P.Chain([P.CenterCropD(keys + ["mask"], m), P.classification(augment, keys, "mask", flip_axis=tuple(flip_axis), prob=prob),
+                   P.CenterCropD(keys + ["mask"], crop), P.ConcatD(keys + ["mask"], "image")]).seed(seed)
+    got = collate.safe_collate([lazy(dict(s)) for s in samples])
+    desc = f"class augment={augment} keys={keys} shape={shape} crop={crop} flip_axis={flip_axis} prob={prob} seed={seed}"
+    bad = sum(int(not torch.equal(got["image"][b], ref(s)["image"])) for b, s in enumerate(samples))
+    return bad, desc
+
+
+def ssl_round(R):
+    shape = (int(R.choice([28, 32, 36])), int(R.choice([28, 32])), int(R.choice([12, 16])))
+    roi = [shape[0] - int(R.choice([4, 8])), shape[1] - int(R.choice([4, 8])), shape[2] - int(R.choice([0, 4]))]
+    vicregl, different = bool(R.rand() < 0.3), bool(R.rand() < 0.4)
+    n_t = int(R.randint(1, 4))
+    names = [m for m in F.FUSED_AUGMENTS if m not in ("contrast", "rician_noise")]
+    names = [m for m in names if R.rand() < 0.8] or ["rotate_z", "shift_intensity", "gaussian_noise"]
+    if vicregl:   # the spatial members are dropped by the builder: keep enough of the others
+        names = ["gaussian_noise", "shift_intensity", "scale_intensity"] + [m for m in names if m not in ("gaussian_noise", "shift_intensity", "scale_intensity")]
+    while len(names) < n_t:
+        names.append([m for m in F.FUSED_AUGMENTS if m not in names and m not in ("contrast", "rician_noise")][0])
+    seed, gseed = int(R.randint(1 << 30)), int(R.randint(1 << 30))
+    samples = samples_of(R, 3, ["image"], shape, mask=False)
+    tf = F.SSLTransforms(["image"], ["image_copy"], adc_keys=[], non_adc_keys=[])
+    lazy = tf.transforms(F.get_augmentations_ssl(["image"], ["image_copy"], None, roi, vicregl, different, n_transforms=n_t,
+                                                 aug_list=list(names))).set_random_state(seed)
+    ref = P.Chain(P.ssl(["image"], ["image_copy"], roi, vicregl, different, names, n_t)).seed(seed)
+    np.random.seed(gseed)
+    got = collate.safe_collate([lazy(dict(s)) for s in samples])
+    np.random.seed(gseed)
+    desc = f"ssl names={names} shape={shape} roi={roi} vicregl={vicregl} different={different} N={n_t} seed={seed}"
+    bad = 0
+    for b, s in enumerate(samples):
+        d = dict(s); d["image_copy"] = s["image"].clone()
+        w = ref(d)
+        for gk, wk in (("augmented_image_1", "image"), ("augmented_image_2", "image_copy")):
+            bad += int(not torch.allclose(got[gk][b], w[wk].to(torch.float32), rtol=2e-6, atol=2e-6))
+    return bad, desc
+
+
+def sweep(rounds, seed, verbose=True):
+    R = np.random.RandomState(seed)
+    T.set_mode(strict=True, fast=False, noise="injected")
+    bad = 0
+    try:
+        for r in range(rounds):
+            fn = [unet_round, class_round, ssl_round][r % 3]
+            b, desc = fn(R)
+            if b:
+                bad += 1
+                if verbose:
+                    print(f"MISMATCH round {r}: {desc} ({b} tensors differ)")
+    finally:
+        T.set_mode(strict=False)
+    return rounds, bad
+
+
+if __name__ == "__main__":
+    rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 60
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    n, bad = sweep(rounds, seed)
+    print(f"fuzz_pipelines: {n} rounds, {bad} with mismatches (seed {seed})")
+    sys.exit(1 if bad else 0)
