@@ -18,7 +18,6 @@ from adell_mri_b200 import collate, engine, transform_factory as F, transforms a
 from oracle import pipelines_ref as P
 from tests.helpers import cref_execute
 
-engine.execute = cref_execute     # CPU stand-in for the launcher (test infrastructure)
 
 
 def samples_of(R, n, keys, shape, mask=True):
@@ -120,6 +119,7 @@ def ssl_round(R):
 def sweep(rounds, seed, verbose=True):
     R = np.random.RandomState(seed)
     T.set_mode(strict=True, fast=False, noise="injected")
+    saved, engine.execute = engine.execute, cref_execute     # CPU stand-in for the launcher (test infrastructure)
     bad = 0
     try:
         for r in range(rounds):
@@ -131,6 +131,7 @@ def sweep(rounds, seed, verbose=True):
                     print(f"MISMATCH round {r}: {desc} ({b} tensors differ)")
     finally:
         T.set_mode(strict=False)
+        engine.execute = saved
     return rounds, bad
 
 
