@@ -99,13 +99,23 @@ class SegmentationBatchAugmenter:
         self._dst_cache = {}
         self.set_random_state(None)
 
-    def set_random_state(self, seed=None):
-        """Seed fan-out of ``Compose.set_random_state`` over the Randomizable children †."""
-        n = (1 if self.random_crop_size is not None else 0) + len(self.samplers) + len(self.flip_axis)
+    def set_random_state(self, seed=None, nested: bool = False):
+        """Seed fan-out of ``Compose.set_random_state`` over the Randomizable children †.  ``seed`` is the seed of
+        the augmentation ``Compose`` (= ``get_augmentations_unet(...).set_random_state(seed)``).  The reference
+        nests that Compose inside the pipeline's outer ``Compose`` and seeds the OUTER one
+        (``transforms_train.set_random_state(args.seed)``, entrypoints/segmentation/train.py:449), which hands its
+        only Randomizable child the first draw of ``RandomState(args.seed)``: ``nested=True`` reproduces that."""
+        if nested and seed is not None:
+            seed = child_seeds(seed, 1)[0]
+        n = len(self.samplers) + len(self.flip_axis)
+        if self.random_crop_size is not None:
+            # crop sandwich (augmentations.py:142-176): Compose([RandSpatialCropd, Compose(augments + flips),
+            # CenterSpatialCropd]) — the outer Compose seeds the crop and the INNER Compose, which fans out again
+            outer = child_seeds(seed, 2) if seed is not None else [None, None]
+            self.crop_R = np.random.RandomState(outer[0])
+            seed = outer[1]
         seeds = child_seeds(seed, n) if seed is not None else [None] * n
         i = 0
-        if self.random_crop_size is not None:
-            self.crop_R = np.random.RandomState(seeds[i]); i += 1
         for s in self.samplers:
             s.set_random_state(seeds[i]); i += 1
         for j in range(len(self.flip_axis)):
@@ -297,7 +307,12 @@ class ClassificationBatchAugmenter(_BatchBase):
             self.samplers.append(RandAffineSampler(prob=prob, shear_range=((0.9, 1.1), (0.9, 1.1), (0.9, 1.1))))
         self.set_random_state(None)
 
-    def set_random_state(self, seed=None):
+    def set_random_state(self, seed=None, nested: bool = False):
+        """``nested=True``: ``seed`` is the seed of the pipeline's OUTER Compose (the reference's
+        ``transforms_train.set_random_state(args.seed)``, entrypoints/classification/train.py:243), whose only
+        Randomizable child is this augmentation Compose."""
+        if nested and seed is not None:
+            seed = child_seeds(seed, 1)[0]
         n = (1 if self.flip_combos else 0) + len(self.samplers)
         seeds = child_seeds(seed, n) if seed is not None else [None] * n
         i = 0

@@ -16,7 +16,15 @@ import torch
 
 from adell_mri_b200 import collate, engine, transform_factory as F, transforms as T
 from oracle import pipelines_ref as P
+from adell_mri_b200.pipelines import ClassificationBatchAugmenter, SegmentationBatchAugmenter
+from oracle import cref
 from tests.helpers import cref_execute
+
+
+def cref_execute_ptrs(plan, dst_ptr, dst_stride, keep=None):
+    launches = plan.build_launches(dst_ptr, dst_stride, lambda n: torch.empty(max(n, 1), dtype=torch.float32))
+    for items in launches:
+        cref.gather(items)
 
 
 
@@ -116,14 +124,71 @@ def ssl_round(R):
     return bad, desc
 
 
+def seg_batch_round(R):
+    """The batch fast path (what bench.py times) against the dictionary surface on the same seed: identical
+    streams drawn batch-wise, one plan for the whole batch."""
+    keys = list(R.choice(["t2", "adc", "dwi", "hbv"], size=int(R.randint(1, 4)), replace=False))
+    shape = shape_of(R)
+    augment = [a for a in ["affine", "shear", "flip"] if R.rand() < 0.7] or ["flip"]
+    flip_axis = sorted(int(a) for a in R.choice([0, 1, 2], size=int(R.randint(1, 4)), replace=False))
+    has_label = bool(R.rand() < 0.7)
+    rc = [int(s * R.uniform(0.5, 0.8)) for s in shape] if (R.rand() < 0.4 and not has_label) else None
+    seed = int(R.randint(1 << 30))
+    all_keys = keys + (["mask"] if has_label else [])
+    samples = samples_of(R, 5, keys, shape, mask=has_label)
+    # the augmenter's seed is the seed of the augmentation Compose itself (the reference nests that Compose inside
+    # the pipeline's outer Compose, which hands it its own child seed: `nested=True` below)
+    nested = bool(R.rand() < 0.5)
+    aug_t = F.get_augmentations_unet(augment, all_keys, keys, [], random_crop_size=rc, has_label=has_label, flip_axis=flip_axis)
+    concat = T.ConcatItemsd(keys, "image")
+    if nested:
+        lazy = T.Compose([aug_t, concat]).set_random_state(seed)
+    else:   # chained by hand: constructing an outer Compose would re-seed its children (MONAI behaviour)
+        aug_t.set_random_state(seed)
+        lazy = lambda d: concat(aug_t(d))   # noqa: E731
+    want = collate.safe_collate([lazy(dict(s)) for s in samples])
+    aug = SegmentationBatchAugmenter(augment, all_keys, keys, random_crop_size=rc, has_label=has_label, flip_axis=flip_axis, strict=True)
+    got = aug.set_random_state(seed, nested=nested)(samples)
+    desc = f"seg_batch nested={nested} augment={augment} keys={keys} shape={shape} flip_axis={flip_axis} rc={rc} label={has_label} seed={seed}"
+    bad = int(not torch.equal(got["image"], want["image"]))
+    if has_label:
+        bad += int(not torch.equal(got["mask"], want["mask"]))
+    return bad, desc
+
+
+def class_batch_round(R):
+    keys = list(R.choice(["t2", "adc", "dwi"], size=int(R.randint(1, 4)), replace=False))
+    shape = (int(R.choice([32, 36, 40])), int(R.choice([32, 40])), int(R.choice([20, 24])))
+    crop = [shape[0] - 16, shape[1] - 16 - int(R.choice([0, 4])), shape[2] - 16]
+    augment = [a for a in ["flip", "affine", "shear"] if R.rand() < 0.7] or ["affine"]
+    flip_axis = sorted(int(a) for a in R.choice([0, 1, 2], size=int(R.randint(1, 4)), replace=False))
+    prob, seed, nested = float(R.choice([0.1, 0.5, 0.9])), int(R.randint(1 << 30)), bool(R.rand() < 0.5)
+    mask_key = "mask" if R.rand() < 0.7 else None
+    samples = samples_of(R, 5, keys, shape, mask=mask_key is not None)
+    all_keys = keys + ([mask_key] if mask_key else [])
+    aug_t = F.get_augmentations_class(augment, keys, mask_key, [], flip_axis=flip_axis, prob=prob)
+    tail = [T.CenterSpatialCropd(all_keys, crop), T.ConcatItemsd(all_keys, "image")]
+    if nested:
+        lazy = T.Compose([aug_t, *tail]).set_random_state(seed)
+    else:
+        aug_t.set_random_state(seed)
+        lazy = lambda d: tail[1](tail[0](aug_t(d)))   # noqa: E731
+    want = collate.safe_collate([lazy(dict(s)) for s in samples])["image"]
+    aug = ClassificationBatchAugmenter(augment, keys, mask_key, flip_axis=flip_axis, prob=prob, crop_size=crop, strict=True)
+    got = aug.set_random_state(seed, nested=nested)(samples)["image"]
+    desc = f"class_batch nested={nested} augment={augment} keys={keys} mask={mask_key} shape={shape} crop={crop} flip_axis={flip_axis} prob={prob} seed={seed}"
+    return int(not torch.equal(got, want)), desc
+
+
 def sweep(rounds, seed, verbose=True):
     R = np.random.RandomState(seed)
     T.set_mode(strict=True, fast=False, noise="injected")
-    saved, engine.execute = engine.execute, cref_execute     # CPU stand-in for the launcher (test infrastructure)
+    saved, engine.execute = engine.execute, cref_execute     # CPU stand-ins for the launcher (test infrastructure)
+    saved_ptrs, engine.execute_ptrs = engine.execute_ptrs, cref_execute_ptrs
     bad = 0
     try:
         for r in range(rounds):
-            fn = [unet_round, class_round, ssl_round][r % 3]
+            fn = [unet_round, class_round, ssl_round, seg_batch_round, class_batch_round][r % 5]
             b, desc = fn(R)
             if b:
                 bad += 1
@@ -132,6 +197,7 @@ def sweep(rounds, seed, verbose=True):
     finally:
         T.set_mode(strict=False)
         engine.execute = saved
+        engine.execute_ptrs = saved_ptrs
     return rounds, bad
 
 
