@@ -434,3 +434,44 @@ def test_reversed_axis_hi_tap_stays_inside_the_staged_box(padding, seed):
         ref = M.spatial_pad(M.affine_resample(M.flip(v[None], fl), A[i], "bilinear", padding), (16, 44, 48))[0]
         assert not torch.isnan(got[i]).any(), (i, int(torch.isnan(got[i]).sum()))
         assert torch.allclose(got[i], ref, rtol=1e-4, atol=1e-4), (i, float((got[i] - ref).abs().max()))
+
+
+@pytest.mark.parametrize("sizes", [[4, 4, 4, 4], [3, 1, 5, 2]])
+def test_prepared_steps_equal_step_by_step_calls(sizes):
+    """`SegmentationBatchAugmenter.prepare_steps` (what bench.py times: several steps drawn, composed and uploaded at
+    once, launched one by one) gives exactly the batches that calling the augmenter step by step gives on the same
+    seed — equal and unequal step sizes, launched in order and again in reverse."""
+    from adell_mri_b200.pipelines import SegmentationBatchAugmenter
+
+    R = np.random.RandomState(4)
+    keys, shape = ["t2", "adc", "dwi"], (48, 40, 16)
+    cache = [{k: torch.from_numpy(R.rand(1, *shape).astype(np.float32)).to(DEV) for k in keys + ["mask"]} for _ in range(6)]
+    batches, i = [], 0
+    for n in sizes:
+        batches.append([cache[(i + j) % len(cache)] for j in range(n)]); i += n
+
+    def make():
+        aug = SegmentationBatchAugmenter(["affine", "flip"], keys + ["mask"], keys, flip_axis=[0, 1, 2])
+        for s in aug.samplers:
+            s.prob = 0.5
+        return aug.set_random_state(9)
+
+    a = make()
+    want = [{k: v.clone() for k, v in a(b).items()} for b in batches]
+    b_aug = make()
+    outs = [{"image": torch.full((len(b), 3, *shape), float("nan"), device=DEV), "mask": torch.full((len(b), 1, *shape), float("nan"), device=DEV)}
+            for b in batches]
+    prepared = b_aug.prepare_steps(batches, outs)
+    assert len(prepared) == len(sizes)
+    for order in (range(len(sizes)), reversed(range(len(sizes)))):
+        for o in outs:
+            for t in o.values():
+                t.fill_(float("nan"))
+        for k in order:
+            prepared.run(k)
+        torch.cuda.synchronize()
+        for k in range(len(sizes)):
+            assert torch.equal(outs[k]["image"], want[k]["image"]), k
+            assert torch.equal(outs[k]["mask"], want[k]["mask"]), k
+    fired = sum(int(not torch.equal(want[k]["image"][j, 0], batches[k][j]["t2"][0])) for k in range(len(sizes)) for j in range(sizes[k]))
+    assert fired >= 3
