@@ -279,7 +279,7 @@ def test_ssl_scaled_crop_matches_eager_reference():
 def test_randomised_builder_configurations_match_the_eager_reference(seed):
     """tools/fuzz_pipelines.py as a test (CPU, through the C restatement): random key sets, shapes, flip axes,
     probabilities, crop sandwiches and augment lists of the unet / classification / SSL builders, lazy surface +
-    fused collation against the eager oracle chains on the same seeds; and the segmentation / classification batch
+    fused collation against the eager oracle chains on the same seeds; and the segmentation / classification / SSL batch
     fast paths against the dictionary surface (plain and nested seeding; the crop sandwich's nested seed fan-out was
     flat in the batch path until this sweep found it)."""
     import os
@@ -287,5 +287,5 @@ def test_randomised_builder_configurations_match_the_eager_reference(seed):
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
     import fuzz_pipelines
 
-    n, bad = fuzz_pipelines.sweep(40, seed)
-    assert n == 40 and bad == 0
+    n, bad = fuzz_pipelines.sweep(48, seed)
+    assert n == 48 and bad == 0

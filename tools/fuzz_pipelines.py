@@ -16,7 +16,7 @@ import torch
 
 from adell_mri_b200 import collate, engine, transform_factory as F, transforms as T
 from oracle import pipelines_ref as P
-from adell_mri_b200.pipelines import ClassificationBatchAugmenter, SegmentationBatchAugmenter
+from adell_mri_b200.pipelines import SSL_FUSED_MEMBERS, ClassificationBatchAugmenter, SegmentationBatchAugmenter, SSLBatchAugmenter
 from oracle import cref
 from tests.helpers import cref_execute
 
@@ -180,6 +180,41 @@ def class_batch_round(R):
     return int(not torch.equal(got, want)), desc
 
 
+def ssl_batch_round(R):
+    shape = (int(R.choice([28, 32, 36])), int(R.choice([28, 32])), int(R.choice([12, 16])))
+    roi = [shape[0] - int(R.choice([4, 8])), shape[1] - int(R.choice([4, 8])), shape[2] - int(R.choice([0, 4]))]
+    vicregl, different = bool(R.rand() < 0.3), bool(R.rand() < 0.4)
+    n_t = int(R.randint(1, 4))
+    members = [m for m in SSL_FUSED_MEMBERS if R.rand() < 0.8]
+    for m in ("gaussian_noise", "shift_intensity", "scale_intensity"):
+        if m not in members:
+            members.insert(0, m)
+    members = [m for m in SSL_FUSED_MEMBERS if m in members]    # the reference's list order
+    seed, gseed = int(R.randint(1 << 30)), int(R.randint(1 << 30))
+    samples = samples_of(R, 4, ["image"], shape, mask=False)
+    tf = F.SSLTransforms(["image"], ["image_copy"], adc_keys=[], non_adc_keys=[])
+    chain = [tf.pre_transforms()[-1],
+             T.Compose(F.get_augmentations_ssl(["image"], ["image_copy"], None, roi, vicregl, different, n_transforms=n_t,
+                                               aug_list=list(members))).set_random_state(seed),
+             *tf.post_transforms()]
+
+    def run(d):
+        for t in chain:
+            d = t(d)
+        return d
+
+    np.random.seed(gseed)
+    want = collate.safe_collate([run(dict(s)) for s in samples])
+    aug = SSLBatchAugmenter(["image"], roi, n_transforms=n_t, different_crop=different, vicregl=vicregl, members=members, strict=True)
+    np.random.seed(gseed)
+    got = aug.set_random_state(seed)(samples)
+    desc = f"ssl_batch members={members} shape={shape} roi={roi} vicregl={vicregl} different={different} N={n_t} seed={seed}"
+    bad = sum(int(not torch.allclose(got[k], want[k], rtol=2e-6, atol=2e-6)) for k in ("augmented_image_1", "augmented_image_2"))
+    if vicregl:
+        bad += sum(int(not np.array_equal(np.asarray(got[k]), np.asarray(want[k]))) for k in ("box_1", "box_2"))
+    return bad, desc
+
+
 def sweep(rounds, seed, verbose=True):
     R = np.random.RandomState(seed)
     T.set_mode(strict=True, fast=False, noise="injected")
@@ -188,7 +223,7 @@ def sweep(rounds, seed, verbose=True):
     bad = 0
     try:
         for r in range(rounds):
-            fn = [unet_round, class_round, ssl_round, seg_batch_round, class_batch_round][r % 5]
+            fn = [unet_round, class_round, ssl_round, seg_batch_round, class_batch_round, ssl_batch_round][r % 6]
             b, desc = fn(R)
             if b:
                 bad += 1
