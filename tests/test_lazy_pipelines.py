@@ -287,5 +287,5 @@ def test_randomised_builder_configurations_match_the_eager_reference(seed):
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
     import fuzz_pipelines
 
-    n, bad = fuzz_pipelines.sweep(48, seed)
-    assert n == 48 and bad == 0
+    n, bad = fuzz_pipelines.sweep(56, seed)
+    assert n == 56 and bad == 0

@@ -215,6 +215,38 @@ def ssl_batch_round(R):
     return bad, desc
 
 
+def posneg_round(R):
+    """RandCropByPosNegLabeld sandwich (has_label, random_crop_size, n_crops): list outputs, fg / bg index lists
+    from the cached stage, masks with few or no foreground voxels."""
+    keys = list(R.choice(["t2", "adc", "dwi"], size=int(R.randint(1, 3)), replace=False))
+    shape = (int(R.choice([24, 28, 32])), int(R.choice([24, 30])), int(R.choice([8, 12])))
+    rc = [int(s * R.uniform(0.4, 0.8)) for s in shape]
+    n_crops = int(R.randint(1, 4))
+    augment = [a for a in ["affine", "flip"] if R.rand() < 0.7] or ["flip"]
+    seed = int(R.randint(1 << 30))
+    thr = float(R.choice([0.7, 0.97, 0.999, 0.02]))
+    samples = samples_of(R, 3, keys, shape)
+    for s in samples:
+        s["mask"] = (torch.from_numpy(R.rand(1, *shape).astype(np.float32)) > thr).to(torch.float32)
+        if not (s["mask"] > 0).any() or (s["mask"] > 0).all():   # MONAI needs both classes (it warns and degenerates otherwise)
+            s["mask"][0, 1, 1, 1] = 1.0; s["mask"][0, 2, 2, 2] = 0.0
+        flat = (s["mask"] > 0).reshape(-1).numpy()
+        s["mask_fg_indices"], s["mask_bg_indices"] = np.nonzero(flat)[0], np.nonzero(~flat)[0]
+    lazy = T.Compose([F.get_augmentations_unet(augment, keys + ["mask"], keys, [], random_crop_size=rc, n_crops=n_crops, flip_axis=[0, 1, 2]),
+                      T.ConcatItemsd(keys, "image"), T.SelectItemsd(["image", "mask"])]).set_random_state(seed)
+    ref = P.Chain([P.unet(augment, keys + ["mask"], keys, random_crop_size=rc, n_crops=n_crops, flip_axis=(0, 1, 2)), P.ConcatD(keys, "image")]).seed(seed)
+    got = collate.safe_collate_crops([lazy(dict(s)) for s in samples])
+    want = [c for s in samples for c in ref(s)]
+    desc = f"posneg augment={augment} keys={keys} shape={shape} rc={rc} n_crops={n_crops} thr={thr} seed={seed}"
+    pre = [int(i * 1.10) for i in rc]
+    if tuple(got["image"].shape) != (3 * n_crops, len(keys), *rc):
+        return 1, desc + f" shape {tuple(got['image'].shape)}"
+    bad = 0
+    for b, w in enumerate(want):
+        bad += int(not torch.equal(got["image"][b], w["image"])) + int(not torch.equal(got["mask"][b], w["mask"]))
+    return bad, desc
+
+
 def sweep(rounds, seed, verbose=True):
     R = np.random.RandomState(seed)
     T.set_mode(strict=True, fast=False, noise="injected")
@@ -223,7 +255,7 @@ def sweep(rounds, seed, verbose=True):
     bad = 0
     try:
         for r in range(rounds):
-            fn = [unet_round, class_round, ssl_round, seg_batch_round, class_batch_round, ssl_batch_round][r % 6]
+            fn = [unet_round, class_round, ssl_round, seg_batch_round, class_batch_round, ssl_batch_round, posneg_round][r % 7]
             b, desc = fn(R)
             if b:
                 bad += 1
