@@ -30,6 +30,31 @@ CASES = {
 }
 
 
+def _random_cases(n=40, seed=11):
+    """Seeded random windows: boxes touching the borders, single voxels, odd sizes, output sizes smaller and larger
+    than the box, empty masks."""
+    import numpy as np
+    R = np.random.RandomState(seed)
+    out = {}
+    for i in range(n):
+        spatial = tuple(int(R.randint(9, 48)) for _ in range(3))
+        if R.rand() < 0.12:
+            box = None
+        else:
+            box = []
+            for s in spatial:
+                a = int(R.randint(0, s)); b = int(R.randint(a + 1, s + 1))
+                if R.rand() < 0.2: a = 0
+                if R.rand() < 0.2: b = s
+                box.append((a, b))
+        osize = None if (box is not None and R.rand() < 0.3) else [int(R.randint(1, s + 1)) for s in spatial]
+        out[f"random_{i:02d}"] = (spatial, box, osize)
+    return out
+
+
+CASES.update(_random_cases())
+
+
 def load_reference():
     class Crop:
         def __init__(self, *a, **k):
