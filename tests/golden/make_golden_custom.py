@@ -62,6 +62,26 @@ ADJUST_CASES = [("even_odd", {"a": (1, 10, 9, 8), "b": (1, 5, 9, 6), "c": (2, 7,
 CROP_CASES = [((2, 70, 61, 20), (32, 32, 8)), ((1, 64, 45, 17), (16, 16, 8)), ((1, 40, 36, 16), (32, 32, 8))]
 
 
+def _random_cases(seed=21):
+    """Seeded random shapes: size differences of every parity for AdjustSizesd, volumes smaller / larger than the
+    crop size and non-multiples of it for GetAllCropsd."""
+    R = np.random.RandomState(seed)
+    adjust, crops = [], []
+    for i in range(8):
+        keys = ["a", "b", "c"][: int(R.randint(2, 4))]
+        adjust.append((f"random_{i}", {k: (int(R.randint(1, 3)), int(R.randint(4, 14)), int(R.randint(4, 14)), int(R.randint(3, 10))) for k in keys}))
+    for i in range(6):
+        size = (int(R.choice([8, 12, 16])), int(R.choice([8, 12, 16])), int(R.choice([4, 6, 8])))
+        shape = (int(R.randint(1, 3)), int(R.randint(5, 40)), int(R.randint(5, 40)), int(R.randint(3, 20)))
+        crops.append((shape, size))
+    return adjust, crops
+
+
+_adj, _crp = _random_cases()
+ADJUST_CASES += _adj
+CROP_CASES += _crp
+
+
 def ramp(shape, mod=251):
     """Position-coded volume (compresses well, every voxel of a crop identifies its origin)."""
     return (np.arange(int(np.prod(shape)), dtype=np.int64) % mod).astype(np.float32).reshape(shape)
