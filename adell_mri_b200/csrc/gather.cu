@@ -979,7 +979,10 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
     rm = true;
     int rlo, rhi;
     if (it.padding == ADELL_PAD_BORDER) {
-      rlo = min(max(lo, 0), S - 1); rhi = min(max(hi, 0), S - 1);
+      // a coordinate clamped onto cell 0 still READS cell 1 (weight 0): a tile that lies entirely below the
+      // volume needs [0, 1], not [0, 0] — on an axis that runs backwards in memory cell 1 would otherwise sit
+      // at box index -1 (an illegal address for the bit-faithful path; found by tools/fuzz_parity.py)
+      rlo = min(max(lo, 0), S - 1); rhi = min(max(hi, min(1, S - 1)), S - 1);
     } else if (lo >= -S && hi < 0) {            // inside the first mirrored period below
       rlo = -1 - hi; rhi = -1 - lo;
     } else if (lo >= S && hi <= 2 * S - 1) {    // inside the first mirrored period above

@@ -475,3 +475,33 @@ def test_prepared_steps_equal_step_by_step_calls(sizes):
             assert torch.equal(outs[k]["mask"], want[k]["mask"]), k
     fired = sum(int(not torch.equal(want[k]["image"][j, 0], batches[k][j]["t2"][0])) for k in range(len(sizes)) for j in range(sizes[k]))
     assert fired >= 3
+
+
+@pytest.mark.parametrize("strict", [True, False])
+@pytest.mark.parametrize("seed", [0, 1])
+def test_border_tiles_entirely_outside_on_a_reversed_axis(strict, seed):
+    """Found by the randomised sweep (an illegal address): border padding, axes flipped BEFORE the resample
+    (negative source strides) and tiles that lie entirely below the volume.  The coordinate clamps onto cell 0,
+    whose hi tap, cell 1 (weight 0, still read), sat at box index -1 on the reversed axis."""
+    from adell_mri_b200 import engine
+
+    R = np.random.RandomState(200 + seed)
+    shape = (72, 72, 64)
+    vols = [torch.from_numpy(R.rand(*shape).astype(np.float32)) for _ in range(3)]
+    A = [rand_affine_matrix(R, rotate=(0.35, 0.35, 0.2), translate=(24, 20, 10), scale=(0.1, 0.1, 0.1)) for _ in vols]
+    flips = np.array([[1, 0, 1], [1, 1, 1], [0, 1, 0]], bool)
+    plan = BatchPlan([v.to(DEV) for v in vols], strict=strict)
+    plan.flip(flips)
+    plan.affine(np.stack([a.numpy() for a in A]), "bilinear", "border")
+    plan.center_crop((70, 64, 62))
+    outs = [torch.full((70, 64, 62), float("nan"), device=DEV) for _ in vols]
+    engine.execute(plan, outs)
+    torch.cuda.synchronize()
+    for i, v in enumerate(vols):
+        fl = [a for a in range(3) if flips[i, a]]
+        ref = M.center_spatial_crop(M.affine_resample(M.flip(v[None], fl), A[i], "bilinear", "border"), (70, 64, 62))[0]
+        got = outs[i].cpu()
+        if strict:
+            assert torch.equal(got, ref), i
+        else:
+            assert torch.allclose(got, ref, rtol=1e-4, atol=1e-4), (i, float((got - ref).abs().max()))
