@@ -72,13 +72,19 @@ def random_item(R):
         roi = [min(r, c) for r, c in zip(roi, cur)]
         st = [int(R.randint(0, c - r + 1)) for c, r in zip(cur, roi)]
         plan.crop(st, roi); ref = M.crop(ref, st, roi); cur = roi; desc.append(f"crop={st}+{roi}")
+    if R.rand() < 0.25:          # an intensity map BEFORE the resample: zero-padded taps must stay 0, not the offset
+        s0, o0 = float(np.float32(R.uniform(0.5, 1.5))), float(np.float32(R.uniform(-0.3, 0.3)))
+        plan.intensity(scale=s0, offset=o0)
+        ref = ref.to(torch.float32) * torch.tensor(s0, dtype=torch.float32) + torch.tensor(o0, dtype=torch.float32)
+        exact = False
+        desc.append("pre-intensity")
     kind = R.rand()
     if kind < 0.55:
         mode = "nearest" if R.rand() < 0.35 else "bilinear"
         padding = str(R.choice(["zeros", "border", "reflection"]))
         A = rand_affine_matrix(R, rotate=(0.4, 0.4, 0.2), translate=(4, 4, 2), scale=(0.1, 0.1, 0.1))
         plan.affine(A.numpy(), mode, padding); ref = M.affine_resample(ref, A, mode, padding); desc.append(f"affine {mode} {padding}")
-        exact = mode == "nearest" or strict
+        exact = exact and (mode == "nearest" or strict)
         if R.rand() < 0.15:      # a second resample (the reference's shear after the affine): one more pass
             A2 = rand_affine_matrix(R, rotate=(0.1, 0.1, 0.1), translate=(1, 1, 1), scale=(0.05, 0.05, 0.05))
             plan.affine(A2.numpy(), mode, padding); ref = M.affine_resample(ref, A2, mode, padding)
