@@ -327,9 +327,6 @@ struct __align__(16) K1Fast {
   int4 fl;               // cold (padded | noise | philox), padded, philox, -
   float4 rf[3];          // per source axis a: {1/(2 S_a), 2 S_a, S_a-1, rA_a} (axes in rmask)
   float4 rb;             // rB_0, rB_1, rB_2: box-local index = rA*u' + rB for the axes in rmask; [3] = tie threshold
-  float4 rl;             // lower clamp of the clamped / folded coordinate per axis: 0, or — on an axis that runs backwards
-                         // in memory (msign < 0: box index = mconst - x) — the smallest x that keeps the box index
-                         // below mconst, so that the hi tap (index + 1) stays inside the box
   float4 ws;             // valid-weight variant (RM 3): {pre_o * post_s, post_o, -, -}; rf[a] = {lo_a - 1, hi_a + 1} then holds
                          // the box-local interval of valid taps along axis a
   int4 vlo, vhi;         // valid output range, tile-local
@@ -346,11 +343,11 @@ struct __align__(16) K1Fast {
 // reflected coordinate is |f| * 2S - 0.5 (then the clamp to [0, S-1] ATen applies as well).  The
 // producer shifts the tile's coordinates by a whole number of periods so that |y| stays small
 // (error of the fold: a few 1e-6 voxel).  rint is the round-to-nearest add of 1.5 * 2^23.
-__device__ __forceinline__ float k1_fold_reflect(float u, float inv2S, float hinv, float twoS, float Sm1, float lo = 0.0f) {
+__device__ __forceinline__ float k1_fold_reflect(float u, float inv2S, float hinv, float twoS, float Sm1) {
   const float y = fmaf(u, inv2S, hinv);
   const float n = __fadd_rn(y, K1_MAGIC) - K1_MAGIC;
   const float x = fmaf(fabsf(y - n), twoS, -0.5f);
-  return fminf(Sm1, fmaxf(x, lo));
+  return fminf(Sm1, fmaxf(x, 0.0f));
 }
 
 // bit-faithful replay for one nearest voxel (tie window of the fast path); cold
@@ -376,7 +373,7 @@ struct K1Hot {
   float D1[3], P[3];      // coordinate along dj: v_a = P_a + D1_a * dj
   float gain, bias;
   uint32_t p0, p1, cbase; // tap address = cbase + 4*(bits0*p0 + bits1*p1 + bits2), bits = float bits of x + MAGIC
-  float inv2S[3], hinv[3], twoS[3], Sm1[3], rA[3], rB[3], lo[3];
+  float inv2S[3], hinv[3], twoS[3], Sm1[3], rA[3], rB[3];
   int rmask, pad;
   float vl[3], vh[3];     // RM 3: valid taps lie strictly between vl and vh (box-local)
   float wb, po;           // RM 3: pre_o * post_s (scaled by the valid weight), post_o
@@ -407,13 +404,12 @@ __device__ __forceinline__ void k1_hot_load(K1Hot<RM>& h, const K1Fast& f) {
     h.wb = ws.x; h.po = ws.y;
   } else if (RM) {
     h.rmask = m.z & 0xff; h.pad = m.z >> 8;
-    const float4 rb = f.rb, rl = f.rl;
+    const float4 rb = f.rb;
     h.rB[0] = rb.x; h.rB[1] = rb.y; h.rB[2] = rb.z;
 #pragma unroll
     for (int a = (RM == 1 ? 2 : 0); a < 3; ++a) {
       const float4 q = f.rf[a];
       h.inv2S[a] = q.x; h.hinv[a] = 0.5f * q.x; h.twoS[a] = q.y; h.Sm1[a] = q.z; h.rA[a] = q.w;
-      h.lo[a] = a == 0 ? rl.x : (a == 1 ? rl.y : rl.z);
     }
   }
 }
@@ -455,8 +451,8 @@ __device__ __forceinline__ bool k1_plane_map(const K1Fast& f, K1Map& m, int di) 
 template <int RM>
 __device__ __forceinline__ float k1_fast_pad_axis(const K1Hot<RM>& h, int a, float v) {
   float x;
-  if (RM == 1 || h.pad == ADELL_PAD_REFLECTION) x = k1_fold_reflect(v, h.inv2S[a], h.hinv[a], h.twoS[a], h.Sm1[a], h.lo[a]);
-  else x = fminf(h.Sm1[a], fmaxf(v, h.lo[a]));
+  if (RM == 1 || h.pad == ADELL_PAD_REFLECTION) x = k1_fold_reflect(v, h.inv2S[a], h.hinv[a], h.twoS[a], h.Sm1[a]);
+  else x = fminf(h.Sm1[a], fmaxf(v, 0.0f));
   return fmaf(h.rA[a], x, h.rB[a]);
 }
 
@@ -584,7 +580,7 @@ template <int RM>
 struct K1Hot2 {
   k1_f2 D1[3], P[3];
   k1_f2 inv2S, hinv, twoS, rA, rB;   // RM == 1: reflection fold of source axis 2
-  float Sm1, lo;
+  float Sm1;
   k1_f2 vl[3], vh[3];                // RM == 3: valid tap interval per axis
 };
 template <int RM>
@@ -597,7 +593,7 @@ __device__ __forceinline__ K1Vox2 k1_fast_vox2(const K1Hot<RM>& h, const K1Hot2<
     const k1_f2 x = f2_fma(f2_abs(f2_sub(y, n)), q.twoS, f2_dup(-0.5f));
     float xa, xb;
     f2_unpack(x, xa, xb);
-    xa = fminf(q.Sm1, fmaxf(xa, q.lo)); xb = fminf(q.Sm1, fmaxf(xb, q.lo));
+    xa = fminf(q.Sm1, fmaxf(xa, 0.0f)); xb = fminf(q.Sm1, fmaxf(xb, 0.0f));
     v2 = f2_fma(q.rA, f2_pack(xa, xb), q.rB);
   }
   // floor on the FMA pipe: round-down add of 1.5*2^23 leaves floor(x) in the low mantissa bits
@@ -647,7 +643,7 @@ __device__ __forceinline__ void k1_tile_staged_trilinear(const K1Fast& f) {
   K1Hot2<RMASK> q;
   if (RMASK == 1) {
     q.inv2S = f2_dup(h.inv2S[2]); q.hinv = f2_dup(h.hinv[2]); q.twoS = f2_dup(h.twoS[2]);
-    q.rA = f2_dup(h.rA[2]); q.rB = f2_dup(h.rB[2]); q.Sm1 = h.Sm1[2]; q.lo = h.lo[2];
+    q.rA = f2_dup(h.rA[2]); q.rB = f2_dup(h.rB[2]); q.Sm1 = h.Sm1[2];
   }
   k1_f2 WB2 = 0, PO2 = 0;
   if (RMASK == 3) {
@@ -997,6 +993,11 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
     // the fast path clamps u' just below S-1: the hi tap never reads cell S, and the lo tap of a
     // coordinate clamped at the upper edge is S-2
     blo = min(rlo, max(S - 2, 0)); bhi = rhi + (S == 1 ? 1 : 0);
+    // an axis that runs backwards in memory (box index = bhi - t): a coordinate clamped / reflected onto the lowest
+    // cell blo puts the lo tap on the LAST needed box index and the hi tap (weight 0, still read) one cell past it.
+    // Stage that cell too (t = blo - 1: real data, or TMA's zero fill outside the volume) — the mirror image of the
+    // clamp one ulp below S-1 on forward axes, at no cost in the voxel loops.
+    if (it.tmap_sign[a] < 0) blo -= 1;
   }
   // cells [blo, bhi] plus, along the contiguous axis, those lost to aligning the box origin down to 16 bytes
   const int mo_raw = it.tmap_sign[a] > 0 ? blo + it.tmap_off[a] : -bhi + it.tmap_off[a];
@@ -1057,13 +1058,7 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
     // clamp just below S-1 (one ulp): floor(u') + 1 <= S-1, the lerp error is <= 2^-23 of the step
     if (rm) {
       f.rf[a] = make_float4(0.5f / c.Sf[a], 2.0f * c.Sf[a], c.Sm1[a] > 0.0f ? __uint_as_float(__float_as_uint(c.Sm1[a]) - 1u) : 0.0f, rA);
-      // reversed axis: box index = mconst - x, and x = 0 (a coordinate clamped / reflected onto the first
-      // cell) would put the lo tap ON mconst and the hi tap one cell past the box: keep x one ulp of the box
-      // index above 0 (the mirror image of the clamp one ulp below S-1 on forward axes)
-      const float mc = static_cast<float>(mconst);
-      reinterpret_cast<float*>(&f.rl)[a] = (msign < 0 && mconst > 0) ? mc - __uint_as_float(__float_as_uint(mc) - 1u) : 0.0f;
     } else {
-      reinterpret_cast<float*>(&f.rl)[a] = 0.0f;
       // box-local interval [m_lo, m_hi] of the valid taps (m = msign * t + mconst, t in [tlo, thi - 1])
       const int ma = msign * c.tlo[a] + mconst, mb = msign * (c.thi[a] - 1) + mconst;
       f.rf[a] = make_float4(static_cast<float>(min(ma, mb) - 1), static_cast<float>(max(ma, mb) + 1), 0.0f, 0.0f);
@@ -1621,6 +1616,7 @@ int64_t k1_box_for_tile(const adell_item& it, const int* T, int* box, bool shear
       // S-1, so the hi tap never leaves the volume), and a thin axis is simply staged whole so that
       // multiply-reflected tiles stay on this path
       if (it.src_shape[a] <= 64 || box[a] >= it.src_shape[a]) { box[a] = it.src_shape[a] > 1 ? it.src_shape[a] : 2; whole = true; }
+      if (it.tmap_sign[a] < 0) box[a] += 1;   // reversed axis: the cell below the staged interval (see k1_tile_setup)
     }
     if (a == 2) {
       // inner extent: a 16-byte multiple, plus the cells lost to aligning the box origin down to 16 bytes
