@@ -289,3 +289,15 @@ def test_randomised_builder_configurations_match_the_eager_reference(seed):
 
     n, bad = fuzz_pipelines.sweep(56, seed)
     assert n == 56 and bad == 0
+
+
+@pytest.mark.gpu
+def test_randomised_builder_configurations_through_the_cuda_path():
+    """The same sweep with the plans executed by the CUDA kernels instead of the C restatement."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import fuzz_pipelines
+
+    n, bad = fuzz_pipelines.sweep(70, 4, device="cuda:0")
+    assert n == 70 and bad == 0

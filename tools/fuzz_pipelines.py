@@ -5,7 +5,7 @@ and SSL builders.  Runs on the CPU: plans execute through the C restatement (ora
 the HOST logic — draw orders, seed fan-out, chain composition, collation — not the CUDA kernels.  Test
 infrastructure (imports oracle/).
 
-    python tools/fuzz_pipelines.py [n_rounds] [seed]
+    python tools/fuzz_pipelines.py [n_rounds] [seed] [cuda:0]
 """
 import os
 import sys
@@ -28,7 +28,11 @@ def cref_execute_ptrs(plan, dst_ptr, dst_stride, keep=None):
 
 
 
+DEVICE = "cpu"
+
+
 def samples_of(R, n, keys, shape, mask=True):
+    """CPU samples (what the eager oracle consumes); `dev()` moves a copy to the device under test."""
     out = []
     for _ in range(n):
         s = {k: torch.from_numpy(R.rand(1, *shape).astype(np.float32)) for k in keys}
@@ -36,6 +40,14 @@ def samples_of(R, n, keys, shape, mask=True):
             s["mask"] = torch.from_numpy((R.rand(1, *shape) > 0.7).astype(np.float32))
         out.append(s)
     return out
+
+
+def dev(s):
+    return {k: (v.to(DEVICE) if isinstance(v, torch.Tensor) else v) for k, v in s.items()}
+
+
+def host(d):
+    return {k: (v.cpu() if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
 
 
 def shape_of(R):
@@ -60,7 +72,7 @@ def unet_round(R):
                       T.ConcatItemsd(keys, "image")]).set_random_state(seed)
     ref = P.Chain([P.unet(augment, all_keys, keys, random_crop_size=rc, has_label=has_label, flip_axis=tuple(flip_axis)),
                    P.ConcatD(keys, "image")]).seed(seed)
-    got = collate.safe_collate([lazy(dict(s)) for s in samples])
+    got = host(collate.safe_collate([lazy(dev(s)) for s in samples]))
     desc = f"unet augment={augment} keys={keys} shape={shape} flip_axis={flip_axis} rc={rc} label={has_label} seed={seed}"
     bad = 0
     for b, s in enumerate(samples):
@@ -88,7 +100,7 @@ def class_round(R):
     m = [c + 16 for c in crop]
     ref = P.Chain([P.CenterCropD(keys + ["mask"], m), P.classification(augment, keys, "mask", flip_axis=tuple(flip_axis), prob=prob),
                    P.CenterCropD(keys + ["mask"], crop), P.ConcatD(keys + ["mask"], "image")]).seed(seed)
-    got = collate.safe_collate([lazy(dict(s)) for s in samples])
+    got = host(collate.safe_collate([lazy(dev(s)) for s in samples]))
     desc = f"class augment={augment} keys={keys} shape={shape} crop={crop} flip_axis={flip_axis} prob={prob} seed={seed}"
     bad = sum(int(not torch.equal(got["image"][b], ref(s)["image"])) for b, s in enumerate(samples))
     return bad, desc
@@ -112,7 +124,7 @@ def ssl_round(R):
                                                  aug_list=list(names))).set_random_state(seed)
     ref = P.Chain(P.ssl(["image"], ["image_copy"], roi, vicregl, different, names, n_t)).seed(seed)
     np.random.seed(gseed)
-    got = collate.safe_collate([lazy(dict(s)) for s in samples])
+    got = host(collate.safe_collate([lazy(dev(s)) for s in samples]))
     np.random.seed(gseed)
     desc = f"ssl names={names} shape={shape} roi={roi} vicregl={vicregl} different={different} N={n_t} seed={seed}"
     bad = 0
@@ -146,9 +158,9 @@ def seg_batch_round(R):
     else:   # chained by hand: constructing an outer Compose would re-seed its children (MONAI behaviour)
         aug_t.set_random_state(seed)
         lazy = lambda d: concat(aug_t(d))   # noqa: E731
-    want = collate.safe_collate([lazy(dict(s)) for s in samples])
+    want = host(collate.safe_collate([lazy(dev(s)) for s in samples]))
     aug = SegmentationBatchAugmenter(augment, all_keys, keys, random_crop_size=rc, has_label=has_label, flip_axis=flip_axis, strict=True)
-    got = aug.set_random_state(seed, nested=nested)(samples)
+    got = host(aug.set_random_state(seed, nested=nested)([dev(s) for s in samples]))
     desc = f"seg_batch nested={nested} augment={augment} keys={keys} shape={shape} flip_axis={flip_axis} rc={rc} label={has_label} seed={seed}"
     bad = int(not torch.equal(got["image"], want["image"]))
     if has_label:
@@ -173,9 +185,9 @@ def class_batch_round(R):
     else:
         aug_t.set_random_state(seed)
         lazy = lambda d: tail[1](tail[0](aug_t(d)))   # noqa: E731
-    want = collate.safe_collate([lazy(dict(s)) for s in samples])["image"]
+    want = host(collate.safe_collate([lazy(dev(s)) for s in samples]))["image"]
     aug = ClassificationBatchAugmenter(augment, keys, mask_key, flip_axis=flip_axis, prob=prob, crop_size=crop, strict=True)
-    got = aug.set_random_state(seed, nested=nested)(samples)["image"]
+    got = aug.set_random_state(seed, nested=nested)([dev(s) for s in samples])["image"].cpu()
     desc = f"class_batch nested={nested} augment={augment} keys={keys} mask={mask_key} shape={shape} crop={crop} flip_axis={flip_axis} prob={prob} seed={seed}"
     return int(not torch.equal(got, want)), desc
 
@@ -204,10 +216,10 @@ def ssl_batch_round(R):
         return d
 
     np.random.seed(gseed)
-    want = collate.safe_collate([run(dict(s)) for s in samples])
+    want = host(collate.safe_collate([run(dev(s)) for s in samples]))
     aug = SSLBatchAugmenter(["image"], roi, n_transforms=n_t, different_crop=different, vicregl=vicregl, members=members, strict=True)
     np.random.seed(gseed)
-    got = aug.set_random_state(seed)(samples)
+    got = host(aug.set_random_state(seed)([dev(s) for s in samples]))
     desc = f"ssl_batch members={members} shape={shape} roi={roi} vicregl={vicregl} different={different} N={n_t} seed={seed}"
     bad = sum(int(not torch.allclose(got[k], want[k], rtol=2e-6, atol=2e-6)) for k in ("augmented_image_1", "augmented_image_2"))
     if vicregl:
@@ -235,7 +247,7 @@ def posneg_round(R):
     lazy = T.Compose([F.get_augmentations_unet(augment, keys + ["mask"], keys, [], random_crop_size=rc, n_crops=n_crops, flip_axis=[0, 1, 2]),
                       T.ConcatItemsd(keys, "image"), T.SelectItemsd(["image", "mask"])]).set_random_state(seed)
     ref = P.Chain([P.unet(augment, keys + ["mask"], keys, random_crop_size=rc, n_crops=n_crops, flip_axis=(0, 1, 2)), P.ConcatD(keys, "image")]).seed(seed)
-    got = collate.safe_collate_crops([lazy(dict(s)) for s in samples])
+    got = host(collate.safe_collate_crops([lazy(dev(s)) for s in samples]))
     want = [c for s in samples for c in ref(s)]
     desc = f"posneg augment={augment} keys={keys} shape={shape} rc={rc} n_crops={n_crops} thr={thr} seed={seed}"
     pre = [int(i * 1.10) for i in rc]
@@ -247,11 +259,15 @@ def posneg_round(R):
     return bad, desc
 
 
-def sweep(rounds, seed, verbose=True):
+def sweep(rounds, seed, verbose=True, device="cpu"):
+    """device="cpu": plans execute through the C restatement (host logic only); "cuda:0": through the CUDA path."""
+    global DEVICE
+    DEVICE = device
     R = np.random.RandomState(seed)
     T.set_mode(strict=True, fast=False, noise="injected")
-    saved, engine.execute = engine.execute, cref_execute     # CPU stand-ins for the launcher (test infrastructure)
-    saved_ptrs, engine.execute_ptrs = engine.execute_ptrs, cref_execute_ptrs
+    saved, saved_ptrs = engine.execute, engine.execute_ptrs
+    if device == "cpu":     # CPU stand-ins for the launcher (test infrastructure)
+        engine.execute, engine.execute_ptrs = cref_execute, cref_execute_ptrs
     bad = 0
     try:
         for r in range(rounds):
@@ -271,6 +287,6 @@ def sweep(rounds, seed, verbose=True):
 if __name__ == "__main__":
     rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 60
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-    n, bad = sweep(rounds, seed)
+    n, bad = sweep(rounds, seed, device=sys.argv[3] if len(sys.argv) > 3 else "cpu")
     print(f"fuzz_pipelines: {n} rounds, {bad} with mismatches (seed {seed})")
     sys.exit(1 if bad else 0)
