@@ -216,6 +216,16 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries the ONE JSON line and nothing else: native libraries write there too (NCCL prints its
+    # version banner on fd 1 when the box sets NCCL_DEBUG), so fd 1 points at stderr until the line is emitted.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+
     desc, shape, image_keys, batch = WORKLOADS[args.workload]
     nk = len(image_keys) + 1
     vox_per_step = batch * nk * shape[0] * shape[1] * shape[2]
@@ -243,7 +253,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": 1e3 * vox_per_step / v, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "cpu_baseline": cb,
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import numpy as np
@@ -430,7 +440,7 @@ def main():
             ref = CpuReference(args.workload)
             line["cpu_baseline"] = ref.run(args.cpu_samples)
             ref.close()
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
