@@ -292,13 +292,18 @@ def main():
         b0 = (i % n_batches) * batch
         return cache[b0:b0 + batch]
 
-    def run_steps(first, count, events=None):
-        """`count` steps starting at global step index `first`: draws + composition + upload for up to
-        CHUNK steps at a time, then one K1 launch per step."""
+    def prep(first, n):
+        return aug.prepare_steps([batch_of(first + k) for k in range(n)], [out] * n), n
+
+    def run_steps(first, count, ahead, next_n, events=None):
+        """`count` steps starting at global step index `first`, software-pipelined the way a training loop
+        runs them: the K1 launches of a chunk are queued, then the host makes the draws + composition + upload
+        of the NEXT chunk (up to CHUNK steps) while the device works.  `ahead` = the prepared first chunk;
+        after the last launch the host prepares `next_n` steps beyond the end and returns them, so a region of
+        `count` steps holds `count` launches and the host work of as many steps as it was handed ready-made."""
         done = 0
         while done < count:
-            n = min(CHUNK, count - done)
-            prepared = aug.prepare_steps([batch_of(first + done + k) for k in range(n)], [out] * n)
+            prepared, n = ahead
             for k in range(n):
                 timed = events is not None and (done + k) % EVERY == 0   # a sample of the launches: each
                 if timed:                                              # event pair costs ~5 us of host time
@@ -307,10 +312,13 @@ def main():
                 if timed:
                     events[2 * ((done + k) // EVERY) + 1].record(stream)
             done += n
+            ahead = prep(first + done, min(CHUNK, count - done) if done < count else next_n)
+        return ahead
 
     # ---- device-resident throughput ("value") ----
     stream = torch.cuda.current_stream()
-    run_steps(0, args.warmup)
+    first_n = min(CHUNK, args.steps)
+    ahead = run_steps(0, args.warmup, prep(0, min(CHUNK, args.warmup)), first_n)
     barrier()
     clocks = ClockSampler(local_rank if not os.environ.get('BENCH_NO_CLOCKS') else -1).start()
     n_timed = (args.steps + EVERY - 1) // EVERY
@@ -318,7 +326,7 @@ def main():
     launches0 = engine.launch_count
     e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e_start.record(stream)
-    run_steps(args.warmup, args.steps, None if os.environ.get('BENCH_NO_EVENTS') else ev)
+    run_steps(args.warmup, args.steps, ahead, first_n, None if os.environ.get('BENCH_NO_EVENTS') else ev)
     e_stop.record(stream)
     barrier()
     clock_info = clocks.stop()
