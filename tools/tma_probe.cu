@@ -1,3 +1,4 @@
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o tools/tma_probe tools/tma_probe.cu -lcuda
 // Stand-alone probe: 3-D TMA tile load (fp32, no swizzle, OOB zero fill) with the descriptor
 // passed (a) as a __grid_constant__ parameter and (b) through global memory.
 #include <cuda.h>

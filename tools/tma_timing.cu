@@ -1,3 +1,4 @@
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o tools/tma_timing tools/tma_timing.cu -lcuda
 // Micro-timing on one SM: cost of the tensormap proxy fence (sys / gpu scope) and of one 3-D TMA
 // box load with short inner rows, in SM cycles.
 #include <cuda.h>
