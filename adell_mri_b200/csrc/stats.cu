@@ -535,6 +535,10 @@ st_hist_select(const unsigned long long* __restrict__ bins, int n_sel, int first
   for (int b = b_lo; b < min(nb, b_lo + per); ++b) local += hb[b];
   __shared__ unsigned long long scan[ST_THREADS];
   scan[threadIdx.x] = local;
+  // every thread reads the requested rank (and the prefix so far) BEFORE the barriers of the scan: the one
+  // selecting thread overwrites both at the end, and a late warp must not see the already-reduced rank
+  const unsigned long long r = rank[blockIdx.x];
+  const uint32_t p_in = first_pass ? 0u : prefix[blockIdx.x];
   __syncthreads();
   // inclusive Hillis-Steele scan over 256 partial sums
   for (int o = 1; o < ST_THREADS; o <<= 1) {
@@ -543,15 +547,13 @@ st_hist_select(const unsigned long long* __restrict__ bins, int n_sel, int first
     scan[threadIdx.x] += t;
     __syncthreads();
   }
-  const unsigned long long r = rank[blockIdx.x];
   const unsigned long long before = scan[threadIdx.x] - local;
   if (r >= before && r < scan[threadIdx.x]) {  // exactly one thread
     unsigned long long cum = before;
     for (int b = b_lo; b < min(nb, b_lo + per); ++b) {
       unsigned long long c = hb[b];
       if (r < cum + c) {
-        uint32_t p = first_pass ? 0u : prefix[blockIdx.x];
-        prefix[blockIdx.x] = p | (static_cast<uint32_t>(b) << shift);
+        prefix[blockIdx.x] = p_in | (static_cast<uint32_t>(b) << shift);
         rank[blockIdx.x] = r - cum;
         break;
       }

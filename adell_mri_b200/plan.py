@@ -354,6 +354,9 @@ class BatchPlan:
             untouched = (
                 (st.post.off == 0).all(1) & (st.post.sign == 1).all(1) & (st.post.size == st.post.vhi).all(1)
                 & (st.post.vlo == 0).all(1) & (st.post_s == 1) & (st.post_o == 0)
+                # a crop that starts at 0 only shrinks post.size: the next affine then acts about the centre
+                # of the CROPPED grid, which a matrix product on the uncropped grid does not express
+                & (st.post.size == st.pre.size).all(1)
             )
             comp &= untouched
             if comp.any():
@@ -365,7 +368,8 @@ class BatchPlan:
         self._close(w & (st.has_affine | self._has_noise()))
         # a pending post map precedes this resample: fold it into the per-tap pre map
         foldable = w & ((st.post_s != 1) | (st.post_o != 0))
-        bad = foldable & ((st.pre.has_invalid() & (st.post_o != 0)) | (st.pre_dev != 0))
+        # (the kernel applies pre -> clip -> post per tap: folding post into pre would move it before the clip)
+        bad = foldable & ((st.pre.has_invalid() & (st.post_o != 0)) | (st.pre_dev != 0) | st.clip)
         self._close(bad)
         foldable &= ~bad
         st.pre_o = np.where(foldable, st.pre_o * st.post_s + st.post_o, st.pre_o)

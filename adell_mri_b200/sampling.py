@@ -35,12 +35,27 @@ def rand_param(R: np.random.RandomState, param_range, add_scalar: float = 0.0) -
     return out
 
 
+#: † MONAI's ``RandAffined.__call__`` re-randomises its inner ``RandAffine`` once per key through
+#: ``self.rand_affine(d[key], None, mode, padding_mode, True, grid)`` — but only inside ``if do_resampling:``
+#: (MONAI >= 1.0; with ``spatial_size=None``, as the reference always uses, ``do_resampling == fired``).  A call
+#: that does not fire therefore consumes one outer gate draw, one inner gate draw and ONE grid randomize, nothing
+#: per key.  Round 1 consumed the per-key draws on idle calls too; that reading is kept behind this switch so a
+#: maintainer with MONAI installed can compare both against the real stream.
+PER_KEY_DRAWS_WHEN_IDLE = False
+
+
 class RandAffineSampler:
     """Draw order of ``monai.transforms.RandAffined.__call__`` (three identically seeded
-    streams: the dict transform, its RandAffine and its RandAffineGrid) †."""
+    streams: the dict transform, its RandAffine and its RandAffineGrid) †.
 
-    def __init__(self, prob=0.1, rotate_range=None, shear_range=None, translate_range=None, scale_range=None):
+    ``per_key_draws_when_idle``: whether a call whose gate did NOT fire still consumes the per-key
+    ``RandAffine.randomize()`` draws (``None`` = module default :data:`PER_KEY_DRAWS_WHEN_IDLE`, i.e. the
+    MONAI >= 1.0 reading: it does not)."""
+
+    def __init__(self, prob=0.1, rotate_range=None, shear_range=None, translate_range=None, scale_range=None,
+                 per_key_draws_when_idle: bool | None = None):
         self.prob = prob
+        self.per_key_draws_when_idle = PER_KEY_DRAWS_WHEN_IDLE if per_key_draws_when_idle is None else bool(per_key_draws_when_idle)
         self.rotate_range, self.shear_range = rotate_range, shear_range
         self.translate_range, self.scale_range = translate_range, scale_range
         self.set_random_state()
@@ -69,9 +84,10 @@ class RandAffineSampler:
         self.R_inner.rand()                        # RandAffine.randomize (prob=1.0) ...
         self._grid_params()                        # ... -> RandAffineGrid.randomize (discarded)
         used = self._grid_params() if fired else None  # RandAffineGrid.__call__ re-randomises: USED
-        for _ in range(n_keys):                    # per key: RandAffine.__call__(randomize=True)
-            self.R_inner.rand()
-            self._grid_params()
+        if fired or self.per_key_draws_when_idle:
+            for _ in range(n_keys):                # per key: RandAffine.__call__(randomize=True), under `if do_resampling`
+                self.R_inner.rand()
+                self._grid_params()
         return fired, used
 
 
@@ -105,8 +121,9 @@ class RandAffineSampler:
             names = ("rotate", "shear", "translate", "scale")
             return fired, {k: np.asarray([p[k] for p in plist], np.float64).reshape(len(plist), -1) for k in names}
         fired = self.R.random_sample(batch) < self.prob
-        self.R_inner.random_sample(batch * (1 + n_keys))
-        calls = 1 + fired.astype(np.int64) + n_keys          # randomize() calls on the grid stream per sample
+        per_key = np.full(batch, n_keys, np.int64) if self.per_key_draws_when_idle else n_keys * fired.astype(np.int64)
+        self.R_inner.random_sample(batch + int(per_key.sum()))
+        calls = 1 + fired.astype(np.int64) + per_key         # randomize() calls on the grid stream per sample
         start = np.concatenate([[0], np.cumsum(calls)[:-1]])
         u = self.R_grid.random_sample(int(calls.sum()) * K).reshape(-1, K) if K else np.zeros((int(calls.sum()), 0))
         used = u[start[fired] + 1]                             # the second randomize of a firing call is the used one

@@ -312,22 +312,6 @@ class Lambdad(MapTransform):
         return d
 
 
-class CopyEntryd(MapTransform):
-    """/root/reference/adell_mri/utils/monai_transforms/generic_data_ops.py:7-26 — the reference
-    deep-copies the voxels; here the *recorded chain* is cloned (both views share the source)."""
-
-    def __init__(self, keys, new_keys):
-        super().__init__(keys)
-        self.new_keys = list(new_keys)
-
-    def __call__(self, data):
-        d = dict(data)
-        for k, nk in zip(self.keys, self.new_keys):
-            d[k] = as_pending(d[k])
-            d[nk] = d[k].clone()
-        return d
-
-
 class ConcatItemsd(MapTransform):
     """Channel concatenation: the recorded chains are concatenated, voxels are written once."""
 

@@ -193,10 +193,14 @@ class RandAffinedDraws:
     to RandAffined, its RandAffine and its RandAffineGrid).  Per call:
       outer.rand() < prob; inner.rand() (prob 1.0); grid params (discarded);
       if fired: grid params again (USED — RandAffineGrid.__call__ re-randomises);
-      then per key: inner.rand() + grid params (discarded).
+      then per key, ONLY when resampling (`if do_resampling:` in RandAffined.__call__, MONAI >= 1.0; with
+      spatial_size=None that is `fired`): inner.rand() + grid params (discarded).
+    ``idle_per_key_draws=True`` restores the round-1 reading (per-key draws on idle calls as well).
     """
 
-    def __init__(self, prob, rotate_range=None, shear_range=None, translate_range=None, scale_range=None, n_keys=1):
+    def __init__(self, prob, rotate_range=None, shear_range=None, translate_range=None, scale_range=None, n_keys=1,
+                 idle_per_key_draws=False):
+        self.idle_per_key_draws = idle_per_key_draws
         self.prob = prob
         self.ranges = dict(
             rotate_range=rotate_range, shear_range=shear_range, translate_range=translate_range, scale_range=scale_range
@@ -217,7 +221,7 @@ class RandAffinedDraws:
         used = None
         if do:
             used = rand_affine_grid_params(self.R_grid, **self.ranges)
-        for _ in range(self.n_keys):
+        for _ in range(self.n_keys if (do or self.idle_per_key_draws) else 0):
             self.R_inner.rand()
             rand_affine_grid_params(self.R_grid, **self.ranges)
         return do, used

@@ -17,15 +17,37 @@ def test_compose_seed_fanout_matches_oracle():
     assert child_seeds(42, 5) == M.compose_set_random_state(42, 5)
 
 
+@pytest.mark.parametrize("idle", [False, True])
 @pytest.mark.parametrize("prob", [0.2, 1.0])
-def test_rand_affine_sampler_follows_the_restated_stream(prob):
+def test_rand_affine_sampler_follows_the_restated_stream(prob, idle):
     kw = dict(rotate_range=[np.pi / 8, np.pi / 8, np.pi / 16], scale_range=[0.1, 0.1, 0.05])
-    a = RandAffineSampler(prob=prob, **kw).set_random_state(7)
-    b = M.RandAffinedDraws(prob, n_keys=4, **kw).set_random_state(7)
+    a = RandAffineSampler(prob=prob, per_key_draws_when_idle=idle, **kw).set_random_state(7)
+    b = M.RandAffinedDraws(prob, n_keys=4, idle_per_key_draws=idle, **kw).set_random_state(7)
     for _ in range(20):
         fa, pa = a.draw(n_keys=4)
         fb, pb = b.draw()
         assert fa == fb and pa == pb
+
+
+def test_idle_calls_consume_no_per_key_draws_by_default():
+    """† MONAI >= 1.0: `self.rand_affine(d[key], ..., randomize=True, grid)` sits under `if do_resampling:`; an idle
+    call advances the gate streams by one draw each and the grid stream by ONE randomize."""
+    kw = dict(rotate_range=[0.3, 0.3, 0.1])
+    s = RandAffineSampler(prob=0.0, **kw).set_random_state(5)
+    for _ in range(6):
+        assert s.draw(n_keys=4) == (False, None)
+    r = np.random.RandomState(5)
+    r.random_sample(6)
+    assert s.R.rand() == r.rand() and s.R_inner.rand() == np.random.RandomState(5).random_sample(7)[-1]
+    g = np.random.RandomState(5)
+    g.random_sample(6 * 3)
+    assert s.R_grid.rand() == g.rand()
+    old = RandAffineSampler(prob=0.0, per_key_draws_when_idle=True, **kw).set_random_state(5)
+    for _ in range(6):
+        old.draw(n_keys=4)
+    g = np.random.RandomState(5)
+    g.random_sample(6 * 3 * 5)
+    assert old.R_grid.rand() == g.rand()
 
 
 def test_vectorised_draws_equal_sequential_draws():
@@ -33,6 +55,7 @@ def test_vectorised_draws_equal_sequential_draws():
         kw = dict(prob=[0.2, 0.5, 1.0][trial % 3], rotate_range=[0.3, 0.3, 0.1],
                   shear_range=((0.9, 1.1),) * 3 if trial % 2 else None,
                   translate_range=[4, 4, 1] if trial % 4 == 0 else None)
+        kw["per_key_draws_when_idle"] = bool(trial % 2) if trial < 6 else None
         a = RandAffineSampler(**kw).set_random_state(trial)
         b = RandAffineSampler(**kw).set_random_state(trial)
         for _ in range(3):
@@ -156,3 +179,27 @@ def test_pooled_percentile_near_tie_matches_numpy():
         got = stats.percentiles(vols, qs, dataset_wide=True, kernels=NumpyKernels(vols)).numpy()[0]
         ref = np.percentile(np.concatenate([v.numpy() for v in vols]), np.asarray(qs, np.float64)).astype(np.float32)
         assert np.array_equal(got, ref), (sizes, qs, got, ref)
+
+
+def test_clip_then_intensity_then_affine_keeps_the_clip_before_the_map():
+    """the kernel applies pre -> clip -> post per tap; folding a pending post map into pre would compute
+    clip(2v + 0.5) instead of 2 clip(v) + 0.5.  The clipped pass is closed first."""
+    R = np.random.RandomState(9)
+    img = torch.from_numpy((R.rand(1, 12, 10, 8) * 2 - 0.5).astype(np.float32))
+    A = rand_affine_matrix(R)
+    plan = BatchPlan([img[0]], strict=True).clip(0.0, 1.0).intensity(2.0, 0.5).affine(A.numpy(), "bilinear", "border")
+    assert len(plan.passes) == 1
+    clipped = torch.clamp(img, 0.0, 1.0) * torch.tensor(2.0) + torch.tensor(0.5)
+    ref = M.affine_resample(clipped, A, "bilinear", "border")[0]
+    assert mismatch(run_plan_cref(plan)[0], ref) == 0
+
+
+def test_fast_mode_does_not_compose_across_a_crop_that_starts_at_zero():
+    """a crop at start 0 only shrinks the grid; the second affine acts about the centre of the CROPPED
+    volume, so the pass is closed exactly as for any other crop start."""
+    R = np.random.RandomState(10)
+    img = torch.from_numpy(R.rand(16, 16, 16).astype(np.float32))
+    A1, A2 = rand_affine_matrix(R).numpy(), rand_affine_matrix(R).numpy()
+    for start in (0, 1):
+        plan = BatchPlan([img], fast=True).affine(A1, "bilinear", "zeros").crop([start] * 3, [8, 8, 8]).affine(A2, "bilinear", "zeros")
+        assert len(plan.passes) == 1, start
