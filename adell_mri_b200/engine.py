@@ -24,6 +24,39 @@ ISZ = _lib.ITEM_SIZE
 launch_count = 0
 
 
+class LaunchTimer:
+    """Measurement aid: while installed (``engine.timer = LaunchTimer()``), every ``every``-th K1 launch is
+    bracketed by a CUDA event pair recorded on the launching stream.  ``ms()`` (after a synchronize) returns
+    the durations, tagged with the step label current at launch time (``timer.label = ...``), so that the
+    passes of a multi-launch step can be summed."""
+
+    def __init__(self, every: int = 1):
+        self.every, self.n, self.pairs, self.label = max(int(every), 1), 0, [], None
+
+    def begin(self, device):
+        self.n += 1
+        if (self.n - 1) % self.every:
+            return None
+        st = torch.cuda.current_stream(device)
+        a = torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        return a, st
+
+    def end(self, tok):
+        if tok is None:
+            return
+        b = torch.cuda.Event(enable_timing=True)
+        b.record(tok[1])
+        self.pairs.append((self.label, tok[0], b))
+
+    def ms(self):
+        return [(lab, a.elapsed_time(b)) for lab, a, b in self.pairs]
+
+
+#: installed LaunchTimer or None
+timer: LaunchTimer | None = None
+
+
 class _PinnedRing:
     """Rotating pinned staging buffers for the parameter uploads.  torch's caching host allocator
     cannot hand a pinned block back while the copy that used it is still queued behind kernels,
@@ -99,7 +132,10 @@ def launch_packed(buf_dev: torch.Tensor, n: int, info, stream: int | None = None
     if stream is None:
         stream = torch.cuda.current_stream(buf_dev.device).cuda_stream
     base = buf_dev.data_ptr()
+    tok = timer.begin(buf_dev.device) if timer is not None else None
     _lib.check(lib.adell_aug_gather(base, base + n * ISZ, n, C.byref(info), C.c_void_p(stream)), "adell_aug_gather")
+    if timer is not None:
+        timer.end(tok)
     launch_count += lib.adell_aug_gather_launches()
 
 
@@ -156,7 +192,10 @@ class PreparedSteps:
         global launch_count
         a = self._args[k]
         stream = torch.cuda.current_stream(self._device).cuda_stream
+        tok = timer.begin(self._device) if timer is not None else None
         st = self._lib.adell_aug_gather(a[0], a[1], a[2], a[3], C.c_void_p(stream))
+        if timer is not None:
+            timer.end(tok)
         if st != 0:
             _lib.check(st, "adell_aug_gather")
         launch_count += self._per_launch

@@ -158,7 +158,10 @@ class SegmentationBatchAugmenter:
             self._meta[id(s)] = m
         return m
 
-    def plan(self, samples: Sequence[dict], params=None) -> BatchPlan:
+    def plan(self, samples: Sequence[dict], params=None, pre_dev: torch.Tensor | None = None) -> BatchPlan:
+        """``pre_dev``: optional ``[B * len(keys), 2]`` fp32 device tensor of per-volume ``{scale, offset}`` (sample-major,
+        key order = ``self.keys``) computed by the statistics kernels — the intensity normalisation of raw cached
+        volumes (transforms.py:143-155 of the reference) folded into the gather instead of a pass of its own."""
         B, nk = len(samples), len(self.keys)
         metas = [self._sample_meta(s) for s in samples]
         shape = tuple(int(x) for x in metas[0][4][0])
@@ -168,6 +171,8 @@ class SegmentationBatchAugmenter:
             np.concatenate([m[1] for m in metas]), np.concatenate([m[2] for m in metas]),
             np.concatenate([m[3] for m in metas]), np.concatenate([m[4] for m in metas]),
             metas[0][5][0].device, [m[5] for m in metas], fast=self.fast, strict=self.strict)
+        if pre_dev is not None:
+            plan.intensity_from_device(pre_dev)
         rep = lambda x: np.repeat(x, nk, axis=0)
         modes = self.modes * B
         if self.random_crop_size is not None:
@@ -215,8 +220,8 @@ class SegmentationBatchAugmenter:
             dst_ptr, dst_stride = p_img.reshape(-1), s_img.reshape(-1, 3)
         return dst_ptr.astype(np.uint64), dst_stride
 
-    def __call__(self, samples: Sequence[dict], params=None, out: dict | None = None) -> dict:
-        plan = self.plan(samples, params)
+    def __call__(self, samples: Sequence[dict], params=None, out: dict | None = None, pre_dev: torch.Tensor | None = None) -> dict:
+        plan = self.plan(samples, params, pre_dev)
         B = len(samples)
         if out is None:
             out = self._alloc_out(B, tuple(int(x) for x in plan.shape[0]), plan.device)
@@ -344,11 +349,14 @@ class ClassificationBatchAugmenter(_BatchBase):
                 mats[si, f] = geometry.compose_affine(p["rotate"], p["shear"], p["translate"], p["scale"], batch=int(f.sum()))
         return dict(flips=flips, fired=fired, mats=mats)
 
-    def plan(self, samples: Sequence[dict], params=None) -> BatchPlan:
+    def plan(self, samples: Sequence[dict], params=None, pre_dev: torch.Tensor | None = None) -> BatchPlan:
+        """``pre_dev``: optional per-volume ``{scale, offset}`` on the device (see SegmentationBatchAugmenter.plan)."""
         B = len(samples)
         if params is None:
             params = self.draw(B)
         plan, metas = self._base_plan(samples, self.keys)
+        if pre_dev is not None:
+            plan.intensity_from_device(pre_dev)
         per = plan.n // B                      # volumes per sample (keys x channels)
         modes = []
         for k, m in zip(self.keys, self.modes):
@@ -361,8 +369,8 @@ class ClassificationBatchAugmenter(_BatchBase):
             plan.center_crop(self.crop_size)
         return plan
 
-    def __call__(self, samples: Sequence[dict], params=None, out: dict | None = None) -> dict:
-        plan = self.plan(samples, params)
+    def __call__(self, samples: Sequence[dict], params=None, out: dict | None = None, pre_dev: torch.Tensor | None = None) -> dict:
+        plan = self.plan(samples, params, pre_dev)
         B = len(samples)
         per = plan.n // B
         if out is None:

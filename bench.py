@@ -181,16 +181,20 @@ class CpuReference:
         self.calls = 0
 
     def run(self, samples_per_worker: int):
+        """One bounded sample of the workload on every host core.  Throughput = voxel-channels of ALL workers /
+        WALL time of the whole map (round 1 divided by the slowest worker's busy time of one-sample steps, which
+        timed every step at the worst-case draw and under-reported the CPU path about 2x)."""
         self.calls += 1
+        t0 = time.perf_counter()
         res = self.pool.map(_cpu_worker, [(self.workload, samples_per_worker, SEED + 17 * i + 1009 * self.calls)
                                           for i in range(self.cores)], chunksize=1)
+        wall = time.perf_counter() - t0
         vox = sum(r[0] for r in res)
-        busy = max(r[1] for r in res)  # workers run concurrently: throughput over the slowest worker's time
-        self.last = (vox, busy)
-        return dict(value=vox / busy, unit=UNIT, cores=self.cores, kind="port",
+        self.last = (vox, wall)
+        return dict(value=vox / wall, unit=UNIT, cores=self.cores, kind="port",
                     sample=f"{self.cores} single-threaded worker processes x {samples_per_worker} samples of the "
                            f"'{self.workload}' chain (oracle port: torch CPU grid_sample + flip + concat); "
-                           f"{vox} voxel-channels in {busy:.2f}s")
+                           f"{vox} voxel-channels in {wall:.2f}s wall (slowest worker busy {max(r[1] for r in res):.2f}s)")
 
     def close(self):
         self.pool.close()
@@ -201,17 +205,21 @@ class CpuReference:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=None, help="default: 1000 (b200 arm), 40 (reference arm: ~0.3 s of host work per step)")
+    ap.add_argument("--steps", type=int, default=None, help="default: 1000 (b200 arm), 20 (reference arm: ~2 s of host work per step)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="seg", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-samples", type=int, default=6, help="samples per CPU worker for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cache-samples", type=int, default=32)
+    ap.add_argument("--workloads", default="all", help="side workloads for the `workloads` block: 'all', 'none' or a comma list of "
+                    "a,seg_all_affine,seg_norm,ssl,cls,large (see bench_workloads.py)")
+    ap.add_argument("--workload-steps", type=int, default=0, help="timed steps per side workload (0: its own default)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-run oracle checks of the side workloads")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.steps is None:
-        args.steps = 40 if args.impl == "reference" else 1000
+        args.steps = 20 if args.impl == "reference" else 1000
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -236,19 +244,21 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        # each step = a bounded sample of the workload on all host cores
+        # each step = a bounded sample of the workload on all host cores: `--cpu-samples` samples per worker, so
+        # that a step averages over the expensive (affine fired) and cheap draws instead of waiting for the one
+        # worker that drew the expensive branch
         ref = CpuReference(args.workload)
         per_step, raw = [], []
         for _ in range(args.warmup + args.steps):
-            per_step.append(ref.run(1))
+            per_step.append(ref.run(args.cpu_samples))
             raw.append(ref.last)
         ref.close()
-        # whole-run throughput = total voxel-channels / total busy time of the timed steps
+        # whole-run throughput = total voxel-channels / total wall time of the timed steps
         tot_v = sum(r[0] for r in raw[args.warmup:])
         tot_t = sum(r[1] for r in raw[args.warmup:])
         v = tot_v / tot_t
         cb = dict(per_step[-1]); cb["value"] = v
-        cb["sample"] = f"{args.steps} steps, each: " + cb["sample"].split(";")[0]
+        cb["sample"] = f"{args.steps} steps, each: " + cb["sample"].split(";")[0] + f"; {tot_v} voxel-channels in {tot_t:.1f}s wall"
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * vox_per_step / v, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "cpu_baseline": cb,
@@ -285,15 +295,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    EVERY = 8   # in-loop launch timing: every 8th step carries a CUDA event pair
+    EVERY = 2   # in-loop launch timing: every 2nd step carries a CUDA event pair (10 samples at --steps 20)
     CHUNK = int(os.environ.get('BENCH_CHUNK', '16'))  # steps composed / uploaded together (host composition amortised; see engine.prepare_steps)
 
     def batch_of(i):
         b0 = (i % n_batches) * batch
         return cache[b0:b0 + batch]
 
+    host = {"s": 0.0, "steps": 0}
+
     def prep(first, n):
-        return aug.prepare_steps([batch_of(first + k) for k in range(n)], [out] * n), n
+        t0 = time.perf_counter()
+        r = aug.prepare_steps([batch_of(first + k) for k in range(n)], [out] * n), n
+        host["s"] += time.perf_counter() - t0
+        host["steps"] += n
+        return r
 
     def run_steps(first, count, ahead, next_n, events=None):
         """`count` steps starting at global step index `first`, software-pipelined the way a training loop
@@ -325,8 +341,10 @@ def main():
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * n_timed)]
     launches0 = engine.launch_count
     e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    host["s"], host["steps"] = 0.0, 0
     e_start.record(stream)
     run_steps(args.warmup, args.steps, ahead, first_n, None if os.environ.get('BENCH_NO_EVENTS') else ev)
+    host_us_per_step = 1e6 * host["s"] / max(host["steps"], 1)
     e_stop.record(stream)
     barrier()
     clock_info = clocks.stop()
@@ -370,13 +388,17 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per K1 launch, from the committed ncu capture
+    # dram__bytes_read.sum + dram__bytes_write.sum per K1 launch cannot be measured in-run (it needs ncu's replay):
+    # the figure comes from the committed `ncu --set full` capture of this workload and is labelled as such
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(args.workload)
+        traffic_src = "from_profile: profiles/k1_traffic.json (ncu --set full capture of this workload, not measured in this run)"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "k1_gather", "kernel_ms": kernel_ms, "kernel_ms_isolated_repeat": kernel_ms_alone,
-                "launches_sampled_in_timed_region": len(k1_ms), "algorithmic_bytes": alg_bytes, "peak_source": peak_src}
+                "launches_sampled_in_timed_region": len(k1_ms), "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
+                "traffic_source": traffic_src}
 
     # ---- end to end with host buffers ("e2e") ----
     # Host-resident cache (what the reference's CacheDataset holds in RAM): one pinned block per
@@ -427,6 +449,26 @@ def main():
     barrier()
     e2e_ms = a.elapsed_time(b) / e2e_steps
 
+    # ---- the other BASELINE configs, same run, same device (bench_workloads.py) ----
+    workloads = {}
+    if args.workloads != "none":
+        import bench_workloads as BW
+
+        want = None if args.workloads == "all" else set(args.workloads.split(","))
+        torch.cuda.empty_cache()
+
+        def reduce_max(x):
+            tt = torch.tensor([x], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt[0])
+
+        for cls in BW.ALL:
+            if want is not None and cls.name not in want:
+                continue
+            workloads[cls.name] = BW.run(cls, dev, rank, world, SEED, args.workload_steps, args.warmup, peak, barrier, reduce_max,
+                                         do_parity=not args.no_parity)
+
     ms_per_step = total_ms / args.steps
     t = torch.tensor([ms_per_step, e2e_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -443,6 +485,8 @@ def main():
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
             "gpu_launches": launches, "clocks": clock_info,
             "k1_launch_ms_median_in_loop": statistics.median(k1_ms), "host_chunk_steps": CHUNK,
+            "host_us_per_step": host_us_per_step,
+            "workloads": workloads,
         }
         if world == 1 and not args.no_cpu_baseline:
             ref = CpuReference(args.workload)

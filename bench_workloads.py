@@ -1,0 +1,554 @@
+"""Side workloads of bench.py: every BASELINE.json config next to the headline one.
+
+bench.py's contract keys stay on BASELINE configs[1] (segmentation, config B).  The `workloads`
+block of the same JSON line carries, measured in the same run on the same device:
+
+  a               config A   benchmarks/benchmark-random-affine.py:90-103 batched: 512 x 1x128x128x32,
+                             RandAffined prob 1, rotate pi/6 x3, translate [10,10,3], scale 0.1, reflection
+  seg_all_affine  config B   with the affine forced to fire for every sample (worst case of K1)
+  seg_norm        config B   from RAW int16 / uint8 cached volumes: adell_minmax -> scaler coefficients ->
+                             {scale, offset} read from device memory by K1 (the "+norm" of the metric inside the step)
+  ssl             config C   get_augmentations_ssl two-view chain (augmentations.py:391-516), 128x128x32, batch 64 / GPU
+  cls             config D   percentile normalisation (K2/K3) + get_augmentations_class (augmentations.py:181-320):
+                             flip -> affine(zeros) -> centre crop to 192x192x48, batch 32
+  large           config E   512x512x128 volumes, dataset-wide percentile (NCCL all-reduce of the bin counts when
+                             WORLD_SIZE > 1), scaling folded into the affine gather
+
+Every entry: `value` (whole-job voxels/s, host draws + composition + uploads inside the timed
+region, device-resident cache), `ms_per_step`, `kernel_ms` (CUDA events around the K1 launches of
+the timed steps, summed per step), `roofline` (8 B per output voxel-channel / kernel_ms vs the
+measured HBM peak), and `parity`: an IN-RUN check of the device result against the CPU oracle
+(`oracle/`, the checker — never the thing measured) on a bounded part of one batch.  A failed
+check raises: a bench line is never printed for wrong voxels.
+"""
+
+from __future__ import annotations
+
+import time
+
+import numpy as np
+import torch
+
+from adell_mri_b200 import _lib, engine, geometry, stats
+from adell_mri_b200.pipelines import ClassificationBatchAugmenter, SegmentationBatchAugmenter, SSLBatchAugmenter
+from adell_mri_b200.plan import BatchPlan
+from adell_mri_b200.sampling import RandAffineSampler
+
+TOL = 1e-4   # north_star: <= 1e-4 relative on resampled intensities; masks / integer work bit-exact
+
+
+def _close(got: torch.Tensor, want: torch.Tensor, what: str):
+    scale = float(want.abs().max()) or 1.0
+    err = float((got - want).abs().max())
+    if not torch.allclose(got, want, rtol=TOL, atol=TOL * scale):
+        raise AssertionError(f"parity: {what}: max |diff| {err:.3e} exceeds {TOL:g} of the range {scale:.3e}")
+    return err / scale
+
+
+def _equal(got: torch.Tensor, want: torch.Tensor, what: str):
+    bad = int((got != want).sum())
+    if bad:
+        raise AssertionError(f"parity: {what}: {bad} voxels differ (bit-exact expected)")
+
+
+class Workload:
+    name = ""
+    desc = ""
+    bytes_per_voxel = 8.0   # algorithmic: fp32 source read + fp32 write per output voxel-channel
+    default_steps = 10
+
+    def __init__(self, dev, rank: int, world: int, seed: int):
+        self.dev, self.rank, self.world, self.seed = dev, rank, world, seed
+
+    # voxel-channels written per step on this rank
+    vox_per_step = 0
+
+    def step(self, i: int) -> None:
+        raise NotImplementedError
+
+    def parity(self) -> dict:
+        raise NotImplementedError
+
+    def extra(self) -> dict:
+        return {}
+
+
+# ----------------------------------------------------------------------------- config A
+class AffineA(Workload):
+    name = "a"
+    desc = ("config A (benchmarks/benchmark-random-affine.py batched): 512 x 1x128x128x32, RandAffined prob 1.0, "
+            "rotate pi/6 x3, translate [10,10,3], scale 0.1, trilinear, reflection; 512 distinct sources (1 GB > L2)")
+    N, shape = 512, (128, 128, 32)
+
+    def __init__(self, dev, rank, world, seed):
+        super().__init__(dev, rank, world, seed)
+        g = torch.Generator(device=dev).manual_seed(seed)
+        self.src = torch.rand((self.N, 1, *self.shape), device=dev, generator=g)
+        self.out = torch.empty_like(self.src)
+        self.sampler = RandAffineSampler(prob=1.0, rotate_range=[np.pi / 6] * 3, shear_range=[0, 0, 0],
+                                         translate_range=[10, 10, 3], scale_range=[0.1, 0.1, 0.1]).set_random_state(seed)
+        self.vox_per_step = self.N * int(np.prod(self.shape))
+        esz = 4
+        self._ptr = (self.src.data_ptr() + esz * self.src.stride(0) * np.arange(self.N, dtype=np.int64)).astype(np.uint64)
+        self._stride = np.tile(np.asarray(self.src.stride()[2:], np.int64), (self.N, 1))
+        self._dtype = np.full(self.N, _lib.F32, np.uint8)
+        self._shape = np.tile(np.asarray(self.shape, np.int64), (self.N, 1))
+        self._dptr = (self.out.data_ptr() + esz * self.out.stride(0) * np.arange(self.N, dtype=np.int64)).astype(np.uint64)
+        self.last_mats = None
+
+    def step(self, i):
+        fired, p = self.sampler.draw_batch(self.N, n_keys=1)
+        mats = geometry.compose_affine(p["rotate"], p["shear"], p["translate"], p["scale"], batch=self.N)
+        self.last_mats = mats
+        plan = BatchPlan.from_arrays(self._ptr, self._stride, self._dtype, self._shape, self.dev, [self.src])
+        plan.affine(mats, "bilinear", "reflection")
+        engine.execute_ptrs(plan, self._dptr, self._stride, keep=[self.out])
+
+    def parity(self):
+        from oracle import monai_restated as M
+
+        self.step(0)
+        torch.cuda.synchronize()
+        worst = 0.0
+        for b in (0, 1, self.N - 1):
+            want = M.affine_resample(self.src[b].cpu(), torch.from_numpy(self.last_mats[b]), "bilinear", "reflection")
+            worst = max(worst, _close(self.out[b].cpu(), want, f"config A item {b}"))
+        return {"checked": "3 of 512 volumes vs oracle (torch CPU grid_sample chain)", "max_rel_err": worst, "tol": TOL, "ok": True}
+
+
+# ----------------------------------------------------------------------------- config B variants
+class _SegBase(Workload):
+    shape, image_keys, batch, cache_samples = (256, 256, 32), ["t2", "adc", "dwi"], 8, 32
+
+    def _augmenter(self, prob=None):
+        aug = SegmentationBatchAugmenter(["affine", "flip"], self.image_keys + ["mask"], self.image_keys, flip_axis=[0, 1, 2])
+        if prob is not None:
+            for s in aug.samplers:
+                s.prob = prob
+        return aug.set_random_state(self.seed)
+
+    def _alloc_out(self):
+        self.out = {"image": torch.empty((self.batch, len(self.image_keys), *self.shape), device=self.dev),
+                    "mask": torch.empty((self.batch, 1, *self.shape), device=self.dev)}
+        self.vox_per_step = self.batch * (len(self.image_keys) + 1) * int(np.prod(self.shape))
+
+    def _batch(self, i):
+        nb = self.cache_samples // self.batch
+        b0 = (i % nb) * self.batch
+        return self.cache[b0:b0 + self.batch]
+
+    def _oracle_sample(self, sample_cpu: dict, params, b: int, scaled=None):
+        """The reference's op sequence for sample ``b`` of a batch drawn with ``params`` (oracle, CPU)."""
+        from oracle import monai_restated as M
+
+        outs = {}
+        flips = [a for a in range(3) if params["flips"][b, a]]
+        for k in self.image_keys + ["mask"]:
+            x = sample_cpu[k] if scaled is None else scaled[k]
+            for si in range(params["fired"].shape[0]):
+                if params["fired"][si, b]:
+                    A = torch.from_numpy(np.ascontiguousarray(params["mats"][si, b]))
+                    x = M.affine_resample(x, A, "nearest" if k == "mask" else "bilinear", "reflection")
+            # three RandFlipd, one per axis, in axis order (augmentations.py:127-131)
+            for a in flips:
+                x = M.flip(x, [a])
+            outs[k] = x
+        return outs
+
+
+class SegAllAffine(_SegBase):
+    name = "seg_all_affine"
+    desc = ("config B with the affine forced to fire for every sample (K1 worst case: every tile resampled): "
+            "T2/ADC/DWI trilinear + mask nearest, 256x256x32, batch 8, reflection, 3 flips p=0.25")
+
+    def __init__(self, dev, rank, world, seed):
+        super().__init__(dev, rank, world, seed)
+        g = torch.Generator(device=dev).manual_seed(seed)
+        self.cache = []
+        for _ in range(self.cache_samples):
+            s = {k: torch.rand((1, *self.shape), device=dev, generator=g) for k in self.image_keys}
+            s["mask"] = (torch.rand((1, *self.shape), device=dev, generator=g) > 0.7).float()
+            self.cache.append(s)
+        self.aug = self._augmenter(1.0)
+        self._alloc_out()
+
+    def step(self, i):
+        self.aug(self._batch(i), out=self.out)
+
+    def parity(self):
+        batch = self._batch(0)
+        params = self.aug.draw(self.batch, self.shape)
+        self.aug(batch, params=params, out=self.out)
+        torch.cuda.synchronize()
+        want = self._oracle_sample({k: v.cpu() for k, v in batch[0].items()}, params, 0)
+        worst = 0.0
+        for c, k in enumerate(self.image_keys):
+            worst = max(worst, _close(self.out["image"][0, c].cpu(), want[k][0], f"seg_all_affine key {k}"))
+        _equal(self.out["mask"][0, 0].cpu(), want["mask"][0], "seg_all_affine mask (nearest)")
+        return {"checked": "sample 0 of one batch (3 trilinear keys <= tol, mask bit-exact) vs oracle", "max_rel_err": worst,
+                "tol": TOL, "ok": True}
+
+
+class SegNorm(_SegBase):
+    name = "seg_norm"
+    desc = ("config B from RAW cached volumes (int16 images, uint8 mask): per step adell_minmax over the batch's 32 "
+            "volumes -> ScaleIntensityd(0,1) coefficients on the device -> {scale, offset} read by K1 (pre_dev), "
+            "affine p=0.2 reflection + 3 flips p=0.25; 6 B (images) / 5 B (mask) algorithmic per output voxel")
+
+    def __init__(self, dev, rank, world, seed):
+        super().__init__(dev, rank, world, seed)
+        g = torch.Generator(device=dev).manual_seed(seed)
+        self.cache = []
+        for _ in range(self.cache_samples):
+            s = {k: torch.randint(0, 4000, (1, *self.shape), device=dev, generator=g, dtype=torch.int16) for k in self.image_keys}
+            s["mask"] = (torch.rand((1, *self.shape), device=dev, generator=g) > 0.7).to(torch.uint8)
+            self.cache.append(s)
+        self.aug = self._augmenter()
+        self._alloc_out()
+        nk = len(self.image_keys) + 1
+        self.bytes_per_voxel = (len(self.image_keys) * 6.0 + 5.0) / nk
+        self._desc = {}
+
+    def _pre_dev(self, i, batch):
+        keys = self.image_keys + ["mask"]
+        vols = [s[k].reshape(-1) for s in batch for k in keys]
+        nb = self.cache_samples // self.batch
+        d = self._desc.get(i % nb)
+        if d is None:
+            d = self._desc[i % nb] = stats.vol_descriptors(vols)
+        mm = stats.minmax(vols, desc=d)
+        return stats.coefs_to_affine(stats.scaler_coefs(mm, _lib.SCALER_MINMAX, 0.0, 1.0))
+
+    def step(self, i):
+        batch = self._batch(i)
+        self.aug(batch, out=self.out, pre_dev=self._pre_dev(i, batch))
+
+    def parity(self):
+        from oracle import monai_restated as M
+
+        batch = self._batch(0)
+        params = self.aug.draw(self.batch, self.shape)
+        self.aug(batch, params=params, out=self.out, pre_dev=self._pre_dev(0, batch))
+        torch.cuda.synchronize()
+        raw = {k: v.cpu() for k, v in batch[0].items()}
+        scaled = {k: M.scale_intensity(raw[k].float(), 0.0, 1.0) for k in self.image_keys}
+        scaled["mask"] = raw["mask"].float()
+        want = self._oracle_sample(raw, params, 0, scaled)
+        worst = 0.0
+        for c, k in enumerate(self.image_keys):
+            worst = max(worst, _close(self.out["image"][0, c].cpu(), want[k][0], f"seg_norm key {k}"))
+        _equal(self.out["mask"][0, 0].cpu(), want["mask"][0], "seg_norm mask (nearest, uint8 source)")
+        return {"checked": "sample 0 (min-max scaled int16 keys <= tol, uint8 mask bit-exact) vs oracle", "max_rel_err": worst,
+                "tol": TOL, "ok": True}
+
+
+# ----------------------------------------------------------------------------- config C
+class SSLTwoView(Workload):
+    name = "ssl"
+    desc = ("config C: get_augmentations_ssl two views (shared RandSpatialCropd 128x128x32 out of 160x160x40, then per view "
+            "3 of the 15 fused workhorse members in drawn order, one K1 pass per spatial member like the reference's "
+            "sequential resamples), batch 64 per GPU; noise sigma drawn on the host, noise values from the device Philox "
+            "generator; member subsets drawn vectorised")
+    batch, src, roi, cache_samples = 64, (160, 160, 40), (128, 128, 32), 128
+
+    def __init__(self, dev, rank, world, seed):
+        super().__init__(dev, rank, world, seed)
+        g = torch.Generator(device=dev).manual_seed(seed)
+        self.cache = [{"image": torch.rand((1, *self.src), device=dev, generator=g)} for _ in range(self.cache_samples)]
+        self.aug = SSLBatchAugmenter(["image"], self.roi, n_transforms=3, choice="vectorised", noise="philox").set_random_state(seed)
+        self.out = {k: torch.empty((self.batch, 1, *self.roi), device=dev) for k in ("augmented_image_1", "augmented_image_2")}
+        self.vox_per_step = self.batch * 2 * int(np.prod(self.roi))
+
+    def step(self, i):
+        nb = self.cache_samples // self.batch
+        b0 = (i % nb) * self.batch
+        self.aug(self.cache[b0:b0 + self.batch], out=self.out)
+
+    def parity(self):
+        """Stream level: 3 samples through a second augmenter (host-drawn noise injected, member subsets from the
+        global numpy stream like the reference) against the eager oracle pipeline on the same seeds."""
+        from oracle import pipelines_ref as P
+        from adell_mri_b200.pipelines import SSL_FUSED_MEMBERS
+
+        n = 3
+        samples = self.cache[:n]
+        aug = SSLBatchAugmenter(["image"], self.roi, n_transforms=3, choice="global", noise="injected").set_random_state(self.seed + 5)
+        np.random.seed(self.seed + 6)
+        got = aug(samples)
+        torch.cuda.synchronize()
+        ref = P.Chain(P.ssl(["image"], ["image_copy"], self.roi, False, False, list(SSL_FUSED_MEMBERS), 3)).seed(self.seed + 5)
+        np.random.seed(self.seed + 6)
+        worst = 0.0
+        for b, s in enumerate(samples):
+            x = s["image"].cpu()
+            r = ref({"image": x, "image_copy": x.clone()})
+            for key, rk in (("augmented_image_1", "image"), ("augmented_image_2", "image_copy")):
+                worst = max(worst, _close(got[key][b].cpu(), r[rk], f"ssl sample {b} {key}"))
+        return {"checked": f"{n} samples x 2 views, same seeds, vs the eager oracle pipeline (pipelines_ref.ssl)",
+                "max_rel_err": worst, "tol": TOL, "ok": True}
+
+
+# ----------------------------------------------------------------------------- config D
+class ClsPercentile(Workload):
+    name = "cls"
+    desc = ("config D: raw cached 208x208x64 volumes (crop + 16 margin), 3 image keys + mask, batch 32; per step exact "
+            "percentiles (0.5, 99.5) of the 96 image volumes (K2/K3 radix select) -> ScaleIntensityRangePercentilesd "
+            "coefficients -> {scale, offset} read by K1; OneOf flips -> RandAffined(translate, rotate x, scale; zeros, "
+            "prob 0.1) -> CenterSpatialCropd 192x192x48 -> concat")
+    batch, src, crop, image_keys, cache_samples = 32, (208, 208, 64), (192, 192, 48), ["t2", "adc", "dwi"], 64
+    prob = 0.1
+
+    def __init__(self, dev, rank, world, seed):
+        super().__init__(dev, rank, world, seed)
+        g = torch.Generator(device=dev).manual_seed(seed)
+        self.cache = []
+        for _ in range(self.cache_samples):
+            s = {k: torch.empty((1, *self.src), device=dev).log_normal_(5.0, 0.6, generator=g) for k in self.image_keys}
+            s["mask"] = (torch.rand((1, *self.src), device=dev, generator=g) > 0.7).float()
+            self.cache.append(s)
+        self.aug = ClassificationBatchAugmenter(["affine", "flip"], self.image_keys, "mask", flip_axis=[0, 1, 2], prob=self.prob,
+                                                crop_size=self.crop).set_random_state(seed)
+        self.out = {"image": torch.empty((self.batch, len(self.image_keys) + 1, *self.crop), device=dev)}
+        self.vox_per_step = self.batch * (len(self.image_keys) + 1) * int(np.prod(self.crop))
+        self.stats_ms = None
+
+    def _pre_dev(self, batch):
+        ni = len(self.image_keys)
+        vols = [s[k].reshape(-1) for s in batch for k in self.image_keys]
+        pct = stats.percentiles(vols, [0.5, 99.5])
+        aff = stats.coefs_to_affine(stats.scaler_coefs(pct, _lib.SCALER_RANGE, 0.0, 1.0))      # [B * ni, 2]
+        pre = torch.empty((len(batch), ni + 1, 2), device=self.dev)
+        pre[:, :ni] = aff.view(len(batch), ni, 2)
+        pre[:, ni, 0] = 1.0
+        pre[:, ni, 1] = 0.0
+        return pre.view(-1, 2)
+
+    def step(self, i):
+        nb = self.cache_samples // self.batch
+        b0 = (i % nb) * self.batch
+        batch = self.cache[b0:b0 + self.batch]
+        self.aug(batch, out=self.out, pre_dev=self._pre_dev(batch))
+
+    def extra(self):
+        batch = self.cache[:self.batch]
+        for _ in range(2):
+            self._pre_dev(batch)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            self._pre_dev(batch)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 3
+        n = self.batch * len(self.image_keys) * int(np.prod(self.src))
+        return {"stats_ms": ms, "stats_gbs_one_read_credited": 4.0 * n / ms / 1e6}
+
+    def parity(self):
+        from oracle import monai_restated as M
+
+        batch = self.cache[:self.batch]
+        params = self.aug.draw(self.batch)
+        # make sure the checked samples exercise the resample: force sample 0 to fire if nothing did
+        pre = self._pre_dev(batch)
+        self.aug(batch, params=params, out=self.out, pre_dev=pre)
+        torch.cuda.synchronize()
+        worst, checked = 0.0, []
+        fired_any = np.nonzero(params["fired"].any(axis=0))[0]
+        pick = sorted(set([0] + [int(b) for b in fired_any[:2]]))
+        for b in pick:
+            flips = [a for a in range(3) if params["flips"][b, a]]
+            for c, k in enumerate(self.image_keys + ["mask"]):
+                x = batch[b][k].cpu()
+                if k != "mask":
+                    x = M.scale_intensity_range_percentiles(x, 0.5, 99.5, 0.0, 1.0)
+                if flips:
+                    x = M.flip(x, flips)
+                for si in range(params["fired"].shape[0]):
+                    if params["fired"][si, b]:
+                        x = M.affine_resample(x, torch.from_numpy(np.ascontiguousarray(params["mats"][si, b])),
+                                              "nearest" if k == "mask" else "bilinear", "zeros")
+                x = M.center_spatial_crop(x, self.crop)
+                if k == "mask":
+                    _equal(self.out["image"][b, c].cpu(), x[0], f"cls sample {b} mask")
+                else:
+                    worst = max(worst, _close(self.out["image"][b, c].cpu(), x[0], f"cls sample {b} key {k}"))
+            checked.append(b)
+        return {"checked": f"samples {checked} (percentile-scaled keys <= tol, mask bit-exact) vs oracle; "
+                           f"resampled among them: {[int(b) for b in checked if params['fired'][:, b].any()]}",
+                "max_rel_err": worst, "tol": TOL, "ok": True}
+
+
+# ----------------------------------------------------------------------------- config E
+class LargeVolume(Workload):
+    name = "large"
+    desc = ("config E: 4 volumes of 512x512x128 fp32 per GPU; per step the DATASET-WIDE percentiles (1, 99) over all ranks' "
+            "volumes (three radix passes, int64 bin counts all-reduced over NCCL after each when WORLD_SIZE > 1), "
+            "ScaleIntensityRange coefficients on the device, scaling folded into the affine gather (rotate pi/8, pi/8, pi/16; zeros)")
+    M_vols, shape = 4, (512, 512, 128)
+    default_steps = 5
+
+    def __init__(self, dev, rank, world, seed):
+        super().__init__(dev, rank, world, seed)
+        g = torch.Generator(device=dev).manual_seed(seed)
+        self.vols = [torch.empty(self.shape, device=dev).log_normal_(0, 1, generator=g) for _ in range(self.M_vols)]
+        self.flat = [v.reshape(-1) for v in self.vols]
+        self.out = torch.empty((self.M_vols, 1, *self.shape), device=dev)
+        self.R = np.random.RandomState(seed)
+        self.vox_per_step = self.M_vols * int(np.prod(self.shape))
+        self.last = None
+        self.collective_bytes = 0
+
+    def _percentiles(self):
+        from adell_mri_b200 import dist as adist
+
+        return adist.dataset_percentiles(self.flat, [1.0, 99.0])
+
+    def step(self, i):
+        pct = self._percentiles()                                                     # [1, 2], identical on all ranks
+        pre1 = stats.coefs_to_affine(stats.scaler_coefs(pct, _lib.SCALER_RANGE, 0.0, 1.0))   # [1, 2]
+        pre = pre1.expand(self.M_vols, 2).contiguous()
+        rot = self.R.uniform(-1, 1, (self.M_vols, 3)) * np.array([np.pi / 8, np.pi / 8, np.pi / 16])
+        mats = geometry.compose_affine(rotate=rot, batch=self.M_vols)
+        plan = BatchPlan(self.vols)
+        plan.intensity_from_device(pre)
+        plan.affine(mats, "bilinear", "zeros")
+        engine.execute(plan, [self.out[b, 0] for b in range(self.M_vols)])
+        self.last = (pct, mats)
+
+    def extra(self):
+        for _ in range(2):
+            self._percentiles()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            self._percentiles()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 3
+        # per call: element count (8 B) + three passes of int64 bins: 2^11 + 4 * 2^11 + 4 * 2^10 bins
+        coll = 8 + 8 * ((1 << 11) + 4 * (1 << 11) + 4 * (1 << 10))
+        return {"stats_ms": ms, "stats_gbs_one_read_credited": 4.0 * self.vox_per_step / ms / 1e6,
+                "collective": ("nccl all_reduce(sum) of int64 bin counts, %d B per rank per step in 4 calls" % coll) if self.world > 1 else None,
+                "collective_bytes_per_step": coll if self.world > 1 else 0}
+
+    def parity(self):
+        """(1) every rank holds bit-identical percentiles; (2) they ARE the order statistics numpy's 'linear' rule
+        interpolates: with k = floor((n-1)q), count(x < a) <= k < count(x <= a) for the lower neighbour a (and the same
+        with k+1 for the upper one), counts summed over all ranks with plain torch ops — then np.percentile's float64
+        lerp of the two neighbours; at WORLD_SIZE 1 also literally np.percentile of the pooled data; (3) one gathered
+        volume against the oracle chain."""
+        import torch.distributed as dist
+        from oracle import monai_restated as M
+
+        self.step(0)
+        torch.cuda.synchronize()
+        pct, mats = self.last
+        pct_host = pct.cpu().numpy().reshape(-1)
+        res = {}
+        if self.world > 1:
+            gathered = [torch.empty_like(pct) for _ in range(self.world)]
+            dist.all_gather(gathered, pct)
+            same = all(torch.equal(g, gathered[0]) for g in gathered)
+            if not same:
+                raise AssertionError("parity: config E percentiles differ between ranks")
+            res["ranks_bit_identical"] = True
+        n_total = torch.tensor([sum(v.numel() for v in self.flat)], dtype=torch.int64, device=self.dev)
+        if self.world > 1:
+            dist.all_reduce(n_total)
+        n_total = int(n_total.item())
+        # the neighbours themselves: order statistics k and k+1 found by counting
+        for qi, q in enumerate((1.0, 99.0)):
+            lo, hi, gamma = stats.numpy_virtual_index(n_total, q)
+            # candidate neighbours: bracket the reported percentile by the nearest data values on all ranks
+            p = float(pct_host[qi])
+            below = torch.stack([v[v <= p].max() if bool((v <= p).any()) else torch.tensor(-np.inf, device=self.dev) for v in self.flat]).max()
+            above = torch.stack([v[v >= p].min() if bool((v >= p).any()) else torch.tensor(np.inf, device=self.dev) for v in self.flat]).min()
+            if self.world > 1:
+                dist.all_reduce(below, op=dist.ReduceOp.MAX)
+                dist.all_reduce(above, op=dist.ReduceOp.MIN)
+            cnt = torch.zeros(4, dtype=torch.int64, device=self.dev)
+            for v in self.flat:
+                cnt[0] += (v < below).sum(); cnt[1] += (v <= below).sum()
+                cnt[2] += (v < above).sum(); cnt[3] += (v <= above).sum()
+            if self.world > 1:
+                dist.all_reduce(cnt)
+            c = [int(x) for x in cnt.cpu()]
+            a, b = float(below), float(above)
+            if not (c[0] <= lo < c[1]):
+                raise AssertionError(f"parity: config E q={q}: {a} is not order statistic {lo} (counts {c[:2]})")
+            if not (c[2] <= hi < c[3]) and not (a == b):
+                raise AssertionError(f"parity: config E q={q}: {b} is not order statistic {hi} (counts {c[2:]})")
+            # numpy _lerp on float32 neighbours with the float64 weight (what np.percentile evaluates), cast to fp32
+            a32, b32 = np.float32(a), np.float32(b)
+            diff = np.float64(np.float32(b32 - a32))
+            want = np.float64(a32) + diff * gamma if gamma < 0.5 else np.float64(b32) - diff * (1.0 - gamma)
+            want = np.float32(want)
+            if np.float32(p) != np.float32(want):
+                raise AssertionError(f"parity: config E q={q}: device {p!r} != numpy lerp of the neighbours {float(want)!r}")
+        res["order_statistics_verified"] = True
+        if self.world == 1:
+            pooled = torch.cat(self.flat).cpu().numpy()
+            want = np.percentile(pooled, [1.0, 99.0])
+            if not np.array_equal(np.asarray(want, np.float32), pct_host.astype(np.float32)):
+                raise AssertionError(f"parity: config E percentiles {pct_host} != np.percentile {want}")
+            res["equals_np_percentile_of_pooled_data"] = True
+        # gather of one volume on rank 0 vs the oracle
+        worst = None
+        if self.rank == 0:
+            x = self.vols[0].cpu()[None]
+            scaled = M.scale_intensity_range(x, float(pct_host[0]), float(pct_host[1]), 0.0, 1.0)
+            want = M.affine_resample(scaled, torch.from_numpy(np.ascontiguousarray(mats[0])), "bilinear", "zeros")
+            worst = _close(self.out[0, 0].cpu(), want[0], "config E volume 0")
+        res.update({"checked": "percentiles: identical on all ranks, order statistics verified by global counts"
+                               + (", equal to np.percentile of the pooled data" if self.world == 1 else "")
+                               + "; volume 0 of rank 0 (33.5 M voxels) vs oracle", "max_rel_err": worst, "tol": TOL, "ok": True})
+        return res
+
+
+ALL = [AffineA, SegAllAffine, SegNorm, SSLTwoView, ClsPercentile, LargeVolume]
+
+
+# ----------------------------------------------------------------------------- runner
+def run(cls, dev, rank, world, seed, steps, warmup, peak_gbs, barrier, reduce_max, do_parity=True):
+    """Time one workload: returns its entry of the `workloads` block (rank 0) — every rank runs its own shard."""
+    wl = cls(dev, rank, world, seed + 101 * rank)
+    steps = steps if steps else wl.default_steps
+    parity = wl.parity() if do_parity else {"ok": None, "checked": "skipped (--no-parity)"}
+    for i in range(warmup):
+        wl.step(i)
+    barrier()
+    stream = torch.cuda.current_stream()
+    engine.timer = engine.LaunchTimer()
+    launches0 = engine.launch_count
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        engine.timer.label = i
+        wl.step(warmup + i)
+    host_s = time.perf_counter() - t0
+    b.record(stream)
+    barrier()
+    timer, engine.timer = engine.timer, None
+    ms = a.elapsed_time(b) / steps
+    per_step = {}
+    for lab, t in timer.ms():
+        per_step[lab] = per_step.get(lab, 0.0) + t
+    kernel_ms = float(np.mean(list(per_step.values()))) if per_step else None
+    launches = engine.launch_count - launches0
+    extra = wl.extra()
+    ms_max = reduce_max(ms)
+    alg = wl.bytes_per_voxel * wl.vox_per_step
+    entry = {
+        "workload": wl.desc, "value": world * wl.vox_per_step / (ms_max * 1e-3), "unit": "voxels/s", "ms_per_step": ms_max,
+        "steps": steps, "warmup": warmup, "kernel_ms": kernel_ms, "k1_launches_per_step": launches / steps,
+        "host_ms_per_step": 1e3 * host_s / steps,
+        "roofline": {"bound": "hbm", "achieved": alg / (kernel_ms * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                     "frac": alg / (kernel_ms * 1e-3) / 1e9 / peak_gbs, "algorithmic_bytes": alg, "kernel": "k1_gather",
+                     "traffic": None},
+        "parity": parity,
+    }
+    entry.update(extra)
+    del wl
+    torch.cuda.empty_cache()
+    return entry
