@@ -81,6 +81,37 @@ ITEM_SIZE = C.sizeof(Item)
 assert ITEM_SIZE == 768, ITEM_SIZE
 
 
+class Chain(C.Structure):
+    """Mirror of ``adell_chain`` (host-side chain descriptor consumed by ``adell_chain_prepare_steps``)."""
+
+    _fields_ = [
+        ("src", C.c_void_p),
+        ("dst", C.c_void_p),
+        ("pre_dev", C.c_void_p),
+        ("src_stride", C.c_int64 * 3),
+        ("dst_stride", C.c_int64 * 3),
+        ("src_shape", C.c_int32 * 3),
+        ("crop0_start", C.c_int32 * 3),
+        ("crop0_size", C.c_int32 * 3),
+        ("crop1_size", C.c_int32 * 3),
+        ("A", C.c_float * 12),
+        ("pre_scale", C.c_float),
+        ("pre_offset", C.c_float),
+        ("post_scale", C.c_float),
+        ("post_offset", C.c_float),
+        ("src_dtype", C.c_uint8),
+        ("interp", C.c_uint8),
+        ("padding", C.c_uint8),
+        ("flags", C.c_uint8),
+        ("flip0", C.c_uint8),
+        ("flip1", C.c_uint8),
+        ("reserved_", C.c_uint8 * 2),
+    ]
+
+
+CHAIN_AFFINE, CHAIN_STRICT = 0x01, 0x02
+
+
 class LaunchInfo(C.Structure):
     """Mirror of ``adell_launch_info``."""
 
@@ -101,10 +132,14 @@ _SIGNATURES = {
     "adell_item_size": (C.c_int, []),
     "adell_device_sm_count": (C.c_int, [C.POINTER(C.c_int)]),
     "adell_mat4_chain": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "adell_affine_compose": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "adell_aug_prepare": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "adell_aug_plan": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "adell_aug_prepare_steps": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "adell_aug_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "adell_chain_size": (C.c_int, []),
+    "adell_chain_compose": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "adell_chain_prepare_steps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "adell_aug_gather_launches": (C.c_int, []),
     "adell_minmax": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     "adell_meanstd": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -130,7 +165,7 @@ _SIGNATURES = {
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 _lib = None
 
 
@@ -153,6 +188,8 @@ def load() -> C.CDLL:
         raise RuntimeError("adell_b200 ABI version mismatch")
     if lib.adell_item_size() != C.sizeof(Item):
         raise RuntimeError("adell_item layout mismatch between header and binding")
+    if lib.adell_chain_size() != C.sizeof(Chain):
+        raise RuntimeError("adell_chain layout mismatch between header and binding")
     _lib = lib
     return lib
 

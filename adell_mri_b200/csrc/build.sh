@@ -7,5 +7,5 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 "${NVCC}" -shared -Xcompiler -fPIC -O3 -std=c++17 -lineinfo \
   -gencode arch=compute_100a,code=sm_100a \
   -Xptxas -v \
-  -o "${out}" "${here}/capi.cu" "${here}/gather.cu" "${here}/stats.cu" "${here}/batch.cu" "${here}/resize.cu" "$@"
+  -o "${out}" "${here}/capi.cu" "${here}/gather.cu" "${here}/stats.cu" "${here}/batch.cu" "${here}/resize.cu" "${here}/compose.cu" "$@"
 echo "built ${out}"

@@ -68,10 +68,11 @@ class _PinnedRing:
         self.events = [None] * slots
         self.i = 0
 
-    def stage(self, buf: np.ndarray, device: torch.device) -> torch.Tensor:
+    def acquire(self, n: int):
+        """Next free slot with room for ``n`` bytes: ``(slot index, pinned uint8 numpy view [n])`` — the caller
+        fills the view in place (the native composer writes the launch parameters straight into it)."""
         k = self.i
         self.i = (self.i + 1) % len(self.slots)
-        n = buf.shape[0]
         if self.events[k] is not None:
             self.events[k].synchronize()  # normally long complete
         if self.slots[k] is None or self.slots[k].numel() < n:
@@ -83,23 +84,34 @@ class _PinnedRing:
                     if self.events[j] is not None:
                         self.events[j].synchronize()
                     self.slots[j] = torch.empty(cap, dtype=torch.uint8).pin_memory()
-        host = self.slots[k][:n]
-        host.numpy()[:] = buf
-        dev = host.to(device, non_blocking=True)
+        return k, self.slots[k][:n].numpy()
+
+    def upload(self, k: int, n: int, device: torch.device) -> torch.Tensor:
+        dev = self.slots[k][:n].to(device, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(device))
         self.events[k] = ev
         return dev
 
+    def stage(self, buf: np.ndarray, device: torch.device) -> torch.Tensor:
+        n = buf.shape[0]
+        k, host = self.acquire(n)
+        host[:] = buf
+        return self.upload(k, n, device)
+
 
 _rings: dict = {}
 
 
-def _stage(buf: np.ndarray, device: torch.device) -> torch.Tensor:
+def _ring(device: torch.device) -> _PinnedRing:
     ring = _rings.get(device)
     if ring is None:
         ring = _rings[device] = _PinnedRing()
-    return ring.stage(buf, device)
+    return ring
+
+
+def _stage(buf: np.ndarray, device: torch.device) -> torch.Tensor:
+    return _ring(device).stage(buf, device)
 
 
 def _require_cuda(device: torch.device):
@@ -241,3 +253,58 @@ def prepare_steps(plan: BatchPlan, dst_ptr: np.ndarray, dst_stride: np.ndarray, 
         dev = _stage(buf, plan.device)
     launches = [(dev[o : o + n * ISZ + 4 * (n + 5)], n, info) for n, o, info in zip(sizes, offs, infos)]
     return PreparedSteps(launches, [dev, plan, infos_arr] + list(keep or []))
+
+
+CHAIN_DTYPE = np.dtype(_lib.Chain)
+_layout_cache: dict = {}
+
+
+def _steps_layout(sizes: tuple):
+    """Byte layout of several steps in one buffer: per step its items (768 B each), the int32 tile prefix and
+    the chunk-queue words, padded to 128 B so every slice stays aligned.  Cached per tuple of step sizes."""
+    hit = _layout_cache.get(sizes)
+    if hit is None:
+        ns = np.asarray(sizes, np.int64)
+        step_bytes = ns * ISZ + ((4 * (ns + 5) + 127) // 128) * 128
+        offs = np.concatenate([[0], np.cumsum(step_bytes)[:-1]]).astype(np.int64)
+        if len(_layout_cache) > 256:
+            _layout_cache.clear()
+        hit = _layout_cache[sizes] = (ns.astype(np.int32), offs, offs + ns * ISZ, int(step_bytes.sum()))
+    return hit
+
+
+def prepare_chain_steps(chains: np.ndarray, step_sizes, device: torch.device, keep=None) -> PreparedSteps:
+    """Native route of :func:`prepare_steps` for single-pass chains: ``chains`` (``CHAIN_DTYPE``, one per volume,
+    the volumes of consecutive steps in order) are composed into items, prepared (tile policy, tensor maps) and
+    written straight into a pinned staging slot by ONE call of ``adell_chain_prepare_steps`` — no numpy work per
+    volume — then uploaded with one copy."""
+    _require_cuda(device)
+    if chains.dtype != CHAIN_DTYPE or not chains.flags.c_contiguous:
+        raise ValueError("chains must be a contiguous array of adell_chain")
+    sizes = tuple(int(x) for x in step_sizes)
+    n32, offs, tile_off, total = _steps_layout(sizes)
+    if int(n32.sum()) != chains.shape[0]:
+        raise ValueError("step_sizes must add up to the number of chains")
+    lib = _lib.load()
+    infos_arr = (_lib.LaunchInfo * len(sizes))()
+    with torch.cuda.device(device):
+        ring = _ring(device)
+        k, host = ring.acquire(total)
+        _lib.check(lib.adell_chain_prepare_steps(chains.ctypes.data, host.ctypes.data, len(sizes), n32.ctypes.data,
+                                                 offs.ctypes.data, tile_off.ctypes.data, infos_arr, 0), "adell_chain_prepare_steps")
+        dev = ring.upload(k, total, device)
+    launches = [(dev[int(o): int(o) + n * ISZ + 4 * (n + 5)], n, infos_arr[i]) for i, (n, o) in enumerate(zip(sizes, offs))]
+    return PreparedSteps(launches, [dev, infos_arr] + list(keep or []))
+
+
+def compose_chains_host(chains: np.ndarray, step_sizes, plan_only: bool = True):
+    """Host-only twin of :func:`prepare_chain_steps` (no device, no driver): returns ``(buffer, offsets, infos)``;
+    used by the tests that compare the native composer with ``BatchPlan`` byte for byte."""
+    sizes = tuple(int(x) for x in step_sizes)
+    n32, offs, tile_off, total = _steps_layout(sizes)
+    buf = np.zeros(total, np.uint8)
+    infos_arr = (_lib.LaunchInfo * len(sizes))()
+    _lib.check(_lib.load().adell_chain_prepare_steps(chains.ctypes.data, buf.ctypes.data, len(sizes), n32.ctypes.data,
+                                                     offs.ctypes.data, tile_off.ctypes.data, infos_arr, int(plan_only)),
+               "adell_chain_prepare_steps")
+    return buf, offs, infos_arr

@@ -96,16 +96,17 @@ def compose_affine(rotate=None, shear=None, translate=None, scale=None, batch: i
             if x is not None and np.asarray(x).ndim == 2:
                 batch = np.asarray(x).shape[0]
     r, sh, t, sc = (_as_param(x, batch) for x in (rotate, shear, translate, scale))
-    mats = [_eye(batch)]
-    if r is not None:
-        mats.extend(rotate_factors(r))
-    if sh is not None:
-        mats.append(shear_matrices(sh))
-    if t is not None:
-        mats.append(translate_matrices(t))
-    if sc is not None:
-        mats.append(scale_matrices(sc))
-    stack = np.ascontiguousarray(np.stack(mats, axis=1))  # [B, K, 4, 4]
     out = np.empty((batch, 4, 4), np.float32)
-    _lib.check(_lib.load().adell_mat4_chain(stack.ctypes.data, batch, stack.shape[1], out.ctypes.data), "adell_mat4_chain")
+    if batch == 0:
+        return out
+    sin_r = cos_r = None
+    if r is not None:
+        if r.shape[1] > 3:
+            r = np.ascontiguousarray(r[:, :3])
+        tr = torch.from_numpy(r)
+        sin_r, cos_r = torch.sin(tr).numpy(), torch.cos(tr).numpy()   # fp32, evaluated by torch exactly as MONAI's create_rotate does
+    p = lambda a: None if a is None else a.ctypes.data
+    k = lambda a: 0 if a is None else a.shape[1]
+    _lib.check(_lib.load().adell_affine_compose(p(sin_r), p(cos_r), k(r), p(sh), k(sh), p(t), k(t), p(sc), k(sc), batch, out.ctypes.data),
+               "adell_affine_compose")
     return out

@@ -28,9 +28,26 @@ from typing import Sequence
 import numpy as np
 import torch
 
-from . import engine, geometry
+from . import _lib, engine, geometry
 from .plan import BatchPlan
 from .sampling import RandAffineSampler, child_seeds
+
+CHAIN_DTYPE = engine.CHAIN_DTYPE
+_FLIP_BITS = np.array([1, 2, 4], np.uint8)
+
+
+def _chain_template(ptr, stride, dtype, shape, dst_ptr, dst_stride, modes, padding: str, strict: bool) -> np.ndarray:
+    """Static part of the ``adell_chain`` descriptors of a batch (one per volume): where the volumes live, where
+    they go, how they are interpolated.  The per-step draws (matrix, flips, crop window) are written into a copy."""
+    n = ptr.shape[0]
+    ch = np.zeros(n, CHAIN_DTYPE)
+    ch["src"], ch["src_stride"], ch["src_dtype"], ch["src_shape"] = ptr, stride, dtype, shape
+    ch["dst"], ch["dst_stride"] = dst_ptr, dst_stride
+    ch["interp"] = [_lib.INTERP_MODES[m] for m in modes]
+    ch["padding"] = _lib.PADDING_MODES[padding]
+    ch["pre_scale"] = ch["post_scale"] = 1.0
+    ch["flags"] = _lib.CHAIN_STRICT if strict else 0
+    return ch
 
 UNET_AUGMENTS = ["intensity", "noise", "rbf", "affine", "shear", "flip", "blur", "distort", "lowres", "trivial"]
 _GPU_AUGMENTS = {"affine", "shear", "flip"}
@@ -97,6 +114,7 @@ class SegmentationBatchAugmenter:
         self.crop_R = np.random.RandomState()
         self._meta = {}
         self._dst_cache = {}
+        self._tmpl_cache = {}
         self.set_random_state(None)
 
     def set_random_state(self, seed=None, nested: bool = False):
@@ -126,7 +144,8 @@ class SegmentationBatchAugmenter:
         """All host-side random parameters of one batch, sample by sample in stream order."""
         nk = len(self.keys)
         fired = np.zeros((len(self.samplers), batch), bool)
-        mats = np.tile(np.eye(4, dtype=np.float32), (len(self.samplers), batch, 1, 1))
+        mats = np.zeros((len(self.samplers), batch, 4, 4), np.float32)
+        mats[..., 0, 0] = mats[..., 1, 1] = mats[..., 2, 2] = mats[..., 3, 3] = 1.0
         flips = np.zeros((batch, 3), bool)
         starts = None
         if self.random_crop_size is not None:
@@ -221,20 +240,93 @@ class SegmentationBatchAugmenter:
         return dst_ptr.astype(np.uint64), dst_stride
 
     def __call__(self, samples: Sequence[dict], params=None, out: dict | None = None, pre_dev: torch.Tensor | None = None) -> dict:
-        plan = self.plan(samples, params, pre_dev)
         B = len(samples)
+        if not self.fast:
+            if out is None:
+                meta = self._sample_meta(samples[0])
+                shape = tuple(int(x) for x in meta[4][0])
+                oshape = shape if self.random_crop_size is None else tuple(min(r, s) for r, s in zip(self.random_crop_size, shape))
+                out = self._alloc_out(B, oshape, meta[5][0].device)
+            ch, params = self.chains([samples], [out], params, pre_dev)
+            if ch is not None:
+                dev = self._sample_meta(samples[0])[5][0].device
+                engine.prepare_chain_steps(ch, [ch.shape[0]], dev, keep=list(out.values()) + [samples, pre_dev]).run(0)
+                return out
+        plan = self.plan(samples, params, pre_dev)
         if out is None:
             out = self._alloc_out(B, tuple(int(x) for x in plan.shape[0]), plan.device)
         dst_ptr, dst_stride = self._dst(out, B)
         engine.execute_ptrs(plan, dst_ptr, dst_stride, keep=list(out.values()))
         return out
 
+    # ---- native route: chains composed by adell_chain_prepare_steps (no numpy work per volume) ----
+    def _template(self, batch: Sequence[dict], out: dict) -> np.ndarray:
+        key = (id(batch[0]), id(batch[-1]), len(batch), id(out))
+        hit = self._tmpl_cache.get(key)
+        if hit is not None:   # ids can be recycled: the cached entry must hold these very objects, at these addresses
+            ok = hit[2] is out and hit[3] == tuple(t.data_ptr() for t in out.values())
+            for a, b in zip(hit[1], batch):
+                ok = ok and a is b
+            if not ok:
+                hit = None
+        if hit is None:
+            metas = [self._sample_meta(s) for s in batch]
+            dst_ptr, dst_stride = self._dst(out, len(batch))
+            ch = _chain_template(np.concatenate([m[1] for m in metas]), np.concatenate([m[2] for m in metas]),
+                                 np.concatenate([m[3] for m in metas]), np.concatenate([m[4] for m in metas]),
+                                 dst_ptr, dst_stride, self.modes * len(batch), "reflection", self.strict)
+            if self.random_crop_size is not None:
+                shape = tuple(int(x) for x in metas[0][4][0])
+                ch["crop0_size"] = [min(int(i * 1.10), s) for i, s in zip(self.random_crop_size, shape)]
+                ch["crop1_size"] = self.random_crop_size
+            if len(self._tmpl_cache) > 256:
+                self._tmpl_cache.clear()
+            hit = self._tmpl_cache[key] = (ch, list(batch), out, tuple(t.data_ptr() for t in out.values()))
+        return hit[0]
+
+    def chains(self, batches: Sequence[Sequence[dict]], outs: Sequence[dict], params=None, pre_dev: torch.Tensor | None = None):
+        """``adell_chain`` descriptors of several consecutive steps (same draws, in the same RandomState order, as
+        :meth:`plan`), or ``None`` when some sample needs more than one resample (both RandAffined fired: the
+        reference resamples twice, which takes the multi-pass route of :class:`BatchPlan`)."""
+        nk = len(self.keys)
+        n_samples = sum(len(b) for b in batches)
+        shape = tuple(int(x) for x in self._sample_meta(batches[0][0])[4][0])
+        if params is None:
+            params = self.draw(n_samples, shape)
+        fired = params["fired"]
+        if fired.shape[0] > 1 and (fired.sum(axis=0) > 1).any():
+            return None, params
+        # (templates are concatenated as raw bytes: numpy's concatenate of structured arrays re-derives the dtype per call)
+        raw = [self._template(b, o).view(np.uint8) for b, o in zip(batches, outs)]
+        ch = (np.concatenate(raw) if len(raw) > 1 else raw[0].copy()).view(CHAIN_DTYPE)
+        if fired.shape[0]:
+            any_fired = fired.any(axis=0)
+            if any_fired.any():
+                which = fired.argmax(axis=0)
+                A = params["mats"][which, np.arange(n_samples), :3].reshape(n_samples, 12)
+                ch["A"] = np.repeat(A, nk, axis=0)
+                ch["flags"] |= np.repeat(np.where(any_fired, _lib.CHAIN_AFFINE, 0).astype(np.uint8), nk)
+        ch["flip1"] = np.repeat(params["flips"].astype(np.uint8) @ _FLIP_BITS, nk)
+        if params["starts"] is not None:
+            ch["crop0_start"] = np.repeat(params["starts"], nk, axis=0)
+        if pre_dev is not None:
+            if pre_dev.shape != (ch.shape[0], 2) or pre_dev.dtype != torch.float32 or not pre_dev.is_contiguous():
+                raise ValueError("pre_dev must be a contiguous [n, 2] float32 tensor")
+            ch["pre_dev"] = pre_dev.data_ptr() + 8 * np.arange(ch.shape[0], dtype=np.uint64)
+        return ch, params
+
     def prepare_steps(self, batches: Sequence[Sequence[dict]], outs: Sequence[dict]) -> "engine.PreparedSteps":
         """Draw and compose several consecutive steps at once (same RandomState order as calling
         the augmenter step by step); ``outs[k]`` receives step ``k`` when ``prepared.run(k)`` is
         called.  Amortises host composition over the steps."""
         samples = [s for b in batches for s in b]
-        plan = self.plan(samples)
+        nk = len(self.keys)
+        ch, params = (None, None) if self.fast else self.chains(batches, outs)
+        if ch is not None:
+            dev = self._sample_meta(samples[0])[5][0].device
+            return engine.prepare_chain_steps(ch, [len(b) * nk for b in batches], dev,
+                                              keep=[t for o in outs for t in o.values()] + [batches])
+        plan = self.plan(samples, params)
         ptrs, strides = [], []
         for b, out in zip(batches, outs):
             p, st = self._dst(out, len(b))
@@ -249,6 +341,7 @@ class _BatchBase:
 
     def __init__(self):
         self._meta = {}
+        self._tmpl_cache = {}
 
     def _sample_meta(self, s: dict, keys):
         m = self._meta.get(id(s))
@@ -369,9 +462,59 @@ class ClassificationBatchAugmenter(_BatchBase):
             plan.center_crop(self.crop_size)
         return plan
 
-    def __call__(self, samples: Sequence[dict], params=None, out: dict | None = None, pre_dev: torch.Tensor | None = None) -> dict:
-        plan = self.plan(samples, params, pre_dev)
+    def chains(self, samples: Sequence[dict], out: dict, params=None, pre_dev: torch.Tensor | None = None):
+        """``adell_chain`` descriptors of one batch for the native composer (``None`` when a sample fired both
+        RandAffined: two resamples, the multi-pass route)."""
         B = len(samples)
+        if params is None:
+            params = self.draw(B)
+        fired = params["fired"]
+        if fired.shape[0] > 1 and (fired.sum(axis=0) > 1).any():
+            return None, params
+        key = (tuple(id(s) for s in samples), id(out), out["image"].data_ptr())
+        hit = self._tmpl_cache.get(key)
+        if hit is None or any(a is not b for a, b in zip(hit[1], samples)):
+            metas = [self._sample_meta(s, self.keys) for s in samples]
+            cat = lambda i: np.concatenate([m[i] for m in metas])
+            modes = []
+            for k, m in zip(self.keys, self.modes):
+                modes += [m] * samples[0][k].shape[0]
+            ptr, stride = self._dst_of(out["image"])
+            ch = _chain_template(cat(1), cat(2), cat(3), cat(4), ptr.reshape(-1), stride.reshape(-1, 3), modes * B, "zeros", self.strict)
+            if self.crop_size is not None:
+                ch["crop1_size"] = self.crop_size
+            if len(self._tmpl_cache) > 256:
+                self._tmpl_cache.clear()
+            hit = self._tmpl_cache[key] = (ch, list(samples))
+        ch = hit[0].copy()
+        per = ch.shape[0] // B
+        if fired.shape[0]:
+            any_fired = fired.any(axis=0)
+            if any_fired.any():
+                which = fired.argmax(axis=0)
+                ch["A"] = np.repeat(params["mats"][which, np.arange(B), :3].reshape(B, 12), per, axis=0)
+                ch["flags"] |= np.repeat(np.where(any_fired, _lib.CHAIN_AFFINE, 0).astype(np.uint8), per)
+        ch["flip0"] = np.repeat(params["flips"].astype(np.uint8) @ _FLIP_BITS, per)
+        if pre_dev is not None:
+            if pre_dev.shape != (ch.shape[0], 2) or pre_dev.dtype != torch.float32 or not pre_dev.is_contiguous():
+                raise ValueError("pre_dev must be a contiguous [n, 2] float32 tensor")
+            ch["pre_dev"] = pre_dev.data_ptr() + 8 * np.arange(ch.shape[0], dtype=np.uint64)
+        return ch, params
+
+    def __call__(self, samples: Sequence[dict], params=None, out: dict | None = None, pre_dev: torch.Tensor | None = None) -> dict:
+        B = len(samples)
+        if not self.fast:
+            if out is None:
+                meta = self._sample_meta(samples[0], self.keys)
+                shape = tuple(int(x) for x in meta[4][0])
+                oshape = shape if self.crop_size is None else tuple(min(r, s) for r, s in zip(self.crop_size, shape))
+                n_ch = sum(samples[0][k].shape[0] for k in self.keys)
+                out = {"image": torch.empty((B, n_ch, *oshape), dtype=torch.float32, device=meta[5][0].device)}
+            ch, params = self.chains(samples, out, params, pre_dev)
+            if ch is not None:
+                engine.prepare_chain_steps(ch, [ch.shape[0]], out["image"].device, keep=[out["image"], samples, pre_dev]).run(0)
+                return out
+        plan = self.plan(samples, params, pre_dev)
         per = plan.n // B
         if out is None:
             out = {"image": torch.empty((B, per, *(int(x) for x in plan.shape[0])), dtype=torch.float32, device=plan.device)}

@@ -468,6 +468,8 @@ def main():
                 continue
             workloads[cls.name] = BW.run(cls, dev, rank, world, SEED, args.workload_steps, args.warmup, peak, barrier, reduce_max,
                                          do_parity=not args.no_parity)
+            if rank == 0:
+                print("[workload] " + json.dumps({cls.name: workloads[cls.name]}), file=sys.stderr, flush=True)
 
     ms_per_step = total_ms / args.steps
     t = torch.tensor([ms_per_step, e2e_ms], device=dev, dtype=torch.float64)

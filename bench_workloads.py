@@ -456,28 +456,46 @@ class LargeVolume(Workload):
         if self.world > 1:
             dist.all_reduce(n_total)
         n_total = int(n_total.item())
-        # the neighbours themselves: order statistics k and k+1 found by counting
-        for qi, q in enumerate((1.0, 99.0)):
-            lo, hi, gamma = stats.numpy_virtual_index(n_total, q)
-            # candidate neighbours: bracket the reported percentile by the nearest data values on all ranks
-            p = float(pct_host[qi])
-            below = torch.stack([v[v <= p].max() if bool((v <= p).any()) else torch.tensor(-np.inf, device=self.dev) for v in self.flat]).max()
-            above = torch.stack([v[v >= p].min() if bool((v >= p).any()) else torch.tensor(np.inf, device=self.dev) for v in self.flat]).min()
+        # the neighbours themselves: order statistics k and k+1 of the data pooled over all ranks, located with plain
+        # torch ops (global counts) starting from the reported value — independent of the radix-select kernels
+        def gmax_below(x, strict):
+            m = torch.stack([(v[v < x] if strict else v[v <= x]).max() if bool(((v < x) if strict else (v <= x)).any())
+                             else torch.tensor(-np.inf, device=self.dev) for v in self.flat]).max()
             if self.world > 1:
-                dist.all_reduce(below, op=dist.ReduceOp.MAX)
-                dist.all_reduce(above, op=dist.ReduceOp.MIN)
-            cnt = torch.zeros(4, dtype=torch.int64, device=self.dev)
+                dist.all_reduce(m, op=dist.ReduceOp.MAX)
+            return m
+
+        def gmin_above(x):
+            m = torch.stack([v[v > x].min() if bool((v > x).any()) else torch.tensor(np.inf, device=self.dev) for v in self.flat]).min()
+            if self.world > 1:
+                dist.all_reduce(m, op=dist.ReduceOp.MIN)
+            return m
+
+        def counts(x):
+            cnt = torch.zeros(2, dtype=torch.int64, device=self.dev)
             for v in self.flat:
-                cnt[0] += (v < below).sum(); cnt[1] += (v <= below).sum()
-                cnt[2] += (v < above).sum(); cnt[3] += (v <= above).sum()
+                cnt[0] += (v < x).sum(); cnt[1] += (v <= x).sum()
             if self.world > 1:
                 dist.all_reduce(cnt)
-            c = [int(x) for x in cnt.cpu()]
-            a, b = float(below), float(above)
-            if not (c[0] <= lo < c[1]):
-                raise AssertionError(f"parity: config E q={q}: {a} is not order statistic {lo} (counts {c[:2]})")
-            if not (c[2] <= hi < c[3]) and not (a == b):
-                raise AssertionError(f"parity: config E q={q}: {b} is not order statistic {hi} (counts {c[2:]})")
+            return int(cnt[0]), int(cnt[1])
+
+        def order_stat(k, start):
+            x = start
+            for _ in range(8):
+                lt, le = counts(x)
+                if k < lt:
+                    x = gmax_below(x, True)
+                elif k >= le:
+                    x = gmin_above(x)
+                else:
+                    return float(x)
+            raise AssertionError(f"parity: config E: order statistic {k} not found near {float(start)}")
+
+        for qi, q in enumerate((1.0, 99.0)):
+            lo, hi, gamma = stats.numpy_virtual_index(n_total, q)
+            p = float(pct_host[qi])
+            a = order_stat(lo, gmax_below(torch.tensor(p, device=self.dev), False))
+            b = order_stat(hi, torch.tensor(a, device=self.dev))
             # numpy _lerp on float32 neighbours with the float64 weight (what np.percentile evaluates), cast to fp32
             a32, b32 = np.float32(a), np.float32(b)
             diff = np.float64(np.float32(b32 - a32))

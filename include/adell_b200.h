@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define ADELL_ABI_VERSION 5
+#define ADELL_ABI_VERSION 6
 
 /* status codes */
 #define ADELL_OK 0
@@ -163,6 +163,13 @@ int adell_device_sm_count(int* out); /* number of SMs of the current device     
  * (monai AffineGrid: affine = eye @ rotate @ shear @ translate @ scale). */
 int adell_mat4_chain(const float* mats, int batch, int k, float* out);
 
+/* Host-only: the MONAI AffineGrid matrix eye @ Rx @ Ry @ Rz @ shear @ translate @ scale of `batch` parameter sets
+ * in one call (k_* parameters given per set, 0 = that factor is absent; sin_r / cos_r are the fp32 sines / cosines of
+ * the k_rot <= 3 leading rotation angles, evaluated by the caller with torch like MONAI's create_rotate); products are
+ * the FMA chains of adell_mat4_chain.  out: [batch][16] row-major. */
+int adell_affine_compose(const float* sin_r, const float* cos_r, int k_rot, const float* shear, int k_shear,
+                         const float* translate, int k_trans, const float* scale, int k_scale, int batch, float* out);
+
 /* -- K1: fused gather ----------------------------------------------------------------- */
 /* What the host learned while preparing one launch. */
 typedef struct adell_launch_info {
@@ -198,6 +205,39 @@ int adell_aug_plan(adell_item* items_host, int n_items, int32_t* tile_start_host
  * (n_items[k] + 5 int32, see adell_aug_prepare) at buf_host + tile_off[k]; runs adell_aug_prepare on each, filling infos[k]. */
 int adell_aug_prepare_steps(void* buf_host, int n_steps, const int32_t* n_items, const int64_t* item_off,
                             const int64_t* tile_off, adell_launch_info* infos);
+/* Host-only chain composer: the integer index algebra that collapses one volume's transform chain
+ *   parent -> SpatialCrop(crop0) -> flips(flip0) -> [RandAffined A] -> flips(flip1) -> CenterSpatialCrop(crop1) -> intensity
+ * (get_augmentations_unet / _class / _ssl single-resample chains,
+ *  adell_mri/transform_factory/augmentations.py:98-176,255-320,427-515) into the canonical adell_item,
+ * without any Python / numpy work per volume.  Semantics are those of adell_mri_b200/plan.py
+ * (BatchPlan.crop / flip / affine / center_crop + _fill_items), which the tests compare byte for byte. */
+#define ADELL_CHAIN_AFFINE 0x01 /* the resample fired: A / interp / padding are used            */
+#define ADELL_CHAIN_STRICT 0x02 /* ADELL_F_STRICT on the item                                      */
+typedef struct adell_chain {
+  const void* src;         /* parent volume, element (0,0,0)                                       */
+  float* dst;              /* fp32 destination, element (0,0,0) of the output                      */
+  const float* pre_dev;    /* optional device {scale, offset} (sets ADELL_F_PRE_DEV) or NULL       */
+  int64_t src_stride[3];   /* parent strides in elements                                           */
+  int64_t dst_stride[3];
+  int32_t src_shape[3];    /* parent extents                                                       */
+  int32_t crop0_start[3];  /* window of the first crop; crop0_size all <= 0: no crop                */
+  int32_t crop0_size[3];
+  int32_t crop1_size[3];   /* CenterSpatialCrop roi after the flips (<= 0 per axis: keep)           */
+  float A[12];             /* rows 0..2 of the fp32 MONAI affine (ADELL_CHAIN_AFFINE)               */
+  float pre_scale, pre_offset, post_scale, post_offset;
+  uint8_t src_dtype, interp, padding, flags;
+  uint8_t flip0, flip1;    /* bit a set: torch.flip over axis a before / after the resample         */
+  uint8_t reserved_[2];
+} adell_chain;
+int adell_chain_size(void);
+int adell_chain_compose(const adell_chain* chains, int n, adell_item* items_host);
+/* Compose + adell_aug_prepare for several steps packed in one (typically pinned) host buffer: step k
+ * takes the next n_items[k] chains, writes its items at buf_host + item_off[k] (64-byte aligned) and
+ * its tile prefix (n_items[k] + 5 int32) at buf_host + tile_off[k].  plan_only != 0: adell_aug_plan
+ * instead (no driver, not launchable; for tests). */
+int adell_chain_prepare_steps(const adell_chain* chains, void* buf_host, int n_steps, const int32_t* n_items,
+                              const int64_t* item_off, const int64_t* tile_off, adell_launch_info* infos,
+                              int plan_only);
 /* Enqueue the fused gather over all items: ONE kernel launch per call. */
 int adell_aug_gather(const adell_item* items_dev, const int32_t* tile_start_dev, int n_items,
                      const adell_launch_info* info, void* stream);
