@@ -51,3 +51,26 @@ def cref_execute(plan: BatchPlan, dsts) -> None:
     launches = plan.build_launches(dst_ptr, dst_stride, lambda n: torch.empty(max(n, 1), dtype=torch.float32))
     for items in launches:
         cref.gather(items)
+
+
+class _CrefSteps:
+    def __init__(self, steps):
+        self.steps = steps
+
+    def __len__(self):
+        return len(self.steps)
+
+    def run(self, k):
+        cref.gather(self.steps[k])
+
+
+def cref_prepare_chain_steps(chains, step_sizes, device, keep=None):
+    """Stand-in for ``engine.prepare_chain_steps`` on CPU-resident chains: the NATIVE composer builds the items
+    (host policy only, nothing encoded) and each step then runs through the C restatement."""
+    from adell_mri_b200 import engine
+    from adell_mri_b200.plan import ITEM_DTYPE
+
+    sizes = [int(x) for x in step_sizes]
+    buf, offs, _ = engine.compose_chains_host(chains, sizes)
+    steps = [buf[int(o): int(o) + n * engine.ISZ].view(ITEM_DTYPE) for n, o in zip(sizes, offs)]
+    return _CrefSteps(steps)

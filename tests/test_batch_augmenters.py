@@ -22,9 +22,10 @@ def _cref_execute_ptrs(plan, dst_ptr, dst_stride, keep=None):
 @pytest.fixture(params=["cpu", pytest.param("cuda:0", marks=pytest.mark.gpu)])
 def dev(request, monkeypatch):
     if request.param == "cpu":
-        from tests.helpers import cref_execute
+        from tests.helpers import cref_execute, cref_prepare_chain_steps
         monkeypatch.setattr(engine, "execute", cref_execute)
         monkeypatch.setattr(engine, "execute_ptrs", _cref_execute_ptrs)
+        monkeypatch.setattr(engine, "prepare_chain_steps", cref_prepare_chain_steps)
     T.set_mode(strict=True, fast=False, noise="injected")
     yield request.param
     T.set_mode(strict=False)

@@ -18,7 +18,7 @@ from adell_mri_b200 import collate, engine, transform_factory as F, transforms a
 from oracle import pipelines_ref as P
 from adell_mri_b200.pipelines import SSL_FUSED_MEMBERS, ClassificationBatchAugmenter, SegmentationBatchAugmenter, SSLBatchAugmenter
 from oracle import cref
-from tests.helpers import cref_execute
+from tests.helpers import cref_execute, cref_prepare_chain_steps
 
 
 def cref_execute_ptrs(plan, dst_ptr, dst_stride, keep=None):
@@ -265,9 +265,10 @@ def sweep(rounds, seed, verbose=True, device="cpu"):
     DEVICE = device
     R = np.random.RandomState(seed)
     T.set_mode(strict=True, fast=False, noise="injected")
-    saved, saved_ptrs = engine.execute, engine.execute_ptrs
+    saved, saved_ptrs, saved_chain = engine.execute, engine.execute_ptrs, engine.prepare_chain_steps
     if device == "cpu":     # CPU stand-ins for the launcher (test infrastructure)
         engine.execute, engine.execute_ptrs = cref_execute, cref_execute_ptrs
+        engine.prepare_chain_steps = cref_prepare_chain_steps
     bad = 0
     try:
         for r in range(rounds):
@@ -281,6 +282,7 @@ def sweep(rounds, seed, verbose=True, device="cpu"):
         T.set_mode(strict=False)
         engine.execute = saved
         engine.execute_ptrs = saved_ptrs
+        engine.prepare_chain_steps = saved_chain
     return rounds, bad
 
 
