@@ -189,23 +189,26 @@ def execute_ptrs(plan: BatchPlan, dst_ptr: np.ndarray, dst_stride: np.ndarray, k
 class PreparedSteps:
     """Several steps composed and uploaded at once (one H2D copy), launched one by one."""
 
-    def __init__(self, launches, keep):
-        self.launches = launches  # [(device buffer view, n_items, LaunchInfo)]
-        self.keep = keep
+    def __init__(self, dev: torch.Tensor, offsets, sizes, infos_arr, keep):
+        self.keep = [dev, infos_arr] + list(keep or [])
         self._lib = _lib.load()
-        self._device = launches[0][0].device if launches else None
-        self._args = [(buf.data_ptr(), buf.data_ptr() + n * ISZ, n, C.byref(info)) for buf, n, info in launches]
+        self._device = dev.device
+        base = dev.data_ptr()
+        self._args = [(base + int(o), base + int(o) + n * ISZ, n, C.byref(infos_arr[i])) for i, (o, n) in enumerate(zip(offsets, sizes))]
         self._per_launch = self._lib.adell_aug_gather_launches()
+        self._gather = self._lib.adell_aug_gather
 
     def __len__(self):
-        return len(self.launches)
+        return len(self._args)
 
-    def run(self, k: int) -> None:
+    def run(self, k: int, stream: int | None = None) -> None:
+        """Enqueue step ``k`` on ``stream`` (a raw ``cudaStream_t``; default: torch's current stream of the device)."""
         global launch_count
         a = self._args[k]
-        stream = torch.cuda.current_stream(self._device).cuda_stream
+        if stream is None:
+            stream = torch.cuda.current_stream(self._device).cuda_stream
         tok = timer.begin(self._device) if timer is not None else None
-        st = self._lib.adell_aug_gather(a[0], a[1], a[2], a[3], C.c_void_p(stream))
+        st = self._gather(a[0], a[1], a[2], a[3], C.c_void_p(stream))
         if timer is not None:
             timer.end(tok)
         if st != 0:
@@ -247,12 +250,9 @@ def prepare_steps(plan: BatchPlan, dst_ptr: np.ndarray, dst_stride: np.ndarray, 
     tile_off = offs + ns * ISZ
     _lib.check(lib.adell_aug_prepare_steps(buf.ctypes.data, len(sizes), n32.ctypes.data, offs.ctypes.data,
                                            tile_off.ctypes.data, infos_arr), "adell_aug_prepare_steps")
-    infos = list(infos_arr)
-    offs = [int(o) for o in offs]
     with torch.cuda.device(plan.device):
         dev = _stage(buf, plan.device)
-    launches = [(dev[o : o + n * ISZ + 4 * (n + 5)], n, info) for n, o, info in zip(sizes, offs, infos)]
-    return PreparedSteps(launches, [dev, plan, infos_arr] + list(keep or []))
+    return PreparedSteps(dev, offs, sizes, infos_arr, [plan] + list(keep or []))
 
 
 CHAIN_DTYPE = np.dtype(_lib.Chain)
@@ -293,8 +293,7 @@ def prepare_chain_steps(chains: np.ndarray, step_sizes, device: torch.device, ke
         _lib.check(lib.adell_chain_prepare_steps(chains.ctypes.data, host.ctypes.data, len(sizes), n32.ctypes.data,
                                                  offs.ctypes.data, tile_off.ctypes.data, infos_arr, 0), "adell_chain_prepare_steps")
         dev = ring.upload(k, total, device)
-    launches = [(dev[int(o): int(o) + n * ISZ + 4 * (n + 5)], n, infos_arr[i]) for i, (n, o) in enumerate(zip(sizes, offs))]
-    return PreparedSteps(launches, [dev, infos_arr] + list(keep or []))
+    return PreparedSteps(dev, offs, sizes, infos_arr, keep)
 
 
 def compose_chains_host(chains: np.ndarray, step_sizes, plan_only: bool = True):

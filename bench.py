@@ -296,7 +296,7 @@ def main():
         torch.cuda.synchronize()
 
     EVERY = 2   # in-loop launch timing: every 2nd step carries a CUDA event pair (10 samples at --steps 20)
-    CHUNK = int(os.environ.get('BENCH_CHUNK', '16'))  # steps composed / uploaded together (host composition amortised; see engine.prepare_steps)
+    CHUNK = int(os.environ.get('BENCH_CHUNK', '32'))  # steps composed / uploaded together (host composition amortised; see engine.prepare_steps)
 
     def batch_of(i):
         b0 = (i % n_batches) * batch
@@ -324,7 +324,7 @@ def main():
                 timed = events is not None and (done + k) % EVERY == 0   # a sample of the launches: each
                 if timed:                                              # event pair costs ~5 us of host time
                     events[2 * ((done + k) // EVERY)].record(stream)
-                prepared.run(k)
+                prepared.run(k, raw_stream)
                 if timed:
                     events[2 * ((done + k) // EVERY) + 1].record(stream)
             done += n
@@ -333,6 +333,7 @@ def main():
 
     # ---- device-resident throughput ("value") ----
     stream = torch.cuda.current_stream()
+    raw_stream = stream.cuda_stream
     first_n = min(CHUNK, args.steps)
     ahead = run_steps(0, args.warmup, prep(0, min(CHUNK, args.warmup)), first_n)
     barrier()
