@@ -167,10 +167,15 @@ struct GlobalTaps {
   }
 };
 struct SmemTaps {
+  // the staged box holds the SOURCE element type (fp32 / int16 / uint8): converted at the tap
   template <int DT>
-  static __device__ __forceinline__ float get(const K1Ctx&, const K1Tile& t, const float* box, int t0, int t1, int t2) {
+  static __device__ __forceinline__ float get(const K1Ctx& c, const K1Tile& t, const float* box, int t0, int t1, int t2) {
     int m0 = t.msign[0] * t0 + t.mconst[0], m1 = t.msign[1] * t1 + t.mconst[1], m2 = t.msign[2] * t2 + t.mconst[2];
-    return box[(m0 * t.box[1] + m1) * t.box[2] + m2];
+    const int idx = (m0 * t.box[1] + m1) * t.box[2] + m2;
+    const int dt = c.it.src_dtype;
+    if (dt == ADELL_F32) return box[idx];
+    if (dt == ADELL_I16) return static_cast<float>(reinterpret_cast<const short*>(box)[idx]);
+    return static_cast<float>(reinterpret_cast<const unsigned char*>(box)[idx]);
   }
 };
 
@@ -364,6 +369,31 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
   return v;
 }
+// Taps of integer sources (int16 / uint8 boxes staged as they are stored: half / a quarter of the bytes through
+// TMA, L2 and shared memory).  The load sign- / zero-extends into a 32-bit register; the conversion to fp32 is
+// the integer add of the bit pattern of 1.5 * 2^23 (exact for |x| < 2^22) followed by one FADD — no XU conversion
+// instruction in the loop.  tap_bits<DT>: F32 -> the float itself, else the biased pattern (needs tap_fix).
+template <int DT>
+__device__ __forceinline__ float tap_raw(uint32_t addr) {
+  if (DT == ADELL_F32) return lds_f32(addr);
+  int v;
+  if (DT == ADELL_I16) asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(addr));
+  else asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return __int_as_float(v + static_cast<int>(K1_MAGIC_BITS));
+}
+template <int DT>
+__device__ __forceinline__ float tap_f32(uint32_t addr) {
+  const float r = tap_raw<DT>(addr);
+  return DT == ADELL_F32 ? r : r - K1_MAGIC;
+}
+template <int DT> struct K1Es { static constexpr uint32_t v = DT == ADELL_F32 ? 4u : (DT == ADELL_I16 ? 2u : 1u); };
+__device__ __forceinline__ uint32_t k1_es(int dt) { return dt == ADELL_F32 ? 4u : (dt == ADELL_I16 ? 2u : 1u); }
+// runtime-dtype tap (cold paths)
+__device__ __forceinline__ float tap_any(uint32_t addr, int dt) {
+  if (dt == ADELL_F32) return tap_f32<ADELL_F32>(addr);
+  if (dt == ADELL_I16) return tap_f32<ADELL_I16>(addr);
+  return tap_f32<ADELL_U8>(addr);
+}
 
 // Per-thread register image of a staged tile.  RM: 0 = every coordinate of the tile stays inside
 // [0,S); 1 = only source axis 2 leaves it and the padding is reflection (the common case of a thin,
@@ -482,14 +512,14 @@ __device__ __forceinline__ float k1_valid_weight(float v, float vl, float vh) {
 }
 
 template <int RM>
-__device__ __forceinline__ K1Vox k1_fast_vox(const K1Hot<RM>& h, float fj) {
+__device__ __forceinline__ K1Vox k1_fast_vox(const K1Hot<RM>& h, float fj, const uint32_t es = 4u) {
   float v0, v1, v2;
   k1_fast_coords<RM>(h, fj, v0, v1, v2);
   // floor on the FMA pipe: round-down add of 1.5*2^23 leaves floor(x) in the low mantissa bits
   const float t0 = __fadd_rd(v0, K1_MAGIC), t1 = __fadd_rd(v1, K1_MAGIC), t2 = __fadd_rd(v2, K1_MAGIC);
   K1Vox x;
   x.r0 = v0 - (t0 - K1_MAGIC); x.r1 = v1 - (t1 - K1_MAGIC); x.r2 = v2 - (t2 - K1_MAGIC);
-  x.a = h.cbase + 4u * (__float_as_uint(t0) * h.p0 + __float_as_uint(t1) * h.p1 + __float_as_uint(t2));
+  x.a = h.cbase + es * (__float_as_uint(t0) * h.p0 + __float_as_uint(t1) * h.p1 + __float_as_uint(t2));
   if (RM == 3) x.w = k1_valid_weight(v0, h.vl[0], h.vh[0]) * k1_valid_weight(v1, h.vl[1], h.vh[1]) * k1_valid_weight(v2, h.vl[2], h.vh[2]);
   return x;
 }
@@ -505,13 +535,14 @@ __device__ __forceinline__ float k1_lerp8(const K1Vox& x, const float* t) {
 // shared-memory taps issued before any arithmetic that depends on them (the loads are volatile
 // asm so ptxas keeps them batched); no per-voxel bounds checks — a thread's voxel count is split
 // into full groups and a one-at-a-time tail.
-template <int NV, int RMASK>
+template <int NV, int RMASK, int DT>
 __device__ __forceinline__ void k1_tile_staged_trilinear_scalar(const K1Fast& f) {
   K1Map m;
   if (!k1_lane_map(f, m)) return;
   K1Hot<RMASK> h;
   k1_hot_load<RMASK>(h, f);
-  const uint32_t o1 = 4u * h.p1, o0 = 4u * h.p0;
+  constexpr uint32_t ES = K1Es<DT>::v;
+  const uint32_t o1 = ES * h.p1, o0 = ES * h.p0;
   const int64_t ds1 = f.ds1;
   const int64_t pstep = m.jstep * ds1;
   const float fstep = static_cast<float>(m.jstep);
@@ -528,16 +559,16 @@ __device__ __forceinline__ void k1_tile_staged_trilinear_scalar(const K1Fast& f)
       K1Vox x[NV];
       float t[NV][8];
 #pragma unroll
-      for (int u = 0; u < NV; ++u) x[u] = k1_fast_vox<RMASK>(h, fj + static_cast<float>(u) * fstep);
+      for (int u = 0; u < NV; ++u) x[u] = k1_fast_vox<RMASK>(h, fj + static_cast<float>(u) * fstep, ES);
 #pragma unroll
       for (int u = 0; u < NV; ++u) {
-        t[u][0] = lds_f32(x[u].a); t[u][1] = lds_f32(x[u].a + 4);
-        t[u][2] = lds_f32(x[u].a + o1); t[u][3] = lds_f32(x[u].a + o1 + 4);
+        t[u][0] = tap_f32<DT>(x[u].a); t[u][1] = tap_f32<DT>(x[u].a + ES);
+        t[u][2] = tap_f32<DT>(x[u].a + o1); t[u][3] = tap_f32<DT>(x[u].a + o1 + ES);
       }
 #pragma unroll
       for (int u = 0; u < NV; ++u) {
-        t[u][4] = lds_f32(x[u].a + o0); t[u][5] = lds_f32(x[u].a + o0 + 4);
-        t[u][6] = lds_f32(x[u].a + o0 + o1); t[u][7] = lds_f32(x[u].a + o0 + o1 + 4);
+        t[u][4] = tap_f32<DT>(x[u].a + o0); t[u][5] = tap_f32<DT>(x[u].a + o0 + ES);
+        t[u][6] = tap_f32<DT>(x[u].a + o0 + o1); t[u][7] = tap_f32<DT>(x[u].a + o0 + o1 + ES);
       }
 #pragma unroll
       for (int u = 0; u < NV; ++u) p[u * pstep] = fmaf(k1_lerp8(x[u], t[u]), h.gain, h.bias);
@@ -546,10 +577,10 @@ __device__ __forceinline__ void k1_tile_staged_trilinear_scalar(const K1Fast& f)
     }
 #pragma unroll 1
     for (; cnt > 0; --cnt) {
-      const K1Vox x = k1_fast_vox<RMASK>(h, fj);
+      const K1Vox x = k1_fast_vox<RMASK>(h, fj, ES);
       float t[8];
-      t[0] = lds_f32(x.a); t[1] = lds_f32(x.a + 4); t[2] = lds_f32(x.a + o1); t[3] = lds_f32(x.a + o1 + 4);
-      t[4] = lds_f32(x.a + o0); t[5] = lds_f32(x.a + o0 + 4); t[6] = lds_f32(x.a + o0 + o1); t[7] = lds_f32(x.a + o0 + o1 + 4);
+      t[0] = tap_f32<DT>(x.a); t[1] = tap_f32<DT>(x.a + ES); t[2] = tap_f32<DT>(x.a + o1); t[3] = tap_f32<DT>(x.a + o1 + ES);
+      t[4] = tap_f32<DT>(x.a + o0); t[5] = tap_f32<DT>(x.a + o0 + ES); t[6] = tap_f32<DT>(x.a + o0 + o1); t[7] = tap_f32<DT>(x.a + o0 + o1 + ES);
       *p = fmaf(k1_lerp8(x, t), h.gain, h.bias);
       p += pstep;
       fj += fstep;
@@ -584,7 +615,7 @@ struct K1Hot2 {
   k1_f2 vl[3], vh[3];                // RM == 3: valid tap interval per axis
 };
 template <int RM>
-__device__ __forceinline__ K1Vox2 k1_fast_vox2(const K1Hot<RM>& h, const K1Hot2<RM>& q, k1_f2 fj2) {
+__device__ __forceinline__ K1Vox2 k1_fast_vox2(const K1Hot<RM>& h, const K1Hot2<RM>& q, k1_f2 fj2, const uint32_t es = 4u) {
   const k1_f2 M = f2_dup(K1_MAGIC), NM = f2_dup(-K1_MAGIC);
   k1_f2 v0 = f2_fma(q.D1[0], fj2, q.P[0]), v1 = f2_fma(q.D1[1], fj2, q.P[1]), v2 = f2_fma(q.D1[2], fj2, q.P[2]);
   if (RM == 1) {  // k1_fold_reflect, two lanes at a time; the clamp has no packed form
@@ -602,8 +633,8 @@ __device__ __forceinline__ K1Vox2 k1_fast_vox2(const K1Hot<RM>& h, const K1Hot2<
   x.r0 = f2_sub(v0, f2_add(t0, NM)); x.r1 = f2_sub(v1, f2_add(t1, NM)); x.r2 = f2_sub(v2, f2_add(t2, NM));
   float t0a, t0b, t1a, t1b, t2a, t2b;
   f2_unpack(t0, t0a, t0b); f2_unpack(t1, t1a, t1b); f2_unpack(t2, t2a, t2b);
-  x.aA = h.cbase + 4u * (__float_as_uint(t0a) * h.p0 + __float_as_uint(t1a) * h.p1 + __float_as_uint(t2a));
-  x.aB = h.cbase + 4u * (__float_as_uint(t0b) * h.p0 + __float_as_uint(t1b) * h.p1 + __float_as_uint(t2b));
+  x.aA = h.cbase + es * (__float_as_uint(t0a) * h.p0 + __float_as_uint(t1a) * h.p1 + __float_as_uint(t2a));
+  x.aB = h.cbase + es * (__float_as_uint(t0b) * h.p0 + __float_as_uint(t1b) * h.p1 + __float_as_uint(t2b));
   if (RM == 3) {  // valid-weight product, the subtractions packed, min / max per lane
     float wa = 1.0f, wb = 1.0f;
     const k1_f2 vv[3] = {v0, v1, v2};
@@ -628,13 +659,21 @@ __device__ __forceinline__ k1_f2 k1_lerp8x2(const K1Vox2& x, const k1_f2* t) {
 
 // Trilinear, plain tiles, RM = 0 / 1: NP pairs of voxels per iteration with packed arithmetic, a
 // one-voxel-at-a-time tail.  Same operations (and roundings) per voxel as the scalar loop.
-template <int NP, int RMASK>
+// two taps (one of each voxel of the pair) -> packed fp32; integer sources: one packed FADD2 removes the bias of both
+template <int DT>
+__device__ __forceinline__ k1_f2 tap_pair(uint32_t aA, uint32_t aB) {
+  const k1_f2 r = f2_pack(tap_raw<DT>(aA), tap_raw<DT>(aB));
+  return DT == ADELL_F32 ? r : f2_add(r, f2_dup(-K1_MAGIC));
+}
+
+template <int NP, int RMASK, int DT>
 __device__ __forceinline__ void k1_tile_staged_trilinear(const K1Fast& f) {
   K1Map m;
   if (!k1_lane_map(f, m)) return;
   K1Hot<RMASK> h;
   k1_hot_load<RMASK>(h, f);
-  const uint32_t o1 = 4u * h.p1, o0 = 4u * h.p0;
+  constexpr uint32_t ES = K1Es<DT>::v;
+  const uint32_t o1 = ES * h.p1, o0 = ES * h.p0;
   const int64_t ds1 = f.ds1;
   const int64_t pstep = m.jstep * ds1;
   const float fstep = static_cast<float>(m.jstep);
@@ -667,18 +706,18 @@ __device__ __forceinline__ void k1_tile_staged_trilinear(const K1Fast& f) {
 #pragma unroll
       for (int u = 0; u < NP; ++u) {
         const float fa = fj + static_cast<float>(2 * u) * fstep;
-        x[u] = k1_fast_vox2<RMASK>(h, q, f2_pack(fa, fa + fstep));
+        x[u] = k1_fast_vox2<RMASK>(h, q, f2_pack(fa, fa + fstep), ES);
       }
 #pragma unroll
       for (int u = 0; u < NP; ++u) {
-        t[u][0] = f2_pack(lds_f32(x[u].aA), lds_f32(x[u].aB)); t[u][1] = f2_pack(lds_f32(x[u].aA + 4), lds_f32(x[u].aB + 4));
-        t[u][2] = f2_pack(lds_f32(x[u].aA + o1), lds_f32(x[u].aB + o1)); t[u][3] = f2_pack(lds_f32(x[u].aA + o1 + 4), lds_f32(x[u].aB + o1 + 4));
+        t[u][0] = tap_pair<DT>(x[u].aA, x[u].aB); t[u][1] = tap_pair<DT>(x[u].aA + ES, x[u].aB + ES);
+        t[u][2] = tap_pair<DT>(x[u].aA + o1, x[u].aB + o1); t[u][3] = tap_pair<DT>(x[u].aA + o1 + ES, x[u].aB + o1 + ES);
       }
 #pragma unroll
       for (int u = 0; u < NP; ++u) {
-        t[u][4] = f2_pack(lds_f32(x[u].aA + o0), lds_f32(x[u].aB + o0)); t[u][5] = f2_pack(lds_f32(x[u].aA + o0 + 4), lds_f32(x[u].aB + o0 + 4));
-        t[u][6] = f2_pack(lds_f32(x[u].aA + o0 + o1), lds_f32(x[u].aB + o0 + o1));
-        t[u][7] = f2_pack(lds_f32(x[u].aA + o0 + o1 + 4), lds_f32(x[u].aB + o0 + o1 + 4));
+        t[u][4] = tap_pair<DT>(x[u].aA + o0, x[u].aB + o0); t[u][5] = tap_pair<DT>(x[u].aA + o0 + ES, x[u].aB + o0 + ES);
+        t[u][6] = tap_pair<DT>(x[u].aA + o0 + o1, x[u].aB + o0 + o1);
+        t[u][7] = tap_pair<DT>(x[u].aA + o0 + o1 + ES, x[u].aB + o0 + o1 + ES);
       }
 #pragma unroll
       for (int u = 0; u < NP; ++u) {
@@ -693,10 +732,10 @@ __device__ __forceinline__ void k1_tile_staged_trilinear(const K1Fast& f) {
     }
 #pragma unroll 1
     for (; cnt > 0; --cnt) {
-      const K1Vox x = k1_fast_vox<RMASK>(h, fj);
+      const K1Vox x = k1_fast_vox<RMASK>(h, fj, ES);
       float t[8];
-      t[0] = lds_f32(x.a); t[1] = lds_f32(x.a + 4); t[2] = lds_f32(x.a + o1); t[3] = lds_f32(x.a + o1 + 4);
-      t[4] = lds_f32(x.a + o0); t[5] = lds_f32(x.a + o0 + 4); t[6] = lds_f32(x.a + o0 + o1); t[7] = lds_f32(x.a + o0 + o1 + 4);
+      t[0] = tap_f32<DT>(x.a); t[1] = tap_f32<DT>(x.a + ES); t[2] = tap_f32<DT>(x.a + o1); t[3] = tap_f32<DT>(x.a + o1 + ES);
+      t[4] = tap_f32<DT>(x.a + o0); t[5] = tap_f32<DT>(x.a + o0 + ES); t[6] = tap_f32<DT>(x.a + o0 + o1); t[7] = tap_f32<DT>(x.a + o0 + o1 + ES);
       *p = fmaf(k1_lerp8(x, t), h.gain, RMASK == 3 ? fmaf(x.w, h.wb, h.po) : h.bias);
       p += pstep;
       fj += fstep;
@@ -705,8 +744,9 @@ __device__ __forceinline__ void k1_tile_staged_trilinear(const K1Fast& f) {
 }
 
 // Nearest, plain tiles: fast coordinates, exact replay inside the tie window.
-template <int RMASK>
+template <int RMASK, int DT>
 __device__ __forceinline__ void k1_tile_staged_nearest(const K1Ctx& c, const K1Tile& tl, const K1Fast& f, const float* __restrict__ box) {
+  constexpr uint32_t ES = K1Es<DT>::v;
   K1Map m;
   if (!k1_lane_map(f, m)) return;
   K1Hot<RMASK> h;
@@ -732,8 +772,8 @@ __device__ __forceinline__ void k1_tile_staged_nearest(const K1Ctx& c, const K1T
       if (fmaxf(fmaxf(fabsf(v0 - n0), fabsf(v1 - n1)), fabsf(v2 - n2)) > tie) {
         val = k1_exact_nearest_smem(c, tl, box, m.ii, dj - m.s1, m.dk);  // inside the tie window of a rounding tie
       } else {
-        const uint32_t a = h.cbase + 4u * (__float_as_uint(t0) * h.p0 + __float_as_uint(t1) * h.p1 + __float_as_uint(t2));
-        val = fmaf(lds_f32(a), h.gain, h.bias);
+        const uint32_t a = h.cbase + ES * (__float_as_uint(t0) * h.p0 + __float_as_uint(t1) * h.p1 + __float_as_uint(t2));
+        val = fmaf(tap_f32<DT>(a), h.gain, h.bias);
         if (RMASK == 3) {  // an invalid (zero-filled) tap is a literal 0 of the padded volume: no pre offset
           const bool ok = (n0 > h.vl[0]) & (n0 < h.vh[0]) & (n1 > h.vl[1]) & (n1 < h.vh[1]) & (n2 > h.vl[2]) & (n2 < h.vh[2]);
           if (!ok) val = h.po;
@@ -755,7 +795,9 @@ __device__ __noinline__ void k1_tile_staged_cold(const K1Ctx& c, const K1Tile& t
   k1_hot_load<2>(h, f);
   const bool nearest = c.it.interp == ADELL_NEAREST;
   const float tie = f.rb.w;
-  const uint32_t o1 = 4u * h.p1, o0 = 4u * h.p0;
+  const int dt = c.it.src_dtype;
+  const uint32_t es = k1_es(dt);
+  const uint32_t o1 = es * h.p1, o0 = es * h.p0;
   const int4 vlo = f.vlo, vhi = f.vhi, fl = f.fl;
   const float4 gb = f.gb;
   const int T0 = f.n.x;
@@ -773,12 +815,12 @@ __device__ __noinline__ void k1_tile_staged_cold(const K1Ctx& c, const K1Tile& t
         if (fabsf(v0 - (t0 - K1_MAGIC)) > tie || fabsf(v1 - (t1 - K1_MAGIC)) > tie || fabsf(v2 - (t2 - K1_MAGIC)) > tie)
           val = k1_exact_nearest_smem(c, tl, box, m.ii, jo, dk);
         else
-          val = fmaf(lds_f32(h.cbase + 4u * (__float_as_uint(t0) * h.p0 + __float_as_uint(t1) * h.p1 + __float_as_uint(t2))), h.gain, h.bias);
+          val = fmaf(tap_any(h.cbase + es * (__float_as_uint(t0) * h.p0 + __float_as_uint(t1) * h.p1 + __float_as_uint(t2)), dt), h.gain, h.bias);
       } else {
-        const K1Vox x = k1_fast_vox<2>(h, static_cast<float>(dj));
+        const K1Vox x = k1_fast_vox<2>(h, static_cast<float>(dj), es);
         float t[8];
-        t[0] = lds_f32(x.a); t[1] = lds_f32(x.a + 4); t[2] = lds_f32(x.a + o1); t[3] = lds_f32(x.a + o1 + 4);
-        t[4] = lds_f32(x.a + o0); t[5] = lds_f32(x.a + o0 + 4); t[6] = lds_f32(x.a + o0 + o1); t[7] = lds_f32(x.a + o0 + o1 + 4);
+        t[0] = tap_any(x.a, dt); t[1] = tap_any(x.a + es, dt); t[2] = tap_any(x.a + o1, dt); t[3] = tap_any(x.a + o1 + es, dt);
+        t[4] = tap_any(x.a + o0, dt); t[5] = tap_any(x.a + o0 + es, dt); t[6] = tap_any(x.a + o0 + o1, dt); t[7] = tap_any(x.a + o0 + o1 + es, dt);
         val = fmaf(k1_lerp8(x, t), h.gain, h.bias);
       }
       if (fl.y) {
@@ -793,12 +835,63 @@ __device__ __noinline__ void k1_tile_staged_cold(const K1Ctx& c, const K1Tile& t
   }
 }
 
+// Plain staged tile (no output pad band, no noise) of a source of element type DT.  fp32 sources are inlined
+// into the kernel's main loop; the integer-source variants are out of line (one call per tile) so that the three
+// copies of the voxel loops do not share the instruction cache footprint of the hot one.
+template <int DT>
+__device__ __forceinline__ void k1_staged_plain_body(const K1Ctx& ctx, const K1Tile& tl, const K1Fast& f, const float* __restrict__ box, int rm) {
+  if (ctx.it.interp == ADELL_NEAREST) {
+    if (rm == 0) k1_tile_staged_nearest<0, DT>(ctx, tl, f, box);
+    else if (rm == 1) k1_tile_staged_nearest<1, DT>(ctx, tl, f, box);
+    else if (rm == 3) k1_tile_staged_nearest<3, DT>(ctx, tl, f, box);
+    else k1_tile_staged_nearest<2, DT>(ctx, tl, f, box);
+  } else {
+    if (rm == 0) k1_tile_staged_trilinear<K1_NP, 0, DT>(f);
+    else if (rm == 1) k1_tile_staged_trilinear<K1_NP, 1, DT>(f);
+    else if (rm == 3) k1_tile_staged_trilinear<K1_NP, 3, DT>(f);
+    else k1_tile_staged_trilinear_scalar<K1_NV, 2, DT>(f);
+  }
+}
+template <int DT>
+__device__ __noinline__ void k1_staged_plain_ool(const K1Ctx& ctx, const K1Tile& tl, const K1Fast& f, const float* __restrict__ box, int rm) {
+  k1_staged_plain_body<DT>(ctx, tl, f, box, rm);
+}
+template <int DT>
+__device__ __forceinline__ void k1_staged_plain(const K1Ctx& ctx, const K1Tile& tl, const K1Fast& f, const float* __restrict__ box, int rm) {
+  if (DT == ADELL_F32) k1_staged_plain_body<DT>(ctx, tl, f, box, rm);
+  else k1_staged_plain_ool<DT>(ctx, tl, f, box, rm);
+}
+
 // Identity items (flip / crop only, everything valid): the producer brings the tile's source box
 // in with one TMA load like any staged tile — the load latency is carried by the TMA queue, several
 // tiles deep, instead of by the consumer threads — and the consumers move it out with 128-bit
 // shared loads and 128-bit streaming global stores.  One 32x16x32 tile = 64 KiB; each thread
 // moves eight float4 (rows di0 + 4r of column quad q).  A flip is a sign in the box index; a flip
 // along the contiguous axis reverses the quad in registers.
+// quad of four consecutive source elements starting at box element index e -> four floats (memory order)
+template <int DT>
+__device__ __forceinline__ float4 k1_load_quad(const float* __restrict__ box, int e, bool vec) {
+  if (DT == ADELL_F32) {
+    const float* p = box + e;
+    return vec ? *reinterpret_cast<const float4*>(p) : make_float4(p[0], p[1], p[2], p[3]);
+  } else if (DT == ADELL_I16) {
+    const short* p = reinterpret_cast<const short*>(box) + e;
+    if (vec) {  // 8-byte aligned: one 64-bit load
+      const short4 q = *reinterpret_cast<const short4*>(p);
+      return make_float4(static_cast<float>(q.x), static_cast<float>(q.y), static_cast<float>(q.z), static_cast<float>(q.w));
+    }
+    return make_float4(static_cast<float>(p[0]), static_cast<float>(p[1]), static_cast<float>(p[2]), static_cast<float>(p[3]));
+  } else {
+    const unsigned char* p = reinterpret_cast<const unsigned char*>(box) + e;
+    if (vec) {
+      const uchar4 q = *reinterpret_cast<const uchar4*>(p);
+      return make_float4(static_cast<float>(q.x), static_cast<float>(q.y), static_cast<float>(q.z), static_cast<float>(q.w));
+    }
+    return make_float4(static_cast<float>(p[0]), static_cast<float>(p[1]), static_cast<float>(p[2]), static_cast<float>(p[3]));
+  }
+}
+
+template <int DT>
 __device__ __forceinline__ void k1_tile_copy_box(const K1Ctx& c, const K1Tile& tl, const float* __restrict__ box) {
   const adell_item& it = c.it;
   constexpr int PS = K1_GTHREADS / 128;  // planes a group covers per step (a plane = 16 rows x 8 quads)
@@ -814,7 +907,7 @@ __device__ __forceinline__ void k1_tile_copy_box(const K1Ctx& c, const K1Tile& t
   const bool rev = s2 < 0;
   const int m2 = rev ? M2 - (o2 + 3) : M2 + o2;  // lowest box column of the quad
   const int p1 = tl.box[2], p0 = tl.box[1] * tl.box[2];
-  const float* sp = box + (s0 * o0 + M0) * p0 + (s1 * o1 + M1) * p1 + m2;
+  const int sp = (s0 * o0 + M0) * p0 + (s1 * o1 + M1) * p1 + m2;   // box element index of the thread's first quad
   const int sstep = PS * s0 * p0;
   const bool vec = (m2 & 3) == 0;  // block-uniform: the same for every quad of every tile of an item
   const bool clip = (it.flags & ADELL_F_CLIP) != 0;
@@ -839,20 +932,18 @@ __device__ __forceinline__ void k1_tile_copy_box(const K1Ctx& c, const K1Tile& t
     return x;
   };
   if (vec) {
-    // eight independent 128-bit loads in flight per thread, then their stores
+    // eight independent vector loads in flight per thread, then their stores
 #pragma unroll 1
     for (int r0 = 0; r0 < nrow; r0 += 8) {
 #pragma unroll
       for (int r = 0; r < 8; ++r)
         if (r0 + r < nrow)
-          K1_STORE(reinterpret_cast<float4*>(dp + (r0 + r) * dstep), fix(*reinterpret_cast<const float4*>(sp + (r0 + r) * sstep)));
+          K1_STORE(reinterpret_cast<float4*>(dp + (r0 + r) * dstep), fix(k1_load_quad<DT>(box, sp + (r0 + r) * sstep, true)));
     }
   } else {
 #pragma unroll 2
-    for (int r = 0; r < nrow; ++r) {
-      const float* p = sp + r * sstep;
-      K1_STORE(reinterpret_cast<float4*>(dp + r * dstep), fix(make_float4(p[0], p[1], p[2], p[3])));
-    }
+    for (int r = 0; r < nrow; ++r)
+      K1_STORE(reinterpret_cast<float4*>(dp + r * dstep), fix(k1_load_quad<DT>(box, sp + r * sstep, false)));
   }
 }
 
@@ -924,7 +1015,7 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
       const int g0 = it.grid_off[a] + it.grid_sign[a] * o0a, g1 = it.grid_off[a] + it.grid_sign[a] * (o0a + na - 1);
       const int msign = it.tmap_sign[a];
       int mo = msign > 0 ? min(g0, g1) + it.tmap_off[a] : -max(g0, g1) + it.tmap_off[a];
-      if (a == 2) mo = (mo >> 2) << 2;  // 16-byte aligned start along the contiguous axis
+      if (a == 2) mo &= ~(static_cast<int>(16u / k1_es(it.src_dtype)) - 1);  // 16-byte aligned start along the contiguous axis
       tl.box[a] = it.tmap_box[a]; tl.msign[a] = msign; tl.mconst[a] = it.tmap_off[a] - mo;
       if (a == 2) { tl.fix_lo = 0; tl.fix_hi = 0; }
     }
@@ -1000,8 +1091,10 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
     if (it.tmap_sign[a] < 0) blo -= 1;
   }
   // cells [blo, bhi] plus, along the contiguous axis, those lost to aligning the box origin down to 16 bytes
+  const int es = static_cast<int>(k1_es(it.src_dtype));
+  const int qm = 16 / es - 1;   // elements per 16 bytes, minus one
   const int mo_raw = it.tmap_sign[a] > 0 ? blo + it.tmap_off[a] : -bhi + it.tmap_off[a];
-  const bool fits = bhi - blo + 1 + (a == 2 ? (mo_raw & 3) : 0) <= it.tmap_box[a];  // else larger than the encoded box
+  const bool fits = bhi - blo + 1 + (a == 2 ? (mo_raw & qm) : 0) <= it.tmap_box[a];  // else larger than the encoded box
   const bool allv = lo >= c.tlo[a] && hi < c.thi[a];
   const bool win_full = c.tlo[a] <= 0 && c.thi[a] >= S;
   if (!__all_sync(FULL, fits)) { if (lane == 0) tl.mode = MODE_DIRECT; return; }
@@ -1013,8 +1106,8 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
   const int msign = it.tmap_sign[a];
   int mo = msign > 0 ? blo + it.tmap_off[a] : -bhi + it.tmap_off[a];
   // TMA needs a 16-byte aligned start along the contiguous axis: round the box origin down to a
-  // multiple of 4 elements (the encoded inner extent carries 3 spare elements for this)
-  if (a == 2) mo = (mo >> 2) << 2;
+  // multiple of 16 bytes (the encoded inner extent carries the spare elements for this)
+  if (a == 2) mo &= ~qm;
   const int mconst = it.tmap_off[a] - mo;
   float V0, Dm0, Dm1, Dm2, rA, rB;
   if (rm) {
@@ -1079,7 +1172,7 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
     for (int g = 0; g < 4; ++g) f.eg[g][3] = __int_as_float(shv[g]);
     const uint32_t p0 = static_cast<uint32_t>(it.tmap_box[1] * it.tmap_box[2]), p1 = static_cast<uint32_t>(it.tmap_box[2]);
     f.m = make_int4(static_cast<int>(p0), static_cast<int>(p1), rmask | (it.padding << 8),
-                    static_cast<int>(box_addr - 4u * (K1_MAGIC_BITS * (p0 + p1 + 1u))));
+                    static_cast<int>(box_addr - static_cast<uint32_t>(es) * (K1_MAGIC_BITS * (p0 + p1 + 1u))));
     f.rb = make_float4(rB0, rB1, rB2, tie);
     f.ws = make_float4(c.pre_o * it.post_scale, it.post_offset, 0.0f, 0.0f);
     f.fl = make_int4((padded || it.noise != nullptr || philox) ? 1 : 0, padded ? 1 : 0, philox, 0);
@@ -1172,10 +1265,18 @@ __device__ __forceinline__ void k1_prepare(const adell_item* __restrict__ items,
 
 // Producer, after the TMA load of a tile whose box contains alignment-slack columns completed:
 // zero them (they hold bytes that precede the valid source box) and hand the stage to the consumers.
-__device__ __forceinline__ void k1_fix_columns(float* box, const K1Tile& tl, int lane) {
+__device__ __forceinline__ void k1_fix_columns(float* box, const K1Tile& tl, int lane, int dt) {
   const int w = tl.fix_hi - tl.fix_lo, p1 = tl.box[2];
   const int rows = tl.box[0] * tl.box[1];
-  for (int e = lane; e < rows * w; e += 32) box[(e / w) * p1 + tl.fix_lo + e % w] = 0.0f;
+  if (dt == ADELL_F32) {
+    for (int e = lane; e < rows * w; e += 32) box[(e / w) * p1 + tl.fix_lo + e % w] = 0.0f;
+  } else if (dt == ADELL_I16) {
+    short* b = reinterpret_cast<short*>(box);
+    for (int e = lane; e < rows * w; e += 32) b[(e / w) * p1 + tl.fix_lo + e % w] = 0;
+  } else {
+    unsigned char* b = reinterpret_cast<unsigned char*>(box);
+    for (int e = lane; e < rows * w; e += 32) b[(e / w) * p1 + tl.fix_lo + e % w] = 0;
+  }
   fence_proxy_async_smem();
   __syncwarp();
 }
@@ -1286,7 +1387,7 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
           const int mo0 = sl.ctx.it.tmap_off[0] - sl.tl.mconst[0], mo1 = sl.ctx.it.tmap_off[1] - sl.tl.mconst[1],
                     mo2 = sl.ctx.it.tmap_off[2] - sl.tl.mconst[2];
           if (sl.tl.item != acq_item) { tmap_acquire(items[sl.tl.item].tmap); acq_item = sl.tl.item; }
-          mbar_expect_tx(landed + stage, static_cast<uint32_t>(sl.tl.box[0] * sl.tl.box[1] * sl.tl.box[2] * 4));
+          mbar_expect_tx(landed + stage, static_cast<uint32_t>(sl.tl.box[0] * sl.tl.box[1] * sl.tl.box[2]) * k1_es(sl.ctx.it.src_dtype));
           tma_load_3d(smem + static_cast<size_t>(stage) * stage_bytes, items[sl.tl.item].tmap, landed + stage, mo2, mo1, mo0);
         } else {
           mbar_arrive(landed + stage);
@@ -1316,7 +1417,7 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
       const K1Tile& tl = slots[slot].tl;
       const int mode = tl.mode;
       if (mode == MODE_STAGED && tl.fix_hi > tl.fix_lo)
-        k1_fix_columns(reinterpret_cast<float*>(smem + static_cast<size_t>(stage) * stage_bytes), tl, lane);
+        k1_fix_columns(reinterpret_cast<float*>(smem + static_cast<size_t>(stage) * stage_bytes), tl, lane, slots[slot].ctx.it.src_dtype);
       if (mode == MODE_TSTORE) {
         // Plain copy tile: the box that just landed goes straight back out through the destination tensor
         // map — no consumer instructions, no LSU traffic.  The box is in SOURCE memory order: an axis whose
@@ -1374,7 +1475,9 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
     const int mode = tl.mode;
     if (mode == MODE_DONE) break;
     if (mode == MODE_COPY) {
-      k1_tile_copy_box(ctx, tl, box);
+      if (it.src_dtype == ADELL_F32) k1_tile_copy_box<ADELL_F32>(ctx, tl, box);
+      else if (it.src_dtype == ADELL_I16) k1_tile_copy_box<ADELL_I16>(ctx, tl, box);
+      else k1_tile_copy_box<ADELL_U8>(ctx, tl, box);
     } else if (mode == MODE_TSTORE) {
       // stored by the hand-over warp (TMA): the consumers only pass the stage on
     } else if (mode == MODE_ZERO) {
@@ -1391,17 +1494,9 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
         // block-uniform variant: 0 = no padding arithmetic, 1 = reflection on the thin axis only, 2 = general,
         // 3 = no padding arithmetic but invalid taps under a pre offset (valid-weight sum)
         const int rm = tl.rmask == 0 ? (leak ? 3 : 0) : ((tl.rmask == 4 && it.padding == ADELL_PAD_REFLECTION) ? 1 : 2);
-        if (it.interp == ADELL_NEAREST) {
-          if (rm == 0) k1_tile_staged_nearest<0>(ctx, tl, f, box);
-          else if (rm == 1) k1_tile_staged_nearest<1>(ctx, tl, f, box);
-          else if (rm == 3) k1_tile_staged_nearest<3>(ctx, tl, f, box);
-          else k1_tile_staged_nearest<2>(ctx, tl, f, box);
-        } else {
-          if (rm == 0) k1_tile_staged_trilinear<K1_NP, 0>(f);
-          else if (rm == 1) k1_tile_staged_trilinear<K1_NP, 1>(f);
-          else if (rm == 3) k1_tile_staged_trilinear<K1_NP, 3>(f);
-          else k1_tile_staged_trilinear_scalar<K1_NV, 2>(f);
-        }
+        if (it.src_dtype == ADELL_F32) k1_staged_plain<ADELL_F32>(ctx, tl, f, box, rm);
+        else if (it.src_dtype == ADELL_I16) k1_staged_plain<ADELL_I16>(ctx, tl, f, box, rm);
+        else k1_staged_plain<ADELL_U8>(ctx, tl, f, box, rm);
       }
     } else if (it.flags & ADELL_F_IDENTITY) {
       k1_tile_exact_dispatch<GlobalTaps, true>(ctx, tl, nullptr);
@@ -1469,11 +1564,13 @@ CUresult k1_encode_nothing(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                            const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                            CUtensorMapL2promotion, CUtensorMapFloatOOBfill) { return CUDA_SUCCESS; }
 
-// Identity item eligible for the box copy: fp32, unit step along axis 2, 16-byte aligned
+// Identity item eligible for the box copy: unit step along axis 2, 16-byte aligned
 // destination rows, nothing invalid, no noise, no strict-order post map.  (The source needs no
 // alignment: it arrives through a TMA box whose origin is rounded down to 16 bytes.)
+int k1_host_es(int dt) { return dt == ADELL_F32 ? 4 : (dt == ADELL_I16 ? 2 : 1); }
+
 bool k1_vcopy_ok(const adell_item& it) {
-  if (!(it.flags & ADELL_F_IDENTITY) || it.src_dtype != ADELL_F32) return false;
+  if (!(it.flags & ADELL_F_IDENTITY)) return false;   // (integer sources are converted on the way out of the box)
   if ((it.src_stride[2] != 1 && it.src_stride[2] != -1) || it.dst_stride[2] != 1 || it.noise != nullptr) return false;
   if ((it.flags & (ADELL_F_PHILOX | ADELL_F_STRICT)) || (it.out_shape[2] & 3) != 0) return false;
   for (int a = 0; a < 3; ++a) {
@@ -1605,6 +1702,7 @@ int k1_tile_extent(const adell_item& it, const int* T, int b, bool sheared) {
 // tmap_sign / tmap_off (k1_tmap_layout).
 int64_t k1_box_for_tile(const adell_item& it, const int* T, int* box, bool sheared) {
   int64_t cells = 1;
+  const int es = k1_host_es(it.src_dtype), q = 16 / es;   // element size; elements per 16 bytes
   for (int a = 0; a < 3; ++a) {
     double span = k1_group_range(it, a, T[2]);
     for (int b = 0; b < 3; ++b) span += fabs(it.fp_D[3 * a + b]) * (k1_tile_extent(it, T, b, sheared) - 1);
@@ -1621,17 +1719,17 @@ int64_t k1_box_for_tile(const adell_item& it, const int* T, int* box, bool shear
     if (a == 2) {
       // inner extent: a 16-byte multiple, plus the cells lost to aligning the box origin down to 16 bytes
       // (known exactly when the axis is staged whole)
-      int lead = 3;
+      int lead = q - 1;
       if (whole) {
         const int mo = it.tmap_sign[2] > 0 ? it.tmap_off[2] : -(it.src_shape[2] - 1) + it.tmap_off[2];
-        lead = mo & 3;
+        lead = mo & (q - 1);
       }
-      box[a] = (box[a] + lead + 3) & ~3;
+      box[a] = (box[a] + lead + q - 1) & ~(q - 1);
     }
     if (box[a] > 256) return 0;
     cells *= box[a];
   }
-  return cells * 4;
+  return cells * es;
 }
 
 // Memory-order layout of the item's valid source box: fills tmap_sign / tmap_off / fp_fix and the
@@ -1639,6 +1737,7 @@ int64_t k1_box_for_tile(const adell_item& it, const int* T, int* box, bool shear
 struct K1Layout {
   cuuint64_t gdim[3], gstride[2];
   uintptr_t base;
+  int es = 4;   // element size in bytes: 4 fp32, 2 int16, 1 uint8
 };
 bool k1_tmap_layout(adell_item& it, K1Layout& L) {
   int64_t base_off = 0;
@@ -1655,15 +1754,18 @@ bool k1_tmap_layout(adell_item& it, K1Layout& L) {
     base_off += static_cast<int64_t>(sign > 0 ? tlo : thi - 1) * it.src_stride[a];
     L.gdim[2 - a] = static_cast<cuuint64_t>(thi - tlo);   // tensor-map dims are innermost first
   }
-  uintptr_t base = reinterpret_cast<uintptr_t>(it.src) + static_cast<uintptr_t>(base_off * 4);
-  L.gstride[0] = static_cast<cuuint64_t>(astride[1]) * 4;
-  L.gstride[1] = static_cast<cuuint64_t>(astride[0]) * 4;
-  if ((base & 3u) || (L.gstride[0] & 15u) || (L.gstride[1] & 15u)) return false;
-  if (L.gstride[0] < L.gdim[0] * 4 || L.gstride[1] < L.gstride[0]) return false;  // rows must not overlap
+  const int es = k1_host_es(it.src_dtype);
+  L.es = es;
+  uintptr_t base = reinterpret_cast<uintptr_t>(it.src) + static_cast<uintptr_t>(base_off * es);
+  L.gstride[0] = static_cast<cuuint64_t>(astride[1]) * es;
+  L.gstride[1] = static_cast<cuuint64_t>(astride[0]) * es;
+  if ((base & static_cast<uintptr_t>(es - 1)) || (L.gstride[0] & 15u) || (L.gstride[1] & 15u)) return false;
+  if (L.gstride[0] < L.gdim[0] * es || L.gstride[1] < L.gstride[0]) return false;  // rows must not overlap
   // a crop window may start anywhere in a row: align the tensor-map base down to 16 bytes; the
-  // 1..3 elements this prepends to every row are zeroed in shared memory after each load (fp_fix)
-  const int slack = static_cast<int>((base & 15u) >> 2);
-  base -= static_cast<uintptr_t>(slack) * 4;
+  // elements this prepends to every row (up to 3 fp32 / 7 int16 / 15 uint8) are zeroed in shared memory
+  // after each load (fp_fix)
+  const int slack = static_cast<int>(base & 15u) / es;
+  base -= static_cast<uintptr_t>(slack) * es;
   L.gdim[0] += static_cast<cuuint64_t>(slack);
   it.tmap_off[2] += slack;
   it.fp_fix = slack;
@@ -1679,7 +1781,7 @@ bool k1_tmap_layout(adell_item& it, K1Layout& L) {
 int k1_encode_map(uint8_t* out_map, const K1Layout& L, const cuuint32_t* bdim, EncodeTiledFn enc) {
   const cuuint32_t estr[3] = {1, 1, 1};
   if (enc == nullptr) return -1;
-  struct Entry { uintptr_t base; cuuint64_t gdim[3], gstride[2]; cuuint32_t box[3]; bool valid; uint8_t map[128]; };
+  struct Entry { uintptr_t base; cuuint64_t gdim[3], gstride[2]; cuuint32_t box[3]; int es; bool valid; uint8_t map[128]; };
   constexpr int kEntries = 2048;
   static thread_local Entry* cache = nullptr;
   if (cache == nullptr) cache = static_cast<Entry*>(calloc(kEntries, sizeof(Entry)));
@@ -1689,12 +1791,13 @@ int k1_encode_map(uint8_t* out_map, const K1Layout& L, const cuuint32_t* bdim, E
     e = cache + (h >> 40) % kEntries;
     if (e->valid && e->base == L.base && e->gdim[0] == L.gdim[0] && e->gdim[1] == L.gdim[1] && e->gdim[2] == L.gdim[2] &&
         e->gstride[0] == L.gstride[0] && e->gstride[1] == L.gstride[1] && e->box[0] == bdim[0] && e->box[1] == bdim[1] &&
-        e->box[2] == bdim[2]) {
+        e->box[2] == bdim[2] && e->es == L.es) {
       memcpy(out_map, e->map, 128);
       return 1;
     }
   }
-  CUresult r = enc(reinterpret_cast<CUtensorMap*>(out_map), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+  const CUtensorMapDataType dt = L.es == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (L.es == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8);
+  CUresult r = enc(reinterpret_cast<CUtensorMap*>(out_map), dt, 3,
                    reinterpret_cast<void*>(L.base), L.gdim, L.gstride, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, K1_L2_PROMO, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return 0;
@@ -1702,6 +1805,7 @@ int k1_encode_map(uint8_t* out_map, const K1Layout& L, const cuuint32_t* bdim, E
     e->base = L.base;
     for (int i = 0; i < 3; ++i) { e->gdim[i] = L.gdim[i]; e->box[i] = bdim[i]; }
     e->gstride[0] = L.gstride[0]; e->gstride[1] = L.gstride[1];
+    e->es = L.es;
     memcpy(e->map, out_map, 128);
     e->valid = true;
   }
@@ -1727,6 +1831,7 @@ int k1_encode_tmap(adell_item& it, const K1Layout& L, const int* box, EncodeTile
 // a driver.  Needs tmap_sign (k1_tmap_layout) and the encoded source box.
 int k1_encode_dst(adell_item& it, const int* T, const int* box, EncodeTiledFn enc) {
   if (k1_tuning().no_tstore) return -1;
+  if (it.src_dtype != ADELL_F32) return -1;   // integer sources are converted by the consumer warps
   if (it.flags & (ADELL_F_CLIP | ADELL_F_PRE_DEV)) return -1;
   if (it.pre_scale != 1.0f || it.pre_offset != 0.0f || it.post_scale != 1.0f || it.post_offset != 0.0f) return -1;
   if (it.tmap_sign[2] * it.grid_sign[2] < 0) return -1;          // a flip along the contiguous axis reverses elements
@@ -1767,8 +1872,9 @@ int k1_encode_copy(adell_item& it, EncodeTiledFn enc) {
   const int n2 = it.out_shape[2] < T[2] ? it.out_shape[2] : T[2];
   const int g0 = it.grid_off[2], g1 = it.grid_off[2] + it.grid_sign[2] * (n2 - 1);
   const int lo = it.tmap_sign[2] > 0 ? (g0 < g1 ? g0 : g1) + it.tmap_off[2] : -(g0 > g1 ? g0 : g1) + it.tmap_off[2];
-  if (lo & 3) {
-    box[2] += 4;
+  const int q = 16 / L.es;
+  if (lo & (q - 1)) {
+    box[2] += q;
     r = k1_encode_tmap(it, L, box, enc);
     if (r <= 0) return r;
   }
@@ -1776,7 +1882,7 @@ int k1_encode_copy(adell_item& it, EncodeTiledFn enc) {
   const int split = k1_encode_dst(it, T, box, enc);
   if (split == -2) return -1;
   it.kind = static_cast<uint8_t>(split < 0 ? ADELL_KIND_VCOPY : ADELL_KIND_TSTORE + split);
-  return box[0] * box[1] * box[2] * 4;
+  return box[0] * box[1] * box[2] * L.es;
 }
 
 // Decides staged-path eligibility for one item and, when eligible, picks its tile shape, encodes
@@ -1785,7 +1891,6 @@ int k1_encode_copy(adell_item& it, EncodeTiledFn enc) {
 int k1_encode_item(adell_item& it, EncodeTiledFn enc, int tile_pref) {
   it.flags &= static_cast<uint8_t>(~ADELL_F_TMAP);
   if (it.flags & ADELL_F_IDENTITY) return 0;
-  if (it.src_dtype != ADELL_F32) return 0;
   if (it.src_stride[2] != 1 && it.src_stride[2] != -1) return 0;
   k1_item_map(it);
   const bool sheared = k1_item_shear(it);
