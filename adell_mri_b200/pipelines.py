@@ -688,54 +688,60 @@ class SSLBatchAugmenter(_BatchBase):
         vol_v = np.tile(np.repeat(np.arange(2), nc), B)
         plan.crop(params["starts"][vol_v, vol_b], self.roi)
         dev = plan.device
-        for v in range(2):
-            choice, draws = params["choice"][v], params["draws"][v]
-            for s in range(self.N):                 # slot s of every sample, member by member
+        ch = np.arange(nc)[None, :]
+        vox = int(np.prod(plan.shape[0]))
+        eye = np.eye(4, dtype=np.float32)
+        for s in range(self.N):
+            # Slot s of every (sample, view): each volume applies exactly ONE member here, so the members of a slot
+            # touch disjoint volumes and collapse into at most one affine / one intensity / one noise record for the
+            # whole batch (the reference runs them one transform call per sample; the order between different
+            # volumes is immaterial).
+            A = np.empty((n, 4, 4), np.float32)
+            A[:] = eye
+            has_aff = np.zeros(n, bool)
+            sc, of, has_int = np.ones(n), np.zeros(n), np.zeros(n, bool)
+            std, seed, off = np.zeros(n, np.float32), np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+            has_phx = np.zeros(n, bool)
+            noise = None
+            for v in range(2):
+                choice, draws = params["choice"][v], params["draws"][v]
                 for mi, m in enumerate(self.members):
                     sel = np.nonzero(choice[:, s] == mi)[0]
                     if sel.size == 0:
                         continue
                     use, vals = draws[m]
-                    pos = np.searchsorted(use, sel)   # index of each selected sample in the member's use list
-                    where = np.zeros(n, bool)
-                    where[(vol_v == v) & np.isin(vol_b, sel)] = True
+                    pos = np.searchsorted(use, sel)                    # index of each selected sample in the member's use list
+                    vidx = (sel[:, None] * 2 + v) * nc + ch            # [len(sel), nc] volume indices (order [b, view, channel])
                     if m in self.views[v].samplers:
-                        A = np.tile(np.eye(4, dtype=np.float32), (n, 1, 1))
-                        for b, q in zip(sel, pos):
-                            A[(vol_b == b) & (vol_v == v)] = vals[q]
-                        plan.affine(A, "bilinear", "zeros", where=where)
+                        A[vidx] = np.asarray(vals)[pos][:, None]
+                        has_aff[vidx] = True
                     elif m == "scale_intensity":
-                        sc = np.ones(n)
-                        for b, q in zip(sel, pos):
-                            sc[(vol_b == b) & (vol_v == v)] = float(np.float32(1 + vals[q]))
-                        plan.intensity(scale=sc, where=where)
+                        sc[vidx] = (1 + np.asarray(vals)[pos]).astype(np.float32)[:, None]
+                        has_int[vidx] = True
                     elif m == "shift_intensity":
-                        of = np.zeros(n)
-                        for b, q in zip(sel, pos):
-                            of[(vol_b == b) & (vol_v == v)] = float(np.float32(vals[q]))
-                        plan.intensity(offset=of, where=where)
-                    else:  # gaussian_noise
-                        if self.noise == "philox":
-                            std, seed, off = np.zeros(n, np.float32), np.zeros(n, np.uint64), np.zeros(n, np.uint64)
-                            vox = int(np.prod(plan.shape[0]))
-                            for b, q in zip(sel, pos):
-                                idx = np.nonzero((vol_b == b) & (vol_v == v))[0]
-                                std[idx], seed[idx] = vals[q][0], vals[q][1]
-                                off[idx] = np.arange(idx.size, dtype=np.uint64) * np.uint64(vox)
-                            plan._close(where & plan._has_noise())
-                            st = plan.st
-                            st.philox_std = np.where(where, std, st.philox_std).astype(np.float32)
-                            st.philox_seed = np.where(where, seed, st.philox_seed).astype(np.uint64)
-                            st.philox_off = np.where(where, off, st.philox_off).astype(np.uint64)
-                        else:
+                        of[vidx] = np.asarray(vals)[pos].astype(np.float32)[:, None]
+                        has_int[vidx] = True
+                    elif self.noise == "philox":
+                        std[vidx] = np.array([vals[q][0] for q in pos], np.float32)[:, None]
+                        seed[vidx] = np.array([vals[q][1] for q in pos], np.uint64)[:, None]
+                        off[vidx] = (np.arange(nc, dtype=np.uint64) * np.uint64(vox))[None, :]
+                        has_phx[vidx] = True
+                    else:
+                        if noise is None:
                             noise = [None] * n
-                            for b, q in zip(sel, pos):
-                                idx = np.nonzero((vol_b == b) & (vol_v == v))[0]
-                                t = torch.from_numpy(vals[q])
-                                t = t.pin_memory().to(dev, non_blocking=True) if dev.type == "cuda" else t
-                                for c, i in enumerate(idx):
-                                    noise[i] = t[c]
-                            plan.add_noise(noise)
+                        for b, q in zip(sel, pos):
+                            t = torch.from_numpy(vals[q])
+                            t = t.pin_memory().to(dev, non_blocking=True) if dev.type == "cuda" else t
+                            for c in range(nc):
+                                noise[int(vidx[0, 0] - sel[0] * 2 * nc + b * 2 * nc) + c] = t[c]
+            if has_aff.any():
+                plan.affine(A, "bilinear", "zeros", where=has_aff)
+            if has_int.any():
+                plan.intensity(scale=sc, offset=of, where=has_int)
+            if has_phx.any():
+                plan.add_philox_noise(std, seed, off, where=has_phx)
+            if noise is not None:
+                plan.add_noise(noise)
         return plan, params
 
     def boxes(self, params, shape):

@@ -497,20 +497,45 @@ class BatchPlan:
     def build_launches(self, dst_ptr: np.ndarray, dst_stride: np.ndarray, alloc):
         """Resolve scratch volumes and return ``[items_array, ...]``, one entry per launch, in
         execution order.  ``alloc(n_elements) -> fp32 tensor`` provides scratch on the plan's device;
-        the returned tensors are appended to ``self.keep``."""
+        the returned tensors are appended to ``self.keep``.
+
+        Closed passes are regrouped by LEVEL: a volume's k-th closed pass goes into launch k, whatever
+        other volumes were closed with it — volumes are independent, only the order of one volume's own
+        passes matters.  A batch whose samples close passes at different moments (the SSL workhorse: every
+        sample draws its own members) then needs as many launches as its deepest chain, not one per
+        ``_close`` call."""
         cur_ptr = self.parent_ptr.copy()
-        launches = []
-        for idx, st, pptr, pstride, pdtype in self.passes:
-            size = st.out_size()
-            offs = np.concatenate([[0], np.cumsum(size.prod(axis=1))])
+        per_level: dict[int, list] = {}
+        if self.passes:
             if alloc is None:
                 raise ValueError("this plan needs scratch volumes (multi-pass) but no allocator was given")
-            buf = alloc(int(offs[-1]))
+            level = np.zeros(self.n, np.int64)
+            # one scratch buffer for all passes; every scratch volume starts on a 256-byte boundary
+            vox = [p[1].out_size().prod(axis=1) for p in self.passes]
+            padded = [(v + 63) // 64 * 64 for v in vox]
+            buf = alloc(int(sum(int(v.sum()) for v in padded)))
             self.keep.append(buf)
-            tptr = (buf.data_ptr() + 4 * offs[:-1]).astype(np.uint64)
-            src_ptr = np.where(pptr != 0, pptr, cur_ptr[idx])
-            launches.append(self._fill_items(st, src_ptr, pstride, pdtype, tptr, _contig_stride(size)))
-            cur_ptr[idx] = tptr
+            base, off = buf.data_ptr(), 0
+            for (idx, st, pptr, pstride, pdtype), pv in zip(self.passes, padded):
+                offs = off + np.concatenate([[0], np.cumsum(pv)])
+                tptr = (base + 4 * offs[:-1]).astype(np.uint64)
+                src_ptr = np.where(pptr != 0, pptr, cur_ptr[idx])
+                items = self._fill_items(st, src_ptr, pstride, pdtype, tptr, _contig_stride(st.out_size()))
+                lv = level[idx]
+                lo, hi = int(lv.min()), int(lv.max())
+                if lo == hi:
+                    per_level.setdefault(lo, []).append(items)
+                else:
+                    for l in range(lo, hi + 1):
+                        m = lv == l
+                        if m.any():
+                            per_level.setdefault(l, []).append(items[m])
+                level[idx] += 1
+                cur_ptr[idx] = tptr
+                off = int(offs[-1])
+        # (concatenated as raw bytes: numpy re-derives a structured dtype on every concatenate)
+        launches = [np.concatenate([x.view(np.uint8) for x in per_level[l]]).view(ITEM_DTYPE) if len(per_level[l]) > 1 else per_level[l][0]
+                    for l in sorted(per_level)]
         launches.append(self._fill_items(self.st, cur_ptr, self.parent_stride, self.parent_dtype,
                                          np.asarray(dst_ptr, np.uint64), np.asarray(dst_stride, np.int64)))
         self.keep.extend(self.st.keep)

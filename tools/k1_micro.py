@@ -29,7 +29,8 @@ dev = torch.device("cuda:0")
 PEAK = 6541.1
 
 
-def seg_items(R, prob, n_batches=4, B=8, shape=(256, 256, 32)):
+def seg_items(R, prob, n_batches=4, B=8, shape=(256, 256, 32), integer=False):
+    """integer=True: int16 image volumes + uint8 mask with a device-side {scale, offset} (config B from raw volumes)."""
     g = torch.Generator(device=dev).manual_seed(0)
     out_img = torch.empty((B, 3, *shape), device=dev)
     out_mask = torch.empty((B, 1, *shape), device=dev)
@@ -43,10 +44,19 @@ def seg_items(R, prob, n_batches=4, B=8, shape=(256, 256, 32)):
             A = geometry.compose_affine(rotate=ang[None])[0]
             fl = R.rand(3) < 0.25
             for k in range(4):
-                vols.append(torch.rand(shape, device=dev, generator=g))
+                if not integer:
+                    vols.append(torch.rand(shape, device=dev, generator=g))
+                elif k < 3:
+                    vols.append(torch.randint(0, 4000, shape, device=dev, generator=g, dtype=torch.int16))
+                else:
+                    vols.append((torch.rand(shape, device=dev, generator=g) > 0.7).to(torch.uint8))
                 mats.append(A); fired.append(f); flips.append(fl)
                 dsts.append(out_img[b, k] if k < 3 else out_mask[b, 0])
         plan = BatchPlan(vols)
+        if integer:
+            pre = torch.tensor([[1.0 / 4000.0, 0.0]] * 3 + [[1.0, 0.0]], device=dev).repeat(B, 1).contiguous()
+            plan.intensity_from_device(pre)
+            keep.append(pre)
         plan.affine(np.stack(mats), (["bilinear"] * 3 + ["nearest"]) * B, "reflection", where=np.array(fired))
         plan.flip(np.stack(flips))
         launches.append(pack(plan, dsts))
@@ -223,6 +233,8 @@ def main():
             L, vox, keep = seg_items(R, 1.0)
         elif name == "seg_copy":
             L, vox, keep = seg_items(R, 0.0)
+        elif name in ("seg_i16", "seg_i16_all", "seg_i16_copy"):
+            L, vox, keep = seg_items(R, {"seg_i16": 0.2, "seg_i16_all": 1.0, "seg_i16_copy": 0.0}[name], integer=True)
         elif name == "ssl":
             L, vox, keep = ssl_items(R)
         elif name == "cls":
