@@ -46,9 +46,9 @@ def test_integer_sources_are_staged_and_match_the_oracle(dtype, shape, padding):
         for mode in ("bilinear", "nearest"):
             ref = M.canonical_item(img, affine=A, mode=mode, padding_mode=padding, post_ops=[("flip", flips)] if flips else [])[0]
             mk = lambda: BatchPlan([img[0].to(DEV)]).affine(A.numpy(), mode, padding).flip(np.array([a in flips for a in range(3)]))
-            # the same path as an fp32 copy of the volume takes (staged wherever the footprint box fits)
+            # staged wherever an fp32 copy of the volume is (i.e. wherever the footprint box fits)
             f32 = BatchPlan([img[0].float().to(DEV)]).affine(A.numpy(), mode, padding).flip(np.array([a in flips for a in range(3)]))
-            assert (_kinds(mk()) == _kinds(f32)).all(), (dtype, shape, mode)
+            assert (_kinds(mk())[_kinds(f32) == KIND_STAGED] == KIND_STAGED).all(), (dtype, shape, mode)   # (smaller elements may fit where fp32 does not)
             if shape == (256, 256, 32):
                 assert (_kinds(mk()) == KIND_STAGED).all(), (dtype, shape, mode)
             out = run_plan_cuda(mk())[0].cpu()
