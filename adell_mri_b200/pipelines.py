@@ -356,8 +356,20 @@ class _BatchBase:
         """One volume per (sample, [view,] key-channel); ``repeat`` > 1 lists each sample's volumes
         that many times (the SSL views share their source)."""
         metas = [self._sample_meta(s, keys) for s in samples]
-        cat = lambda i: np.concatenate([np.tile(m[i], (repeat,) + (1,) * (m[i].ndim - 1)) for m in metas])
-        return BatchPlan.from_arrays(cat(1), cat(2), cat(3), cat(4), metas[0][5][0].device, [m[5] for m in metas],
+        key = ("base", id(samples[0]), id(samples[-1]), len(samples), repeat)
+        hit = self._tmpl_cache.get(key)
+        if hit is not None:
+            for a, b in zip(hit[1], samples):
+                if a is not b:
+                    hit = None
+                    break
+        if hit is None:
+            cat = lambda i: np.concatenate([np.tile(m[i], (repeat,) + (1,) * (m[i].ndim - 1)) for m in metas])
+            if len(self._tmpl_cache) > 256:
+                self._tmpl_cache.clear()
+            hit = self._tmpl_cache[key] = ((cat(1), cat(2), cat(3), cat(4)), list(samples))
+        a1, a2, a3, a4 = hit[0]
+        return BatchPlan.from_arrays(a1, a2, a3, a4, metas[0][5][0].device, [m[5] for m in metas],
                                      fast=self.fast, strict=self.strict), metas
 
     @staticmethod
@@ -580,13 +592,14 @@ class _WorkhorseDraws:
         """``choice``: [B, N] member indices.  Returns per member the samples using it and its
         parameters (matrices / factors / offsets / noise)."""
         out = {}
+        spatial = []   # (member, use, params): composed in ONE call below (absent factors = identity matrices: exact)
         for mi, m in enumerate(self.members):
             use = np.nonzero((choice == mi).any(axis=1))[0]
             if use.size == 0:
                 continue
             if m in self.samplers:
                 _, p = self.samplers[m].draw_batch(use.size, n_keys=self.n_keys)
-                out[m] = (use, geometry.compose_affine(p["rotate"], p["shear"], p["translate"], p["scale"], batch=use.size))
+                spatial.append((m, use, p))
             elif m == "gaussian_noise":
                 self.R_outer[m].random_sample(use.size)
                 vals = []
@@ -603,6 +616,20 @@ class _WorkhorseDraws:
                 u = self.R_inner[m].random_sample(2 * use.size).reshape(-1, 2)[:, 1]   # gate, then uniform(lo, hi)
                 f = self.shift if m == "shift_intensity" else self.scale
                 out[m] = (use, -f + (f - (-f)) * u)
+        if spatial:
+            n = sum(u.size for _, u, _ in spatial)
+            full = {"rotate": np.zeros((n, 3)), "shear": np.zeros((n, 3)), "translate": np.zeros((n, 3)), "scale": np.ones((n, 3))}
+            o = 0
+            for _, use, p in spatial:
+                for name, arr in p.items():
+                    if arr.shape[1]:
+                        full[name][o:o + use.size, : arr.shape[1]] = arr
+                o += use.size
+            mats = geometry.compose_affine(full["rotate"], full["shear"], full["translate"], full["scale"], batch=n)
+            o = 0
+            for m, use, _ in spatial:
+                out[m] = (use, mats[o:o + use.size])
+                o += use.size
         return out
 
 

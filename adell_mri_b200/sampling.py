@@ -121,6 +121,11 @@ class RandAffineSampler:
             names = ("rotate", "shear", "translate", "scale")
             return fired, {k: np.asarray([p[k] for p in plist], np.float64).reshape(len(plist), -1) for k in names}
         fired = self.R.random_sample(batch) < self.prob
+        if fired.all():   # (every call fires, e.g. the workhorse members with prob 1: a fixed stride through the streams)
+            calls = 2 + n_keys
+            self.R_inner.random_sample(batch * (1 + n_keys))
+            u = self.R_grid.random_sample(batch * calls * K).reshape(batch, calls, K) if K else np.zeros((batch, calls, 0))
+            return fired, self._params_from_uniforms(u[:, 1])
         per_key = np.full(batch, n_keys, np.int64) if self.per_key_draws_when_idle else n_keys * fired.astype(np.int64)
         self.R_inner.random_sample(batch + int(per_key.sum()))
         calls = 1 + fired.astype(np.int64) + per_key         # randomize() calls on the grid stream per sample
