@@ -37,8 +37,8 @@ constexpr int K1_CTHREADS = 32 * K1_CWARPS;    // consumer threads
 // The CTA runs K1_GROUPS independent streams: stream p = one producer warp, one hand-over warp and
 // one group of consumer warps, with its own ring stages (p, p + K1_GROUPS, ...) and tile-state slots.
 #define K1_GROUPS 2
-#define K1_NPROD (2 * K1_GROUPS)
-constexpr int K1_THREADS = K1_CTHREADS + 64 * K1_GROUPS;   // consumers + per stream two producer warps (they take alternate tiles)
+#define K1_NPROD K1_GROUPS
+constexpr int K1_THREADS = K1_CTHREADS + 64 * K1_GROUPS;   // consumers + per stream a hand-over and a producer warp
 constexpr int K1_GWARPS = K1_CWARPS / K1_GROUPS;   // warps per group; a warp takes planes di = w, w + K1_GWARPS, ...
 constexpr int K1_GTHREADS = 32 * K1_GWARPS;
 constexpr int K1_T = 16;                       // base tile edge
@@ -68,8 +68,7 @@ __device__ __forceinline__ void k1_wt_store(float4* p, float4 v) { __stwt(p, v);
 #define K1_NV 4                                 // trilinear voxels interleaved per consumer-thread iteration
 #endif
 
-// MODE_DONE: filler of a producer whose queues are drained while its partner still works; MODE_EXIT: both are drained
-enum { MODE_DIRECT = 0, MODE_STAGED = 1, MODE_ZERO = 2, MODE_COPY = 3, MODE_DONE = 4, MODE_TSTORE = 5, MODE_EXIT = 6 };
+enum { MODE_DIRECT = 0, MODE_STAGED = 1, MODE_ZERO = 2, MODE_COPY = 3, MODE_DONE = 4, MODE_TSTORE = 5 };
 
 struct K1Tile {
   int mode;
@@ -1207,12 +1206,11 @@ __device__ unsigned long long k1_prof[16];
 struct K1Walk {
   int prev_tile = -2;      // last tile this producer prepared
   int b0 = 0, b1 = 0, b2 = 0;  // its tile coordinates inside the item
-  int fresh = 0;           // own slots of the ring that already hold the current item's context
-  const K1Ctx* last = nullptr;  // context of the slot this producer prepared last (same item while cached_item holds)
+  int fresh = 0;           // slots of the stream's ring that already hold the current item's context
 };
 __device__ __forceinline__ void k1_prepare(const adell_item* __restrict__ items, const int32_t* ts, int n_items,
                                            int tile, int& item, int& cur_start, int& next_start, int& cached_item,
-                                           K1Slot& sl, uint32_t box_addr, int lane, K1Walk& wk, int ring_slots) {
+                                           K1Ctx& priv, K1Slot& sl, uint32_t box_addr, int lane, K1Walk& wk, int ring_slots) {
   // monotone walk over the per-item tile prefix, 32 entries per step (one load latency per step,
   // not one per item skipped); `ts` is the shared-memory copy of the prefix when it fits
   while (tile >= next_start) {
@@ -1224,35 +1222,33 @@ __device__ __forceinline__ void k1_prepare(const adell_item* __restrict__ items,
     const int nxt = __shfl_sync(0xffffffffu, v, adv & 31);
     next_start = adv < 32 ? nxt : (item + 1 <= n_items ? ts[item + 1] : 0x7fffffff);
   }
-  // The slot's context = the item image (minus the tensor-map bytes, which only the TMA unit reads, from global
-  // memory) + derived constants.  A new item is fetched from global memory straight into the slot; further tiles
-  // of the same item copy the context from the slot this producer filled last, and only while some of its own
-  // slots (visited round-robin) still hold another item's context: an item has hundreds of tiles.
-  constexpr int kItemWords = (sizeof(adell_item) - 128) / 4;
-  constexpr int kWords = (sizeof(K1Ctx) - 128) / 4;
-  uint32_t* dw = reinterpret_cast<uint32_t*>(&sl.ctx) + 32;
+  constexpr int kItemWords = (sizeof(adell_item) - 128) / 4;  // without the tensor map
+  uint32_t* pw = reinterpret_cast<uint32_t*>(&priv) + 32;
   const bool new_item = item != cached_item;
   if (new_item) {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(items + item) + 32;
 #pragma unroll
     for (int w = 0; w < (kItemWords + 31) / 32; ++w)
-      if (w * 32 + lane < kItemWords) dw[w * 32 + lane] = __ldg(src + w * 32 + lane);
+      if (w * 32 + lane < kItemWords) pw[w * 32 + lane] = __ldg(src + w * 32 + lane);
     __syncwarp();
-    if (lane == 0) k1_ctx_finish(sl.ctx);
+    if (lane == 0) k1_ctx_finish(priv);
     __syncwarp();
     cached_item = item;
-    wk.fresh = 1;
-  } else if (wk.fresh < ring_slots) {
-    const uint32_t* pw = reinterpret_cast<const uint32_t*>(wk.last) + 32;
+    wk.fresh = 0;
+  }
+  // whole K1Ctx (item image + derived constants), minus the unused tensor-map bytes — only while some
+  // slot of the ring (visited round-robin) still holds another item's context: an item has hundreds of tiles
+  if (wk.fresh < ring_slots) {
+    constexpr int kWords = (sizeof(K1Ctx) - 128) / 4;
+    uint32_t* dw = reinterpret_cast<uint32_t*>(&sl.ctx) + 32;
 #pragma unroll
     for (int w = 0; w < (kWords + 31) / 32; ++w)
       if (w * 32 + lane < kWords) dw[w * 32 + lane] = pw[w * 32 + lane];
     ++wk.fresh;
     __syncwarp();
   }
-  wk.last = &sl.ctx;
   // tile coordinates inside the item: the successor of the previous tile by carries, else two divisions
-  const int n1 = sl.ctx.it.n_tiles[1], n2 = sl.ctx.it.n_tiles[2];
+  const int n1 = priv.it.n_tiles[1], n2 = priv.it.n_tiles[2];
   if (!new_item && tile == wk.prev_tile + 1 && tile > cur_start) {
     if (++wk.b2 == n2) { wk.b2 = 0; if (++wk.b1 == n1) { wk.b1 = 0; ++wk.b0; } }
   } else {
@@ -1286,39 +1282,32 @@ __device__ __forceinline__ void k1_fix_columns(float* box, const K1Tile& tl, int
 }
 
 // Persistent, warp-specialised, dynamically scheduled.  One CTA per SM runs K1_GROUPS independent
-// streams.  A stream is a ring of tile positions n = 0, 1, 2, ...: position n uses ring stage n % S
-// (S = n_stages / K1_GROUPS; full / empty / landed mbarriers each) and tile-state slot n % L.  Two
-// producer warps serve a stream, taking ALTERNATE positions (warp `sub` the positions n = sub mod 2):
-// each pulls its own chunks of `chunk` consecutive tiles from a global queue (an atomic counter in the
-// caller's launch buffer: SMs that run faster simply take more chunks, so no SM idles at the tail),
-// derives the tile state, waits for the stage to be released, issues ONE TMA box load, waits for it to
-// land, zeroes alignment-slack columns (or sends a plain copy tile straight back out through the
-// destination tensor map) and hands the stage to the stream's K1_GWARPS consumer warps.  Round 1 had one
-// producer (+ one warp that only handed stages over) per stream: its ~8 000 cycles of set-up per tile —
-// one warp's worth of dependent instructions — matched the consumers' ~10 000 cycles of a full tile and
-// exceeded those of every partial tile, so the consumers waited 16 % of the time; two warps halve it.
-// L is even and >= S + 2: a producer owns the slots of its parity and may fill the next one while the
-// consumers still read the S tiles in flight.  With a single stage per stream (S == 1: staged boxes over
-// ~55 KB) one producer serves every position.
-// End of a stream: a producer whose queues are drained sets its `fin` flag and emits MODE_DONE fillers
-// until it sees its partner's flag, then MODE_EXIT; the consumers leave after the EXIT of every producer
-// (no position of a producer is waited for after its EXIT).
-__device__ __forceinline__ int k1_slots_per_stream(int S) { return (S + 3) & ~1; }
+// streams.  Stream p: its producer warp pulls chunks of `chunk` consecutive tiles from a global queue
+// (an atomic counter in the caller's launch buffer: SMs that run faster simply take more chunks, so
+// no SM idles at the tail), prepares the tile state and issues one TMA box load per tile into the
+// stream's next free ring stage; its hand-over warp sits between the TMA completion and the
+// consumers (alignment-slack columns); its K1_GWARPS consumer warps produce the voxels.  Per stream:
+// n_stages / K1_GROUPS ring stages (full / empty / landed mbarriers each) and one more tile-state
+// slot than stages, so set-up never waits for shared-memory space.  A tile with mode MODE_DONE ends
+// the stream.
+struct K1Ring {
+  int n, i, phase;   // stages (or slots) of the stream, position, phase bit of the current lap
+  __device__ __forceinline__ void init(int n_) { n = n_; i = 0; phase = 0; }
+  __device__ __forceinline__ void next() { if (++i == n) { i = 0; phase ^= 1; } }
+};
 
 __global__ void __launch_bounds__(K1_THREADS, 1)
 k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile_start, int n_items, int total_tiles,
           int n_stages, int stage_bytes, int chunk, int n_big_r, int n_big_c, int first_copy,
           unsigned int* __restrict__ sched) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int S = n_stages / K1_GROUPS;          // ring stages per stream
-  const int L = k1_slots_per_stream(S);        // tile-state slots per stream
-  const int np = S >= 2 ? 2 : 1;               // producers that serve a stream
+  const int n_slots = n_stages + K1_GROUPS;
   K1Slot* slots = reinterpret_cast<K1Slot*>(smem + static_cast<size_t>(n_stages) * stage_bytes);
-  uint64_t* full = reinterpret_cast<uint64_t*>(slots + K1_GROUPS * L);
+  K1Ctx* priv = reinterpret_cast<K1Ctx*>(slots + n_slots);   // the producers' private item copies
+  uint64_t* full = reinterpret_cast<uint64_t*>(priv + K1_GROUPS);
   uint64_t* empty = full + n_stages;
-  uint64_t* landed = empty + n_stages;   // TMA completion, seen by the issuing producer
-  volatile int* fin = reinterpret_cast<volatile int*>(landed + n_stages);   // [K1_GROUPS][2]: that producer's queues are drained
-  int32_t* ts_s = reinterpret_cast<int32_t*>(landed + n_stages) + 2 * K1_GROUPS;
+  uint64_t* landed = empty + n_stages;   // TMA completion, seen by the hand-over warp first
+  int32_t* ts_s = reinterpret_cast<int32_t*>(landed + n_stages);
   const bool ts_cached = n_items + 1 <= K1_TS_CACHE;
   if (ts_cached)
     for (int i = threadIdx.x; i <= n_items; i += K1_THREADS) ts_s[i] = __ldg(tile_start + i);
@@ -1329,7 +1318,6 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(empty + s)), "r"(K1_GWARPS));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(landed + s)), "r"(1));
     }
-    for (int i = 0; i < 2 * K1_GROUPS; ++i) fin[i] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -1337,34 +1325,31 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
   const int warp = threadIdx.x >> 5;
   // stream of this warp, its stages p, p + K1_GROUPS, ... and slots p, p + K1_GROUPS, ...
   const int strm = warp < K1_CWARPS ? warp / K1_GWARPS : (warp - K1_CWARPS) % K1_GROUPS;
+  K1Ring rs, rl;
+  rs.init(n_stages / K1_GROUPS);
+  rl.init(n_slots / K1_GROUPS);
 
-  if (warp >= K1_CWARPS) {
-    // ------------------------------------------------------------------ producer `sub` of stream `strm`
-    const int sub = (warp - K1_CWARPS) / K1_GROUPS;
-    if (sub >= np) return;
+  if (warp >= K1_CWARPS + K1_GROUPS) {
+    // ------------------------------------------------------------------ producer warp of stream `strm`
     int item = 0, cached_item = -1, cur_start = 0;
     int next_start = ts[1];
-    int acq_item = -1;                  // item whose source tensor map this warp acquired last
-    int acq_dst = -1;                   // item whose destination tensor map this warp acquired last
+    int acq_item = -1;                  // item whose tensor map this warp acquired last
     int64_t cur = 0, cur_end = 0;       // tiles left of the current chunk
     // Two queues: 0 = tiles of resampled / generic items [0, first_copy), 1 = tiles of box-copy items
     // [first_copy, total).  Stream 0 drains the resampled queue first, stream 1 the copy queue, each
     // moving on to the other queue when its own is empty: most of the time an SM then works on a
     // compute-bound and a memory-bound tile at once instead of all SMs going through the same phases.
     int q = strm & 1;
-    bool switched = false, drained = false;
+    bool switched = false;
     K1Walk wk;
     const bool idle = (chunk >> 16) == strm + 1;   // measurement aid (ADELL_K1_IDLE_STREAM)
     chunk &= 0xffff;
-    const int own_slots = L / np;
     K1_PROF_DECL
-    for (int n = sub;; n += np) {
-      const int si = n % S, ph = (n / S) & 1;      // stage of this position and the phase bit of its lap
-      const int stage = strm + K1_GROUPS * si, slot = strm + K1_GROUPS * (n % L);
-      uint8_t* box = smem + static_cast<size_t>(stage) * stage_bytes;
+    for (;; rs.next(), rl.next()) {
+      const int stage = strm + K1_GROUPS * rs.i, slot = strm + K1_GROUPS * rl.i;
       K1_PROF_T0
-      while (!drained && cur >= cur_end) {          // next unit from the current queue, or from the other one
-        if (idle) { drained = true; break; }
+      while (cur >= cur_end) {          // next unit from the current queue, or from the other one
+        if (idle) { cur = cur_end = total_tiles; break; }
         unsigned int c = 0;
         if (lane == 0) c = atomicAdd(sched + q, 1u);
         c = __shfl_sync(0xffffffffu, c, 0);
@@ -1375,102 +1360,101 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
         else { cur = lo + static_cast<int64_t>(nb) * chunk + (c - nb); cur_end = cur + 1; }
         cur_end = min(cur_end, hi);
         if (cur < hi) break;
-        if (switched) { drained = true; break; }             // both queues drained
+        if (switched) { cur = cur_end = total_tiles; break; }   // both queues drained
         switched = true;
         q ^= 1;
         item = 0; cur_start = 0; next_start = ts[1];            // the other queue's tiles may lie behind: restart the walk
-        cached_item = -1;
         cur = cur_end = 0;
       }
-      if (drained) {
-        // filler until the partner is drained as well, then the end-of-stream marker
+      if (cur >= total_tiles || cur >= cur_end) {         // queues drained: end-of-stream marker
+        if (lane == 0) slots[slot].tl.mode = MODE_DONE;
         __syncwarp();
-        int both = 1;
-        if (lane == 0) {
-          fin[strm * 2 + sub] = 1;
-          __threadfence_block();
-          both = np == 1 ? 1 : fin[strm * 2 + (sub ^ 1)];
-          slots[slot].tl.mode = both ? MODE_EXIT : MODE_DONE;
-        }
-        both = __shfl_sync(0xffffffffu, both, 0);
-        __syncwarp();
-        mbar_wait_relaxed(empty + stage, ph ^ 1);
-        if (lane == 0) { mbar_arrive(landed + stage); mbar_arrive(full + stage); }   // every position completes one lap of each barrier
-        if (both) break;
-        continue;
+        mbar_wait_relaxed(empty + stage, rs.phase ^ 1);
+        if (lane == 0) mbar_arrive(landed + stage);
+        break;
       }
       const int tile = static_cast<int>(cur++);
-      // safe to overwrite: this producer owns the slots of its parity, L >= S + 2, and its previous issue
-      // waited for the release of the stage of the tile S positions before that one
-      k1_prepare(items, ts, n_items, tile, item, cur_start, next_start, cached_item, slots[slot],
-                 smem_u32(box), lane, wk, own_slots);
+      // safe to overwrite: the stream has one more slot than stages, and this warp's previous issue
+      // waited for the release of the stage of the slot's previous tile
+      k1_prepare(items, ts, n_items, tile, item, cur_start, next_start, cached_item, priv[strm], slots[slot],
+                 smem_u32(smem + static_cast<size_t>(stage) * stage_bytes), lane, wk, rl.n);
       K1_PROF_ADD(2)
-      mbar_wait_relaxed(empty + stage, ph ^ 1);
+      mbar_wait_relaxed(empty + stage, rs.phase ^ 1);
       K1_PROF_ADD(0)
-      const K1Slot& sl = slots[slot];
-      const int mode = sl.tl.mode;
-      const bool loads = mode == MODE_STAGED || mode == MODE_COPY || mode == MODE_TSTORE;   // tiles with a TMA box load
       if (lane == 0) {
-        if (loads) {
+        const K1Slot& sl = slots[slot];
+        if (sl.tl.mode == MODE_STAGED || sl.tl.mode == MODE_COPY || sl.tl.mode == MODE_TSTORE) {  // tiles with a TMA box load
           const int mo0 = sl.ctx.it.tmap_off[0] - sl.tl.mconst[0], mo1 = sl.ctx.it.tmap_off[1] - sl.tl.mconst[1],
                     mo2 = sl.ctx.it.tmap_off[2] - sl.tl.mconst[2];
           if (sl.tl.item != acq_item) { tmap_acquire(items[sl.tl.item].tmap); acq_item = sl.tl.item; }
           mbar_expect_tx(landed + stage, static_cast<uint32_t>(sl.tl.box[0] * sl.tl.box[1] * sl.tl.box[2]) * k1_es(sl.ctx.it.src_dtype));
-          tma_load_3d(box, items[sl.tl.item].tmap, landed + stage, mo2, mo1, mo0);
+          tma_load_3d(smem + static_cast<size_t>(stage) * stage_bytes, items[sl.tl.item].tmap, landed + stage, mo2, mo1, mo0);
         } else {
-          mbar_arrive(landed + stage);   // every position completes one lap of each barrier
+          mbar_arrive(landed + stage);
         }
       }
       __syncwarp();
       K1_PROF_ADD(1)
-      if (loads) {
-        mbar_wait_relaxed(landed + stage, ph);
-        const K1Tile& tl = sl.tl;
-        if (mode == MODE_STAGED && tl.fix_hi > tl.fix_lo)
-          k1_fix_columns(reinterpret_cast<float*>(box), tl, lane, sl.ctx.it.src_dtype);
-        if (mode == MODE_TSTORE) {
-          // Plain copy tile: the box that just landed goes straight back out through the destination tensor
-          // map — no consumer instructions, no LSU traffic.  The box is in SOURCE memory order: an axis whose
-          // net direction is reversed (a flip) is stored slice by slice to the mirrored coordinate (planes for
-          // axis 0, rows for axis 1; the item's map was encoded with that box shape: kind - ADELL_KIND_TSTORE).
-          const adell_item& it = sl.ctx.it;
-          if (tl.item != acq_dst) { tmap_acquire(items[tl.item].dmap); acq_dst = tl.item; }
-          const void* dmap = items[tl.item].dmap;
-          const uint32_t base = smem_u32(box);
-          const int split = it.kind - ADELL_KIND_TSTORE;
-          const int n0 = min(tl.T[0], it.out_shape[0] - tl.o0[0]), n1 = min(tl.T[1], it.out_shape[1] - tl.o0[1]);
-          const bool r0 = tl.msign[0] * it.grid_sign[0] < 0, r1 = tl.msign[1] * it.grid_sign[1] < 0;
-          const uint32_t row = static_cast<uint32_t>(tl.box[2]) * 4u, plane = row * static_cast<uint32_t>(tl.box[1]);
-          bool issued = false;
-          if (split == 0) {
-            if (lane == 0) { tma_store_3d(dmap, base, tl.o0[2], tl.o0[1], tl.o0[0]); issued = true; }
-          } else if (split == 1) {
-            if (lane < n0) {
-              const int b0 = r0 ? n0 - 1 - lane : lane;
-              tma_store_3d(dmap, base + b0 * plane, tl.o0[2], tl.o0[1], tl.o0[0] + lane);
-              issued = true;
-            }
-          } else {
-            for (int idx = lane; idx < n0 * n1; idx += 32) {
-              const int d0 = idx / n1, d1 = idx - d0 * n1;
-              const int b0 = r0 ? n0 - 1 - d0 : d0, b1 = r1 ? n1 - 1 - d1 : d1;
-              tma_store_3d(dmap, base + b0 * plane + b1 * row, tl.o0[2], tl.o0[1] + d1, tl.o0[0] + d0);
-              issued = true;
-            }
-          }
-          if (issued) { tma_store_commit(); tma_store_wait_read(); }
-        }
-        __syncwarp();
-      }
-      if (lane == 0) mbar_arrive(full + stage);
     }
-    tma_store_wait_all();   // every store of this warp is complete before the kernel ends
     // the last producer of the grid to drain the queue re-arms it for the next launch of this buffer
     if (lane == 0) {
       const unsigned int done = atomicAdd(sched + 2, 1u);
-      if (done == static_cast<unsigned int>(np * K1_GROUPS) * gridDim.x - 1) { sched[0] = 0u; sched[1] = 0u; sched[2] = 0u; }
+      if (done == K1_GROUPS * gridDim.x - 1) { sched[0] = 0u; sched[1] = 0u; sched[2] = 0u; }
     }
     K1_PROF_FLUSH
+    return;
+  }
+
+  if (warp >= K1_CWARPS) {
+    // ------------------------------------------------------------------ hand-over warp of stream `strm`
+    // Sits between the TMA completion (landed) and the consumers (full): zeroes the alignment-slack
+    // columns of boxes that have any (crop windows that start mid-row), off the producer's path, so
+    // that the producer never waits for a load to land.
+    int acq_dst = -1;   // item whose destination tensor map this warp acquired last
+    for (;; rs.next(), rl.next()) {
+      const int stage = strm + K1_GROUPS * rs.i, slot = strm + K1_GROUPS * rl.i;
+      mbar_wait_relaxed(landed + stage, rs.phase);
+      const K1Tile& tl = slots[slot].tl;
+      const int mode = tl.mode;
+      if (mode == MODE_STAGED && tl.fix_hi > tl.fix_lo)
+        k1_fix_columns(reinterpret_cast<float*>(smem + static_cast<size_t>(stage) * stage_bytes), tl, lane, slots[slot].ctx.it.src_dtype);
+      if (mode == MODE_TSTORE) {
+        // Plain copy tile: the box that just landed goes straight back out through the destination tensor
+        // map — no consumer instructions, no LSU traffic.  The box is in SOURCE memory order: an axis whose
+        // net direction is reversed (a flip) is stored slice by slice to the mirrored coordinate (planes for
+        // axis 0, rows for axis 1; the item's map was encoded with that box shape: kind - ADELL_KIND_TSTORE).
+        const adell_item& it = slots[slot].ctx.it;
+        if (tl.item != acq_dst) { tmap_acquire(items[tl.item].dmap); acq_dst = tl.item; }
+        const void* dmap = items[tl.item].dmap;
+        const uint32_t base = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+        const int split = it.kind - ADELL_KIND_TSTORE;
+        const int n0 = min(tl.T[0], it.out_shape[0] - tl.o0[0]), n1 = min(tl.T[1], it.out_shape[1] - tl.o0[1]);
+        const bool r0 = tl.msign[0] * it.grid_sign[0] < 0, r1 = tl.msign[1] * it.grid_sign[1] < 0;
+        const uint32_t row = static_cast<uint32_t>(tl.box[2]) * 4u, plane = row * static_cast<uint32_t>(tl.box[1]);
+        bool issued = false;
+        if (split == 0) {
+          if (lane == 0) { tma_store_3d(dmap, base, tl.o0[2], tl.o0[1], tl.o0[0]); issued = true; }
+        } else if (split == 1) {
+          if (lane < n0) {
+            const int b0 = r0 ? n0 - 1 - lane : lane;
+            tma_store_3d(dmap, base + b0 * plane, tl.o0[2], tl.o0[1], tl.o0[0] + lane);
+            issued = true;
+          }
+        } else {
+          for (int idx = lane; idx < n0 * n1; idx += 32) {
+            const int d0 = idx / n1, d1 = idx - d0 * n1;
+            const int b0 = r0 ? n0 - 1 - d0 : d0, b1 = r1 ? n1 - 1 - d1 : d1;
+            tma_store_3d(dmap, base + b0 * plane + b1 * row, tl.o0[2], tl.o0[1] + d1, tl.o0[0] + d0);
+            issued = true;
+          }
+        }
+        if (issued) { tma_store_commit(); tma_store_wait_read(); }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full + stage);
+      if (mode == MODE_DONE) break;
+    }
+    tma_store_wait_all();   // every store of this warp is complete before the kernel ends
     return;
   }
 
@@ -1479,29 +1463,17 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
 #ifdef K1_PROFILE
   const long long _tstart = clock64();
 #endif
-  int exited = np == 1 ? 2 : 0;   // bit p: producer p of this stream has sent its MODE_EXIT
-  for (int n = 0;; ++n) {
-    const int prod = np == 2 ? (n & 1) : 0;      // the producer that serves this position
-    if ((exited >> prod) & 1) continue;          // no position of an exited producer is waited for
-    const int si = n % S;
-    const int stage = strm + K1_GROUPS * si, slot = strm + K1_GROUPS * (n % L);
+  for (;; rs.next(), rl.next()) {
+    const int stage = strm + K1_GROUPS * rs.i, slot = strm + K1_GROUPS * rl.i;
     K1_PROF_T0
-    mbar_wait(full + stage, (n / S) & 1);
+    mbar_wait(full + stage, rs.phase);
     K1_PROF_ADD(3)
     const K1Ctx& ctx = slots[slot].ctx;
     const K1Tile& tl = slots[slot].tl;
     const float* box = reinterpret_cast<const float*>(smem + static_cast<size_t>(stage) * stage_bytes);
     const adell_item& it = ctx.it;
     const int mode = tl.mode;
-    if (mode == MODE_DONE || mode == MODE_EXIT) {
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty + stage);
-      if (mode == MODE_EXIT) {
-        exited |= 1 << prod;
-        if (exited == 3) break;
-      }
-      continue;
-    }
+    if (mode == MODE_DONE) break;
     if (mode == MODE_COPY) {
       if (it.src_dtype == ADELL_F32) k1_tile_copy_box<ADELL_F32>(ctx, tl, box);
       else if (it.src_dtype == ADELL_I16) k1_tile_copy_box<ADELL_I16>(ctx, tl, box);
@@ -1551,17 +1523,11 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
 
 // Shared-memory plan of the persistent CTA: ring stages (box + tile state + 3 mbarriers each) next to
 // the fixed part (extra tile-state slots and item copies of the producers, barriers, tile prefix).
-// fixed part for n_stages ring stages: the tile-state slots beyond one per stage (L - S per stream), the
-// producers' `fin` flags, barrier slack, the tile prefix
-int k1_host_slots_per_stream(int S) { return (S + 3) & ~1; }
-int k1_smem_fixed(int n_stages) {
-  const int S = n_stages / K1_GROUPS;
-  return K1_GROUPS * (k1_host_slots_per_stream(S) - S) * static_cast<int>(sizeof(K1Slot)) + 64 + 8 * K1_GROUPS + K1_TS_CACHE * 4;
-}
+int k1_smem_fixed() { return K1_GROUPS * static_cast<int>(sizeof(K1Slot) + sizeof(K1Ctx)) + 64 + K1_TS_CACHE * 4; }
 int k1_smem_per_stage(int stage_bytes) { return stage_bytes + static_cast<int>(sizeof(K1Slot)) + 24; }
 // largest box that still leaves room for four ring stages (two per stream: one at work, one in flight)
 int k1_pref_box_bytes() {
-  const int b = ((K1_SMEM_BUDGET - k1_smem_fixed(4)) / 4 - static_cast<int>(sizeof(K1Slot)) - 24) & ~127;
+  const int b = ((K1_SMEM_BUDGET - k1_smem_fixed()) / 4 - static_cast<int>(sizeof(K1Slot)) - 24) & ~127;
   return b < K1_MAX_BOX_BYTES ? b : K1_MAX_BOX_BYTES;
 }
 
@@ -2106,10 +2072,12 @@ extern "C" int adell_aug_gather(const adell_item* items_dev, const int32_t* tile
   // ring of staged boxes: as many stages as fit next to the per-stage tile state
   const int stage_bytes = (info->smem_bytes + 127) & ~127;
   const int per_stage = k1_smem_per_stage(stage_bytes);
-  int n_stages = K1_MAX_STAGES - K1_MAX_STAGES % K1_GROUPS;   // the same number of stages for every stream
-  while (n_stages >= K1_GROUPS && n_stages * per_stage + k1_smem_fixed(n_stages) > K1_SMEM_BUDGET) n_stages -= K1_GROUPS;
+  const int fixed = k1_smem_fixed();
+  int n_stages = (K1_SMEM_BUDGET - fixed) / per_stage;
+  if (n_stages > K1_MAX_STAGES) n_stages = K1_MAX_STAGES;
+  n_stages -= n_stages % K1_GROUPS;  // the same number of stages for every stream
   if (n_stages < K1_GROUPS) return ADELL_ERR_BAD_ARG;
-  const int smem = n_stages * per_stage + k1_smem_fixed(n_stages);
+  const int smem = n_stages * per_stage + fixed;
   e = cudaFuncSetAttribute(k1_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BUDGET);
   if (e != cudaSuccess) { (void)cudaGetLastError(); return adell_map_cuda_error(e); }
   // consecutive tiles a producer takes from the queue at a time (they share the item and neighbouring
