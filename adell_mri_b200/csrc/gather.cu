@@ -86,7 +86,20 @@ struct K1Tile {
   int all_valid;    // every tap of the tile lies inside the valid source region
   int fix_lo, fix_hi;  // box columns [fix_lo, fix_hi) along axis 2 hold bytes that precede the valid
                        // source box (16-byte alignment slack of the tensor map): zeroed after the load
+  int next_plane;      // staged tiles: the next plane di to hand out (the group's warps draw planes from this
+                       // counter instead of owning fixed ones: see k1_next_plane)
 };
+
+// Planes of a staged tile are handed out dynamically: a warp takes the next plane from a shared-memory counter
+// when it has finished one.  With fixed planes (w, w + 8) the warps of a group finished a tile up to a plane's
+// worth of time apart — partial tiles and sheared column groups leave some planes (nearly) empty — and since a
+// stream has only two or three stages in flight, the fastest warp ran into the ring's limit and waited for the
+// slowest: 16 % of the consumer cycles (k1_micro --prof, wait-full).
+__device__ __forceinline__ int k1_next_plane(const K1Tile& tl) {
+  int di = 0;
+  if ((threadIdx.x & 31) == 0) di = atomicAdd(const_cast<int*>(&tl.next_plane), 1);
+  return __shfl_sync(0xffffffffu, di, 0);
+}
 
 // ------------------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -461,7 +474,8 @@ __device__ __forceinline__ bool k1_lane_map(const K1Fast& f, K1Map& m) {
   const int lane = threadIdx.x & 31;
   if (n.w == 32) { m.dk = lane; m.jj = 0; m.jstep = 1; }
   else { m.dk = lane & 15; m.jj = lane >> 4; m.jstep = 2; }
-  if (m.dk >= n.z) return false;
+  const bool in_row = m.dk < n.z;
+  if (!in_row) m.dk = 0;   // (lanes beyond the row stay in the loops — the plane counter is drawn warp-wide — with no voxels)
   m.e = *reinterpret_cast<const float4*>(f.eg[m.dk >> 3]);
   const int sh = __float_as_int(m.e.w);
   m.s0 = sh & 0xffff;
@@ -469,7 +483,7 @@ __device__ __forceinline__ bool k1_lane_map(const K1Fast& f, K1Map& m) {
   const int4 lim = f.lim;
   m.jlo = max(0, lim.z + m.s1); m.jhi = min(n.y, lim.w + m.s1);
   m.j0 = m.jlo + ((m.jj - m.jlo) & (m.jstep - 1));
-  m.cnt = m.jhi > m.j0 ? (m.jhi - m.j0 + m.jstep - 1) / m.jstep : 0;
+  m.cnt = (in_row && m.jhi > m.j0) ? (m.jhi - m.j0 + m.jstep - 1) / m.jstep : 0;
   return m.cnt > 0;
 }
 // per plane di: false when the plane's row of this lane lies outside the output
@@ -536,9 +550,9 @@ __device__ __forceinline__ float k1_lerp8(const K1Vox& x, const float* t) {
 // asm so ptxas keeps them batched); no per-voxel bounds checks — a thread's voxel count is split
 // into full groups and a one-at-a-time tail.
 template <int NV, int RMASK, int DT>
-__device__ __forceinline__ void k1_tile_staged_trilinear_scalar(const K1Fast& f) {
+__device__ __forceinline__ void k1_tile_staged_trilinear_scalar(const K1Tile& tl, const K1Fast& f) {
   K1Map m;
-  if (!k1_lane_map(f, m)) return;
+  k1_lane_map(f, m);   // lanes without voxels: cnt == 0
   K1Hot<RMASK> h;
   k1_hot_load<RMASK>(h, f);
   constexpr uint32_t ES = K1Es<DT>::v;
@@ -548,7 +562,9 @@ __device__ __forceinline__ void k1_tile_staged_trilinear_scalar(const K1Fast& f)
   const float fstep = static_cast<float>(m.jstep);
   const int T0 = f.n.x;
 #pragma unroll 1
-  for (int di = (threadIdx.x >> 5) % K1_GWARPS; di < T0; di += K1_GWARPS) {
+  for (;;) {
+    const int di = k1_next_plane(tl);
+    if (di >= T0) break;
     if (!k1_plane_map(f, m, di)) continue;
     k1_hot_plane<RMASK>(h, f, di, m.dk, m.e);
     float* p = f.dst + m.ii * f.ds0 + m.dk * f.ds2 + (m.j0 - m.s1) * ds1;
@@ -667,9 +683,9 @@ __device__ __forceinline__ k1_f2 tap_pair(uint32_t aA, uint32_t aB) {
 }
 
 template <int NP, int RMASK, int DT>
-__device__ __forceinline__ void k1_tile_staged_trilinear(const K1Fast& f) {
+__device__ __forceinline__ void k1_tile_staged_trilinear(const K1Tile& tl, const K1Fast& f) {
   K1Map m;
-  if (!k1_lane_map(f, m)) return;
+  k1_lane_map(f, m);   // lanes without voxels: cnt == 0
   K1Hot<RMASK> h;
   k1_hot_load<RMASK>(h, f);
   constexpr uint32_t ES = K1Es<DT>::v;
@@ -691,7 +707,9 @@ __device__ __forceinline__ void k1_tile_staged_trilinear(const K1Fast& f) {
     WB2 = f2_dup(h.wb); PO2 = f2_dup(h.po);
   }
 #pragma unroll 1
-  for (int di = (threadIdx.x >> 5) % K1_GWARPS; di < T0; di += K1_GWARPS) {
+  for (;;) {
+    const int di = k1_next_plane(tl);
+    if (di >= T0) break;
     if (!k1_plane_map(f, m, di)) continue;
     k1_hot_plane<RMASK>(h, f, di, m.dk, m.e);
 #pragma unroll
@@ -748,7 +766,7 @@ template <int RMASK, int DT>
 __device__ __forceinline__ void k1_tile_staged_nearest(const K1Ctx& c, const K1Tile& tl, const K1Fast& f, const float* __restrict__ box) {
   constexpr uint32_t ES = K1Es<DT>::v;
   K1Map m;
-  if (!k1_lane_map(f, m)) return;
+  k1_lane_map(f, m);   // lanes without voxels: cnt == 0
   K1Hot<RMASK> h;
   k1_hot_load<RMASK>(h, f);
   const float tie = f.rb.w;
@@ -756,7 +774,9 @@ __device__ __forceinline__ void k1_tile_staged_nearest(const K1Ctx& c, const K1T
   const int64_t pstep = m.jstep * ds1;
   const int T0 = f.n.x;
 #pragma unroll 1
-  for (int di = (threadIdx.x >> 5) % K1_GWARPS; di < T0; di += K1_GWARPS) {
+  for (;;) {
+    const int di = k1_next_plane(tl);
+    if (di >= T0) break;
     if (!k1_plane_map(f, m, di)) continue;
     k1_hot_plane<RMASK>(h, f, di, m.dk, m.e);
     float* p = f.dst + m.ii * f.ds0 + m.dk * f.ds2 + (m.j0 - m.s1) * ds1;
@@ -789,7 +809,7 @@ __device__ __forceinline__ void k1_tile_staged_nearest(const K1Ctx& c, const K1T
 // arithmetic as the plain loops, one voxel at a time, out of line.
 __device__ __noinline__ void k1_tile_staged_cold(const K1Ctx& c, const K1Tile& tl, const K1Fast& f, const float* __restrict__ box) {
   K1Map m;
-  if (!k1_lane_map(f, m)) return;
+  k1_lane_map(f, m);   // lanes without voxels: cnt == 0
   const int dk = m.dk;
   K1Hot<2> h;
   k1_hot_load<2>(h, f);
@@ -801,7 +821,9 @@ __device__ __noinline__ void k1_tile_staged_cold(const K1Ctx& c, const K1Tile& t
   const int4 vlo = f.vlo, vhi = f.vhi, fl = f.fl;
   const float4 gb = f.gb;
   const int T0 = f.n.x;
-  for (int di = (threadIdx.x >> 5) % K1_GWARPS; di < T0; di += K1_GWARPS) {
+  for (;;) {
+    const int di = k1_next_plane(tl);
+    if (di >= T0) break;
     if (!k1_plane_map(f, m, di)) continue;
     k1_hot_plane<2>(h, f, di, dk, m.e);
     int dj = m.j0;
@@ -846,10 +868,10 @@ __device__ __forceinline__ void k1_staged_plain_body(const K1Ctx& ctx, const K1T
     else if (rm == 3) k1_tile_staged_nearest<3, DT>(ctx, tl, f, box);
     else k1_tile_staged_nearest<2, DT>(ctx, tl, f, box);
   } else {
-    if (rm == 0) k1_tile_staged_trilinear<K1_NP, 0, DT>(f);
-    else if (rm == 1) k1_tile_staged_trilinear<K1_NP, 1, DT>(f);
-    else if (rm == 3) k1_tile_staged_trilinear<K1_NP, 3, DT>(f);
-    else k1_tile_staged_trilinear_scalar<K1_NV, 2, DT>(f);
+    if (rm == 0) k1_tile_staged_trilinear<K1_NP, 0, DT>(tl, f);
+    else if (rm == 1) k1_tile_staged_trilinear<K1_NP, 1, DT>(tl, f);
+    else if (rm == 3) k1_tile_staged_trilinear<K1_NP, 3, DT>(tl, f);
+    else k1_tile_staged_trilinear_scalar<K1_NV, 2, DT>(tl, f);
   }
 }
 template <int DT>
@@ -1259,7 +1281,7 @@ __device__ __forceinline__ void k1_prepare(const adell_item* __restrict__ items,
   }
   wk.prev_tile = tile;
   k1_tile_setup(sl.ctx, sl, wk.b0, wk.b1, wk.b2, box_addr, lane);
-  if (lane == 0) sl.tl.item = item;
+  if (lane == 0) { sl.tl.item = item; sl.tl.next_plane = 0; }
   __syncwarp();
 }
 
