@@ -116,7 +116,7 @@ class _Stage:
 
     _ARR = (
         "has_affine", "A", "interp", "padding", "pre_s", "pre_o", "clip", "clip_lo", "clip_hi",
-        "post_s", "post_o", "noise_ptr", "philox_std", "philox_seed", "philox_off", "strict", "pre_dev",
+        "post_s", "post_o", "noise_ptr", "philox_std", "philox_seed", "philox_off", "strict", "pre_dev", "grid",
     )
 
     def __init__(self, size: np.ndarray):
@@ -140,6 +140,8 @@ class _Stage:
         self.philox_off = np.zeros(n, np.uint64)
         self.strict = np.zeros(n, bool)
         self.pre_dev = np.zeros(n, np.uint64)
+        self.grid = size.astype(np.int64, copy=True)  # output grid of the resample (where has_affine): the source size for
+        #                                               RandAffined(spatial_size=None), the new size for a Spacingd resample
         self.keep = []  # tensors that must outlive the launch (noise)
 
     def take(self, idx):
@@ -335,9 +337,10 @@ class BatchPlan:
         return self
 
     # ------------------------------------------------------------------ resample
-    def affine(self, A, mode="bilinear", padding_mode="reflection", where=None):
+    def affine(self, A, mode="bilinear", padding_mode="reflection", where=None, out_size=None):
         """One RandAffine firing: ``A`` is the fp32 4x4 MONAI matrix ([4,4] or [n,4,4]); the
-        output grid is the current size (``spatial_size=None`` as the reference always uses)."""
+        output grid is the current size (``spatial_size=None`` as the reference always uses) unless
+        ``out_size`` ([3] or [n,3]) names another one (:meth:`resample_to`)."""
         w = _where(where, self.n)
         A = np.asarray(A, dtype=np.float32)
         if A.ndim == 2:
@@ -348,7 +351,7 @@ class BatchPlan:
             interp = np.asarray([_lib.INTERP_MODES[m] for m in mode], np.uint8)
         padding = np.uint8(_lib.PADDING_MODES[padding_mode])
         st = self.st
-        if self.fast:
+        if self.fast and out_size is None:
             # compose into the pending matrix: M = M_prev @ A (only legal if nothing integer sits between)
             comp = w & st.has_affine & ~self._has_noise()
             untouched = (
@@ -380,10 +383,30 @@ class BatchPlan:
         st.A[w] = A[w, :3]
         st.interp = np.where(w, interp, st.interp).astype(np.uint8)
         st.padding = np.where(w, padding, st.padding).astype(np.uint8)
-        fresh = IntMap(st.pre.size)
+        grid = st.pre.size if out_size is None else _i3(out_size, self.n)
+        st.grid = np.where(w[:, None], grid, st.grid)
+        fresh = IntMap(grid)
         idx = np.nonzero(w)[0]
         st.post.put(idx, fresh.take(idx))
         return self
+
+    def resample_to(self, step, out_size, mode="bilinear", padding_mode="border", where=None):
+        """Axis-aligned resample onto a grid of another size: output voxel ``o`` reads source index ``step * o``
+        per axis (``step`` [3] or [n,3] float64) — ``monai.transforms.Spacingd`` on an axis-aligned volume †
+        (``step = pixdim / spacing``; SpatialResample keeps voxel 0 in place and maps index to index with
+        ``align_corners=False``).  Expressed as a MONAI-style affine for K1: with the centred grid coordinate
+        ``c = o - (G-1)/2`` the kernel computes ``u = A c + t + (S-1)/2``, hence ``A = diag(step)`` and
+        ``t = step (G-1)/2 - (S-1)/2``."""
+        cur = self.shape.astype(np.float64)
+        G = _i3(out_size, self.n).astype(np.float64)
+        step = np.asarray(step, np.float64)
+        if step.ndim == 1:
+            step = np.broadcast_to(step, (self.n, 3))
+        A = np.tile(np.eye(4, dtype=np.float32), (self.n, 1, 1))
+        for a in range(3):
+            A[:, a, a] = step[:, a].astype(np.float32)
+            A[:, a, 3] = (step[:, a] * (G[:, a] - 1) / 2 - (cur[:, a] - 1) / 2).astype(np.float32)
+        return self.affine(A, mode, padding_mode, where=where, out_size=G.astype(np.int64))
 
     # ------------------------------------------------------------------ intensity
     def intensity(self, scale=1.0, offset=0.0, where=None):
@@ -465,7 +488,7 @@ class BatchPlan:
         it["src_vhi"] = st.pre.vhi
         ha = st.has_affine[:, None]
         it["out_shape"] = np.where(ha, st.post.size, st.pre.size)
-        it["grid_shape"] = st.pre.size  # spatial_size=None: the affine grid has the source size
+        it["grid_shape"] = np.where(ha, st.grid, st.pre.size)  # spatial_size=None: the affine grid has the source size
         it["grid_off"] = np.where(ha, st.post.off, 0)
         it["grid_sign"] = np.where(ha, st.post.sign, 1)
         it["out_vlo"] = np.where(ha, st.post.vlo, 0)

@@ -591,7 +591,7 @@ class TransformMixin:
 
 def _reject(name, value):
     if value is not None and value is not False and value != []:
-        raise NotImplementedError(f"{name} belongs to the cached loading stage (file IO / Spacingd): outside the fused hot path")
+        raise NotImplementedError(f"{name} belongs to the cached loading stage (file IO / clinical tables): outside the fused hot path")
 
 
 def _intensity_stage(non_adc_keys, adc_keys, offset_adc: bool):
@@ -638,7 +638,6 @@ class SegmentationTransforms(TransformMixin):
     convert_to_tensor: bool = True
 
     def __post_init__(self):
-        _reject("target_spacing", self.target_spacing)
         _reject("fill_missing", self.fill_missing)
         _reject("brunet", self.brunet)
         _reject("all_aux_keys", list(self.all_aux_keys))
@@ -648,7 +647,10 @@ class SegmentationTransforms(TransformMixin):
         self.mask_key = ["mask"] if self.label_keys is not None else []
 
     def pre_transforms(self):
-        transforms = _intensity_stage(self.non_adc_keys, self.adc_keys, offset_adc=False)
+        transforms = []
+        if self.target_spacing is not None:   # transforms.py:133-140 (after Orientationd, before the intensity scalers)
+            transforms.append(T.Spacingd(keys=self.all_keys, pixdim=self.target_spacing, mode=self.intp_resampling_augmentations))
+        transforms += _intensity_stage(self.non_adc_keys, self.adc_keys, offset_adc=False)
         if self.resize_size is not None and self.resize_keys:   # transforms.py:157-167
             intp_ = [k for k, kk in zip(self.intp, self.all_keys) if kk in self.resize_keys]
             transforms.append(T.Resized(list(self.resize_keys), tuple(self.resize_size), mode=intp_))
@@ -697,7 +699,6 @@ class ClassificationTransforms(TransformMixin):
     target_size: Sequence[int] | None = None
 
     def __post_init__(self):
-        _reject("target_spacing", self.target_spacing)
         _reject("target_size", self.target_size)
         _reject("image_masking", self.image_masking)
         self.keys = list(self.keys)
@@ -710,6 +711,9 @@ class ClassificationTransforms(TransformMixin):
 
     def pre_transforms(self):
         transforms = _intensity_stage(self.non_adc_keys, self.adc_keys, offset_adc=True)
+        if self.target_spacing is not None:   # transforms.py:444-454 (after the scalers here; IMAGE_INTERPOLATION / nearest for the mask)
+            interpolation = ["bilinear" if k != self.mask_key else "nearest" for k in self.all_keys]
+            transforms.append(T.Spacingd(self.all_keys, pixdim=self.target_spacing, dtype=torch.float32, mode=interpolation))
         if self.pad_size is not None:
             transforms.append(T.SpatialPadd(self.all_keys, self.crop_size_with_margin))
         if self.image_crop_from_mask is True:
@@ -746,7 +750,6 @@ class SSLTransforms(TransformMixin):
     jpeg_dataset: bool = False
 
     def __post_init__(self):
-        _reject("target_spacing", self.target_spacing)
         _reject("jpeg_dataset", self.jpeg_dataset)
         if self.n_dim != 3:
             raise NotImplementedError("the fused hot path is volumetric (n_dim=3)")
@@ -755,7 +758,10 @@ class SSLTransforms(TransformMixin):
         self.concat_keys = [self.all_keys] if self.skip_augmentations else [self.all_keys, self.copied_keys]
 
     def pre_transforms(self):
-        transforms = _intensity_stage(self.non_adc_keys, self.adc_keys, offset_adc=False)
+        transforms = []
+        if self.target_spacing is not None:   # transforms.py:761-771 (IMAGE_INTERPOLATION for every key)
+            transforms.append(T.Spacingd(keys=self.all_keys, pixdim=self.target_spacing, mode=["bilinear" for _ in self.all_keys]))
+        transforms += _intensity_stage(self.non_adc_keys, self.adc_keys, offset_adc=False)
         if self.crop_size is not None:
             transforms.append(T.CenterSpatialCropd(self.all_keys, [int(j) for j in self.crop_size]))
         if self.pad_size is not None:

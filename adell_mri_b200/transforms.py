@@ -756,6 +756,72 @@ class Resized(MapTransform):
         return d
 
 
+def _axis_spacing(entry, d: dict, key: str) -> np.ndarray:
+    """Voxel spacing of ``d[key]`` along its three axes: from ``d[f"{key}_spacing"]`` (3 numbers), else from an
+    ``affine`` (attribute of the tensor, like MONAI's MetaTensor, or ``d[f"{key}_meta_dict"]["affine"]``), which
+    must be axis-aligned (what ``Orientationd("RAS")`` leaves for a scanner-aligned acquisition)."""
+    if f"{key}_spacing" in d:
+        return np.asarray(d[f"{key}_spacing"], np.float64).reshape(3)
+    aff = getattr(entry, "affine", None)
+    if aff is None and isinstance(getattr(entry, "meta", None), dict):
+        aff = entry.meta.get("affine")
+    if aff is None and isinstance(d.get(f"{key}_meta_dict"), dict):
+        aff = d[f"{key}_meta_dict"].get("affine")
+    if aff is None:
+        raise KeyError(f"Spacingd: no spacing for '{key}' (give '{key}_spacing', an .affine attribute or '{key}_meta_dict')")
+    aff = np.asarray(aff, np.float64)[:3, :3]
+    if np.abs(aff - np.diag(np.diag(aff))).max() > 1e-6 * np.abs(aff).max() or (np.diag(aff) <= 0).any():
+        raise NotImplementedError("Spacingd on the fused path needs an axis-aligned affine with positive spacings (oblique "
+                                  "acquisitions need the general SpatialResample of the loading stage)")
+    return np.diag(aff).copy()
+
+
+class Spacingd(MapTransform):
+    """``monai.transforms.Spacingd(keys, pixdim, mode)`` † for axis-aligned volumes
+    (/root/reference/adell_mri/transform_factory/transforms.py:133-140,444-454: the cached stage's resample to
+    ``target_spacing``).  MONAI's ``Spacing`` builds the output affine with the new pixel size and the SAME
+    origin (voxel 0 stays in place), sizes the output with ``compute_shape_offset``
+    (``round((S - 1) * spacing / pixdim + 1)`` per axis), and resamples index-to-index
+    (``align_corners=False``, ``padding_mode="border"``): output voxel ``o`` reads source index
+    ``o * pixdim / spacing``.  Recorded as one K1 resample item (:meth:`BatchPlan.resample_to`).
+    † restated from MONAI 1.3-1.6 (``Spacing.__call__`` -> ``SpatialResample``); MONAI evaluates the grid in
+    float64 by default, K1 in fp32: trilinear results agree within the path's 1e-4, nearest ones except at
+    coordinates within ~1e-5 voxel of a rounding tie (exactly representable steps such as 0.5 / 2 are exact)."""
+
+    def __init__(self, keys, pixdim, diagonal: bool = False, mode="bilinear", padding_mode="border",
+                 align_corners: bool = False, dtype=None, allow_missing_keys: bool = False, **_):
+        super().__init__(keys, allow_missing_keys)
+        if diagonal or align_corners:
+            raise NotImplementedError("Spacingd: diagonal=True / align_corners=True are not used by the reference")
+        self.pixdim = np.asarray(pixdim, np.float64).reshape(-1)
+        self.mode = _per_key(mode, self.keys, "mode")
+        self.padding_mode = _per_key(padding_mode, self.keys, "padding_mode")
+
+    @staticmethod
+    def output_size(shape, spacing, pixdim):
+        """compute_shape_offset for an axis-aligned affine: ``np.round(ptp + 1)`` per axis (round half to even)."""
+        ext = (np.asarray(shape, np.float64) - 1.0) * (np.asarray(spacing, np.float64) / np.asarray(pixdim, np.float64))
+        return np.round(ext + 1.0).astype(np.int64)
+
+    def __call__(self, data):
+        d = dict(data)
+        for k, mode, pad in zip(self.keys, self.mode, self.padding_mode):
+            if k not in d:
+                if self.allow_missing_keys:
+                    continue
+                raise KeyError(k)
+            spacing = _axis_spacing(d[k], d, k)
+            pixdim = np.where(self.pixdim[:3] > 0, self.pixdim[:3], spacing) if self.pixdim.size >= 3 else np.full(3, self.pixdim[0])
+            d[k] = as_pending(d[k])
+            shape = d[k].spatial_shape
+            out = self.output_size(shape, spacing, pixdim)
+            if np.allclose(pixdim, spacing, rtol=0, atol=1e-3) and tuple(out) == tuple(shape):
+                continue   # MONAI: affine unchanged -> the image is handed on as it is
+            d[k].plan.resample_to(pixdim / spacing, out, mode, pad)
+            d[f"{k}_spacing"] = pixdim.copy()
+        return d
+
+
 class RandRicianNoised(_RandIntensityd):
     """``monai.transforms.RandRicianNoised`` †: the dict transform's ``R.rand()`` gate, then PER KEY the
     wrapped ``RandRicianNoise(prob=1.0)``: its own ``R.rand()``, ``sigma ~ U(0, std)`` (``sample_std``)

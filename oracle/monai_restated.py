@@ -562,3 +562,25 @@ def std_shift_intensity(img: torch.Tensor, factor: float) -> torch.Tensor:
     img = img.to(torch.float32)
     offset = factor * torch.std(img, unbiased=False)
     return img + offset
+
+
+def spacing(img: torch.Tensor, spacing_in: Sequence[float], pixdim: Sequence[float], mode: str = "bilinear",
+            padding_mode: str = "border", dtype=torch.float64) -> torch.Tensor:
+    """monai.transforms.Spacing † on an axis-aligned volume (affine = diag(spacing_in), origin anywhere):
+    ``new_affine = zoom_affine(affine, pixdim)`` keeps the origin; ``compute_shape_offset`` sizes the output as
+    ``round((S-1) * spacing_in / pixdim + 1)``; ``SpatialResample(align_corners=False)`` maps output index ``o`` to
+    source index ``solve(src_affine, dst_affine) @ o = o * pixdim / spacing_in``; ``grid_sample`` evaluates it in
+    ``dtype`` (MONAI's default float64) and the result is cast back to float32.
+    (/root/reference/adell_mri/transform_factory/transforms.py:133-140,444-454)"""
+    S = np.asarray(img.shape[1:], np.float64)
+    r = np.asarray(pixdim, np.float64) / np.asarray(spacing_in, np.float64)
+    out = np.round((S - 1.0) / r + 1.0).astype(np.int64)
+    x = img.to(dtype)[None]
+    axes = []
+    for a in range(3):
+        u = torch.arange(int(out[a]), dtype=dtype) * float(r[a])           # source index of output voxel o
+        axes.append((2.0 * u + 1.0) / float(S[a]) - 1.0)                    # grid_sample, align_corners=False
+    g0, g1, g2 = torch.meshgrid(*axes, indexing="ij")
+    grid = torch.stack([g2, g1, g0], dim=-1)[None]                          # grid_sample wants (x, y, z) = axes (2, 1, 0)
+    y = F.grid_sample(x, grid, mode=mode, padding_mode=padding_mode, align_corners=False)
+    return y[0].to(torch.float32)
