@@ -13,11 +13,11 @@ from __future__ import annotations
 
 from typing import Sequence
 
+import numpy as np
 import torch
 
 from . import engine
-from .plan import BatchPlan
-from .transforms import Pending
+from .transforms import Pending, replay_parts
 
 
 def _cat(x):
@@ -33,17 +33,25 @@ def _cat(x):
 
 def execute_pending(groups: Sequence[Sequence[Pending]]) -> list[torch.Tensor]:
     """``groups[g]`` = the entries of one key over the batch (same output shape): returns one
-    ``[B, C, H, W, D]`` float32 tensor per group, all produced by the same fused launch(es)."""
-    plans, dsts, outs = [], [], []
+    ``[B, C, H, W, D]`` float32 tensor per group, all produced by the same fused launch(es).  The recorded chains
+    of every sample and key are composed here, grouped by chain signature: each op is one vectorised call for all
+    the volumes that recorded it (``transforms.replay_parts``), not one per sample."""
+    parts, ptrs, strides, outs = [], [], [], []
     for entries in groups:
         first = entries[0]
+        nc = first.n_channels
         out = torch.empty((len(entries), *first.shape), dtype=torch.float32, device=first.device)
         outs.append(out)
-        for b, e in enumerate(entries):
-            plans.append(e.plan)
-            dsts.extend(out[b, c] for c in range(e.n_channels))
-    if plans:
-        engine.execute(BatchPlan.concat(plans), dsts)
+        for e in entries:
+            if e.n_channels != nc:
+                raise ValueError("entries of one key must have the same number of channels")
+            parts.extend(e.parts)
+        # destination of volume [b, c]: computed, not sliced (a tensor view per volume costs more than its chain)
+        b, c = np.arange(len(entries), dtype=np.int64)[:, None], np.arange(nc, dtype=np.int64)[None, :]
+        ptrs.append((out.data_ptr() + 4 * (b * out.stride(0) + c * out.stride(1))).reshape(-1).astype(np.uint64))
+        strides.append(np.broadcast_to(np.asarray(out.stride()[2:], np.int64), (len(entries) * nc, 3)))
+    if parts:
+        engine.execute_ptrs(replay_parts(parts), np.concatenate(ptrs), np.concatenate(strides), keep=outs)
     return outs
 
 

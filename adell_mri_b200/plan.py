@@ -263,6 +263,19 @@ class BatchPlan:
             )
         return out
 
+    def permuted(self, perm: np.ndarray) -> "BatchPlan":
+        """The same plan with its volumes reordered: volume ``i`` of the result is volume ``perm[i]`` of this one."""
+        perm = np.asarray(perm, np.int64)
+        inv = np.empty_like(perm)
+        inv[perm] = np.arange(perm.shape[0])
+        out = BatchPlan.__new__(BatchPlan)
+        out.n, out.fast, out.default_strict, out.device = self.n, self.fast, self.default_strict, self.device
+        out.keep = list(self.keep)
+        out.parent_ptr, out.parent_stride, out.parent_dtype = self.parent_ptr[perm], self.parent_stride[perm], self.parent_dtype[perm]
+        out.st = self.st.take(perm)
+        out.passes = [(inv[idx], st, a, b, c) for idx, st, a, b, c in self.passes]
+        return out
+
     def _close(self, mask: np.ndarray):
         """Close the open pass of the volumes in ``mask``: it will be materialised into a
         scratch fp32 volume which becomes their new parent."""

@@ -31,6 +31,7 @@ from .sampling import MAX_SEED, RandAffineSampler, rand_param
 
 # --------------------------------------------------------------------------- execution mode
 _MODE = {"strict": False, "fast": False, "noise": "injected"}
+_EYE4 = np.eye(4, dtype=np.float32)
 
 
 def set_mode(strict: bool | None = None, fast: bool | None = None, noise: str | None = None):
@@ -51,46 +52,274 @@ def set_mode(strict: bool | None = None, fast: bool | None = None, noise: str | 
     return dict(_MODE)
 
 
-class Pending:
-    """One dict entry ``[C, H, W, D]`` whose transform chain is recorded, not yet executed."""
+class _Part:
+    """Channels of one entry that share a recorded chain: the parent volumes, the chain as DATA — a list of
+    ``(name, static, dyn, per_volume)`` — and the logical spatial shape the chain has reached.  Nothing numeric
+    happens while a pipeline runs; :func:`replay_parts` turns the parts of a whole batch into BatchPlans, one per
+    distinct chain signature, each op applied once to all the volumes that recorded it."""
 
-    def __init__(self, tensor: torch.Tensor | None = None, plan: BatchPlan | None = None, meta: dict | None = None):
-        if plan is None:
-            if tensor.dim() != 4:
-                raise ValueError("expected a channel-first [C, H, W, D] volume")
-            plan = BatchPlan([tensor[c] for c in range(tensor.shape[0])], fast=_MODE["fast"], strict=_MODE["strict"])
-        self.plan = plan
-        self.meta = meta if meta is not None else {}
+    __slots__ = ("vols", "ops", "shape", "strict", "fast", "_sig", "meta")
+
+    def __init__(self, vols, shape, strict, fast, ops=None, meta=None):
+        self.vols, self.shape, self.strict, self.fast = vols, tuple(int(x) for x in shape), strict, fast
+        self.ops = [] if ops is None else ops
+        self._sig = None
+        self.meta = meta   # what BatchPlan needs to know about the parents: gathered at replay (parent_meta)
+
+    def copy(self):
+        return _Part(self.vols, self.shape, self.strict, self.fast, list(self.ops), self.meta)
+
+    def signature(self):
+        if self._sig is None or self._sig[0] != len(self.ops):
+            self._sig = (len(self.ops), (len(self.vols), self.strict, self.fast, self.vols[0].dtype, str(self.vols[0].device),
+                                         tuple((o[0], o[1]) for o in self.ops)))
+        return self._sig[1]
+
+
+def parent_meta(part: _Part, source=None):
+    """(ptr, stride, dtype, shape) arrays of a part's parent volumes.  Gathered once per part — and remembered on the
+    SOURCE tensor the entry was made from (``source._adell_meta``): a device-resident cache hands the same tensor
+    objects back every epoch, so after the first one this costs a dictionary lookup."""
+    if part.meta is None:
+        from .plan import _TORCH_TO_ADELL
+        vols = part.vols
+        for v in vols:
+            if v.dim() != 3 or v.dtype not in _TORCH_TO_ADELL:
+                raise TypeError("expected [H, W, D] float32 / int16 / uint8 volumes")
+        part.meta = (np.array([v.data_ptr() for v in vols], np.uint64), np.array([v.stride() for v in vols], np.int64),
+                     np.array([_TORCH_TO_ADELL[v.dtype] for v in vols], np.uint8), np.array([v.shape for v in vols], np.int64))
+    return part.meta
+
+
+def _shape_after(name, shape, dyn):
+    """Logical spatial shape after one recorded op (the integer rules of BatchPlan.crop / center_crop / pad /
+    spatial_pad / resample_to, on plain ints)."""
+    if name == "crop":
+        start, size = dyn
+        out = []
+        for c, st, sz in zip(shape, start, size):
+            st = min(max(int(st), 0), c)
+            out.append(min(int(sz), c - st))
+        return tuple(out)
+    if name == "center_crop":
+        return tuple(c if int(r) <= 0 else min(int(r), c) for c, r in zip(shape, dyn[0]))
+    if name == "pad":
+        return tuple(c + int(b) + int(a) for c, b, a in zip(shape, dyn[0], dyn[1]))
+    if name == "spatial_pad":
+        return tuple(max(c, int(w)) if int(w) > 0 else c for c, w in zip(shape, dyn[0]))
+    if name == "resample_to":
+        return tuple(int(x) for x in dyn[1])
+    return shape
+
+
+class ChainRecorder:
+    """``Pending.plan``: the methods of :class:`~adell_mri_b200.plan.BatchPlan` the dictionary transforms call,
+    recording instead of composing (a tuple append and an integer shape update per call)."""
+
+    __slots__ = ("parts",)
+
+    def __init__(self, parts):
+        self.parts = parts
+
+    def _rec(self, name, static, dyn, per_volume=False):
+        for p in self.parts:
+            p.ops.append((name, static, dyn, per_volume))
+            p.shape = _shape_after(name, p.shape, dyn)
+        return self
+
+    # integer ops
+    def crop(self, start, size):
+        return self._rec("crop", (), (tuple(int(x) for x in start), tuple(int(x) for x in size)))
+
+    def center_crop(self, roi):
+        return self._rec("center_crop", (), (tuple(int(x) for x in roi),))
+
+    def pad(self, before, after):
+        return self._rec("pad", (), (tuple(int(x) for x in before), tuple(int(x) for x in after)))
+
+    def spatial_pad(self, spatial_size):
+        return self._rec("spatial_pad", (), (tuple(int(x) for x in spatial_size),))
+
+    def flip(self, mask):
+        if type(mask) is not tuple:
+            mask = tuple(bool(x) for x in np.asarray(mask).reshape(3))
+        return self._rec("flip", (), (mask,))
+
+    # resamples
+    def affine(self, A, mode="bilinear", padding_mode="reflection", fired: bool = True):
+        return self._rec("affine", (padding_mode,), (np.asarray(A, np.float32), mode, bool(fired)))
+
+    def resample_to(self, step, out_size, mode="bilinear", padding_mode="border"):
+        return self._rec("resample_to", (mode, padding_mode), (tuple(float(x) for x in step), tuple(int(x) for x in out_size)))
+
+    # intensity / noise
+    def intensity(self, scale=1.0, offset=0.0):
+        return self._rec("intensity", (), (float(scale), float(offset)))
+
+    def intensity_from_device(self, pre_dev: torch.Tensor):
+        n = sum(len(p.vols) for p in self.parts)
+        if pre_dev.shape != (n, 2) or pre_dev.dtype != torch.float32:
+            raise ValueError("pre_dev must be a [n, 2] float32 tensor")
+        o = 0
+        for p in self.parts:
+            if p.ops:
+                raise ValueError("device-side intensity must be the first recorded op")
+            p.ops.append(("intensity_from_device", (), (pre_dev[o:o + len(p.vols)],), True))
+            o += len(p.vols)
+        return self
+
+    def add_philox_noise(self, std, seed, offset=0):
+        o = 0
+        for p in self.parts:
+            off = np.broadcast_to(np.asarray(offset, np.uint64), (sum(len(q.vols) for q in self.parts),))[o:o + len(p.vols)]
+            p.ops.append(("add_philox_noise", (), (np.float32(std), np.uint64(seed), off.copy()), True))
+            o += len(p.vols)
+        return self
+
+    def add_noise(self, noise):
+        o = 0
+        for p in self.parts:
+            p.ops.append(("add_noise", (), (list(noise[o:o + len(p.vols)]),), True))
+            o += len(p.vols)
+        return self
 
     @property
-    def n_channels(self) -> int:
-        return self.plan.n
-
-    @property
-    def spatial_shape(self) -> tuple:
-        return tuple(int(x) for x in self.plan.shape[0])
-
-    @property
-    def shape(self) -> tuple:
-        return (self.plan.n, *self.spatial_shape)
+    def n(self) -> int:
+        return sum(len(p.vols) for p in self.parts)
 
     @property
     def device(self):
-        return self.plan.device
+        return self.parts[0].vols[0].device
+
+    @property
+    def shape(self) -> np.ndarray:
+        return np.array([p.shape for p in self.parts for _ in p.vols], np.int64)
+
+    def build(self) -> BatchPlan:
+        """The composed plan of this entry alone."""
+        return replay_parts(self.parts)
+
+
+def replay_parts(parts: Sequence[_Part]) -> BatchPlan:
+    """Compose the recorded chains of many parts (in order: the plan's volumes are the parts' volumes concatenated).
+    Parts are grouped by chain signature (op names + static arguments, channel count, mode flags); every op of a
+    group is ONE vectorised BatchPlan call over all of the group's volumes, its per-part arguments stacked."""
+    groups: dict = {}
+    for i, p in enumerate(parts):
+        groups.setdefault(p.signature(), []).append(i)
+    plans, order = [], []
+    for sig, idx in groups.items():
+        grp = [parts[i] for i in idx]
+        nv = len(grp[0].vols)
+        dev = grp[0].vols[0].device
+        for p in grp:
+            if p.vols[0].device != dev:
+                raise ValueError("all parents of a plan must live on one device")
+        metas = [parent_meta(p) for p in grp]
+        cat = (lambda i: metas[0][i]) if len(grp) == 1 else (lambda i: np.concatenate([m[i] for m in metas]))
+        plan = BatchPlan.from_arrays(cat(0), cat(1), cat(2), cat(3), dev, [p.vols for p in grp], fast=grp[0].fast, strict=grp[0].strict)
+        rep = (lambda x: x) if nv == 1 else (lambda x: np.repeat(x, nv, axis=0))
+        for j, (name, static, _, per_volume) in enumerate(grp[0].ops):
+            dyn = [p.ops[j][2] for p in grp]
+            if name == "crop":
+                plan.crop(rep(np.array([d[0] for d in dyn], np.int64)), rep(np.array([d[1] for d in dyn], np.int64)))
+            elif name == "center_crop":
+                plan.center_crop(rep(np.array([d[0] for d in dyn], np.int64)))
+            elif name == "pad":
+                plan.pad(rep(np.array([d[0] for d in dyn], np.int64)), rep(np.array([d[1] for d in dyn], np.int64)))
+            elif name == "spatial_pad":
+                plan.spatial_pad(rep(np.array([d[0] for d in dyn], np.int64)))
+            elif name == "flip":
+                plan.flip(rep(np.array([d[0] for d in dyn], bool)))
+            elif name == "affine":
+                fired = np.array([d[2] for d in dyn], bool)
+                if fired.any():
+                    modes = [d[1] for d in dyn for _ in range(nv)]
+                    plan.affine(rep(np.stack([d[0] for d in dyn])), modes, static[0], where=None if fired.all() else rep(fired))
+            elif name == "resample_to":
+                plan.resample_to(rep(np.array([d[0] for d in dyn], np.float64)), rep(np.array([d[1] for d in dyn], np.int64)), static[0], static[1])
+            elif name == "intensity":
+                plan.intensity(scale=rep(np.array([d[0] for d in dyn], np.float64)), offset=rep(np.array([d[1] for d in dyn], np.float64)))
+            elif name == "intensity_from_device":
+                plan.intensity_from_device(dyn[0][0].contiguous() if len(dyn) == 1 else torch.cat([d[0] for d in dyn]).contiguous())
+            elif name == "add_philox_noise":
+                plan.add_philox_noise(rep(np.array([d[0] for d in dyn], np.float32)), rep(np.array([d[1] for d in dyn], np.uint64)),
+                                      np.concatenate([d[2] for d in dyn]))
+            elif name == "add_noise":
+                plan.add_noise([t for d in dyn for t in d[0]])
+            else:
+                raise ValueError(name)
+        plans.append(plan)
+        order.extend((i, k) for i in idx for k in range(nv))
+    if len(plans) == 1 and order == [(i, k) for i in range(len(parts)) for k in range(len(parts[0].vols))]:
+        return plans[0]
+    # volumes back into the callers' order (parts in order, their channels in order)
+    plan = BatchPlan.concat(plans)
+    want = {}
+    pos = 0
+    for i, p in enumerate(parts):
+        for k in range(len(p.vols)):
+            want[(i, k)] = pos
+            pos += 1
+    perm = np.empty(len(order), np.int64)     # perm[target position] = position in the concatenated plan
+    for src, key in enumerate(order):
+        perm[want[key]] = src
+    return plan.permuted(perm)
+
+
+class Pending:
+    """One dict entry ``[C, H, W, D]`` whose transform chain is recorded, not yet executed."""
+
+    def __init__(self, tensor: torch.Tensor | None = None, parts: list | None = None, meta: dict | None = None):
+        if parts is None:
+            if tensor.dim() != 4:
+                raise ValueError("expected a channel-first [C, H, W, D] volume")
+            cached = getattr(tensor, "_adell_part", None)   # (vols, meta) of an earlier entry made from this very tensor
+            if cached is not None and cached[2] == tensor._version and cached[3] == tensor.data_ptr():
+                part = _Part(cached[0], tensor.shape[1:], _MODE["strict"], _MODE["fast"], meta=cached[1])
+            else:
+                part = _Part([tensor[c] for c in range(tensor.shape[0])], tensor.shape[1:], _MODE["strict"], _MODE["fast"])
+                try:
+                    tensor._adell_part = (part.vols, parent_meta(part), tensor._version, tensor.data_ptr())
+                except Exception:   # noqa: BLE001 — tensors that refuse attributes simply do not cache
+                    pass
+            parts = [part]
+        self.parts = parts
+        self.meta = meta if meta is not None else {}
+
+    @property
+    def plan(self) -> ChainRecorder:
+        return ChainRecorder(self.parts)
+
+    @property
+    def n_channels(self) -> int:
+        return sum(len(p.vols) for p in self.parts)
+
+    @property
+    def spatial_shape(self) -> tuple:
+        return self.parts[0].shape
+
+    @property
+    def shape(self) -> tuple:
+        return (self.n_channels, *self.spatial_shape)
+
+    @property
+    def device(self):
+        return self.parts[0].vols[0].device
 
     def clone(self) -> "Pending":
-        return Pending(plan=BatchPlan.concat([self.plan]), meta={k: (list(v) if isinstance(v, list) else v) for k, v in self.meta.items()})
+        return Pending(parts=[p.copy() for p in self.parts], meta={k: (list(v) if isinstance(v, list) else v) for k, v in self.meta.items()})
 
     @staticmethod
     def cat(entries: Sequence["Pending"]) -> "Pending":
-        return Pending(plan=BatchPlan.concat([e.plan for e in entries]))
+        return Pending(parts=[p for e in entries for p in e.parts])
 
     def tensor(self) -> torch.Tensor:
         """Materialise this entry alone (one launch per pass)."""
         from . import engine
 
         out = torch.empty(self.shape, dtype=torch.float32, device=self.device)
-        engine.execute(self.plan, [out[c] for c in range(self.plan.n)])
+        engine.execute(replay_parts(self.parts), [out[c] for c in range(self.n_channels)])
         return out
 
 
@@ -529,9 +758,9 @@ class RandFlipd(RandomizableTransform, MapTransform):
     def __call__(self, data):
         d = dict(data)
         self.randomize(None)
-        if not self._do_transform:
-            return d
-        mask = np.array([a in self.spatial_axis for a in range(3)])
+        # (an idle call records the empty flip: every sample of a batch then carries the same chain, and
+        # safe_collate composes the whole batch as one group)
+        mask = tuple(self._do_transform and a in self.spatial_axis for a in range(3))
         for k in self.key_iterator(d):
             d[k] = as_pending(d[k])
             d[k].plan.flip(mask)
@@ -568,16 +797,13 @@ class RandAffined(RandomizableTransform, MapTransform):
         keys = list(self.key_iterator(d))
         fired, p = self.sampler.draw(n_keys=len(keys))
         self._do_transform = bool(fired)
-        if not fired:
-            self.last_affine = None
-            return d
-        A = geometry.compose_affine(p["rotate"], p["shear"], p["translate"], p["scale"])[0]
-        self.last_affine = A
+        A = geometry.compose_affine(p["rotate"], p["shear"], p["translate"], p["scale"])[0] if fired else _EYE4
+        self.last_affine = A if fired else None
         for k, mode, pad in zip(self.keys, self.mode, self.padding_mode):
             if k not in d:
                 continue
             d[k] = as_pending(d[k])
-            d[k].plan.affine(A, mode, pad)
+            d[k].plan.affine(A, mode, pad, fired=bool(fired))   # idle calls record "not fired" (same chain for the whole batch)
         return d
 
 

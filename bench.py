@@ -498,6 +498,30 @@ def main():
     barrier()
     e2e_raw_ms = a.elapsed_time(b) / e2e_steps
 
+    # ---- the drop-in dictionary surface: the reference's own call pattern ----
+    # one transform-pipeline call per sample (get_augmentations_unet + post_transforms, same keys / arguments /
+    # RandomState streams as the reference), then safe_collate: the recorded chains of the batch are composed once
+    # and leave as one K1 launch.  Device-resident cache, like `value`; what an import swap costs per step.
+    from adell_mri_b200 import collate as _collate, transform_factory as _F, transforms as _T
+
+    tf_d = _F.SegmentationTransforms(keys, image_keys, None, image_keys, [])
+    pipe_d = _T.Compose([_F.get_augmentations_unet(["affine", "flip"], keys, image_keys, [], flip_axis=[0, 1, 2]),
+                         *tf_d.post_transforms()]).set_random_state(SEED + 2000 + rank)
+    dict_steps = max(4, min(args.steps, 40))
+    for i in range(3):
+        _collate.safe_collate([pipe_d(dict(smp)) for smp in batch_of(i)])
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    a.record(stream)
+    for i in range(dict_steps):
+        res_d = _collate.safe_collate([pipe_d(dict(smp)) for smp in batch_of(i)])
+    b.record(stream)
+    dict_host_ms = 1e3 * (time.perf_counter() - t0) / dict_steps
+    barrier()
+    dict_ms = a.elapsed_time(b) / dict_steps
+    del res_d
+
     # ---- the other BASELINE configs, same run, same device (bench_workloads.py) ----
     workloads = {}
     if args.workloads != "none":
@@ -521,10 +545,10 @@ def main():
                 print("[workload] " + json.dumps({cls.name: workloads[cls.name]}), file=sys.stderr, flush=True)
 
     ms_per_step = total_ms / args.steps
-    t = torch.tensor([ms_per_step, e2e_ms, e2e_raw_ms], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms_per_step, e2e_ms, e2e_raw_ms, dict_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step, e2e_ms, e2e_raw_ms = float(t[0]), float(t[1]), float(t[2])
+    ms_per_step, e2e_ms, e2e_raw_ms, dict_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
 
     if rank == 0:
         line = {
@@ -541,6 +565,8 @@ def main():
             "gpu_launches": launches, "clocks": clock_info,
             "k1_launch_ms_median_in_loop": statistics.median(k1_ms), "host_chunk_steps": CHUNK,
             "host_us_per_step": host_us_per_step,
+            "dict_surface_ms_per_step": dict_ms, "dict_surface_host_ms_per_step": dict_host_ms,
+            "dict_surface": "reference call pattern (one pipeline call per sample + safe_collate), batch %d, device-resident cache" % batch,
             "workloads": workloads,
         }
         if world == 1 and not args.no_cpu_baseline:

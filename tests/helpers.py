@@ -74,3 +74,19 @@ def cref_prepare_chain_steps(chains, step_sizes, device, keep=None):
     buf, offs, _ = engine.compose_chains_host(chains, sizes)
     steps = [buf[int(o): int(o) + n * engine.ISZ].view(ITEM_DTYPE) for n, o in zip(sizes, offs)]
     return _CrefSteps(steps)
+
+
+def cref_execute_ptrs(plan: BatchPlan, dst_ptr, dst_stride, keep=None) -> None:
+    """Stand-in for ``engine.execute_ptrs`` on CPU-resident plans (see :func:`cref_execute`)."""
+    launches = plan.build_launches(dst_ptr, dst_stride, lambda n: torch.empty(max(n, 1), dtype=torch.float32))
+    for items in launches:
+        cref.gather(items)
+
+
+def patch_engine_for_cpu(monkeypatch) -> None:
+    """Route every execution entry of the engine through the C restatement (CPU tests of the host logic)."""
+    from adell_mri_b200 import engine
+
+    monkeypatch.setattr(engine, "execute", cref_execute)
+    monkeypatch.setattr(engine, "execute_ptrs", cref_execute_ptrs)
+    monkeypatch.setattr(engine, "prepare_chain_steps", cref_prepare_chain_steps)

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from adell_mri_b200 import collate, engine, transform_factory as F, transforms as T
-from tests.helpers import cref_execute
+from tests.helpers import cref_execute, patch_engine_for_cpu
 
 input_tensor_size = np.array([1, 128, 128, 16])
 crop_size = np.array([32, 32, 8])
@@ -19,7 +19,7 @@ n_crops = np.prod(input_tensor_size[1:] / crop_size)
 @pytest.fixture(params=["cpu", pytest.param("cuda:0", marks=pytest.mark.gpu)])
 def dev(request, monkeypatch):
     if request.param == "cpu":
-        monkeypatch.setattr(engine, "execute", cref_execute)
+        patch_engine_for_cpu(monkeypatch)
     return request.param
 
 

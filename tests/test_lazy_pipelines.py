@@ -9,13 +9,13 @@ import torch
 
 from adell_mri_b200 import collate, engine, transform_factory as F, transforms as T
 from oracle import pipelines_ref as P
-from tests.helpers import cref_execute
+from tests.helpers import cref_execute, patch_engine_for_cpu
 
 
 @pytest.fixture(params=["cpu", pytest.param("cuda:0", marks=pytest.mark.gpu)])
 def dev(request, monkeypatch):
     if request.param == "cpu":
-        monkeypatch.setattr(engine, "execute", cref_execute)
+        patch_engine_for_cpu(monkeypatch)
     T.set_mode(strict=True, fast=False, noise="injected")
     yield request.param
     T.set_mode(strict=False)

@@ -13,7 +13,7 @@ import torch
 
 from adell_mri_b200 import collate, engine, transform_factory as F, transforms as T
 from oracle import monai_restated as M
-from tests.helpers import cref_execute
+from tests.helpers import cref_execute, patch_engine_for_cpu
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 _spec = importlib.util.spec_from_file_location("make_golden_custom", os.path.join(HERE, "golden", "make_golden_custom.py"))
@@ -25,7 +25,7 @@ GOLD = np.load(os.path.join(HERE, "golden", "custom_transforms.npz"))
 @pytest.fixture(params=["cpu", pytest.param("cuda:0", marks=pytest.mark.gpu)])
 def dev(request, monkeypatch):
     if request.param == "cpu":
-        monkeypatch.setattr(engine, "execute", cref_execute)
+        patch_engine_for_cpu(monkeypatch)
     return request.param
 
 
