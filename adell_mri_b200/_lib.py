@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("ADELL_B200_LIB") or os.path.join(_HERE, "libadell_b20
 F32, I16, U8 = 0, 1, 2
 NEAREST, TRILINEAR = 0, 1
 PAD_ZEROS, PAD_BORDER, PAD_REFLECTION = 0, 1, 2
-F_IDENTITY, F_CLIP, F_STRICT, F_PHILOX, F_PRE_DEV, F_TMAP, F_FASTCOORD = 0x01, 0x02, 0x04, 0x08, 0x10, 0x20, 0x40
+F_IDENTITY, F_CLIP, F_STRICT, F_PHILOX, F_PRE_DEV, F_TMAP, F_FASTCOORD, F_WIN_DEV = 0x01, 0x02, 0x04, 0x08, 0x10, 0x20, 0x40, 0x80
 SCALER_MINMAX, SCALER_ADC_SEG, SCALER_ADC_CLASS, SCALER_RANGE, SCALER_ZSCORE = 0, 1, 2, 3, 4
 
 PADDING_MODES = {"zeros": PAD_ZEROS, "border": PAD_BORDER, "reflection": PAD_REFLECTION}
@@ -33,7 +33,7 @@ class Item(C.Structure):
         ("dst", C.c_void_p),
         ("noise", C.c_void_p),
         ("pre_dev", C.c_void_p),
-        ("tmap_base", C.c_void_p),
+        ("win_dev", C.c_void_p),
         ("src_stride", C.c_int64 * 3),
         ("dst_stride", C.c_int64 * 3),
         ("src_shape", C.c_int32 * 3),
@@ -112,6 +112,15 @@ class Chain(C.Structure):
 CHAIN_AFFINE, CHAIN_STRICT = 0x01, 0x02
 
 
+class PosNeg(C.Structure):
+    """Mirror of ``adell_posneg``."""
+
+    _fields_ = [("indices", C.c_void_p), ("pick", C.c_int64), ("shape", C.c_int32 * 3), ("size", C.c_int32 * 3)]
+
+
+assert C.sizeof(PosNeg) == 40
+
+
 class LaunchInfo(C.Structure):
     """Mirror of ``adell_launch_info``."""
 
@@ -159,6 +168,7 @@ _SIGNATURES = {
         [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p],
     ),
     "adell_hist_select": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "adell_posneg_starts": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "adell_mixup": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
     "adell_percentile_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
 }

@@ -1561,6 +1561,13 @@ int k1_validate(const adell_item& it) {
   if (it.src_dtype > ADELL_U8) return ADELL_ERR_DTYPE;
   if (it.interp > ADELL_TRILINEAR || it.padding > ADELL_PAD_REFLECTION) return ADELL_ERR_BAD_ARG;
   if (it.src == nullptr || it.dst == nullptr) return ADELL_ERR_BAD_ARG;
+  if (it.flags & ADELL_F_WIN_DEV) {
+    if (it.win_dev == nullptr) return ADELL_ERR_BAD_ARG;
+    for (int a = 0; a < 3; ++a)
+      if (it.src_vlo[a] != 0 || it.src_vhi[a] < it.src_shape[a]) return ADELL_ERR_BAD_ARG;   // src_vhi = the parent's extents
+    // zeros padding would have to stop at the window's edge: only the parent's edge is known to the staged box
+    if (!(it.flags & ADELL_F_IDENTITY) && it.padding == ADELL_PAD_ZEROS) return ADELL_ERR_UNSUPPORTED;
+  }
   return ADELL_OK;
 }
 
@@ -1742,7 +1749,7 @@ int64_t k1_box_for_tile(const adell_item& it, const int* T, int* box, bool shear
       // inner extent: a 16-byte multiple, plus the cells lost to aligning the box origin down to 16 bytes
       // (known exactly when the axis is staged whole)
       int lead = q - 1;
-      if (whole) {
+      if (whole && !(it.flags & ADELL_F_WIN_DEV)) {   // (a device-side window can start anywhere in its 16 bytes)
         const int mo = it.tmap_sign[2] > 0 ? it.tmap_off[2] : -(it.src_shape[2] - 1) + it.tmap_off[2];
         lead = mo & (q - 1);
       }
@@ -1774,7 +1781,9 @@ bool k1_tmap_layout(adell_item& it, K1Layout& L) {
     it.tmap_sign[a] = sign;
     it.tmap_off[a] = sign > 0 ? -tlo : thi - 1;           // m = sign*t + off, m = 0 at the lowest address
     base_off += static_cast<int64_t>(sign > 0 ? tlo : thi - 1) * it.src_stride[a];
-    L.gdim[2 - a] = static_cast<cuuint64_t>(thi - tlo);   // tensor-map dims are innermost first
+    // tensor-map dims are innermost first; a device-side window (ADELL_F_WIN_DEV) maps the whole parent: the
+    // kernel adds the window's start to the box coordinates
+    L.gdim[2 - a] = static_cast<cuuint64_t>((it.flags & ADELL_F_WIN_DEV) ? it.src_vhi[a] : thi - tlo);
   }
   const int es = k1_host_es(it.src_dtype);
   L.es = es;
@@ -1841,7 +1850,6 @@ int k1_encode_tmap(adell_item& it, const K1Layout& L, const int* box, EncodeTile
   const cuuint32_t bdim[3] = {static_cast<cuuint32_t>(box[2]), static_cast<cuuint32_t>(box[1]), static_cast<cuuint32_t>(box[0])};
   const int r = k1_encode_map(it.tmap, L, bdim, enc);
   if (r <= 0) return r;
-  it.tmap_base = reinterpret_cast<const void*>(L.base);
   it.flags |= ADELL_F_TMAP;
   return 1;
 }
@@ -1854,6 +1862,7 @@ int k1_encode_tmap(adell_item& it, const K1Layout& L, const int* box, EncodeTile
 int k1_encode_dst(adell_item& it, const int* T, const int* box, EncodeTiledFn enc) {
   if (k1_tuning().no_tstore) return -1;
   if (it.src_dtype != ADELL_F32) return -1;   // integer sources are converted by the consumer warps
+  if (it.flags & ADELL_F_WIN_DEV) return -1;  // window alignment unknown on the host
   if (it.flags & (ADELL_F_CLIP | ADELL_F_PRE_DEV)) return -1;
   if (it.pre_scale != 1.0f || it.pre_offset != 0.0f || it.post_scale != 1.0f || it.post_offset != 0.0f) return -1;
   if (it.tmap_sign[2] * it.grid_sign[2] < 0) return -1;          // a flip along the contiguous axis reverses elements
@@ -1895,7 +1904,7 @@ int k1_encode_copy(adell_item& it, EncodeTiledFn enc) {
   const int g0 = it.grid_off[2], g1 = it.grid_off[2] + it.grid_sign[2] * (n2 - 1);
   const int lo = it.tmap_sign[2] > 0 ? (g0 < g1 ? g0 : g1) + it.tmap_off[2] : -(g0 > g1 ? g0 : g1) + it.tmap_off[2];
   const int q = 16 / L.es;
-  if (lo & (q - 1)) {
+  if ((lo & (q - 1)) || (it.flags & ADELL_F_WIN_DEV)) {   // (a device-side window: its alignment is not known here)
     box[2] += q;
     r = k1_encode_tmap(it, L, box, enc);
     if (r <= 0) return r;

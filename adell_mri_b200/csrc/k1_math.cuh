@@ -41,6 +41,20 @@ __device__ __forceinline__ void k1_ctx_finish(K1Ctx& c) {
     for (int a = 0; a < 3; ++a) ext = max(ext, max(c.it.src_shape[a], c.it.grid_shape[a]));
     c.tie = 0.5f - fmaxf(2.0e-4f, 2.0e-6f * static_cast<float>(ext));
   }
+  if (c.it.flags & ADELL_F_WIN_DEV) {
+    // device-side crop window (RandCropByPosNegLabeld centres chosen by adell_posneg_starts): the item was composed
+    // for a window at parent index (0,0,0); shift the source and the tensor-map coordinates by the real start
+    const int es = c.it.src_dtype == ADELL_F32 ? 4 : (c.it.src_dtype == ADELL_I16 ? 2 : 1);
+    int64_t shift = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int w = c.it.win_dev[a];
+      const int64_t st = c.it.src_stride[a];
+      shift += static_cast<int64_t>(w) * (st < 0 ? -st : st);
+      c.it.tmap_off[a] += w;
+    }
+    c.it.src = static_cast<const char*>(c.it.src) + shift * es;
+  }
   if (c.it.flags & ADELL_F_PRE_DEV) {
     c.pre_s = c.it.pre_dev[0];
     c.pre_o = c.it.pre_dev[1];

@@ -575,7 +575,42 @@ __global__ void st_percentile_finalize(const uint32_t* __restrict__ keys, const 
   out[i] = static_cast<float>(r);
 }
 
+// One thread per crop: centre = the voxel the host's draw selected from the sample's foreground / background index
+// list, corrected like monai correct_crop_centers (allow_smaller semantics: centre clamped into
+// [size/2, shape + 1 - size/2 (as uint16) - 1], the upper bound bumped when it equals the lower one), then the
+// start of SpatialCrop(roi_center, roi_size): max(centre - size/2, 0).
+__global__ void st_posneg_starts(const adell_posneg* __restrict__ crops, int n, int32_t* __restrict__ starts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const adell_posneg c = crops[i];
+  int64_t idx = c.indices[c.pick];
+  int centre[3];
+  centre[2] = static_cast<int>(idx % c.shape[2]); idx /= c.shape[2];
+  centre[1] = static_cast<int>(idx % c.shape[1]); idx /= c.shape[1];
+  centre[0] = static_cast<int>(idx);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const int sz = c.size[a] < c.shape[a] ? c.size[a] : c.shape[a];
+    const int vs = sz / 2;
+    // np.subtract(shape + 1, size / 2).astype(uint16): float subtraction, truncation
+    int ve = static_cast<int>(static_cast<unsigned short>(static_cast<int>(static_cast<double>(c.shape[a] + 1) - static_cast<double>(sz) / 2.0)));
+    if (vs == ve) ve += 1;
+    int ctr = centre[a] > vs ? centre[a] : vs;
+    ctr = ctr < ve - 1 ? ctr : ve - 1;
+    const int st = ctr - sz / 2;
+    starts[3 * i + a] = st > 0 ? st : 0;
+  }
+}
+
 }  // namespace
+
+extern "C" int adell_posneg_starts(const adell_posneg* crops_dev, int n_crops, int32_t* starts_dev, void* stream) {
+  if (n_crops == 0) return ADELL_OK;
+  if (crops_dev == nullptr || starts_dev == nullptr || n_crops < 0) return ADELL_ERR_BAD_ARG;
+  st_posneg_starts<<<(n_crops + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(crops_dev, n_crops, starts_dev);
+  ADELL_CUDA_CHECK_LAUNCH();
+  return ADELL_OK;
+}
 
 extern "C" int adell_minmax(const adell_vol* vols_dev, int n_vols, int64_t max_n, float* out_dev, void* stream) {
   if (n_vols == 0) return ADELL_OK;

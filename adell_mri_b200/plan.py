@@ -117,6 +117,7 @@ class _Stage:
     _ARR = (
         "has_affine", "A", "interp", "padding", "pre_s", "pre_o", "clip", "clip_lo", "clip_hi",
         "post_s", "post_o", "noise_ptr", "philox_std", "philox_seed", "philox_off", "strict", "pre_dev", "grid",
+        "win_dev", "win_parent",
     )
 
     def __init__(self, size: np.ndarray):
@@ -142,6 +143,8 @@ class _Stage:
         self.pre_dev = np.zeros(n, np.uint64)
         self.grid = size.astype(np.int64, copy=True)  # output grid of the resample (where has_affine): the source size for
         #                                               RandAffined(spatial_size=None), the new size for a Spacingd resample
+        self.win_dev = np.zeros(n, np.uint64)         # device int32[3]: start of a crop window chosen on the device
+        self.win_parent = np.zeros((n, 3), np.int64)  # extents of the volume that window lives in
         self.keep = []  # tensors that must outlive the launch (noise)
 
     def take(self, idx):
@@ -312,6 +315,29 @@ class BatchPlan:
         start = np.clip(_i3(start, self.n), 0, cur)
         size = np.minimum(_i3(size, self.n), cur - start)
         self._int_op(w, "crop", start, size)
+        return self
+
+    def crop_from_device(self, win_dev: torch.Tensor, size, where=None):
+        """SpatialCrop whose START lives in device memory (``win_dev``: contiguous ``[n, 3]`` int32, one row per
+        volume; e.g. written by ``adell_posneg_starts``): the volumes become windows of ``size`` whose position K1
+        reads when it fetches their items (``ADELL_F_WIN_DEV``).  Must be the first recorded op of those volumes."""
+        w = _where(where, self.n)
+        if isinstance(win_dev, torch.Tensor):
+            if win_dev.shape != (self.n, 3) or win_dev.dtype != torch.int32 or not win_dev.is_contiguous():
+                raise ValueError("win_dev must be a contiguous [n, 3] int32 tensor")
+            self.keep.append(win_dev)
+            ptrs = win_dev.data_ptr() + 12 * np.arange(self.n, dtype=np.uint64)
+        else:   # per-volume device addresses of int32[3] rows (the caller keeps the tensors alive)
+            ptrs = np.asarray(win_dev, np.uint64).reshape(self.n)
+        st = self.st
+        touched = st.has_affine | st.pre.has_invalid() | (st.pre.off != 0).any(1) | (st.pre.sign != 1).any(1) | (st.win_dev != 0)
+        if (w & touched).any():
+            raise ValueError("a device-side crop window must be the first recorded op")
+        cur = st.pre.size
+        size = np.minimum(_i3(size, self.n), cur)
+        st.win_parent = np.where(w[:, None], cur, st.win_parent)
+        st.win_dev = np.where(w, ptrs, st.win_dev).astype(np.uint64)
+        st.pre.crop(np.zeros_like(size), size, w)
         return self
 
     def center_crop(self, roi, where=None):
@@ -498,7 +524,16 @@ class BatchPlan:
         it["src_stride"] = st.pre.sign * parent_stride
         it["src_shape"] = st.pre.size
         it["src_vlo"] = st.pre.vlo
-        it["src_vhi"] = st.pre.vhi
+        win = st.win_dev != 0
+        if win.any():
+            if (st.pre.has_invalid() & win).any():
+                raise ValueError("a device-side crop window cannot be padded before the resample")
+            # ADELL_F_WIN_DEV: src_vhi carries the parent's extent counted from the window's lowest element at start 0
+            lo = np.where(st.pre.sign > 0, st.pre.off, st.pre.off - (st.pre.size - 1))
+            it["src_vhi"] = np.where(win[:, None], st.win_parent - lo, st.pre.vhi)
+        else:
+            it["src_vhi"] = st.pre.vhi
+        it["win_dev"] = st.win_dev
         ha = st.has_affine[:, None]
         it["out_shape"] = np.where(ha, st.post.size, st.pre.size)
         it["grid_shape"] = np.where(ha, st.grid, st.pre.size)  # spatial_size=None: the affine grid has the source size
@@ -525,6 +560,7 @@ class BatchPlan:
         flags |= np.where(st.strict, _lib.F_STRICT, 0).astype(np.uint8)
         flags |= np.where(st.philox_std != 0, _lib.F_PHILOX, 0).astype(np.uint8)
         flags |= np.where(st.pre_dev != 0, _lib.F_PRE_DEV, 0).astype(np.uint8)
+        flags |= np.where(win, _lib.F_WIN_DEV, 0).astype(np.uint8)
         it["flags"] = flags
         it["dst"] = dst_ptr
         it["dst_stride"] = dst_stride

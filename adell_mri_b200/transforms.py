@@ -131,6 +131,16 @@ class ChainRecorder:
     def crop(self, start, size):
         return self._rec("crop", (), (tuple(int(x) for x in start), tuple(int(x) for x in size)))
 
+    def crop_from_device(self, win_row: torch.Tensor, size):
+        """Crop whose start is the int32[3] ``win_row`` in device memory (see BatchPlan.crop_from_device)."""
+        size = tuple(int(x) for x in size)
+        for p in self.parts:
+            if p.ops:
+                raise ValueError("a device-side crop window must be the first recorded op")
+            p.ops.append(("crop_from_device", (), (int(win_row.data_ptr()), size, win_row), False))
+            p.shape = tuple(min(c, s) for c, s in zip(p.shape, size))
+        return self
+
     def center_crop(self, roi):
         return self._rec("center_crop", (), (tuple(int(x) for x in roi),))
 
@@ -223,6 +233,9 @@ def replay_parts(parts: Sequence[_Part]) -> BatchPlan:
             dyn = [p.ops[j][2] for p in grp]
             if name == "crop":
                 plan.crop(rep(np.array([d[0] for d in dyn], np.int64)), rep(np.array([d[1] for d in dyn], np.int64)))
+            elif name == "crop_from_device":
+                plan.crop_from_device(rep(np.array([d[0] for d in dyn], np.uint64)), rep(np.array([d[1] for d in dyn], np.int64)))
+                plan.keep.extend(d[2] for d in dyn)
             elif name == "center_crop":
                 plan.center_crop(rep(np.array([d[0] for d in dyn], np.int64)))
             elif name == "pad":
@@ -670,20 +683,48 @@ class RandSpatialCropd(Randomizable, MapTransform):
 
 class FgBgToIndicesd(MapTransform):
     """``monai.transforms.FgBgToIndicesd`` †: flat indices of foreground (>0) and background
-    voxels of a (materialised, cached) label volume, kept on the host for the crop draws."""
+    voxels of a (materialised, cached) label volume.  For a label on the device the two lists STAY there
+    (int64 tensors: their lengths are host integers); for a host label they are numpy arrays."""
 
-    def __init__(self, keys, fg_postfix: str = "_fg_indices", bg_postfix: str = "_bg_indices", allow_missing_keys: bool = False):
+    def __init__(self, keys, fg_postfix: str = "_fg_indices", bg_postfix: str = "_bg_indices", allow_missing_keys: bool = False,
+                 on_device: bool | None = None):
         super().__init__(keys, allow_missing_keys)
         self.fg_postfix, self.bg_postfix = fg_postfix, bg_postfix
+        self.on_device = on_device   # None: where the label lives
 
     def __call__(self, data):
         d = dict(data)
         for k in self.key_iterator(d):
             lab = d[k].tensor() if isinstance(d[k], Pending) else torch.as_tensor(d[k])
             flat = (lab > 0).any(dim=0).reshape(-1)
-            d[k + self.fg_postfix] = torch.nonzero(flat).reshape(-1).cpu().numpy()
-            d[k + self.bg_postfix] = torch.nonzero(~flat).reshape(-1).cpu().numpy()
+            fg, bg = torch.nonzero(flat).reshape(-1), torch.nonzero(~flat).reshape(-1)
+            if not (self.on_device if self.on_device is not None else lab.is_cuda):
+                fg, bg = fg.cpu().numpy(), bg.cpu().numpy()
+            # (device lists: only their lengths are known to the host, which is all the crop draws need —
+            # RandCropByPosNegLabeld then selects the centres with adell_posneg_starts)
+            d[k + self.fg_postfix], d[k + self.bg_postfix] = fg, bg
         return d
+
+
+def _posneg_starts(picks, label_shape, size, device) -> torch.Tensor:
+    """``[len(picks), 3]`` int32 crop starts on ``device`` for host draws ``picks = [(index list tensor, entry)]``."""
+    import ctypes as C
+
+    from . import _lib, engine
+
+    n = len(picks)
+    arr = np.zeros(n, np.dtype(_lib.PosNeg))
+    arr["indices"] = [lst.data_ptr() for lst, _ in picks]
+    arr["pick"] = [p for _, p in picks]
+    arr["shape"] = [int(x) for x in label_shape]
+    arr["size"] = [int(x) for x in size]
+    out = torch.empty((n, 3), dtype=torch.int32, device=device)
+    with torch.cuda.device(device):
+        desc = engine._stage(arr.view(np.uint8).reshape(-1), device)
+        _lib.check(_lib.load().adell_posneg_starts(desc.data_ptr(), n, out.data_ptr(),
+                                                   C.c_void_p(torch.cuda.current_stream(device).cuda_stream)), "adell_posneg_starts")
+    out._adell_keep = [lst for lst, _ in picks]   # the lists must outlive the select kernel's launch
+    return out
 
 
 class RandCropByPosNegLabeld(Randomizable, MapTransform):
@@ -704,13 +745,23 @@ class RandCropByPosNegLabeld(Randomizable, MapTransform):
 
     def randomize(self, label_shape, fg_indices, bg_indices) -> None:
         size = [min(int(s), int(d)) if s > 0 else int(d) for s, d in zip(self.spatial_size, label_shape)]
-        fg_indices, bg_indices = np.asarray(fg_indices), np.asarray(bg_indices)
+        if not isinstance(fg_indices, torch.Tensor):
+            fg_indices, bg_indices = np.asarray(fg_indices), np.asarray(bg_indices)
         pos_ratio = self.pos_ratio
         if len(fg_indices) == 0 or len(bg_indices) == 0:
             if len(fg_indices) == 0 and len(bg_indices) == 0:
                 raise ValueError("No sampling location available.")
             pos_ratio = 0 if len(fg_indices) == 0 else 1
         centers = []
+        if isinstance(fg_indices, torch.Tensor):
+            # device lists: the same two draws per crop; the entry itself is looked up on the device
+            self._picks = []
+            for _ in range(self.num_samples):
+                use_fg = self.R.rand() < pos_ratio
+                lst = fg_indices if use_fg else bg_indices
+                self._picks.append((lst, int(self.R.randint(len(lst)))))
+            self.centers, self._size = None, size
+            return
         for _ in range(self.num_samples):
             indices_to_use = fg_indices if self.R.rand() < pos_ratio else bg_indices
             idx = indices_to_use[self.R.randint(len(indices_to_use))]
@@ -734,6 +785,18 @@ class RandCropByPosNegLabeld(Randomizable, MapTransform):
             fg, bg = torch.nonzero(flat).reshape(-1).cpu().numpy(), torch.nonzero(~flat).reshape(-1).cpu().numpy()
         self.randomize(lab.spatial_shape, fg, bg)
         out = []
+        if self.centers is None:
+            # centres selected on the device: adell_posneg_starts writes the crop starts where K1 reads them
+            # (ADELL_F_WIN_DEV); nothing about the label's content ever reaches the host
+            win = _posneg_starts(self._picks, lab.spatial_shape, self._size, lab.device)
+            for i in range(self.num_samples):
+                r = dict(d)
+                for k in self.key_iterator(d):
+                    e = as_pending(d[k]).clone()
+                    e.plan.crop_from_device(win[i], self._size)
+                    r[k] = e
+                out.append(r)
+            return out
         for center in self.centers:
             r = dict(d)
             for k in self.key_iterator(d):

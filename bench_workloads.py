@@ -95,14 +95,20 @@ class AffineA(Workload):
         self._shape = np.tile(np.asarray(self.shape, np.int64), (self.N, 1))
         self._dptr = (self.out.data_ptr() + esz * self.out.stride(0) * np.arange(self.N, dtype=np.int64)).astype(np.uint64)
         self.last_mats = None
+        self._chains = None
 
     def step(self, i):
         fired, p = self.sampler.draw_batch(self.N, n_keys=1)
         mats = geometry.compose_affine(p["rotate"], p["shear"], p["translate"], p["scale"], batch=self.N)
         self.last_mats = mats
-        plan = BatchPlan.from_arrays(self._ptr, self._stride, self._dtype, self._shape, self.dev, [self.src])
-        plan.affine(mats, "bilinear", "reflection")
-        engine.execute_ptrs(plan, self._dptr, self._stride, keep=[self.out])
+        if self._chains is None:   # static part of the adell_chain descriptors: one per volume
+            from adell_mri_b200.pipelines import _chain_template
+            self._chains = _chain_template(self._ptr, self._stride, self._dtype, self._shape, self._dptr, self._stride,
+                                           ["bilinear"] * self.N, "reflection", False)
+            self._chains["flags"] |= _lib.CHAIN_AFFINE
+        ch = self._chains.copy()
+        ch["A"] = mats[:, :3].reshape(self.N, 12)
+        engine.prepare_chain_steps(ch, [self.N], self.dev, keep=[self.src, self.out]).run(0)
 
     def parity(self):
         from oracle import monai_restated as M

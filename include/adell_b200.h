@@ -75,6 +75,14 @@ extern "C" {
 #define ADELL_F_TMAP 0x20     /* tmap holds a valid CUtensorMap of the valid source box (staged path)*/
 #define ADELL_F_FASTCOORD 0x40 /* trilinear only: incremental coordinates (<=1e-4 contract), no
                                   bit-faithful replay of the MONAI/ATen fp32 coordinate chain         */
+#define ADELL_F_WIN_DEV 0x80  /* the resample domain is a WINDOW of a parent volume whose start is only known
+                                 on the device (RandCropByPosNegLabeld centres selected by adell_posneg_starts):
+                                 src / src_stride describe the window as if it started at parent index (0,0,0),
+                                 src_shape is the window's extent, src_vlo must be 0 and src_vhi holds the
+                                 PARENT's extents; the kernel reads win_dev[0..2] (int32, 0 <= start <=
+                                 parent - window) when it fetches the item and shifts the source by it.
+                                 Resampled items need border / reflection padding (zeros padding would have to
+                                 stop at the window, which the staged box cannot know: such items are refused) */
 
 /*
  * One unit of work = one (sample, key): the whole reference chain for one volume,
@@ -101,7 +109,7 @@ typedef struct __attribute__((aligned(64))) adell_item {
   float* dst;              /* fp32 output, element o=(0,0,0)                                        */
   const float* noise;      /* optional injected noise, contiguous [O0,O1,O2] fp32, or NULL          */
   const float* pre_dev;    /* optional device {scale, offset} (ADELL_F_PRE_DEV)                     */
-  const void* tmap_base;   /* device address of tmap box element (0,0,0) (informational)            */
+  const int32_t* win_dev;  /* ADELL_F_WIN_DEV: device int32[3], start of the source window in the parent  */
   int64_t src_stride[3];   /* signed, in elements                                                   */
   int64_t dst_stride[3];   /* in elements                                                           */
   int32_t src_shape[3];    /* S                                                                      */
@@ -363,6 +371,21 @@ int adell_hist_select(const uint64_t* bins_dev, int n_hist, int n_sel, int pass_
  * [n_vols][n_q][2], frac_dev [n_vols][n_q] float64, out_dev [n_vols][n_q] fp32. */
 int adell_percentile_finalize(const uint32_t* keys_dev, const double* frac_dev, int n_vols, int n_q,
                               int dtype, float* out_dev, void* stream);
+
+/* -- RandCropByPosNegLabeld: crop windows selected on the device ----------------------------- */
+/* One crop: the host made the two draws of monai generate_pos_neg_label_crop_centers
+ * (`R.rand() < pos_ratio` picks the foreground or the background list, `R.randint(len(list))` the entry:
+ * /root/reference/adell_mri/transform_factory/augmentations.py:147-158 -> RandCropByPosNegLabeld); the index
+ * lists themselves (FgBgToIndicesd, transform_factory/transforms.py:196-203) stay on the device. */
+typedef struct adell_posneg {
+  const int64_t* indices; /* device: the chosen list (flat voxel indices of the label volume)   */
+  int64_t pick;           /* host draw: entry of that list                                        */
+  int32_t shape[3];       /* label volume extents                                                 */
+  int32_t size[3];        /* crop size (clipped to shape)                                         */
+} adell_posneg;
+/* starts_dev[3*i..] = start of crop i (centre corrected like monai correct_crop_centers, then
+ * SpatialCrop(roi_center, roi_size)): what an ADELL_F_WIN_DEV item's win_dev points at. */
+int adell_posneg_starts(const adell_posneg* crops_dev, int n_crops, int32_t* starts_dev, void* stream);
 
 /* -- K4: batch-level mixing after collation ------------------------------------------------ */
 /* (partial) mixup of a collated fp32 batch [batch, per_sample] in one pass

@@ -130,7 +130,22 @@ static float voxel(const adell_item* it, int g0, int g1, int g2, float pre_s, fl
 
 int adell_ref_gather(const adell_item* items, int n_items) {
   for (int n = 0; n < n_items; ++n) {
+    adell_item shifted;
     const adell_item* it = items + n;
+    if (it->flags & ADELL_F_WIN_DEV) {
+      /* window of a parent volume whose start is read at run time (here: from host memory): the item
+         describes the window at start (0,0,0) */
+      const int es = it->src_dtype == ADELL_F32 ? 4 : (it->src_dtype == ADELL_I16 ? 2 : 1);
+      int64_t shift = 0;
+      memcpy(&shifted, it, sizeof(shifted));
+      for (int a = 0; a < 3; ++a) {
+        const int64_t st = it->src_stride[a];
+        shift += (int64_t)it->win_dev[a] * (st < 0 ? -st : st);
+        shifted.src_vhi[a] = it->src_shape[a]; /* src_vhi carried the parent's extents */
+      }
+      shifted.src = (const char*)it->src + shift * es;
+      it = &shifted;
+    }
     float pre_s = it->pre_scale, pre_o = it->pre_offset;
     if (it->flags & ADELL_F_PRE_DEV) {
       pre_s = it->pre_dev[0];
