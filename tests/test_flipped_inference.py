@@ -58,3 +58,61 @@ def test_flipped_inference_on_the_device_equals_the_reference_recipe():
     assert torch.allclose(got, _ref_call(fn, x, flips), rtol=0, atol=1e-6)
     # channel flips are not voxel flips: they go through torch.flip like the reference
     assert torch.equal(FlippedInference(fn, [[1]]).flip(x, [1]), torch.flip(x, (1,)))
+
+
+def _ref_sliding(X, fn, window, stride, n_classes, ibs):
+    """The reference's SlidingWindowSegmentation.__call__ restated for one batched tensor [B, C, H, W, D]."""
+    sh = X.shape[-3:]
+    out = torch.zeros(X.shape[0], n_classes, *sh, device=X.device)
+    den = torch.zeros_like(out)
+    coords = []
+    for i in range(0, sh[0], stride[0]):
+        for j in range(0, sh[1], stride[1]):
+            for k in range(0, sh[2], stride[2]):
+                c = []
+                for a, s in zip((i, j, k), range(3)):
+                    x1, x2 = a, a + window[s]
+                    if x2 > sh[s]:
+                        x1, x2 = sh[s] - window[s], sh[s]
+                    c.append((x1, x2))
+                coords.append(tuple(c))
+    for b0 in range(0, len(coords), ibs):
+        cc = coords[b0:b0 + ibs]
+        batch = torch.cat([X[..., c[0][0]:c[0][1], c[1][0]:c[1][1], c[2][0]:c[2][1]] for c in cc], 0)
+        res = torch.split(fn(batch), X.shape[0], 0)
+        for r, c in zip(res, cc):
+            out[..., c[0][0]:c[0][1], c[1][0]:c[1][1], c[2][0]:c[2][1]] += r
+            den[..., c[0][0]:c[0][1], c[1][0]:c[1][1], c[2][0]:c[2][1]] += 1.0
+    return out / den
+
+
+def test_sliding_window_matches_the_reference_recipe_on_cpu():
+    from adell_mri_b200.inference import SlidingWindowSegmentation
+
+    x = torch.rand(2, 3, 20, 18, 10)
+    fn = lambda b: b[:, :2] * 2 + b[:, 2:3]
+    sw = SlidingWindowSegmentation([8, 8, 4], fn, n_classes=2, stride=[6, 5, 3], inference_batch_size=4)
+    assert torch.allclose(sw(x), _ref_sliding(x, fn, [8, 8, 4], [6, 5, 3], 2, 4))
+    # a dict of inputs, unbatched arrays
+    fn_d = lambda b: b["a"][:, :1] + torch.as_tensor(b["b"][:, :1])
+    got = SlidingWindowSegmentation([8, 8, 4], fn_d, n_classes=1, inference_batch_size=2)({"a": x[0], "b": x[1]})
+    assert got.shape == (1, 20, 18, 10)
+
+
+@pytest.mark.gpu
+def test_sliding_window_gathers_each_inference_batch_with_one_k1_launch():
+    from adell_mri_b200 import engine
+    from adell_mri_b200.inference import SlidingWindowSegmentation, gather_windows
+
+    x = torch.rand(2, 3, 40, 36, 24, device="cuda:0")
+    coords = [((0, 16), (4, 20), (8, 16)), ((24, 40), (20, 36), (16, 24)), ((5, 21), (1, 17), (3, 11))]
+    before = engine.launch_count
+    got = gather_windows(x, coords, batched=True)
+    assert engine.launch_count - before == 1
+    want = torch.cat([x[..., c[0][0]:c[0][1], c[1][0]:c[1][1], c[2][0]:c[2][1]] for c in coords], 0)
+    assert torch.equal(got, want)
+    assert torch.equal(gather_windows(x[0], coords, batched=False),
+                       torch.stack([x[0][..., c[0][0]:c[0][1], c[1][0]:c[1][1], c[2][0]:c[2][1]] for c in coords], 0))
+    fn = lambda b: torch.sigmoid(b[:, :2] * 3 - b[:, 2:3])
+    sw = SlidingWindowSegmentation([16, 16, 8], fn, n_classes=2, stride=[12, 12, 8], inference_batch_size=5)
+    assert torch.allclose(sw(x), _ref_sliding(x, fn, [16, 16, 8], [12, 12, 8], 2, 5), rtol=0, atol=1e-6)

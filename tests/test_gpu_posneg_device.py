@@ -103,7 +103,7 @@ def test_unet_crop_sandwich_device_selection_equals_host_selection(n_crops):
             fgbg = T.FgBgToIndicesd("mask", on_device=on_device)
             aug = F.get_augmentations_unet(["affine", "flip"], keys + ["mask"], keys, [], random_crop_size=rc, has_label=True,
                                            n_crops=n_crops, flip_axis=[0, 1, 2]).set_random_state(11)
-            tf = F.SegmentationTransforms(keys + ["mask"], keys, None, keys, [])
+            tf = F.SegmentationTransforms(keys + ["mask"], keys, ["mask"], keys, [])
             post = T.Compose(tf.post_transforms())
             batch = []
             for s in samples:
