@@ -58,9 +58,6 @@ constexpr uint32_t K1_MAGIC_BITS = 0x4B400000u;
 #endif
 __device__ __forceinline__ void k1_plain_store(float4* p, float4 v) { *p = v; }
 __device__ __forceinline__ void k1_wt_store(float4* p, float4 v) { __stwt(p, v); }
-#ifndef K1_WAIT_NS
-#define K1_WAIT_NS 128u                         // back-off of the producer / hand-over polling loops
-#endif
 #ifndef K1_NP
 #define K1_NP 1                                 // trilinear voxel PAIRS (packed fp32) per consumer-thread iteration (1 measured best: smaller loop body)
 #endif
@@ -115,33 +112,27 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Waits are done by the hardware, not by polling: mbarrier.try_wait takes a suspend-time hint and parks the thread
+// until the phase completes (or the hint expires, then the loop retries).  Round 1 polled — try_wait without a hint
+// returns after a short system-dependent time, and the nanosleep(128) between the polls of the producer / hand-over
+// warps turned out to last ~14 ns — so that 11.5 % of all instructions the kernel executed were the polling loops of
+// warps that had nothing to do (ncu source page, profiles/r02_k1_ncu_summary.md), competing for issue slots with the
+// consumer warps of their schedulers.
+#ifndef K1_WAIT_HINT_NS
+#define K1_WAIT_HINT_NS 0x989680u   // 10 ms: effectively "until the barrier flips"
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra WAIT_DONE;\n"
       "bra WAIT_LOOP;\n"
       "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(K1_WAIT_HINT_NS) : "memory");
 }
-// Same, for the producer / hand-over warps, which wait for thousands of cycles at a time: back off
-// with nanosleep between polls, so that a warp that is merely waiting for its turn does not take
-// issue slots from the consumer warps on its scheduler (the polling loops were ~8 % of all issued
-// instructions).
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "RWAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra RWAIT_DONE;\n"
-      "nanosleep.u32 %2;\n"
-      "bra RWAIT_LOOP;\n"
-      "RWAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(K1_WAIT_NS) : "memory");
-}
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 // The descriptor lives in global memory and was written by a host copy: the tensormap proxy
 // must acquire it before the TMA unit reads it (CUDA programming guide, "tensor map in global
 // memory").
@@ -675,28 +666,6 @@ __device__ __forceinline__ k1_f2 k1_lerp8x2(const K1Vox2& x, const k1_f2* t) {
 
 // Trilinear, plain tiles, RM = 0 / 1: NP pairs of voxels per iteration with packed arithmetic, a
 // one-voxel-at-a-time tail.  Same operations (and roundings) per voxel as the scalar loop.
-// Four shared-memory taps that are only FETCHED by the lanes with share == 0; the others take the values they
-// already hold in registers (f0..f3).  A predicated-off lane issues no shared-memory access at all, so it adds
-// neither bytes nor bank conflicts to the load's wavefronts.
-__device__ __forceinline__ void lds4_unless(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, int share,
-                                            float f0, float f1, float f2, float f3, float& v0, float& v1, float& v2, float& v3) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.eq.s32 p, %8, 0;\n"
-      "mov.f32 %0, %9;\n"
-      "mov.f32 %1, %10;\n"
-      "mov.f32 %2, %11;\n"
-      "mov.f32 %3, %12;\n"
-      "@p ld.shared.f32 %0, [%4];\n"
-      "@p ld.shared.f32 %1, [%5];\n"
-      "@p ld.shared.f32 %2, [%6];\n"
-      "@p ld.shared.f32 %3, [%7];\n"
-      "}\n"
-      : "=&f"(v0), "=&f"(v1), "=&f"(v2), "=&f"(v3)
-      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(share), "f"(f0), "f"(f1), "f"(f2), "f"(f3));
-}
-
 // two taps (one of each voxel of the pair) -> packed fp32; integer sources: one packed FADD2 removes the bias of both
 template <int DT>
 __device__ __forceinline__ k1_f2 tap_pair(uint32_t aA, uint32_t aB) {
@@ -739,20 +708,6 @@ __device__ __forceinline__ void k1_tile_staged_trilinear(const K1Tile& tl, const
     float* p = f.dst + m.ii * f.ds0 + m.dk * f.ds2 + (m.j0 - m.s1) * ds1;
     float fj = static_cast<float>(m.j0);
     int cnt = m.cnt;
-    if constexpr (DT == ADELL_F32 && NP == 1) {
-      // Tap sharing along the march.  A thread walks the rows dj, dj + 1, ... of one column; the source coordinate
-      // advances by D1 per row — for the rotations of the reference that is about one cell along source axis 1 and
-      // a fraction of a cell along the others — so most of the time the cell of a voxel is the cell of the previous
-      // one plus (0, +1, 0): its four low-row taps ARE the previous voxel's four high-row taps.  Those lanes keep
-      // them in registers and skip the loads (predicated off): fewer bytes through the shared-memory data pipe,
-      // which bounds this loop, and fewer bank-conflict replays for the lanes that do load.  Same values, same
-      // arithmetic: the results are bit-identical to loading all eight taps.
-      uint32_t prevB = 0xffffffffu;                       // address of tap (0,0,0) of the previous row's voxel
-      float pb2 = 0.0f, pb3 = 0.0f, pb6 = 0.0f, pb7 = 0.0f;  // its high-row taps
-#pragma unroll 1
-      for (; cnt >= 2; cnt -= 2) {
-        const K1Vox2 x = k1_fast_vox2<RMASK>(h, q, f2_pack(fj, fj + fstep), ES);
-        const int sA = x.aA == prevB + o1, sB = x.aB == x.aA + o1;
         const float a2 = lds_f32(x.aA + o1), a3 = lds_f32(x.aA + o1 + ES), a6 = lds_f32(x.aA + o0 + o1), a7 = lds_f32(x.aA + o0 + o1 + ES);
         const float b2 = lds_f32(x.aB + o1), b3 = lds_f32(x.aB + o1 + ES), b6 = lds_f32(x.aB + o0 + o1), b7 = lds_f32(x.aB + o0 + o1 + ES);
         float a0, a1, a4, a5, b0, b1, b4, b5;
@@ -769,6 +724,7 @@ __device__ __forceinline__ void k1_tile_staged_trilinear(const K1Tile& tl, const
         prevB = x.aB; pb2 = b2; pb3 = b3; pb6 = b6; pb7 = b7;
       }
     }
+#endif
 #pragma unroll 1
     for (; cnt >= 2 * NP; cnt -= 2 * NP) {
       K1Vox2 x[NP];
