@@ -708,23 +708,6 @@ __device__ __forceinline__ void k1_tile_staged_trilinear(const K1Tile& tl, const
     float* p = f.dst + m.ii * f.ds0 + m.dk * f.ds2 + (m.j0 - m.s1) * ds1;
     float fj = static_cast<float>(m.j0);
     int cnt = m.cnt;
-        const float a2 = lds_f32(x.aA + o1), a3 = lds_f32(x.aA + o1 + ES), a6 = lds_f32(x.aA + o0 + o1), a7 = lds_f32(x.aA + o0 + o1 + ES);
-        const float b2 = lds_f32(x.aB + o1), b3 = lds_f32(x.aB + o1 + ES), b6 = lds_f32(x.aB + o0 + o1), b7 = lds_f32(x.aB + o0 + o1 + ES);
-        float a0, a1, a4, a5, b0, b1, b4, b5;
-        lds4_unless(x.aA, x.aA + ES, x.aA + o0, x.aA + o0 + ES, sA, pb2, pb3, pb6, pb7, a0, a1, a4, a5);
-        lds4_unless(x.aB, x.aB + ES, x.aB + o0, x.aB + o0 + ES, sB, a2, a3, a6, a7, b0, b1, b4, b5);
-        const k1_f2 t[8] = {f2_pack(a0, b0), f2_pack(a1, b1), f2_pack(a2, b2), f2_pack(a3, b3),
-                            f2_pack(a4, b4), f2_pack(a5, b5), f2_pack(a6, b6), f2_pack(a7, b7)};
-        float za, zb;
-        f2_unpack(f2_fma(k1_lerp8x2(x, t), G2, RMASK == 3 ? f2_fma(x.w, WB2, PO2) : B2), za, zb);
-        p[0] = za;
-        p[pstep] = zb;
-        p += 2 * pstep;
-        fj += 2.0f * fstep;
-        prevB = x.aB; pb2 = b2; pb3 = b3; pb6 = b6; pb7 = b7;
-      }
-    }
-#endif
 #pragma unroll 1
     for (; cnt >= 2 * NP; cnt -= 2 * NP) {
       K1Vox2 x[NP];
