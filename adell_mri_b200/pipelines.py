@@ -30,7 +30,7 @@ import torch
 
 from . import _lib, engine, geometry
 from .plan import BatchPlan
-from .sampling import RandAffineSampler, child_seeds
+from .sampling import RandAffineSampler, child_seeds, draw_used_uniforms
 
 CHAIN_DTYPE = engine.CHAIN_DTYPE
 _FLIP_BITS = np.array([1, 2, 4], np.uint8)
@@ -577,6 +577,15 @@ class _WorkhorseDraws:
                 self.samplers[m] = RandAffineSampler(prob=1.0, **_ssl_member_ranges(m, max_mult))
         self.noise_std = 1 * max_mult
         self.shift, self.scale = 0.5 * max_mult, 0.5 * max_mult
+        # per spatial member: which of the 12 parameter columns (rotate 0-2, shear 3-5, translate 6-8, scale 9-11) its
+        # three uniforms fill, and the affine map u -> lo + (hi - lo) u (+ 1 for scale) of numpy's uniform()
+        self._cols = {}
+        for m, smp in self.samplers.items():
+            base, rng, add = next((b, r, a) for b, r, a in ((0, smp.rotate_range, 0.0), (3, smp.shear_range, 0.0),
+                                                            (6, smp.translate_range, 0.0), (9, smp.scale_range, 1.0)) if r is not None)
+            lo = np.array([(f[0] if isinstance(f, (tuple, list)) else -f) for f in rng], np.float64)
+            hi = np.array([(f[1] if isinstance(f, (tuple, list)) else f) for f in rng], np.float64)
+            self._cols[m] = (base, lo, hi - lo, add)
 
     def set_random_state(self, seed):
         self.R = np.random.RandomState(seed)
@@ -598,8 +607,12 @@ class _WorkhorseDraws:
             if use.size == 0:
                 continue
             if m in self.samplers:
-                _, p = self.samplers[m].draw_batch(use.size, n_keys=self.n_keys)
-                spatial.append((m, use, p))
+                smp = self.samplers[m]
+                if smp.R is not smp.R_inner:   # (separately seeded streams: one numpy call each)
+                    spatial.append((m, use, draw_used_uniforms(smp, use.size, self.n_keys)))
+                else:
+                    _, p = smp.draw_batch(use.size, n_keys=self.n_keys)
+                    spatial.append((m, use, p))
             elif m == "gaussian_noise":
                 self.R_outer[m].random_sample(use.size)
                 vals = []
@@ -618,14 +631,19 @@ class _WorkhorseDraws:
                 out[m] = (use, -f + (f - (-f)) * u)
         if spatial:
             n = sum(u.size for _, u, _ in spatial)
-            full = {"rotate": np.zeros((n, 3)), "shear": np.zeros((n, 3)), "translate": np.zeros((n, 3)), "scale": np.ones((n, 3))}
+            par = np.zeros((n, 12))
+            par[:, 9:] = 1.0
             o = 0
-            for _, use, p in spatial:
-                for name, arr in p.items():
-                    if arr.shape[1]:
-                        full[name][o:o + use.size, : arr.shape[1]] = arr
+            for m, use, p in spatial:
+                if isinstance(p, np.ndarray):        # raw uniforms of the used randomize
+                    base, lo, span, add = self._cols[m]
+                    par[o:o + use.size, base:base + 3] = lo + span * p + add
+                else:
+                    for b, name in ((0, "rotate"), (3, "shear"), (6, "translate"), (9, "scale")):
+                        if p[name].shape[1]:
+                            par[o:o + use.size, b:b + p[name].shape[1]] = p[name]
                 o += use.size
-            mats = geometry.compose_affine(full["rotate"], full["shear"], full["translate"], full["scale"], batch=n)
+            mats = geometry.compose_affine(par[:, 0:3], par[:, 3:6], par[:, 6:9], par[:, 9:12], batch=n)
             o = 0
             for m, use, _ in spatial:
                 out[m] = (use, mats[o:o + use.size])
@@ -718,6 +736,34 @@ class SSLBatchAugmenter(_BatchBase):
         ch = np.arange(nc)[None, :]
         vox = int(np.prod(plan.shape[0]))
         eye = np.eye(4, dtype=np.float32)
+        # Per view: where every member's per-use values live, so that a slot of the whole batch is gathered with a few
+        # fancy-index operations instead of a Python loop over the members.
+        nm = len(self.members)
+        kind = np.array([0 if m in self.views[0].samplers else (1 if m == "scale_intensity" else (2 if m == "shift_intensity" else 3))
+                         for m in self.members])
+        tables = []
+        for v in range(2):
+            choice, draws = params["choice"][v], params["draws"][v]
+            used = np.zeros((nm, B), bool)
+            used[choice.reshape(-1), np.repeat(np.arange(B), self.N)] = True
+            pos = np.cumsum(used, axis=1) - 1                       # index of sample b in member mi's use list
+            off = np.zeros(nm, np.int64)                            # start of member mi inside the concatenated values of its kind
+            cat = {0: [], 1: [], 2: [], 3: []}
+            cnt = {0: 0, 1: 0, 2: 0, 3: 0}
+            for mi, m in enumerate(self.members):
+                if m not in draws:
+                    continue
+                k = int(kind[mi])
+                off[mi] = cnt[k]
+                vals = draws[m][1]
+                cat[k].append(vals)
+                cnt[k] += len(vals)
+            mats = np.concatenate(cat[0]) if cat[0] else np.zeros((0, 4, 4), np.float32)
+            scv = np.concatenate(cat[1]) if cat[1] else np.zeros(0)
+            shv = np.concatenate(cat[2]) if cat[2] else np.zeros(0)
+            noise_vals = [x for lst in cat[3] for x in lst]          # philox: (std, seed) pairs; injected: arrays
+            tables.append((pos, off, mats, scv, shv, noise_vals))
+        barange = np.arange(B)
         for s in range(self.N):
             # Slot s of every (sample, view): each volume applies exactly ONE member here, so the members of a slot
             # touch disjoint volumes and collapse into at most one affine / one intensity / one noise record for the
@@ -727,46 +773,48 @@ class SSLBatchAugmenter(_BatchBase):
             A[:] = eye
             has_aff = np.zeros(n, bool)
             sc, of, has_int = np.ones(n), np.zeros(n), np.zeros(n, bool)
-            std, seed, off = np.zeros(n, np.float32), np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+            std, seed, off_p = np.zeros(n, np.float32), np.zeros(n, np.uint64), np.zeros(n, np.uint64)
             has_phx = np.zeros(n, bool)
             noise = None
             for v in range(2):
-                choice, draws = params["choice"][v], params["draws"][v]
-                for mi, m in enumerate(self.members):
-                    sel = np.nonzero(choice[:, s] == mi)[0]
-                    if sel.size == 0:
-                        continue
-                    use, vals = draws[m]
-                    pos = np.searchsorted(use, sel)                    # index of each selected sample in the member's use list
-                    vidx = (sel[:, None] * 2 + v) * nc + ch            # [len(sel), nc] volume indices (order [b, view, channel])
-                    if m in self.views[v].samplers:
-                        A[vidx] = np.asarray(vals)[pos][:, None]
-                        has_aff[vidx] = True
-                    elif m == "scale_intensity":
-                        sc[vidx] = (1 + np.asarray(vals)[pos]).astype(np.float32)[:, None]
-                        has_int[vidx] = True
-                    elif m == "shift_intensity":
-                        of[vidx] = np.asarray(vals)[pos].astype(np.float32)[:, None]
-                        has_int[vidx] = True
-                    elif self.noise == "philox":
-                        std[vidx] = np.array([vals[q][0] for q in pos], np.float32)[:, None]
-                        seed[vidx] = np.array([vals[q][1] for q in pos], np.uint64)[:, None]
-                        off[vidx] = (np.arange(nc, dtype=np.uint64) * np.uint64(vox))[None, :]
-                        has_phx[vidx] = True
+                pos, off, mats, scv, shv, noise_vals = tables[v]
+                mi = params["choice"][v][:, s]                       # member of every sample in this slot
+                k = kind[mi]
+                where = off[mi] + pos[mi, barange]                   # row of the sample's value among its kind's values
+                vol = (barange[:, None] * 2 + v) * nc + ch           # [B, nc] volume indices (order [b, view, channel])
+                sel = k == 0
+                if sel.any():
+                    A[vol[sel]] = mats[where[sel]][:, None]
+                    has_aff[vol[sel]] = True
+                sel = k == 1
+                if sel.any():
+                    sc[vol[sel]] = (1 + scv[where[sel]]).astype(np.float32)[:, None]
+                    has_int[vol[sel]] = True
+                sel = k == 2
+                if sel.any():
+                    of[vol[sel]] = shv[where[sel]].astype(np.float32)[:, None]
+                    has_int[vol[sel]] = True
+                sel = np.nonzero(k == 3)[0]
+                if sel.size:
+                    if self.noise == "philox":
+                        std[vol[sel]] = np.array([noise_vals[q][0] for q in where[sel]], np.float32)[:, None]
+                        seed[vol[sel]] = np.array([noise_vals[q][1] for q in where[sel]], np.uint64)[:, None]
+                        off_p[vol[sel]] = (np.arange(nc, dtype=np.uint64) * np.uint64(vox))[None, :]
+                        has_phx[vol[sel]] = True
                     else:
                         if noise is None:
                             noise = [None] * n
-                        for b, q in zip(sel, pos):
-                            t = torch.from_numpy(vals[q])
+                        for b, q in zip(sel, where[sel]):
+                            t = torch.from_numpy(noise_vals[q])
                             t = t.pin_memory().to(dev, non_blocking=True) if dev.type == "cuda" else t
                             for c in range(nc):
-                                noise[int(vidx[0, 0] - sel[0] * 2 * nc + b * 2 * nc) + c] = t[c]
+                                noise[int(vol[b, c])] = t[c]
             if has_aff.any():
                 plan.affine(A, "bilinear", "zeros", where=has_aff)
             if has_int.any():
                 plan.intensity(scale=sc, offset=of, where=has_int)
             if has_phx.any():
-                plan.add_philox_noise(std, seed, off, where=has_phx)
+                plan.add_philox_noise(std, seed, off_p, where=has_phx)
             if noise is not None:
                 plan.add_noise(noise)
         return plan, params

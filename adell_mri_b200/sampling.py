@@ -135,6 +135,17 @@ class RandAffineSampler:
         return fired, self._params_from_uniforms(used)
 
 
+def draw_used_uniforms(smp: RandAffineSampler, m: int, n_keys: int) -> np.ndarray:
+    """``m`` consecutive calls of a sampler that ALWAYS fires (prob >= 1, e.g. the workhorse members): the raw
+    uniforms ``[m, K]`` of the USED randomize of each call, the three streams advanced exactly as ``m`` calls of
+    :meth:`RandAffineSampler.draw` would (one numpy call per stream)."""
+    K = smp._n_per_randomize()
+    calls = 2 + n_keys
+    smp.R.random_sample(m)
+    smp.R_inner.random_sample(m * (1 + n_keys))
+    return smp.R_grid.random_sample(m * calls * K).reshape(m, calls, K)[:, 1] if K else np.zeros((m, 0))
+
+
 def child_seeds(seed: int, n: int) -> list[int]:
     """``Compose.set_random_state(seed)``: one ``R.randint(MAX_SEED, dtype=uint32)`` per Randomizable child †."""
     R = np.random.RandomState(seed)
