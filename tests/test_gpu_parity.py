@@ -505,3 +505,37 @@ def test_border_tiles_entirely_outside_on_a_reversed_axis(strict, seed):
             assert torch.equal(got, ref), i
         else:
             assert torch.allclose(got, ref, rtol=1e-4, atol=1e-4), (i, float((got - ref).abs().max()))
+
+
+@pytest.mark.parametrize("padding", ["zeros", "border", "reflection"])
+@pytest.mark.parametrize("shape", [(128, 128, 32), (96, 80, 48)])
+def test_strong_zooms_take_the_small_tile_shapes_and_match_the_oracle(shape, padding):
+    """The workhorse's scale members draw factors around 2 (reference quirk) and fast mode
+    multiplies them: footprints that the regular tile shapes cannot stage within the preferred box get the small
+    shapes (8x16x16 ... 4x8x16) instead of a ~100 KB box that would leave the launch with one ring stage per stream."""
+    import ctypes as C
+
+    from adell_mri_b200 import _lib, engine
+
+    R = np.random.RandomState(sum(shape))
+    img = torch.from_numpy(R.rand(1, *shape).astype(np.float32))
+    dev = img[0].to(DEV)
+    seen = set()
+    for trial, scale in enumerate([(2.0, 1.0, 1.0), (1.0, 2.1, 1.0), (3.1, 1.9, 1.1), (1.0, 1.0, 2.0), (2.0, 2.0, 2.0), (0.4, 0.5, 1.0)]):
+        rot = R.uniform(-0.3, 0.3, 3)
+        A = M.compose_affine(list(rot), None, list(R.uniform(-4, 4, 3)), list(scale))
+        for mode in ("bilinear", "nearest"):
+            plan = BatchPlan([dev]).affine(A.numpy(), mode, padding)
+            out = torch.empty(shape, device=DEV)
+            items = plan.build_launches(np.array([out.data_ptr()], np.uint64), np.array([out.stride()], np.int64), None)[-1]
+            buf, n, info = engine.pack_launch(items)
+            it = buf[: n * engine.ISZ].view(engine.ITEM_DTYPE)[0]
+            seen.add((int(it["kind"]), tuple(int(x) for x in it["tile_dim"])))
+            assert info.smem_bytes <= 56 * 1024, (scale, info.smem_bytes)       # never the single-stage regime
+            ref = M.affine_resample(img, A, mode, padding)[0]
+            got = run_plan_cuda(BatchPlan([dev]).affine(A.numpy(), mode, padding))[0].cpu()
+            if mode == "nearest":
+                assert mismatch(got, ref) == 0, (scale, padding)
+            else:
+                assert torch.allclose(got, ref, rtol=1e-4, atol=1e-4), (scale, padding, float((got - ref).abs().max()))
+    assert any(k == 1 and t[0] * t[1] * t[2] < 16 * 16 * 16 for k, t in seen), seen     # some item did take a small shape
