@@ -1641,7 +1641,7 @@ struct K1Tuning {
     copy_t0 = num("ADELL_K1_COPY_T0", 8, 32, K1_COPY_T0);
     if (copy_t0 != 8 && copy_t0 != 16 && copy_t0 != 32) copy_t0 = K1_COPY_T0;
     pref_box = num("ADELL_K1_PREF_BOX", 1024, K1_MAX_BOX_BYTES, -1);
-    tile_pref = num("ADELL_K1_TILE", 0, 7, -1);               // 0 = 16x16x32, 1 = 16x32x16, 2 = 8x16x32, 3 = 16x16x16, 4.. the small shapes only
+    tile_pref = num("ADELL_K1_TILE", 0, 8, -1);               // 0 = 16x16x32, 1 = 16x32x16, 2 = 8x16x32, 3 = 16x16x16, 4.. the small shapes only
     chunk = num("ADELL_K1_CHUNK", 1, 64, 4);
     tail = num("ADELL_K1_TAIL", 0, 64, 3);
     idle_stream = num("ADELL_K1_IDLE_STREAM", 0, K1_GROUPS - 1, -1);   // measurement aid: that stream of every CTA takes no tiles
@@ -1927,7 +1927,7 @@ int k1_encode_item(adell_item& it, EncodeTiledFn enc, int tile_pref) {
   // Shapes 4.. are small tiles for footprints that the regular ones cannot stage within the preferred box (strong
   // zooms: the workhorse's scale members draw factors around 2): ONE item with a ~100 KB box would leave the whole
   // launch with a single ring stage per stream (no load in flight while a tile is consumed).
-  static const int kShapes[8][3] = {{16, 16, 32}, {16, 32, 16}, {8, 16, 32}, {16, 16, 16}, {8, 16, 16}, {8, 8, 32}, {8, 8, 16}, {4, 8, 16}};
+  static const int kShapes[9][3] = {{16, 16, 32}, {16, 32, 16}, {8, 16, 32}, {16, 16, 16}, {8, 16, 16}, {8, 8, 32}, {8, 8, 16}, {4, 8, 16}, {4, 4, 16}};
   const int pref_bytes = k1_tuning().pref_box > 0 ? k1_tuning().pref_box : k1_pref_box_bytes();
   int box[3] = {0, 0, 0}, T[3] = {16, 16, 16};
   int64_t bytes = 0;
@@ -1937,7 +1937,7 @@ int k1_encode_item(adell_item& it, EncodeTiledFn enc, int tile_pref) {
   for (int pass = 0; pass < 3 && bytes == 0; ++pass) {
     const int limit = pass < 2 ? pref_bytes : K1_MAX_BOX_BYTES;
     int64_t best_cover = -1;
-    for (int s = (pass == 1 ? 4 : 0); s < (pass == 0 ? 4 : 8); ++s) {
+    for (int s = (pass == 1 ? 4 : 0); s < (pass == 0 ? 4 : 9); ++s) {
       if (tile_pref >= 0 && s != tile_pref) continue;
       if (kShapes[s][2] == 32 && it.out_shape[2] <= 16) continue;
       if (s == 1 && it.out_shape[1] <= 16) continue;
@@ -1951,6 +1951,7 @@ int k1_encode_item(adell_item& it, EncodeTiledFn enc, int tile_pref) {
         cover *= nt * kShapes[s][a];
       }
       cover += tiles * tile_cost;
+      if (pass == 2) cover = b;   // nothing fits the preferred box: the SMALLEST box (the launch keeps the most stages)
       if (best_cover >= 0 && cover >= best_cover) continue;
       best_cover = cover;
       bytes = b;

@@ -170,15 +170,30 @@ def execute(plan: BatchPlan, dsts: Sequence[torch.Tensor]) -> None:
     execute_ptrs(plan, dst_ptr, dst_stride)
 
 
+_scratch: dict = {}
+
+
+def _scratch_for(device: torch.device):
+    """Allocator of the scratch volumes of multi-pass plans: ONE buffer per (device, stream), grown geometrically and
+    reused by every later plan executed on that stream (launches of one stream are ordered, so the next plan's first
+    pass cannot overtake the previous plan's last one).  A fresh ``torch.empty`` per plan made the caching allocator
+    call cudaMalloc — a device-wide synchronisation — whenever a step closed more volumes than any step before it."""
+    def alloc(n: int) -> torch.Tensor:
+        key = (device, torch.cuda.current_stream(device).cuda_stream)
+        buf = _scratch.get(key)
+        if buf is None or buf.numel() < n:
+            buf = _scratch[key] = torch.empty(max(2 * n, 1 << 20), dtype=torch.float32, device=device)
+        return buf[:max(n, 1)]
+    return alloc
+
+
 def execute_ptrs(plan: BatchPlan, dst_ptr: np.ndarray, dst_stride: np.ndarray, keep=None) -> None:
     """Like :func:`execute` with raw destination pointers (``[n]`` uint64, ``[n,3]`` element strides)."""
     _require_cuda(plan.device)
     if keep:
         plan.keep.extend(keep)
     with torch.cuda.device(plan.device):
-        launches = plan.build_launches(
-            dst_ptr, dst_stride, lambda n: torch.empty(max(n, 1), dtype=torch.float32, device=plan.device)
-        )
+        launches = plan.build_launches(dst_ptr, dst_stride, _scratch_for(plan.device))
         for items in launches:
             buf, n, info = pack_launch(items)
             dev = _stage(buf, plan.device)

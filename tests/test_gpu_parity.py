@@ -512,7 +512,7 @@ def test_border_tiles_entirely_outside_on_a_reversed_axis(strict, seed):
 def test_strong_zooms_take_the_small_tile_shapes_and_match_the_oracle(shape, padding):
     """The workhorse's scale members draw factors around 2 (reference quirk) and fast mode
     multiplies them: footprints that the regular tile shapes cannot stage within the preferred box get the small
-    shapes (8x16x16 ... 4x8x16) instead of a ~100 KB box that would leave the launch with one ring stage per stream."""
+    shapes (8x16x16 ... 4x4x16) instead of a ~100 KB box that would leave the launch with one ring stage per stream."""
     import ctypes as C
 
     from adell_mri_b200 import _lib, engine
