@@ -8,6 +8,7 @@ block of the same JSON line carries, measured in the same run on the same device
   seg_all_affine  config B   with the affine forced to fire for every sample (worst case of K1)
   seg_norm        config B   from RAW int16 / uint8 cached volumes: adell_minmax -> scaler coefficients ->
                              {scale, offset} read from device memory by K1 (the "+norm" of the metric inside the step)
+  seg_crop        config B   with the label-guided crop sandwich, through the dictionary surface (device-side crop centres)
   ssl             config C   get_augmentations_ssl two-view chain (augmentations.py:391-516), 128x128x32, batch 64 / GPU
   ssl_fast        config C   the same in fast mode (consecutive resamples composed: documented deviation)
   cls             config D   percentile normalisation (K2/K3) + get_augmentations_class (augmentations.py:181-320):
@@ -247,6 +248,67 @@ class SegNorm(_SegBase):
         _equal(self.out["mask"][0, 0].cpu(), want["mask"][0], "seg_norm mask (nearest, uint8 source)")
         return {"checked": "sample 0 (min-max scaled int16 keys <= tol, uint8 mask bit-exact) vs oracle", "max_rel_err": worst,
                 "tol": TOL, "ok": True}
+
+
+class SegCrop(_SegBase):
+    name = "seg_crop"
+    desc = ("config B with the label-guided crop sandwich (get_augmentations_unet(random_crop_size=[128,128,24], n_crops=2): "
+            "RandCropByPosNegLabeld(1.1x) -> affine p=0.2 reflection -> 3 flips -> CenterSpatialCropd) through the DICTIONARY "
+            "surface: one pipeline call per sample, FgBgToIndicesd lists resident on the device, crop centres selected by "
+            "adell_posneg_starts, K1 reading the window starts from device memory, safe_collate_crops -> one launch")
+    rc, n_crops = [128, 128, 24], 2
+
+    def __init__(self, dev, rank, world, seed):
+        super().__init__(dev, rank, world, seed)
+        from adell_mri_b200 import collate, transform_factory as F, transforms as T
+
+        self._collate = collate
+        g = torch.Generator(device=dev).manual_seed(seed)
+        fgbg = T.FgBgToIndicesd("mask")
+        self.cache = []
+        for _ in range(self.cache_samples):
+            s = {k: torch.rand((1, *self.shape), device=dev, generator=g) for k in self.image_keys}
+            s["mask"] = (torch.rand((1, *self.shape), device=dev, generator=g) > 0.7).float()
+            self.cache.append(fgbg(s))   # cached stage: the index lists are made once per sample and stay on the device
+        keys = self.image_keys + ["mask"]
+        self.F, self.T = F, T
+        self.pipe = self._pipeline(seed)
+        self.vox_per_step = self.batch * self.n_crops * len(keys) * int(np.prod(self.rc))
+        self.bytes_per_voxel = 8.0
+
+    def _pipeline(self, seed):
+        keys = self.image_keys + ["mask"]
+        aug = self.F.get_augmentations_unet(["affine", "flip"], keys, self.image_keys, [], random_crop_size=self.rc, has_label=True,
+                                            n_crops=self.n_crops, flip_axis=[0, 1, 2])
+        tf = self.F.SegmentationTransforms(keys, self.image_keys, ["mask"], self.image_keys, [])
+        return self.T.Compose([aug, *tf.post_transforms()]).set_random_state(seed)
+
+    def step(self, i):
+        self.last = self._collate.safe_collate_crops([self.pipe(dict(s)) for s in self._batch(i)])
+
+    def parity(self):
+        """Same seed through the eager oracle pipeline (pipelines_ref.unet with the host-side centre selection of
+        monai_restated.pos_neg_crop_centers) on the first two samples."""
+        from oracle import pipelines_ref as P
+
+        n = 2
+        pipe = self._pipeline(self.seed + 3)
+        got = self._collate.safe_collate_crops([pipe(dict(s)) for s in self.cache[:n]])
+        torch.cuda.synchronize()
+        keys = self.image_keys + ["mask"]
+        # the reference seeds the OUTER Compose; its only Randomizable child is the augmentation Compose
+        ref = P.Chain([P.unet(["affine", "flip"], keys, self.image_keys, self.rc, True, self.n_crops, (0, 1, 2))]).seed(self.seed + 3)
+        worst = 0.0
+        for b, s in enumerate(self.cache[:n]):
+            d = {k: s[k].cpu() for k in keys}
+            d["mask_fg_indices"], d["mask_bg_indices"] = s["mask_fg_indices"].cpu().numpy(), s["mask_bg_indices"].cpu().numpy()
+            crops = ref(d)
+            for c, r in enumerate(crops):
+                img = torch.cat([r[k] for k in self.image_keys], 0)
+                worst = max(worst, _close(got["image"][b * self.n_crops + c].cpu(), img, f"seg_crop sample {b} crop {c} image"))
+                _equal(got["mask"][b * self.n_crops + c].cpu(), r["mask"], f"seg_crop sample {b} crop {c} mask")
+        return {"checked": f"{n} samples x {self.n_crops} crops, same seed, vs the eager oracle pipeline (pipelines_ref.unet, host-side "
+                           "centre selection): image keys <= tol, masks bit-exact", "max_rel_err": worst, "tol": TOL, "ok": True}
 
 
 # ----------------------------------------------------------------------------- config C
@@ -556,7 +618,7 @@ class LargeVolume(Workload):
         return res
 
 
-ALL = [AffineA, SegAllAffine, SegNorm, SSLTwoView, SSLTwoViewFast, ClsPercentile, LargeVolume]
+ALL = [AffineA, SegAllAffine, SegNorm, SegCrop, SSLTwoView, SSLTwoViewFast, ClsPercentile, LargeVolume]
 
 
 # ----------------------------------------------------------------------------- runner
