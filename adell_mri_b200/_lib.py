@@ -112,6 +112,48 @@ class Chain(C.Structure):
 CHAIN_AFFINE, CHAIN_STRICT = 0x01, 0x02
 
 
+class SeqOp(C.Structure):
+    """Mirror of ``adell_seq_op`` (one member of a volume's ordered op list)."""
+
+    _fields_ = [
+        ("A", C.c_float * 12),
+        ("scale", C.c_double),
+        ("offset", C.c_double),
+        ("philox_seed", C.c_uint64),
+        ("philox_offset", C.c_uint64),
+        ("philox_std", C.c_float),
+        ("kind", C.c_uint8),
+        ("interp", C.c_uint8),
+        ("padding", C.c_uint8),
+        ("reserved_", C.c_uint8),
+    ]
+
+
+SEQ_MAX_OPS = 4
+OP_NONE, OP_AFFINE, OP_INTENSITY, OP_PHILOX = 0, 1, 2, 3
+SEQ_FAST, SEQ_STRICT = 0x01, 0x02
+ERR_NO_SPACE = -8
+
+
+class Seq(C.Structure):
+    """Mirror of ``adell_seq`` (host-side sequence descriptor consumed by ``adell_seq_prepare_steps``)."""
+
+    _fields_ = [
+        ("src", C.c_void_p),
+        ("dst", C.c_void_p),
+        ("src_stride", C.c_int64 * 3),
+        ("dst_stride", C.c_int64 * 3),
+        ("src_shape", C.c_int32 * 3),
+        ("crop0_start", C.c_int32 * 3),
+        ("crop0_size", C.c_int32 * 3),
+        ("src_dtype", C.c_uint8),
+        ("n_ops", C.c_uint8),
+        ("flags", C.c_uint8),
+        ("reserved_", C.c_uint8),
+        ("ops", SeqOp * SEQ_MAX_OPS),
+    ]
+
+
 class PosNeg(C.Structure):
     """Mirror of ``adell_posneg``."""
 
@@ -125,6 +167,12 @@ class LaunchInfo(C.Structure):
     """Mirror of ``adell_launch_info``."""
 
     _fields_ = [("total_tiles", C.c_int64), ("smem_bytes", C.c_int32), ("n_staged", C.c_int32), ("first_copy_tile", C.c_int64)]
+
+
+class SeqLaunch(C.Structure):
+    """Mirror of ``adell_seq_launch``."""
+
+    _fields_ = [("item_off", C.c_int64), ("n_items", C.c_int32), ("step", C.c_int32), ("info", LaunchInfo)]
 
 
 class Vol(C.Structure):
@@ -149,6 +197,9 @@ _SIGNATURES = {
     "adell_chain_size": (C.c_int, []),
     "adell_chain_compose": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "adell_chain_prepare_steps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "adell_seq_size": (C.c_int, []),
+    "adell_seq_prepare_steps": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                          C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "adell_aug_gather_launches": (C.c_int, []),
     "adell_minmax": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     "adell_meanstd": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -175,7 +226,7 @@ _SIGNATURES = {
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 _lib = None
 
 
@@ -200,6 +251,8 @@ def load() -> C.CDLL:
         raise RuntimeError("adell_item layout mismatch between header and binding")
     if lib.adell_chain_size() != C.sizeof(Chain):
         raise RuntimeError("adell_chain layout mismatch between header and binding")
+    if lib.adell_seq_size() != C.sizeof(Seq):
+        raise RuntimeError("adell_seq layout mismatch between header and binding")
     _lib = lib
     return lib
 

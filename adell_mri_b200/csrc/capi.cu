@@ -15,6 +15,7 @@ extern "C" const char* adell_status_string(int status) {
     case ADELL_ERR_NO_DEVICE: return "no CUDA device (there is no CPU fallback)";
     case ADELL_ERR_NO_DRIVER: return "CUDA driver entry point unavailable";
     case ADELL_ERR_UNSUPPORTED: return "unsupported configuration";
+    case ADELL_ERR_NO_SPACE: return "caller-provided buffer too small";
     default: return "unknown status";
   }
 }

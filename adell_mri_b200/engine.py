@@ -322,3 +322,108 @@ def compose_chains_host(chains: np.ndarray, step_sizes, plan_only: bool = True):
                                                      offs.ctypes.data, tile_off.ctypes.data, infos_arr, int(plan_only)),
                "adell_chain_prepare_steps")
     return buf, offs, infos_arr
+
+
+# ----------------------------------------------------------------------------- multi-pass sequences (native)
+SEQ_DTYPE = np.dtype(_lib.Seq)
+SEQ_OP_DTYPE = np.dtype(_lib.SeqOp)
+
+
+class PreparedSeqSteps:
+    """Steps whose volumes need several K1 passes (``adell_seq``): composed, prepared and uploaded at once; ``run(k)``
+    enqueues the launches of step ``k`` in order (closed levels first, the final pass last)."""
+
+    def __init__(self, dev: torch.Tensor, launches, n_launches: int, n_steps: int, keep):
+        self.keep = [dev, launches] + list(keep or [])
+        self._lib = _lib.load()
+        self._device = dev.device
+        base = dev.data_ptr()
+        self._steps = [[] for _ in range(n_steps)]
+        for i in range(n_launches):
+            L = launches[i]
+            self._steps[L.step].append((base + L.item_off, base + L.item_off + L.n_items * ISZ, L.n_items, C.byref(L.info)))
+        self._per_launch = self._lib.adell_aug_gather_launches()
+        self._gather = self._lib.adell_aug_gather
+
+    def __len__(self):
+        return len(self._steps)
+
+    def launches(self, k: int) -> int:
+        return len(self._steps[k])
+
+    def run(self, k: int, stream: int | None = None) -> None:
+        global launch_count
+        if stream is None:
+            stream = torch.cuda.current_stream(self._device).cuda_stream
+        for a in self._steps[k]:
+            tok = timer.begin(self._device) if timer is not None else None
+            st = self._gather(a[0], a[1], a[2], a[3], C.c_void_p(stream))
+            if timer is not None:
+                timer.end(tok)
+            if st != 0:
+                _lib.check(st, "adell_aug_gather")
+            launch_count += self._per_launch
+
+
+def _seq_call(seqs: np.ndarray, sizes, scratch_ptr: int, scratch_elems: int, host_ptr: int, host_bytes: int, launches, mode: int):
+    n32 = np.asarray(sizes, np.int32)
+    nl, used, sused = C.c_int32(0), C.c_int64(0), C.c_int64(0)
+    st = _lib.load().adell_seq_prepare_steps(seqs.ctypes.data, len(sizes), n32.ctypes.data, scratch_ptr, scratch_elems, host_ptr,
+                                             host_bytes, launches, len(launches), C.byref(nl), C.byref(used), C.byref(sused), mode)
+    return st, nl.value, used.value, sused.value
+
+
+def _seq_bytes_bound(seqs: np.ndarray, sizes) -> int:
+    """Upper bound of the staging bytes: a volume's first op never closes a pass, every later one at most once."""
+    items = int(np.maximum(seqs["n_ops"].astype(np.int64), 1).sum())
+    return items * ISZ + sum((_lib.SEQ_MAX_OPS + 1) * (4 * (n + 5) + 128) for n in sizes)
+
+
+def prepare_seq_steps(seqs: np.ndarray, step_sizes, device: torch.device, keep=None) -> PreparedSeqSteps:
+    """Native route for multi-pass chains: ``seqs`` (``SEQ_DTYPE``, one per volume, the volumes of consecutive steps in
+    order) are composed pass by pass (BatchPlan's closing rules), every launch is prepared and written straight into a
+    pinned staging slot by ONE call of ``adell_seq_prepare_steps``, then uploaded with one copy.  Scratch volumes live in
+    the (device, stream) scratch buffer, reused by every step."""
+    _require_cuda(device)
+    if seqs.dtype != SEQ_DTYPE or not seqs.flags.c_contiguous:
+        raise ValueError("seqs must be a contiguous array of adell_seq")
+    sizes = tuple(int(x) for x in step_sizes)
+    if sum(sizes) != seqs.shape[0]:
+        raise ValueError("step_sizes must add up to the number of sequences")
+    max_l = len(sizes) * (2 * _lib.SEQ_MAX_OPS + 1)
+    launches = (_lib.SeqLaunch * max_l)()
+    with torch.cuda.device(device):
+        alloc = _scratch_for(device)
+        scratch = alloc(1)
+        ring = _ring(device)
+        need = _seq_bytes_bound(seqs, sizes)
+        for _ in range(3):
+            k, host = ring.acquire(need)
+            st, nl, used, sused = _seq_call(seqs, sizes, scratch.data_ptr(), scratch.numel(), host.ctypes.data, need, launches, 0)
+            if st == _lib.ERR_NO_SPACE and sused > scratch.numel():
+                scratch = alloc(int(sused))   # grows the (device, stream) buffer
+                continue
+            _lib.check(st, "adell_seq_prepare_steps")
+            break
+        else:
+            raise RuntimeError("adell_seq_prepare_steps: scratch / staging space could not be provided")
+        dev = ring.upload(k, used, device)
+    return PreparedSeqSteps(dev, launches, nl, len(sizes), [scratch] + list(keep or []))
+
+
+def compose_seqs_host(seqs: np.ndarray, step_sizes, mode: int = 2, scratch_ptr: int = 0, scratch_elems: int = 1 << 60):
+    """Host-only twin of :func:`prepare_seq_steps` (no device): returns ``[(step, items_array), ...]`` in execution
+    order.  ``mode`` 2: the composed items as they are (what ``BatchPlan.build_launches`` returns), 1: after
+    ``adell_aug_plan``."""
+    sizes = tuple(int(x) for x in step_sizes)
+    max_l = len(sizes) * (2 * _lib.SEQ_MAX_OPS + 1)
+    launches = (_lib.SeqLaunch * max_l)()
+    need = _seq_bytes_bound(seqs, sizes)
+    buf = np.zeros(max(need, 1), np.uint8)
+    st, nl, used, sused = _seq_call(seqs, sizes, scratch_ptr, scratch_elems, buf.ctypes.data, need, launches, mode)
+    _lib.check(st, "adell_seq_prepare_steps")
+    out = []
+    for i in range(nl):
+        L = launches[i]
+        out.append((L.step, buf[L.item_off: L.item_off + L.n_items * ISZ].view(ITEM_DTYPE).copy()))
+    return out, sused

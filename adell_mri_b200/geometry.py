@@ -103,8 +103,16 @@ def compose_affine(rotate=None, shear=None, translate=None, scale=None, batch: i
     if r is not None:
         if r.shape[1] > 3:
             r = np.ascontiguousarray(r[:, :3])
-        tr = torch.from_numpy(r)
-        sin_r, cos_r = torch.sin(tr).numpy(), torch.cos(tr).numpy()   # fp32, evaluated by torch exactly as MONAI's create_rotate does
+        # fp32, evaluated by torch exactly as MONAI's create_rotate does.  In slices of <= 1024 elements: above a few
+        # thousand elements torch hands the call to a threaded vector-math region, whose worker threads cost milliseconds
+        # to wake when the host's cores are shared (8 ranks per box; 20-50 ms per call measured in a CPU-limited
+        # container) — per element the result is the same.
+        tr = torch.from_numpy(np.ascontiguousarray(r)).reshape(-1)
+        sin_t, cos_t = torch.empty_like(tr), torch.empty_like(tr)
+        for o in range(0, tr.numel(), 1024):
+            torch.sin(tr[o:o + 1024], out=sin_t[o:o + 1024])
+            torch.cos(tr[o:o + 1024], out=cos_t[o:o + 1024])
+        sin_r, cos_r = sin_t.numpy().reshape(r.shape), cos_t.numpy().reshape(r.shape)
     p = lambda a: None if a is None else a.ctypes.data
     k = lambda a: 0 if a is None else a.shape[1]
     _lib.check(_lib.load().adell_affine_compose(p(sin_r), p(cos_r), k(r), p(sh), k(sh), p(t), k(t), p(sc), k(sc), batch, out.ctypes.data),

@@ -615,13 +615,18 @@ class _WorkhorseDraws:
                     spatial.append((m, use, p))
             elif m == "gaussian_noise":
                 self.R_outer[m].random_sample(use.size)
-                vals = []
-                for _ in range(use.size):   # the noise volume itself is drawn per use (host float64 normal)
-                    self.R_inner[m].random_sample()
-                    std = self.R_inner[m].uniform(0, self.noise_std)
-                    if philox:
-                        vals.append((np.float32(std), int(self.R_inner[m].randint(2 ** 32, dtype="uint32"))))
-                    else:
+                if philox:
+                    # per use: gate random_sample(), uniform(0, noise_std), randint(2**32) = 2 + 2 + 1 words of the
+                    # Mersenne twister, drawn raw in one call and assembled the way numpy does (53-bit doubles)
+                    w = self.R_inner[m].randint(0, 2 ** 32, size=5 * use.size, dtype=np.uint32).reshape(-1, 5).astype(np.uint64)
+                    u = ((w[:, 2] >> np.uint64(5)).astype(np.float64) * 67108864.0 + (w[:, 3] >> np.uint64(6)).astype(np.float64)) / 9007199254740992.0
+                    std = (0.0 + (self.noise_std - 0.0) * u).astype(np.float32)
+                    vals = list(zip(std, (int(x) for x in w[:, 4])))
+                else:
+                    vals = []
+                    for _ in range(use.size):   # the noise volume itself is drawn per use (host float64 normal)
+                        self.R_inner[m].random_sample()
+                        std = self.R_inner[m].uniform(0, self.noise_std)
                         vals.append(self.R_inner[m].normal(0.0, std, size=shape).astype(np.float32))
                 out[m] = (use, vals)
             else:
@@ -703,10 +708,15 @@ class SSLBatchAugmenter(_BatchBase):
         self._ensure_views(n_keys)
         nm = len(self.members)
         starts = np.zeros((2, batch, 3), np.int64)
-        for b in range(batch):   # RandSpatialCropd(random_size=False): a randint per axis that can move
-            starts[0, b] = [int(self.crop_R[0].randint(low=0, high=d - r + 1)) if d > r else 0 for d, r in zip(shape, self.roi)]
+        # RandSpatialCropd(random_size=False): a randint per axis that can move, sample by sample — drawn for the whole
+        # batch by ONE call with an array of upper bounds (the legacy generator fills it element by element with the same
+        # masked rejection as scalar calls: identical values, identical stream position; tests/test_host_logic.py)
+        mov = [a for a, (d, r) in enumerate(zip(shape, self.roi)) if d > r]
+        if mov and batch:
+            high = np.tile(np.array([shape[a] - self.roi[a] + 1 for a in mov], np.int64), (batch, 1))
+            starts[0][:, mov] = self.crop_R[0].randint(0, high)
             if self.different_crop:
-                starts[1, b] = [int(self.crop_R[1].randint(low=0, high=d - r + 1)) if d > r else 0 for d, r in zip(shape, self.roi)]
+                starts[1][:, mov] = self.crop_R[1].randint(0, high)
         if not self.different_crop:
             starts[1] = starts[0]
         choice = np.zeros((2, batch, self.N), np.int64)
@@ -721,20 +731,14 @@ class SSLBatchAugmenter(_BatchBase):
         draws = [self.views[v].draw_members(choice[v], (n_keys, *roi_shape), self.noise == "philox") for v in range(2)]
         return dict(starts=starts, choice=choice, draws=draws)
 
-    def plan(self, samples: Sequence[dict], params=None):
-        B = len(samples)
-        nc = self._n_channels(samples[0])
-        plan, metas = self._base_plan(samples, self.keys, repeat=2)      # volume order: [b, view, channel]
-        shape = tuple(int(x) for x in metas[0][4][0])
-        if params is None:
-            params = self.draw(B, shape, nc)
-        n = plan.n
-        vol_b = np.repeat(np.arange(B), 2 * nc)
-        vol_v = np.tile(np.repeat(np.arange(2), nc), B)
-        plan.crop(params["starts"][vol_v, vol_b], self.roi)
-        dev = plan.device
+    def _slots(self, params, B: int, nc: int, vox: int, dev=None):
+        """Slot ``s`` of every (sample, view) of a drawn batch, as batch-wide records: each volume applies exactly ONE
+        member per slot, so the members of a slot touch disjoint volumes and collapse into at most one affine / one
+        intensity / one noise record for the whole batch (the reference runs them one transform call per sample; the
+        order between different volumes is immaterial).  Yields ``dict(A, has_aff, sc, of, has_int, std, seed, off_p,
+        has_phx, noise)`` over the ``n = B * 2 * nc`` volumes (order ``[b, view, channel]``)."""
+        n = B * 2 * nc
         ch = np.arange(nc)[None, :]
-        vox = int(np.prod(plan.shape[0]))
         eye = np.eye(4, dtype=np.float32)
         # Per view: where every member's per-use values live, so that a slot of the whole batch is gathered with a few
         # fancy-index operations instead of a Python loop over the members.
@@ -762,13 +766,11 @@ class SSLBatchAugmenter(_BatchBase):
             scv = np.concatenate(cat[1]) if cat[1] else np.zeros(0)
             shv = np.concatenate(cat[2]) if cat[2] else np.zeros(0)
             noise_vals = [x for lst in cat[3] for x in lst]          # philox: (std, seed) pairs; injected: arrays
+            if self.noise == "philox" and noise_vals:
+                noise_vals = (np.array([q[0] for q in noise_vals], np.float32), np.array([q[1] for q in noise_vals], np.uint64))
             tables.append((pos, off, mats, scv, shv, noise_vals))
         barange = np.arange(B)
         for s in range(self.N):
-            # Slot s of every (sample, view): each volume applies exactly ONE member here, so the members of a slot
-            # touch disjoint volumes and collapse into at most one affine / one intensity / one noise record for the
-            # whole batch (the reference runs them one transform call per sample; the order between different
-            # volumes is immaterial).
             A = np.empty((n, 4, 4), np.float32)
             A[:] = eye
             has_aff = np.zeros(n, bool)
@@ -797,8 +799,8 @@ class SSLBatchAugmenter(_BatchBase):
                 sel = np.nonzero(k == 3)[0]
                 if sel.size:
                     if self.noise == "philox":
-                        std[vol[sel]] = np.array([noise_vals[q][0] for q in where[sel]], np.float32)[:, None]
-                        seed[vol[sel]] = np.array([noise_vals[q][1] for q in where[sel]], np.uint64)[:, None]
+                        std[vol[sel]] = noise_vals[0][where[sel]][:, None]
+                        seed[vol[sel]] = noise_vals[1][where[sel]][:, None]
                         off_p[vol[sel]] = (np.arange(nc, dtype=np.uint64) * np.uint64(vox))[None, :]
                         has_phx[vol[sel]] = True
                     else:
@@ -806,18 +808,101 @@ class SSLBatchAugmenter(_BatchBase):
                             noise = [None] * n
                         for b, q in zip(sel, where[sel]):
                             t = torch.from_numpy(noise_vals[q])
-                            t = t.pin_memory().to(dev, non_blocking=True) if dev.type == "cuda" else t
+                            t = t.pin_memory().to(dev, non_blocking=True) if dev is not None and dev.type == "cuda" else t
                             for c in range(nc):
                                 noise[int(vol[b, c])] = t[c]
-            if has_aff.any():
-                plan.affine(A, "bilinear", "zeros", where=has_aff)
-            if has_int.any():
-                plan.intensity(scale=sc, offset=of, where=has_int)
-            if has_phx.any():
-                plan.add_philox_noise(std, seed, off_p, where=has_phx)
-            if noise is not None:
-                plan.add_noise(noise)
+            yield dict(A=A, has_aff=has_aff, sc=sc, of=of, has_int=has_int, std=std, seed=seed, off_p=off_p, has_phx=has_phx, noise=noise)
+
+    def plan(self, samples: Sequence[dict], params=None):
+        B = len(samples)
+        nc = self._n_channels(samples[0])
+        plan, metas = self._base_plan(samples, self.keys, repeat=2)      # volume order: [b, view, channel]
+        shape = tuple(int(x) for x in metas[0][4][0])
+        if params is None:
+            params = self.draw(B, shape, nc)
+        vol_b = np.repeat(np.arange(B), 2 * nc)
+        vol_v = np.tile(np.repeat(np.arange(2), nc), B)
+        plan.crop(params["starts"][vol_v, vol_b], self.roi)
+        vox = int(np.prod(plan.shape[0]))
+        for r in self._slots(params, B, nc, vox, plan.device):
+            if r["has_aff"].any():
+                plan.affine(r["A"], "bilinear", "zeros", where=r["has_aff"])
+            if r["has_int"].any():
+                plan.intensity(scale=r["sc"], offset=r["of"], where=r["has_int"])
+            if r["has_phx"].any():
+                plan.add_philox_noise(r["std"], r["seed"], r["off_p"], where=r["has_phx"])
+            if r["noise"] is not None:
+                plan.add_noise(r["noise"])
         return plan, params
+
+    # ------------------------------------------------------------------ native route (adell_seq)
+    def native_ok(self) -> bool:
+        """The native sequence composer covers every member except host-drawn (injected) noise volumes."""
+        return (self.noise == "philox" or "gaussian_noise" not in self.members) and self.N <= _lib.SEQ_MAX_OPS
+
+    def seqs(self, batches: Sequence[Sequence[dict]], outs: Sequence[dict], params=None) -> np.ndarray:
+        """``adell_seq`` descriptors of several consecutive steps (``batches[k]`` written to ``outs[k]``): ONE draw over
+        all their samples (the streams are consumed in sample order, so this equals step-by-step draws) and a handful
+        of numpy assignments per slot; composition itself happens in ``adell_seq_prepare_steps``."""
+        samples = [s for b in batches for s in b]
+        Bt = len(samples)
+        nc = self._n_channels(samples[0])
+        metas = [self._sample_meta(s, self.keys) for s in samples]
+        shape = tuple(int(x) for x in metas[0][4][0])
+        if params is None:
+            params = self.draw(Bt, shape, nc)
+        key = ("seq", id(samples[0]), id(samples[-1]), Bt, tuple(id(o["augmented_image_1"]) for o in outs))
+        hit = self._tmpl_cache.get(key)
+        if hit is not None and any(a is not b for a, b in zip(hit[1], samples)):
+            hit = None
+        if hit is None:
+            n = Bt * 2 * nc
+            sq = np.zeros(n, engine.SEQ_DTYPE)
+            rep = lambda i: np.concatenate([np.tile(m[i], (2,) + (1,) * (m[i].ndim - 1)) for m in metas])
+            sq["src"], sq["src_stride"], sq["src_dtype"], sq["src_shape"] = rep(1), rep(2), rep(3), rep(4)
+            ptrs, strides = [], []
+            for o in outs:
+                p1, s1 = self._dst_of(o["augmented_image_1"])
+                p2, s2 = self._dst_of(o["augmented_image_2"])
+                ptrs.append(np.stack([p1, p2], axis=1).reshape(-1))          # [b, view, channel]
+                strides.append(np.stack([s1, s2], axis=1).reshape(-1, 3))
+            sq["dst"], sq["dst_stride"] = np.concatenate(ptrs), np.concatenate(strides)
+            sq["crop0_size"] = self.roi
+            sq["n_ops"] = self.N
+            sq["flags"] = (_lib.SEQ_FAST if self.fast else 0) | (_lib.SEQ_STRICT if self.strict else 0)
+            if len(self._tmpl_cache) > 256:
+                self._tmpl_cache.clear()
+            hit = self._tmpl_cache[key] = (sq, list(samples))
+        sq = hit[0].copy()
+        vol_b = np.repeat(np.arange(Bt), 2 * nc)
+        vol_v = np.tile(np.repeat(np.arange(2), nc), Bt)
+        sq["crop0_start"] = params["starts"][vol_v, vol_b]
+        vox = int(np.prod([min(r, d) for r, d in zip(self.roi, shape)]))
+        ops = sq["ops"]
+        zeros_pad, bilinear = _lib.PADDING_MODES["zeros"], _lib.INTERP_MODES["bilinear"]
+        for s, r in enumerate(self._slots(params, Bt, nc, vox)):
+            o = ops[:, s]
+            o["kind"] = np.where(r["has_aff"], _lib.OP_AFFINE, np.where(r["has_int"], _lib.OP_INTENSITY,
+                                                                         np.where(r["has_phx"], _lib.OP_PHILOX, _lib.OP_NONE)))
+            o["A"] = r["A"][:, :3].reshape(-1, 12)
+            o["interp"], o["padding"] = bilinear, zeros_pad
+            o["scale"], o["offset"] = r["sc"], r["of"]
+            o["philox_std"], o["philox_seed"], o["philox_offset"] = r["std"], r["seed"], r["off_p"]
+            ops[:, s] = o
+        return sq, params
+
+    def prepare_steps(self, batches: Sequence[Sequence[dict]], outs: Sequence[dict], params=None) -> "engine.PreparedSeqSteps":
+        """Draw, compose and upload several consecutive steps at once (like a prefetching loader working ahead);
+        ``run(k)`` then only enqueues step ``k``'s launches."""
+        if not self.native_ok():
+            raise NotImplementedError("injected (host-drawn) noise volumes are composed by BatchPlan: use __call__")
+        self._ensure_views(self._n_channels(batches[0][0]))
+        sq, _ = self.seqs(batches, outs, params)
+        nc = self._n_channels(batches[0][0])
+        dev = batches[0][0][self.keys[0]].device
+        keep = [o[k] for o in outs for k in ("augmented_image_1", "augmented_image_2")] + [m[5] for b in batches for m in
+                                                                                             (self._sample_meta(s, self.keys) for s in b)]
+        return engine.prepare_seq_steps(sq, [len(b) * 2 * nc for b in batches], dev, keep=keep)
 
     def boxes(self, params, shape):
         """``box_1`` / ``box_2`` of the VICRegL variant: ``flatten_box(extra_info.cropped)``
@@ -830,18 +915,31 @@ class SSLBatchAugmenter(_BatchBase):
             out.append(np.concatenate([st, np.asarray(self.roi)[None, :] - end_gap], axis=1).astype(np.float32))
         return out
 
-    def __call__(self, samples: Sequence[dict], params=None, out: dict | None = None) -> dict:
-        plan, params = self.plan(samples, params)
+    def __call__(self, samples: Sequence[dict], params=None, out: dict | None = None, native: bool | None = None) -> dict:
         B, nc = len(samples), self._n_channels(samples[0])
-        oshape = tuple(int(x) for x in plan.shape[0])
-        if out is None:
-            out = {k: torch.empty((B, nc, *oshape), dtype=torch.float32, device=plan.device)
-                   for k in ("augmented_image_1", "augmented_image_2")}
-        p1, s1 = self._dst_of(out["augmented_image_1"])
-        p2, s2 = self._dst_of(out["augmented_image_2"])
-        ptr = np.stack([p1, p2], axis=1).reshape(-1)          # [b, view, channel]
-        stride = np.stack([s1, s2], axis=1).reshape(-1, 3)
-        engine.execute_ptrs(plan, ptr, stride, keep=[out["augmented_image_1"], out["augmented_image_2"]])
+        if native is None:
+            native = self.native_ok()
+        if native:
+            shape = tuple(int(x) for x in self._sample_meta(samples[0], self.keys)[4][0])
+            oshape = tuple(min(r, d) for r, d in zip(self.roi, shape))
+            dev = samples[0][self.keys[0]].device
+            if out is None:
+                out = {k: torch.empty((B, nc, *oshape), dtype=torch.float32, device=dev)
+                       for k in ("augmented_image_1", "augmented_image_2")}
+            if params is None:
+                params = self.draw(B, shape, nc)
+            self.prepare_steps([samples], [out], params).run(0)
+        else:
+            plan, params = self.plan(samples, params)
+            oshape = tuple(int(x) for x in plan.shape[0])
+            if out is None:
+                out = {k: torch.empty((B, nc, *oshape), dtype=torch.float32, device=plan.device)
+                       for k in ("augmented_image_1", "augmented_image_2")}
+            p1, s1 = self._dst_of(out["augmented_image_1"])
+            p2, s2 = self._dst_of(out["augmented_image_2"])
+            ptr = np.stack([p1, p2], axis=1).reshape(-1)          # [b, view, channel]
+            stride = np.stack([s1, s2], axis=1).reshape(-1, 3)
+            engine.execute_ptrs(plan, ptr, stride, keep=[out["augmented_image_1"], out["augmented_image_2"]])
         if self.vicregl:
             shape = tuple(int(x) for x in self._meta[id(samples[0])][4][0])
             b1, b2 = self.boxes(params, shape)

@@ -317,7 +317,7 @@ class SSLTwoView(Workload):
     desc = ("config C: get_augmentations_ssl two views (shared RandSpatialCropd 128x128x32 out of 160x160x40, then per view "
             "3 of the 15 fused workhorse members in drawn order, one K1 pass per spatial member like the reference's "
             "sequential resamples), batch 64 per GPU; noise sigma drawn on the host, noise values from the device Philox "
-            "generator; member subsets drawn vectorised")
+            "generator; member subsets drawn vectorised; 16 steps drawn + composed by the native sequence composer per host call")
     batch, src, roi, cache_samples = 64, (160, 160, 40), (128, 128, 32), 128
 
     def __init__(self, dev, rank, world, seed):
@@ -327,11 +327,18 @@ class SSLTwoView(Workload):
         self.aug = SSLBatchAugmenter(["image"], self.roi, n_transforms=3, choice="vectorised", noise="philox").set_random_state(seed)
         self.out = {k: torch.empty((self.batch, 1, *self.roi), device=dev) for k in ("augmented_image_1", "augmented_image_2")}
         self.vox_per_step = self.batch * 2 * int(np.prod(self.roi))
+        self._prep = None
+
+    chunk = 16   # steps drawn, composed (adell_seq_prepare_steps) and uploaded per host call, like a loader working ahead
+    default_steps = 32
 
     def step(self, i):
-        nb = self.cache_samples // self.batch
-        b0 = (i % nb) * self.batch
-        self.aug(self.cache[b0:b0 + self.batch], out=self.out)
+        j = i % self.chunk
+        if j == 0 or self._prep is None:
+            nb = self.cache_samples // self.batch
+            batches = [self.cache[((i - j + t) % nb) * self.batch:((i - j + t) % nb + 1) * self.batch] for t in range(self.chunk)]
+            self._prep = self.aug.prepare_steps(batches, [self.out] * self.chunk)
+        self._prep.run(j)
 
     def parity(self):
         """Stream level: 3 samples through a second augmenter (host-drawn noise injected, member subsets from the
@@ -353,7 +360,15 @@ class SSLTwoView(Workload):
             r = ref({"image": x, "image_copy": x.clone()})
             for key, rk in (("augmented_image_1", "image"), ("augmented_image_2", "image_copy")):
                 worst = max(worst, _close(got[key][b].cpu(), r[rk], f"ssl sample {b} {key}"))
-        return {"checked": f"{n} samples x 2 views, same seeds, vs the eager oracle pipeline (pipelines_ref.ssl)",
+        # the timed route (native sequence composer, device Philox noise) against the numpy BatchPlan route on one draw
+        params = self.aug.draw(8, self.src, 1)
+        a = self.aug(self.cache[:8], params=params, native=False)
+        b = self.aug(self.cache[:8], params=params, native=True)
+        torch.cuda.synchronize()
+        for key in ("augmented_image_1", "augmented_image_2"):
+            _equal(b[key], a[key], f"ssl native route vs BatchPlan route {key}")
+        return {"checked": f"{n} samples x 2 views, same seeds, vs the eager oracle pipeline (pipelines_ref.ssl); the timed native "
+                           "route == the BatchPlan route bit for bit on 8 samples (same draws, device Philox noise)",
                 "max_rel_err": worst, "tol": TOL, "ok": True}
 
 
@@ -366,6 +381,7 @@ class SSLTwoViewFast(SSLTwoView):
     def __init__(self, dev, rank, world, seed):
         super().__init__(dev, rank, world, seed)
         self.aug = SSLBatchAugmenter(["image"], self.roi, n_transforms=3, choice="vectorised", noise="philox", fast=True).set_random_state(seed)
+        self._prep = None
 
     def parity(self):
         return {"ok": None, "checked": "not applicable: fast mode composes consecutive resamples (documented deviation); the "

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define ADELL_ABI_VERSION 6
+#define ADELL_ABI_VERSION 7
 
 /* status codes */
 #define ADELL_OK 0
@@ -49,6 +49,7 @@ extern "C" {
 #define ADELL_ERR_NO_DEVICE (-5)
 #define ADELL_ERR_NO_DRIVER (-6)
 #define ADELL_ERR_UNSUPPORTED (-7)
+#define ADELL_ERR_NO_SPACE (-8) /* a caller-provided buffer is too small (the needed size is reported) */
 
 /* source element types */
 #define ADELL_F32 0
@@ -246,6 +247,60 @@ int adell_chain_compose(const adell_chain* chains, int n, adell_item* items_host
 int adell_chain_prepare_steps(const adell_chain* chains, void* buf_host, int n_steps, const int32_t* n_items,
                               const int64_t* item_off, const int64_t* tile_off, adell_launch_info* infos,
                               int plan_only);
+/* Host-only SEQUENCE composer: volumes whose chain is an ordered list of up to ADELL_SEQ_MAX_OPS members after one
+ * crop — the two-view stream of get_augmentations_ssl, where every sample applies its own drawn ORDER of the fused
+ * AugmentationWorkhorsed members (adell_mri/transform_factory/augmentations.py:391-516,
+ * adell_mri/modules/augmentations.py:165-256).  A second resample, or anything after a noise member, closes the
+ * volume's pass: it is materialised into a scratch fp32 volume by an earlier launch (the reference's sequential
+ * resamples).  Closed passes are grouped by LEVEL (a volume's k-th closed pass goes into launch k), the final launch
+ * holds every volume.  Semantics — pass closing, pre / post folding of the intensity maps, scratch layout, item order —
+ * are those of adell_mri_b200/plan.py (BatchPlan.crop / affine / intensity / add_philox_noise + build_launches) applied
+ * slot by slot (slot s = the s-th op of every volume; within a slot: the affines, then the intensity maps, then the
+ * noise members), which the tests compare byte for byte.  ADELL_SEQ_FAST composes consecutive affines into one matrix
+ * instead of closing (documented deviation of fast mode). */
+#define ADELL_OP_NONE 0
+#define ADELL_OP_AFFINE 1    /* A (rows 0..2 of the fp32 MONAI matrix), interp, padding; output grid = current size */
+#define ADELL_OP_INTENSITY 2 /* v * scale + offset                                                                 */
+#define ADELL_OP_PHILOX 3    /* + philox_std * N(0,1) from the device generator (seed, offset)                      */
+#define ADELL_SEQ_MAX_OPS 4
+#define ADELL_SEQ_FAST 0x01
+#define ADELL_SEQ_STRICT 0x02
+typedef struct adell_seq_op {
+  float A[12];
+  double scale, offset;
+  uint64_t philox_seed, philox_offset;
+  float philox_std;
+  uint8_t kind, interp, padding, reserved_;
+} adell_seq_op;
+typedef struct adell_seq {
+  const void* src;        /* parent volume, element (0,0,0)                              */
+  float* dst;             /* fp32 destination of the LAST pass                           */
+  int64_t src_stride[3];  /* parent strides in elements                                  */
+  int64_t dst_stride[3];
+  int32_t src_shape[3];
+  int32_t crop0_start[3]; /* SpatialCrop before the members; crop0_size all <= 0: none   */
+  int32_t crop0_size[3];
+  uint8_t src_dtype, n_ops, flags, reserved_;
+  adell_seq_op ops[ADELL_SEQ_MAX_OPS];
+} adell_seq;
+/* One launch of a composed step: its items start at buf_host + item_off (n_items x 768 B, followed by the int32 tile
+ * prefix of n_items + 5 words); launches of one step are listed in execution order. */
+typedef struct adell_seq_launch {
+  int64_t item_off;
+  int32_t n_items;
+  int32_t step;
+  adell_launch_info info;
+} adell_seq_launch;
+int adell_seq_size(void);
+/* Composes n_steps consecutive steps (step k = the next n_vols[k] sequences) into buf_host (buf_bytes available;
+ * typically pinned) and prepares every launch (adell_aug_prepare; prepare_mode 1: adell_aug_plan, 2: composed items
+ * only — tests).  Scratch volumes are placed in [scratch_dev, scratch_dev + 4 * scratch_elems) — every step starts
+ * again at scratch_dev: launches of one stream are ordered.  *n_launches, *bytes_used and *scratch_used are always
+ * reported; ADELL_ERR_NO_SPACE when buf_bytes, max_launches or scratch_elems is too small (nothing launchable then). */
+int adell_seq_prepare_steps(const adell_seq* seqs, int n_steps, const int32_t* n_vols, uint64_t scratch_dev,
+                            int64_t scratch_elems, void* buf_host, int64_t buf_bytes, adell_seq_launch* launches,
+                            int max_launches, int32_t* n_launches, int64_t* bytes_used, int64_t* scratch_used,
+                            int prepare_mode);
 /* Enqueue the fused gather over all items: ONE kernel launch per call. */
 int adell_aug_gather(const adell_item* items_dev, const int32_t* tile_start_dev, int n_items,
                      const adell_launch_info* info, void* stream);

@@ -76,6 +76,36 @@ def cref_prepare_chain_steps(chains, step_sizes, device, keep=None):
     return _CrefSteps(steps)
 
 
+class _CrefSeqSteps:
+    def __init__(self, steps, keep):
+        self.steps, self.keep = steps, keep
+
+    def __len__(self):
+        return len(self.steps)
+
+    def launches(self, k):
+        return len(self.steps[k])
+
+    def run(self, k):
+        for items in self.steps[k]:
+            cref.gather(items)
+
+
+def cref_prepare_seq_steps(seqs, step_sizes, device, keep=None):
+    """Stand-in for ``engine.prepare_seq_steps`` on CPU-resident sequences: the NATIVE sequence composer builds every
+    launch (scratch volumes in a host buffer), each then runs through the C restatement."""
+    from adell_mri_b200 import engine
+
+    sizes = [int(x) for x in step_sizes]
+    _, need = engine.compose_seqs_host(seqs, sizes, mode=2, scratch_ptr=4096)
+    scratch = torch.empty(max(int(need), 1), dtype=torch.float32)
+    launches, _ = engine.compose_seqs_host(seqs, sizes, mode=1, scratch_ptr=scratch.data_ptr(), scratch_elems=scratch.numel())
+    steps = [[] for _ in sizes]
+    for k, items in launches:
+        steps[k].append(items)
+    return _CrefSeqSteps(steps, [scratch, keep])
+
+
 def cref_execute_ptrs(plan: BatchPlan, dst_ptr, dst_stride, keep=None) -> None:
     """Stand-in for ``engine.execute_ptrs`` on CPU-resident plans (see :func:`cref_execute`)."""
     launches = plan.build_launches(dst_ptr, dst_stride, lambda n: torch.empty(max(n, 1), dtype=torch.float32))
@@ -90,3 +120,4 @@ def patch_engine_for_cpu(monkeypatch) -> None:
     monkeypatch.setattr(engine, "execute", cref_execute)
     monkeypatch.setattr(engine, "execute_ptrs", cref_execute_ptrs)
     monkeypatch.setattr(engine, "prepare_chain_steps", cref_prepare_chain_steps)
+    monkeypatch.setattr(engine, "prepare_seq_steps", cref_prepare_seq_steps)

@@ -28,7 +28,7 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 def test_item_layout_and_status_strings():
     lib = _lib.load()
-    assert lib.adell_abi_version() == _lib.ABI_VERSION == 6
+    assert lib.adell_abi_version() == _lib.ABI_VERSION == 7
     assert lib.adell_item_size() == C.sizeof(_lib.Item) == 768
     assert b"no CUDA device" in lib.adell_status_string(-5)
     assert lib.adell_status_string(0) == b"ok"

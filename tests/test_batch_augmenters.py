@@ -22,7 +22,8 @@ def _cref_execute_ptrs(plan, dst_ptr, dst_stride, keep=None):
 @pytest.fixture(params=["cpu", pytest.param("cuda:0", marks=pytest.mark.gpu)])
 def dev(request, monkeypatch):
     if request.param == "cpu":
-        from tests.helpers import cref_execute, cref_prepare_chain_steps
+        from tests.helpers import cref_execute, cref_prepare_chain_steps, cref_prepare_seq_steps
+        monkeypatch.setattr(engine, "prepare_seq_steps", cref_prepare_seq_steps)
         monkeypatch.setattr(engine, "execute", cref_execute)
         monkeypatch.setattr(engine, "execute_ptrs", _cref_execute_ptrs)
         monkeypatch.setattr(engine, "prepare_chain_steps", cref_prepare_chain_steps)
@@ -84,3 +85,30 @@ def test_ssl_batch_equals_dictionary_surface(dev, different_crop, vicregl):
     if vicregl:
         for k in ("box_1", "box_2"):
             assert np.array_equal(np.asarray(got[k]), np.asarray(want[k]))
+
+
+@pytest.mark.parametrize("fast,vicregl", [(False, False), (True, False), (False, True)])
+def test_ssl_native_sequences_equal_batchplan_route(dev, fast, vicregl):
+    """The native sequence route (adell_seq: several steps composed by one call) writes the very voxels of the numpy
+    BatchPlan route on the same draws — device Philox noise included."""
+    R = np.random.RandomState(8)
+    shape, roi = (36, 32, 16), [24, 24, 12]
+    samples = _samples(R, 8, ["image"], shape, dev, mask=False)
+    # (the C restatement of the CPU leg has no Philox generator: the noise member is exercised on the GPU leg)
+    members = None if dev != "cpu" else [m for m in SSL_FUSED_MEMBERS if m != "gaussian_noise"]
+    aug = SSLBatchAugmenter(["image"], roi, n_transforms=(2 if vicregl and dev == "cpu" else 3), vicregl=vicregl, choice="vectorised",
+                            noise="philox", fast=fast, members=members).set_random_state(4)
+    assert aug.native_ok()
+    params = aug.draw(8, shape, 1)
+    want = aug(samples, params=params, native=False)
+    got = aug(samples, params=params, native=True)
+    for k in ("augmented_image_1", "augmented_image_2"):
+        assert torch.equal(got[k].cpu(), want[k].cpu()), k
+    # two steps prepared at once == the same samples as one batch
+    outs = [{k: torch.empty(4, 1, *roi, device=dev) for k in ("augmented_image_1", "augmented_image_2")} for _ in range(2)]
+    steps = aug.prepare_steps([samples[:4], samples[4:]], outs, params)
+    assert len(steps) == 2
+    for k in range(2):
+        steps.run(k)
+    for k in ("augmented_image_1", "augmented_image_2"):
+        assert torch.equal(torch.cat([outs[0][k], outs[1][k]]).cpu(), want[k].cpu()), k

@@ -117,3 +117,104 @@ def test_classification_chains_equal_batchplan_items(augment):
         plan = aug.plan(samples, params)
         ptr, stride = aug._dst_of(out["image"])
         _same(_native_items(ch, [18]), _plan_items(plan, ptr.reshape(-1), stride.reshape(-1, 3), [18]))
+
+
+# ----------------------------------------------------------------------------- multi-pass sequences (adell_seq)
+def _ssl_setup(seed, B, fast=False, strict=False, members=None, nk=1, shape=(40, 36, 20), roi=(32, 32, 16), choice="vectorised"):
+    from adell_mri_b200.pipelines import SSLBatchAugmenter
+
+    R = np.random.RandomState(seed)
+    keys = ["image"] if nk == 1 else ["image", "aux"]
+    samples = [{k: torch.from_numpy(R.rand(1, *shape).astype(np.float32)) for k in keys} for _ in range(B)]
+    aug = SSLBatchAugmenter(keys, roi, n_transforms=3, choice=choice, noise="philox", fast=fast, strict=strict,
+                            members=members).set_random_state(seed + 1)
+    return aug, samples, shape, roi
+
+
+@pytest.mark.parametrize("fast,strict,nk", [(False, False, 1), (False, True, 1), (True, False, 1), (False, False, 2)])
+def test_ssl_sequences_equal_batchplan_launches(fast, strict, nk):
+    """adell_seq_prepare_steps == BatchPlan.build_launches for the two-view SSL stream: the same launches in the same
+    order, every item byte for byte (scratch addresses included), over several drawn batches."""
+    B = 10
+    aug, samples, shape, roi = _ssl_setup(11, B, fast, strict, nk=nk)
+    out = {k: torch.empty(B, nk, *roi) for k in ("augmented_image_1", "augmented_image_2")}
+    depth = set()
+    for trial in range(5):
+        params = aug.draw(B, shape, nk)
+        plan, _ = aug.plan(samples, params)
+        holder = {}
+
+        def alloc(n):
+            holder["buf"] = torch.empty(max(n, 1))
+            return holder["buf"]
+
+        p1, s1 = aug._dst_of(out["augmented_image_1"])
+        p2, s2 = aug._dst_of(out["augmented_image_2"])
+        ptr = np.stack([p1, p2], axis=1).reshape(-1)
+        stride = np.stack([s1, s2], axis=1).reshape(-1, 3)
+        want = plan.build_launches(ptr, stride, alloc)
+        sq, _ = aug.seqs([samples], [out], params)
+        got, scratch_used = engine.compose_seqs_host(sq, [len(sq)], mode=2,
+                                                     scratch_ptr=holder["buf"].data_ptr() if "buf" in holder else 0)
+        assert len(got) == len(want)
+        depth.add(len(want))
+        if "buf" in holder:
+            assert scratch_used <= holder["buf"].numel()
+        for (step, it), w in zip(got, want):
+            assert step == 0 and it.shape == w.shape
+            if fast:   # the composed matrices come from a float64 product: numpy's BLAS may sum in another order
+                assert np.allclose(it["A"], w["A"], rtol=0, atol=1e-6)
+                it = it.copy(); it["A"] = w["A"]
+            assert it.tobytes() == w.tobytes()
+    assert max(depth) >= 2   # the draws did exercise closed passes
+
+
+def test_ssl_sequences_several_steps_equal_step_by_step():
+    """One native call over three steps == three single-step calls, with every step's scratch volumes starting at the
+    scratch base again; and with the reference's member choice (global numpy stream, sample by sample) one draw over the
+    samples of three steps equals three consecutive draws (every stream is consumed in sample order)."""
+    B = 6
+    aug, samples, shape, roi = _ssl_setup(21, 3 * B, choice="global")
+    np.random.seed(77)
+    outs = [{k: torch.empty(B, 1, *roi) for k in ("augmented_image_1", "augmented_image_2")} for _ in range(3)]
+    batches = [samples[0:B], samples[B:2 * B], samples[2 * B:]]
+    sq, params = aug.seqs(batches, outs)
+    n = 2 * B
+    got, _ = engine.compose_seqs_host(sq, [n] * 3, mode=1, scratch_ptr=4096)
+    for k in range(3):
+        one, _ = engine.compose_seqs_host(np.ascontiguousarray(sq[k * n:(k + 1) * n]), [n], mode=1, scratch_ptr=4096)
+        mine = [it for step, it in got if step == k]
+        assert len(mine) == len(one)
+        for a, (_, b) in zip(mine, one):
+            assert a.tobytes() == b.tobytes()
+    # and the draws of the big batch are those of three consecutive small ones
+    aug2, _, _, _ = _ssl_setup(21, 3 * B, choice="global")
+    np.random.seed(77)
+    for k in range(3):
+        p = aug2.draw(B, shape, 1)
+        assert np.array_equal(p["starts"], params["starts"][:, k * B:(k + 1) * B])
+        assert np.array_equal(p["choice"], params["choice"][:, k * B:(k + 1) * B])
+        for v in range(2):
+            for m, (use, vals) in p["draws"][v].items():
+                big_use, big_vals = params["draws"][v][m]
+                sel = (big_use >= k * B) & (big_use < (k + 1) * B)
+                assert np.array_equal(big_use[sel] - k * B, use)
+                if isinstance(vals, np.ndarray):
+                    assert np.array_equal(np.asarray(big_vals)[sel], vals)
+                else:
+                    assert [big_vals[i] for i in np.nonzero(sel)[0]] == list(vals)
+
+
+def test_seq_prepare_reports_missing_space():
+    aug, samples, shape, roi = _ssl_setup(31, 8)
+    out = {k: torch.empty(8, 1, *roi) for k in ("augmented_image_1", "augmented_image_2")}
+    sq, _ = aug.seqs([samples], [out])
+    launches = (_lib.SeqLaunch * 16)()
+    buf = np.zeros(1 << 20, np.uint8)
+    st, nl, used, sused = engine._seq_call(sq, (len(sq),), 4096, 0, buf.ctypes.data, buf.size, launches, 2)
+    if sused > 0:
+        assert st == _lib.ERR_NO_SPACE
+    st, nl, used, sused2 = engine._seq_call(sq, (len(sq),), 4096, sused, buf.ctypes.data, 256, launches, 2)
+    assert st == _lib.ERR_NO_SPACE and sused2 == sused and used > 256
+    st, nl, used, _ = engine._seq_call(sq, (len(sq),), 4096, sused, buf.ctypes.data, buf.size, launches, 2)
+    assert st == 0 and nl >= 1
