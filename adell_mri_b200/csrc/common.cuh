@@ -44,8 +44,10 @@ __device__ __forceinline__ float adell_unkey_f32(uint32_t k) {
   uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
   return __uint_as_float(u);
 }
+#define ADELL_KEY32 3   /* internal: the elements ARE order-preserving keys (candidate lists of adell_quantile_keys) */
 __device__ __forceinline__ uint32_t adell_key(const void* __restrict__ base, int64_t idx, int dtype) {
   if (dtype == ADELL_F32) return adell_key_f32(__ldg(reinterpret_cast<const float*>(base) + idx));
+  if (dtype == ADELL_KEY32) return __ldg(reinterpret_cast<const uint32_t*>(base) + idx);
   if (dtype == ADELL_I16)
     return (static_cast<uint32_t>(static_cast<int>(__ldg(reinterpret_cast<const short*>(base) + idx)) + 32768)) << 16;
   return static_cast<uint32_t>(__ldg(reinterpret_cast<const unsigned char*>(base) + idx)) << 24;

@@ -380,8 +380,10 @@ __global__ void st_coefs_to_affine(const float* __restrict__ coefs, int n_vols, 
 // instead of 32-way.  Later passes: only elements whose high bits match a selection's prefix
 // count; matching lanes are warp-aggregated with __match_any_sync before the atomic.
 __global__ void __launch_bounds__(ST_THREADS)
-st_hist_first(const adell_vol* __restrict__ vols, int shared_bins, int bits, unsigned long long* __restrict__ bins) {
+st_hist_first(const adell_vol* __restrict__ vols, int shared_bins, int bits, unsigned long long* __restrict__ bins,
+              const int* __restrict__ gate = nullptr) {
   extern __shared__ uint32_t sh[];  // [nb][HIST_REPL]
+  if (gate != nullptr && *gate == 0) return;   // fallback of adell_quantile_keys: runs only when a bracket failed
   const int nb = 1 << bits;
   for (int i = threadIdx.x; i < nb * HIST_REPL; i += blockDim.x) sh[i] = 0u;
   __syncthreads();
@@ -430,8 +432,9 @@ constexpr int NEXT_REPL = 2;  // shared-memory copies of the later passes' histo
 
 __global__ void __launch_bounds__(ST_THREADS)
 st_hist_next(const adell_vol* __restrict__ vols, int n_sel, int shared_bins, const uint32_t* __restrict__ prefix,
-             int shift, int bits, unsigned long long* __restrict__ bins) {
+             int shift, int bits, unsigned long long* __restrict__ bins, const int* __restrict__ gate = nullptr) {
   extern __shared__ uint32_t sh[];  // [n_uniq][nb]: one histogram per DISTINCT selected prefix
+  if (gate != nullptr && *gate == 0) return;
   __shared__ uint32_t spre[8];      // distinct prefixes (high bits)
   __shared__ int s_uniq[8];         // selection -> index of its prefix in spre
   __shared__ int s_nu;
@@ -525,7 +528,8 @@ st_hist_next(const adell_vol* __restrict__ vols, int n_sel, int shared_bins, con
 // One block per (histogram, selection): find the bin that holds the requested rank.
 __global__ void __launch_bounds__(ST_THREADS)
 st_hist_select(const unsigned long long* __restrict__ bins, int n_sel, int first_pass, int shift, int bits,
-               uint32_t* __restrict__ prefix, unsigned long long* __restrict__ rank) {
+               uint32_t* __restrict__ prefix, unsigned long long* __restrict__ rank, const int* __restrict__ gate = nullptr) {
+  if (gate != nullptr && *gate == 0) return;
   const int h = blockIdx.x / n_sel, s = blockIdx.x % n_sel;
   const int nb = 1 << bits;
   const unsigned long long* hb = bins + ((first_pass ? static_cast<size_t>(h) : static_cast<size_t>(h) * n_sel + s) << bits);
@@ -573,6 +577,424 @@ __global__ void st_percentile_finalize(const uint32_t* __restrict__ keys, const 
   double r = __dadd_rn(static_cast<double>(a), __dmul_rn(static_cast<double>(diff), t));
   if (t >= 0.5) r = __dsub_rn(static_cast<double>(b), __dmul_rn(static_cast<double>(diff), __dsub_rn(1.0, t)));
   out[i] = static_cast<float>(r);
+}
+
+// ---------------------------------------------------------------- one-read order statistics -------
+// adell_quantile_keys: the radix passes above read every volume three times (fp32).  Here a strided SAMPLE of the
+// volume (<= 32 Ki keys, ~3 % of its sectors) brackets each requested order statistic between two sample order
+// statistics 6 sigma apart; ONE full read then counts the keys outside the bracket, the keys equal to its two ends
+// (so that the heavy ties of a background level never have to be stored) and appends the few keys strictly inside
+// (~0.5 % of the volume at the 0.5th / 99.5th percentile) to a candidate list; the order statistic is selected
+// exactly among those.  A bracket that missed (or overflowed its list) raises a flag that un-gates the three
+// radix passes: the result is exact either way.
+constexpr int QS_THREADS = 1024;
+constexpr int QS_SAMPLE = 32768;   // sample keys per volume (128 KiB of shared memory)
+constexpr int QMAX = 4;            // quantiles per call
+constexpr int QS_POOL = 64;        // volumes a pooled (dataset-wide) call may hold
+
+struct QBracket {
+  uint32_t lo, hi;                    // sample order statistics bracketing the (lo, hi) ranks of one quantile
+  uint32_t n_cand, pad_;              // keys strictly inside (may exceed the list's capacity: overflow)
+  unsigned long long out, ne_lo, ne_hi;   // keys beyond the bracket on the counted side, keys equal to its ends
+};
+
+__device__ __forceinline__ uint32_t st_key_at(const adell_vol& v, int64_t i) { return adell_key(v.data, i, v.dtype); }
+
+// Exact radix selection of n_sel ranks among `m` keys that all lie in [klo, khi], by one block.  Only the bits below
+// the common prefix of klo and khi vary: digits of 8 bits are taken from there downwards, so the keys spread over the
+// 256 bins of every pass (selecting on fixed byte positions sent every key of a narrow bracket to ONE bin for the first
+// passes: its shared-memory atomics serialised).  hist: [n_sel][256] shared words; on return sel_key[s] holds the key
+// of rank sel_rank[s] (ranks are consumed).
+__device__ void st_block_select(const uint32_t* __restrict__ keys, int m, int n_sel, uint32_t klo, uint32_t khi,
+                                unsigned long long* sel_rank, uint32_t* sel_key, uint32_t* hist) {
+  const int vary = 32 - __clz(static_cast<int>(klo ^ khi));   // number of low bits that differ inside the bracket (0..32)
+  const uint32_t common = vary >= 32 ? 0u : (klo >> vary) << vary;
+  for (int s = threadIdx.x; s < n_sel; s += blockDim.x) sel_key[s] = common;
+  __syncthreads();
+  for (int top = vary; top > 0; top -= 8) {
+    const int shift = top > 8 ? top - 8 : 0, bits = top - shift;
+    const uint32_t mask = (1u << bits) - 1u;
+    const bool first = top == vary;   // every key shares the bits above `vary`: one histogram serves all selections
+    for (int i = threadIdx.x; i < (first ? 1 : n_sel) * 256; i += blockDim.x) hist[i] = 0u;
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+      const uint32_t k = keys[i];
+      if (first) { atomicAdd(&hist[(k >> shift) & mask], 1u); continue; }
+      for (int s = 0; s < n_sel; ++s)
+        if ((k >> top) == (sel_key[s] >> top)) atomicAdd(&hist[s * 256 + ((k >> shift) & mask)], 1u);
+    }
+    __syncthreads();
+    if ((threadIdx.x >> 5) < n_sel) {   // warp s places selection s: 8 bins per lane, warp scan, then the lane's own bins
+      const int s = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      const uint32_t* hs = hist + (first ? 0 : s * 256);
+      uint32_t part = 0;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) part += hs[8 * lane + b];   // (bins beyond the digit's width are zero)
+      uint32_t incl = part;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+      const unsigned long long r = sel_rank[s];
+      const unsigned hit = __ballot_sync(0xffffffffu, r < incl);   // lanes whose inclusive count exceeds the rank
+      const int owner = hit ? __ffs(hit) - 1 : 31;
+      if (lane == owner) {
+        unsigned long long cum = incl - part;
+        uint32_t b = 8 * lane;
+        const uint32_t last = min(8u * lane + 7u, mask);
+        for (; b < last; ++b) {
+          const unsigned long long c = hs[b];
+          if (r < cum + c) break;
+          cum += c;
+        }
+        sel_key[s] |= b << shift;
+        sel_rank[s] = r - cum;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(QS_THREADS)
+st_quantile_sample(const adell_vol* __restrict__ vols, int n_vols, int shared, long long total_n, int n_q,
+                   const unsigned long long* __restrict__ rank, QBracket* __restrict__ br, int* __restrict__ any_fail) {
+  extern __shared__ uint32_t qsm[];           // [QS_SAMPLE] keys, then [8][256] histogram words
+  __shared__ unsigned long long s_rank[8];
+  __shared__ uint32_t s_key[8], s_mn[32], s_mx[32];
+  __shared__ int s_open[8];
+  __shared__ int s_first[QS_POOL + 1];        // pooled mode: first sample group of every volume
+  uint32_t* hist = qsm + QS_SAMPLE;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *any_fail = 0;
+  int m;
+  long long n_all;
+  auto load_groups = [&](const adell_vol& v, int g0, int ng) {
+    // ng groups of four consecutive elements (one 16-byte load of fp32), evenly strided over the volume
+    const int64_t groups = v.n >> 2, sg = groups / ng;
+    const bool vec = v.dtype == ADELL_F32 && (reinterpret_cast<uintptr_t>(v.data) & 15u) == 0;
+    for (int g = threadIdx.x; g < ng; g += blockDim.x) {
+      const int64_t e = static_cast<int64_t>(g) * sg;
+      if (vec) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(v.data) + e);
+        qsm[4 * (g0 + g)] = adell_key_f32(q.x); qsm[4 * (g0 + g) + 1] = adell_key_f32(q.y);
+        qsm[4 * (g0 + g) + 2] = adell_key_f32(q.z); qsm[4 * (g0 + g) + 3] = adell_key_f32(q.w);
+      } else {
+        for (int c = 0; c < 4; ++c) qsm[4 * (g0 + g) + c] = st_key_at(v, 4 * e + c);
+      }
+    }
+  };
+  if (!shared) {
+    const adell_vol v = vols[blockIdx.x];
+    n_all = v.n;
+    if (v.n <= QS_SAMPLE) {
+      m = static_cast<int>(v.n);
+      for (int i = threadIdx.x; i < m; i += blockDim.x) qsm[i] = st_key_at(v, i);
+    } else {
+      m = QS_SAMPLE;
+      load_groups(v, 0, QS_SAMPLE / 4);
+    }
+  } else {
+    // one sample of the POOLED data: every volume contributes groups in proportion to its size (the host sends only
+    // pools of at most QS_POOL volumes, each of at least 4 * QS_SAMPLE elements, this way)
+    n_all = total_n;
+    if (threadIdx.x == 0) {
+      long long acc = 0;
+      int g = 0;
+      for (int v = 0; v < n_vols; ++v) {
+        s_first[v] = g;
+        acc += vols[v].n;
+        g = static_cast<int>((static_cast<long long>(QS_SAMPLE / 4) * acc) / total_n);
+      }
+      s_first[n_vols] = QS_SAMPLE / 4;
+    }
+    __syncthreads();
+    m = QS_SAMPLE;
+    for (int v = 0; v < n_vols; ++v) {
+      const int ng = s_first[v + 1] - s_first[v];
+      if (ng > 0) load_groups(vols[v], s_first[v], ng);
+    }
+  }
+  __syncthreads();
+  // range of the sample (the digits of the selection are taken below the common prefix of its extremes)
+  uint32_t mn = 0xffffffffu, mx = 0u;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) { const uint32_t k = qsm[i]; mn = min(mn, k); mx = max(mx, k); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+  if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = mn; s_mx[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    mn = s_mn[threadIdx.x]; mx = s_mx[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+    if (threadIdx.x == 0) { s_mn[0] = mn; s_mx[0] = mx; }
+  }
+  if (threadIdx.x < n_q) {
+    // bracket of quantile j in sample ranks: position of its lo rank, 6 standard deviations of the binomial either way
+    const int j = threadIdx.x;
+    const double R = static_cast<double>(rank[(static_cast<size_t>(blockIdx.x) * n_q + j) * 2]);
+    const double p = n_all > 0 ? R * m / static_cast<double>(n_all) : 0.0;
+    const double var = p * (1.0 - p / static_cast<double>(m > 0 ? m : 1));
+    const double sd = var > 0.0 ? sqrt(var) : 0.0;
+    const double d = 6.0 * sd + 8.0;
+    const double lo = floor(p - d), hi = ceil(p + d) + 1.0;
+    s_open[2 * j] = lo < 0.0; s_open[2 * j + 1] = hi >= m;
+    s_rank[2 * j] = lo < 0.0 ? 0ull : static_cast<unsigned long long>(lo);
+    s_rank[2 * j + 1] = hi >= m ? static_cast<unsigned long long>(m > 0 ? m - 1 : 0) : static_cast<unsigned long long>(hi);
+  }
+  __syncthreads();
+  if (m > 0) st_block_select(qsm, m, 2 * n_q, s_mn[0], s_mx[0], s_rank, s_key, hist);
+  __syncthreads();
+  if (threadIdx.x < n_q) {
+    const int j = threadIdx.x;
+    QBracket b;
+    b.lo = (s_open[2 * j] || m == 0) ? 0u : s_key[2 * j];
+    b.hi = (s_open[2 * j + 1] || m == 0) ? 0xffffffffu : s_key[2 * j + 1];
+    b.n_cand = 0u; b.pad_ = 0u; b.out = 0ull; b.ne_lo = 0ull; b.ne_hi = 0ull;
+    br[static_cast<size_t>(blockIdx.x) * n_q + j] = b;
+  }
+}
+
+// A caller that keeps its workspace may reuse the brackets of an earlier call on the same volumes (a device-resident
+// cache hands the same volumes back every epoch, and a bracket is only a hint: one that misses un-gates the fallback):
+// this replaces the sample kernel by clearing the counters.
+__global__ void st_quantile_reset(QBracket* __restrict__ br, int n, int* __restrict__ any_fail) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *any_fail = 0;
+  if (i < n) { br[i].n_cand = 0u; br[i].out = 0ull; br[i].ne_lo = 0ull; br[i].ne_hi = 0ull; }
+}
+
+// the counted side of a bracket: keys BELOW it for quantiles in the lower half, keys ABOVE it otherwise (the common
+// element, far from every bracket, then touches no counter at all)
+__device__ __forceinline__ bool st_low_side(unsigned long long rank_lo, int64_t n) { return 2ull * rank_lo < static_cast<unsigned long long>(n); }
+
+constexpr int QSTAGE = 128;   // candidate keys a WARP stages per quantile before one global append
+constexpr int QQUEUE = 512;   // keys of one iteration (16 per lane) a warp can defer to its slow loop
+
+template <int NQ>
+__global__ void __launch_bounds__(ST_THREADS)
+st_quantile_main(const adell_vol* __restrict__ vols, int shared, long long total_n, const unsigned long long* __restrict__ rank,
+                 QBracket* __restrict__ br_all, uint32_t* __restrict__ cand_all, int64_t cap) {
+  // The streaming loop is bound by instruction issue, not by HBM (ncu: 28 thread instructions per element and 21 of
+  // 32 lanes active when every key was classified where it was loaded).  So the loop only TESTS each key (two
+  // instructions for the order-preserving key, one unsigned range test per quantile, one warp vote) and defers the
+  // ~1.5 % that concern a bracket to a per-warp queue in shared memory, written without divergence (ballot +
+  // prefix popcount); the queue is drained once per iteration with all lanes busy.  Candidates are staged per warp
+  // and appended to the volume's list with ONE global atomic per flush (an atomic per candidate serialises on the
+  // list's counter: 2 ms per call for a 512x512x128 volume).
+  __shared__ uint32_t s_buf[ST_THREADS / 32][NQ][QSTAGE];
+  __shared__ uint32_t s_queue[ST_THREADS / 32][QQUEUE];
+  __shared__ uint32_t s_cnt[ST_THREADS / 32][NQ], s_qn[ST_THREADS / 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const adell_vol v = vols[blockIdx.y];
+  const size_t h = shared ? 0 : blockIdx.y;            // pooled statistics: every volume counts into bracket set 0
+  QBracket* __restrict__ br = br_all + h * NQ;
+  uint32_t* __restrict__ cand = cand_all + h * NQ * cap;
+  rank += h * NQ * 2;
+  uint32_t lo[NQ], hi[NQ], c_out[NQ], c_lo[NQ], c_hi[NQ], ia[NQ], iw[NQ];
+  bool low[NQ];
+#pragma unroll
+  for (int j = 0; j < NQ; ++j) {
+    const QBracket& b = br[j];
+    lo[j] = b.lo; hi[j] = b.hi;
+    low[j] = st_low_side(rank[j * 2], shared ? total_n : v.n);
+    c_out[j] = c_lo[j] = c_hi[j] = 0u;
+    // the keys that concern bracket j: its counted side up to the far end of the bracket
+    ia[j] = low[j] ? 0u : lo[j]; iw[j] = low[j] ? hi[j] : 0xffffffffu - lo[j];
+  }
+#pragma unroll
+  for (int j = 0; j < NQ; ++j) {   // keep the two test constants in registers (the compiler otherwise re-derives them
+    asm volatile("" : "+r"(ia[j]), "+r"(iw[j]));   // from the 64-bit rank / size comparison at every use)
+  }
+  if (lane < NQ) s_cnt[warp][lane] = 0u;
+  if (lane == 0) s_qn[warp] = 0u;
+  __syncwarp();
+  uint32_t* queue = s_queue[warp];
+  auto visit = [&](uint32_t k) {
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) any |= (k - ia[j]) <= iw[j];
+    if (any) queue[atomicAdd(&s_qn[warp], 1u)] = k;   // rare (~1.5 % of the keys)
+  };
+  auto classify = [&](uint32_t k) {
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) {
+      if (low[j] ? (k > hi[j]) : (k < lo[j])) continue;      // the uncounted side: nothing to do
+      if (k < lo[j] || k > hi[j]) { ++c_out[j]; continue; }   // beyond the bracket on the counted side
+      if (k == lo[j]) { ++c_lo[j]; continue; }                // (lo == hi: every tie is counted here)
+      if (k == hi[j]) { ++c_hi[j]; continue; }
+      const uint32_t pos = atomicAdd(&s_cnt[warp][j], 1u);
+      if (pos < QSTAGE) {
+        s_buf[warp][j][pos] = k;
+      } else {   // staging area full before the next flush point (a wide bracket): straight to the list
+        const uint32_t g = atomicAdd(&br[j].n_cand, 1u);
+        if (g < cap) cand[j * cap + g] = k;
+      }
+    }
+  };
+  // called by every lane of the warp, once per iteration: drain the queue, then append full staging areas
+  auto drain = [&](bool force) {
+    __syncwarp();
+    const uint32_t qn = s_qn[warp];
+    for (uint32_t i = lane; i < qn; i += 32) classify(queue[i]);
+    __syncwarp();
+    if (lane == 0) s_qn[warp] = 0u;
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) {
+      const uint32_t c = min(s_cnt[warp][j], static_cast<uint32_t>(QSTAGE));
+      if (!(force ? c > 0u : c > QSTAGE / 2)) continue;      // warp-uniform
+      uint32_t base = 0u;
+      if (lane == 0) base = atomicAdd(&br[j].n_cand, c);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      for (uint32_t i = lane; i < c; i += 32)
+        if (base + i < cap) cand[j * cap + base + i] = s_buf[warp][j][i];
+      __syncwarp();
+      if (lane == 0) s_cnt[warp][j] = 0u;
+    }
+    __syncwarp();
+  };
+  // order-preserving key of raw fp32 bits in two instructions: u ^ (sign ? 0xffffffff : 0x80000000)
+  auto fkey = [](float f) { const uint32_t u = __float_as_uint(f); return u ^ (static_cast<uint32_t>(static_cast<int32_t>(u) >> 31) | 0x80000000u); };
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nthr = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  // every lane of a warp runs the same number of iterations and votes in each visit (lanes past the end vote "no")
+  if (v.dtype == ADELL_F32 && (reinterpret_cast<uintptr_t>(v.data) & 15u) == 0) {
+    const float4* p4 = reinterpret_cast<const float4*>(v.data);
+    const int64_t n4 = v.n >> 2;
+    const int64_t full = n4 / (4 * nthr);   // iterations in which every thread of the grid has four loads
+    for (int64_t it = 0; it < full; ++it) {
+      const float4* p = p4 + tid + it * 4 * nthr;
+      const float4 q0 = __ldcs(p), q1 = __ldcs(p + nthr), q2 = __ldcs(p + 2 * nthr), q3 = __ldcs(p + 3 * nthr);   // four independent 128-bit loads in flight
+      visit(fkey(q0.x)); visit(fkey(q0.y)); visit(fkey(q0.z)); visit(fkey(q0.w));
+      visit(fkey(q1.x)); visit(fkey(q1.y)); visit(fkey(q1.z)); visit(fkey(q1.w));
+      visit(fkey(q2.x)); visit(fkey(q2.y)); visit(fkey(q2.z)); visit(fkey(q2.w));
+      visit(fkey(q3.x)); visit(fkey(q3.y)); visit(fkey(q3.z)); visit(fkey(q3.w));
+      drain(false);
+    }
+    for (int64_t i = full * 4 * nthr + tid; i < n4; i += nthr) {   // the ragged rest (< 4 loads per thread): classified directly
+      const float4 q = __ldcs(p4 + i);
+      classify(fkey(q.x)); classify(fkey(q.y)); classify(fkey(q.z)); classify(fkey(q.w));
+    }
+    for (int64_t j0 = (n4 << 2); j0 < v.n; j0 += nthr) {   // (at most three elements of the whole volume)
+      const int64_t j = j0 + tid;
+      if (j < v.n) classify(st_key_at(v, j));
+    }
+  } else {
+    const int64_t full = v.n / (8 * nthr);
+    for (int64_t it = 0; it < full; ++it) {
+      const int64_t i0 = tid + it * 8 * nthr;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) visit(st_key_at(v, i0 + u * nthr));
+      drain(false);
+    }
+    for (int64_t i = full * 8 * nthr + tid; i < v.n; i += nthr) classify(st_key_at(v, i));
+  }
+  drain(true);
+  // block totals: warp shuffles, then one atomic per counter per warp that saw anything
+#pragma unroll
+  for (int j = 0; j < NQ; ++j) {
+    uint32_t a = c_out[j], b = c_lo[j], c = c_hi[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_down_sync(0xffffffffu, a, o); b += __shfl_down_sync(0xffffffffu, b, o); c += __shfl_down_sync(0xffffffffu, c, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      QBracket& q = br[j];
+      if (a) atomicAdd(&q.out, static_cast<unsigned long long>(a));
+      if (b) atomicAdd(&q.ne_lo, static_cast<unsigned long long>(b));
+      if (c) atomicAdd(&q.ne_hi, static_cast<unsigned long long>(c));
+    }
+  }
+}
+
+// One block per (volume, quantile): place the lo / hi ranks among {below, == lo, candidates, == hi} and select.
+__global__ void __launch_bounds__(QS_THREADS)
+st_quantile_finish(const adell_vol* __restrict__ vols, int shared, long long total_n, int n_q, const unsigned long long* __restrict__ rank,
+                   const QBracket* __restrict__ br, const uint32_t* __restrict__ cand, int64_t cap,
+                   uint32_t* __restrict__ keys_out, int* __restrict__ any_fail) {
+  __shared__ uint32_t hist[2 * 256];
+  __shared__ unsigned long long s_rank[2];
+  __shared__ uint32_t s_key[2];
+  __shared__ int s_kind[2];   // 0 = lo key, 1 = candidate, 2 = hi key, 3 = failed
+  const int v = blockIdx.x / n_q;
+  const int64_t n = shared ? total_n : vols[v].n;
+  const QBracket b = br[blockIdx.x];
+  if (threadIdx.x < 2) {
+    const unsigned long long r0 = rank[static_cast<size_t>(blockIdx.x) * 2 + threadIdx.x];
+    const bool low = st_low_side(rank[static_cast<size_t>(blockIdx.x) * 2], n);
+    const unsigned long long nc = b.n_cand;
+    const unsigned long long below = low ? b.out : static_cast<unsigned long long>(n) - b.out - b.ne_hi - nc - b.ne_lo;
+    int kind = 3;
+    unsigned long long r = r0;
+    if (n > 0 && nc <= static_cast<unsigned long long>(cap) && r >= below) {
+      r -= below;
+      if (r < b.ne_lo) kind = 0;
+      else {
+        r -= b.ne_lo;
+        if (r < nc) kind = 1;
+        else { r -= nc; if (r < b.ne_hi) kind = 2; }
+      }
+    }
+    s_kind[threadIdx.x] = kind;
+    s_rank[threadIdx.x] = kind == 1 ? r : 0ull;
+  }
+  __syncthreads();
+  const int m = static_cast<int>(b.n_cand < static_cast<unsigned long long>(cap) ? b.n_cand : cap);
+  if (s_kind[0] == 1 || s_kind[1] == 1) st_block_select(cand + static_cast<size_t>(blockIdx.x) * cap, m, 2, b.lo, b.hi, s_rank, s_key, hist);
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    const int kind = s_kind[threadIdx.x];
+    uint32_t k = 0u;
+    if (kind == 0) k = b.lo;
+    else if (kind == 1) k = s_key[threadIdx.x];
+    else if (kind == 2) k = b.hi;
+    else if (n > 0) atomicExch(any_fail, 1);
+    keys_out[static_cast<size_t>(blockIdx.x) * 2 + threadIdx.x] = k;
+  }
+}
+
+// Long candidate lists (volumes of tens of millions of elements list hundreds of thousands of keys per bracket) are
+// not selected by ONE block: st_quantile_place turns every list into a "volume" of raw keys and the two residual
+// ranks, the radix kernels above select among them with the whole grid, st_quantile_merge assembles the keys.
+__global__ void st_quantile_place(const adell_vol* __restrict__ vols, int shared, long long total_n, int n_q, int n_sets,
+                                  const unsigned long long* __restrict__ rank, const QBracket* __restrict__ br,
+                                  uint32_t* __restrict__ cand, int64_t cap, adell_vol* __restrict__ cvol,
+                                  unsigned long long* __restrict__ crank, int* __restrict__ kinds, int* __restrict__ any_fail) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (set, lo / hi rank)
+  if (i >= n_sets * 2) return;
+  const int set = i >> 1, v = set / n_q;
+  const int64_t n = shared ? total_n : vols[v].n;
+  const QBracket b = br[set];
+  const unsigned long long r0 = rank[i];
+  const bool low = st_low_side(rank[static_cast<size_t>(set) * 2], n);
+  const unsigned long long nc = b.n_cand;
+  const unsigned long long below = low ? b.out : static_cast<unsigned long long>(n) - b.out - b.ne_hi - nc - b.ne_lo;
+  int kind = 3;
+  unsigned long long r = r0;
+  if (n > 0 && nc <= static_cast<unsigned long long>(cap) && r >= below) {
+    r -= below;
+    if (r < b.ne_lo) kind = 0;
+    else {
+      r -= b.ne_lo;
+      if (r < nc) kind = 1;
+      else { r -= nc; if (r < b.ne_hi) kind = 2; }
+    }
+  }
+  kinds[i] = kind;
+  crank[i] = kind == 1 ? r : 0ull;
+  if (kind == 3 && n > 0) atomicExch(any_fail, 1);
+  if ((i & 1) == 0) {
+    adell_vol c;
+    c.data = cand + static_cast<size_t>(set) * cap;
+    c.n = static_cast<int64_t>(nc < static_cast<unsigned long long>(cap) ? nc : static_cast<unsigned long long>(cap));
+    c.dtype = ADELL_KEY32; c._pad = 0;
+    cvol[set] = c;
+  }
+}
+
+__global__ void st_quantile_merge(const QBracket* __restrict__ br, const int* __restrict__ kinds, const uint32_t* __restrict__ ckeys,
+                                  int n, uint32_t* __restrict__ keys_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int kind = kinds[i];
+  const QBracket b = br[i >> 1];
+  keys_out[i] = kind == 0 ? b.lo : (kind == 1 ? ckeys[i] : (kind == 2 ? b.hi : 0u));
 }
 
 // One thread per crop: centre = the voxel the host's draw selected from the sample's foreground / background index
@@ -781,5 +1203,169 @@ extern "C" int adell_percentile_finalize(const uint32_t* keys_dev, const double*
   st_percentile_finalize<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(keys_dev, frac_dev, n, dtype,
                                                                                          out_dev);
   ADELL_CUDA_CHECK_LAUNCH();
+  return ADELL_OK;
+}
+
+namespace {
+struct QLayout {
+  int64_t cap, off_br, off_flag, off_cand, off_rank, off_bins, off_cvol, off_crank, off_ckeys, off_kinds, total;
+};
+// n_hist: sets of statistics (one per volume, or ONE for pooled statistics); span: elements behind one set
+QLayout st_quantile_layout(int n_hist, int n_q, int64_t span) {
+  QLayout L;
+  L.cap = span / 24 > 4096 ? span / 24 : 4096;
+  auto up = [](int64_t x) { return (x + 255) / 256 * 256; };
+  int64_t o = 0;
+  L.off_br = o; o += up(static_cast<int64_t>(sizeof(QBracket)) * n_hist * n_q);
+  L.off_flag = o; o += 256;
+  L.off_cand = o; o += up(4 * L.cap * n_hist * n_q);
+  L.off_rank = o; o += up(8ll * n_hist * n_q * 2);
+  L.off_bins = o; o += up((8ll * n_hist * n_q * 2 * 2) << HIST_MAX_BITS);   // (fallback: n_hist x 2 n_q; candidate lists: n_hist n_q x 2)
+  L.off_cvol = o; o += up(static_cast<int64_t>(sizeof(adell_vol)) * n_hist * n_q);
+  L.off_crank = o; o += up(8ll * n_hist * n_q * 2);
+  L.off_ckeys = o; o += up(4ll * n_hist * n_q * 2);
+  L.off_kinds = o; o += up(4ll * n_hist * n_q * 2);
+  L.total = o;
+  return L;
+}
+}  // namespace
+
+extern "C" int64_t adell_quantile_workspace(int n_vols, int n_q, int64_t max_n, int64_t pooled_n) {
+  if (n_vols < 0 || n_q < 1 || n_q > QMAX || max_n < 0 || pooled_n < 0) return -1;
+  return pooled_n > 0 ? st_quantile_layout(1, n_q, pooled_n).total : st_quantile_layout(n_vols, n_q, max_n).total;
+}
+
+extern "C" int adell_quantile_keys(const adell_vol* vols_dev, int n_vols, int64_t max_n, int64_t pooled_n, int dtype, int n_q,
+                                   const uint64_t* rank_dev, uint32_t* keys_dev, void* workspace_dev, int64_t workspace_bytes,
+                                   int flags, void* stream) {
+  if (n_vols == 0) return ADELL_OK;
+  if (vols_dev == nullptr || rank_dev == nullptr || keys_dev == nullptr || workspace_dev == nullptr || n_vols < 0 || max_n < 0 ||
+      pooled_n < 0 || n_q < 1 || n_q > QMAX || dtype < 0 || dtype > ADELL_U8)
+    return ADELL_ERR_BAD_ARG;
+  const int shared = pooled_n > 0 ? 1 : 0;
+  // pooled statistics: the sample takes groups from every volume in proportion to its size
+  if (shared && (n_vols > QS_POOL || pooled_n < 4ll * QS_SAMPLE)) return ADELL_ERR_UNSUPPORTED;
+  const int n_hist = shared ? 1 : n_vols;
+  const QLayout L = st_quantile_layout(n_hist, n_q, shared ? pooled_n : max_n);
+  if (workspace_bytes < L.total) return ADELL_ERR_NO_SPACE;
+  if (reinterpret_cast<uintptr_t>(workspace_dev) & 255u) return ADELL_ERR_ALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
+  QBracket* br = reinterpret_cast<QBracket*>(ws + L.off_br);
+  int* flag = reinterpret_cast<int*>(ws + L.off_flag);
+  uint32_t* cand = reinterpret_cast<uint32_t*>(ws + L.off_cand);
+  unsigned long long* rank_copy = reinterpret_cast<unsigned long long*>(ws + L.off_rank);
+  unsigned long long* bins = reinterpret_cast<unsigned long long*>(ws + L.off_bins);
+  const unsigned long long* rank = reinterpret_cast<const unsigned long long*>(rank_dev);
+  const long long total_n = static_cast<long long>(pooled_n);
+  const size_t smem = (QS_SAMPLE + 8 * 256) * sizeof(uint32_t);
+  cudaError_t e = cudaFuncSetAttribute(st_quantile_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return adell_map_cuda_error(e); }
+  if (flags & ADELL_QUANTILE_REUSE_BRACKETS)
+    st_quantile_reset<<<(n_hist * n_q + 127) / 128, 128, 0, st>>>(br, n_hist * n_q, flag);
+  else
+    st_quantile_sample<<<n_hist, QS_THREADS, smem, st>>>(vols_dev, n_vols, shared, total_n, n_q, rank, br, flag);
+  ADELL_CUDA_CHECK_LAUNCH();
+  dim3 grid(st_blocks_per_vol(max_n, n_vols, 64), n_vols);
+  {
+    // one wave: as many blocks as are resident at once (the generic estimate assumes 8 per SM; this kernel's registers
+    // allow fewer, and a second, partial wave leaves most SMs idle at the end)
+    int dev = 0, sms = 148, occ = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t oe = cudaSuccess;
+    switch (n_q) {
+      case 1: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, st_quantile_main<1>, ST_THREADS, 0); break;
+      case 2: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, st_quantile_main<2>, ST_THREADS, 0); break;
+      case 3: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, st_quantile_main<3>, ST_THREADS, 0); break;
+      default: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, st_quantile_main<4>, ST_THREADS, 0); break;
+    }
+    if (oe != cudaSuccess) { (void)cudaGetLastError(); occ = 0; }
+    if (occ > 0) {
+      const int per_vol = (sms * occ) / n_vols;
+      if (per_vol >= 1 && per_vol < static_cast<int>(grid.x)) grid.x = static_cast<unsigned>(per_vol);
+    }
+  }
+  switch (n_q) {
+    case 1: st_quantile_main<1><<<grid, ST_THREADS, 0, st>>>(vols_dev, shared, total_n, rank, br, cand, L.cap); break;
+    case 2: st_quantile_main<2><<<grid, ST_THREADS, 0, st>>>(vols_dev, shared, total_n, rank, br, cand, L.cap); break;
+    case 3: st_quantile_main<3><<<grid, ST_THREADS, 0, st>>>(vols_dev, shared, total_n, rank, br, cand, L.cap); break;
+    default: st_quantile_main<4><<<grid, ST_THREADS, 0, st>>>(vols_dev, shared, total_n, rank, br, cand, L.cap); break;
+  }
+  ADELL_CUDA_CHECK_LAUNCH();
+  const int64_t span = shared ? static_cast<int64_t>(pooled_n) : max_n;
+  if (span < (1ll << 23)) {
+    // short candidate lists (a few ten thousand keys): one block per (set, quantile) selects both ranks
+    st_quantile_finish<<<n_hist * n_q, QS_THREADS, 0, st>>>(vols_dev, shared, total_n, n_q, rank, br, cand, L.cap, keys_dev, flag);
+    ADELL_CUDA_CHECK_LAUNCH();
+  } else {
+    // long lists: the radix kernels select among the candidates with the whole grid (three passes over a few MB)
+    const int n_sets = n_hist * n_q;
+    adell_vol* cvol = reinterpret_cast<adell_vol*>(ws + L.off_cvol);
+    unsigned long long* crank = reinterpret_cast<unsigned long long*>(ws + L.off_crank);
+    uint32_t* ckeys = reinterpret_cast<uint32_t*>(ws + L.off_ckeys);
+    int* kinds = reinterpret_cast<int*>(ws + L.off_kinds);
+    st_quantile_place<<<(2 * n_sets + 63) / 64, 64, 0, st>>>(vols_dev, shared, total_n, n_q, n_sets, rank, br, cand, L.cap, cvol, crank,
+                                                              kinds, flag);
+    ADELL_CUDA_CHECK_LAUNCH();
+    static const int kKeySched[3][2] = {{21, 11}, {10, 11}, {0, 10}};
+    dim3 cgrid(st_blocks_per_vol(L.cap / 8 + 1, n_sets, 64), n_sets);   // (a list holds a fraction of its capacity)
+    for (int p = 0; p < 3; ++p) {
+      const int shift = kKeySched[p][0], bits = kKeySched[p][1];
+      const bool first = p == 0;
+      const size_t nbins = (static_cast<size_t>(n_sets) * (first ? 1 : 2)) << bits;
+      e = cudaMemsetAsync(bins, 0, nbins * sizeof(unsigned long long), st);
+      if (e != cudaSuccess) { (void)cudaGetLastError(); return adell_map_cuda_error(e); }
+      if (first) {
+        const size_t sm = (static_cast<size_t>(1) << bits) * HIST_REPL * sizeof(uint32_t);
+        if (sm > 48 * 1024) cudaFuncSetAttribute(st_hist_first, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm));
+        st_hist_first<<<cgrid, ST_THREADS, sm, st>>>(cvol, 0, bits, bins, nullptr);
+      } else {
+        const size_t sm = (static_cast<size_t>(1) << bits) * 2 * NEXT_REPL * sizeof(uint32_t);
+        if (sm > 48 * 1024) cudaFuncSetAttribute(st_hist_next, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm));
+        st_hist_next<<<cgrid, ST_THREADS, sm, st>>>(cvol, 2, 0, ckeys, shift, bits, bins, nullptr);
+      }
+      ADELL_CUDA_CHECK_LAUNCH();
+      st_hist_select<<<n_sets * 2, ST_THREADS, 0, st>>>(bins, 2, first ? 1 : 0, shift, bits, ckeys, crank, nullptr);
+      ADELL_CUDA_CHECK_LAUNCH();
+    }
+    st_quantile_merge<<<(2 * n_sets + 63) / 64, 64, 0, st>>>(br, kinds, ckeys, 2 * n_sets, keys_dev);
+    ADELL_CUDA_CHECK_LAUNCH();
+  }
+  // Fallback, gated on the flag (every kernel returns at once when no bracket failed): the three radix passes over
+  // all volumes, writing the same keys.
+  const int n_sel = 2 * n_q;
+  e = cudaMemcpyAsync(rank_copy, rank, sizeof(unsigned long long) * static_cast<size_t>(n_hist) * n_sel, cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return adell_map_cuda_error(e); }
+  static const int kSched[3][3][2] = {{{21, 11}, {10, 11}, {0, 10}}, {{21, 11}, {16, 5}, {-1, 0}}, {{24, 8}, {-1, 0}, {-1, 0}}};
+  dim3 hgrid(st_blocks_per_vol(max_n, n_vols, 64), n_vols);
+  for (int p = 0; p < 3; ++p) {
+    const int shift = kSched[dtype][p][0], bits = kSched[dtype][p][1];
+    if (shift < 0) break;
+    const bool first = p == 0;
+    const size_t nbins = (static_cast<size_t>(n_hist) * (first ? 1 : n_sel)) << bits;
+    e = cudaMemsetAsync(bins, 0, nbins * sizeof(unsigned long long), st);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return adell_map_cuda_error(e); }
+    if (first) {
+      const size_t sm = (static_cast<size_t>(1) << bits) * HIST_REPL * sizeof(uint32_t);
+      if (sm > 48 * 1024) cudaFuncSetAttribute(st_hist_first, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm));
+      st_hist_first<<<hgrid, ST_THREADS, sm, st>>>(vols_dev, shared, bits, bins, flag);
+    } else {
+      const size_t sm = (static_cast<size_t>(1) << bits) * n_sel * NEXT_REPL * sizeof(uint32_t);
+      if (sm > 48 * 1024) cudaFuncSetAttribute(st_hist_next, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm));
+      st_hist_next<<<hgrid, ST_THREADS, sm, st>>>(vols_dev, n_sel, shared, keys_dev, shift, bits, bins, flag);
+    }
+    ADELL_CUDA_CHECK_LAUNCH();
+    st_hist_select<<<n_hist * n_sel, ST_THREADS, 0, st>>>(bins, n_sel, first ? 1 : 0, shift, bits, keys_dev, rank_copy, flag);
+    ADELL_CUDA_CHECK_LAUNCH();
+  }
+  return ADELL_OK;
+}
+
+// debugging / test aid: 1 when the last adell_quantile_keys on this workspace took the gated fallback (read after a sync)
+extern "C" int adell_quantile_fell_back(const void* workspace_dev, int n_vols, int n_q, int64_t max_n, int64_t pooled_n, int* out_host) {
+  if (workspace_dev == nullptr || out_host == nullptr) return ADELL_ERR_BAD_ARG;
+  const QLayout L = pooled_n > 0 ? st_quantile_layout(1, n_q, pooled_n) : st_quantile_layout(n_vols, n_q, max_n);
+  cudaError_t e = cudaMemcpy(out_host, static_cast<const uint8_t*>(workspace_dev) + L.off_flag, sizeof(int), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return adell_map_cuda_error(e); }
   return ADELL_OK;
 }

@@ -315,17 +315,21 @@ class SegmentationBatchAugmenter:
             ch["pre_dev"] = pre_dev.data_ptr() + 8 * np.arange(ch.shape[0], dtype=np.uint64)
         return ch, params
 
-    def prepare_steps(self, batches: Sequence[Sequence[dict]], outs: Sequence[dict]) -> "engine.PreparedSteps":
+    def prepare_steps(self, batches: Sequence[Sequence[dict]], outs: Sequence[dict], pre_dev: torch.Tensor | None = None) -> "engine.PreparedSteps":
         """Draw and compose several consecutive steps at once (same RandomState order as calling
         the augmenter step by step); ``outs[k]`` receives step ``k`` when ``prepared.run(k)`` is
-        called.  Amortises host composition over the steps."""
+        called.  Amortises host composition over the steps.  ``pre_dev``: ``[volumes of all steps, 2]`` device
+        ``{scale, offset}`` rows the kernel reads when a step RUNS — the statistics kernels of step ``k`` may fill its
+        rows right before ``run(k)``."""
         samples = [s for b in batches for s in b]
         nk = len(self.keys)
-        ch, params = (None, None) if self.fast else self.chains(batches, outs)
+        ch, params = (None, None) if self.fast else self.chains(batches, outs, pre_dev=pre_dev)
         if ch is not None:
             dev = self._sample_meta(samples[0])[5][0].device
             return engine.prepare_chain_steps(ch, [len(b) * nk for b in batches], dev,
-                                              keep=[t for o in outs for t in o.values()] + [batches])
+                                              keep=[t for o in outs for t in o.values()] + [batches, pre_dev])
+        if pre_dev is not None:
+            raise NotImplementedError("device-side intensity rows need the single-resample route (some sample fired both RandAffined)")
         plan = self.plan(samples, params)
         ptrs, strides = [], []
         for b, out in zip(batches, outs):
@@ -512,6 +516,31 @@ class ClassificationBatchAugmenter(_BatchBase):
                 raise ValueError("pre_dev must be a contiguous [n, 2] float32 tensor")
             ch["pre_dev"] = pre_dev.data_ptr() + 8 * np.arange(ch.shape[0], dtype=np.uint64)
         return ch, params
+
+    def prepare_steps(self, batches: Sequence[Sequence[dict]], outs: Sequence[dict], pre_dev: torch.Tensor | None = None):
+        """Draw and compose several consecutive steps at once (one draw over all their samples: every stream is consumed
+        in sample order, so this equals step-by-step draws); ``outs[k]`` receives step ``k`` when ``prepared.run(k)`` is
+        called.  ``pre_dev``: ``[volumes of all steps, 2]`` device ``{scale, offset}`` rows read when a step RUNS — the
+        statistics kernels of step ``k`` may fill its rows right before ``run(k)``.  Returns ``None`` when some sample
+        fired both RandAffined (two resamples: call the augmenter step by step)."""
+        if self.fast:
+            return None
+        total = sum(len(b) for b in batches)
+        params = self.draw(total)
+        chs, sizes, s0, v0 = [], [], 0, 0
+        for b, o in zip(batches, outs):
+            B = len(b)
+            sub = dict(flips=params["flips"][s0:s0 + B], fired=params["fired"][:, s0:s0 + B], mats=params["mats"][:, s0:s0 + B])
+            per = sum(b[0][k].shape[0] for k in self.keys)
+            ch, _ = self.chains(b, o, sub, None if pre_dev is None else pre_dev[v0:v0 + B * per])
+            if ch is None:
+                return None
+            chs.append(ch.view(np.uint8))
+            sizes.append(ch.shape[0])
+            s0 += B
+            v0 += B * per
+        ch = np.concatenate(chs).view(CHAIN_DTYPE)
+        return engine.prepare_chain_steps(ch, sizes, outs[0]["image"].device, keep=[o["image"] for o in outs] + [batches, pre_dev])
 
     def __call__(self, samples: Sequence[dict], params=None, out: dict | None = None, pre_dev: torch.Tensor | None = None) -> dict:
         B = len(samples)

@@ -51,11 +51,17 @@ def vol_descriptors(vols: Sequence[torch.Tensor]) -> tuple[torch.Tensor, int]:
     return host.to(dev, non_blocking=True), int(arr["n"].max())
 
 
-def minmax(vols: Sequence[torch.Tensor], desc=None) -> torch.Tensor:
-    """``[n, 2]`` fp32 (min, max) per volume."""
-    dev = _check_vols(vols)
-    d, max_n = desc if desc is not None else vol_descriptors(vols)
-    out = torch.empty(len(vols), 2, dtype=torch.float32, device=dev)
+def minmax(vols: Sequence[torch.Tensor], desc=None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """``[n, 2]`` fp32 (min, max) per volume.  With ``desc`` (the uploaded descriptors of these very volumes) the
+    per-volume checks are skipped; ``out``: a preallocated contiguous ``[n, 2]`` fp32 result."""
+    if desc is None:
+        dev = _check_vols(vols)
+        d, max_n = vol_descriptors(vols)
+    else:
+        d, max_n = desc
+        dev = d.device
+    if out is None:
+        out = torch.empty(len(vols), 2, dtype=torch.float32, device=dev)
     _lib.check(_lib.load().adell_minmax(d.data_ptr(), len(vols), max_n, out.data_ptr(), _stream(dev)), "adell_minmax")
     return out
 
@@ -165,10 +171,10 @@ def resize(vols: Sequence[torch.Tensor], out_shape: Sequence[int], mode: str = "
     return outs
 
 
-def scaler_coefs(stats: torch.Tensor, scaler: int, p0: float, p1: float) -> torch.Tensor:
+def scaler_coefs(stats: torch.Tensor, scaler: int, p0: float, p1: float, out: torch.Tensor | None = None) -> torch.Tensor:
     """``[n, 6]`` coefficients of ``y = ((x*m0 - a)/d)*m1*m2 + b`` for one of the reference scalers."""
     n = stats.shape[0]
-    coefs = torch.empty(n, 6, dtype=torch.float32, device=stats.device)
+    coefs = out if out is not None else torch.empty(n, 6, dtype=torch.float32, device=stats.device)
     _lib.check(
         _lib.load().adell_scaler_coefs(stats.data_ptr(), n, scaler, float(p0), float(p1), coefs.data_ptr(), _stream(stats.device)),
         "adell_scaler_coefs",
@@ -176,10 +182,14 @@ def scaler_coefs(stats: torch.Tensor, scaler: int, p0: float, p1: float) -> torc
     return coefs
 
 
-def coefs_to_affine(coefs: torch.Tensor) -> torch.Tensor:
-    """Collapse the exact program into the fused-mode ``{scale, offset}`` pair (``[n, 2]``)."""
+def coefs_to_affine(coefs: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Collapse the exact program into the fused-mode ``{scale, offset}`` pair (``[n, 2]``; ``out``: a preallocated
+    contiguous ``[n, 2]`` fp32 destination, e.g. the rows a prepared K1 step reads through ``pre_dev``)."""
     n = coefs.shape[0]
-    out = torch.empty(n, 2, dtype=torch.float32, device=coefs.device)
+    if out is None:
+        out = torch.empty(n, 2, dtype=torch.float32, device=coefs.device)
+    elif out.shape != (n, 2) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous [n, 2] float32 tensor")
     _lib.check(_lib.load().adell_coefs_to_affine(coefs.data_ptr(), n, out.data_ptr(), _stream(coefs.device)), "adell_coefs_to_affine")
     return out
 
@@ -234,6 +244,8 @@ class _CudaKernels:
         self.n_vols = len(vols)
         self.dtype = vols[0].dtype
         self.st = _stream(self.dev)
+        self.rank_cache = {}
+        self.workspace, self.brackets_of, self.reuse_brackets = None, None, True
 
     def zeros(self, n, dtype):
         return torch.zeros(n, dtype=dtype, device=self.dev)
@@ -248,6 +260,34 @@ class _CudaKernels:
     def hist_select(self, bins, n_hist, n_sel, shift, bits, prefix, rank):
         _lib.check(self.lib.adell_hist_select(bins.data_ptr(), n_hist, n_sel, shift, bits, prefix.data_ptr(),
                                               rank.data_ptr(), self.st), "adell_hist_select")
+
+    POOL_MAX_VOLS, POOL_MIN_N = 64, 4 * 32768   # what the pooled one-read path accepts (adell_quantile_keys)
+
+    def quantile_keys(self, rank_dev, n_q, pooled_n: int = 0):
+        """``adell_quantile_keys``: exact (lo, hi) keys of every (volume, quantile) — or of the POOLED data when
+        ``pooled_n`` (the total element count) is given — in one full read."""
+        need = self.lib.adell_quantile_workspace(self.n_vols, n_q, self.max_n, pooled_n)
+        # the workspace belongs to this object (= these volumes): the brackets a call leaves in it are reused by the next
+        # call with the same ranks instead of sampling the volumes again
+        ws = self.workspace
+        if ws is None or ws.numel() < need:
+            ws = self.workspace = torch.empty(int(need) + 256, dtype=torch.uint8, device=self.dev)
+            self.brackets_of = None
+        reuse = self.reuse_brackets and self.brackets_of == (n_q, pooled_n, rank_dev.data_ptr())
+        keys = torch.empty((1 if pooled_n else self.n_vols) * n_q * 2, dtype=torch.int32, device=self.dev)
+        _lib.check(self.lib.adell_quantile_keys(self.desc.data_ptr(), self.n_vols, self.max_n, pooled_n, _TORCH_TO_ADELL[self.dtype], n_q,
+                                                rank_dev.data_ptr(), keys.data_ptr(), ws.data_ptr(), ws.numel(), int(reuse), self.st),
+                   "adell_quantile_keys")
+        self.brackets_of = (n_q, pooled_n, rank_dev.data_ptr())
+        self.last_workspace, self.last_pooled = ws, pooled_n
+        return keys
+
+    def fell_back(self, n_q) -> bool:
+        """Whether the last :meth:`quantile_keys` call needed the radix fallback (synchronises; tests / diagnostics)."""
+        out = C.c_int(0)
+        _lib.check(self.lib.adell_quantile_fell_back(self.last_workspace.data_ptr(), self.n_vols, n_q, self.max_n, self.last_pooled,
+                                                     C.byref(out)), "adell_quantile_fell_back")
+        return bool(out.value)
 
     def finalize(self, prefix, frac, n_hist, n_q):
         out = torch.empty(n_hist, n_q, dtype=torch.float32, device=self.dev)
@@ -264,6 +304,7 @@ def percentiles(
     all_reduce=None,
     total_n: int | None = None,
     kernels=None,
+    one_read: bool = True,
 ) -> torch.Tensor:
     """Exact percentiles (numpy 'linear' method) of each volume: ``[n_vols, len(qs)]`` fp32.
 
@@ -272,6 +313,8 @@ def percentiles(
     called on the int64 bin counts after every pass so that every rank selects identically,
     with ``total_n`` the element count over all ranks.  ``kernels`` is the device back end
     (the C ABI by default; the multi-rank host protocol is unit-tested with an injected one).
+    Per-volume statistics take the one-read path (sampled brackets + exact selection among the few keys inside, radix
+    passes as the in-call fallback); ``one_read=False`` forces the three radix passes.
     """
     kern = kernels if kernels is not None else _CudaKernels(vols)
     dtype = vols[0].dtype
@@ -282,16 +325,36 @@ def percentiles(
     if n_sel > 8:
         raise ValueError("at most 4 quantiles per call")
     n_hist = 1 if dataset_wide else n_vols
-    counts = [sum(v.numel() for v in vols) if total_n is None else total_n] if dataset_wide else [v.numel() for v in vols]
-    ranks = np.zeros((n_hist, n_q, 2), np.uint64)
-    frac = np.zeros((n_hist, n_q), np.float64)
-    for h, n in enumerate(counts):
-        for j, q in enumerate(qs):
-            lo, hi, g = numpy_virtual_index(n, q)
-            ranks[h, j] = (lo, hi)
-            frac[h, j] = g
-    rank_dev = kern.upload(ranks.reshape(-1).view(np.int64))
-    frac_dev = kern.upload(frac.reshape(-1))
+    # ranks / interpolation weights depend only on the element counts and the quantiles: computed and uploaded once per
+    # (kernel object, quantiles) — a device-resident cache hands the same volumes back every epoch
+    cache = getattr(kern, "rank_cache", None)
+    ckey = (tuple(float(q) for q in qs), bool(dataset_wide), total_n)
+    hit = cache.get(ckey) if cache is not None else None
+    if hit is None:
+        counts = [sum(v.numel() for v in vols) if total_n is None else total_n] if dataset_wide else [v.numel() for v in vols]
+        ranks = np.zeros((n_hist, n_q, 2), np.uint64)
+        frac = np.zeros((n_hist, n_q), np.float64)
+        by_n = {}
+        for h, n in enumerate(counts):
+            row = by_n.get(n)
+            if row is None:
+                row = by_n[n] = [numpy_virtual_index(n, q) for q in qs]
+            for j, (lo, hi, g) in enumerate(row):
+                ranks[h, j] = (lo, hi)
+                frac[h, j] = g
+        hit = (kern.upload(ranks.reshape(-1).view(np.int64)), kern.upload(frac.reshape(-1)))
+        if cache is not None:
+            cache[ckey] = hit
+    rank_dev, frac_dev = hit
+    if all_reduce is None and isinstance(kern, _CudaKernels) and one_read:
+        # statistics of one rank: one full read of every volume (adell_quantile_keys) instead of one per radix pass
+        if not dataset_wide:
+            return kern.finalize(kern.quantile_keys(rank_dev, n_q), frac_dev, n_hist, n_q)
+        pooled = sum(v.numel() for v in vols)
+        if total_n in (None, pooled) and len(vols) <= kern.POOL_MAX_VOLS and pooled >= kern.POOL_MIN_N:
+            return kern.finalize(kern.quantile_keys(rank_dev, n_q, pooled), frac_dev, 1, n_q)
+    if cache is not None:
+        rank_dev = rank_dev.clone()   # adell_hist_select consumes the ranks
     prefix = kern.zeros(n_hist * n_sel, torch.int32)
     first = True
     for shift, bits in _pass_schedule(dtype):

@@ -200,7 +200,7 @@ class SegAllAffine(_SegBase):
 class SegNorm(_SegBase):
     name = "seg_norm"
     desc = ("config B from RAW cached volumes (int16 images, uint8 mask): per step adell_minmax over the batch's 32 "
-            "volumes -> ScaleIntensityd(0,1) coefficients on the device -> {scale, offset} read by K1 (pre_dev), "
+            "volumes -> ScaleIntensityd(0,1) coefficients on the device -> {scale, offset} read by K1 (pre_dev; 16 steps composed per host call), "
             "affine p=0.2 reflection + 3 flips p=0.25; 6 B (images) / 5 B (mask) algorithmic per output voxel")
 
     def __init__(self, dev, rank, world, seed):
@@ -216,20 +216,32 @@ class SegNorm(_SegBase):
         nk = len(self.image_keys) + 1
         self.bytes_per_voxel = (len(self.image_keys) * 6.0 + 5.0) / nk
         self._desc = {}
+        self._prep = None
+        self._pre = torch.zeros((self.chunk * self.batch * nk, 2), device=dev)
+        self._mm = torch.empty((self.batch * nk, 2), device=dev)
+        self._coefs = torch.empty((self.batch * nk, 6), device=dev)
 
-    def _pre_dev(self, i, batch):
-        keys = self.image_keys + ["mask"]
-        vols = [s[k].reshape(-1) for s in batch for k in keys]
+    def _pre_dev(self, i, batch, out=None):
         nb = self.cache_samples // self.batch
-        d = self._desc.get(i % nb)
-        if d is None:
-            d = self._desc[i % nb] = stats.vol_descriptors(vols)
-        mm = stats.minmax(vols, desc=d)
-        return stats.coefs_to_affine(stats.scaler_coefs(mm, _lib.SCALER_MINMAX, 0.0, 1.0))
+        hit = self._desc.get(i % nb)
+        if hit is None:   # (the descriptors of a cached batch are uploaded once: the cache hands the same volumes back)
+            keys = self.image_keys + ["mask"]
+            vols = [s[k].reshape(-1) for s in batch for k in keys]
+            hit = self._desc[i % nb] = (vols, stats.vol_descriptors(vols))
+        vols, d = hit
+        mm = stats.minmax(vols, desc=d, out=self._mm)
+        return stats.coefs_to_affine(stats.scaler_coefs(mm, _lib.SCALER_MINMAX, 0.0, 1.0, out=self._coefs), out=out)
+
+    chunk = 16   # steps drawn + composed per host call; the statistics kernels of a step fill its pre_dev rows when it runs
 
     def step(self, i):
-        batch = self._batch(i)
-        self.aug(batch, out=self.out, pre_dev=self._pre_dev(i, batch))
+        j = i % self.chunk
+        nv = self.batch * (len(self.image_keys) + 1)
+        if j == 0 or self._prep is None:
+            batches = [self._batch(i - j + t) for t in range(self.chunk)]
+            self._prep = self.aug.prepare_steps(batches, [self.out] * self.chunk, pre_dev=self._pre)
+        self._pre_dev(i, self._batch(i), out=self._pre[j * nv:(j + 1) * nv])
+        self._prep.run(j)
 
     def parity(self):
         from oracle import monai_restated as M
@@ -392,7 +404,7 @@ class SSLTwoViewFast(SSLTwoView):
 class ClsPercentile(Workload):
     name = "cls"
     desc = ("config D: raw cached 208x208x64 volumes (crop + 16 margin), 3 image keys + mask, batch 32; per step exact "
-            "percentiles (0.5, 99.5) of the 96 image volumes (K2/K3 radix select) -> ScaleIntensityRangePercentilesd "
+            "percentiles (0.5, 99.5) of the 96 image volumes (one read per volume: sampled brackets + exact selection, adell_quantile_keys) -> ScaleIntensityRangePercentilesd "
             "coefficients -> {scale, offset} read by K1; OneOf flips -> RandAffined(translate, rotate x, scale; zeros, "
             "prob 0.1) -> CenterSpatialCropd 192x192x48 -> concat")
     batch, src, crop, image_keys, cache_samples = 32, (208, 208, 64), (192, 192, 48), ["t2", "adc", "dwi"], 64
@@ -414,8 +426,10 @@ class ClsPercentile(Workload):
         self._kern = {}
         self._pre_tmpl = torch.zeros((self.batch, len(self.image_keys) + 1, 2), device=dev)
         self._pre_tmpl[:, :, 0] = 1.0
+        self._pre = self._pre_tmpl.repeat(self.chunk, 1, 1).view(-1, 2).contiguous()   # rows of every step of a chunk
+        self._prep = None
 
-    def _pre_dev(self, batch):
+    def _pre_dev(self, batch, out=None):
         ni = len(self.image_keys)
         key = id(batch[0])
         hit = self._kern.get(key)
@@ -426,15 +440,29 @@ class ClsPercentile(Workload):
         kern.st = stats._stream(self.dev)
         pct = stats.percentiles(vols, [0.5, 99.5], kernels=kern)
         aff = stats.coefs_to_affine(stats.scaler_coefs(pct, _lib.SCALER_RANGE, 0.0, 1.0))      # [B * ni, 2]
-        pre = self._pre_tmpl.clone()                                                             # mask rows: {1, 0}
-        pre[:, :ni] = aff.view(len(batch), ni, 2)
-        return pre.view(-1, 2)
+        if out is None:
+            out = self._pre_tmpl.clone().view(-1, 2)                                             # mask rows: {1, 0}
+        out.view(len(batch), ni + 1, 2)[:, :ni] = aff.view(len(batch), ni, 2)
+        return out
 
-    def step(self, i):
+    chunk = 8   # steps drawn + composed per host call; the percentile kernels of a step fill its pre_dev rows when it runs
+
+    def _batch(self, i):
         nb = self.cache_samples // self.batch
         b0 = (i % nb) * self.batch
-        batch = self.cache[b0:b0 + self.batch]
-        self.aug(batch, out=self.out, pre_dev=self._pre_dev(batch))
+        return self.cache[b0:b0 + self.batch]
+
+    def step(self, i):
+        j = i % self.chunk
+        nv = self.batch * (len(self.image_keys) + 1)
+        if j == 0 or self._prep is None:
+            self._prep = self.aug.prepare_steps([self._batch(i - j + t) for t in range(self.chunk)], [self.out] * self.chunk, pre_dev=self._pre)
+            self._prep_at = i - j
+        if self._prep is None:   # some sample of the chunk fired both RandAffined: step by step (two resamples)
+            self.aug(self._batch(i), out=self.out, pre_dev=self._pre_dev(self._batch(i)))
+            return
+        self._pre_dev(self._batch(i), out=self._pre[j * nv:(j + 1) * nv])
+        self._prep.run(j)
 
     def extra(self):
         batch = self.cache[:self.batch]

@@ -420,6 +420,28 @@ int adell_hist_pass(const adell_vol* vols_dev, int n_vols, int64_t max_n, int n_
  * last pass (shift==0) prefix_dev holds the full key of the order statistic. */
 int adell_hist_select(const uint64_t* bins_dev, int n_hist, int n_sel, int pass_shift, int pass_bits,
                       uint32_t* prefix_dev, uint64_t* rank_dev, void* stream);
+/* The same order statistics in ONE full read of every volume (per-volume statistics only; fp32 reads a volume three
+ * times through the passes above): a strided sample of <= 32 Ki keys brackets each quantile's (lo, hi) ranks between
+ * two sample order statistics 6 standard deviations apart, one streaming pass counts the keys beyond the bracket and
+ * equal to its ends and lists the keys strictly inside (a few 0.1 % of the volume), the ranks are then selected
+ * exactly among those.  A bracket that misses, or overflows its list, un-gates the three radix passes inside the same
+ * call, so keys_dev always holds the exact keys ([n_vols][n_q][2], like the prefix array adell_hist_select leaves after
+ * the last pass: feed it to adell_percentile_finalize).  rank_dev: [n_vols][n_q][2] 0-based (lo, hi) ranks, not
+ * modified.  workspace_dev: 256-byte aligned scratch of adell_quantile_workspace(...) bytes.  n_q <= 4; all volumes of
+ * element type `dtype`. */
+/* pooled_n > 0: POOLED statistics over all n_vols volumes (pooled_n = their total element count; dataset-wide
+ * percentiles of one rank): rank_dev / keys_dev are then [1][n_q][2]; at most 64 volumes of >= 128 Ki elements in
+ * total (else ADELL_ERR_UNSUPPORTED: use the radix passes). */
+int64_t adell_quantile_workspace(int n_vols, int n_q, int64_t max_n, int64_t pooled_n);
+/* flags: ADELL_QUANTILE_REUSE_BRACKETS keeps the brackets the previous call with the same arguments left in this
+ * workspace instead of sampling again (the same cached volumes come back every epoch; a bracket is a hint: one that
+ * misses — data changed in place — un-gates the fallback, so the keys stay exact). */
+#define ADELL_QUANTILE_REUSE_BRACKETS 0x01
+int adell_quantile_keys(const adell_vol* vols_dev, int n_vols, int64_t max_n, int64_t pooled_n, int dtype, int n_q,
+                        const uint64_t* rank_dev, uint32_t* keys_dev, void* workspace_dev, int64_t workspace_bytes, int flags,
+                        void* stream);
+/* Test aid (synchronises): *out_host = 1 when the last adell_quantile_keys on this workspace took the radix fallback. */
+int adell_quantile_fell_back(const void* workspace_dev, int n_vols, int n_q, int64_t max_n, int64_t pooled_n, int* out_host);
 /* Converts selected keys back to values and evaluates numpy's 'linear' percentile
  *   v = a + (b-a)*t  (t<0.5)   |   v = b - (b-a)*(1-t)  (t>=0.5)      in float64, cast to fp32
  * for n_q quantiles per volume from the (lo, hi) order statistics; keys_dev is

@@ -257,3 +257,131 @@ def test_randomised_statistics_sweep_against_numpy(seed):
 
     checked, bad = fuzz_stats.sweep(60, seed)
     assert checked > 100 and bad == 0
+
+
+# ----------------------------------------------------------------------------- one-read order statistics
+def _one_read(vols, qs):
+    """(percentiles through adell_quantile_keys, through the three radix passes, whether the one-read call fell back)."""
+    dv = [v.to(DEV) for v in vols]
+    kern = stats._CudaKernels(dv)
+    a = stats.percentiles(dv, qs, kernels=kern).cpu().numpy()
+    fb = kern.fell_back(len(qs))
+    b = stats.percentiles(dv, qs, one_read=False).cpu().numpy()
+    return a, b, fb
+
+
+@pytest.mark.parametrize("kind", ["uniform", "lognormal", "signed", "mri"])
+@pytest.mark.parametrize("qs", [[0.5, 99.5], [1.0, 99.0], [50.0], [0.0, 25.0, 75.0, 100.0]])
+def test_one_read_percentiles_equal_radix_passes_and_numpy(kind, qs):
+    """Volumes larger than the sample (so the brackets ARE estimates): the sampled brackets hold (no fallback) and the
+    keys selected among the candidates equal the three radix passes and np.percentile bit for bit."""
+    R = np.random.RandomState(5)
+    vols = _vols(R, 3, (160, 128, 48), kind)     # 983 040 elements each, 30 x the sample
+    a, b, fb = _one_read(vols, qs)
+    assert np.array_equal(a, b)
+    assert not fb
+    for i, v in enumerate(vols):
+        ref = np.percentile(v.numpy().reshape(-1), np.asarray(qs, np.float64)).astype(np.float32)
+        assert np.array_equal(a[i], ref), (a[i], ref)
+
+
+def test_one_read_percentiles_adversarial_layouts_fall_back_and_stay_exact():
+    """A volume whose values follow the period of the sample stride shows the sample a single phase: its brackets miss,
+    the flag un-gates the radix passes inside the same call, and the result is still exact.  Next to it in the same
+    call: a constant volume, heavy ties, a sorted ramp, a tiny volume."""
+    R = np.random.RandomState(6)
+    n = 160 * 128 * 48
+    stride = 4 * ((n // 4) // (32768 // 4))          # elements between two sampled groups (st_quantile_sample)
+    phase = (np.arange(n) % stride).astype(np.float32)    # sampled positions all hold 0..3
+    periodic = torch.from_numpy(phase + R.rand(n).astype(np.float32) * 0.5).reshape(160, 128, 48)
+    const = torch.full((160, 128, 48), 3.25)
+    ties = torch.from_numpy(R.randint(0, 5, size=n).astype(np.float32)).reshape(160, 128, 48)
+    ramp = torch.arange(n, dtype=torch.float32).reshape(160, 128, 48)
+    qs = [0.5, 99.5]
+    for vols, expect_fb in (([periodic, const, ties, ramp], True), ([const, ties, ramp], False)):
+        a, b, fb = _one_read(vols, qs)
+        assert fb == expect_fb
+        assert np.array_equal(a, b)
+        for i, v in enumerate(vols):
+            ref = np.percentile(v.numpy().reshape(-1), np.asarray(qs, np.float64)).astype(np.float32)
+            assert np.array_equal(a[i], ref), (i, a[i], ref)
+    tiny = [torch.tensor([5.0]).reshape(1, 1, 1), torch.tensor([2.0, -1.0]).reshape(2, 1, 1),
+            torch.from_numpy(R.rand(7, 5, 3).astype(np.float32))]
+    for v in tiny:    # (volumes of different sizes go in separate calls here: ranks depend on n)
+        a, b, fb = _one_read([v], [0.0, 50.0, 100.0])
+        assert not fb and np.array_equal(a, b)
+        assert np.array_equal(a[0], np.percentile(v.numpy().reshape(-1), [0.0, 50.0, 100.0]).astype(np.float32))
+
+
+def test_one_read_percentiles_integer_sources_and_mixed_sizes():
+    R = np.random.RandomState(7)
+    v16 = [torch.from_numpy(R.randint(-300, 4000, size=s).astype(np.int16)) for s in ((96, 96, 40), (50, 40, 30))]
+    a, b, fb = _one_read(v16, [0.5, 50.0, 99.5])
+    assert np.array_equal(a, b) and not fb
+    for i, v in enumerate(v16):
+        assert np.array_equal(a[i], np.percentile(v.numpy().astype(np.float32).reshape(-1), [0.5, 50.0, 99.5]).astype(np.float32))
+    u8 = [torch.from_numpy((R.rand(128, 128, 32) > 0.7).astype(np.uint8) * 200)]
+    a, b, fb = _one_read(u8, [1.0, 99.0])
+    assert np.array_equal(a, b) and not fb
+    assert np.array_equal(a[0], np.percentile(u8[0].numpy().astype(np.float32).reshape(-1), [1.0, 99.0]).astype(np.float32))
+
+
+def test_one_read_pooled_percentiles_equal_radix_passes_and_numpy():
+    """Dataset-wide (pooled) statistics of one rank through the one-read path: volumes of different sizes pooled into one
+    sample, one bracket set, one candidate list."""
+    R = np.random.RandomState(9)
+    vols = [torch.from_numpy(R.lognormal(0, 1, size=s).astype(np.float32)) for s in ((96, 96, 40), (128, 100, 30), (64, 64, 64))]
+    dv = [v.to(DEV) for v in vols]
+    pooled = np.concatenate([v.numpy().reshape(-1) for v in vols])
+    for qs in ([1.0, 99.0], [50.0], [0.0, 0.5, 99.5, 100.0]):
+        kern = stats._CudaKernels(dv)
+        a = stats.percentiles(dv, qs, dataset_wide=True, kernels=kern).cpu().numpy()
+        assert kern.last_pooled == pooled.size and not kern.fell_back(len(qs))
+        b = stats.percentiles(dv, qs, dataset_wide=True, one_read=False).cpu().numpy()
+        ref = np.percentile(pooled, np.asarray(qs, np.float64)).astype(np.float32)
+        assert np.array_equal(a, b) and np.array_equal(a[0], ref), (a, b, ref)
+    # a pool too small for the sampled path takes the radix passes (same result)
+    tiny = [torch.from_numpy(R.rand(10, 10, 10).astype(np.float32)).to(DEV) for _ in range(3)]
+    got = stats.percentiles(tiny, [5.0, 95.0], dataset_wide=True).cpu().numpy()[0]
+    ref = np.percentile(np.concatenate([t.cpu().numpy().reshape(-1) for t in tiny]), [5.0, 95.0]).astype(np.float32)
+    assert np.array_equal(got, ref)
+
+
+def test_one_read_brackets_are_reused_and_a_stale_bracket_falls_back():
+    """The second call on the same kernel object (= the same cached volumes) skips the sampling kernel and reuses the
+    brackets left in its workspace; when the data changed in place those brackets miss, the gated radix passes run,
+    and the percentiles are still exact."""
+    R = np.random.RandomState(10)
+    vols = _vols(R, 2, (160, 128, 48), "lognormal")
+    dv = [v.to(DEV) for v in vols]
+    qs = [0.5, 99.5]
+    kern = stats._CudaKernels(dv)
+    a = stats.percentiles(dv, qs, kernels=kern).cpu().numpy()
+    assert kern.brackets_of is not None and not kern.fell_back(2)
+    b = stats.percentiles(dv, qs, kernels=kern).cpu().numpy()          # reused brackets
+    assert np.array_equal(a, b) and not kern.fell_back(2)
+    for i, v in enumerate(vols):
+        assert np.array_equal(a[i], np.percentile(v.numpy().reshape(-1), np.asarray(qs)).astype(np.float32))
+    dv[0].mul_(1000.0).add_(5.0)                                         # same storage, new content
+    c = stats.percentiles(dv, qs, kernels=kern).cpu().numpy()
+    assert kern.fell_back(2)
+    assert np.array_equal(c[0], np.percentile(dv[0].cpu().numpy().reshape(-1), np.asarray(qs)).astype(np.float32))
+    assert np.array_equal(c[1], a[1])
+
+
+def test_one_read_percentiles_long_candidate_lists():
+    """Volumes / pools of >= 2^23 elements select among their candidate lists with the radix kernels on the whole grid
+    (st_quantile_place / merge) instead of one block per list."""
+    R = np.random.RandomState(11)
+    big = torch.from_numpy(R.lognormal(0, 1, size=(256, 256, 128)).astype(np.float32))
+    big[R.rand(256, 256, 128) < 0.3] = 0.0                                 # a background level: heavy ties at the low end
+    for qs in ([1.0, 99.0], [0.5, 50.0, 99.5]):
+        a, b, fb = _one_read([big], qs)
+        assert not fb and np.array_equal(a, b)
+        assert np.array_equal(a[0], np.percentile(big.numpy().reshape(-1), np.asarray(qs, np.float64)).astype(np.float32))
+    parts = [p.contiguous() for p in big.reshape(4, 64, 256, 128)]
+    dv = [p.to(DEV) for p in parts]
+    kern = stats._CudaKernels(dv)
+    got = stats.percentiles(dv, [1.0, 99.0], dataset_wide=True, kernels=kern).cpu().numpy()[0]
+    assert kern.last_pooled == big.numel() and not kern.fell_back(2)
+    assert np.array_equal(got, np.percentile(big.numpy().reshape(-1), [1.0, 99.0]).astype(np.float32))
