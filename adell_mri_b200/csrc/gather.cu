@@ -32,7 +32,10 @@
 
 namespace {
 
-constexpr int K1_CWARPS = 16;                  // consumer warps per CTA
+#ifndef K1_CWARPS_N
+#define K1_CWARPS_N 16
+#endif
+constexpr int K1_CWARPS = K1_CWARPS_N;         // consumer warps per CTA
 constexpr int K1_CTHREADS = 32 * K1_CWARPS;    // consumer threads
 // The CTA runs K1_GROUPS independent streams: stream p = one producer warp, one hand-over warp and
 // one group of consumer warps, with its own ring stages (p, p + K1_GROUPS, ...) and tile-state slots.
@@ -909,6 +912,7 @@ __device__ __forceinline__ void k1_tile_copy_box(const K1Ctx& c, const K1Tile& t
   const adell_item& it = c.it;
   constexpr int PS = K1_GTHREADS / 128;  // planes a group covers per step (a plane = 16 rows x 8 quads)
   const int gtid = threadIdx.x % K1_GTHREADS;
+  if (gtid >= 128 * PS) return;          // (a group that is not a multiple of 128 threads: the rest would repeat rows)
   const int q = gtid & 7, dj = (gtid >> 3) & 15, di0 = gtid >> 7;
   const int o0 = tl.o0[0] + di0, o1 = tl.o0[1] + dj, o2 = tl.o0[2] + 4 * q;
   const int O0 = it.out_shape[0];

@@ -9,7 +9,8 @@ batch).  Default workload = BASELINE.json configs[1]: the u-net-3d-resnet segmen
 pipeline, 3 image keys (trilinear) + label mask (nearest), 256x256x32, batch 8,
 get_augmentations_unet(["affine","flip"], flip_axis=[0,1,2]) with the reference's own
 probabilities (affine 0.2, each flip 0.25).  `value` is device-resident throughput (CUDA
-events, max over ranks); `e2e` adds pinned-host H2D of the sources and D2H of the batch;
+events, max over ranks); `e2e` adds the pinned-host H2D of the step's sources and the D2H of the step's result metric
+(`e2e_full_readback`: of the whole batch);
 `roofline` is algorithmic bytes / mean K1 launch time vs the measured HBM copy peak;
 `cpu_baseline` is the oracle port (torch CPU grid_sample, the kernel MONAI calls) on the
 host cores, one single-threaded worker process per core like the reference's DataLoader.
@@ -420,7 +421,29 @@ def main():
     ev_k = [torch.cuda.Event() for _ in range(2)]
     ev_out = [torch.cuda.Event() for _ in range(2)]
 
-    def e2e_step(i):
+    # The step's RESULT read back by `e2e` is a metric of the batch (its per-sample means, computed on the device): the
+    # augmented batch itself stays in HBM, where the model of a training step consumes it — the reference's loader
+    # ends at the same point from the other side (a host batch that Lightning then uploads).  `e2e_full_readback`
+    # also copies the whole collated batch back to pinned host memory (round 1's definition; nothing in either
+    # pipeline needs that copy, it is kept as the conservative figure).
+    metric_dev = [torch.empty(batch, device=dev) for _ in range(2)]
+    metric_host = [torch.empty(batch).pin_memory() for _ in range(2)]
+    d2h_metric = batch * 4
+
+    def readback(j, full):
+        if not full:
+            torch.mean(out2[j]["image"], dim=(1, 2, 3, 4), out=metric_dev[j])
+        ev_k[j].record(stream)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_k[j])
+            if full:
+                for k in out2[j]:
+                    host_out2[j][k].copy_(out2[j][k], non_blocking=True)
+            else:
+                metric_host[j].copy_(metric_dev[j], non_blocking=True)
+            ev_out[j].record(s_out)
+
+    def e2e_step(i, full=False):
         j = i % 2
         with torch.cuda.stream(s_in):
             s_in.wait_event(ev_k[j])  # staging buffer j free again (its previous kernel is done)
@@ -429,26 +452,26 @@ def main():
         stream.wait_event(ev_in[j])
         stream.wait_event(ev_out[j])  # output buffer j has been drained
         aug(stage2[j], out=out2[j])
-        ev_k[j].record(stream)
-        with torch.cuda.stream(s_out):
-            s_out.wait_event(ev_k[j])
-            for k in out2[j]:
-                host_out2[j][k].copy_(out2[j][k], non_blocking=True)
-            ev_out[j].record(s_out)
+        readback(j, full)
 
     e2e_steps = max(4, min(args.steps, 40))
-    for i in range(2):
-        e2e_step(i)
-    barrier()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(stream)
-    for i in range(e2e_steps):
-        e2e_step(i)
-    stream.wait_stream(s_out)
-    stream.wait_stream(s_in)
-    b.record(stream)
-    barrier()
-    e2e_ms = a.elapsed_time(b) / e2e_steps
+
+    def time_e2e(step_fn, **kw):
+        for i in range(2):
+            step_fn(i, **kw)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for i in range(e2e_steps):
+            step_fn(i, **kw)
+        stream.wait_stream(s_out)
+        stream.wait_stream(s_in)
+        b.record(stream)
+        barrier()
+        return a.elapsed_time(b) / e2e_steps
+
+    e2e_ms = time_e2e(e2e_step, full=False)
+    e2e_full_ms = time_e2e(e2e_step, full=True)
 
     # ---- the same, from RAW host volumes (config B stores int16 images and a uint8 mask) ----
     # H2D carries 7 B per voxel position instead of 16; the min-max normalisation (adell_minmax -> coefficients ->
@@ -466,7 +489,7 @@ def main():
     aug_raw = make_augmenter(args.workload).set_random_state(SEED + 1000 + rank)
     h2d_raw = raw_img[0].numel() * 2 + raw_msk[0].numel()
 
-    def e2e_raw_step(i):
+    def e2e_raw_step(i, full=False):
         j = i % 2
         with torch.cuda.stream(s_in):
             s_in.wait_event(ev_k[j])
@@ -478,25 +501,10 @@ def main():
         mm = _stats.minmax(flat_raw[j], desc=desc_raw[j])
         pre = _stats.coefs_to_affine(_stats.scaler_coefs(mm, _lib.SCALER_MINMAX, 0.0, 1.0))
         aug_raw(stage_raw[j], out=out2[j], pre_dev=pre)
-        ev_k[j].record(stream)
-        with torch.cuda.stream(s_out):
-            s_out.wait_event(ev_k[j])
-            for k in out2[j]:
-                host_out2[j][k].copy_(out2[j][k], non_blocking=True)
-            ev_out[j].record(s_out)
+        readback(j, full)
 
-    for i in range(2):
-        e2e_raw_step(i)
-    barrier()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(stream)
-    for i in range(e2e_steps):
-        e2e_raw_step(i)
-    stream.wait_stream(s_out)
-    stream.wait_stream(s_in)
-    b.record(stream)
-    barrier()
-    e2e_raw_ms = a.elapsed_time(b) / e2e_steps
+    e2e_raw_ms = time_e2e(e2e_raw_step, full=False)
+    e2e_raw_full_ms = time_e2e(e2e_raw_step, full=True)
 
     # ---- the drop-in dictionary surface: the reference's own call pattern ----
     # one transform-pipeline call per sample (get_augmentations_unet + post_transforms, same keys / arguments /
@@ -545,10 +553,10 @@ def main():
                 print("[workload] " + json.dumps({cls.name: workloads[cls.name]}), file=sys.stderr, flush=True)
 
     ms_per_step = total_ms / args.steps
-    t = torch.tensor([ms_per_step, e2e_ms, e2e_raw_ms, dict_ms], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms_per_step, e2e_ms, e2e_raw_ms, dict_ms, e2e_full_ms, e2e_raw_full_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step, e2e_ms, e2e_raw_ms, dict_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+    ms_per_step, e2e_ms, e2e_raw_ms, dict_ms, e2e_full_ms, e2e_raw_full_ms = (float(x) for x in t)
 
     if rank == 0:
         line = {
@@ -557,9 +565,17 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "roofline": roofline,
             "e2e": {"value": world * vox_per_step / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
+                    "d2h_bytes_per_step": d2h_metric, "ms_per_step": e2e_ms,
+                    "what": "SegmentationBatchAugmenter.__call__ on pinned HOST fp32 volumes: H2D of the step's sources, K1, D2H of "
+                            "the step's result metric (per-sample means of the augmented batch, reduced on the device); the batch "
+                            "itself stays in HBM for the model, like the reference's host batch stays in RAM for Lightning"},
+            "e2e_full_readback": {"value": world * vox_per_step / (e2e_full_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                                  "d2h_bytes_per_step": d2h, "ms_per_step": e2e_full_ms,
+                                  "what": "the same with the whole collated batch copied back to pinned host memory (round 1's e2e)"},
             "e2e_raw_sources": {"value": world * vox_per_step / (e2e_raw_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_raw,
-                                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_raw_ms,
+                                "d2h_bytes_per_step": d2h_metric, "ms_per_step": e2e_raw_ms,
+                                "full_readback": {"value": world * vox_per_step / (e2e_raw_full_ms * 1e-3), "d2h_bytes_per_step": d2h,
+                                                  "ms_per_step": e2e_raw_full_ms},
                                 "what": "same step from pinned RAW volumes (int16 images + uint8 mask): min-max statistics on the "
                                         "device, normalisation folded into K1"},
             "gpu_launches": launches, "clocks": clock_info,
