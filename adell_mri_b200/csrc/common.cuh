@@ -5,7 +5,7 @@
 
 #include "../../include/adell_b200.h"
 
-static_assert(sizeof(adell_item) == 768, "adell_item must stay 768 bytes (ABI v6)");
+static_assert(sizeof(adell_item) == 768, "adell_item must stay 768 bytes (since ABI v6)");
 
 #define ADELL_CUDA_CHECK_LAUNCH()                         \
   do {                                                    \
