@@ -85,6 +85,7 @@ class SegmentationBatchAugmenter:
         output_image_key: str = "image",
         strict: bool = False,
         fast: bool = False,
+        n_crops: int = 1,
     ):
         _check_augment(augment, UNET_AUGMENTS)
         if "trivial" in augment:
@@ -97,11 +98,12 @@ class SegmentationBatchAugmenter:
         self.random_crop_size = None if random_crop_size is None else [int(x) for x in random_crop_size]
         self.has_label = has_label
         self.strict, self.fast = strict, fast
-        if self.random_crop_size is not None and has_label:
-            raise NotImplementedError(
-                "RandCropByPosNegLabeld (label-guided crop centres) is served by the dict-transform surface; "
-                "the batch fast path implements the has_label=False RandSpatialCropd sandwich"
-            )
+        # has_label + random_crop_size: the label-guided sandwich (RandCropByPosNegLabeld(1.1x, num_samples=n_crops) ->
+        # augments per crop -> CenterSpatialCropd, augmentations.py:142-176): the samples must carry the device-resident
+        # index lists of FgBgToIndicesd (``mask_fg_indices`` / ``mask_bg_indices``); the crop centres are selected on
+        # the device (adell_posneg_starts) and K1 reads the window starts from device memory.  Output batch = B * n_crops.
+        self.posneg = self.random_crop_size is not None and has_label
+        self.n_crops = int(n_crops) if self.posneg else 1
         prob = 0.2
         # Randomizable children in Compose order: [crop], affine, shear, flips...
         self.samplers = []
@@ -140,15 +142,32 @@ class SegmentationBatchAugmenter:
             self.flip_R[j] = np.random.RandomState(seeds[i]); i += 1
         return self
 
+    def draw_picks(self, samples: Sequence[dict], shape):
+        """The two host draws of every crop of ``RandCropByPosNegLabeld`` (foreground or background list, entry), sample
+        by sample from the crop transform's stream: ``[(index list tensor, entry), ...]`` in ``[sample, crop]`` order."""
+        picks = []
+        for s in samples:
+            fg, bg = s[f"{self.mask_key}_fg_indices"], s[f"{self.mask_key}_bg_indices"]
+            pos_ratio = 0.5
+            if len(fg) == 0 or len(bg) == 0:
+                if len(fg) == 0 and len(bg) == 0:
+                    raise ValueError("No sampling location available.")
+                pos_ratio = 0 if len(fg) == 0 else 1
+            for _ in range(self.n_crops):
+                lst = fg if self.crop_R.rand() < pos_ratio else bg
+                picks.append((lst, int(self.crop_R.randint(len(lst)))))
+        return picks
+
     def draw(self, batch: int, shape):
-        """All host-side random parameters of one batch, sample by sample in stream order."""
+        """All host-side random parameters of one batch, sample by sample in stream order (``batch`` counts CROPS for the
+        label-guided sandwich: every crop of a sample runs the inner chain on its own)."""
         nk = len(self.keys)
         fired = np.zeros((len(self.samplers), batch), bool)
         mats = np.zeros((len(self.samplers), batch, 4, 4), np.float32)
         mats[..., 0, 0] = mats[..., 1, 1] = mats[..., 2, 2] = mats[..., 3, 3] = 1.0
         flips = np.zeros((batch, 3), bool)
         starts = None
-        if self.random_crop_size is not None:
+        if self.random_crop_size is not None and not self.posneg:
             pre = [int(i * 1.10) for i in self.random_crop_size]
             pre = [min(p, s) for p, s in zip(pre, shape)]
             starts = np.zeros((batch, 3), np.int64)
@@ -184,17 +203,28 @@ class SegmentationBatchAugmenter:
         B, nk = len(samples), len(self.keys)
         metas = [self._sample_meta(s) for s in samples]
         shape = tuple(int(x) for x in metas[0][4][0])
+        nc = self.n_crops
         if params is None:
-            params = self.draw(B, shape)
-        plan = BatchPlan.from_arrays(
-            np.concatenate([m[1] for m in metas]), np.concatenate([m[2] for m in metas]),
-            np.concatenate([m[3] for m in metas]), np.concatenate([m[4] for m in metas]),
-            metas[0][5][0].device, [m[5] for m in metas], fast=self.fast, strict=self.strict)
+            picks = self.draw_picks(samples, shape) if self.posneg else None
+            params = self.draw(B * nc, shape)
+            params["picks"] = picks
+        # volume order [sample, crop, key]: every crop of a sample reads the sample's volumes
+        cat = lambda i: np.concatenate([np.tile(m[i], (nc,) + (1,) * (m[i].ndim - 1)) for m in metas])
+        plan = BatchPlan.from_arrays(cat(1), cat(2), cat(3), cat(4), metas[0][5][0].device, [m[5] for m in metas],
+                                     fast=self.fast, strict=self.strict)
         if pre_dev is not None:
             plan.intensity_from_device(pre_dev)
         rep = lambda x: np.repeat(x, nk, axis=0)
+        B = B * nc                              # from here on one "sample" per crop
         modes = self.modes * B
-        if self.random_crop_size is not None:
+        if self.posneg:
+            from .transforms import _posneg_starts
+
+            pre = [min(int(i * 1.10), s) for i, s in zip(self.random_crop_size, shape)]
+            win = _posneg_starts(params["picks"], shape, pre, plan.device)          # [B, 3] int32 crop starts, on the device
+            plan.keep.append(win)
+            plan.crop_from_device(np.repeat(win.data_ptr() + 12 * np.arange(B, dtype=np.uint64), nk), pre)
+        elif self.random_crop_size is not None:
             pre = [min(int(i * 1.10), s) for i, s in zip(self.random_crop_size, shape)]
             plan.crop(rep(params["starts"]), pre)
         for si in range(len(self.samplers)):
@@ -240,8 +270,8 @@ class SegmentationBatchAugmenter:
         return dst_ptr.astype(np.uint64), dst_stride
 
     def __call__(self, samples: Sequence[dict], params=None, out: dict | None = None, pre_dev: torch.Tensor | None = None) -> dict:
-        B = len(samples)
-        if not self.fast:
+        B = len(samples) * self.n_crops
+        if not self.fast and not self.posneg:
             if out is None:
                 meta = self._sample_meta(samples[0])
                 shape = tuple(int(x) for x in meta[4][0])
@@ -323,7 +353,7 @@ class SegmentationBatchAugmenter:
         rows right before ``run(k)``."""
         samples = [s for b in batches for s in b]
         nk = len(self.keys)
-        ch, params = (None, None) if self.fast else self.chains(batches, outs, pre_dev=pre_dev)
+        ch, params = (None, None) if (self.fast or self.posneg) else self.chains(batches, outs, pre_dev=pre_dev)
         if ch is not None:
             dev = self._sample_meta(samples[0])[5][0].device
             return engine.prepare_chain_steps(ch, [len(b) * nk for b in batches], dev,
@@ -333,10 +363,10 @@ class SegmentationBatchAugmenter:
         plan = self.plan(samples, params)
         ptrs, strides = [], []
         for b, out in zip(batches, outs):
-            p, st = self._dst(out, len(b))
+            p, st = self._dst(out, len(b) * self.n_crops)
             ptrs.append(p); strides.append(st)
         nk = len(self.keys)
-        return engine.prepare_steps(plan, np.concatenate(ptrs), np.concatenate(strides), [len(b) * nk for b in batches],
+        return engine.prepare_steps(plan, np.concatenate(ptrs), np.concatenate(strides), [len(b) * self.n_crops * nk for b in batches],
                                     keep=[t for o in outs for t in o.values()])
 
 

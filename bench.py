@@ -214,7 +214,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cache-samples", type=int, default=32)
     ap.add_argument("--workloads", default="all", help="side workloads for the `workloads` block: 'all', 'none' or a comma list of "
-                    "a,seg_all_affine,seg_norm,seg_crop,ssl,ssl_fast,cls,large (see bench_workloads.py)")
+                    "a,seg_all_affine,seg_norm,seg_crop,seg_crop_batch,ssl,ssl_fast,cls,large (see bench_workloads.py)")
     ap.add_argument("--workload-steps", type=int, default=0, help="timed steps per side workload (0: its own default)")
     ap.add_argument("--no-parity", action="store_true", help="skip the in-run oracle checks of the side workloads")
     args = ap.parse_args()

@@ -323,6 +323,44 @@ class SegCrop(_SegBase):
                            "centre selection): image keys <= tol, masks bit-exact", "max_rel_err": worst, "tol": TOL, "ok": True}
 
 
+class SegCropBatch(SegCrop):
+    name = "seg_crop_batch"
+    desc = ("config B with the label-guided crop sandwich on the BATCH fast path: SegmentationBatchAugmenter(random_crop_size="
+            "[128,128,24], has_label=True, n_crops=2): the two host draws per crop from the lengths of the device-resident "
+            "FgBgToIndicesd lists, centres selected by adell_posneg_starts, K1 reading the window starts from device memory, "
+            "affine p=0.2 reflection + 3 flips per crop, centre crop; 16 crops of 4 keys per step, 8 steps composed per host call")
+    chunk = 8
+
+    def __init__(self, dev, rank, world, seed):
+        super().__init__(dev, rank, world, seed)
+        self.aug = SegmentationBatchAugmenter(["affine", "flip"], self.image_keys + ["mask"], self.image_keys, random_crop_size=self.rc,
+                                              has_label=True, flip_axis=[0, 1, 2], n_crops=self.n_crops).set_random_state(seed, nested=True)
+        self.out = self.aug._alloc_out(self.batch * self.n_crops, tuple(self.rc), dev)
+        self._prep = None
+
+    def step(self, i):
+        j = i % self.chunk
+        if j == 0 or self._prep is None:
+            self._prep = self.aug.prepare_steps([self._batch(i - j + t) for t in range(self.chunk)], [self.out] * self.chunk)
+        self._prep.run(j)
+
+    def parity(self):
+        """The batch path against the dictionary surface on the same seed (which `seg_crop` checks against the eager
+        oracle pipeline): identical batches."""
+        n = 4
+        seed = self.seed + 3
+        want = self._collate.safe_collate_crops([pipe_s for pipe_s in map(self._pipeline(seed), (dict(s) for s in self.cache[:n]))])
+        aug = SegmentationBatchAugmenter(["affine", "flip"], self.image_keys + ["mask"], self.image_keys, random_crop_size=self.rc,
+                                         has_label=True, flip_axis=[0, 1, 2], n_crops=self.n_crops).set_random_state(seed, nested=True)
+        got = aug(self.cache[:n])
+        torch.cuda.synchronize()
+        worst = _close(got["image"], want["image"], "seg_crop_batch image vs the dictionary surface")
+        _equal(got["mask"], want["mask"], "seg_crop_batch mask vs the dictionary surface")
+        return {"checked": f"{n} samples x {self.n_crops} crops vs the dictionary surface on the same seed (itself checked against "
+                           "the eager oracle pipeline by `seg_crop`): image keys <= tol, masks bit-exact", "max_rel_err": worst,
+                "tol": TOL, "ok": True}
+
+
 # ----------------------------------------------------------------------------- config C
 class SSLTwoView(Workload):
     name = "ssl"
@@ -662,7 +700,7 @@ class LargeVolume(Workload):
         return res
 
 
-ALL = [AffineA, SegAllAffine, SegNorm, SegCrop, SSLTwoView, SSLTwoViewFast, ClsPercentile, LargeVolume]
+ALL = [AffineA, SegAllAffine, SegNorm, SegCrop, SegCropBatch, SSLTwoView, SSLTwoViewFast, ClsPercentile, LargeVolume]
 
 
 # ----------------------------------------------------------------------------- runner

@@ -115,3 +115,50 @@ def test_unet_crop_sandwich_device_selection_equals_host_selection(n_crops):
             assert torch.equal(outs[0][k], outs[1][k]), k
     finally:
         T.set_mode(strict=False)
+
+
+def test_batch_fast_path_of_the_label_guided_sandwich_equals_the_dictionary_surface():
+    """SegmentationBatchAugmenter(random_crop_size, has_label=True, n_crops): the vectorised draws consume the crop
+    transform's / samplers' / flips' streams like one pipeline call per sample does, the centres are selected on the
+    device, and the collated [B * n_crops] batch equals safe_collate_crops of the dictionary surface bit for bit; several
+    steps prepared at once equal step-by-step calls."""
+    from adell_mri_b200 import collate, transform_factory as F, transforms as T
+    from adell_mri_b200.pipelines import SegmentationBatchAugmenter
+
+    R = np.random.RandomState(12)
+    shape, rc, n_crops = (56, 48, 20), [24, 24, 10], 2
+    image_keys = ["t2", "adc"]
+    keys = image_keys + ["mask"]
+    fgbg = T.FgBgToIndicesd("mask")
+    cache = []
+    for _ in range(6):
+        s = {k: torch.from_numpy(R.rand(1, *shape).astype(np.float32)).to(DEV) for k in image_keys}
+        s["mask"] = torch.from_numpy((R.rand(1, *shape) > 0.8).astype(np.float32)).to(DEV)
+        cache.append(fgbg(s))
+    T.set_mode(strict=True, fast=False, noise="injected")
+    try:
+        aug = F.get_augmentations_unet(["affine", "flip"], keys, image_keys, [], random_crop_size=rc, has_label=True, n_crops=n_crops,
+                                       flip_axis=[0, 1, 2])
+        tf = F.SegmentationTransforms(keys, image_keys, ["mask"], image_keys, [])
+        for t in aug.transforms[1].transforms:          # make the affine fire often enough to matter in a small batch
+            if isinstance(t, T.RandAffined):
+                t.prob = t.sampler.prob = 0.6
+        pipe = T.Compose([aug, *tf.post_transforms()]).set_random_state(41)
+        want = collate.safe_collate_crops([pipe(dict(s)) for s in cache])
+    finally:
+        T.set_mode(strict=False)
+    bat = SegmentationBatchAugmenter(["affine", "flip"], keys, image_keys, random_crop_size=rc, has_label=True, flip_axis=[0, 1, 2],
+                                     n_crops=n_crops, strict=True)
+    for smp in bat.samplers:
+        smp.prob = 0.6
+    got = bat.set_random_state(41, nested=True)(cache)
+    assert got["image"].shape == (6 * n_crops, 2, *rc) and got["mask"].shape == (6 * n_crops, 1, *rc)
+    assert torch.equal(got["image"], want["image"]) and torch.equal(got["mask"], want["mask"])
+    # three steps of two samples prepared at once == the same six samples in one call (same seed)
+    outs = [bat._alloc_out(2 * n_crops, tuple(rc), torch.device(DEV)) for _ in range(3)]
+    steps = bat.set_random_state(41, nested=True).prepare_steps([cache[0:2], cache[2:4], cache[4:6]], outs)
+    for k in range(3):
+        steps.run(k)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.cat([o["image"] for o in outs]), want["image"])
+    assert torch.equal(torch.cat([o["mask"] for o in outs]), want["mask"])
