@@ -88,6 +88,7 @@ class Chain(C.Structure):
         ("src", C.c_void_p),
         ("dst", C.c_void_p),
         ("pre_dev", C.c_void_p),
+        ("win_dev", C.c_void_p),
         ("src_stride", C.c_int64 * 3),
         ("dst_stride", C.c_int64 * 3),
         ("src_shape", C.c_int32 * 3),

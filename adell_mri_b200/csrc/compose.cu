@@ -64,7 +64,17 @@ int compose_one(const adell_chain& c, adell_item& it) {
   int64_t st[3], n[3];
   bool has_crop0 = false;
   for (int a = 0; a < 3; ++a) has_crop0 |= c.crop0_size[a] > 0;
-  if (has_crop0) {   // BatchPlan.crop: start clipped to [0, cur], size to cur - start
+  const bool win = c.win_dev != nullptr;   // BatchPlan.crop_from_device: the window's start lives in device memory
+  if (win) {
+    if (!has_crop0) return ADELL_ERR_BAD_ARG;
+    for (int a = 0; a < 3; ++a) {
+      if (c.crop0_start[a] != 0) return ADELL_ERR_BAD_ARG;
+      st[a] = 0;
+      const int64_t want = c.crop0_size[a] > 0 ? c.crop0_size[a] : pre.size[a];
+      n[a] = want < pre.size[a] ? want : pre.size[a];
+    }
+    pre.crop(st, n);
+  } else if (has_crop0) {   // BatchPlan.crop: start clipped to [0, cur], size to cur - start
     for (int a = 0; a < 3; ++a) {
       st[a] = IntMap3::clip(c.crop0_start[a], 0, pre.size[a]);
       const int64_t want = c.crop0_size[a] > 0 ? c.crop0_size[a] : pre.size[a];
@@ -100,6 +110,11 @@ int compose_one(const adell_chain& c, adell_item& it) {
     it.src_shape[a] = static_cast<int32_t>(pre.size[a]);
     it.src_vlo[a] = static_cast<int32_t>(pre.vlo[a]);
     it.src_vhi[a] = static_cast<int32_t>(pre.vhi[a]);
+    if (win) {
+      // ADELL_F_WIN_DEV: src_vhi carries the parent's extent counted from the window's lowest element at start 0
+      const int64_t lo = pre.sign[a] > 0 ? pre.off[a] : pre.off[a] - (pre.size[a] - 1);
+      it.src_vhi[a] = static_cast<int32_t>(c.src_shape[a] - lo);
+    }
     it.out_shape[a] = static_cast<int32_t>(affine ? post.size[a] : pre.size[a]);
     it.grid_shape[a] = static_cast<int32_t>(pre.size[a]);
     it.grid_off[a] = static_cast<int32_t>(affine ? post.off[a] : 0);
@@ -124,6 +139,7 @@ int compose_one(const adell_chain& c, adell_item& it) {
   if (!affine) flags |= ADELL_F_IDENTITY;
   if (c.flags & ADELL_CHAIN_STRICT) flags |= ADELL_F_STRICT;
   if (c.pre_dev != nullptr) flags |= ADELL_F_PRE_DEV;
+  if (win) { flags |= ADELL_F_WIN_DEV; it.win_dev = c.win_dev; }
   it.flags = flags;
   return ADELL_OK;
 }

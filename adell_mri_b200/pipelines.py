@@ -221,7 +221,9 @@ class SegmentationBatchAugmenter:
             from .transforms import _posneg_starts
 
             pre = [min(int(i * 1.10), s) for i, s in zip(self.random_crop_size, shape)]
-            win = _posneg_starts(params["picks"], shape, pre, plan.device)          # [B, 3] int32 crop starts, on the device
+            win = params.get("win")
+            if win is None:
+                win = params["win"] = _posneg_starts(params["picks"], shape, pre, plan.device)   # [B, 3] int32 crop starts, on the device
             plan.keep.append(win)
             plan.crop_from_device(np.repeat(win.data_ptr() + 12 * np.arange(B, dtype=np.uint64), nk), pre)
         elif self.random_crop_size is not None:
@@ -271,7 +273,7 @@ class SegmentationBatchAugmenter:
 
     def __call__(self, samples: Sequence[dict], params=None, out: dict | None = None, pre_dev: torch.Tensor | None = None) -> dict:
         B = len(samples) * self.n_crops
-        if not self.fast and not self.posneg:
+        if not self.fast:
             if out is None:
                 meta = self._sample_meta(samples[0])
                 shape = tuple(int(x) for x in meta[4][0])
@@ -280,7 +282,7 @@ class SegmentationBatchAugmenter:
             ch, params = self.chains([samples], [out], params, pre_dev)
             if ch is not None:
                 dev = self._sample_meta(samples[0])[5][0].device
-                engine.prepare_chain_steps(ch, [ch.shape[0]], dev, keep=list(out.values()) + [samples, pre_dev]).run(0)
+                engine.prepare_chain_steps(ch, [ch.shape[0]], dev, keep=list(out.values()) + [samples, pre_dev, params.get("win")]).run(0)
                 return out
         plan = self.plan(samples, params, pre_dev)
         if out is None:
@@ -301,10 +303,10 @@ class SegmentationBatchAugmenter:
                 hit = None
         if hit is None:
             metas = [self._sample_meta(s) for s in batch]
-            dst_ptr, dst_stride = self._dst(out, len(batch))
-            ch = _chain_template(np.concatenate([m[1] for m in metas]), np.concatenate([m[2] for m in metas]),
-                                 np.concatenate([m[3] for m in metas]), np.concatenate([m[4] for m in metas]),
-                                 dst_ptr, dst_stride, self.modes * len(batch), "reflection", self.strict)
+            nc = self.n_crops                     # volume order [sample, crop, key]: every crop reads the sample's volumes
+            dst_ptr, dst_stride = self._dst(out, len(batch) * nc)
+            cat = lambda i: np.concatenate([np.tile(m[i], (nc,) + (1,) * (m[i].ndim - 1)) for m in metas])
+            ch = _chain_template(cat(1), cat(2), cat(3), cat(4), dst_ptr, dst_stride, self.modes * (len(batch) * nc), "reflection", self.strict)
             if self.random_crop_size is not None:
                 shape = tuple(int(x) for x in metas[0][4][0])
                 ch["crop0_size"] = [min(int(i * 1.10), s) for i, s in zip(self.random_crop_size, shape)]
@@ -319,10 +321,12 @@ class SegmentationBatchAugmenter:
         :meth:`plan`), or ``None`` when some sample needs more than one resample (both RandAffined fired: the
         reference resamples twice, which takes the multi-pass route of :class:`BatchPlan`)."""
         nk = len(self.keys)
-        n_samples = sum(len(b) for b in batches)
+        n_samples = sum(len(b) for b in batches) * self.n_crops      # (one "sample" per crop from here on)
         shape = tuple(int(x) for x in self._sample_meta(batches[0][0])[4][0])
         if params is None:
+            picks = self.draw_picks([s for b in batches for s in b], shape) if self.posneg else None
             params = self.draw(n_samples, shape)
+            params["picks"] = picks
         fired = params["fired"]
         if fired.shape[0] > 1 and (fired.sum(axis=0) > 1).any():
             return None, params
@@ -339,6 +343,17 @@ class SegmentationBatchAugmenter:
         ch["flip1"] = np.repeat(params["flips"].astype(np.uint8) @ _FLIP_BITS, nk)
         if params["starts"] is not None:
             ch["crop0_start"] = np.repeat(params["starts"], nk, axis=0)
+        if self.posneg:
+            # label-guided crops: ONE select launch for the crops of all these steps; K1 reads each window's start from
+            # device memory when its step runs
+            from .transforms import _posneg_starts
+
+            dev = self._sample_meta(batches[0][0])[5][0].device
+            pre = [min(int(i * 1.10), s) for i, s in zip(self.random_crop_size, shape)]
+            win = params.get("win")
+            if win is None:
+                win = params["win"] = _posneg_starts(params["picks"], shape, pre, dev)       # [crops, 3] int32 on the device
+            ch["win_dev"] = np.repeat(win.data_ptr() + 12 * np.arange(n_samples, dtype=np.uint64), nk)
         if pre_dev is not None:
             if pre_dev.shape != (ch.shape[0], 2) or pre_dev.dtype != torch.float32 or not pre_dev.is_contiguous():
                 raise ValueError("pre_dev must be a contiguous [n, 2] float32 tensor")
@@ -353,11 +368,11 @@ class SegmentationBatchAugmenter:
         rows right before ``run(k)``."""
         samples = [s for b in batches for s in b]
         nk = len(self.keys)
-        ch, params = (None, None) if (self.fast or self.posneg) else self.chains(batches, outs, pre_dev=pre_dev)
+        ch, params = (None, None) if self.fast else self.chains(batches, outs, pre_dev=pre_dev)
         if ch is not None:
             dev = self._sample_meta(samples[0])[5][0].device
-            return engine.prepare_chain_steps(ch, [len(b) * nk for b in batches], dev,
-                                              keep=[t for o in outs for t in o.values()] + [batches, pre_dev])
+            return engine.prepare_chain_steps(ch, [len(b) * self.n_crops * nk for b in batches], dev,
+                                              keep=[t for o in outs for t in o.values()] + [batches, pre_dev, params.get("win")])
         if pre_dev is not None:
             raise NotImplementedError("device-side intensity rows need the single-resample route (some sample fired both RandAffined)")
         plan = self.plan(samples, params)

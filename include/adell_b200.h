@@ -226,6 +226,8 @@ typedef struct adell_chain {
   const void* src;         /* parent volume, element (0,0,0)                                       */
   float* dst;              /* fp32 destination, element (0,0,0) of the output                      */
   const float* pre_dev;    /* optional device {scale, offset} (sets ADELL_F_PRE_DEV) or NULL       */
+  const int32_t* win_dev;  /* optional device int32[3]: START of the first crop, chosen on the device (adell_posneg_starts;
+                              sets ADELL_F_WIN_DEV): crop0_start must then be 0 and crop0_size the window's extents  */
   int64_t src_stride[3];   /* parent strides in elements                                           */
   int64_t dst_stride[3];
   int32_t src_shape[3];    /* parent extents                                                       */

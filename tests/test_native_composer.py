@@ -218,3 +218,32 @@ def test_seq_prepare_reports_missing_space():
     assert st == _lib.ERR_NO_SPACE and sused2 == sused and used > 256
     st, nl, used, _ = engine._seq_call(sq, (len(sq),), 4096, sused, buf.ctypes.data, buf.size, launches, 2)
     assert st == 0 and nl >= 1
+
+
+def test_label_guided_sandwich_chains_equal_batchplan_items(monkeypatch):
+    """The crop sandwich with device-side windows (RandCropByPosNegLabeld on the batch path): adell_chain.win_dev ==
+    BatchPlan.crop_from_device, byte for byte (the select kernel itself is replaced by a host tensor here: only the
+    addresses of the window rows enter the items)."""
+    from adell_mri_b200 import transforms as T
+
+    monkeypatch.setattr(T, "_posneg_starts", lambda picks, shape, size, dev: torch.zeros((len(picks), 3), dtype=torch.int32))
+    R = np.random.RandomState(6)
+    keys, shape, rc, nc = ["t2", "adc"], (36, 40, 12), [20, 24, 8], 2
+    samples = _samples(R, 6, keys, shape)
+    for s in samples:
+        flat = (s["mask"] > 0).reshape(-1)
+        s["mask_fg_indices"], s["mask_bg_indices"] = torch.nonzero(flat).reshape(-1), torch.nonzero(~flat).reshape(-1)
+    aug = SegmentationBatchAugmenter(["affine", "flip"], keys + ["mask"], keys, random_crop_size=rc, has_label=True, flip_axis=[0, 1, 2],
+                                     n_crops=nc).set_random_state(2)
+    for smp in aug.samplers:
+        smp.prob = 0.5
+    outs = [aug._alloc_out(2 * nc, tuple(rc), torch.device("cpu")) for _ in range(3)]
+    batches = [samples[0:2], samples[2:4], samples[4:6]]
+    ch, params = aug.chains(batches, outs)
+    assert ch is not None and (ch["win_dev"] != 0).all()
+    plan = aug.plan(samples, params)
+    assert not plan.passes
+    ptrs, strides = zip(*[aug._dst(o, 2 * nc) for o in outs])
+    nk = len(aug.keys)
+    sizes = [2 * nc * nk] * 3
+    _same(_native_items(ch, sizes), _plan_items(plan, np.concatenate(ptrs), np.concatenate(strides), sizes))
