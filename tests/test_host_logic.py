@@ -203,3 +203,34 @@ def test_fast_mode_does_not_compose_across_a_crop_that_starts_at_zero():
     for start in (0, 1):
         plan = BatchPlan([img], fast=True).affine(A1, "bilinear", "zeros").crop([start] * 3, [8, 8, 8]).affine(A2, "bilinear", "zeros")
         assert len(plan.passes) == 1, start
+
+
+def test_batch_posneg_picks_consume_the_crop_stream_like_the_dictionary_transform():
+    """SegmentationBatchAugmenter.draw_picks (label-guided crop sandwich on the batch path) makes, sample by sample, the
+    two draws per crop RandCropByPosNegLabeld.randomize makes on device-resident index lists — same stream, same
+    values, same list chosen — including samples with an empty foreground."""
+    import torch
+
+    from adell_mri_b200 import transforms as T
+    from adell_mri_b200.pipelines import SegmentationBatchAugmenter
+
+    R = np.random.RandomState(4)
+    shape, n_crops = (20, 18, 10), 3
+    samples = []
+    for i in range(5):
+        m = (R.rand(*shape) > (1.1 if i == 2 else 0.8))          # sample 2: no foreground at all
+        flat = torch.from_numpy(m.reshape(-1))
+        samples.append({"mask_fg_indices": torch.nonzero(flat).reshape(-1), "mask_bg_indices": torch.nonzero(~flat).reshape(-1)})
+    aug = SegmentationBatchAugmenter(["affine", "flip"], ["t2", "mask"], ["t2"], random_crop_size=[8, 8, 4], has_label=True, n_crops=n_crops)
+    aug.crop_R = np.random.RandomState(77)
+    picks = aug.draw_picks(samples, shape)
+    t = T.RandCropByPosNegLabeld(["t2", "mask"], "mask", [8, 8, 4], num_samples=n_crops, allow_smaller=True)
+    t.R = np.random.RandomState(77)
+    want = []
+    for s in samples:
+        t.randomize(shape, s["mask_fg_indices"], s["mask_bg_indices"])
+        want += t._picks
+    assert len(picks) == len(want) == 5 * n_crops
+    for (la, pa), (lb, pb) in zip(picks, want):
+        assert la is lb and pa == pb
+    assert aug.crop_R.randint(1 << 30) == t.R.randint(1 << 30)
