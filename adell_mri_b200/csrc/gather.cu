@@ -1012,6 +1012,16 @@ struct K1Slot {
   K1Fast fast;
 };
 
+#ifdef K1_PROFILE
+// producer sub-phases (debug builds): cycles of lane 0 between checkpoints, summed over tiles
+__device__ unsigned long long k1_prof2[16];
+#define K1_P2_DECL long long _p2 = clock64();
+#define K1_P2(i) { if (lane == 0) { const long long _t = clock64(); atomicAdd(&k1_prof2[i], static_cast<unsigned long long>(_t - _p2)); _p2 = _t; } else { _p2 = clock64(); } }
+#else
+#define K1_P2_DECL
+#define K1_P2(i)
+#endif
+
 // Warp-parallel: lanes 0..2 own one source axis each (footprint, padding fold, box placement,
 // fast coordinates), lane 3 fills the scalar part of the consumers' register image.  Everything
 // per-item (the fp64 coordinate of output voxel 0 and its derivative, the footprint of a full
@@ -1022,6 +1032,7 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
   const unsigned FULL = 0xffffffffu;
   const bool ax = lane < 3;
   const int a = ax ? lane : 0;
+  K1_P2_DECL
   const int o00 = b0 * it.tile_dim[0], o01 = b1 * it.tile_dim[1], o02 = b2 * it.tile_dim[2];
   const int o0a = a == 0 ? o00 : (a == 1 ? o01 : o02);
   if (ax) { tl.o0[a] = o0a; tl.T[a] = it.tile_dim[a]; }
@@ -1047,6 +1058,7 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
   const double U0 = fma(it.fp_D[3 * a + 2], static_cast<double>(o02),
                         fma(it.fp_D[3 * a + 1], static_cast<double>(o01),
                             fma(it.fp_D[3 * a + 0], static_cast<double>(o00), it.fp_U0[a])));
+  K1_P2(0)   // tile origin coordinate (fp64)
   // column groups of this tile: group term e(g) = D_a2*8g - D_a0*s0(G) - D_a1*s1(G) (see k1_item_shear);
   // fp_smin/fp_smax hold the footprint of ONE group (di, dj over the tile, 8 voxels along axis 2)
   const int G0 = o02 >> 3;
@@ -1068,6 +1080,7 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
       shv[g] = s0 | (s1 << 16);
     }
   }
+  K1_P2(1)   // column-group loop
   const double umin = U0 + emin + static_cast<double>(it.fp_smin[a]), umax = U0 + emax + static_cast<double>(it.fp_smax[a]);
   const bool finite = (umin > -1.0e6) && (umax < 1.0e6);
   if (!__all_sync(FULL, finite)) { if (lane == 0) tl.mode = MODE_DIRECT; return; }
@@ -1116,6 +1129,7 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
   const bool win_full = c.tlo[a] <= 0 && c.thi[a] >= S;
   if (!__all_sync(FULL, fits)) { if (lane == 0) tl.mode = MODE_DIRECT; return; }
   if (!__all_sync(FULL, anyv)) { if (lane == 0) tl.mode = MODE_ZERO; return; }
+  K1_P2(2)   // footprint interval, padding case analysis, fit checks
   const int rmask = static_cast<int>(__ballot_sync(FULL, ax && rm) & 7u);
   const bool allv_all = __all_sync(FULL, allv), win_all = __all_sync(FULL, win_full);
   // a pre offset must not leak into zero-filled (invalid) taps: such tiles use the exact path
@@ -1143,6 +1157,7 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
     Dm2 = static_cast<float>(msign * it.fp_D[3 * a + 2]);
     rA = 1.0f; rB = 0.0f;
   }
+  K1_P2(3)   // votes, box placement, fast coordinate of the tile origin
   K1Fast& f = sl.fast;
   const int na = min(static_cast<int>(it.tile_dim[a]), it.out_shape[a] - o0a);
   const int vlo = it.out_vlo[a] - o0a, vhi = it.out_vhi[a] - o0a;
@@ -1158,6 +1173,7 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
   const float tie = fminf(c.tie, 0.5f - 2.0e-6f * mag);
   const int vl0 = __shfl_sync(FULL, vlo, 0), vl1 = __shfl_sync(FULL, vlo, 1), vl2 = __shfl_sync(FULL, vlo, 2);
   const int vh0 = __shfl_sync(FULL, vhi, 0), vh1 = __shfl_sync(FULL, vhi, 1), vh2 = __shfl_sync(FULL, vhi, 2);
+  K1_P2(4)   // shuffles
   if (ax) {
     tl.lo_t[a] = lo; tl.hi_t[a] = hi;
     tl.box[a] = it.tmap_box[a]; tl.msign[a] = msign; tl.mconst[a] = mconst;
@@ -1202,6 +1218,7 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
     f.noise = it.noise ? it.noise + f.olin0 : nullptr;
     f.philox_seed = it.philox_seed; f.philox_offset = it.philox_offset;
   }
+  K1_P2(5)   // stores of the tile state and the consumers' register image
 }
 
 #ifdef K1_PROFILE
@@ -1228,6 +1245,7 @@ struct K1Walk {
 __device__ __forceinline__ void k1_prepare(const adell_item* __restrict__ items, const int32_t* ts, int n_items,
                                            int tile, int& item, int& cur_start, int& next_start, int& cached_item,
                                            K1Ctx& priv, K1Slot& sl, uint32_t box_addr, int lane, K1Walk& wk, int ring_slots) {
+  K1_P2_DECL
   // monotone walk over the per-item tile prefix, 32 entries per step (one load latency per step,
   // not one per item skipped); `ts` is the shared-memory copy of the prefix when it fits
   while (tile >= next_start) {
@@ -1239,6 +1257,7 @@ __device__ __forceinline__ void k1_prepare(const adell_item* __restrict__ items,
     const int nxt = __shfl_sync(0xffffffffu, v, adv & 31);
     next_start = adv < 32 ? nxt : (item + 1 <= n_items ? ts[item + 1] : 0x7fffffff);
   }
+  K1_P2(8)   // walk over the tile prefix
   constexpr int kItemWords = (sizeof(adell_item) - 128) / 4;  // without the tensor map
   uint32_t* pw = reinterpret_cast<uint32_t*>(&priv) + 32;
   const bool new_item = item != cached_item;
@@ -1264,6 +1283,7 @@ __device__ __forceinline__ void k1_prepare(const adell_item* __restrict__ items,
     ++wk.fresh;
     __syncwarp();
   }
+  K1_P2(9)   // item fetch / context copies
   // tile coordinates inside the item: the successor of the previous tile by carries, else two divisions
   const int n1 = priv.it.n_tiles[1], n2 = priv.it.n_tiles[2];
   if (!new_item && tile == wk.prev_tile + 1 && tile > cur_start) {
@@ -1275,6 +1295,7 @@ __device__ __forceinline__ void k1_prepare(const adell_item* __restrict__ items,
     wk.b0 = local / n1;
   }
   wk.prev_tile = tile;
+  K1_P2(10)  // tile coordinates
   k1_tile_setup(sl.ctx, sl, wk.b0, wk.b1, wk.b2, box_addr, lane);
   if (lane == 0) { sl.tl.item = item; sl.tl.next_plane = 0; }
   __syncwarp();
@@ -2144,6 +2165,11 @@ extern "C" int adell_aug_gather_launches(void) { return 1; }
 extern "C" int adell_debug_prof(unsigned long long* out16, int reset) {
   cudaMemcpyFromSymbol(out16, k1_prof, sizeof(unsigned long long) * 16);
   if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(k1_prof, z, sizeof(z)); }
+  return 0;
+}
+extern "C" int adell_debug_prof2(unsigned long long* out16, int reset) {
+  cudaMemcpyFromSymbol(out16, k1_prof2, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(k1_prof2, z, sizeof(z)); }
   return 0;
 }
 #endif

@@ -249,6 +249,8 @@ def main():
         if PROF:
             out = (ctypes.c_ulonglong * 16)()
             lib.adell_debug_prof(out, 1)
+            lib.adell_debug_prof2.argtypes = [ctypes.c_void_p, ctypes.c_int]
+            lib.adell_debug_prof2((ctypes.c_ulonglong * 16)(), 1)
         ts = time_launches(L)
         ms = statistics.mean(ts)
         gbs = 8.0 * vox / (ms * 1e-3) / 1e9
@@ -264,6 +266,13 @@ def main():
             for lbl, k in (("resampled", 8), ("consumer-copy", 10), ("TMA-store", 12), ("other", 14)):
                 if v[k + 1]:
                     print("   %s tiles: %d, %.0f cycles per tile (first warp of the group)" % (lbl, v[k + 1], v[k] / v[k + 1]))
+            lib.adell_debug_prof2.argtypes = [ctypes.c_void_p, ctypes.c_int]
+            o2 = (ctypes.c_ulonglong * 16)()
+            lib.adell_debug_prof2(o2, 1)
+            w = list(o2)
+            print("   producer phases, cycles per tile (lane 0): origin %.0f | column groups %.0f | footprint / padding cases / fit %.0f | votes, box, "
+                  "fast origin %.0f | shuffles %.0f | stores %.0f || prefix walk %.0f | item fetch + context copies %.0f | tile coordinates %.0f"
+                  % tuple(x / nt for x in (w[0], w[1], w[2], w[3], w[4], w[5], w[8], w[9], w[10])))
             nl = len(ts)
             print("   consumer-group kernel time: mean %.0f cycles per launch, max over groups and launches %d cycles; event time %.0f cycles at 1965 MHz"
                   % (v[5] / (nl * 148 * 2), v[6], ms * 1e-3 * 1965e6))
