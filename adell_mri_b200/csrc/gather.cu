@@ -1026,7 +1026,19 @@ __device__ unsigned long long k1_prof2[16];
 // fast coordinates), lane 3 fills the scalar part of the consumers' register image.  Everything
 // per-item (the fp64 coordinate of output voxel 0 and its derivative, the footprint of a full
 // tile) was computed on the host by adell_aug_prepare.
-__device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0, int b1, int b2, uint32_t box_addr, int lane) {
+// The column-group terms of a tile depend on the item and on the tile's position along axis 2 only: the producer keeps
+// those of its last (item, b2) in registers (a 32-deep volume has ONE tile along axis 2: every tile of the item reuses
+// them).  The group loop was the longest phase of the set-up (profiles/r02_k1_ncu_summary.md: ~1 800 of ~8 500 cycles).
+struct K1GroupCache {
+  int item = -1, b2 = -1;
+  double emin = 0.0, emax = 0.0;
+  float egv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  int shv[4] = {0, 0, 0, 0};
+  int sa_max = 0;
+};
+
+__device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0, int b1, int b2, uint32_t box_addr, int lane,
+                                              K1GroupCache& gc, int item_id, bool slot_fresh) {
   const adell_item& it = c.it;
   K1Tile& tl = sl.tl;
   const unsigned FULL = 0xffffffffu;
@@ -1061,25 +1073,30 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
   K1_P2(0)   // tile origin coordinate (fp64)
   // column groups of this tile: group term e(g) = D_a2*8g - D_a0*s0(G) - D_a1*s1(G) (see k1_item_shear);
   // fp_smin/fp_smax hold the footprint of ONE group (di, dj over the tile, 8 voxels along axis 2)
-  const int G0 = o02 >> 3;
-  const int ng = min(static_cast<int>(it.tile_dim[2]) >> 3, (it.out_shape[2] - o02 + 7) >> 3);
-  double emin = 0.0, emax = 0.0;
-  float egv[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // -D_a0*s0(G) - D_a1*s1(G): added to the group's fast coordinates
-  int shv[4] = {0, 0, 0, 0};
-  int sa_max = 0;  // largest shift of this tile's groups along output axis a (axes 0, 1)
+  if (gc.item != item_id || gc.b2 != b2) {   // (warp-uniform)
+    const int G0 = o02 >> 3;
+    const int ng = min(static_cast<int>(it.tile_dim[2]) >> 3, (it.out_shape[2] - o02 + 7) >> 3);
+    gc.item = item_id; gc.b2 = b2;
+    gc.emin = 0.0; gc.emax = 0.0; gc.sa_max = 0;
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    if (g < ng) {
-      const int s0 = it.shear[0][(G0 + g) & 15], s1 = it.shear[1][(G0 + g) & 15];
-      sa_max = max(sa_max, a == 0 ? s0 : (a == 1 ? s1 : 0));
-      const double sh = -(it.fp_D[3 * a + 0] * s0 + it.fp_D[3 * a + 1] * s1);
-      const double ev = fma(it.fp_D[3 * a + 2], 8.0 * g, sh);
-      emin = g == 0 ? ev : fmin(emin, ev);
-      emax = g == 0 ? ev : fmax(emax, ev);
-      egv[g] = static_cast<float>(sh);
-      shv[g] = s0 | (s1 << 16);
+    for (int g = 0; g < 4; ++g) {
+      gc.egv[g] = 0.0f; gc.shv[g] = 0;
+      if (g < ng) {
+        const int s0 = it.shear[0][(G0 + g) & 15], s1 = it.shear[1][(G0 + g) & 15];
+        gc.sa_max = max(gc.sa_max, a == 0 ? s0 : (a == 1 ? s1 : 0));
+        const double sh = -(it.fp_D[3 * a + 0] * s0 + it.fp_D[3 * a + 1] * s1);
+        const double ev = fma(it.fp_D[3 * a + 2], 8.0 * g, sh);
+        gc.emin = g == 0 ? ev : fmin(gc.emin, ev);
+        gc.emax = g == 0 ? ev : fmax(gc.emax, ev);
+        gc.egv[g] = static_cast<float>(sh);   // -D_a0*s0(G) - D_a1*s1(G): added to the group's fast coordinates
+        gc.shv[g] = s0 | (s1 << 16);
+      }
     }
   }
+  const double emin = gc.emin, emax = gc.emax;
+  float egv[4] = {gc.egv[0], gc.egv[1], gc.egv[2], gc.egv[3]};
+  const int shv[4] = {gc.shv[0], gc.shv[1], gc.shv[2], gc.shv[3]};
+  const int sa_max = gc.sa_max;  // largest shift of this tile's groups along output axis a (axes 0, 1)
   K1_P2(1)   // column-group loop
   const double umin = U0 + emin + static_cast<double>(it.fp_smin[a]), umax = U0 + emax + static_cast<double>(it.fp_smax[a]);
   const bool finite = (umin > -1.0e6) && (umax < 1.0e6);
@@ -1198,7 +1215,13 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
     tl.mode = MODE_STAGED;
     tl.rmask = rmask; tl.all_valid = all_valid;
     const int philox = (it.flags & ADELL_F_PHILOX) ? 1 : 0;
-    f.gb = make_float4(c.pre_s * it.post_scale, fmaf(c.pre_o, it.post_scale, it.post_offset), it.post_offset, it.noise_std);
+    if (slot_fresh) {   // the item-constant part: written when the slot receives this item's context (see k1_prepare)
+      f.gb = make_float4(c.pre_s * it.post_scale, fmaf(c.pre_o, it.post_scale, it.post_offset), it.post_offset, it.noise_std);
+      f.ws = make_float4(c.pre_o * it.post_scale, it.post_offset, 0.0f, 0.0f);
+      f.ds0 = it.dst_stride[0]; f.ds1 = it.dst_stride[1]; f.ds2 = it.dst_stride[2];
+      f.ns1 = it.out_shape[2]; f.ns0 = static_cast<int64_t>(it.out_shape[1]) * it.out_shape[2];
+      f.philox_seed = it.philox_seed; f.philox_offset = it.philox_offset;
+    }
     f.n = make_int4(it.tile_dim[0], it.tile_dim[1], n2, it.tile_dim[2]);
     f.lim = make_int4(-o00, it.out_shape[0] - o00, -o01, it.out_shape[1] - o01);
 #pragma unroll
@@ -1207,16 +1230,13 @@ __device__ __forceinline__ void k1_tile_setup(const K1Ctx& c, K1Slot& sl, int b0
     f.m = make_int4(static_cast<int>(p0), static_cast<int>(p1), rmask | (it.padding << 8),
                     static_cast<int>(box_addr - static_cast<uint32_t>(es) * (K1_MAGIC_BITS * (p0 + p1 + 1u))));
     f.rb = make_float4(rB0, rB1, rB2, tie);
-    f.ws = make_float4(c.pre_o * it.post_scale, it.post_offset, 0.0f, 0.0f);
     f.fl = make_int4((padded || it.noise != nullptr || philox) ? 1 : 0, padded ? 1 : 0, philox, 0);
     f.vlo = make_int4(vl0, vl1, vl2, 0);
     f.vhi = make_int4(vh0, vh1, vh2, 0);
-    f.ds0 = it.dst_stride[0]; f.ds1 = it.dst_stride[1]; f.ds2 = it.dst_stride[2];
     f.dst = it.dst + o00 * it.dst_stride[0] + o01 * it.dst_stride[1] + o02 * it.dst_stride[2];
-    f.ns1 = it.out_shape[2]; f.ns0 = static_cast<int64_t>(it.out_shape[1]) * it.out_shape[2];
-    f.olin0 = (static_cast<uint64_t>(o00) * it.out_shape[1] + o01) * it.out_shape[2] + o02;
-    f.noise = it.noise ? it.noise + f.olin0 : nullptr;
-    f.philox_seed = it.philox_seed; f.philox_offset = it.philox_offset;
+    const uint64_t olin0 = (static_cast<uint64_t>(o00) * it.out_shape[1] + o01) * it.out_shape[2] + o02;
+    f.olin0 = olin0;
+    f.noise = it.noise ? it.noise + olin0 : nullptr;
   }
   K1_P2(5)   // stores of the tile state and the consumers' register image
 }
@@ -1241,10 +1261,12 @@ struct K1Walk {
   int prev_tile = -2;      // last tile this producer prepared
   int b0 = 0, b1 = 0, b2 = 0;  // its tile coordinates inside the item
   int fresh = 0;           // slots of the stream's ring that already hold the current item's context
+  K1GroupCache gc;         // column-group terms of the last (item, tile position along axis 2)
+  unsigned const_mask = 0; // ring slots whose register image already holds the current item's constant part
 };
 __device__ __forceinline__ void k1_prepare(const adell_item* __restrict__ items, const int32_t* ts, int n_items,
                                            int tile, int& item, int& cur_start, int& next_start, int& cached_item,
-                                           K1Ctx& priv, K1Slot& sl, uint32_t box_addr, int lane, K1Walk& wk, int ring_slots) {
+                                           K1Ctx& priv, K1Slot& sl, uint32_t box_addr, int lane, K1Walk& wk, int ring_slots, int slot_pos) {
   K1_P2_DECL
   // monotone walk over the per-item tile prefix, 32 entries per step (one load latency per step,
   // not one per item skipped); `ts` is the shared-memory copy of the prefix when it fits
@@ -1271,6 +1293,7 @@ __device__ __forceinline__ void k1_prepare(const adell_item* __restrict__ items,
     __syncwarp();
     cached_item = item;
     wk.fresh = 0;
+    wk.const_mask = 0u;
   }
   // whole K1Ctx (item image + derived constants), minus the unused tensor-map bytes — only while some
   // slot of the ring (visited round-robin) still holds another item's context: an item has hundreds of tiles
@@ -1296,9 +1319,11 @@ __device__ __forceinline__ void k1_prepare(const adell_item* __restrict__ items,
   }
   wk.prev_tile = tile;
   K1_P2(10)  // tile coordinates
-  k1_tile_setup(sl.ctx, sl, wk.b0, wk.b1, wk.b2, box_addr, lane);
+  const bool need_const = !(wk.const_mask >> slot_pos & 1u);
+  k1_tile_setup(sl.ctx, sl, wk.b0, wk.b1, wk.b2, box_addr, lane, wk.gc, item, need_const);
   if (lane == 0) { sl.tl.item = item; sl.tl.next_plane = 0; }
   __syncwarp();
+  if (need_const && sl.tl.mode == MODE_STAGED) wk.const_mask |= 1u << slot_pos;   // (only a staged tile writes the image)
 }
 
 // Producer, after the TMA load of a tile whose box contains alignment-slack columns completed:
@@ -1415,7 +1440,7 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
       // safe to overwrite: the stream has one more slot than stages, and this warp's previous issue
       // waited for the release of the stage of the slot's previous tile
       k1_prepare(items, ts, n_items, tile, item, cur_start, next_start, cached_item, priv[strm], slots[slot],
-                 smem_u32(smem + static_cast<size_t>(stage) * stage_bytes), lane, wk, rl.n);
+                 smem_u32(smem + static_cast<size_t>(stage) * stage_bytes), lane, wk, rl.n, rl.i);
       K1_PROF_ADD(2)
       mbar_wait_relaxed(empty + stage, rs.phase ^ 1);
       K1_PROF_ADD(0)
