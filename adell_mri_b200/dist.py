@@ -66,9 +66,19 @@ def dataset_percentiles(vols: Sequence[torch.Tensor], qs: Sequence[float], group
     local_n = sum(v.numel() for v in vols)
     if world == 1:
         return stats.percentiles(vols, qs, dataset_wide=True, kernels=kernels)
-    n = torch.tensor([local_n], dtype=torch.int64, device=vols[0].device)
-    dist.all_reduce(n, group=group)
+    # the pooled element count: all-reduced once per kernel object (= per set of cached volumes), not per call — it costs a
+    # collective AND a host synchronisation
+    total = getattr(kernels, "pooled_total", None) if kernels is not None else None
+    if total is None or total[0] != (local_n, world):
+        n = torch.tensor([local_n], dtype=torch.int64, device=vols[0].device)
+        dist.all_reduce(n, group=group)
+        total = ((local_n, world), int(n.item()))
+        if kernels is not None:
+            try:
+                kernels.pooled_total = total
+            except AttributeError:
+                pass
     return stats.percentiles(
-        vols, qs, dataset_wide=True, total_n=int(n.item()),
+        vols, qs, dataset_wide=True, total_n=total[1],
         all_reduce=lambda bins: dist.all_reduce(bins, group=group), kernels=kernels,
     )

@@ -394,14 +394,16 @@ def prepare_seq_steps(seqs: np.ndarray, step_sizes, device: torch.device, keep=N
     launches = (_lib.SeqLaunch * max_l)()
     with torch.cuda.device(device):
         alloc = _scratch_for(device)
-        scratch = alloc(1)
+        alloc(1)
+        scratch = _scratch[(device, torch.cuda.current_stream(device).cuda_stream)]   # the WHOLE (device, stream) buffer
         ring = _ring(device)
         need = _seq_bytes_bound(seqs, sizes)
         for _ in range(3):
             k, host = ring.acquire(need)
             st, nl, used, sused = _seq_call(seqs, sizes, scratch.data_ptr(), scratch.numel(), host.ctypes.data, need, launches, 0)
             if st == _lib.ERR_NO_SPACE and sused > scratch.numel():
-                scratch = alloc(int(sused))   # grows the (device, stream) buffer
+                alloc(int(sused))   # grows the (device, stream) buffer
+                scratch = _scratch[(device, torch.cuda.current_stream(device).cuda_stream)]
                 continue
             _lib.check(st, "adell_seq_prepare_steps")
             break
