@@ -1320,6 +1320,10 @@ __device__ __forceinline__ void k1_prepare(const adell_item* __restrict__ items,
   wk.prev_tile = tile;
   K1_P2(10)  // tile coordinates
   const bool need_const = !(wk.const_mask >> slot_pos & 1u);
+#ifdef K1_EXP_FREE_PRODUCER
+  // TIMING EXPERIMENT (wrong voxels): 7 of 8 tiles re-use the state this slot holds of an earlier tile of the same item
+  if (!need_const && (tile & 7) != 0) { if (lane == 0) sl.tl.next_plane = 0; __syncwarp(); return; }
+#endif
   k1_tile_setup(sl.ctx, sl, wk.b0, wk.b1, wk.b2, box_addr, lane, wk.gc, item, need_const);
   if (lane == 0) { sl.tl.item = item; sl.tl.next_plane = 0; }
   __syncwarp();
@@ -1545,6 +1549,9 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
       // stored by the hand-over warp (TMA): the consumers only pass the stage on
     } else if (mode == MODE_ZERO) {
       k1_tile_zero(ctx, tl);
+#ifdef K1_EXP_NO_CONSUME
+    } else if (mode == MODE_STAGED) {   // TIMING EXPERIMENT (no voxels written): what the producer + TMA side alone sustains
+#endif
     } else if (mode == MODE_STAGED) {
       // a pre offset must not leak into zero-filled (invalid) taps: the fast loops then scale it by the
       // sum of the valid tap weights (variant 3); where that is not available, the exact path
