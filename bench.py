@@ -516,15 +516,26 @@ def main():
     pipe_d = _T.Compose([_F.get_augmentations_unet(["affine", "flip"], keys, image_keys, [], flip_axis=[0, 1, 2]),
                          *tf_d.post_transforms()]).set_random_state(SEED + 2000 + rank)
     dict_steps = max(4, min(args.steps, 40))
-    for i in range(3):
-        _collate.safe_collate([pipe_d(dict(smp)) for smp in batch_of(i)])
+    # warm-up: the collated outputs are fresh torch allocations (a cold cudaMalloc of 200 MB costs milliseconds); the loop
+    # below keeps the previous step's batch alive while the next one is produced, like a training loop does
+    for i in range(12):
+        res_d = _collate.safe_collate([pipe_d(dict(smp)) for smp in batch_of(i)])
     barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    _prof = None
+    if os.environ.get("BENCH_PROFILE_DICT") == "1":
+        import cProfile
+        _prof = cProfile.Profile()
+        _prof.enable()
     t0 = time.perf_counter()
     a.record(stream)
     for i in range(dict_steps):
         res_d = _collate.safe_collate([pipe_d(dict(smp)) for smp in batch_of(i)])
     b.record(stream)
+    if _prof is not None:
+        import pstats
+        _prof.disable()
+        pstats.Stats(_prof, stream=sys.stderr).sort_stats("tottime").print_stats(25)
     dict_host_ms = 1e3 * (time.perf_counter() - t0) / dict_steps
     barrier()
     dict_ms = a.elapsed_time(b) / dict_steps

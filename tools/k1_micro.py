@@ -29,7 +29,7 @@ dev = torch.device("cuda:0")
 PEAK = 6541.1
 
 
-def seg_items(R, prob, n_batches=4, B=8, shape=(256, 256, 32), integer=False):
+def seg_items(R, prob, n_batches=4, B=8, shape=(256, 256, 32), integer=False, exact_k=None):
     """integer=True: int16 image volumes + uint8 mask with a device-side {scale, offset} (config B from raw volumes)."""
     g = torch.Generator(device=dev).manual_seed(0)
     out_img = torch.empty((B, 3, *shape), device=dev)
@@ -38,8 +38,11 @@ def seg_items(R, prob, n_batches=4, B=8, shape=(256, 256, 32), integer=False):
     keep = [out_img, out_mask]
     for _ in range(n_batches):
         vols, mats, fired, flips, dsts = [], [], [], [], []
+        fired_b = R.permutation(B) < exact_k if exact_k is not None else None
         for b in range(B):
             f = R.rand() < prob
+            if fired_b is not None:
+                f = bool(fired_b[b])
             ang = R.uniform(-1, 1, 3) * np.array([np.pi / 8, np.pi / 8, np.pi / 16])
             A = geometry.compose_affine(rotate=ang[None])[0]
             fl = R.rand(3) < 0.25
@@ -233,6 +236,8 @@ def main():
             L, vox, keep = seg_items(R, 1.0)
         elif name == "seg_copy":
             L, vox, keep = seg_items(R, 0.0)
+        elif name.startswith("seg_k"):   # exactly k of the 8 samples of every batch resampled
+            L, vox, keep = seg_items(R, 0.0, exact_k=int(name[5:]))
         elif name in ("seg_i16", "seg_i16_all", "seg_i16_copy"):
             L, vox, keep = seg_items(R, {"seg_i16": 0.2, "seg_i16_all": 1.0, "seg_i16_copy": 0.0}[name], integer=True)
         elif name == "ssl":
