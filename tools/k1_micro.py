@@ -29,7 +29,7 @@ dev = torch.device("cuda:0")
 PEAK = 6541.1
 
 
-def seg_items(R, prob, n_batches=4, B=8, shape=(256, 256, 32), integer=False, exact_k=None):
+def seg_items(R, prob, n_batches=4, B=8, shape=(256, 256, 32), integer=False, exact_k=None, drop=None):
     """integer=True: int16 image volumes + uint8 mask with a device-side {scale, offset} (config B from raw volumes)."""
     g = torch.Generator(device=dev).manual_seed(0)
     out_img = torch.empty((B, 3, *shape), device=dev)
@@ -46,6 +46,13 @@ def seg_items(R, prob, n_batches=4, B=8, shape=(256, 256, 32), integer=False, ex
             ang = R.uniform(-1, 1, 3) * np.array([np.pi / 8, np.pi / 8, np.pi / 16])
             A = geometry.compose_affine(rotate=ang[None])[0]
             fl = R.rand(3) < 0.25
+            tstore = (not f) and not fl[1] and not fl[2]   # identity item that takes the TMA-store path
+            if drop == "tstore" and tstore:
+                continue
+            if drop == "not_tstore" and not tstore:
+                continue
+            if drop == "vcopy" and not f and not tstore:
+                continue
             for k in range(4):
                 if not integer:
                     vols.append(torch.rand(shape, device=dev, generator=g))
@@ -55,15 +62,20 @@ def seg_items(R, prob, n_batches=4, B=8, shape=(256, 256, 32), integer=False, ex
                     vols.append((torch.rand(shape, device=dev, generator=g) > 0.7).to(torch.uint8))
                 mats.append(A); fired.append(f); flips.append(fl)
                 dsts.append(out_img[b, k] if k < 3 else out_mask[b, 0])
+        if not vols:
+            continue
+        nb = len(vols) // 4
         plan = BatchPlan(vols)
         if integer:
-            pre = torch.tensor([[1.0 / 4000.0, 0.0]] * 3 + [[1.0, 0.0]], device=dev).repeat(B, 1).contiguous()
+            pre = torch.tensor([[1.0 / 4000.0, 0.0]] * 3 + [[1.0, 0.0]], device=dev).repeat(nb, 1).contiguous()
             plan.intensity_from_device(pre)
             keep.append(pre)
-        plan.affine(np.stack(mats), (["bilinear"] * 3 + ["nearest"]) * B, "reflection", where=np.array(fired))
+        plan.affine(np.stack(mats), (["bilinear"] * 3 + ["nearest"]) * nb, "reflection", where=np.array(fired))
         plan.flip(np.stack(flips))
         launches.append(pack(plan, dsts))
         keep.append(vols)
+    if drop is not None:
+        print("   voxel-channels per launch (mean over the batches):", sum(l[1] for l in launches) * int(np.prod(shape)) // len(launches))
     return launches, B * 4 * int(np.prod(shape)), keep
 
 
@@ -236,8 +248,9 @@ def main():
             L, vox, keep = seg_items(R, 1.0)
         elif name == "seg_copy":
             L, vox, keep = seg_items(R, 0.0)
-        elif name.startswith("seg_k"):   # exactly k of the 8 samples of every batch resampled
-            L, vox, keep = seg_items(R, 0.0, exact_k=int(name[5:]))
+        elif name.startswith("seg_k"):   # exactly k of the 8 samples of every batch resampled; suffix _rv / _t: without / only the TMA-store samples
+            kk, _, sfx = name[5:].partition("_")
+            L, vox, keep = seg_items(R, 0.0, exact_k=int(kk), drop={"": None, "rv": "tstore", "t": "not_tstore", "rt": "vcopy"}[sfx])
         elif name in ("seg_i16", "seg_i16_all", "seg_i16_copy"):
             L, vox, keep = seg_items(R, {"seg_i16": 0.2, "seg_i16_all": 1.0, "seg_i16_copy": 0.0}[name], integer=True)
         elif name == "ssl":
