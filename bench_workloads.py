@@ -68,6 +68,28 @@ class Workload:
     def step(self, i: int) -> None:
         raise NotImplementedError
 
+    # Chunked composition with look-ahead, like a loader that works ahead of the consumer: the chunk of `chunk` steps
+    # that contains step i is drawn + composed + uploaded by ONE host call, make(first_step); the NEXT chunk is composed
+    # right after the last step of the current one has been launched, while the device still has (most of) a chunk
+    # queued — the composition burst overlaps with it.  Draw order is unchanged (chunks are composed in order).
+    chunk = 1
+    _prep = None
+    _prep_first = None
+    _ahead = None
+
+    def _prepared(self, i: int, make):
+        first = i - i % self.chunk
+        if self._prep is None or self._prep_first != first:
+            nxt = self._ahead
+            self._prep = nxt[1] if (nxt is not None and nxt[0] == first) else make(first)
+            self._prep_first, self._ahead = first, None
+        return self._prep
+
+    def _lookahead(self, i: int, make) -> None:
+        if i % self.chunk == self.chunk - 1 and self._ahead is None:
+            first = i - i % self.chunk + self.chunk
+            self._ahead = (first, make(first))
+
     def parity(self) -> dict:
         raise NotImplementedError
 
@@ -98,11 +120,11 @@ class AffineA(Workload):
         self._dptr = (self.out.data_ptr() + esz * self.out.stride(0) * np.arange(self.N, dtype=np.int64)).astype(np.uint64)
         self.last_mats = None
         self._chains = None
+        self._next = None
 
-    def step(self, i):
+    def _compose(self):
         fired, p = self.sampler.draw_batch(self.N, n_keys=1)
         mats = geometry.compose_affine(p["rotate"], p["shear"], p["translate"], p["scale"], batch=self.N)
-        self.last_mats = mats
         if self._chains is None:   # static part of the adell_chain descriptors: one per volume
             from adell_mri_b200.pipelines import _chain_template
             self._chains = _chain_template(self._ptr, self._stride, self._dtype, self._shape, self._dptr, self._stride,
@@ -110,7 +132,15 @@ class AffineA(Workload):
             self._chains["flags"] |= _lib.CHAIN_AFFINE
         ch = self._chains.copy()
         ch["A"] = mats[:, :3].reshape(self.N, 12)
-        engine.prepare_chain_steps(ch, [self.N], self.dev, keep=[self.src, self.out]).run(0)
+        return mats, engine.prepare_chain_steps(ch, [self.N], self.dev, keep=[self.src, self.out])
+
+    def step(self, i):
+        # every step is drawn + composed + uploaded on its own (512 items), one step ahead of the launch: the host
+        # composes step i + 1 while the device runs step i
+        mats, prep = self._next if self._next is not None else self._compose()
+        self.last_mats = mats
+        prep.run(0)
+        self._next = self._compose()
 
     def parity(self):
         from oracle import monai_restated as M
@@ -180,8 +210,14 @@ class SegAllAffine(_SegBase):
         self.aug = self._augmenter(1.0)
         self._alloc_out()
 
+    chunk = 16   # steps drawn + composed per host call
+
+    def _make(self, first):
+        return self.aug.prepare_steps([self._batch(first + t) for t in range(self.chunk)], [self.out] * self.chunk)
+
     def step(self, i):
-        self.aug(self._batch(i), out=self.out)
+        self._prepared(i, self._make).run(i % self.chunk)
+        self._lookahead(i, self._make)
 
     def parity(self):
         batch = self._batch(0)
@@ -234,14 +270,16 @@ class SegNorm(_SegBase):
 
     chunk = 16   # steps drawn + composed per host call; the statistics kernels of a step fill its pre_dev rows when it runs
 
+    def _make(self, first):
+        return self.aug.prepare_steps([self._batch(first + t) for t in range(self.chunk)], [self.out] * self.chunk, pre_dev=self._pre)
+
     def step(self, i):
         j = i % self.chunk
         nv = self.batch * (len(self.image_keys) + 1)
-        if j == 0 or self._prep is None:
-            batches = [self._batch(i - j + t) for t in range(self.chunk)]
-            self._prep = self.aug.prepare_steps(batches, [self.out] * self.chunk, pre_dev=self._pre)
+        prep = self._prepared(i, self._make)
         self._pre_dev(i, self._batch(i), out=self._pre[j * nv:(j + 1) * nv])
-        self._prep.run(j)
+        prep.run(j)
+        self._lookahead(i, self._make)
 
     def parity(self):
         from oracle import monai_restated as M
@@ -338,11 +376,12 @@ class SegCropBatch(SegCrop):
         self.out = self.aug._alloc_out(self.batch * self.n_crops, tuple(self.rc), dev)
         self._prep = None
 
+    def _make(self, first):
+        return self.aug.prepare_steps([self._batch(first + t) for t in range(self.chunk)], [self.out] * self.chunk)
+
     def step(self, i):
-        j = i % self.chunk
-        if j == 0 or self._prep is None:
-            self._prep = self.aug.prepare_steps([self._batch(i - j + t) for t in range(self.chunk)], [self.out] * self.chunk)
-        self._prep.run(j)
+        self._prepared(i, self._make).run(i % self.chunk)
+        self._lookahead(i, self._make)
 
     def parity(self):
         """The batch path against the dictionary surface on the same seed (which `seg_crop` checks against the eager
@@ -382,13 +421,14 @@ class SSLTwoView(Workload):
     chunk = 16   # steps drawn, composed (adell_seq_prepare_steps) and uploaded per host call, like a loader working ahead
     default_steps = 32
 
+    def _make(self, first):
+        nb = self.cache_samples // self.batch
+        batches = [self.cache[((first + t) % nb) * self.batch:((first + t) % nb + 1) * self.batch] for t in range(self.chunk)]
+        return self.aug.prepare_steps(batches, [self.out] * self.chunk)
+
     def step(self, i):
-        j = i % self.chunk
-        if j == 0 or self._prep is None:
-            nb = self.cache_samples // self.batch
-            batches = [self.cache[((i - j + t) % nb) * self.batch:((i - j + t) % nb + 1) * self.batch] for t in range(self.chunk)]
-            self._prep = self.aug.prepare_steps(batches, [self.out] * self.chunk)
-        self._prep.run(j)
+        self._prepared(i, self._make).run(i % self.chunk)
+        self._lookahead(i, self._make)
 
     def parity(self):
         """Stream level: 3 samples through a second augmenter (host-drawn noise injected, member subsets from the
@@ -490,17 +530,19 @@ class ClsPercentile(Workload):
         b0 = (i % nb) * self.batch
         return self.cache[b0:b0 + self.batch]
 
+    def _make(self, first):
+        return self.aug.prepare_steps([self._batch(first + t) for t in range(self.chunk)], [self.out] * self.chunk, pre_dev=self._pre)
+
     def step(self, i):
         j = i % self.chunk
         nv = self.batch * (len(self.image_keys) + 1)
-        if j == 0 or self._prep is None:
-            self._prep = self.aug.prepare_steps([self._batch(i - j + t) for t in range(self.chunk)], [self.out] * self.chunk, pre_dev=self._pre)
-            self._prep_at = i - j
-        if self._prep is None:   # some sample of the chunk fired both RandAffined: step by step (two resamples)
+        prep = self._prepared(i, self._make)
+        if prep is None:   # some sample of the chunk fired both RandAffined: step by step (two resamples)
             self.aug(self._batch(i), out=self.out, pre_dev=self._pre_dev(self._batch(i)))
             return
         self._pre_dev(self._batch(i), out=self._pre[j * nv:(j + 1) * nv])
-        self._prep.run(j)
+        prep.run(j)
+        self._lookahead(i, self._make)
 
     def extra(self):
         batch = self.cache[:self.batch]
@@ -570,6 +612,8 @@ class LargeVolume(Workload):
         self.R = np.random.RandomState(seed)
         self.vox_per_step = self.M_vols * int(np.prod(self.shape))
         self.last = None
+        self._next = None
+        self._pre = torch.zeros((self.M_vols, 2), device=dev)
         self.collective_bytes = 0
         self._kern = None
 
@@ -581,17 +625,29 @@ class LargeVolume(Workload):
         self._kern.st = stats._stream(self.dev)
         return adist.dataset_percentiles(self.flat, [1.0, 99.0], kernels=self._kern)
 
-    def step(self, i):
-        pct = self._percentiles()                                                     # [1, 2], identical on all ranks
-        pre1 = stats.coefs_to_affine(stats.scaler_coefs(pct, _lib.SCALER_RANGE, 0.0, 1.0))   # [1, 2]
-        pre = pre1.expand(self.M_vols, 2).contiguous()
+    def _compose(self):
+        """Draws the step's affines and composes + uploads its K1 launch; the {scale, offset} rows are read by K1 from
+        ``self._pre`` (device memory) when it runs, so this needs no statistics yet."""
         rot = self.R.uniform(-1, 1, (self.M_vols, 3)) * np.array([np.pi / 8, np.pi / 8, np.pi / 16])
         mats = geometry.compose_affine(rotate=rot, batch=self.M_vols)
         plan = BatchPlan(self.vols)
-        plan.intensity_from_device(pre)
+        plan.intensity_from_device(self._pre)
         plan.affine(mats, "bilinear", "zeros")
-        engine.execute(plan, [self.out[b, 0] for b in range(self.M_vols)])
+        outs = [self.out[b, 0] for b in range(self.M_vols)]
+        dst_ptr = np.array([o.data_ptr() for o in outs], np.uint64)
+        dst_stride = np.array([o.stride() for o in outs], np.int64)
+        return mats, engine.prepare_steps(plan, dst_ptr, dst_stride, [self.M_vols], keep=[self.vols, self.out, self._pre])
+
+    def step(self, i):
+        # the K1 launch of a step is composed one step ahead (while the device runs the previous step), so that it follows
+        # the statistics kernels on the stream without a host gap
+        mats, prep = self._next if self._next is not None else self._compose()
+        pct = self._percentiles()                                                     # [1, 2], identical on all ranks
+        pre1 = stats.coefs_to_affine(stats.scaler_coefs(pct, _lib.SCALER_RANGE, 0.0, 1.0))   # [1, 2]
+        self._pre.copy_(pre1.expand(self.M_vols, 2))
+        prep.run(0)
         self.last = (pct, mats)
+        self._next = self._compose()
 
     def extra(self):
         for _ in range(2):
