@@ -79,7 +79,7 @@ class Workload:
 
     def _prepared(self, i: int, make):
         first = i - i % self.chunk
-        if self._prep is None or self._prep_first != first:
+        if self._prep_first != first:   # (a chunk whose composition came back None stays None: its steps run one by one)
             nxt = self._ahead
             self._prep = nxt[1] if (nxt is not None and nxt[0] == first) else make(first)
             self._prep_first, self._ahead = first, None
