@@ -767,6 +767,16 @@ __device__ __forceinline__ void k1_tile_staged_nearest(const K1Ctx& c, const K1T
   const int64_t ds1 = f.ds1;
   const int64_t pstep = m.jstep * ds1;
   const int T0 = f.n.x;
+  // Voxels inside the tie window of a rounding tie take the bit-faithful replay (k1_exact_nearest_smem: several hundred
+  // instructions, and the whole warp waits for the one lane that needs it).  A few per mille of the voxels do — about
+  // one warp iteration in ten — which made a mask tile cost 1.6-2x a trilinear one.  They are DEFERRED instead: a lane
+  // remembers its tie voxel (tile-local plane and row, biased into 16 bits each) and the warp replays them together
+  // once, after the tile's planes (a lane that meets a second one first replays the remembered voxel on the spot).
+  int pend = -1;
+  auto replay = [&](int pk) {
+    const int ii = (pk >> 16) - 0x4000, jj = (pk & 0xffff) - 0x4000;
+    f.dst[ii * f.ds0 + m.dk * f.ds2 + jj * ds1] = k1_exact_nearest_smem(c, tl, box, ii, jj, m.dk);
+  };
 #pragma unroll 1
   for (;;) {
     const int di = k1_next_plane(tl);
@@ -775,28 +785,35 @@ __device__ __forceinline__ void k1_tile_staged_nearest(const K1Ctx& c, const K1T
     k1_hot_plane<RMASK>(h, f, di, m.dk, m.e);
     float* p = f.dst + m.ii * f.ds0 + m.dk * f.ds2 + (m.j0 - m.s1) * ds1;
     int dj = m.j0;
+    int cnt = m.cnt;
+    while (cnt > 0) {
+      bool full = false;   // the lane met a second tie voxel: leave the voxel loop (which holds no call), replay, come back
 #pragma unroll 2
-    for (int cnt = m.cnt; cnt > 0; --cnt, dj += m.jstep) {
-      float v0, v1, v2;
-      k1_fast_coords<RMASK>(h, static_cast<float>(dj), v0, v1, v2);
-      // rint (ties to even) on the FMA pipe: x + 1.5*2^23 rounds to the nearest integer
-      const float t0 = __fadd_rn(v0, K1_MAGIC), t1 = __fadd_rn(v1, K1_MAGIC), t2 = __fadd_rn(v2, K1_MAGIC);
-      const float n0 = t0 - K1_MAGIC, n1 = t1 - K1_MAGIC, n2 = t2 - K1_MAGIC;
-      float val;
-      if (fmaxf(fmaxf(fabsf(v0 - n0), fabsf(v1 - n1)), fabsf(v2 - n2)) > tie) {
-        val = k1_exact_nearest_smem(c, tl, box, m.ii, dj - m.s1, m.dk);  // inside the tie window of a rounding tie
-      } else {
+      for (; cnt > 0; --cnt, dj += m.jstep, p += pstep) {
+        float v0, v1, v2;
+        k1_fast_coords<RMASK>(h, static_cast<float>(dj), v0, v1, v2);
+        // rint (ties to even) on the FMA pipe: x + 1.5*2^23 rounds to the nearest integer
+        const float t0 = __fadd_rn(v0, K1_MAGIC), t1 = __fadd_rn(v1, K1_MAGIC), t2 = __fadd_rn(v2, K1_MAGIC);
+        const float n0 = t0 - K1_MAGIC, n1 = t1 - K1_MAGIC, n2 = t2 - K1_MAGIC;
+        // the fast tap is loaded unconditionally, off the tie check's dependency chain (inside the tie window the fast
+        // cell is one of the two tied cells: both lie in the staged box); only the store depends on the check
         const uint32_t a = h.cbase + ES * (__float_as_uint(t0) * h.p0 + __float_as_uint(t1) * h.p1 + __float_as_uint(t2));
-        val = fmaf(tap_f32<DT>(a), h.gain, h.bias);
+        float val = fmaf(tap_f32<DT>(a), h.gain, h.bias);
         if (RMASK == 3) {  // an invalid (zero-filled) tap is a literal 0 of the padded volume: no pre offset
           const bool ok = (n0 > h.vl[0]) & (n0 < h.vh[0]) & (n1 > h.vl[1]) & (n1 < h.vh[1]) & (n2 > h.vl[2]) & (n2 < h.vh[2]);
           if (!ok) val = h.po;
         }
+        if (fmaxf(fmaxf(fabsf(v0 - n0), fabsf(v1 - n1)), fabsf(v2 - n2)) > tie) {   // inside the tie window of a rounding tie
+          if (pend >= 0) { full = true; break; }
+          pend = ((m.ii + 0x4000) << 16) | (dj - m.s1 + 0x4000);
+        } else {
+          *p = val;
+        }
       }
-      *p = val;
-      p += pstep;
+      if (full) { replay(pend); pend = -1; }   // (the voxel that did not fit is evaluated again and remembered)
     }
   }
+  if (pend >= 0) replay(pend);
 }
 
 // Rare tiles: output pad band (SpatialPadd after the resample), injected or Philox noise.  Same
