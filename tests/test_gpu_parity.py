@@ -235,6 +235,21 @@ def test_philox_noise_statistics():
     assert torch.equal(out, out2)
 
 
+def test_philox_noise_depends_on_the_output_position_only():
+    """The device noise of a voxel is a function of (seed, offset, output position): the generic path of an identity
+    item, the staged path of a resampled item (whatever its tile shape) and a second staged geometry add the very same
+    values (zero volumes, zeros padding: the output IS the noise)."""
+    for shape in [(48, 40, 32), (33, 22, 16), (64, 64, 20)]:
+        x = torch.zeros(shape, device=DEV)
+        a = run_plan_cuda(BatchPlan([x]).add_philox_noise(0.5, seed=77, offset=123))[0]
+        R = np.random.RandomState(sum(shape))
+        for _ in range(2):
+            A = rand_affine_matrix(R, rotate=(0.3, 0.2, 0.1), translate=(1, 1, 1), scale=(0.05, 0.05, 0.05)).numpy()
+            b = run_plan_cuda(BatchPlan([x]).affine(A, "bilinear", "zeros").add_philox_noise(0.5, seed=77, offset=123))[0]
+            assert torch.equal(a, b)
+        assert abs(float(a.std()) - 0.5) < 2e-2 and abs(float(a.mean())) < 2e-2
+
+
 def test_c_abi_rejects_bad_items():
     import ctypes as C
 
