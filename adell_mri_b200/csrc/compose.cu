@@ -150,6 +150,7 @@ extern "C" int adell_chain_size(void) { return static_cast<int>(sizeof(adell_cha
 
 extern "C" int adell_chain_compose(const adell_chain* chains, int n, adell_item* items_host) {
   if (n < 0 || (n > 0 && (chains == nullptr || items_host == nullptr))) return ADELL_ERR_BAD_ARG;
+  if (n > 0 && (reinterpret_cast<uintptr_t>(items_host) & 63u) != 0) return ADELL_ERR_ALIGN;  // adell_item is 64-byte aligned
   for (int i = 0; i < n; ++i) {
     const int st = compose_one(chains[i], items_host[i]);
     if (st != ADELL_OK) return st;
@@ -442,6 +443,7 @@ extern "C" int adell_seq_prepare_steps(const adell_seq* seqs, int n_steps, const
   if (seqs == nullptr || n_vols == nullptr || buf_host == nullptr || launches == nullptr || n_launches == nullptr ||
       bytes_used == nullptr || scratch_used == nullptr || n_steps < 0 || buf_bytes < 0 || max_launches < 0)
     return ADELL_ERR_BAD_ARG;
+  if ((reinterpret_cast<uintptr_t>(buf_host) & 63u) != 0) return ADELL_ERR_ALIGN;  // items are written at 64-byte multiples of it
   uint8_t* base = static_cast<uint8_t*>(buf_host);
   int64_t off = 0, smax = 0, first = 0;
   int nl = 0;

@@ -2056,11 +2056,17 @@ namespace {
 int k1_prepare_impl(adell_item* items_host, int n_items, int32_t* tile_start_host, adell_launch_info* info, bool plan_only);
 }  // namespace
 
+// adell_item is declared 64-byte aligned and the host code is compiled against that: a misaligned host buffer is refused
+// (it used to be silent undefined behaviour that only vector moves of a wider ISA would have turned into a fault).
+static inline bool k1_items_misaligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 63u) != 0; }
+
 extern "C" int adell_aug_prepare(adell_item* items_host, int n_items, int32_t* tile_start_host, adell_launch_info* info) {
+  if (n_items > 0 && k1_items_misaligned(items_host)) return ADELL_ERR_ALIGN;
   return k1_prepare_impl(items_host, n_items, tile_start_host, info, false);
 }
 
 extern "C" int adell_aug_plan(adell_item* items_host, int n_items, int32_t* tile_start_host, adell_launch_info* info) {
+  if (n_items > 0 && k1_items_misaligned(items_host)) return ADELL_ERR_ALIGN;
   const int st = k1_prepare_impl(items_host, n_items, tile_start_host, info, true);
   if (st == ADELL_OK) {
     for (int i = 0; i < n_items; ++i) items_host[i].flags &= static_cast<uint8_t>(~ADELL_F_TMAP);  // nothing was encoded

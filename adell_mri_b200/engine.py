@@ -53,6 +53,23 @@ class LaunchTimer:
         return [(lab, a.elapsed_time(b)) for lab, a, b in self.pairs]
 
 
+def aligned_bytes(n: int) -> np.ndarray:
+    """Zeroed uint8 host buffer of ``n`` bytes starting on a 64-byte boundary: ``adell_item`` is declared 64-byte
+    aligned (``include/adell_b200.h:107``) and the library refuses item buffers that are not
+    (``ADELL_ERR_ALIGN``); numpy only promises 16 bytes for small allocations.  Pinned staging slots are page-aligned."""
+    raw = np.zeros(int(n) + 64, np.uint8)
+    o = (-raw.ctypes.data) % 64
+    return raw[o: o + int(n)]
+
+
+def aligned_items(n: int, like: np.ndarray | None = None) -> np.ndarray:
+    """``n`` zeroed items (``ITEM_DTYPE``) on a 64-byte boundary, optionally filled from ``like``."""
+    it = aligned_bytes(int(n) * ISZ).view(ITEM_DTYPE)
+    if like is not None:
+        it[:] = like
+    return it
+
+
 #: installed LaunchTimer or None
 timer: LaunchTimer | None = None
 
@@ -128,7 +145,7 @@ def pack_launch(items: np.ndarray):
     buffer.  Returns ``(uint8 buffer, n_items, LaunchInfo)``."""
     lib = _lib.load()
     n = items.shape[0]
-    buf = np.empty(n * ISZ + 4 * (n + 5), np.uint8)  # items, tile prefix (n + 1), chunk queues (4 words)
+    buf = aligned_bytes(n * ISZ + 4 * (n + 5))  # items, tile prefix (n + 1), chunk queues (4 words)
     it = buf[: n * ISZ].view(ITEM_DTYPE)
     it[:] = items
     tiles = buf[n * ISZ :].view(np.int32)
@@ -250,7 +267,7 @@ def prepare_steps(plan: BatchPlan, dst_ptr: np.ndarray, dst_stride: np.ndarray, 
     step_bytes = ns * ISZ + ((4 * (ns + 5) + 127) // 128) * 128
     offs = np.concatenate([[0], np.cumsum(step_bytes)[:-1]]).astype(np.int64)
     total = int(step_bytes.sum())
-    buf = np.zeros(total, np.uint8)
+    buf = aligned_bytes(total)
     if len(sizes) and (ns == ns[0]).all():
         # equal steps: one strided assignment places every step's items
         n0, stride = int(ns[0]), int(step_bytes[0])
@@ -316,7 +333,7 @@ def compose_chains_host(chains: np.ndarray, step_sizes, plan_only: bool = True):
     used by the tests that compare the native composer with ``BatchPlan`` byte for byte."""
     sizes = tuple(int(x) for x in step_sizes)
     n32, offs, tile_off, total = _steps_layout(sizes)
-    buf = np.zeros(total, np.uint8)
+    buf = aligned_bytes(total)
     infos_arr = (_lib.LaunchInfo * len(sizes))()
     _lib.check(_lib.load().adell_chain_prepare_steps(chains.ctypes.data, buf.ctypes.data, len(sizes), n32.ctypes.data,
                                                      offs.ctypes.data, tile_off.ctypes.data, infos_arr, int(plan_only)),
@@ -421,7 +438,7 @@ def compose_seqs_host(seqs: np.ndarray, step_sizes, mode: int = 2, scratch_ptr: 
     max_l = len(sizes) * (2 * _lib.SEQ_MAX_OPS + 1)
     launches = (_lib.SeqLaunch * max_l)()
     need = _seq_bytes_bound(seqs, sizes)
-    buf = np.zeros(max(need, 1), np.uint8)
+    buf = aligned_bytes(max(need, 1))
     st, nl, used, sused = _seq_call(seqs, sizes, scratch_ptr, scratch_elems, buf.ctypes.data, need, launches, mode)
     _lib.check(st, "adell_seq_prepare_steps")
     out = []

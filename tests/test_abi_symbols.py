@@ -50,7 +50,8 @@ def test_mat4_chain_matches_torch_cpu_products():
 
 def test_prepare_validates_and_never_falls_back():
     lib = _lib.load()
-    items = np.zeros(2, np.dtype(_lib.Item))
+    from adell_mri_b200.engine import aligned_items
+    items = aligned_items(2)
     tiles = np.full(7, -1, np.int32)   # tile prefix (n + 1) + the launch's four chunk-queue words
     info = _lib.LaunchInfo()
     assert lib.adell_aug_prepare(items.ctypes.data, 2, tiles.ctypes.data, C.byref(info)) == -1  # zero shapes
@@ -64,3 +65,19 @@ def test_prepare_validates_and_never_falls_back():
         it["flags"] = _lib.F_IDENTITY
     assert lib.adell_aug_prepare(items.ctypes.data, 2, tiles.ctypes.data, C.byref(info)) == 0
     assert info.total_tiles == 2 * 2 * 3 * 3 and list(tiles) == [0, 18, 36, 0, 0, 0, 0] and info.n_staged == 0
+
+
+def test_misaligned_item_buffers_are_refused():
+    """``adell_item`` is declared 64-byte aligned (include/adell_b200.h:107): the host entry points answer
+    ADELL_ERR_ALIGN for a buffer that is not, instead of reading it with the aligned moves they were compiled with."""
+    from adell_mri_b200.engine import ISZ, aligned_bytes
+    lib = _lib.load()
+    raw = aligned_bytes(2 * ISZ + 64)
+    off = raw[16: 16 + 2 * ISZ]
+    tiles = np.zeros(7, np.int32)
+    info = _lib.LaunchInfo()
+    assert lib.adell_aug_prepare(off.ctypes.data, 2, tiles.ctypes.data, C.byref(info)) == -3
+    assert lib.adell_aug_plan(off.ctypes.data, 2, tiles.ctypes.data, C.byref(info)) == -3
+    chains = np.zeros(2 * lib.adell_chain_size(), np.uint8)
+    assert lib.adell_chain_compose(chains.ctypes.data, 2, off.ctypes.data) == -3
+    assert lib.adell_aug_prepare(raw.ctypes.data, 0, tiles.ctypes.data, C.byref(info)) == 0   # empty launch: nothing is read

@@ -256,7 +256,8 @@ def test_c_abi_rejects_bad_items():
     from adell_mri_b200 import _lib
 
     lib = _lib.load()
-    items = np.zeros(1, np.dtype(_lib.Item))
+    from adell_mri_b200.engine import aligned_items
+    items = aligned_items(1)
     tiles = np.zeros(2, np.int32)
     info = _lib.LaunchInfo()
     assert lib.adell_aug_prepare(items.ctypes.data, 1, tiles.ctypes.data, C.byref(info)) == -1
@@ -384,7 +385,8 @@ def test_tma_store_copy_tiles_are_bit_exact(shape, roi, start):
     dst_ptr = np.array([d.data_ptr() for d in dsts], np.uint64)
     dst_stride = np.array([d.stride() for d in dsts], np.int64)
     items = plan.build_launches(dst_ptr, dst_stride, None)[-1]
-    probe = np.zeros(n, ITEM_DTYPE); probe[:] = items
+    from adell_mri_b200.engine import aligned_items
+    probe = aligned_items(n, items)
     tiles = np.zeros(n + 5, np.int32)
     info = _lib.LaunchInfo()
     _lib.check(_lib.load().adell_aug_plan(probe.ctypes.data, n, tiles.ctypes.data, C.byref(info)), "adell_aug_plan")

@@ -15,6 +15,7 @@ import pytest
 import torch
 
 from adell_mri_b200 import _lib, geometry
+from adell_mri_b200.engine import aligned_items
 from adell_mri_b200.plan import ITEM_DTYPE, BatchPlan
 
 
@@ -24,8 +25,7 @@ def plan_items(plan, out_shapes):
     dst_stride = np.array([o.stride() for o in outs], np.int64)
     items = plan.build_launches(dst_ptr, dst_stride, None)[-1]
     n = items.shape[0]
-    it = np.zeros(n, ITEM_DTYPE)
-    it[:] = items
+    it = aligned_items(n, items)
     tiles = np.zeros(n + 5, np.int32)
     info = _lib.LaunchInfo()
     _lib.check(_lib.load().adell_aug_plan(it.ctypes.data, n, tiles.ctypes.data, C.byref(info)), "adell_aug_plan")

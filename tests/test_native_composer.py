@@ -18,7 +18,7 @@ def _plan_items(plan, dst_ptr, dst_stride, sizes):
     items = plan.build_launches(dst_ptr, dst_stride, None)[-1].copy()
     out, start = [], 0
     for n in sizes:
-        it = items[start:start + n].copy()
+        it = engine.aligned_items(n, items[start:start + n])
         tiles = np.zeros(n + 5, np.int32)
         info = _lib.LaunchInfo()
         _lib.check(_lib.load().adell_aug_plan(it.ctypes.data, n, tiles.ctypes.data, C.byref(info)), "plan")
@@ -210,7 +210,7 @@ def test_seq_prepare_reports_missing_space():
     out = {k: torch.empty(8, 1, *roi) for k in ("augmented_image_1", "augmented_image_2")}
     sq, _ = aug.seqs([samples], [out])
     launches = (_lib.SeqLaunch * 16)()
-    buf = np.zeros(1 << 20, np.uint8)
+    buf = engine.aligned_bytes(1 << 20)
     st, nl, used, sused = engine._seq_call(sq, (len(sq),), 4096, 0, buf.ctypes.data, buf.size, launches, 2)
     if sused > 0:
         assert st == _lib.ERR_NO_SPACE

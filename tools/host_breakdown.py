@@ -29,7 +29,7 @@ for rep in range(REPS + 2):
     tick("fill items", t)
     t = time.perf_counter()
     n = 32
-    buf = np.zeros(16 * (n * ISZ + 256), np.uint8)
+    buf = engine.aligned_bytes(16 * (n * ISZ + 256))
     infos = []
     for k in range(16):
         o = k * (n * ISZ + 256)
