@@ -234,6 +234,18 @@ ABI_VERSION = 7
 _lib = None
 
 
+def _require_fma() -> None:
+    """The host composers are compiled with ``-mfma`` (csrc/build.sh): refuse a host CPU without the instruction
+    instead of dying on it."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            flags = next((ln for ln in f if ln.startswith("flags")), "")
+    except OSError:
+        return
+    if flags and " fma" not in flags:
+        raise RuntimeError("libadell_b200.so needs a host CPU with FMA (x86-64-v3); rebuild csrc/build.sh without -mfma")
+
+
 def load() -> C.CDLL:
     """Load ``libadell_b200.so`` (once).  Raises if it has not been built."""
     global _lib
@@ -244,6 +256,7 @@ def load() -> C.CDLL:
             f"{LIB_PATH} is missing: build it with adell_mri_b200/csrc/build.sh "
             "(or __graft_entry__.build()); there is no CPU fallback."
         )
+    _require_fma()
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported

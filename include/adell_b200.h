@@ -201,7 +201,9 @@ typedef struct adell_launch_info {
  * (resampled tiles, copy tiles) from which the SMs draw their tiles at run time.  The items may be
  * REORDERED in place (identity items last); they are independent, so the result does not change.  The caller then uploads items + prefix + queue words and
  * calls adell_aug_gather; the kernel leaves the queue words zero again, so a buffer can be
- * launched repeatedly (not concurrently with itself). */
+ * launched repeatedly (not concurrently with itself).  items_host must start on a 64-byte boundary like every
+ * adell_item array (host or device): ADELL_ERR_ALIGN otherwise, also from adell_aug_plan, adell_chain_compose, the
+ * *_prepare_steps entry points (through their item offsets) and adell_seq_prepare_steps (buf_host). */
 int adell_aug_prepare(adell_item* items_host, int n_items, int32_t* tile_start_host,
                       adell_launch_info* info);
 /* Host-only, needs neither a GPU nor a driver: the same decisions as adell_aug_prepare (item order,
