@@ -543,7 +543,9 @@ __device__ __forceinline__ float k1_lerp8(const K1Vox& x, const float* t) {
 // shared-memory taps issued before any arithmetic that depends on them (the loads are volatile
 // asm so ptxas keeps them batched); no per-voxel bounds checks — a thread's voxel count is split
 // into full groups and a one-at-a-time tail.
-template <int NV, int RMASK, int DT>
+// NZ: the tile's only special feature is device (Philox) noise — one N(0,1) per output position added after the post map,
+// the same fmaf as the cold loop's (the counter is the voxel's linear output index: independent of the tile shape).
+template <int NV, int RMASK, int DT, bool NZ = false>
 __device__ __forceinline__ void k1_tile_staged_trilinear_scalar(const K1Tile& tl, const K1Fast& f) {
   K1Map m;
   k1_lane_map(f, m);   // lanes without voxels: cnt == 0
@@ -555,6 +557,8 @@ __device__ __forceinline__ void k1_tile_staged_trilinear_scalar(const K1Tile& tl
   const int64_t pstep = m.jstep * ds1;
   const float fstep = static_cast<float>(m.jstep);
   const int T0 = f.n.x;
+  const uint64_t nz_base = NZ ? f.philox_offset + f.olin0 : 0, nz_step = NZ ? static_cast<uint64_t>(m.jstep * f.ns1) : 0;
+  const float nz_std = NZ ? f.gb.w : 0.0f;
 #pragma unroll 1
   for (;;) {
     const int di = k1_next_plane(tl);
@@ -564,6 +568,8 @@ __device__ __forceinline__ void k1_tile_staged_trilinear_scalar(const K1Tile& tl
     float* p = f.dst + m.ii * f.ds0 + m.dk * f.ds2 + (m.j0 - m.s1) * ds1;
     float fj = static_cast<float>(m.j0);
     int cnt = m.cnt;
+    uint64_t nc = 0;
+    if (NZ) nc = nz_base + static_cast<uint64_t>(m.ii * f.ns0 + (m.j0 - m.s1) * f.ns1 + m.dk);
 #pragma unroll 1
     for (; cnt >= NV; cnt -= NV) {
       K1Vox x[NV];
@@ -581,9 +587,14 @@ __device__ __forceinline__ void k1_tile_staged_trilinear_scalar(const K1Tile& tl
         t[u][6] = tap_f32<DT>(x[u].a + o0 + o1); t[u][7] = tap_f32<DT>(x[u].a + o0 + o1 + ES);
       }
 #pragma unroll
-      for (int u = 0; u < NV; ++u) p[u * pstep] = fmaf(k1_lerp8(x[u], t[u]), h.gain, h.bias);
+      for (int u = 0; u < NV; ++u) {
+        float z = fmaf(k1_lerp8(x[u], t[u]), h.gain, h.bias);
+        if (NZ) z = fmaf(nz_std, adell_philox_normal(f.philox_seed, nc + static_cast<uint64_t>(u) * nz_step), z);
+        p[u * pstep] = z;
+      }
       p += NV * pstep;
       fj += static_cast<float>(NV) * fstep;
+      if (NZ) nc += static_cast<uint64_t>(NV) * nz_step;
     }
 #pragma unroll 1
     for (; cnt > 0; --cnt) {
@@ -591,7 +602,9 @@ __device__ __forceinline__ void k1_tile_staged_trilinear_scalar(const K1Tile& tl
       float t[8];
       t[0] = tap_f32<DT>(x.a); t[1] = tap_f32<DT>(x.a + ES); t[2] = tap_f32<DT>(x.a + o1); t[3] = tap_f32<DT>(x.a + o1 + ES);
       t[4] = tap_f32<DT>(x.a + o0); t[5] = tap_f32<DT>(x.a + o0 + ES); t[6] = tap_f32<DT>(x.a + o0 + o1); t[7] = tap_f32<DT>(x.a + o0 + o1 + ES);
-      *p = fmaf(k1_lerp8(x, t), h.gain, h.bias);
+      float z = fmaf(k1_lerp8(x, t), h.gain, h.bias);
+      if (NZ) { z = fmaf(nz_std, adell_philox_normal(f.philox_seed, nc), z); nc += nz_step; }
+      *p = z;
       p += pstep;
       fj += fstep;
     }
@@ -676,7 +689,7 @@ __device__ __forceinline__ k1_f2 tap_pair(uint32_t aA, uint32_t aB) {
   return DT == ADELL_F32 ? r : f2_add(r, f2_dup(-K1_MAGIC));
 }
 
-template <int NP, int RMASK, int DT>
+template <int NP, int RMASK, int DT, bool NZ = false>
 __device__ __forceinline__ void k1_tile_staged_trilinear(const K1Tile& tl, const K1Fast& f) {
   K1Map m;
   k1_lane_map(f, m);   // lanes without voxels: cnt == 0
@@ -689,6 +702,8 @@ __device__ __forceinline__ void k1_tile_staged_trilinear(const K1Tile& tl, const
   const float fstep = static_cast<float>(m.jstep);
   const int T0 = f.n.x;
   const k1_f2 G2 = f2_dup(h.gain), B2 = f2_dup(h.bias);
+  const uint64_t nz_base = NZ ? f.philox_offset + f.olin0 : 0, nz_step = NZ ? static_cast<uint64_t>(m.jstep * f.ns1) : 0;
+  const float nz_std = NZ ? f.gb.w : 0.0f;
   K1Hot2<RMASK> q;
   if (RMASK == 1) {
     q.inv2S = f2_dup(h.inv2S[2]); q.hinv = f2_dup(h.hinv[2]); q.twoS = f2_dup(h.twoS[2]);
@@ -711,6 +726,8 @@ __device__ __forceinline__ void k1_tile_staged_trilinear(const K1Tile& tl, const
     float* p = f.dst + m.ii * f.ds0 + m.dk * f.ds2 + (m.j0 - m.s1) * ds1;
     float fj = static_cast<float>(m.j0);
     int cnt = m.cnt;
+    uint64_t nc = 0;
+    if (NZ) nc = nz_base + static_cast<uint64_t>(m.ii * f.ns0 + (m.j0 - m.s1) * f.ns1 + m.dk);
 #pragma unroll 1
     for (; cnt >= 2 * NP; cnt -= 2 * NP) {
       K1Vox2 x[NP];
@@ -736,11 +753,16 @@ __device__ __forceinline__ void k1_tile_staged_trilinear(const K1Tile& tl, const
         float za, zb;
         // RM 3: gain * sum(w v) + (pre_o post_s) * sum(w valid) + post_o
         f2_unpack(f2_fma(k1_lerp8x2(x[u], t[u]), G2, RMASK == 3 ? f2_fma(x[u].w, WB2, PO2) : B2), za, zb);
+        if (NZ) {
+          za = fmaf(nz_std, adell_philox_normal(f.philox_seed, nc + static_cast<uint64_t>(2 * u) * nz_step), za);
+          zb = fmaf(nz_std, adell_philox_normal(f.philox_seed, nc + static_cast<uint64_t>(2 * u + 1) * nz_step), zb);
+        }
         p[(2 * u) * pstep] = za;
         p[(2 * u + 1) * pstep] = zb;
       }
       p += 2 * NP * pstep;
       fj += static_cast<float>(2 * NP) * fstep;
+      if (NZ) nc += static_cast<uint64_t>(2 * NP) * nz_step;
     }
 #pragma unroll 1
     for (; cnt > 0; --cnt) {
@@ -748,7 +770,9 @@ __device__ __forceinline__ void k1_tile_staged_trilinear(const K1Tile& tl, const
       float t[8];
       t[0] = tap_f32<DT>(x.a); t[1] = tap_f32<DT>(x.a + ES); t[2] = tap_f32<DT>(x.a + o1); t[3] = tap_f32<DT>(x.a + o1 + ES);
       t[4] = tap_f32<DT>(x.a + o0); t[5] = tap_f32<DT>(x.a + o0 + ES); t[6] = tap_f32<DT>(x.a + o0 + o1); t[7] = tap_f32<DT>(x.a + o0 + o1 + ES);
-      *p = fmaf(k1_lerp8(x, t), h.gain, RMASK == 3 ? fmaf(x.w, h.wb, h.po) : h.bias);
+      float z = fmaf(k1_lerp8(x, t), h.gain, RMASK == 3 ? fmaf(x.w, h.wb, h.po) : h.bias);
+      if (NZ) { z = fmaf(nz_std, adell_philox_normal(f.philox_seed, nc), z); nc += nz_step; }
+      *p = z;
       p += pstep;
       fj += fstep;
     }
@@ -866,6 +890,14 @@ __device__ __noinline__ void k1_tile_staged_cold(const K1Ctx& c, const K1Tile& t
       f.dst[m.ii * f.ds0 + jo * f.ds1 + dk * f.ds2] = val;
     }
   }
+}
+
+// Trilinear fp32 tiles whose only special feature is device noise (RandGaussianNoised of the SSL views: a fifth of them):
+// the plain loops with the noise epilogue instead of the one-voxel-at-a-time cold loop.  Out of line: one call per tile.
+__device__ __noinline__ void k1_tile_staged_noisy(const K1Tile& tl, const K1Fast& f, int rm) {
+  if (rm == 0) k1_tile_staged_trilinear<K1_NP, 0, ADELL_F32, true>(tl, f);
+  else if (rm == 1) k1_tile_staged_trilinear<K1_NP, 1, ADELL_F32, true>(tl, f);
+  else k1_tile_staged_trilinear_scalar<K1_NV, 2, ADELL_F32, true>(tl, f);
 }
 
 // Plain staged tile (no output pad band, no noise) of a source of element type DT.  fp32 sources are inlined
@@ -1576,8 +1608,14 @@ k1_gather(const adell_item* __restrict__ items, const int32_t* __restrict__ tile
       const bool leak = ctx.pre_o != 0.0f && !tl.all_valid;
       const bool exact = (it.flags & (ADELL_F_STRICT | ADELL_F_CLIP)) != 0 || (leak && (tl.rmask != 0 || f.fl.x));
       if (exact) k1_tile_exact_dispatch<SmemTaps, false>(ctx, tl, box);
-      else if (f.fl.x) k1_tile_staged_cold(ctx, tl, f, box);
-      else {
+      else if (f.fl.x) {
+        // (leak is false here, so the variant is 0, 1 or 2)
+        const int rm = tl.rmask == 0 ? 0 : ((tl.rmask == 4 && it.padding == ADELL_PAD_REFLECTION) ? 1 : 2);
+        if (f.fl.z && !f.fl.y && f.noise == nullptr && it.interp != ADELL_NEAREST && it.src_dtype == ADELL_F32)
+          k1_tile_staged_noisy(tl, f, rm);
+        else
+          k1_tile_staged_cold(ctx, tl, f, box);
+      } else {
         // block-uniform variant: 0 = no padding arithmetic, 1 = reflection on the thin axis only, 2 = general,
         // 3 = no padding arithmetic but invalid taps under a pre offset (valid-weight sum)
         const int rm = tl.rmask == 0 ? (leak ? 3 : 0) : ((tl.rmask == 4 && it.padding == ADELL_PAD_REFLECTION) ? 1 : 2);

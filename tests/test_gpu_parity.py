@@ -250,6 +250,21 @@ def test_philox_noise_depends_on_the_output_position_only():
         assert abs(float(a.std()) - 0.5) < 2e-2 and abs(float(a.mean())) < 2e-2
 
 
+def test_philox_noise_on_resampled_tiles_is_the_plain_tile_plus_the_noise():
+    """Tiles whose only special feature is device noise run the plain trilinear loops with a noise epilogue: the result is
+    fmaf(std, N(position), plain value) bit for bit, with N read back from an identity item over zeros (std 1: the output
+    IS the noise) and the plain value from the same item without noise — every padding mode, ragged and multi-tile shapes."""
+    R = np.random.RandomState(5)
+    for shape, padding in [((64, 64, 32), "reflection"), ((48, 40, 32), "border"), ((33, 22, 16), "zeros"), ((96, 80, 24), "reflection")]:
+        x = torch.from_numpy(R.rand(*shape).astype(np.float32)).to(DEV)
+        N = run_plan_cuda(BatchPlan([torch.zeros(shape, device=DEV)]).add_philox_noise(1.0, seed=9, offset=4321))[0]
+        A = rand_affine_matrix(R, rotate=(0.3, 0.2, 0.1), translate=(2, 2, 1), scale=(0.1, 0.1, 0.1)).numpy()
+        plain = run_plan_cuda(BatchPlan([x]).affine(A, "bilinear", padding).intensity(1.5, -0.25))[0]
+        noisy = run_plan_cuda(BatchPlan([x]).affine(A, "bilinear", padding).intensity(1.5, -0.25).add_philox_noise(0.3, seed=9, offset=4321))[0]
+        want = (np.float64(np.float32(0.3)) * N.cpu().numpy().astype(np.float64) + plain.cpu().numpy().astype(np.float64)).astype(np.float32)
+        assert np.array_equal(noisy.cpu().numpy(), want), (shape, padding)
+
+
 def test_c_abi_rejects_bad_items():
     import ctypes as C
 
