@@ -104,7 +104,16 @@ class _PinnedRing:
         return k, self.slots[k][:n].numpy()
 
     def upload(self, k: int, n: int, device: torch.device) -> torch.Tensor:
-        dev = self.slots[k][:n].to(device, non_blocking=True)
+        # Blocks of a few hundred KB come out of the caching allocator's 2 MiB small-pool segments, two to six per
+        # segment: a second live chunk of launch parameters then costs a cudaMalloc — 0.5 ms as a rule, 5-50 ms now and
+        # then (seen in `bench.py`'s short runs: the whole queue drained behind it).  Asked for as MORE than 1 MiB (the
+        # allocator's small / large boundary) they are carved out of one 20 MiB large-pool segment that the first upload
+        # brought in.
+        if n > (256 << 10):
+            dev = torch.empty(max(n, (1 << 20) + 512), dtype=torch.uint8, device=device)[:n]
+            dev.copy_(self.slots[k][:n], non_blocking=True)
+        else:
+            dev = self.slots[k][:n].to(device, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(device))
         self.events[k] = ev

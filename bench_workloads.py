@@ -26,6 +26,8 @@ check raises: a bench line is never printed for wrong voxels.
 
 from __future__ import annotations
 
+import os
+import sys
 import time
 
 import numpy as np
@@ -57,7 +59,9 @@ class Workload:
     name = ""
     desc = ""
     bytes_per_voxel = 8.0   # algorithmic: fp32 source read + fp32 write per output voxel-channel
-    default_steps = 10
+    # timed steps when the command line gives none: long enough (20-30 ms) that one scheduling hiccup of the host — 10-70 ms
+    # stalls were seen on two-rank runs of a shared box, on both ranks at once — does not decide a 10-step mean
+    default_steps = 32
 
     def __init__(self, dev, rank: int, world: int, seed: int):
         self.dev, self.rank, self.world, self.seed = dev, rank, world, seed
@@ -307,6 +311,7 @@ class SegCrop(_SegBase):
             "surface: one pipeline call per sample, FgBgToIndicesd lists resident on the device, crop centres selected by "
             "adell_posneg_starts, K1 reading the window starts from device memory, safe_collate_crops -> one launch")
     rc, n_crops = [128, 128, 24], 2
+    default_steps = 10   # (3 ms of Python per step)
 
     def __init__(self, dev, rank, world, seed):
         super().__init__(dev, rank, world, seed)
@@ -368,6 +373,7 @@ class SegCropBatch(SegCrop):
             "FgBgToIndicesd lists, centres selected by adell_posneg_starts, K1 reading the window starts from device memory, "
             "affine p=0.2 reflection + 3 flips per crop, centre crop; 16 crops of 4 keys per step, 8 steps composed per host call")
     chunk = 8
+    default_steps = 32
 
     def __init__(self, dev, rank, world, seed):
         super().__init__(dev, rank, world, seed)
@@ -601,7 +607,7 @@ class LargeVolume(Workload):
             "bin counts all-reduced over NCCL after each), "
             "ScaleIntensityRange coefficients on the device, scaling folded into the affine gather (rotate pi/8, pi/8, pi/16; zeros)")
     M_vols, shape = 4, (512, 512, 128)
-    default_steps = 5
+    default_steps = 16
 
     def __init__(self, dev, rank, world, seed):
         super().__init__(dev, rank, world, seed)
@@ -765,6 +771,11 @@ def run(cls, dev, rank, world, seed, steps, warmup, peak_gbs, barrier, reduce_ma
     """Time one workload: returns its entry of the `workloads` block (rank 0) — every rank runs its own shard."""
     wl = cls(dev, rank, world, seed + 101 * rank)
     steps = steps if steps else wl.default_steps
+    # Warm-up reaches the loader's steady state: two full chunks and the look-ahead of the third, so that the device blocks
+    # of the chunk uploads exist before the timed region.  (The SECOND live chunk makes torch's caching allocator take a
+    # new segment: a cudaMalloc that usually costs 0.5 ms and now and then 5-50 ms — caught with ADELL_BENCH_DIAG in
+    # `_PinnedRing.upload` of the first look-ahead, which a 5-step warm-up left inside the timed region.)
+    warmup = max(warmup, 2 * wl.chunk + 1)
     parity = wl.parity() if do_parity else {"ok": None, "checked": "skipped (--no-parity)"}
     for i in range(warmup):
         wl.step(i)
@@ -774,11 +785,60 @@ def run(cls, dev, rank, world, seed, steps, warmup, peak_gbs, barrier, reduce_ma
     launches0 = engine.launch_count
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(stream)
+    diag = os.environ.get("ADELL_BENCH_DIAG")
+    gc_log = []
+    if diag:
+        import gc
+
+        def _gc_cb(phase, info, _t=[0.0]):
+            if phase == "start":
+                _t[0] = time.perf_counter()
+            else:
+                gc_log.append((info.get("generation"), round(1e3 * (time.perf_counter() - _t[0]), 3)))
+        gc.callbacks.append(_gc_cb)
+        parts = {}
+
+        def _wrap(obj, attr):
+            fn = getattr(obj, attr, None)
+            if fn is None:
+                return
+
+            def w(*a, **k):
+                t = time.perf_counter()
+                try:
+                    return fn(*a, **k)
+                finally:
+                    parts.setdefault(attr, []).append(round(1e3 * (time.perf_counter() - t), 3))
+            setattr(obj, attr, w)
+        for attr in ("_make", "_pre_dev"):
+            _wrap(wl, attr)
+        saved = {a: getattr(engine._PinnedRing, a) for a in ("acquire", "upload")}
+        for attr in saved:
+            _wrap(engine._PinnedRing, attr)
+        seg0 = torch.cuda.memory_stats().get("segment.all.allocated", 0)
+        slow = None
     t0 = time.perf_counter()
+    t_prev, host_max, per_host = t0, 0.0, []
     for i in range(steps):
         engine.timer.label = i
         wl.step(warmup + i)
+        t_now = time.perf_counter()
+        per_host.append(round(1e3 * (t_now - t_prev), 3))
+        if diag:
+            if slow is None or per_host[-1] > slow[1]:
+                slow = (i, per_host[-1], {k: list(v) for k, v in parts.items()},
+                        torch.cuda.memory_stats().get("segment.all.allocated", 0) - seg0)
+            for v in parts.values():
+                v.clear()
+            seg0 = torch.cuda.memory_stats().get("segment.all.allocated", 0)
+        host_max, t_prev = max(host_max, t_now - t_prev), t_now
     host_s = time.perf_counter() - t0
+    if diag:
+        gc.callbacks.remove(_gc_cb)
+        for attr, fn in saved.items():
+            setattr(engine._PinnedRing, attr, fn)
+        print(f"[diag] rank {rank} {wl.name}: slowest step (index, host ms, parts ms, new allocator segments) {slow}", file=sys.stderr, flush=True)
+        print(f"[diag] rank {rank} {wl.name}: host ms per step {per_host}; gc (generation, ms) {gc_log}", file=sys.stderr, flush=True)
     b.record(stream)
     barrier()
     timer, engine.timer = engine.timer, None
@@ -794,7 +854,7 @@ def run(cls, dev, rank, world, seed, steps, warmup, peak_gbs, barrier, reduce_ma
     entry = {
         "workload": wl.desc, "value": world * wl.vox_per_step / (ms_max * 1e-3), "unit": "voxels/s", "ms_per_step": ms_max,
         "steps": steps, "warmup": warmup, "kernel_ms": kernel_ms, "k1_launches_per_step": launches / steps,
-        "host_ms_per_step": 1e3 * host_s / steps,
+        "host_ms_per_step": 1e3 * host_s / steps, "host_ms_slowest_step": 1e3 * host_max,
         "roofline": {"bound": "hbm", "achieved": alg / (kernel_ms * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
                      "frac": alg / (kernel_ms * 1e-3) / 1e9 / peak_gbs, "algorithmic_bytes": alg, "kernel": "k1_gather",
                      "traffic": None},
